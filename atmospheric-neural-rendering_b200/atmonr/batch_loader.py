@@ -1,0 +1,40 @@
+"""Batch-wise loader over a dataset's ray (or voxel) index (reference: src/atmonr/batch_loader.py).
+
+Same constructor and iteration protocol. The reference builds every batch index from a Python
+list of B ints (batch_loader.py:45-49); here one permutation per epoch is drawn as a tensor
+(torch's generator, so seeding works the same way) and sliced, which removes the O(B) Python
+work per step. Under torch.distributed every rank draws the SAME permutation and
+takes its own contiguous slice of each global batch (data-parallel ray sharding).
+"""
+
+from __future__ import annotations
+
+from collections.abc import Iterator
+
+import torch
+
+
+class BatchLoader:
+    def __init__(self, dataset, batch_size: int, shuffle: bool = True, drop_last: bool = False,
+                 rank: int = 0, world_size: int = 1, seed: int | None = None):
+        self.dataset = dataset
+        self.idx = dataset.ray_idx if hasattr(dataset, "ray_idx") else dataset.idx
+        self.batch_size, self.shuffle, self.drop_last = int(batch_size), shuffle, drop_last
+        self.rank, self.world_size = rank, world_size
+        self.generator = None
+        if seed is not None or world_size > 1:
+            self.generator = torch.Generator().manual_seed(0 if seed is None else seed)
+
+    def __len__(self) -> int:
+        n = self.idx.shape[0]
+        return n // self.batch_size if self.drop_last else -(-n // self.batch_size)
+
+    def __iter__(self) -> Iterator[dict[str, torch.Tensor]]:
+        n = self.idx.shape[0]
+        order = torch.randperm(n, generator=self.generator) if self.shuffle else torch.arange(n)
+        for b in range(len(self)):
+            idx = order[b * self.batch_size:(b + 1) * self.batch_size]
+            if self.world_size > 1:
+                per = -(-idx.shape[0] // self.world_size)
+                idx = idx[self.rank * per:(self.rank + 1) * per]
+            yield self.dataset.__getbatch__(idx.to(self.idx.device))

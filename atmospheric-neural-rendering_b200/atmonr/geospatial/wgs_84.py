@@ -1,0 +1,140 @@
+"""WGS-84 conversions and ray construction (reference: src/atmonr/geospatial/wgs_84.py).
+
+These run ONCE per run at dataset construction (a1, a2), on whatever device the
+granule arrays live on, as plain torch expressions in float64 where the reference uses
+float64. The per-step, per-sample use of the ECEF -> geodetic conversion (the point
+preprocessor) does NOT go through this module: it is fused into the sm_100a sampler kernel
+(csrc/device_math.cuh: ecef_to_geodetic).
+"""
+
+from __future__ import annotations
+
+import math
+
+import torch
+
+WGS_84_A = 6378137.0
+WGS_84_B = 6356752.314245
+WGS_84_E = (WGS_84_A**2 - WGS_84_B**2) / (WGS_84_A**2)   # first eccentricity, squared
+WGS_84_E2 = (WGS_84_A**2 - WGS_84_B**2) / (WGS_84_B**2)  # second eccentricity, squared
+WGS_84_F = (WGS_84_A - WGS_84_B) / WGS_84_A
+
+
+def horizontal_to_cartesian(lat, lon, alt):
+    """(lat, lon in degrees, ellipsoidal height in m) -> ECEF x, y, z. wgs_84.py:24-53."""
+    if not (lat.shape == lon.shape == alt.shape):
+        raise ValueError("lat, lon, alt must share a shape")
+    shape = lat.shape
+    phi = lat.flatten() * math.pi / 180
+    lam = lon.flatten() * math.pi / 180
+    h = alt.flatten()
+    sin_phi, cos_phi = torch.sin(phi), torch.cos(phi)
+    prime_vertical = WGS_84_A / torch.sqrt(1 - (WGS_84_E * sin_phi**2))
+    x = (prime_vertical + h) * cos_phi * torch.cos(lam)
+    y = (prime_vertical + h) * cos_phi * torch.sin(lam)
+    z = (prime_vertical * (1 - WGS_84_E) + h) * sin_phi
+    return x.view(shape), y.view(shape), z.view(shape)
+
+
+def cartesian_to_horizontal(x, y, z):
+    """ECEF -> (lat deg, lon deg, height m) with ONE Bowring iteration; the height is recovered
+    as x / (cos lat cos lon) - N. wgs_84.py:56-97 (kept literal: same accuracy, same
+    singularities)."""
+    if not (x.shape == y.shape == z.shape):
+        raise ValueError("x, y, z must share a shape")
+    shape = x.shape
+    x, y, z = x.flatten(), y.flatten(), z.flatten()
+    lam = torch.atan2(y, x)
+    horiz = torch.sqrt(x**2 + y**2)
+    param_lat = torch.atan2(z / horiz, torch.zeros_like(x) + WGS_84_A / WGS_84_B)
+    phi = torch.atan2(
+        z + (WGS_84_E2 * WGS_84_B) * (torch.sin(param_lat) ** 3),
+        horiz - (WGS_84_E * WGS_84_A) * (torch.cos(param_lat) ** 3),
+    )
+    prime_vertical = WGS_84_A / torch.sqrt(1 - (WGS_84_E * torch.sin(phi) ** 2))
+    height = x / (torch.cos(phi) * torch.cos(lam)) - prime_vertical
+    to_deg = lambda t: t.view(shape) * 180 / torch.pi
+    return to_deg(phi), to_deg(lam), height.view(shape)
+
+
+def horizontal_coords_to_rot_mtx(theta, phi):
+    """Rotation matrices (n,3,3) from zenith/azimuth in degrees; both angles are negated to match
+    the 3-D rotation convention. wgs_84.py:100-132."""
+    if theta.dim() != 1 or theta.shape != phi.shape:
+        raise ValueError("theta and phi must be 1-D and the same length")
+    t = -theta * torch.pi / 180
+    p = -phi * torch.pi / 180
+    st, ct, sp, cp = torch.sin(t), torch.cos(t), torch.sin(p), torch.cos(p)
+    zero = torch.zeros_like(t)
+    row0 = torch.stack([cp, -sp * ct, sp * st], dim=1)
+    row1 = torch.stack([sp, cp * ct, -cp * st], dim=1)
+    row2 = torch.stack([zero, st, ct], dim=1)
+    return torch.stack([row0, row1, row2], dim=1)
+
+
+def horizontal_coords_to_dirvecs(theta, phi):
+    """Unit vectors for (zenith, azimuth) in the local +z-up frame. wgs_84.py:135-160."""
+    if theta.shape != phi.shape:
+        raise ValueError("theta and phi must share a shape")
+    shape = tuple(theta.shape)
+    rot = horizontal_coords_to_rot_mtx(theta.flatten(), phi.flatten())
+    up = torch.zeros((rot.shape[0], 3, 1), dtype=rot.dtype, device=rot.device)
+    up[:, 2] = 1
+    return (rot @ up).view(*shape, 3)
+
+
+def dirvecs_to_horizontal_coords(dirs):
+    """Inverse of horizontal_coords_to_dirvecs. wgs_84.py:163-186."""
+    d = dirs.view(-1, 3)
+    theta = torch.atan2(torch.linalg.norm(d[..., :2]), d[..., 2])
+    phi = -torch.atan2(d[..., 0], -d[..., 1])
+    return (theta * 180 / torch.pi) % 360, (phi * 180 / torch.pi) % 360 - 180
+
+
+def compose_dirs_and_surface_normals(dirs, lat, lon):
+    """Local-frame directions -> ECEF directions. wgs_84.py:189-220 (includes the 180 degree
+    turn about z between the scene convention and the WGS convention)."""
+    rot = horizontal_coords_to_rot_mtx(90 - lat, 90 - lon).to(dtype=dirs.dtype)
+    turn = torch.tensor([-1.0, -1.0, 1.0], dtype=dirs.dtype, device=dirs.device)
+    return (rot @ (dirs * turn)[..., None])[..., 0]
+
+
+def get_rays(lat, lon, alt, thetav, phiv, ray_origin_height, tol: float = 10.0, max_iters: int = 20):
+    """Ray entry (top of the shell at `ray_origin_height`) and exit (surface) for every
+    pixel/view. wgs_84.py:223-290. Returns origins (P*A,3), directions (P*A,3), lengths (P*A,)."""
+    x, y, z = horizontal_to_cartesian(lat.double(), lon.double(), alt.double())
+    surface = torch.stack([x, y, z], dim=-1).float()
+    local = horizontal_coords_to_dirvecs(thetav.double(), phiv.double())
+    dirs = -compose_dirs_and_surface_normals(local.view(-1, 3), lat.flatten(), lon.flatten()).view(local.shape)
+
+    lens = (ray_origin_height - alt) / torch.cos(thetav * torch.pi / 180).view(dirs.shape[:-1]).double()
+
+    def height_at(length):
+        p = surface - length[..., None] * dirs
+        return cartesian_to_horizontal(p[..., 0], p[..., 1], p[..., 2])[2]
+
+    height = height_at(lens)
+    n_iter = 0
+    while n_iter < max_iters and (torch.abs(ray_origin_height - height) > tol).any():
+        lens = lens * ray_origin_height / height
+        height = height_at(lens)
+        n_iter += 1
+    lens = lens.float()
+    origins = (surface - dirs * lens[..., None]).view(-1, 3)
+    return origins.float(), dirs.view(-1, 3).float(), lens.float().flatten()
+
+
+def filter_rays(ray_origin, ray_dir, ray_rad):
+    """Mask of rays whose origin, direction and radiance are all finite. wgs_84.py:293-313."""
+    bad = ray_origin.isnan().any(dim=1) | ray_dir.isnan().any(dim=1) | ray_rad.isnan()
+    return ~bad
+
+
+def normalize_rays(ray_origin, ray_dir, ray_len):
+    """Scale/offset that maps origins and end points into [-1,1]^3. wgs_84.py:316-339."""
+    ends = torch.cat([ray_origin, ray_origin + ray_dir * ray_len[:, None]], dim=0)
+    hi = ends.max(dim=0)[0].double()
+    lo = ends.min(dim=0)[0].double()
+    scale = ((hi - lo).max() / 2).item()
+    offset = (hi + lo) / 2
+    return torch.clamp((ray_origin - offset) / scale, -1, 1).float(), scale, offset

@@ -1,0 +1,62 @@
+"""AtmoNeRF MLP (reference: src/atmonr/models/nerf.py).
+
+Eleven biased linear layers, width `hidden_dim`, a skip connection that re-injects the encoded
+position at layer 6, a density head on layer 9 (with unit Gaussian noise while training) and a
+direction-conditioned colour head. The layers are torch.nn.Linear (cuBLAS GEMMs -- plain library
+GEMMs; the hand-written tcgen05 path of this build targets the Instant-NGP MLPs). Parameter names
+(`fc1`..`fc11`) match the reference so checkpoints interchange.
+"""
+
+from __future__ import annotations
+
+import torch
+import torch.nn as nn
+import torch.nn.functional as F
+
+
+class AtmoNeRF(nn.Module):
+    def __init__(self, pos_channels: int, dir_channels: int, out_channels: int, volume_channels: int,
+                 hidden_dim: int = 256) -> None:
+        super().__init__()
+        self.pos_channels, self.dir_channels = pos_channels, dir_channels
+        self.out_channels, self.volume_channels, self.hidden_dim = out_channels, volume_channels, hidden_dim
+        h = hidden_dim
+        widths = [(pos_channels, h), (h, h), (h, h), (h, h), (h, h), (h + pos_channels, h), (h, h), (h, h),
+                  (h, h + volume_channels), (h + dir_channels, h // 2), (h // 2, out_channels)]
+        for k, (fan_in, fan_out) in enumerate(widths, start=1):
+            layer = nn.Linear(fan_in, fan_out)
+            nn.init.kaiming_normal_(layer.weight, mode="fan_out")
+            setattr(self, f"fc{k}", layer)
+
+    def forward_pos_only(self, x_pos: torch.Tensor):
+        """Trunk up to the density head. models/nerf.py:48-73."""
+        x = x_pos
+        for k in range(1, 6):
+            x = F.relu(getattr(self, f"fc{k}")(x))
+        x = F.relu(self.fc6(torch.cat([x, x_pos], dim=1)))
+        x = F.relu(self.fc7(x))
+        x = F.relu(self.fc8(x))
+        x = self.fc9(x)
+        sigma = x[:, self.hidden_dim:]
+        if self.training:
+            sigma = sigma + torch.randn(sigma.shape, device=sigma.device)
+        return x, F.relu(sigma)
+
+    def forward(self, x: torch.Tensor):
+        """models/nerf.py:75-93 -> (colour in (0,1), density >= 0)."""
+        x_pos, d = x[:, : self.pos_channels], x[:, self.pos_channels:]
+        feat, sigma = self.forward_pos_only(x_pos)
+        hid = F.relu(self.fc10(torch.cat([feat[:, : self.hidden_dim], d], dim=1)))
+        return torch.sigmoid(self.fc11(hid)), sigma
+
+
+def get_model(hidden_dim: int, N_lambda: int, L_x, L_d: int, include_height: bool):
+    """models/nerf.py:96-144 -> (coarse, fine): the coarse net has one density, the fine net one
+    density per band."""
+    if isinstance(L_x, int):
+        pos_channels = L_x * (8 if include_height else 6)
+    else:
+        assert len(L_x) == (4 if include_height else 3)
+        pos_channels = 2 * sum(L_x)
+    common = dict(pos_channels=pos_channels, dir_channels=6 * L_d, out_channels=N_lambda, hidden_dim=hidden_dim)
+    return AtmoNeRF(volume_channels=1, **common), AtmoNeRF(volume_channels=N_lambda, **common)

@@ -1,0 +1,164 @@
+"""Fused Instant-NGP render step (forward and backward) on libatmonr_b200.
+
+Forward (instant_ngp.py:129-192 of the reference):
+    rays -> [sample + geodetic preprocess] -> [hash grid + pos_mlp + SH + dir_mlp per sample]
+         -> [surface branch per ray] -> [compositing]  ->  colour maps (B, 4)
+Backward: compositing backward -> field backward (recomputes the per-sample activations,
+accumulates MLP weight gradients per CTA, scatters table gradients with vector REDs) ->
+surface backward.
+
+Per-sample tensors kept between forward and backward: x01 (12 B), z (4 B), raw sigma (4 B),
+raw colour (16 B). The (B, N, .) outputs the reference returns eagerly are materialised only
+when somebody reads them (LazyResults).
+"""
+
+from __future__ import annotations
+
+import ctypes as C
+from dataclasses import dataclass, field
+
+import torch
+
+from atmonr.native import lib as L
+from atmonr.native import ops
+
+_f32 = torch.float32
+
+
+@dataclass
+class NGPState:
+    """Static description of one InstantNGPPipeline for the fused kernels."""
+
+    frame: L.FrameT
+    grid3: L.GridT
+    grid2: L.GridT
+    pos_mlp: L.MlpT
+    dir_mlp: L.MlpT
+    surf_mlp: L.MlpT
+    n_samples: int
+    alt_compress: float
+    z_scale: float            # scale / 1000 (normalised distance -> km)
+    seed: int = 0
+    step: int = 0             # advances once per forward: new stratified draws every step
+    ray_index_base: int = 0   # global index of the first ray of this rank's shard
+    bins: torch.Tensor | None = None
+    last: dict = field(default_factory=dict)
+
+
+def field_forward(st: NGPState, table16, pos_w16, dir_w16, x01, dirs, b, n):
+    sigma_raw = torch.empty(b * n, device=x01.device, dtype=_f32)
+    color_raw = torch.empty((b * n, 4), device=x01.device, dtype=_f32)
+    L.call("atmonr_ngp_field_fwd", C.byref(st.grid3), L.ptr(table16), C.byref(st.pos_mlp), L.ptr(pos_w16),
+           C.byref(st.dir_mlp), L.ptr(dir_w16), L.ptr(x01), L.ptr(dirs), b, n, L.ptr(sigma_raw), L.ptr(color_raw),
+           L.stream())
+    return sigma_raw, color_raw
+
+
+def surface_forward(st: NGPState, table16, w16, origin, direction, length):
+    b = origin.shape[0]
+    out = torch.empty((b, 4), device=origin.device, dtype=_f32)
+    L.call("atmonr_ngp_surface_fwd", C.byref(st.grid2), L.ptr(table16), C.byref(st.surf_mlp), L.ptr(w16),
+           L.ptr(origin), L.ptr(direction), L.ptr(length), b, L.ptr(out), L.stream())
+    return out
+
+
+class NGPRenderFn(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, pos_table, pos_w, dir_w, surf_table, surf_w, st: NGPState, shadows, origin, direction, length, u):
+        t16, pw16, dw16, s16, sw16 = shadows
+        origin = origin.contiguous().float()
+        direction = direction.contiguous().float()
+        length = length.contiguous().float()
+        b, n = origin.shape[0], st.n_samples
+        if st.bins is None or st.bins.device != origin.device or st.bins.numel() != n:
+            st.bins = ops.linspace_bins(n, origin.device)
+        seed = (st.seed * 0x9E3779B97F4A7C15 + st.step) & 0xFFFFFFFFFFFFFFFF
+        x01, z = ops.ngp_sample_points(st.frame, origin, direction, length, n, st.alt_compress, u=u, random=True,
+                                       seed=seed, ray_index_base=st.ray_index_base, bins=st.bins)
+        sigma_raw, color_raw = field_forward(st, t16, pw16, dw16, x01, direction, b, n)
+        cs_raw = surface_forward(st, s16, sw16, origin, direction, length)
+        cmap, catmo, csurf, tsurf, _, _ = ops.composite_forward(
+            z, color_raw.view(b, n, 4), sigma_raw.view(b, n, 1), cs_raw, st.z_scale, relu=True,
+            want_weights=False, want_alpha=False)
+        ctx.st = st
+        ctx.save_for_backward(t16, pw16, dw16, s16, sw16, origin, direction, length, x01, z, sigma_raw, color_raw,
+                              cs_raw, catmo, tsurf)
+        ctx.sizes = (pos_table.numel(), pos_w.numel(), dir_w.numel(), surf_table.numel(), surf_w.numel())
+        st.last = {"z": z, "sigma_raw": sigma_raw.view(b, n, 1), "color_raw": color_raw.view(b, n, 4),
+                   "color_surf_raw": cs_raw, "x01": x01}
+        return cmap, catmo, csurf
+
+    @staticmethod
+    def backward(ctx, g_map, g_atmo, g_surf):
+        st = ctx.st
+        (t16, pw16, dw16, s16, sw16, origin, direction, length, x01, z, sigma_raw, color_raw, cs_raw, catmo,
+         tsurf) = ctx.saved_tensors
+        b, n = z.shape
+        dev = z.device
+        g_map = torch.zeros_like(catmo) if g_map is None else g_map
+        d_atmo = (g_map + g_atmo if g_atmo is not None else g_map).contiguous().float()
+        d_surf = (g_map + g_surf if g_surf is not None else g_map).contiguous().float()
+        dcolor, dsigma, dcs = ops.composite_backward(
+            z, color_raw.view(b, n, 4), sigma_raw.view(b, n, 1), cs_raw, catmo, tsurf, d_atmo, d_surf,
+            st.z_scale, relu=True)
+        n_t, n_pw, n_dw, n_s, n_sw = ctx.sizes
+        d_table = torch.zeros(n_t, device=dev, dtype=_f32)
+        d_pw = torch.zeros(n_pw, device=dev, dtype=_f32)
+        d_dw = torch.zeros(n_dw, device=dev, dtype=_f32)
+        d_s = torch.zeros(n_s, device=dev, dtype=_f32)
+        d_sw = torch.zeros(n_sw, device=dev, dtype=_f32)
+        L.call("atmonr_ngp_field_bwd", C.byref(st.grid3), L.ptr(t16), C.byref(st.pos_mlp), L.ptr(pw16),
+               C.byref(st.dir_mlp), L.ptr(dw16), L.ptr(x01), L.ptr(direction), L.ptr(dsigma), L.ptr(dcolor), b, n,
+               L.ptr(d_table), L.ptr(d_pw), L.ptr(d_dw), L.stream())
+        L.call("atmonr_ngp_surface_bwd", C.byref(st.grid2), L.ptr(s16), C.byref(st.surf_mlp), L.ptr(sw16),
+               L.ptr(origin), L.ptr(direction), L.ptr(length), L.ptr(dcs), b, L.ptr(d_s), L.ptr(d_sw), L.stream())
+        return d_table, d_pw, d_dw, d_s, d_sw, None, None, None, None, None, None
+
+
+class LazyResults(dict):
+    """Result dict of InstantNGPPipeline.forward. The (B, N, .) entries of the reference
+    (instant_ngp.py:194-203) are computed on first access from the saved raw field outputs;
+    they are detached (the trainer never differentiates through them)."""
+
+    LAZY = ("color_fine", "sigma_fine", "weights_fine", "z_vals_fine", "color_surf")
+
+    def __init__(self, eager: dict, st: NGPState):
+        super().__init__(eager)
+        self._st = st
+        self._buf = dict(st.last)
+
+    def _materialise(self, key):
+        b = self._buf
+        if key == "color_fine":
+            return torch.relu(b["color_raw"])[:, :-1]
+        if key == "sigma_fine":
+            return torch.relu(b["sigma_raw"])[:, :-1]
+        if key == "z_vals_fine":
+            return b["z"]
+        if key == "color_surf":
+            return torch.relu(b["color_surf_raw"])
+        if key == "weights_fine":
+            return ops.composite_forward(b["z"], b["color_raw"], b["sigma_raw"], b["color_surf_raw"],
+                                         self._st.z_scale, relu=True, want_weights=True, want_alpha=False)[4]
+        raise KeyError(key)
+
+    def __getitem__(self, key):
+        if not dict.__contains__(self, key) and key in self.LAZY:
+            dict.__setitem__(self, key, self._materialise(key))
+        return dict.__getitem__(self, key)
+
+    def __contains__(self, key):
+        return dict.__contains__(self, key) or key in self.LAZY
+
+    def keys(self):
+        return list(dict.keys(self)) + [k for k in self.LAZY if not dict.__contains__(self, k)]
+
+
+def extract_sigma(st: NGPState, table16, pos_w16, pts: torch.Tensor) -> torch.Tensor:
+    """instant_ngp.py:208-247: (n,3) float64 normalised points -> (n,1) float32 density."""
+    p = pts.contiguous().double()
+    n = p.shape[0]
+    out = torch.empty(n, device=p.device, dtype=_f32)
+    L.call("atmonr_extract_sigma", C.byref(st.frame), C.byref(st.grid3), L.ptr(table16), C.byref(st.pos_mlp),
+           L.ptr(pos_w16), L.ptr(p), n, float(st.alt_compress), L.ptr(out), L.stream())
+    return out.view(n, 1)

@@ -1,0 +1,270 @@
+"""Operator layer over libatmonr_b200: tensor-in / tensor-out functions and the
+torch.autograd.Function wrappers the pipelines are built from.
+
+PyTorch is plumbing here (device memory, streams, autograd bookkeeping); every arithmetic
+step on the hot path is a kernel of the shared library. No function in this module has a
+CPU implementation: CPU tensors raise.
+"""
+
+from __future__ import annotations
+
+import ctypes as C
+
+import torch
+
+from atmonr.native import lib as L
+
+_f32 = torch.float32
+
+LOSS_KINDS = {"dark": 0, "hdr": 1, "l1": 2, "l1_plus_hdr": 3, "mse": 4, "mse_plus_hdr": 5}
+
+
+def _c(t: torch.Tensor, dtype=None) -> torch.Tensor:
+    if dtype is not None and t.dtype != dtype:
+        t = t.to(dtype)
+    return t.contiguous()
+
+
+def linspace_bins(n_bins: int, device) -> torch.Tensor:
+    """linspace(0, 1, n+1)[:-1], computed by torch so the kernel uses the reference's exact
+    bin edges (samplers.py:34)."""
+    return torch.linspace(0, 1, n_bins + 1, device=device)[:-1].contiguous()
+
+
+# ------------------------------------------------------------------------------------------
+# samplers / preprocessor
+# ------------------------------------------------------------------------------------------
+def sample_uniform(origin, direction, length, n_bins, u=None, random=True, seed=0, ray_index_base=0):
+    """samplers.py:8-47. u given -> mode 1; random and no u -> in-kernel Philox; else mid-points."""
+    origin, direction, length = _c(origin, _f32), _c(direction, _f32), _c(length, _f32)
+    b = origin.shape[0]
+    mode = 1 if u is not None else (2 if random else 0)
+    if u is not None:
+        u = _c(u, _f32)
+        assert u.shape == (b, n_bins)
+    pts = torch.empty((b, n_bins, 3), device=origin.device, dtype=_f32)
+    z = torch.empty((b, n_bins), device=origin.device, dtype=_f32)
+    bins = linspace_bins(n_bins, origin.device)
+    L.call("atmonr_sample_uniform", L.ptr(origin), L.ptr(direction), L.ptr(length), L.ptr(u), L.ptr(bins),
+           b, n_bins, mode, seed, ray_index_base, L.ptr(pts), L.ptr(z), L.stream())
+    return pts, z
+
+
+def preprocess_horizontal(frame: L.FrameT, pts: torch.Tensor) -> torch.Tensor:
+    """harp2.py:372-386 on float32 or float64 points of shape (..., 3)."""
+    if pts.dtype not in (torch.float32, torch.float64):
+        pts = pts.float()
+    p = pts.contiguous()
+    out = torch.empty_like(p)
+    L.call("atmonr_preprocess_horizontal", C.byref(frame), L.ptr(p), L.ptr(out), p.numel() // 3,
+           int(p.dtype == torch.float64), L.stream())
+    return out
+
+
+def ngp_sample_points(frame, origin, direction, length, n, alt_compress, u=None, random=True, seed=0,
+                      ray_index_base=0, bins=None):
+    """Fused instant_ngp.py:139-160 -> (x01 (B*n,3), z (B,n))."""
+    origin, direction, length = _c(origin, _f32), _c(direction, _f32), _c(length, _f32)
+    b = origin.shape[0]
+    mode = 1 if u is not None else (2 if random else 0)
+    if u is not None:
+        u = _c(u, _f32)
+    x01 = torch.empty((b * n, 3), device=origin.device, dtype=_f32)
+    z = torch.empty((b, n), device=origin.device, dtype=_f32)
+    if bins is None:
+        bins = linspace_bins(n, origin.device)
+    L.call("atmonr_ngp_sample_points", C.byref(frame), L.ptr(origin), L.ptr(direction), L.ptr(length), L.ptr(u),
+           L.ptr(bins), b, n, mode, seed, ray_index_base, float(alt_compress), L.ptr(x01), L.ptr(z), L.stream())
+    return x01, z
+
+
+# ------------------------------------------------------------------------------------------
+# hash grid
+# ------------------------------------------------------------------------------------------
+def hashgrid_indices(grid: L.GridT, x: torch.Tensor) -> torch.Tensor:
+    x = _c(x, _f32)
+    m = x.shape[0]
+    idx = torch.empty((m, grid.n_levels, 1 << grid.n_dims), device=x.device, dtype=torch.int32)
+    L.call("atmonr_hashgrid_indices", C.byref(grid), L.ptr(x), x.shape[1], m, L.ptr(idx), L.stream())
+    return idx
+
+
+class HashGridFn(torch.autograd.Function):
+    """tcnn.Encoding(HashGrid).forward: x (M, >=D) float32, params flat float32."""
+
+    @staticmethod
+    def forward(ctx, x, params, table_f16, grid):
+        x = _c(x, _f32)
+        m = x.shape[0]
+        out = torch.empty((m, 2 * grid.n_levels), device=x.device, dtype=_f32)
+        L.call("atmonr_hashgrid_fwd", C.byref(grid), L.ptr(x), x.shape[1], L.ptr(table_f16), m, L.ptr(out), L.stream())
+        ctx.save_for_backward(x)
+        ctx.grid, ctx.n_params = grid, params.numel()
+        return out
+
+    @staticmethod
+    def backward(ctx, dout):
+        (x,) = ctx.saved_tensors
+        dtable = torch.zeros(ctx.n_params, device=x.device, dtype=_f32)
+        L.call("atmonr_hashgrid_bwd", C.byref(ctx.grid), L.ptr(x), x.shape[1], L.ptr(_c(dout, _f32)), x.shape[0],
+               L.ptr(dtable), L.stream())
+        return None, dtable, None, None
+
+
+# ------------------------------------------------------------------------------------------
+# MLP
+# ------------------------------------------------------------------------------------------
+class MlpFn(torch.autograd.Function):
+    """tcnn.Network.forward: x (M, n_in) float32 -> (M, n_out) float32."""
+
+    @staticmethod
+    def forward(ctx, x, params, w_f16, shape):
+        x = _c(x, _f32)
+        m = x.shape[0]
+        out = torch.empty((m, shape.n_out), device=x.device, dtype=_f32)
+        L.call("atmonr_mlp_fwd", C.byref(shape), L.ptr(w_f16), L.ptr(x), m, L.ptr(out), L.stream())
+        ctx.save_for_backward(x, w_f16)
+        ctx.shape, ctx.need_dx = shape, x.requires_grad
+        return out
+
+    @staticmethod
+    def backward(ctx, dout):
+        x, w_f16 = ctx.saved_tensors
+        shape = ctx.shape
+        dw = torch.zeros(shape.n_params, device=x.device, dtype=_f32)
+        dx = torch.empty_like(x) if ctx.needs_input_grad[0] else None
+        L.call("atmonr_mlp_bwd", C.byref(shape), L.ptr(w_f16), L.ptr(x), L.ptr(_c(dout, _f32)), x.shape[0],
+               L.ptr(dx), L.ptr(dw), L.stream())
+        return dx, dw, None, None
+
+
+# ------------------------------------------------------------------------------------------
+# compositing
+# ------------------------------------------------------------------------------------------
+def composite_forward(z, color, sigma, color_surf, z_scale, relu, want_weights=True, want_alpha=True):
+    b, n = z.shape
+    k, v = color.shape[-1], sigma.shape[-1]
+    dev = z.device
+    cmap = torch.empty((b, k), device=dev, dtype=_f32)
+    catmo = torch.empty((b, k), device=dev, dtype=_f32)
+    csurf = torch.empty((b, k), device=dev, dtype=_f32)
+    tsurf = torch.empty((b, v), device=dev, dtype=_f32)
+    weights = torch.empty((b, n, v), device=dev, dtype=_f32) if want_weights else None
+    alpha = torch.empty((b, n, v), device=dev, dtype=_f32) if want_alpha else None
+    L.call("atmonr_composite_fwd", L.ptr(z), L.ptr(color), L.ptr(sigma), L.ptr(color_surf), float(z_scale), b, n, k, v,
+           int(relu), L.ptr(cmap), L.ptr(catmo), L.ptr(csurf), L.ptr(tsurf), L.ptr(weights), L.ptr(alpha), L.stream())
+    return cmap, catmo, csurf, tsurf, weights, alpha
+
+
+def composite_backward(z, color, sigma, color_surf, catmo, tsurf, d_atmo, d_surf, z_scale, relu, want_dz=False):
+    b, n = z.shape
+    k, v = color.shape[-1], sigma.shape[-1]
+    dcolor = torch.empty_like(color)
+    dsigma = torch.empty_like(sigma)
+    dcs = torch.empty_like(color_surf) if color_surf is not None else None
+    ddelta = torch.empty_like(z) if want_dz else None
+    L.call("atmonr_composite_bwd", L.ptr(z), L.ptr(color), L.ptr(sigma), L.ptr(color_surf), L.ptr(catmo), L.ptr(tsurf),
+           L.ptr(d_atmo), L.ptr(d_surf), float(z_scale), b, n, k, v, int(relu), L.ptr(dcolor), L.ptr(dsigma),
+           L.ptr(dcs), L.ptr(ddelta), L.stream())
+    if not want_dz:
+        return dcolor, dsigma, dcs
+    # delta_i = hi_i - lo_i with hi_i = (z_i+z_{i+1})/2 (last: z_{N-1}), lo_i = (z_{i-1}+z_i)/2 (first: 0)
+    dz = torch.zeros_like(z)
+    dz[:, :-1] += 0.5 * ddelta[:, :-1]
+    dz[:, 1:] += 0.5 * ddelta[:, :-1]
+    dz[:, -1] += ddelta[:, -1]
+    dz[:, :-1] -= 0.5 * ddelta[:, 1:]
+    dz[:, 1:] -= 0.5 * ddelta[:, 1:]
+    return dcolor, dsigma, dcs, dz * z_scale
+
+
+class CompositeFn(torch.autograd.Function):
+    """graphics_utils.py render / render_with_surface, differentiable w.r.t. colour, density,
+    surface colour and (NeRF fine pass) the sample distances z."""
+
+    @staticmethod
+    def forward(ctx, z, color, sigma, color_surf, z_scale, relu):
+        z, color, sigma = _c(z, _f32), _c(color, _f32), _c(sigma, _f32)
+        cs = _c(color_surf, _f32) if color_surf is not None else None
+        cmap, catmo, csurf, tsurf, weights, alpha = composite_forward(z, color, sigma, cs, z_scale, relu)
+        ctx.save_for_backward(z, color, sigma, cs, catmo, tsurf)
+        ctx.z_scale, ctx.relu = z_scale, relu
+        ctx.want_dz = z.requires_grad
+        ctx.mark_non_differentiable(weights, alpha)
+        return cmap, catmo, csurf, weights, alpha
+
+    @staticmethod
+    def backward(ctx, g_map, g_atmo, g_surf, _gw, _ga):
+        z, color, sigma, cs, catmo, tsurf = ctx.saved_tensors
+        zero = torch.zeros_like(catmo)
+        g_map = zero if g_map is None else g_map
+        d_atmo = _c(g_map + (g_atmo if g_atmo is not None else 0), _f32)
+        d_surf = _c(g_map + (g_surf if g_surf is not None else 0), _f32)
+        out = composite_backward(z, color, sigma, cs, catmo, tsurf, d_atmo, d_surf, ctx.z_scale, ctx.relu,
+                                 want_dz=ctx.needs_input_grad[0])
+        dz = out[3] if ctx.needs_input_grad[0] else None
+        return dz, out[0], out[1], out[2], None, None
+
+
+# ------------------------------------------------------------------------------------------
+# loss
+# ------------------------------------------------------------------------------------------
+class BandLossFn(torch.autograd.Function):
+    """instant_ngp.py:249-263: select the ray's band, apply losses.py:<kind>, mean over rays.
+    The gradient w.r.t. the colour map is produced by the same kernel."""
+
+    @staticmethod
+    def forward(ctx, color_map, band, rad, max_i, kind):
+        cm = _c(color_map, _f32)
+        b, k = cm.shape
+        loss = torch.empty(1, device=cm.device, dtype=_f32)
+        dcm = torch.empty_like(cm)
+        partial = torch.empty(1024, device=cm.device, dtype=_f32)
+        L.call("atmonr_band_loss", L.ptr(cm), L.ptr(_c(band, torch.int64)), L.ptr(_c(rad, _f32)), float(max_i), int(kind),
+               b, k, 1.0, L.ptr(loss), L.ptr(dcm), L.ptr(partial), L.stream())
+        ctx.save_for_backward(dcm)
+        return loss[0]
+
+    @staticmethod
+    def backward(ctx, g):
+        (dcm,) = ctx.saved_tensors
+        return dcm * g, None, None, None, None
+
+
+def band_loss(color_map, band, rad, max_i, kind: str):
+    return BandLossFn.apply(color_map, band, rad, max_i, LOSS_KINDS[kind])
+
+
+# ------------------------------------------------------------------------------------------
+# optimizer
+# ------------------------------------------------------------------------------------------
+def adamw_step(param, grad, exp_avg, exp_avg_sq, param_f16, lr, beta1, beta2, eps, weight_decay, step,
+               grad_scale=1.0, zero_grad=False):
+    L.call("atmonr_adamw_step", L.ptr(param), L.ptr(grad), L.ptr(exp_avg), L.ptr(exp_avg_sq), L.ptr(param_f16),
+           param.numel(), float(lr), float(beta1), float(beta2), float(eps), float(weight_decay), int(step),
+           float(grad_scale), int(zero_grad), L.stream())
+
+
+# ------------------------------------------------------------------------------------------
+# NeRF helpers
+# ------------------------------------------------------------------------------------------
+def positional_encoding(pts: torch.Tensor, freqs, interleaved: bool) -> torch.Tensor:
+    p = _c(pts, _f32)
+    c = p.shape[-1]
+    flat = p.reshape(-1, c)
+    fl = list(freqs) if not isinstance(freqs, int) else [freqs] * c
+    arr = (C.c_int32 * len(fl))(*fl)
+    out = torch.empty((flat.shape[0], 2 * sum(fl)), device=p.device, dtype=_f32)
+    L.call("atmonr_positional_encoding", L.ptr(flat), flat.shape[0], c, arr, int(interleaved), L.ptr(out), L.stream())
+    return out
+
+
+def sample_pdf_z(weights, z_coarse, u):
+    """samplers.py:72-101 -> (z_sorted, inds)."""
+    w, zc, u = _c(weights, _f32), _c(z_coarse, _f32), _c(u, _f32)
+    b, nc = zc.shape
+    nf = u.shape[1]
+    z = torch.empty((b, nc + nf), device=zc.device, dtype=_f32)
+    inds = torch.empty((b, nf), device=zc.device, dtype=torch.int64)
+    L.call("atmonr_sample_pdf", L.ptr(w), L.ptr(zc), L.ptr(u), b, nc, nf, L.ptr(z), L.ptr(inds), L.stream())
+    return z, inds

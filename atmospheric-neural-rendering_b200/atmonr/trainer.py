@@ -1,0 +1,175 @@
+"""Training loop (reference: src/atmonr/trainer.py): same constructor, `train`, `save`, `load`,
+checkpoint layout, schedulers and TensorBoard tags, so scripts/train.py runs unchanged.
+
+Differences are host-side only: the three per-step progress-tracker copies are
+gathered on the device and written to the host in one transfer, and the loss is read back once
+per step instead of twice. Under torch.distributed (torchrun) gradients are all-reduced over
+NCCL before the optimizer step (atmonr.distributed).
+"""
+
+from __future__ import annotations
+
+from datetime import datetime
+from pathlib import Path
+
+import numpy as np
+import torch
+from torch.optim.lr_scheduler import ExponentialLR
+from torch.utils.data import DataLoader
+
+from atmonr import distributed as dist
+from atmonr.batch_loader import BatchLoader
+from atmonr.utils import dict_to
+
+
+class _NullWriter:
+    def add_scalar(self, *a, **k): ...
+    def add_image(self, *a, **k): ...
+
+
+def _make_writer(log_dir):
+    try:
+        from torch.utils.tensorboard.writer import SummaryWriter  # noqa: PLC0415
+        return SummaryWriter(log_dir)
+    except Exception:  # tensorboard not installed
+        return _NullWriter()
+
+
+class Trainer:
+    def __init__(self, config: dict, dataset, pipeline, exp_name: str) -> None:
+        self.config, self.dataset, self.pipeline = config, dataset, pipeline
+        self.device = torch.cuda.current_device()
+        self.rank, self.world_size = dist.rank(), dist.world_size()
+        if config["all_gpu"]:
+            assert config["num_workers"] == 0
+            self.dataloader = BatchLoader(dataset, batch_size=config["batch_size"], shuffle=True,
+                                          rank=self.rank, world_size=self.world_size)
+        else:
+            self.dataloader = DataLoader(dataset, num_workers=config["num_workers"],
+                                         batch_size=config["batch_size"], shuffle=True)
+        self.epoch_idx = 0
+        self.iter_count = 0
+        self.num_epochs = int(-(self.config["num_iters"] // -len(self.dataloader)))
+        self.optimizer = pipeline.get_optimizer(self.config["optimizer"])
+        sched = self.config["scheduler"]
+        if sched["type"] == "target_lr":
+            gamma = (sched["final_lr"] / self.config["optimizer"]["lr"]) ** (1 / self.num_epochs)
+        elif sched["type"] == "fixed":
+            gamma = sched["gamma"]
+        else:
+            raise NotImplementedError(f"Unknown scheduler type {sched['type']}")
+        self.scheduler = ExponentialLR(optimizer=self.optimizer, gamma=gamma)
+        stamp = datetime.now().strftime("%Y%m%d_%H%M%S")
+        self.tensorboard_dir = Path("data") / "tensorboard" / f"{exp_name}_{stamp}"
+        self.writer = _make_writer(self.tensorboard_dir) if self.rank == 0 else _NullWriter()
+
+    def train_step(self, batch):
+        """forward -> loss -> zero_grad -> backward -> (all-reduce) -> step. trainer.py:99-105."""
+        results = self.pipeline.forward(batch)
+        loss = self.pipeline.compute_loss(batch, results)
+        self.optimizer.zero_grad()
+        loss.backward()
+        dist.all_reduce_gradients(self.optimizer)
+        self.optimizer.step()
+        return results, loss
+
+    def train(self, output_path: Path, profile: bool = False) -> None:
+        prof = self.get_profiler() if profile else None
+        if prof:
+            prof.start()
+        progress = self.dataset.get_progress_tracker()
+        last_len, running = 0, []
+        sched = self.config["scheduler"]
+        while self.iter_count < self.config["num_iters"]:
+            for batch in self.dataloader:
+                if prof:
+                    prof.step()
+                if not self.config["all_gpu"]:
+                    batch = dict_to(batch, self.device)
+                results, loss = self.train_step(batch)
+                loss_val = loss.item()
+                self.writer.add_scalar("Loss", loss_val, self.iter_count)
+                running = running[-self.config["print_frequency"]:] + [loss_val]
+                self.iter_count += 1
+                if (sched["type"] == "fixed" and self.iter_count % sched["decay_interval"] == 0
+                        and self.iter_count > sched["decay_start"]):
+                    self.scheduler.step()
+                # progress tracker: one gather on the device, one copy to the host (trainer.py:123-140)
+                band = batch["irgb_idx"][:, None]
+                maps = torch.stack([results["color_map_fine"], results["color_map_surf"], results["color_map_atmo"]])
+                pix = torch.take_along_dim(maps.detach(), band[None].expand(3, -1, -1), dim=2)[..., 0].float().cpu().numpy()
+                where = batch["idx"].cpu().numpy()
+                progress.pred_pixels[where] = pix[0]
+                progress.pred_pixels_surf[where] = pix[1]
+                progress.pred_pixels_atmo[where] = pix[2]
+                if self.iter_count >= self.config["num_iters"]:
+                    break
+                if self.iter_count % self.config["print_frequency"] == 0 and self.rank == 0:
+                    line = f"{self.iter_count}/{self.config['num_iters']} | Loss: {sum(running) / len(running):.5f}"
+                    print(line + max(0, last_len - len(line)) * " ", end="\r")
+                    last_len = len(line)
+            self._end_of_epoch(progress, output_path, last_len)
+            if prof:
+                prof.stop()
+                prof = None
+        print()
+
+    def _end_of_epoch(self, progress, output_path, last_len) -> None:
+        """trainer.py:160-214: images, metrics, scheduler (target_lr), checkpoint."""
+        dev = self.pipeline.device
+
+        def as_cube(img, pixels):
+            img[progress.valid] = pixels
+            return torch.from_numpy(img).to(dev).permute(2, 0, 1)
+
+        pred = as_cube(progress.pred_img, progress.pred_pixels)
+        pred_surf = as_cube(progress.pred_img_surf, progress.pred_pixels_surf)
+        pred_atmo = as_cube(progress.pred_img_atmo, progress.pred_pixels_atmo)
+        target = torch.from_numpy(progress.target_img).to(dev)
+        target[target.isnan()] = 0
+        target = target.permute(2, 0, 1)
+        self.epoch_idx += 1
+        if self.config["scheduler"]["type"] == "target_lr":
+            self.scheduler.step()
+        if self.rank != 0:
+            return
+        metrics = self.dataset.get_image_metrics(pred, target)
+        line = f"Epoch {self.epoch_idx}/{self.num_epochs}"
+        for name, val in metrics.items():
+            if isinstance(val, list):
+                continue
+            line += f" | {name}: {val:.3f}"
+            self.writer.add_scalar(name, val, self.epoch_idx)
+        print(line + max(0, last_len - len(line)) * " ")
+        rgb = lambda cube: self.dataset.get_rgb(cube).cpu().numpy()
+        viz = np.concatenate([rgb(pred_surf), rgb(pred_atmo), rgb(pred), progress.target_img_rgb], axis=1)
+        self.writer.add_image(f"Epoch {self.epoch_idx}", np.transpose(viz, (2, 0, 1)))
+        self.save(output_path, self.epoch_idx)
+
+    def get_profiler(self) -> torch.profiler.profile:
+        return torch.profiler.profile(
+            activities=[torch.profiler.ProfilerActivity.CPU, torch.profiler.ProfilerActivity.CUDA],
+            schedule=torch.profiler.schedule(wait=2, warmup=2, active=10, repeat=1),
+            on_trace_ready=torch.profiler.tensorboard_trace_handler(str(self.tensorboard_dir)),
+            record_shapes=True, profile_memory=True, with_stack=True, with_flops=True, with_modules=True,
+        )
+
+    def save(self, output_path: Path, epoch: int) -> None:
+        """trainer.py:239-256: epoch_NNNN.pt with the same keys as the reference."""
+        torch.save(
+            {"pipeline": self.pipeline.state_dict(), "optimizer": self.optimizer.state_dict(),
+             "scheduler": self.scheduler.state_dict(), "tensorboard_dir": self.tensorboard_dir,
+             "epoch_idx": self.epoch_idx, "iter_count": self.iter_count},
+            Path(output_path) / f"epoch_{epoch:04d}.pt",
+        )
+
+    def load(self, output_path: Path) -> None:
+        """trainer.py:258-274: resume from the newest epoch_*.pt."""
+        ckpts = sorted(Path(output_path).glob("epoch_*.pt"), key=lambda c: int(c.stem.split("_")[1]))
+        ckpt = torch.load(ckpts[-1], weights_only=False)
+        self.pipeline.load_state_dict(ckpt["pipeline"])
+        self.optimizer.load_state_dict(ckpt["optimizer"])
+        self.scheduler.load_state_dict(ckpt["scheduler"])
+        self.tensorboard_dir = ckpt["tensorboard_dir"]
+        self.writer = _make_writer(self.tensorboard_dir) if self.rank == 0 else _NullWriter()
+        self.epoch_idx, self.iter_count = ckpt["epoch_idx"], ckpt["iter_count"]

@@ -1,0 +1,1225 @@
+// atmonr_b200.cu -- kernels and C ABI of libatmonr_b200.so (sm_100a).
+// Interface contract: include/atmonr_b200.h. Reference citations are relative to the
+// nasa/atmospheric-neural-rendering tree.
+#include "common.cuh"
+#include "hashgrid.cuh"
+#include "mlp_simt.cuh"
+
+// The translation unit is compiled in four parts (in parallel, see build.py): each part
+// instantiates a subset of the kernels. ATM_PART unset = everything.
+#ifndef ATM_PART
+#define ATM_PART_BASIC 1
+#define ATM_PART_MLP 1
+#define ATM_PART_FIELD 1
+#define ATM_PART_SURF 1
+#else
+#define ATM_PART_BASIC (ATM_PART == 0)
+#define ATM_PART_MLP (ATM_PART == 1)
+#define ATM_PART_FIELD (ATM_PART == 2)
+#define ATM_PART_SURF (ATM_PART == 3)
+#endif
+
+namespace atm {
+#if ATM_PART_BASIC
+thread_local char g_last_error[512] = "";
+#endif
+
+#if ATM_PART_BASIC
+// =========================================================================================
+// Samplers and the point preprocessor
+// =========================================================================================
+__device__ __forceinline__ float draw_t(int mode, const float* u, int64_t idx, uint64_t seed,
+                                        uint64_t ray, int bin) {
+  if (mode == 0) return 0.5f;
+  if (mode == 1) return u[idx];
+  return philox_uniform(seed, ray, (uint32_t)bin);
+}
+
+// samplers.py:8-47
+__global__ void k_sample_uniform(const float* __restrict__ o, const float* __restrict__ d,
+                                 const float* __restrict__ len, const float* __restrict__ u,
+                                 const float* __restrict__ bins, int64_t total, int N, int mode,
+                                 uint64_t seed, uint64_t base, float* __restrict__ pts,
+                                 float* __restrict__ z) {
+  const int64_t idx = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+  if (idx >= total) return;
+  const int64_t ray = idx / N;
+  const int i = (int)(idx - ray * N);
+  const float t = draw_t(mode, u, idx, seed, base + ray, i);
+  const float lo = bins ? bins[i] : (float)i / (float)N;
+  const float zz = stratified_z(lo, t, N, len[ray]);
+  z[idx] = zz;
+#pragma unroll
+  for (int k = 0; k < 3; ++k) pts[idx * 3 + k] = o[ray * 3 + k] + d[ray * 3 + k] * zz;
+}
+
+// harp2.py:372-386
+__global__ void k_preprocess_f32(atmonr_frame_t f, const float* __restrict__ p, float* __restrict__ out,
+                                 int64_t n) {
+  const int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  float a, b, c;
+  preprocess_f32(f, p[3 * i], p[3 * i + 1], p[3 * i + 2], a, b, c);
+  out[3 * i] = a;
+  out[3 * i + 1] = b;
+  out[3 * i + 2] = c;
+}
+__global__ void k_preprocess_f64(atmonr_frame_t f, const double* __restrict__ p, double* __restrict__ out,
+                                 int64_t n) {
+  const int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  double a, b, c;
+  preprocess_f64(f, p[3 * i], p[3 * i + 1], p[3 * i + 2], a, b, c);
+  out[3 * i] = a;
+  out[3 * i + 1] = b;
+  out[3 * i + 2] = c;
+}
+
+// instant_ngp.py:139-160 in one pass: stratified sample -> ECEF -> geodetic -> [0,1]^3 with
+// compressed altitude. One thread per sample; consecutive threads walk along a ray.
+__global__ void k_ngp_sample_points(atmonr_frame_t f, const float* __restrict__ o,
+                                    const float* __restrict__ d, const float* __restrict__ len,
+                                    const float* __restrict__ u, const float* __restrict__ bins,
+                                    int64_t total, int N, int mode, uint64_t seed, uint64_t base,
+                                    float alt_compress, float* __restrict__ x01, float* __restrict__ z) {
+  const int64_t idx = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+  if (idx >= total) return;
+  const int64_t ray = idx / N;
+  const int i = (int)(idx - ray * N);
+  const float t = draw_t(mode, u, idx, seed, base + ray, i);
+  const float lo = bins ? bins[i] : (float)i / (float)N;
+  const float zz = stratified_z(lo, t, N, len[ray]);
+  z[idx] = zz;
+  float p[3];
+#pragma unroll
+  for (int k = 0; k < 3; ++k) p[k] = o[ray * 3 + k] + d[ray * 3 + k] * zz;
+  float c0 = p[0], c1 = p[1], c2 = p[2];
+  if (f.enabled) preprocess_f32(f, p[0], p[1], p[2], c0, c1, c2);
+  float x0, x1, x2;
+  to_unit_cube(c0, c1, c2, alt_compress, x0, x1, x2);
+  x01[idx * 3] = x0;
+  x01[idx * 3 + 1] = x1;
+  x01[idx * 3 + 2] = x2;
+}
+
+// =========================================================================================
+// Hash grid (modular operators)
+// =========================================================================================
+template <int D>
+__global__ void k_hashgrid_fwd(atmonr_grid_t g, const float* __restrict__ x, int xs,
+                               const __half2* __restrict__ table, int64_t M, float* __restrict__ out) {
+  const int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+  if (i >= M) return;
+  float p[D];
+#pragma unroll
+  for (int k = 0; k < D; ++k) p[k] = x[i * xs + k];
+  __half2 enc[ATMONR_MAX_LEVELS];
+  hash_encode<D>(g, table, p, enc);
+  float* row = out + i * 2 * g.n_levels;
+#pragma unroll
+  for (int l = 0; l < ATMONR_MAX_LEVELS; ++l)
+    if (l < g.n_levels) {
+      const float2 v = __half22float2(enc[l]);
+      row[2 * l] = v.x;
+      row[2 * l + 1] = v.y;
+    }
+}
+
+template <int D>
+__global__ void k_hashgrid_bwd(atmonr_grid_t g, const float* __restrict__ x, int xs,
+                               const float* __restrict__ dout, int64_t M, float* __restrict__ dtable) {
+  const int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+  if (i >= M) return;
+  float p[D];
+#pragma unroll
+  for (int k = 0; k < D; ++k) p[k] = x[i * xs + k];
+  float d[2 * ATMONR_MAX_LEVELS];
+#pragma unroll
+  for (int l = 0; l < 2 * ATMONR_MAX_LEVELS; ++l) d[l] = l < 2 * g.n_levels ? dout[i * 2 * g.n_levels + l] : 0.0f;
+  hash_scatter<D>(g, dtable, p, d, 1.0f);
+}
+
+template <int D>
+__global__ void k_hashgrid_indices(atmonr_grid_t g, const float* __restrict__ x, int xs, int64_t M,
+                                   uint32_t* __restrict__ idx) {
+  const int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+  if (i >= M) return;
+  float p[D];
+#pragma unroll
+  for (int k = 0; k < D; ++k) p[k] = x[i * xs + k];
+  for (int l = 0; l < g.n_levels; ++l) {
+    uint32_t cell[D];
+    float frac[D];
+    grid_cell<D>(p, g.scale[l], cell, frac);
+#pragma unroll
+    for (int c = 0; c < (1 << D); ++c) {
+      uint32_t e;
+      float w;
+      grid_corner<D>(cell, frac, c, g.res[l], g.size[l], e, w);
+      idx[(i * g.n_levels + l) * (1 << D) + c] = g.offset[l] + e;
+    }
+  }
+}
+
+#endif  // ATM_PART_BASIC
+#if ATM_PART_MLP
+// =========================================================================================
+// MLP (modular operators)
+// =========================================================================================
+template <int IN>
+__device__ __forceinline__ void load_padded_input(const float* __restrict__ x, int n_in, bool valid,
+                                                  __half2 (&xh)[IN / 2]) {
+#pragma unroll
+  for (int i = 0; i < IN / 2; ++i) {
+    const float a = !valid ? 0.0f : (2 * i < n_in ? x[2 * i] : 1.0f);
+    const float b = !valid ? 0.0f : (2 * i + 1 < n_in ? x[2 * i + 1] : 1.0f);
+    xh[i] = __floats2half2_rn(a, b);
+  }
+}
+
+template <int IN, int NH>
+__global__ void __launch_bounds__(kTile) k_mlp_fwd(const __half* __restrict__ w, const float* __restrict__ x,
+                                                   int n_in, int n_out, int64_t M, float* __restrict__ out) {
+  using S = MlpShape<IN, NH>;
+  extern __shared__ __align__(16) float smem[];
+  load_weights(w, smem, S::kNumWeights);
+  __syncthreads();
+  for (int64_t tile = blockIdx.x; tile * kTile < M; tile += gridDim.x) {
+    const int64_t i = tile * kTile + threadIdx.x;
+    if (i >= M) continue;
+    __half2 xh[IN / 2], h[NH][kWidth / 2];
+    load_padded_input<IN>(x + i * n_in, n_in, true, xh);
+    float y[kOutPad];
+    mlp_forward<IN, NH, kOutPad>(smem, xh, h, y);
+#pragma unroll
+    for (int o = 0; o < kOutPad; ++o)
+      if (o < n_out) out[i * n_out + o] = y[o];
+  }
+}
+
+template <int IN, int NH>
+__global__ void __launch_bounds__(kTile) k_mlp_bwd(const __half* __restrict__ w, const float* __restrict__ x,
+                                                   const float* __restrict__ dout, int n_in, int n_out,
+                                                   int64_t M, float* __restrict__ dx, float* __restrict__ dw) {
+  using S = MlpShape<IN, NH>;
+  extern __shared__ __align__(16) float smem[];
+  float* sW = smem;
+  float* sdW = sW + S::kNumWeights;
+  float* scratch = sdW + S::kNumWeights;
+  load_weights(w, sW, S::kNumWeights);
+  for (int i = threadIdx.x; i < S::kNumWeights; i += blockDim.x) sdW[i] = 0.0f;
+  __syncthreads();
+  for (int64_t tile = blockIdx.x; tile * kTile < M; tile += gridDim.x) {
+    const int64_t i = tile * kTile + threadIdx.x;
+    const bool valid = i < M;
+    __half2 xh[IN / 2], h[NH][kWidth / 2];
+    load_padded_input<IN>(x + (valid ? i : 0) * n_in, n_in, valid, xh);
+    float y[kOutPad], dy[kOutPad], dxi[IN];
+    mlp_forward<IN, NH, kOutPad>(sW, xh, h, y);
+#pragma unroll
+    for (int o = 0; o < kOutPad; ++o) dy[o] = (valid && o < n_out) ? dout[i * n_out + o] : 0.0f;
+    mlp_backward<IN, NH>(sW, sdW, scratch, xh, h, dy, dxi);
+    if (valid && dx) {
+#pragma unroll
+      for (int k = 0; k < IN; ++k)
+        if (k < n_in) dx[i * n_in + k] = dxi[k];
+    }
+  }
+  flush_dw(sdW, dw, S::kNumWeights);
+}
+
+#endif  // ATM_PART_MLP
+// =========================================================================================
+// Fused radiance field: hash grid -> pos_mlp -> [SH2(dir) | features | 1-pad] -> dir_mlp
+// =========================================================================================
+using PosMlp = MlpShape<32, 1>;
+using DirMlp = MlpShape<32, 2>;
+constexpr int kNumBands = 4;
+
+#if ATM_PART_FIELD
+// Assemble the padded dir_mlp input from the ray direction and the pos_mlp output
+// (instant_ngp.py:165-169; tcnn Composite{SH2, Identity} then 1.0 padding to 32).
+__device__ __forceinline__ void build_dir_input(const float* __restrict__ dir, const float (&po)[kOutPad],
+                                                __half2 (&din)[16]) {
+  float v[32];
+  float sh[4];
+  sh_degree2(dir[0], dir[1], dir[2], sh);
+#pragma unroll
+  for (int k = 0; k < 4; ++k) v[k] = sh[k];
+#pragma unroll
+  for (int k = 1; k < kOutPad; ++k) v[3 + k] = po[k];
+#pragma unroll
+  for (int k = 19; k < 32; ++k) v[k] = 1.0f;
+#pragma unroll
+  for (int k = 0; k < 16; ++k) din[k] = __floats2half2_rn(v[2 * k], v[2 * k + 1]);
+}
+
+__global__ void __launch_bounds__(kTile)
+k_field_fwd(atmonr_grid_t g, const __half2* __restrict__ table, const __half* __restrict__ pos_w,
+            const __half* __restrict__ dir_w, const float* __restrict__ x01, const float* __restrict__ dirs,
+            int64_t M, int N, float* __restrict__ sigma_raw, float* __restrict__ color_raw) {
+  __shared__ __align__(16) float sW[PosMlp::kNumWeights + DirMlp::kNumWeights];
+  float* sWp = sW;
+  float* sWd = sW + PosMlp::kNumWeights;
+  load_weights(pos_w, sWp, PosMlp::kNumWeights);
+  load_weights(dir_w, sWd, DirMlp::kNumWeights);
+  __syncthreads();
+  for (int64_t tile = blockIdx.x; tile * kTile < M; tile += gridDim.x) {
+    const int64_t i = tile * kTile + threadIdx.x;
+    if (i >= M) continue;
+    const float p[3] = {x01[3 * i], x01[3 * i + 1], x01[3 * i + 2]};
+    __half2 enc[16], hp[1][16], din[16], hd[2][16];
+    hash_encode<3>(g, table, p, enc);
+    float po[kOutPad];
+    mlp_forward<32, 1, kOutPad>(sWp, enc, hp, po);
+    sigma_raw[i] = po[0];
+    build_dir_input(dirs + (i / N) * 3, po, din);
+    float c[kNumBands];
+    mlp_forward<32, 2, kNumBands>(sWd, din, hd, c);
+    *reinterpret_cast<float4*>(color_raw + 4 * i) = make_float4(c[0], c[1], c[2], c[3]);
+  }
+}
+
+__global__ void __launch_bounds__(kTile)
+k_field_bwd(atmonr_grid_t g, const __half2* __restrict__ table, const __half* __restrict__ pos_w,
+            const __half* __restrict__ dir_w, const float* __restrict__ x01, const float* __restrict__ dirs,
+            const float* __restrict__ dsigma_raw, const float* __restrict__ dcolor_raw, int64_t M, int N,
+            float* __restrict__ dtable, float* __restrict__ dpos_w, float* __restrict__ ddir_w) {
+  extern __shared__ __align__(16) float smem[];
+  float* sWp = smem;
+  float* sWd = sWp + PosMlp::kNumWeights;
+  float* sdWp = sWd + DirMlp::kNumWeights;
+  float* sdWd = sdWp + PosMlp::kNumWeights;
+  float* scratch = sdWd + DirMlp::kNumWeights;
+  load_weights(pos_w, sWp, PosMlp::kNumWeights);
+  load_weights(dir_w, sWd, DirMlp::kNumWeights);
+  for (int i = threadIdx.x; i < PosMlp::kNumWeights + DirMlp::kNumWeights; i += blockDim.x) sdWp[i] = 0.0f;
+  __syncthreads();
+  for (int64_t tile = blockIdx.x; tile * kTile < M; tile += gridDim.x) {
+    const int64_t i = tile * kTile + threadIdx.x;
+    const bool valid = i < M;
+    const int64_t j = valid ? i : 0;
+    const float p[3] = {x01[3 * j], x01[3 * j + 1], x01[3 * j + 2]};
+    __half2 enc[16], hp[1][16], din[16], hd[2][16];
+    hash_encode<3>(g, table, p, enc);
+    float po[kOutPad];
+    mlp_forward<32, 1, kOutPad>(sWp, enc, hp, po);
+    build_dir_input(dirs + (j / N) * 3, po, din);
+    float c[kNumBands];
+    mlp_forward<32, 2, kNumBands>(sWd, din, hd, c);
+
+    float dout[kOutPad];
+#pragma unroll
+    for (int k = 0; k < kOutPad; ++k) dout[k] = 0.0f;
+    if (valid) {
+      const float4 dc = *reinterpret_cast<const float4*>(dcolor_raw + 4 * i);
+      dout[0] = dc.x; dout[1] = dc.y; dout[2] = dc.z; dout[3] = dc.w;
+    }
+    float ddin[32];
+    mlp_backward<32, 2>(sWd, sdWd, scratch, din, hd, dout, ddin);
+    float dpo[kOutPad];
+    dpo[0] = valid ? dsigma_raw[i] : 0.0f;
+#pragma unroll
+    for (int k = 1; k < kOutPad; ++k) dpo[k] = ddin[3 + k];
+    float denc[32];
+    mlp_backward<32, 1>(sWp, sdWp, scratch, enc, hp, dpo, denc);
+    if (valid) hash_scatter<3>(g, dtable, p, denc, 1.0f);
+  }
+  flush_dw(sdWp, dpos_w, PosMlp::kNumWeights);
+  flush_dw(sdWd, ddir_w, DirMlp::kNumWeights);
+}
+
+#endif  // ATM_PART_FIELD
+// =========================================================================================
+// Surface branch (one row per ray): [hash2d(end point xy) | SH2(dir)] -> surf_mlp (48 wide in)
+// =========================================================================================
+using SurfMlp = MlpShape<48, 2>;
+#if ATM_PART_SURF
+
+__device__ __forceinline__ void surface_input(const atmonr_grid_t& g, const __half2* __restrict__ table,
+                                              const float* __restrict__ o, const float* __restrict__ d,
+                                              float len, float (&xy)[2], __half2 (&x)[24]) {
+  // instant_ngp.py:140,150: end point of the ray in normalised Cartesian, mapped to [0,1]
+#pragma unroll
+  for (int k = 0; k < 2; ++k) xy[k] = ((o[k] + d[k] * len) + 1.0f) / 2.0f;
+  __half2 enc[ATMONR_MAX_LEVELS];
+  hash_encode<2>(g, table, xy, enc);
+#pragma unroll
+  for (int k = 0; k < 16; ++k) x[k] = enc[k];
+  float sh[4];
+  sh_degree2(d[0], d[1], d[2], sh);
+  x[16] = __floats2half2_rn(sh[0], sh[1]);
+  x[17] = __floats2half2_rn(sh[2], sh[3]);
+#pragma unroll
+  for (int k = 18; k < 24; ++k) x[k] = __floats2half2_rn(1.0f, 1.0f);
+}
+
+__global__ void __launch_bounds__(kTile)
+k_surface_fwd(atmonr_grid_t g, const __half2* __restrict__ table, const __half* __restrict__ w,
+              const float* __restrict__ o, const float* __restrict__ d, const float* __restrict__ len,
+              int64_t B, float* __restrict__ color_surf_raw) {
+  extern __shared__ __align__(16) float smem[];
+  load_weights(w, smem, SurfMlp::kNumWeights);
+  __syncthreads();
+  for (int64_t tile = blockIdx.x; tile * kTile < B; tile += gridDim.x) {
+    const int64_t i = tile * kTile + threadIdx.x;
+    if (i >= B) continue;
+    float xy[2];
+    __half2 x[24], h[2][16];
+    surface_input(g, table, o + 3 * i, d + 3 * i, len[i], xy, x);
+    float c[kNumBands];
+    mlp_forward<48, 2, kNumBands>(smem, x, h, c);
+    *reinterpret_cast<float4*>(color_surf_raw + 4 * i) = make_float4(c[0], c[1], c[2], c[3]);
+  }
+}
+
+__global__ void __launch_bounds__(kTile)
+k_surface_bwd(atmonr_grid_t g, const __half2* __restrict__ table, const __half* __restrict__ w,
+              const float* __restrict__ o, const float* __restrict__ d, const float* __restrict__ len,
+              const float* __restrict__ dcs, int64_t B, float* __restrict__ dtable, float* __restrict__ dw) {
+  extern __shared__ __align__(16) float smem[];
+  float* sW = smem;
+  float* sdW = sW + SurfMlp::kNumWeights;
+  float* scratch = sdW + SurfMlp::kNumWeights;
+  load_weights(w, sW, SurfMlp::kNumWeights);
+  for (int i = threadIdx.x; i < SurfMlp::kNumWeights; i += blockDim.x) sdW[i] = 0.0f;
+  __syncthreads();
+  for (int64_t tile = blockIdx.x; tile * kTile < B; tile += gridDim.x) {
+    const int64_t i = tile * kTile + threadIdx.x;
+    const bool valid = i < B;
+    const int64_t j = valid ? i : 0;
+    float xy[2];
+    __half2 x[24], h[2][16];
+    surface_input(g, table, o + 3 * j, d + 3 * j, len[j], xy, x);
+    float c[kNumBands];
+    mlp_forward<48, 2, kNumBands>(sW, x, h, c);
+    float dout[kOutPad];
+#pragma unroll
+    for (int k = 0; k < kOutPad; ++k) dout[k] = (valid && k < kNumBands) ? dcs[4 * i + k] : 0.0f;
+    float dx[48];
+    mlp_backward<48, 2>(sW, sdW, scratch, x, h, dout, dx);
+    if (valid) hash_scatter<2>(g, dtable, xy, dx, 1.0f);
+  }
+  flush_dw(sdW, dw, SurfMlp::kNumWeights);
+}
+
+#endif  // ATM_PART_SURF
+#if ATM_PART_BASIC
+// =========================================================================================
+// Emission-absorption compositing: one warp per ray (graphics_utils.py:6-77)
+// =========================================================================================
+struct RaySample {
+  float delta;          // Voronoi cell width (km)
+  float sig[4];         // post-ReLU density per V
+  float col[4];         // post-ReLU colour per K
+};
+
+__device__ __forceinline__ float voronoi_delta(const float* __restrict__ zr, int i, int N, float zs) {
+  const float zi = zr[i] * zs;
+  const float lo = i == 0 ? zi * 0.0f : (zr[i - 1] * zs + zi) / 2.0f;
+  const float hi = i == N - 1 ? zi : (zi + zr[i + 1] * zs) / 2.0f;
+  return hi - lo;
+}
+
+template <int K, int V>
+__global__ void __launch_bounds__(128)
+k_composite_fwd(const float* __restrict__ z, const float* __restrict__ color, const float* __restrict__ sigma,
+                const float* __restrict__ color_surf, float zs, int64_t B, int N, int relu,
+                float* __restrict__ cmap, float* __restrict__ catmo, float* __restrict__ csurf,
+                float* __restrict__ tsurf, float* __restrict__ weights, float* __restrict__ alpha_out) {
+  const int lane = threadIdx.x & 31;
+  const int64_t ray = (blockIdx.x * (int64_t)blockDim.x + threadIdx.x) >> 5;
+  if (ray >= B) return;
+  const float* zr = z + ray * N;
+  float carry[V], surf[V], acc[K];
+#pragma unroll
+  for (int v = 0; v < V; ++v) carry[v] = 1.0f, surf[v] = 1.0f;
+#pragma unroll
+  for (int k = 0; k < K; ++k) acc[k] = 0.0f;
+  for (int base = 0; base < N; base += 32) {
+    const int i = base + lane;
+    const bool in = i < N;
+    const float delta = in ? voronoi_delta(zr, i, N, zs) : 0.0f;
+    float c[K];
+#pragma unroll
+    for (int k = 0; k < K; ++k) {
+      const float raw = in ? color[(ray * N + i) * K + k] : 0.0f;
+      c[k] = relu ? fmaxf(raw, 0.0f) : raw;
+    }
+#pragma unroll
+    for (int v = 0; v < V; ++v) {
+      const float raw = in ? sigma[(ray * N + i) * V + v] : 0.0f;
+      const float s = relu ? fmaxf(raw, 0.0f) : raw;
+      const float a = 1.0f - expf(-s * delta);
+      const float t = in ? (1.0f - a) + 1e-10f : 1.0f;
+      const float incl = warp_scan_prod(t, lane);
+      float excl = __shfl_up_sync(0xffffffffu, incl, 1);
+      if (lane == 0) excl = 1.0f;
+      const float T = carry[v] * excl;
+      const float w = a * T;
+      carry[v] *= __shfl_sync(0xffffffffu, incl, 31);
+      surf[v] *= in ? (1.0f - a) : 1.0f;
+      if (in) {
+        if (weights) weights[(ray * N + i) * V + v] = w;
+        if (alpha_out) alpha_out[(ray * N + i) * V + v] = a;
+      }
+      if (V == 1) {
+#pragma unroll
+        for (int k = 0; k < K; ++k) acc[k] += w * c[k];
+      } else {
+        acc[v] += w * c[v];
+      }
+    }
+  }
+  float S[V];
+#pragma unroll
+  for (int v = 0; v < V; ++v) S[v] = warp_prod(surf[v]);
+#pragma unroll
+  for (int k = 0; k < K; ++k) acc[k] = warp_sum(acc[k]);
+  if (lane == 0) {
+#pragma unroll
+    for (int v = 0; v < V; ++v)
+      if (tsurf) tsurf[ray * V + v] = S[v];
+#pragma unroll
+    for (int k = 0; k < K; ++k) {
+      float cs = 0.0f;
+      if (color_surf) {
+        const float raw = color_surf[ray * K + k];
+        cs = S[V == 1 ? 0 : k] * (relu ? fmaxf(raw, 0.0f) : raw);
+      }
+      if (catmo) catmo[ray * K + k] = acc[k];
+      if (csurf) csurf[ray * K + k] = cs;
+      cmap[ray * K + k] = acc[k] + cs;
+    }
+  }
+}
+
+// Backward: front-to-back with the saved totals. For sample i and density channel v
+// (q = sum_k g_atmo[k] c[k] over the colour channels that v attenuates):
+//   dL/dc[k]  = g_atmo[k] * w_i
+//   dL/dsig_v = delta_i * ( e_i * (T_i q_i - (Q_v - Qpre_i) / t_i) - S_v G_v )
+// with e = exp(-sig delta), t = (1-a)+1e-10, Q_v = sum_i w_i q_i (= g_atmo . C_atmo),
+// Qpre the inclusive prefix of w q, S_v = prod(1-a), G_v = sum_k g_surf[k] c_surf[k].
+template <int K, int V>
+__global__ void __launch_bounds__(128)
+k_composite_bwd(const float* __restrict__ z, const float* __restrict__ color, const float* __restrict__ sigma,
+                const float* __restrict__ color_surf, const float* __restrict__ catmo,
+                const float* __restrict__ tsurf, const float* __restrict__ g_atmo,
+                const float* __restrict__ g_surf, float zs, int64_t B, int N, int relu,
+                float* __restrict__ dcolor, float* __restrict__ dsigma, float* __restrict__ dcolor_surf,
+                float* __restrict__ ddelta) {
+  const int lane = threadIdx.x & 31;
+  const int64_t ray = (blockIdx.x * (int64_t)blockDim.x + threadIdx.x) >> 5;
+  if (ray >= B) return;
+  const float* zr = z + ray * N;
+  float ga[K], gs[K], Qtot[V], SG[V], carryT[V], carryQ[V];
+#pragma unroll
+  for (int k = 0; k < K; ++k) {
+    ga[k] = g_atmo[ray * K + k];
+    gs[k] = (g_surf && color_surf) ? g_surf[ray * K + k] : 0.0f;
+  }
+#pragma unroll
+  for (int v = 0; v < V; ++v) Qtot[v] = 0.0f, SG[v] = 0.0f, carryT[v] = 1.0f, carryQ[v] = 0.0f;
+#pragma unroll
+  for (int k = 0; k < K; ++k) {
+    const int v = V == 1 ? 0 : k;
+    Qtot[v] += ga[k] * catmo[ray * K + k];
+    if (color_surf) {
+      const float raw = color_surf[ray * K + k];
+      const float cs = relu ? fmaxf(raw, 0.0f) : raw;
+      const float S = tsurf[ray * V + v];
+      SG[v] += S * gs[k] * cs;
+      if (lane == 0 && dcolor_surf) dcolor_surf[ray * K + k] = (relu && !(raw > 0.0f)) ? 0.0f : gs[k] * S;
+    }
+  }
+  for (int base = 0; base < N; base += 32) {
+    const int i = base + lane;
+    const bool in = i < N;
+    const float delta = in ? voronoi_delta(zr, i, N, zs) : 0.0f;
+    float c[K], craw[K];
+#pragma unroll
+    for (int k = 0; k < K; ++k) {
+      craw[k] = in ? color[(ray * N + i) * K + k] : 0.0f;
+      c[k] = relu ? fmaxf(craw[k], 0.0f) : craw[k];
+    }
+    float dc[K];
+    float dd = 0.0f;  // dL/d(delta_i), summed over density channels
+#pragma unroll
+    for (int k = 0; k < K; ++k) dc[k] = 0.0f;
+#pragma unroll
+    for (int v = 0; v < V; ++v) {
+      const float raw = in ? sigma[(ray * N + i) * V + v] : 0.0f;
+      const float s = relu ? fmaxf(raw, 0.0f) : raw;
+      const float e = expf(-s * delta);
+      const float a = 1.0f - e;
+      const float t = in ? (1.0f - a) + 1e-10f : 1.0f;
+      const float incl = warp_scan_prod(t, lane);
+      float excl = __shfl_up_sync(0xffffffffu, incl, 1);
+      if (lane == 0) excl = 1.0f;
+      const float T = carryT[v] * excl;
+      const float w = a * T;
+      float q = 0.0f;
+      if (V == 1) {
+#pragma unroll
+        for (int k = 0; k < K; ++k) q += ga[k] * c[k], dc[k] = ga[k] * w;
+      } else {
+        q = ga[v] * c[v];
+        dc[v] = ga[v] * w;
+      }
+      const float wq = in ? w * q : 0.0f;
+      const float qincl = carryQ[v] + warp_scan_sum(wq, lane);
+      carryT[v] *= __shfl_sync(0xffffffffu, incl, 31);
+      carryQ[v] = __shfl_sync(0xffffffffu, qincl, 31);
+      const float core = e * (T * q - (Qtot[v] - qincl) / t) - SG[v];  // dL/d(sigma*delta)
+      float ds = delta * core;
+      dd += s * core;
+      if (relu && !(raw > 0.0f)) ds = 0.0f;
+      if (in) dsigma[(ray * N + i) * V + v] = ds;
+    }
+    if (in && ddelta) ddelta[ray * N + i] = dd;
+    if (in) {
+#pragma unroll
+      for (int k = 0; k < K; ++k)
+        dcolor[(ray * N + i) * K + k] = (relu && !(craw[k] > 0.0f)) ? 0.0f : dc[k];
+    }
+  }
+}
+
+// =========================================================================================
+// Per-band loss + gradient (instant_ngp.py:249-263, losses.py:5-33)
+// =========================================================================================
+__device__ __forceinline__ void loss_term(int kind, float p, float g, float max_i, float& val, float& dp) {
+  const float eps = 1e-3f * max_i;
+  float v_mse = 0, d_mse = 0, v_hdr = 0, d_hdr = 0, v_l1 = 0, d_l1 = 0;
+  if (kind == 4 || kind == 5) {
+    const float r = p / max_i - g / max_i;
+    v_mse = r * r;
+    d_mse = 2.0f * r / max_i;
+  }
+  if (kind == 2 || kind == 3) {
+    const float r = p / max_i - g / max_i;
+    v_l1 = fabsf(r);
+    d_l1 = (r > 0.0f ? 1.0f : (r < 0.0f ? -1.0f : 0.0f)) / max_i;
+  }
+  if (kind == 1 || kind == 3 || kind == 5) {
+    const float r = logf(g + eps) - logf(p + eps);
+    v_hdr = r * r;
+    d_hdr = -2.0f * r / (p + eps);
+  }
+  if (kind == 0) {
+    const float r = (p - g) / (p + eps);
+    val = r * r;
+    dp = 2.0f * r / (p + eps);
+    return;
+  }
+  if (kind == 1) { val = v_hdr; dp = d_hdr; }
+  else if (kind == 2) { val = v_l1; dp = d_l1; }
+  else if (kind == 3) { val = v_l1 + 0.2f * v_hdr; dp = d_l1 + 0.2f * d_hdr; }
+  else if (kind == 4) { val = v_mse; dp = d_mse; }
+  else { val = v_mse + 0.2f * v_hdr; dp = d_mse + 0.2f * d_hdr; }
+}
+
+__global__ void __launch_bounds__(256)
+k_band_loss(const float* __restrict__ cmap, const int64_t* __restrict__ band, const float* __restrict__ rad,
+            float max_i, int kind, int64_t B, int K, float gscale, float* __restrict__ dcmap,
+            float* __restrict__ partial) {
+  __shared__ float red[8];
+  float sum = 0.0f;
+  const float invB = 1.0f / (float)B;
+  for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < B; i += (int64_t)gridDim.x * blockDim.x) {
+    const int b = (int)band[i];
+    float val, dp;
+    loss_term(kind, cmap[i * K + b], rad[i], max_i, val, dp);
+    sum += val;
+    if (dcmap) {
+      for (int k = 0; k < K; ++k) dcmap[i * K + k] = k == b ? dp * invB * gscale : 0.0f;
+    }
+  }
+  sum = warp_sum(sum);
+  if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = sum;
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    float s = 0.0f;
+    for (int w = 0; w < 8; ++w) s += red[w];
+    partial[blockIdx.x] = s;
+  }
+}
+__global__ void k_loss_finish(const float* __restrict__ partial, int n, int64_t B, float* __restrict__ loss) {
+  // single warp, fixed order -> deterministic
+  float s = 0.0f;
+  for (int i = threadIdx.x; i < n; i += 32) s += partial[i];
+  s = warp_sum(s);
+  if (threadIdx.x == 0) loss[0] = s / (float)B;
+}
+
+// =========================================================================================
+// Fused AdamW (dense; mirrors torch.optim.AdamW single-tensor arithmetic)
+// =========================================================================================
+struct AdamConsts {
+  float decay_mul;      // 1 - lr * weight_decay
+  float w1;             // 1 - beta1 (lerp weight)
+  float beta2;
+  float w2;             // 1 - beta2
+  float bc2_sqrt;       // sqrt(1 - beta2^step)
+  float neg_step_size;  // -lr / (1 - beta1^step)
+  float eps;
+  float gscale;
+};
+
+__device__ __forceinline__ void adam_one(const AdamConsts& c, float& p, float g, float& m, float& v) {
+  const float gr = g * c.gscale;
+  p = p * c.decay_mul;                                                             // param.mul_(1 - lr*wd)
+  m = c.w1 < 0.5f ? m + c.w1 * (gr - m) : gr - (gr - m) * (1.0f - c.w1);           // exp_avg.lerp_(grad, 1-beta1)
+  v = v * c.beta2;                                                                 // exp_avg_sq.mul_(beta2)
+  v = v + (c.w2 * gr) * gr;                                                        //   .addcmul_(g, g, 1-beta2)
+  const float denom = sqrtf(v) / c.bc2_sqrt + c.eps;
+  p = p + (c.neg_step_size * m) / denom;                                           // param.addcdiv_(m, denom, -step)
+}
+
+__global__ void __launch_bounds__(256)
+k_adamw(float* __restrict__ p, float* __restrict__ g, float* __restrict__ m, float* __restrict__ v,
+        __half* __restrict__ p16, int64_t n, AdamConsts c, int zero_grad) {
+  const int64_t stride = (int64_t)gridDim.x * blockDim.x * 4;
+  for (int64_t i = (blockIdx.x * (int64_t)blockDim.x + threadIdx.x) * 4; i < n; i += stride) {
+    if (i + 4 <= n) {
+      float4 P = *reinterpret_cast<float4*>(p + i), G = *reinterpret_cast<float4*>(g + i);
+      float4 Mv = *reinterpret_cast<float4*>(m + i), Vv = *reinterpret_cast<float4*>(v + i);
+      adam_one(c, P.x, G.x, Mv.x, Vv.x);
+      adam_one(c, P.y, G.y, Mv.y, Vv.y);
+      adam_one(c, P.z, G.z, Mv.z, Vv.z);
+      adam_one(c, P.w, G.w, Mv.w, Vv.w);
+      *reinterpret_cast<float4*>(p + i) = P;
+      *reinterpret_cast<float4*>(m + i) = Mv;
+      *reinterpret_cast<float4*>(v + i) = Vv;
+      if (zero_grad) *reinterpret_cast<float4*>(g + i) = make_float4(0.f, 0.f, 0.f, 0.f);
+      if (p16) {
+        *reinterpret_cast<__half2*>(p16 + i) = __floats2half2_rn(P.x, P.y);
+        *reinterpret_cast<__half2*>(p16 + i + 2) = __floats2half2_rn(P.z, P.w);
+      }
+    } else {
+      for (int64_t j = i; j < n; ++j) {
+        float pj = p[j], mj = m[j], vj = v[j];
+        adam_one(c, pj, g[j], mj, vj);
+        p[j] = pj; m[j] = mj; v[j] = vj;
+        if (zero_grad) g[j] = 0.0f;
+        if (p16) p16[j] = __float2half_rn(pj);
+      }
+    }
+  }
+}
+
+// =========================================================================================
+// Extraction: float64 point -> preprocess -> hash -> pos_mlp -> max(sigma, 0)
+// =========================================================================================
+__global__ void __launch_bounds__(kTile)
+k_extract_sigma(atmonr_frame_t f, atmonr_grid_t g, const __half2* __restrict__ table,
+                const __half* __restrict__ pos_w, const double* __restrict__ pts, int64_t n,
+                float alt_compress, float* __restrict__ sigma) {
+  __shared__ __align__(16) float sW[PosMlp::kNumWeights];
+  load_weights(pos_w, sW, PosMlp::kNumWeights);
+  __syncthreads();
+  for (int64_t tile = blockIdx.x; tile * kTile < n; tile += gridDim.x) {
+    const int64_t i = tile * kTile + threadIdx.x;
+    if (i >= n) continue;
+    double c0 = pts[3 * i], c1 = pts[3 * i + 1], c2 = pts[3 * i + 2];
+    if (f.enabled) preprocess_f64(f, c0, c1, c2, c0, c1, c2);
+    // instant_ngp.py:224-233 stay in float64; tcnn casts its input to float32
+    const float p[3] = {(float)((c0 + 1.0) / 2.0), (float)((c1 + 1.0) / 2.0),
+                        (float)(((c2 + 1.0) / 2.0) / (double)alt_compress)};
+    __half2 enc[16], hp[1][16];
+    hash_encode<3>(g, table, p, enc);
+    float po[1];
+    mlp_forward<32, 1, 1>(sW, enc, hp, po);
+    sigma[i] = fmaxf(po[0], 0.0f);
+  }
+}
+
+// =========================================================================================
+// NeRF helpers: positional encoding and inverse-CDF sampling
+// =========================================================================================
+struct PeCfg {
+  int32_t freqs[4];
+  int32_t col0[4];
+  int32_t C, width, interleaved;
+};
+
+__global__ void k_positional_encoding(const float* __restrict__ pts, int64_t M, PeCfg cfg, float* __restrict__ out) {
+  const int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+  if (i >= M) return;
+  const float PI_F = 3.14159265358979323846f;
+  float* row = out + i * cfg.width;
+  for (int a = 0; a < cfg.C; ++a) {
+    const float p = pts[i * cfg.C + a];
+    const int L = cfg.freqs[a];
+    float f = 1.0f;
+    for (int l = 0; l < L; ++l) {
+      const float arg = (f * PI_F) * p;
+      if (cfg.interleaved) {
+        row[cfg.col0[a] + 2 * l] = sinf(arg);
+        row[cfg.col0[a] + 2 * l + 1] = cosf(arg);
+      } else {
+        row[cfg.col0[a] + l] = sinf(arg);
+        row[cfg.col0[a] + L + l] = cosf(arg);
+      }
+      f *= 2.0f;
+    }
+  }
+}
+
+// samplers.py:72-101: one warp per ray. Shared memory: cdf[Nc-1], mids[Nc-1], merged[P] with
+// P the next power of two >= Nc+Nf (bitonic sort).
+__global__ void k_sample_pdf(const float* __restrict__ weights, const float* __restrict__ zc,
+                             const float* __restrict__ u, int64_t B, int Nc, int Nf, int P,
+                             float* __restrict__ zout, int64_t* __restrict__ inds) {
+  extern __shared__ float sm[];
+  const int lane = threadIdx.x;
+  const int64_t ray = blockIdx.x;
+  if (ray >= B) return;
+  const int nb = Nc - 2;       // pdf bins
+  const int ncdf = Nc - 1;     // cdf entries == number of mid points
+  float* cdf = sm;
+  float* mids = sm + ncdf;
+  float* merged = mids + ncdf;
+  const float* w = weights + ray * Nc;
+  const float* zr = zc + ray * Nc;
+  if (lane == 0) {
+    // torch CPU accumulates sum/cumsum of float32 in a wider type and rounds on store
+    double tot_d = 0.0;
+    for (int j = 0; j < nb; ++j) tot_d += (double)(w[1 + j] + 1e-8f);
+    const float tot = (float)tot_d;
+    double run = 0.0;
+    cdf[0] = 0.0f;
+    for (int j = 0; j < nb; ++j) {
+      run += (double)((w[1 + j] + 1e-8f) / tot);
+      cdf[1 + j] = (float)run;
+    }
+  }
+  for (int j = lane; j < ncdf; j += 32) mids[j] = 0.5f * (zr[j + 1] + zr[j]);
+  for (int j = lane; j < P; j += 32) merged[j] = j < Nc ? zr[j] : INFINITY;
+  __syncwarp();
+  for (int s = lane; s < Nf; s += 32) {
+    const float uu = u[ray * Nf + s];
+    int lo = 0, hi = ncdf;  // first index with cdf[idx] > uu  (right=True)
+    while (lo < hi) {
+      const int mid = (lo + hi) >> 1;
+      if (cdf[mid] <= uu) lo = mid + 1; else hi = mid;
+    }
+    const int ind = lo;
+    const int below = max(ind - 1, 0), above = min(ind, ncdf - 1);
+    float den = cdf[above] - cdf[below];
+    if (den < 1e-8f) den = 1.0f;
+    const float t = (uu - cdf[below]) / den;
+    merged[Nc + s] = mids[below] + t * (mids[above] - mids[below]);
+    if (inds) inds[ray * Nf + s] = ind;
+  }
+  __syncwarp();
+  for (int k = 2; k <= P; k <<= 1)
+    for (int j = k >> 1; j > 0; j >>= 1) {
+      for (int i = lane; i < P; i += 32) {
+        const int ixj = i ^ j;
+        if (ixj > i) {
+          const float a = merged[i], b = merged[ixj];
+          const bool up = (i & k) == 0;
+          if ((a > b) == up) { merged[i] = b; merged[ixj] = a; }
+        }
+      }
+      __syncwarp();
+    }
+  for (int j = lane; j < Nc + Nf; j += 32) zout[ray * (Nc + Nf) + j] = merged[j];
+}
+
+#endif  // ATM_PART_BASIC
+}  // namespace atm
+
+// =========================================================================================
+// C ABI
+// =========================================================================================
+using namespace atm;
+
+static inline cudaStream_t S(void* s) { return reinterpret_cast<cudaStream_t>(s); }
+
+static int num_sms() {
+  static int n = 0;
+  if (n == 0) {
+    int dev = 0;
+    cudaGetDevice(&dev);
+    cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev);
+    if (n <= 0) n = 148;
+  }
+  return n;
+}
+
+template <typename Kern>
+static int set_smem(Kern k, size_t bytes, const char* name) {
+  if (bytes > 48 * 1024) {
+    cudaError_t e = cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bytes);
+    if (e != cudaSuccess) return fail(name, cudaGetErrorString(e));
+  }
+  return 0;
+}
+
+static bool mlp_supported(const atmonr_mlp_t* m) {
+  return m && m->width == kWidth && m->out_pad == kOutPad && (m->n_hidden == 1 || m->n_hidden == 2) &&
+         (m->in_pad == 32 || m->in_pad == 48) && m->n_in <= m->in_pad && m->n_out <= m->out_pad;
+}
+static bool is_shape(const atmonr_mlp_t* m, int in_pad, int nh) {
+  return mlp_supported(m) && m->in_pad == in_pad && m->n_hidden == nh;
+}
+
+#if ATM_PART_MLP
+template <int IN, int NH>
+static int launch_mlp_fwd(const atmonr_mlp_t* m, const void* w, const float* x, int64_t M, float* out, void* stream) {
+  using Sh = MlpShape<IN, NH>;
+  const size_t smem = Sh::kNumWeights * sizeof(float);
+  if (set_smem(k_mlp_fwd<IN, NH>, smem, "atmonr_mlp_fwd")) return -1;
+  const int grid = grid_for((M + kTile - 1) / kTile, 1, num_sms() * 8);
+  k_mlp_fwd<IN, NH><<<grid, kTile, smem, S(stream)>>>((const __half*)w, x, m->n_in, m->n_out, M, out);
+  ATM_CHECK_LAUNCH("atmonr_mlp_fwd");
+  return 0;
+}
+template <int IN, int NH>
+static int launch_mlp_bwd(const atmonr_mlp_t* m, const void* w, const float* x, const float* dout, int64_t M,
+                          float* dx, float* dw, void* stream) {
+  using Sh = MlpShape<IN, NH>;
+  const size_t smem = (2 * Sh::kNumWeights + BwdScratch<IN>::kFloats) * sizeof(float);
+  if (set_smem(k_mlp_bwd<IN, NH>, smem, "atmonr_mlp_bwd")) return -1;
+  const int grid = grid_for((M + kTile - 1) / kTile, 1, num_sms() * 2);
+  k_mlp_bwd<IN, NH><<<grid, kTile, smem, S(stream)>>>((const __half*)w, x, dout, m->n_in, m->n_out, M, dx, dw);
+  ATM_CHECK_LAUNCH("atmonr_mlp_bwd");
+  return 0;
+}
+
+#endif  // ATM_PART_MLP
+extern "C" {
+
+#if ATM_PART_BASIC
+int atmonr_abi_version(void) { return ATMONR_ABI_VERSION; }
+const char* atmonr_last_error(void) { return g_last_error; }
+
+int atmonr_grid_layout(int n_dims, int n_levels, int log2_hashmap_size, int base_resolution,
+                       float per_level_scale, atmonr_grid_t* out) {
+  ATM_REQUIRE(out, "atmonr_grid_layout", "null output");
+  ATM_REQUIRE(n_dims == 2 || n_dims == 3, "atmonr_grid_layout", "n_dims must be 2 or 3");
+  ATM_REQUIRE(n_levels >= 1 && n_levels <= ATMONR_MAX_LEVELS, "atmonr_grid_layout", "n_levels out of range");
+  ATM_REQUIRE(log2_hashmap_size >= 3 && log2_hashmap_size <= 30, "atmonr_grid_layout", "log2_hashmap_size out of range");
+  memset(out, 0, sizeof(*out));
+  out->n_dims = n_dims;
+  out->n_levels = n_levels;
+  out->n_feat = 2;
+  const uint32_t cap = 1u << log2_hashmap_size;
+  const uint32_t max_params = 0xFFFFFFFFu / 2;
+  uint32_t offset = 0;
+  for (int l = 0; l < n_levels; ++l) {
+    const float scale = grid_level_scale(l, per_level_scale, base_resolution);
+    const uint32_t res = (uint32_t)ceilf(scale) + 1u;
+    uint32_t n;
+    if (powf((float)res, (float)n_dims) > (float)max_params) {
+      n = max_params;
+    } else {
+      n = 1;
+      for (int k = 0; k < n_dims; ++k) n *= res;
+    }
+    n = (n + 7u) / 8u * 8u;
+    if (n > cap) n = cap;
+    out->scale[l] = scale;
+    out->res[l] = res;
+    out->size[l] = n;
+    out->offset[l] = offset;
+    offset += n;
+  }
+  out->offset[n_levels] = offset;
+  return 0;
+}
+
+int atmonr_sample_uniform(const float* origin, const float* dir, const float* len, const float* u,
+                          const float* bins, int64_t B, int N, int mode, uint64_t seed,
+                          uint64_t ray_index_base, float* pts, float* z, void* stream) {
+  ATM_REQUIRE(mode >= 0 && mode <= 2 && (mode != 1 || u), "atmonr_sample_uniform", "bad mode / missing u");
+  if (B * N == 0) return 0;
+  k_sample_uniform<<<grid_for(B * N, 256), 256, 0, S(stream)>>>(origin, dir, len, u, bins, B * N, N, mode, seed,
+                                                               ray_index_base, pts, z);
+  ATM_CHECK_LAUNCH("atmonr_sample_uniform");
+  return 0;
+}
+
+int atmonr_preprocess_horizontal(const atmonr_frame_t* f, const void* pts, void* out, int64_t n, int is_f64,
+                                 void* stream) {
+  ATM_REQUIRE(f && f->enabled, "atmonr_preprocess_horizontal", "frame missing or disabled");
+  if (n == 0) return 0;
+  if (is_f64)
+    k_preprocess_f64<<<grid_for(n, 256), 256, 0, S(stream)>>>(*f, (const double*)pts, (double*)out, n);
+  else
+    k_preprocess_f32<<<grid_for(n, 256), 256, 0, S(stream)>>>(*f, (const float*)pts, (float*)out, n);
+  ATM_CHECK_LAUNCH("atmonr_preprocess_horizontal");
+  return 0;
+}
+
+int atmonr_ngp_sample_points(const atmonr_frame_t* f, const float* origin, const float* dir, const float* len,
+                             const float* u, const float* bins, int64_t B, int N, int mode, uint64_t seed,
+                             uint64_t ray_index_base, float alt_compress, float* x01, float* z, void* stream) {
+  ATM_REQUIRE(f, "atmonr_ngp_sample_points", "null frame");
+  ATM_REQUIRE(mode >= 0 && mode <= 2 && (mode != 1 || u), "atmonr_ngp_sample_points", "bad mode / missing u");
+  if (B * N == 0) return 0;
+  k_ngp_sample_points<<<grid_for(B * N, 256), 256, 0, S(stream)>>>(*f, origin, dir, len, u, bins, B * N, N, mode,
+                                                                  seed, ray_index_base, alt_compress, x01, z);
+  ATM_CHECK_LAUNCH("atmonr_ngp_sample_points");
+  return 0;
+}
+
+#define ATM_GRID_DISPATCH(g, CALL2, CALL3)          \
+  if ((g)->n_dims == 2) { CALL2; } else { CALL3; }
+
+int atmonr_hashgrid_fwd(const atmonr_grid_t* g, const float* x, int xs, const void* table, int64_t M, float* out,
+                        void* stream) {
+  ATM_REQUIRE(g && g->n_feat == 2, "atmonr_hashgrid_fwd", "bad grid");
+  if (M == 0) return 0;
+  const int grid = grid_for(M, 128);
+  ATM_GRID_DISPATCH(g, (k_hashgrid_fwd<2><<<grid, 128, 0, S(stream)>>>(*g, x, xs, (const __half2*)table, M, out)),
+                    (k_hashgrid_fwd<3><<<grid, 128, 0, S(stream)>>>(*g, x, xs, (const __half2*)table, M, out)));
+  ATM_CHECK_LAUNCH("atmonr_hashgrid_fwd");
+  return 0;
+}
+
+int atmonr_hashgrid_bwd(const atmonr_grid_t* g, const float* x, int xs, const float* dout, int64_t M,
+                        float* dtable, void* stream) {
+  ATM_REQUIRE(g && g->n_feat == 2, "atmonr_hashgrid_bwd", "bad grid");
+  if (M == 0) return 0;
+  const int grid = grid_for(M, 128);
+  ATM_GRID_DISPATCH(g, (k_hashgrid_bwd<2><<<grid, 128, 0, S(stream)>>>(*g, x, xs, dout, M, dtable)),
+                    (k_hashgrid_bwd<3><<<grid, 128, 0, S(stream)>>>(*g, x, xs, dout, M, dtable)));
+  ATM_CHECK_LAUNCH("atmonr_hashgrid_bwd");
+  return 0;
+}
+
+int atmonr_hashgrid_indices(const atmonr_grid_t* g, const float* x, int xs, int64_t M, uint32_t* idx,
+                            void* stream) {
+  ATM_REQUIRE(g, "atmonr_hashgrid_indices", "bad grid");
+  if (M == 0) return 0;
+  const int grid = grid_for(M, 128);
+  ATM_GRID_DISPATCH(g, (k_hashgrid_indices<2><<<grid, 128, 0, S(stream)>>>(*g, x, xs, M, idx)),
+                    (k_hashgrid_indices<3><<<grid, 128, 0, S(stream)>>>(*g, x, xs, M, idx)));
+  ATM_CHECK_LAUNCH("atmonr_hashgrid_indices");
+  return 0;
+}
+
+#endif  // ATM_PART_BASIC
+#if ATM_PART_MLP
+int atmonr_mlp_fwd(const atmonr_mlp_t* m, const void* w, const float* x, int64_t M, float* out, void* stream) {
+  ATM_REQUIRE(mlp_supported(m), "atmonr_mlp_fwd", "unsupported MLP shape (width 32, in_pad 32|48, 1|2 hidden layers)");
+  if (M == 0) return 0;
+  if (m->in_pad == 32 && m->n_hidden == 1) return launch_mlp_fwd<32, 1>(m, w, x, M, out, stream);
+  if (m->in_pad == 32 && m->n_hidden == 2) return launch_mlp_fwd<32, 2>(m, w, x, M, out, stream);
+  if (m->in_pad == 48 && m->n_hidden == 1) return launch_mlp_fwd<48, 1>(m, w, x, M, out, stream);
+  return launch_mlp_fwd<48, 2>(m, w, x, M, out, stream);
+}
+
+int atmonr_mlp_bwd(const atmonr_mlp_t* m, const void* w, const float* x, const float* dout, int64_t M, float* dx,
+                   float* dw, void* stream) {
+  ATM_REQUIRE(mlp_supported(m), "atmonr_mlp_bwd", "unsupported MLP shape (width 32, in_pad 32|48, 1|2 hidden layers)");
+  ATM_REQUIRE(dw, "atmonr_mlp_bwd", "null dw");
+  if (M == 0) return 0;
+  if (m->in_pad == 32 && m->n_hidden == 1) return launch_mlp_bwd<32, 1>(m, w, x, dout, M, dx, dw, stream);
+  if (m->in_pad == 32 && m->n_hidden == 2) return launch_mlp_bwd<32, 2>(m, w, x, dout, M, dx, dw, stream);
+  if (m->in_pad == 48 && m->n_hidden == 1) return launch_mlp_bwd<48, 1>(m, w, x, dout, M, dx, dw, stream);
+  return launch_mlp_bwd<48, 2>(m, w, x, dout, M, dx, dw, stream);
+}
+
+#endif  // ATM_PART_MLP
+#if ATM_PART_FIELD
+static int check_field(const atmonr_grid_t* g, const atmonr_mlp_t* pm, const atmonr_mlp_t* dm, const char* name) {
+  ATM_REQUIRE(g && g->n_dims == 3 && g->n_feat == 2 && g->n_levels == 16, name, "field needs a 3-D grid with 16 levels x 2 features");
+  ATM_REQUIRE(is_shape(pm, 32, 1) && pm->n_in == 32 && pm->n_out == 16, name, "pos_mlp must be 32 -> [32] -> 16");
+  ATM_REQUIRE(is_shape(dm, 32, 2) && dm->n_in == 19 && dm->n_out == 4, name, "dir_mlp must be 19 -> [32,32] -> 4");
+  return 0;
+}
+
+int atmonr_ngp_field_fwd(const atmonr_grid_t* g, const void* table, const atmonr_mlp_t* pm, const void* pos_w,
+                         const atmonr_mlp_t* dm, const void* dir_w, const float* x01, const float* dirs, int64_t B,
+                         int N, float* sigma_raw, float* color_raw, void* stream) {
+  if (check_field(g, pm, dm, "atmonr_ngp_field_fwd")) return -1;
+  const int64_t M = B * N;
+  if (M == 0) return 0;
+  const int grid = grid_for((M + kTile - 1) / kTile, 1, num_sms() * 16);
+  k_field_fwd<<<grid, kTile, 0, S(stream)>>>(*g, (const __half2*)table, (const __half*)pos_w, (const __half*)dir_w,
+                                            x01, dirs, M, N, sigma_raw, color_raw);
+  ATM_CHECK_LAUNCH("atmonr_ngp_field_fwd");
+  return 0;
+}
+
+int atmonr_ngp_field_bwd(const atmonr_grid_t* g, const void* table, const atmonr_mlp_t* pm, const void* pos_w,
+                         const atmonr_mlp_t* dm, const void* dir_w, const float* x01, const float* dirs,
+                         const float* dsigma_raw, const float* dcolor_raw, int64_t B, int N, float* dtable,
+                         float* dpos_w, float* ddir_w, void* stream) {
+  if (check_field(g, pm, dm, "atmonr_ngp_field_bwd")) return -1;
+  const int64_t M = B * N;
+  if (M == 0) return 0;
+  const size_t smem = (2 * (PosMlp::kNumWeights + DirMlp::kNumWeights) + BwdScratch<32>::kFloats) * sizeof(float);
+  if (set_smem(k_field_bwd, smem, "atmonr_ngp_field_bwd")) return -1;
+  const int grid = grid_for((M + kTile - 1) / kTile, 1, num_sms() * 3);
+  k_field_bwd<<<grid, kTile, smem, S(stream)>>>(*g, (const __half2*)table, (const __half*)pos_w,
+                                               (const __half*)dir_w, x01, dirs, dsigma_raw, dcolor_raw, M, N,
+                                               dtable, dpos_w, ddir_w);
+  ATM_CHECK_LAUNCH("atmonr_ngp_field_bwd");
+  return 0;
+}
+
+#endif  // ATM_PART_FIELD
+#if ATM_PART_SURF
+static int check_surface(const atmonr_grid_t* g, const atmonr_mlp_t* m, const char* name) {
+  ATM_REQUIRE(g && g->n_dims == 2 && g->n_feat == 2 && g->n_levels == 16, name, "surface needs a 2-D grid with 16 levels x 2 features");
+  ATM_REQUIRE(is_shape(m, 48, 2) && m->n_in == 36 && m->n_out == 4, name, "surf_mlp must be 36 -> [32,32] -> 4");
+  return 0;
+}
+
+int atmonr_ngp_surface_fwd(const atmonr_grid_t* g, const void* table, const atmonr_mlp_t* m, const void* w,
+                           const float* origin, const float* dir, const float* len, int64_t B,
+                           float* color_surf_raw, void* stream) {
+  if (check_surface(g, m, "atmonr_ngp_surface_fwd")) return -1;
+  if (B == 0) return 0;
+  const size_t smem = SurfMlp::kNumWeights * sizeof(float);
+  const int grid = grid_for((B + kTile - 1) / kTile, 1, num_sms() * 8);
+  k_surface_fwd<<<grid, kTile, smem, S(stream)>>>(*g, (const __half2*)table, (const __half*)w, origin, dir, len, B,
+                                                 color_surf_raw);
+  ATM_CHECK_LAUNCH("atmonr_ngp_surface_fwd");
+  return 0;
+}
+
+int atmonr_ngp_surface_bwd(const atmonr_grid_t* g, const void* table, const atmonr_mlp_t* m, const void* w,
+                           const float* origin, const float* dir, const float* len, const float* dcs, int64_t B,
+                           float* dtable, float* dw, void* stream) {
+  if (check_surface(g, m, "atmonr_ngp_surface_bwd")) return -1;
+  if (B == 0) return 0;
+  const size_t smem = (2 * SurfMlp::kNumWeights + BwdScratch<48>::kFloats) * sizeof(float);
+  if (set_smem(k_surface_bwd, smem, "atmonr_ngp_surface_bwd")) return -1;
+  const int grid = grid_for((B + kTile - 1) / kTile, 1, num_sms() * 2);
+  k_surface_bwd<<<grid, kTile, smem, S(stream)>>>(*g, (const __half2*)table, (const __half*)w, origin, dir, len, dcs,
+                                                 B, dtable, dw);
+  ATM_CHECK_LAUNCH("atmonr_ngp_surface_bwd");
+  return 0;
+}
+
+#endif  // ATM_PART_SURF
+#if ATM_PART_BASIC
+#define ATM_KV_DISPATCH(K, V, CALL)                                                       \
+  if (K == 4 && V == 1) { CALL(4, 1); } else if (K == 4 && V == 4) { CALL(4, 4); }          \
+  else if (K == 3 && V == 1) { CALL(3, 1); } else if (K == 3 && V == 3) { CALL(3, 3); }     \
+  else if (K == 2 && V == 1) { CALL(2, 1); } else if (K == 2 && V == 2) { CALL(2, 2); }     \
+  else if (K == 1 && V == 1) { CALL(1, 1); } else { return fail("atmonr_composite", "unsupported (K, V); need K<=4 and V in {1, K}"); }
+
+int atmonr_composite_fwd(const float* z, const float* color, const float* sigma, const float* color_surf,
+                         float z_scale, int64_t B, int N, int K, int V, int relu, float* color_map,
+                         float* color_map_atmo, float* color_map_surf, float* trans_surf, float* weights,
+                         float* alpha, void* stream) {
+  ATM_REQUIRE(color_map, "atmonr_composite_fwd", "null color_map");
+  if (B == 0) return 0;
+  const int grid = grid_for(B * 32, 128);
+#define CALL(KK, VV)                                                                                      \
+  k_composite_fwd<KK, VV><<<grid, 128, 0, S(stream)>>>(z, color, sigma, color_surf, z_scale, B, N, relu,   \
+                                                      color_map, color_map_atmo, color_map_surf, trans_surf, \
+                                                      weights, alpha)
+  ATM_KV_DISPATCH(K, V, CALL)
+#undef CALL
+  ATM_CHECK_LAUNCH("atmonr_composite_fwd");
+  return 0;
+}
+
+int atmonr_composite_bwd(const float* z, const float* color, const float* sigma, const float* color_surf,
+                         const float* color_map_atmo, const float* trans_surf, const float* d_atmo,
+                         const float* d_surf, float z_scale, int64_t B, int N, int K, int V, int relu,
+                         float* dcolor, float* dsigma, float* dcolor_surf, float* ddelta, void* stream) {
+  ATM_REQUIRE(color_map_atmo && d_atmo && dcolor && dsigma, "atmonr_composite_bwd", "null argument");
+  ATM_REQUIRE(!color_surf || trans_surf, "atmonr_composite_bwd", "trans_surf required with a surface");
+  if (B == 0) return 0;
+  const int grid = grid_for(B * 32, 128);
+#define CALL(KK, VV)                                                                                         \
+  k_composite_bwd<KK, VV><<<grid, 128, 0, S(stream)>>>(z, color, sigma, color_surf, color_map_atmo, trans_surf, \
+                                                      d_atmo, d_surf, z_scale, B, N, relu, dcolor, dsigma,    \
+                                                      dcolor_surf, ddelta)
+  ATM_KV_DISPATCH(K, V, CALL)
+#undef CALL
+  ATM_CHECK_LAUNCH("atmonr_composite_bwd");
+  return 0;
+}
+
+int atmonr_band_loss(const float* color_map, const int64_t* band, const float* rad, float max_i, int kind,
+                     int64_t B, int K, float grad_scale, float* loss, float* dcolor_map, float* partial,
+                     void* stream) {
+  ATM_REQUIRE(kind >= 0 && kind <= 5, "atmonr_band_loss", "unknown loss kind");
+  ATM_REQUIRE(B > 0 && loss && partial, "atmonr_band_loss", "empty batch or null argument");
+  const int grid = grid_for(B, 256, 1024);
+  k_band_loss<<<grid, 256, 0, S(stream)>>>(color_map, band, rad, max_i, kind, B, K, grad_scale, dcolor_map, partial);
+  ATM_CHECK_LAUNCH("atmonr_band_loss");
+  k_loss_finish<<<1, 32, 0, S(stream)>>>(partial, grid, B, loss);
+  ATM_CHECK_LAUNCH("atmonr_band_loss");
+  return 0;
+}
+
+int atmonr_adamw_step(float* param, float* grad, float* exp_avg, float* exp_avg_sq, void* param_f16, int64_t n,
+                      double lr, double beta1, double beta2, double eps, double weight_decay, int64_t step,
+                      double grad_scale, int zero_grad, void* stream) {
+  ATM_REQUIRE(step >= 1, "atmonr_adamw_step", "step must be >= 1");
+  if (n == 0) return 0;
+  // torch/optim/adam.py _single_tensor_adam: the hyper-parameters are python floats (doubles)
+  // combined in double precision and only then cast to the parameter dtype.
+  AdamConsts c;
+  c.decay_mul = (float)(1.0 - lr * weight_decay);
+  c.w1 = (float)(1.0 - beta1);
+  c.beta2 = (float)beta2;
+  c.w2 = (float)(1.0 - beta2);
+  c.bc2_sqrt = (float)sqrt(1.0 - pow(beta2, (double)step));
+  c.neg_step_size = (float)(-(lr / (1.0 - pow(beta1, (double)step))));
+  c.eps = (float)eps;
+  c.gscale = (float)grad_scale;
+  const int grid = grid_for((n + 3) / 4, 256, num_sms() * 16);
+  k_adamw<<<grid, 256, 0, S(stream)>>>(param, grad, exp_avg, exp_avg_sq, (__half*)param_f16, n, c, zero_grad);
+  ATM_CHECK_LAUNCH("atmonr_adamw_step");
+  return 0;
+}
+
+int atmonr_extract_sigma(const atmonr_frame_t* f, const atmonr_grid_t* g, const void* table,
+                         const atmonr_mlp_t* pm, const void* pos_w, const double* pts, int64_t n,
+                         float alt_compress, float* sigma, void* stream) {
+  ATM_REQUIRE(f && g && g->n_dims == 3 && g->n_levels == 16, "atmonr_extract_sigma", "bad frame/grid");
+  ATM_REQUIRE(is_shape(pm, 32, 1) && pm->n_in == 32, "atmonr_extract_sigma", "pos_mlp must be 32 -> [32] -> 16");
+  if (n == 0) return 0;
+  const int grid = grid_for((n + kTile - 1) / kTile, 1, num_sms() * 16);
+  k_extract_sigma<<<grid, kTile, 0, S(stream)>>>(*f, *g, (const __half2*)table, (const __half*)pos_w, pts, n,
+                                                alt_compress, sigma);
+  ATM_CHECK_LAUNCH("atmonr_extract_sigma");
+  return 0;
+}
+
+int atmonr_positional_encoding(const float* pts, int64_t M, int C, const int32_t* freqs, int interleaved,
+                               float* out, void* stream) {
+  ATM_REQUIRE(C >= 1 && C <= 4 && freqs, "atmonr_positional_encoding", "C must be 1..4");
+  PeCfg cfg;
+  int col = 0;
+  for (int a = 0; a < 4; ++a) {
+    cfg.freqs[a] = a < C ? freqs[a] : 0;
+    cfg.col0[a] = col;
+    col += 2 * cfg.freqs[a];
+  }
+  cfg.C = C;
+  cfg.width = col;
+  cfg.interleaved = interleaved;
+  if (M == 0) return 0;
+  k_positional_encoding<<<grid_for(M, 256), 256, 0, S(stream)>>>(pts, M, cfg, out);
+  ATM_CHECK_LAUNCH("atmonr_positional_encoding");
+  return 0;
+}
+
+int atmonr_sample_pdf(const float* weights, const float* z_coarse, const float* u, int64_t B, int Nc, int Nf,
+                      float* z_sorted, int64_t* inds, void* stream) {
+  ATM_REQUIRE(Nc >= 3 && Nf >= 1, "atmonr_sample_pdf", "need Nc >= 3 and Nf >= 1");
+  if (B == 0) return 0;
+  int P = 1;
+  while (P < Nc + Nf) P <<= 1;
+  const size_t smem = (2 * (size_t)(Nc - 1) + P) * sizeof(float);
+  ATM_REQUIRE(smem <= 48 * 1024, "atmonr_sample_pdf", "Nc + Nf too large");
+  k_sample_pdf<<<(unsigned)B, 32, smem, S(stream)>>>(weights, z_coarse, u, B, Nc, Nf, P, z_sorted, inds);
+  ATM_CHECK_LAUNCH("atmonr_sample_pdf");
+  return 0;
+}
+
+#endif  // ATM_PART_BASIC
+}  // extern "C"

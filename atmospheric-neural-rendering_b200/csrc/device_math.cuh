@@ -1,0 +1,217 @@
+// device_math.cuh -- per-sample arithmetic shared by every kernel of libatmonr_b200.
+//
+// Everything here is __host__ __device__ and free of CUDA-only intrinsics, so the same code
+// is compiled by g++ into a host self-check library (csrc/hostcheck.cpp; used by the CPU test
+// suite to verify index/geodesy logic without a GPU). The library is built with
+// -fmad=false (nvcc) / -ffp-contract=off (g++): every a*b+c below is two rounded operations
+// exactly like the eager torch ops of the reference; fused multiply-adds are explicit.
+#pragma once
+
+#include <math.h>
+#include <stdint.h>
+
+#include "../../include/atmonr_b200.h"
+
+#if defined(__CUDACC__)
+#define ATM_HD __host__ __device__ __forceinline__
+#else
+#define ATM_HD inline
+#endif
+
+namespace atm {
+
+// ---------------------------------------------------------------------------------------
+// Philox4x32-10 counter-based generator: one (seed, ray, bin) -> one uniform in [0,1).
+// Partition-invariant: the draw of a sample depends only on its global ray index and bin.
+// ---------------------------------------------------------------------------------------
+ATM_HD void philox_round(uint32_t (&c)[4], uint32_t k0, uint32_t k1) {
+  const uint64_t p0 = (uint64_t)0xD2511F53u * c[0];
+  const uint64_t p1 = (uint64_t)0xCD9E8D57u * c[2];
+  const uint32_t n0 = (uint32_t)(p1 >> 32) ^ c[1] ^ k0;
+  const uint32_t n2 = (uint32_t)(p0 >> 32) ^ c[3] ^ k1;
+  c[1] = (uint32_t)p1;
+  c[3] = (uint32_t)p0;
+  c[0] = n0;
+  c[2] = n2;
+}
+
+ATM_HD float philox_uniform(uint64_t seed, uint64_t ray, uint32_t bin) {
+  uint32_t c[4] = {(uint32_t)ray, (uint32_t)(ray >> 32), bin, 0x5eedu};
+  uint32_t k0 = (uint32_t)seed, k1 = (uint32_t)(seed >> 32);
+#if defined(__CUDA_ARCH__)
+#pragma unroll
+#endif
+  for (int r = 0; r < 10; ++r) {
+    philox_round(c, k0, k1);
+    k0 += 0x9E3779B9u;
+    k1 += 0xBB67AE85u;
+  }
+  return (float)(c[0] >> 8) * (1.0f / 16777216.0f);  // 24 bits -> [0,1)
+}
+
+// ---------------------------------------------------------------------------------------
+// samplers.py:34-45: stratified distance and the point on the ray.
+// ---------------------------------------------------------------------------------------
+ATM_HD float stratified_z(float bin_lo, float t, int n_bins, float len) {
+  return (bin_lo + t / (float)n_bins) * len;
+}
+
+// ---------------------------------------------------------------------------------------
+// wgs_84.py:56-97 cartesian_to_horizontal: one Bowring iteration, float64.
+// ---------------------------------------------------------------------------------------
+#define ATM_WGS_A 6378137.0
+#define ATM_WGS_B 6356752.314245
+
+ATM_HD void ecef_to_geodetic(double x, double y, double z, double& lat_deg, double& lon_deg,
+                             double& alt) {
+  const double A = ATM_WGS_A, B = ATM_WGS_B;
+  const double E_SQ = (A * A - B * B) / (A * A);
+  const double EP_SQ = (A * A - B * B) / (B * B);
+  const double PI = 3.141592653589793;
+  const double lam = atan2(y, x);
+  const double d = sqrt(x * x + y * y);
+  const double u = atan2(z / d, 0.0 + A / B);
+  const double su = sin(u), cu = cos(u);
+  const double phi = atan2(z + (EP_SQ * B) * ((su * su) * su), d - (E_SQ * A) * ((cu * cu) * cu));
+  const double sp = sin(phi);
+  const double n = A / sqrt(1.0 - (E_SQ * (sp * sp)));
+  alt = x / (cos(phi) * cos(lam)) - n;
+  lat_deg = phi * 180.0 / PI;
+  lon_deg = lam * 180.0 / PI;
+}
+
+ATM_HD double py_mod(double a, double m) {  // torch remainder: sign follows the divisor
+  double r = fmod(a, m);
+  if (r != 0.0 && ((r < 0.0) != (m < 0.0))) r += m;
+  return r;
+}
+
+// harp2.py:372-386 preprocess_coords after `coords * scale + offset`; returns UNCLIPPED
+// float64 normalised (lat, lon, alt).
+ATM_HD void horizontal_normalise(const atmonr_frame_t& f, double x, double y, double z, double& o0,
+                                 double& o1, double& o2) {
+  double lat, lon, alt;
+  ecef_to_geodetic(x, y, z, lat, lon, alt);
+  if (f.shift_lon) lon = py_mod(lon, 360.0) - 180.0;
+  o0 = 2.0 * (lat - f.lat_min) / f.lat_range - 1.0;
+  o1 = 2.0 * (lon - f.lon_min) / f.lon_range - 1.0;
+  o2 = 2.0 * alt / f.origin_height - 1.0;
+}
+
+ATM_HD float clip1(float v) { return v < -1.0f ? -1.0f : (v > 1.0f ? 1.0f : v); }
+ATM_HD double clip1(double v) { return v < -1.0 ? -1.0 : (v > 1.0 ? 1.0 : v); }
+
+// float32 flavour (training): the multiply by `scale` is a float32 op (tensor * python
+// float keeps float32), the offset add promotes to float64, the result is cast back to
+// float32 and clipped.
+ATM_HD void preprocess_f32(const atmonr_frame_t& f, float px, float py, float pz, float& o0,
+                           float& o1, float& o2) {
+  const float s = (float)f.scale;
+  const double x = (double)(px * s) + f.offset[0];
+  const double y = (double)(py * s) + f.offset[1];
+  const double z = (double)(pz * s) + f.offset[2];
+  double a, b, c;
+  horizontal_normalise(f, x, y, z, a, b, c);
+  o0 = clip1((float)a);
+  o1 = clip1((float)b);
+  o2 = clip1((float)c);
+}
+
+// float64 flavour (extract path, scripts/extract.py:205 feeds float64 points).
+ATM_HD void preprocess_f64(const atmonr_frame_t& f, double px, double py, double pz, double& o0,
+                           double& o1, double& o2) {
+  double a, b, c;
+  horizontal_normalise(f, px * f.scale + f.offset[0], py * f.scale + f.offset[1],
+                       pz * f.scale + f.offset[2], a, b, c);
+  o0 = clip1(a);
+  o1 = clip1(b);
+  o2 = clip1(c);
+}
+
+// instant_ngp.py:149,160: [-1,1] -> [0,1], altitude divided by alt_compress_factor.
+ATM_HD void to_unit_cube(float c0, float c1, float c2, float alt_compress, float& x0, float& x1,
+                         float& x2) {
+  x0 = (c0 + 1.0f) / 2.0f;
+  x1 = (c1 + 1.0f) / 2.0f;
+  x2 = ((c2 + 1.0f) / 2.0f) / alt_compress;
+}
+
+// ---------------------------------------------------------------------------------------
+// Multiresolution hash grid indexing (tiny-cuda-nn grid.h, upstream-recalled).
+// ---------------------------------------------------------------------------------------
+// tcnn evaluates exp2f(level * log2f(per_level_scale)) * base - 1 in float32 (and its host and
+// device libm disagree in the last bits). Here the expression is evaluated in float64 and rounded
+// ONCE to float32, so that independent implementations (this library, the oracle) agree bit for
+// bit; the result is within a few float32 ulps of tcnn's.
+inline float grid_level_scale(int level, float per_level_scale, int base_resolution) {
+  return (float)(exp2((double)level * log2((double)per_level_scale)) * (double)base_resolution - 1.0);
+}
+
+template <int D>
+ATM_HD uint32_t grid_entry(const uint32_t (&g)[D], uint32_t res, uint32_t size) {
+  uint32_t stride = 1, index = 0;
+#if defined(__CUDA_ARCH__)
+#pragma unroll
+#endif
+  for (int k = 0; k < D; ++k) {
+    if (stride <= size) {
+      index += g[k] * stride;
+      stride *= res;
+    }
+  }
+  if (size < stride) {
+    const uint32_t primes[4] = {1u, 2654435761u, 805459861u, 3674653429u};
+    index = 0;
+#if defined(__CUDA_ARCH__)
+#pragma unroll
+#endif
+    for (int k = 0; k < D; ++k) index ^= g[k] * primes[k];
+  }
+  return index % size;
+}
+
+// Cell and fractional position of x in [0,1]^D at one level: pos = fmaf(scale, x, 0.5).
+template <int D>
+ATM_HD void grid_cell(const float* x, float scale, uint32_t (&cell)[D], float (&frac)[D]) {
+#if defined(__CUDA_ARCH__)
+#pragma unroll
+#endif
+  for (int k = 0; k < D; ++k) {
+    const float pos = fmaf(scale, x[k], 0.5f);
+    const float fl = floorf(pos);
+    cell[k] = (uint32_t)(int)fl;
+    frac[k] = pos - fl;
+  }
+}
+
+// Entry index (within the level) and trilinear weight of corner `c` (bit k set -> +1 in dim k).
+template <int D>
+ATM_HD void grid_corner(const uint32_t (&cell)[D], const float (&frac)[D], int c, uint32_t res,
+                        uint32_t size, uint32_t& entry, float& w) {
+  uint32_t g[D];
+  w = 1.0f;
+#if defined(__CUDA_ARCH__)
+#pragma unroll
+#endif
+  for (int k = 0; k < D; ++k) {
+    if (c & (1 << k)) {
+      g[k] = cell[k] + 1u;
+      w *= frac[k];
+    } else {
+      g[k] = cell[k];
+      w *= 1.0f - frac[k];
+    }
+  }
+  entry = grid_entry<D>(g, res, size);
+}
+
+// tcnn SphericalHarmonics degree 2 on v = 2*d - 1 (4 outputs), upstream-recalled.
+ATM_HD void sh_degree2(float dx, float dy, float dz, float (&out)[4]) {
+  const float vx = dx * 2.0f - 1.0f, vy = dy * 2.0f - 1.0f, vz = dz * 2.0f - 1.0f;
+  out[0] = 0.28209479177387814f;
+  out[1] = -0.48860251190291987f * vy;
+  out[2] = 0.48860251190291987f * vz;
+  out[3] = -0.48860251190291987f * vx;
+}
+
+}  // namespace atm

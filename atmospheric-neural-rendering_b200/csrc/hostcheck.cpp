@@ -1,0 +1,69 @@
+// hostcheck.cpp -- host build of the per-sample arithmetic in device_math.cuh.
+//
+// NOT a CPU fallback: nothing in the product imports this library. The CPU test-suite uses
+// it to check, without a GPU, that the exact code the kernels execute (indexing, geodesy,
+// Philox, stratified sampling) agrees with the oracle bit for bit / within tolerance.
+#include "device_math.cuh"
+
+template <int D>
+static void indices_impl(const atmonr_grid_t* g, const float* x, int xs, int64_t M, uint32_t* idx, float* w) {
+  for (int64_t i = 0; i < M; ++i) {
+    float p[D];
+    for (int k = 0; k < D; ++k) p[k] = x[i * xs + k];
+    for (int l = 0; l < g->n_levels; ++l) {
+      uint32_t cell[D];
+      float frac[D];
+      atm::grid_cell<D>(p, g->scale[l], cell, frac);
+      for (int c = 0; c < (1 << D); ++c) {
+        uint32_t e;
+        float wc;
+        atm::grid_corner<D>(cell, frac, c, g->res[l], g->size[l], e, wc);
+        const int64_t at = (i * g->n_levels + l) * (1 << D) + c;
+        idx[at] = g->offset[l] + e;
+        if (w) w[at] = wc;
+      }
+    }
+  }
+}
+
+extern "C" {
+
+void hc_preprocess_f32(const atmonr_frame_t* f, const float* p, float* out, int64_t n) {
+  for (int64_t i = 0; i < n; ++i)
+    atm::preprocess_f32(*f, p[3 * i], p[3 * i + 1], p[3 * i + 2], out[3 * i], out[3 * i + 1], out[3 * i + 2]);
+}
+
+void hc_preprocess_f64(const atmonr_frame_t* f, const double* p, double* out, int64_t n) {
+  for (int64_t i = 0; i < n; ++i)
+    atm::preprocess_f64(*f, p[3 * i], p[3 * i + 1], p[3 * i + 2], out[3 * i], out[3 * i + 1], out[3 * i + 2]);
+}
+
+void hc_ngp_sample_points(const atmonr_frame_t* f, const float* o, const float* d, const float* len,
+                          const float* u, const float* bins, int64_t B, int N, int mode, uint64_t seed,
+                          uint64_t base, float alt_compress, float* x01, float* z) {
+  for (int64_t ray = 0; ray < B; ++ray)
+    for (int i = 0; i < N; ++i) {
+      const int64_t idx = ray * N + i;
+      const float t = mode == 0 ? 0.5f : (mode == 1 ? u[idx] : atm::philox_uniform(seed, base + ray, (uint32_t)i));
+      const float lo = bins ? bins[i] : (float)i / (float)N;
+      const float zz = atm::stratified_z(lo, t, N, len[ray]);
+      z[idx] = zz;
+      float p[3];
+      for (int k = 0; k < 3; ++k) p[k] = o[ray * 3 + k] + d[ray * 3 + k] * zz;
+      float c0 = p[0], c1 = p[1], c2 = p[2];
+      if (f->enabled) atm::preprocess_f32(*f, p[0], p[1], p[2], c0, c1, c2);
+      atm::to_unit_cube(c0, c1, c2, alt_compress, x01[idx * 3], x01[idx * 3 + 1], x01[idx * 3 + 2]);
+    }
+}
+
+void hc_hashgrid_indices(const atmonr_grid_t* g, const float* x, int xs, int64_t M, uint32_t* idx, float* w) {
+  if (g->n_dims == 2) indices_impl<2>(g, x, xs, M, idx, w);
+  else indices_impl<3>(g, x, xs, M, idx, w);
+}
+
+void hc_philox(uint64_t seed, uint64_t ray0, int64_t B, int N, float* out) {
+  for (int64_t r = 0; r < B; ++r)
+    for (int i = 0; i < N; ++i) out[r * N + i] = atm::philox_uniform(seed, ray0 + r, (uint32_t)i);
+}
+
+}  // extern "C"

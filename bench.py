@@ -1,0 +1,303 @@
+"""bench.py -- training throughput of the Instant-NGP hot path (BASELINE.json configs[1]):
+
+    rays/s of forward + loss + backward + AdamW, 2^18-ray batches x 1024 samples per ray,
+    synthetic HARP2-shaped granule (4 bands, 10/10/60/10 views), random-init weights.
+
+    python bench.py --gpus N --steps K --warmup W            (N>1: launched with torchrun)
+    python bench.py --impl reference ...                     (CPU arm: the oracle port)
+
+Prints ONE JSON line (rank 0). `value` = device-resident inputs; `e2e` = the same step through
+the pipeline API with pinned-host batches (H2D of the batch + D2H of the loss inside the timed
+region). Scaling is weak: every rank processes `--rays` rays per step.
+"""
+
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+PKG = os.path.join(ROOT, "atmospheric-neural-rendering_b200")
+for p in (ROOT, PKG, os.path.join(ROOT, "tests")):
+    if p not in sys.path:
+        sys.path.insert(0, p)
+
+import torch  # noqa: E402
+
+METRIC = "training rays/sec (fwd+bwd+Adam), Instant-NGP"
+UNIT = "rays/s"
+OPT_CFG = {"lr": 1e-2, "betas": [0.9, 0.99], "eps": 1e-15, "weight_decay": 1e-2}
+N_PARAMS = 47812560
+
+
+def parse():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=5)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="native", choices=["native", "reference"])
+    ap.add_argument("--rays", type=int, default=1 << 18, help="rays per step per GPU")
+    ap.add_argument("--samples", type=int, default=1024)
+    ap.add_argument("--granule", default="synthetic:H=256,W=256,seed=0")
+    ap.add_argument("--cpu-rays", type=int, default=256, help="rays per step of the CPU baseline sample")
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    return ap.parse_args()
+
+
+def pipeline_config(samples: int) -> dict:
+    cfg = json.load(open(os.path.join(ROOT, "configs", "instant_ngp.json")))
+    cfg["pipeline"]["num_samples_per_ray"] = samples
+    return cfg
+
+
+# ------------------------------------------------------------------------------------------
+# clocks
+# ------------------------------------------------------------------------------------------
+class ClockSampler:
+    """nvidia-smi clocks and throttle reasons sampled DURING the timed region."""
+
+    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,"
+         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
+         "clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, gpu_index: int):
+        self.gpu, self.rows, self.proc = gpu_index, [], None
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(
+                ["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-lms", "100", "-i", str(self.gpu)],
+                stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            threading.Thread(target=self._read, daemon=True).start()
+        except OSError:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.rows.append([c.strip() for c in line.split(",")])
+
+    def stop(self) -> dict:
+        if self.proc is None:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        time.sleep(0.15)
+        self.proc.terminate()
+        sm, mx, reasons = [], [], set()
+        for r in self.rows:
+            try:
+                sm.append(float(r[1])); mx.append(float(r[2]))
+            except (ValueError, IndexError):
+                continue
+            for name, col in (("hw_slowdown", 4), ("hw_thermal_slowdown", 5), ("sw_thermal_slowdown", 6), ("sw_power_cap", 7)):
+                if len(r) > col and r[col].lower().startswith("active"):
+                    reasons.add(name)
+        sm.sort()
+        return {"sm_mhz": sm[len(sm) // 2] if sm else None, "sm_max_mhz": max(mx) if mx else None,
+                "reasons": sorted(reasons), "samples": len(sm)}
+
+
+# ------------------------------------------------------------------------------------------
+# CPU arm: the oracle port of the same step
+# ------------------------------------------------------------------------------------------
+def cpu_step_rate(samples: int, rays: int, steps: int, warmup: int) -> dict:
+    """Time the oracle's Instant-NGP training step (torch CPU, all host threads) on a bounded
+    sample: `rays` rays x `samples` samples per step."""
+    from helpers import random_params, take, tiny_scene
+    from oracle.ngp import NGPOracle
+
+    torch.set_num_threads(os.cpu_count() or 1)
+    scene = tiny_scene(h=16, w=16, n_views=9)
+    cfg = pipeline_config(samples)["pipeline"]
+    orc = NGPOracle(cfg, scene.frame, scene.max_i, fp16=False)
+    params = random_params(orc, seed=0)
+    opt = orc.make_optimizer(params, OPT_CFG)
+    g = torch.Generator().manual_seed(0)
+    n = scene.batch["origin"].shape[0]
+    times = []
+    for it in range(warmup + steps):
+        sel = torch.randint(0, n, (rays,), generator=g)
+        batch = take(scene.batch, sel)
+        u = torch.rand(rays, samples, generator=g)
+        t0 = time.perf_counter()
+        orc.train_step(batch, params, opt, u)
+        if it >= warmup:
+            times.append(time.perf_counter() - t0)
+    sec = sum(times) / len(times)
+    return {"value": rays / sec, "unit": UNIT, "cores": torch.get_num_threads(), "kind": "port",
+            "sample": f"{steps} steps x {rays} rays x {samples} samples/ray, oracle/ngp.py (torch CPU fp32), "
+                      f"{sec:.2f} s/step; the reference's own NGP path cannot run (tiny-cuda-nn absent)",
+            "ms_per_step": sec * 1e3}
+
+
+def run_reference(args) -> None:
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    steps, warm = max(1, min(args.steps, 3)), max(0, min(args.warmup, 1))
+    cb = cpu_step_rate(args.samples, args.cpu_rays, steps, warm)
+    line = {
+        "metric": METRIC, "value": cb["value"], "unit": UNIT, "n_gpus": args.gpus, "steps": steps, "warmup": warm,
+        "ms_per_step": cb["ms_per_step"], "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+        "dtype": "f32", "data": "synthetic", "impl": "reference",
+        "config": {"workload": f"Instant-NGP train step, bounded CPU sample of configs[1]: {args.cpu_rays} rays x "
+                               f"{args.samples} samples/ray per step", "l2": "n/a (CPU)"},
+        "cpu_baseline": {k: cb[k] for k in ("value", "unit", "cores", "kind", "sample")},
+        "e2e": {"value": cb["value"], "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "gpu_launches": 0,
+    }
+    print(json.dumps(line))
+
+
+# ------------------------------------------------------------------------------------------
+# native arm
+# ------------------------------------------------------------------------------------------
+def run_native(args) -> None:
+    from atmonr import distributed as dist
+    from atmonr.batch_loader import BatchLoader
+    from atmonr.datasets.factory import get_dataset
+    from atmonr.native import lib as L
+    from atmonr.pipelines.factory import get_pipeline
+
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py (native arm) needs a CUDA device; there is no CPU fallback")
+    rank, world, local = dist.init_from_env("nccl")
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    L.load()
+
+    cfg = pipeline_config(args.samples)
+    torch.manual_seed(0)
+    dataset = get_dataset(cfg["dataset"], args.granule)
+    pipe = get_pipeline(cfg["pipeline"], dataset)
+    pipe.send_tensors_to(local)
+    dist.broadcast_parameters(p for name in pipe.module_names for p in getattr(pipe, name).parameters())
+    opt = pipe.get_optimizer(OPT_CFG)
+    B, K, W = args.rays, args.steps, args.warmup
+
+    # fixed set of batches, each rank its own rays (weak scaling)
+    loader = BatchLoader(dataset, batch_size=B, shuffle=True, seed=1234 + rank)
+    keys = ("origin", "dir", "len", "rad", "irgb_idx")
+    batches = []
+    for b in loader:
+        if b["origin"].shape[0] == B:
+            batches.append({k: b[k].contiguous() for k in keys})
+        if len(batches) >= 4:
+            break
+    assert batches, "granule too small for the requested batch size"
+    host = [{k: v.cpu().pin_memory() for k, v in b.items()} for b in batches]
+    h2d_bytes = sum(v.numel() * v.element_size() for v in host[0].values())
+
+    def step(batch):
+        res = pipe.forward(batch)
+        loss = pipe.compute_loss(batch, res)
+        opt.zero_grad()
+        loss.backward()
+        dist.all_reduce_gradients(opt)
+        opt.step()
+        return loss
+
+    def barrier():
+        torch.cuda.synchronize()
+        if world > 1:
+            torch.distributed.barrier()
+        torch.cuda.synchronize()
+
+    def timed(n_steps, fn):
+        barrier()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for i in range(n_steps):
+            fn(i)
+        e1.record()
+        barrier()
+        ms = torch.tensor([e0.elapsed_time(e1)], device=dev)
+        if world > 1:
+            torch.distributed.all_reduce(ms, op=torch.distributed.ReduceOp.MAX)
+        return float(ms.item())
+
+    # ---- warm-up, then the device-resident measurement (inputs cycle through > L2 of data) ----
+    for i in range(W):
+        step(batches[i % len(batches)])
+    clocks = ClockSampler(local)
+    if rank == 0:
+        clocks.start()
+    L.STATS = L.CallStats(timed=False)
+    ms_total = timed(K, lambda i: step(batches[i % len(batches)]))
+    launches = L.STATS.launches
+    L.STATS = None
+    clock_info = clocks.stop() if rank == 0 else {}
+    ms_step = ms_total / K
+    value = world * B * 1e3 / ms_step
+
+    # ---- per-kernel durations (CUDA events around every C-ABI call, separate pass) ----
+    L.STATS = L.CallStats(timed=True)
+    for i in range(min(K, 3)):
+        step(batches[i % len(batches)])
+    dur = L.STATS.durations_ms()
+    calls = dict(L.STATS.calls)
+    L.STATS = None
+    per_step = {k: sum(v) / min(K, 3) for k, v in dur.items()}
+    top = max(per_step, key=per_step.get)
+    M = B * args.samples
+    alg_bytes = {  # 512 B gathered / 512 B scattered per sample; AdamW 28 B + 2 B shadow per param
+        "atmonr_ngp_field_fwd": 512 * M, "atmonr_ngp_field_bwd": 1024 * M,
+        "atmonr_adamw_step": 30 * N_PARAMS, "atmonr_ngp_sample_points": 16 * M + 28 * B,
+        "atmonr_composite_fwd": 24 * M, "atmonr_composite_bwd": 44 * M,
+    }
+    peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json"))) if os.path.exists(os.path.join(ROOT, "MEASURED_PEAKS.json")) else {}
+    hbm_peak = float(peaks.get("hbm_gbs", 6650.0))
+    n_top = max(1, calls.get(top, 1) // min(K, 3))
+    achieved = alg_bytes.get(top, 0) / (per_step[top] / n_top * 1e-3) / 1e9 if top in alg_bytes else None
+    roofline = {
+        "kernel": top, "bound": "hbm", "achieved": achieved, "peak": hbm_peak, "unit": "GB/s",
+        "frac": (achieved / hbm_peak) if achieved else None, "traffic": None,
+        "peak_source": "MEASURED_PEAKS.json hbm_gbs" if peaks else "fallback 6650 GB/s (B200_PROFILING.md)",
+        "note": "algorithmic bytes = table gathers (+ gradient scatters) per SURVEY 8d; the fp16 table is "
+                "L2-resident, so this is table traffic served by L2, quoted against the HBM copy peak",
+        "ms_per_step_by_kernel": {k: round(v, 3) for k, v in sorted(per_step.items(), key=lambda kv: -kv[1])},
+    }
+
+    # ---- end to end through the pipeline API with host buffers ----
+    def e2e_step(i):
+        hb = host[i % len(host)]
+        batch = {k: v.to(dev, non_blocking=True) for k, v in hb.items()}
+        return step(batch).item()
+
+    e2e_step(0)
+    ms_e2e = timed(K, e2e_step) / K
+    e2e = {"value": world * B * 1e3 / ms_e2e, "unit": UNIT, "h2d_bytes_per_step": h2d_bytes, "d2h_bytes_per_step": 4,
+           "ms_per_step": ms_e2e}
+
+    if rank != 0:
+        return
+    cpu = None if args.no_cpu_baseline else cpu_step_rate(args.samples, args.cpu_rays, 2, 1)
+    line = {
+        "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": K, "warmup": W,
+        "ms_per_step": ms_step, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+        "dtype": "f16 table/MLP operands, f32 accumulate, f64 geodesy", "data": "synthetic",
+        "config": {
+            "workload": f"Instant-NGP (configs/instant_ngp.json) train step, {B} rays/GPU x {args.samples} samples/ray, "
+                        f"{args.granule} HARP2-shaped granule, 4 bands 10/10/60/10 views",
+            "rays_per_gpu": B, "samples_per_ray": args.samples, "parallelism": f"dp{world}",
+            "l2": "inputs larger than L2: per-step working set (x01, sigma, colour, gradients) is several GB",
+        },
+        "clocks": clock_info, "e2e": e2e, "gpu_launches": launches, "roofline": roofline,
+        "cpu_baseline": {k: cpu[k] for k in ("value", "unit", "cores", "kind", "sample")} if cpu else None,
+    }
+    print(json.dumps(line))
+
+
+def main():
+    args = parse()
+    if args.impl == "reference":
+        run_reference(args)
+    else:
+        run_native(args)
+
+
+if __name__ == "__main__":
+    main()

@@ -1,0 +1,196 @@
+/*
+ * atmonr_b200.h -- C ABI of libatmonr_b200.so, the sm_100a implementation of the AtmoNR
+ * training / extraction hot path (nasa/atmospheric-neural-rendering).
+ *
+ * Conventions
+ *   - every pointer is a DEVICE pointer owned by the caller unless the name ends in _host;
+ *   - every call is asynchronous on `stream` (a cudaStream_t passed as void*);
+ *   - return value: 0 = ok, negative = error; atmonr_last_error() gives the message
+ *     (thread-local);
+ *   - no allocation happens inside the library, no torch types cross this boundary;
+ *   - the reference has no native interface: each entry point names the Python function or
+ *     third-party (tiny-cuda-nn) module of the reference it replaces (file:line relative to
+ *     the reference tree).
+ */
+#ifndef ATMONR_B200_H
+#define ATMONR_B200_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define ATMONR_MAX_LEVELS 16
+#define ATMONR_ABI_VERSION 1
+
+/* Level table of a multiresolution hash grid (tiny-cuda-nn GridEncoding, used at
+ * src/atmonr/pipelines/instant_ngp.py:60-63 and :78-80). Filled by atmonr_grid_layout. */
+typedef struct {
+  int32_t n_dims;    /* 2 or 3 */
+  int32_t n_levels;  /* <= ATMONR_MAX_LEVELS */
+  int32_t n_feat;    /* features per entry; only 2 is supported */
+  int32_t reserved;
+  float scale[ATMONR_MAX_LEVELS];     /* exp2f(l*log2f(per_level_scale))*base - 1 */
+  uint32_t res[ATMONR_MAX_LEVELS];    /* ceilf(scale)+1 */
+  uint32_t size[ATMONR_MAX_LEVELS];   /* entries in the level */
+  uint32_t offset[ATMONR_MAX_LEVELS + 1]; /* first entry of the level; [n_levels] = total */
+} atmonr_grid_t;
+
+/* Constants of the 'horizontal' point preprocessor closure,
+ * src/atmonr/datasets/harp2.py:351-388. enabled == 0 means no preprocessor. */
+typedef struct {
+  double scale;      /* metres per normalised unit (dataset.scale) */
+  double offset[3];  /* dataset.offset, float64 */
+  double lat_min, lat_range, lon_min, lon_range; /* float32 granule stats, up-cast */
+  double origin_height;                          /* config ray_origin_height */
+  int32_t shift_lon;                             /* granule crosses the dateline */
+  int32_t enabled;
+} atmonr_frame_t;
+
+/* Bias-free fully fused MLP (tiny-cuda-nn FullyFusedMLP behind tcnn.Network,
+ * instant_ngp.py:64-68,73-77,81-85). Weights: fp16 copies of the row-major [out][in]
+ * matrices, concatenated first to last; the input is padded to in_pad with 1.0. */
+typedef struct {
+  int32_t n_in;      /* logical input width  */
+  int32_t in_pad;    /* multiple of 16       */
+  int32_t width;     /* hidden width (32)    */
+  int32_t n_hidden;  /* hidden layers (1|2)  */
+  int32_t n_out;     /* logical output width */
+  int32_t out_pad;   /* multiple of 16 (16)  */
+} atmonr_mlp_t;
+
+int atmonr_abi_version(void);
+const char* atmonr_last_error(void);
+
+/* Host only (no GPU needed): level table of tcnn's GridEncoding. */
+int atmonr_grid_layout(int n_dims, int n_levels, int log2_hashmap_size, int base_resolution,
+                       float per_level_scale, atmonr_grid_t* out_host);
+
+/* ---- samplers.py:8-47 sample_uniform_bins ------------------------------------------------
+ * mode 0: bin mid-points (random=False); 1: uniforms read from u (B,N); 2: in-kernel Philox
+ * keyed by (seed, ray_index_base + ray, bin). bins: N floats = linspace(0,1,N+1)[:-1] or NULL
+ * (then i/N is used). pts (B,N,3), z (B,N). */
+int atmonr_sample_uniform(const float* origin, const float* dir, const float* len,
+                          const float* u, const float* bins, int64_t B, int N, int mode,
+                          uint64_t seed, uint64_t ray_index_base, float* pts, float* z,
+                          void* stream);
+
+/* ---- harp2.py:372-386 preprocess_coords (+ wgs_84.py:56-97) ------------------------------
+ * is_f64 selects float64 in/out (extract path) or float32 in/out (training path). n points. */
+int atmonr_preprocess_horizontal(const atmonr_frame_t* frame_host, const void* pts, void* out,
+                                 int64_t n, int is_f64, void* stream);
+
+/* ---- instant_ngp.py:139-160 fused: sampler -> preprocessor -> (p+1)/2 -> z /= alt_compress
+ * x01 (B*N,3) float32 is the hash-grid input; z (B,N) are the normalised sample distances. */
+int atmonr_ngp_sample_points(const atmonr_frame_t* frame_host, const float* origin,
+                             const float* dir, const float* len, const float* u,
+                             const float* bins, int64_t B, int N, int mode, uint64_t seed,
+                             uint64_t ray_index_base, float alt_compress, float* x01, float* z,
+                             void* stream);
+
+/* ---- tcnn.Encoding HashGrid forward/backward (instant_ngp.py:163,236) --------------------
+ * x (M, x_stride) float32, the first n_dims columns are used. table: fp16 shadow of the
+ * parameters, (entries, 2). out (M, 2*n_levels) float32 holding fp16-rounded values.
+ * bwd accumulates dL/dtable into a float32 (entries, 2) buffer with vector atomics. */
+int atmonr_hashgrid_fwd(const atmonr_grid_t* grid_host, const float* x, int x_stride,
+                        const void* table_f16, int64_t M, float* out, void* stream);
+int atmonr_hashgrid_bwd(const atmonr_grid_t* grid_host, const float* x, int x_stride,
+                        const float* dout, int64_t M, float* dtable, void* stream);
+/* Debug/parity: uint32 entry index of every (sample, level, corner): (M, L, 2^D). */
+int atmonr_hashgrid_indices(const atmonr_grid_t* grid_host, const float* x, int x_stride,
+                            int64_t M, uint32_t* idx, void* stream);
+
+/* ---- tcnn.Network forward/backward -------------------------------------------------------
+ * x (M, n_in) float32; out (M, n_out) float32. bwd recomputes the activations; dx may be
+ * NULL; dw (float32, same layout as the weights) is accumulated into. */
+int atmonr_mlp_fwd(const atmonr_mlp_t* mlp_host, const void* w_f16, const float* x, int64_t M,
+                   float* out, void* stream);
+int atmonr_mlp_bwd(const atmonr_mlp_t* mlp_host, const void* w_f16, const float* x,
+                   const float* dout, int64_t M, float* dx, float* dw, void* stream);
+
+/* ---- fused radiance field: hash grid -> pos_mlp -> [SH2(dir) | feat] -> dir_mlp ------------
+ * instant_ngp.py:163-171,178 per sample. x01 (M,3); dirs (B,3) with M = B*N; outputs are the
+ * RAW (pre-ReLU) density sigma (M) and colour (M,4).  n_sigma == 1, num_bands == 4. */
+int atmonr_ngp_field_fwd(const atmonr_grid_t* grid_host, const void* table_f16,
+                         const atmonr_mlp_t* pos_mlp_host, const void* pos_w_f16,
+                         const atmonr_mlp_t* dir_mlp_host, const void* dir_w_f16,
+                         const float* x01, const float* dirs, int64_t B, int N, float* sigma_raw,
+                         float* color_raw, void* stream);
+int atmonr_ngp_field_bwd(const atmonr_grid_t* grid_host, const void* table_f16,
+                         const atmonr_mlp_t* pos_mlp_host, const void* pos_w_f16,
+                         const atmonr_mlp_t* dir_mlp_host, const void* dir_w_f16,
+                         const float* x01, const float* dirs, const float* dsigma_raw,
+                         const float* dcolor_raw, int64_t B, int N, float* dtable, float* dpos_w,
+                         float* ddir_w, void* stream);
+
+/* ---- surface branch, per ray: [hash2d(pts_surf.xy) | SH2(dir)] -> surf_mlp ----------------
+ * instant_ngp.py:140,150,173-174. color_surf_raw (B,4) pre-ReLU. */
+int atmonr_ngp_surface_fwd(const atmonr_grid_t* grid2d_host, const void* table_f16,
+                           const atmonr_mlp_t* mlp_host, const void* w_f16, const float* origin,
+                           const float* dir, const float* len, int64_t B, float* color_surf_raw,
+                           void* stream);
+int atmonr_ngp_surface_bwd(const atmonr_grid_t* grid2d_host, const void* table_f16,
+                           const atmonr_mlp_t* mlp_host, const void* w_f16, const float* origin,
+                           const float* dir, const float* len, const float* dcolor_surf_raw,
+                           int64_t B, float* dtable, float* dw, void* stream);
+
+/* ---- graphics_utils.py:6-77 render / render_with_surface (+ the ReLUs of
+ * instant_ngp.py:178-184 when relu != 0) -------------------------------------------------
+ * z (B,N) normalised distances, multiplied by z_scale (= scale/1000, km); color (B,N,K);
+ * sigma (B,N,V) with V == 1 or V == K; color_surf (B,K) or NULL. Outputs: color_map,
+ * color_map_atmo, color_map_surf (B,K); trans_surf (B,V) = prod(1-alpha); optional weights
+ * and alpha (B,N,V). K <= 4. */
+int atmonr_composite_fwd(const float* z, const float* color, const float* sigma,
+                         const float* color_surf, float z_scale, int64_t B, int N, int K, int V,
+                         int relu, float* color_map, float* color_map_atmo,
+                         float* color_map_surf, float* trans_surf, float* weights, float* alpha,
+                         void* stream);
+/* Backward given dL/dcolor_map_atmo (B,K) and dL/dcolor_map_surf (B,K). Produces dcolor
+ * (B,N,K), dsigma (B,N,V) and dcolor_surf (B,K) w.r.t. the RAW inputs when relu != 0, and
+ * optionally ddelta (B,N) = dL/d(Voronoi cell width in km) for callers that differentiate
+ * through the sample distances (NeRF fine pass, samplers.py:96 keeps that path alive). */
+int atmonr_composite_bwd(const float* z, const float* color, const float* sigma,
+                         const float* color_surf, const float* color_map_atmo,
+                         const float* trans_surf, const float* d_atmo, const float* d_surf,
+                         float z_scale, int64_t B, int N, int K, int V, int relu, float* dcolor,
+                         float* dsigma, float* dcolor_surf, float* ddelta, void* stream);
+
+/* ---- per-band loss and its gradient (instant_ngp.py:249-263, losses.py:5-33) ---------------
+ * kind: 0 dark, 1 hdr, 2 l1, 3 l1_plus_hdr, 4 mse, 5 mse_plus_hdr. color_map (B,K); band
+ * (B) int64; rad (B). Writes loss (1 float, mean over B) and dcolor_map (B,K) scaled by
+ * grad_scale. partial: scratch of at least 1024 floats. */
+int atmonr_band_loss(const float* color_map, const int64_t* band, const float* rad, float max_i,
+                     int kind, int64_t B, int K, float grad_scale, float* loss,
+                     float* dcolor_map, float* partial, void* stream);
+
+/* ---- fused AdamW (torch.optim.AdamW as configured at instant_ngp.py:107-127) --------------
+ * Dense update of n parameters; grad is multiplied by grad_scale first; optionally writes the
+ * fp16 shadow and zeroes the gradient. step is the 1-based step count. */
+int atmonr_adamw_step(float* param, float* grad, float* exp_avg, float* exp_avg_sq,
+                      void* param_f16, int64_t n, double lr, double beta1, double beta2, double eps,
+                      double weight_decay, int64_t step, double grad_scale, int zero_grad,
+                      void* stream);
+
+/* ---- extract (instant_ngp.py:208-247; loop at scripts/extract.py:203-209) -----------------
+ * pts (n,3) float64 normalised scene coordinates -> sigma (n) float32 = max(pos_mlp[...,0],0). */
+int atmonr_extract_sigma(const atmonr_frame_t* frame_host, const atmonr_grid_t* grid_host,
+                         const void* table_f16, const atmonr_mlp_t* pos_mlp_host,
+                         const void* pos_w_f16, const double* pts, int64_t n, float alt_compress,
+                         float* sigma, void* stream);
+
+/* ---- NeRF path helpers ----------------------------------------------------------------------
+ * encoders.py:4-28 positional_encoding; list variant (per-axis frequency counts, layout
+ * [sin x L | cos x L] per axis) when interleaved == 0, int variant ([sin,cos] per frequency)
+ * otherwise. pts (M,C) float32, C <= 4. */
+int atmonr_positional_encoding(const float* pts, int64_t M, int C, const int32_t* freqs_host,
+                               int interleaved, float* out, void* stream);
+/* samplers.py:50-103 sample_pdf up to and including the sort: weights (B,Nc) (the V == 1
+ * column), z_coarse (B,Nc), u (B,Nf) -> z_sorted (B,Nc+Nf), inds (B,Nf) int64. */
+int atmonr_sample_pdf(const float* weights, const float* z_coarse, const float* u, int64_t B,
+                      int Nc, int Nf, float* z_sorted, int64_t* inds, void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* ATMONR_B200_H */

@@ -37,13 +37,16 @@ def _ste_half(x: torch.Tensor) -> torch.Tensor:
 def grid_levels(n_dims, n_levels, log2_hashmap_size, base_resolution, per_level_scale):
     """[upstream-recalled] level table of tcnn's GridEncoding (grid.h).
 
-    scale_l = exp2f(l * log2f(per_level_scale)) * base - 1   (float32 throughout)
+    scale_l = exp2(l * log2(per_level_scale)) * base - 1, evaluated in float64 on the float32
+              per_level_scale and rounded once to float32 (tcnn evaluates it in float32 with
+              exp2f/log2f, whose host and device versions disagree in the last bits; the
+              once-rounded value is within a few ulps and reproducible everywhere)
     res_l   = ceilf(scale_l) + 1
     size_l  = min(next_multiple(res_l ** D, 8), 2 ** log2T)  (entries, each F features)
     a level is 'hashed' iff res_l ** D (stride after D dims) exceeds size_l.
     """
     f32 = np.float32
-    log2_pls = np.log2(f32(per_level_scale)).astype(f32)
+    log2_pls = np.log2(np.float64(f32(per_level_scale)))
     scale = np.zeros(n_levels, dtype=f32)
     res = np.zeros(n_levels, dtype=np.uint32)
     size = np.zeros(n_levels, dtype=np.uint32)
@@ -51,7 +54,7 @@ def grid_levels(n_dims, n_levels, log2_hashmap_size, base_resolution, per_level_
     cap = 1 << log2_hashmap_size
     max_params = (2**32 - 1) // 2
     for lvl in range(n_levels):
-        s = f32(np.exp2(f32(f32(lvl) * log2_pls)).astype(f32) * f32(base_resolution)) - f32(1.0)
+        s = f32(np.exp2(np.float64(lvl) * log2_pls) * np.float64(base_resolution) - 1.0)
         scale[lvl] = s
         r = int(np.ceil(s)) + 1
         res[lvl] = r

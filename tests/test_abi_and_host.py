@@ -1,0 +1,166 @@
+"""CPU-side checks: the shared library exports every symbol the header declares, host-only entry
+points work without a GPU, and the exact per-sample code the kernels run (built for the host in
+libatmonr_hostcheck.so) agrees with the oracle."""
+
+import ctypes as C
+import os
+import re
+
+import numpy as np
+import pytest
+import torch
+
+from helpers import ROOT, ngp_config, take, tiny_scene
+from oracle import geodesy, sampling, tcnn_spec
+from oracle.ngp import NGPOracle
+
+
+@pytest.fixture(scope="module", autouse=True)
+def built():
+    import __graft_entry__ as ge
+    ge.build()
+
+
+def _header_functions():
+    text = open(os.path.join(ROOT, "include", "atmonr_b200.h")).read()
+    text = re.sub(r"/\*.*?\*/", "", text, flags=re.S)
+    return sorted(set(re.findall(r"\b(atmonr_[a-z0-9_]+)\s*\(", text)))
+
+
+def test_library_exports_every_declared_symbol():
+    from atmonr.native import lib as L
+    lib = L.load()
+    names = _header_functions()
+    assert len(names) >= 20
+    for n in names:
+        assert hasattr(lib, n), f"{n} declared in include/atmonr_b200.h but not exported"
+    assert sorted(L.SIGNATURES) == names, "ctypes SIGNATURES out of sync with the header"
+    assert lib.atmonr_abi_version() == 1
+
+
+def test_no_cpu_fallback():
+    from atmonr.native import lib as L, ops
+    with pytest.raises(L.NativeLibraryError):
+        ops.sample_uniform(torch.zeros(2, 3), torch.zeros(2, 3), torch.ones(2), 4, random=False)
+    from atmonr import losses
+    with pytest.raises(L.NativeLibraryError):
+        losses.mse_loss(torch.rand(4), torch.rand(4), 1.0)
+
+
+def test_bad_arguments_report_errors():
+    from atmonr.native import lib as L
+    g = L.GridT()
+    with pytest.raises(L.NativeLibraryError, match="n_dims"):
+        L.call("atmonr_grid_layout", 5, 16, 19, 16, 1.5, C.byref(g))
+    with pytest.raises(L.NativeLibraryError, match="n_levels"):
+        L.call("atmonr_grid_layout", 3, 17, 19, 16, 1.5, C.byref(g))
+
+
+@pytest.mark.parametrize("dims,key", [(3, "encoding"), (2, "surface_encoding")])
+def test_grid_layout_matches_oracle_bit_for_bit(dims, key):
+    from atmonr.native import lib as L
+    cfg = ngp_config()["instant_ngp"][key]
+    if dims == 2:
+        cfg = cfg["nested"][0]
+    g = L.grid_layout(dims, cfg)
+    lv = tcnn_spec.grid_levels(dims, 16, cfg["log2_hashmap_size"], cfg["base_resolution"], cfg["per_level_scale"])
+    assert np.array_equal(np.array(g.scale[:16], dtype=np.float32).view(np.uint32), lv["scale"].view(np.uint32))
+    assert list(g.res[:16]) == lv["res"].tolist() and list(g.size[:16]) == lv["size"].tolist()
+    assert list(g.offset[:17]) == lv["offset"].tolist()
+    assert g.n_entries == (21141696 if dims == 3 else 2761000)
+
+
+def _hc():
+    lib = C.CDLL(os.path.join(ROOT, "atmospheric-neural-rendering_b200", "lib", "libatmonr_hostcheck.so"))
+    return lib
+
+
+def _frame_struct(fr):
+    from atmonr.native import lib as L
+    return L.make_frame(fr.scale, fr.offset, fr.lat_min, fr.lat_range, fr.lon_min, fr.lon_range, fr.origin_height, fr.shift_lon)
+
+
+def _p(a):
+    return a.ctypes.data_as(C.c_void_p)
+
+
+def test_host_build_of_kernel_math_matches_oracle():
+    scene = tiny_scene()
+    b = take(scene.batch, slice(0, 64))
+    n = 48
+    u = torch.rand(64, n, generator=torch.Generator().manual_seed(0))
+    orc = NGPOracle(ngp_config(n), scene.frame, scene.max_i)
+    want = orc.forward(b, orc.init_params(0), u)
+    hc, fr = _hc(), _frame_struct(scene.frame)
+    x01 = np.zeros((64 * n, 3), np.float32)
+    z = np.zeros((64, n), np.float32)
+    bins = torch.linspace(0, 1, n + 1)[:-1].numpy().copy()
+    o, d, ln, un = (t.numpy().copy() for t in (b["origin"], b["dir"], b["len"], u))
+    hc.hc_ngp_sample_points(C.byref(fr), _p(o), _p(d), _p(ln), _p(un), _p(bins), C.c_int64(64), n, 1,
+                            C.c_uint64(0), C.c_uint64(0), C.c_float(8.0), _p(x01), _p(z))
+    assert np.array_equal(z, want["z_vals_fine"].numpy())
+    assert np.abs(x01 - want["pts01"].numpy()).max() < 1.5e-7
+    # float64 flavour
+    p64 = (torch.rand(500, 3, dtype=torch.float64, generator=torch.Generator().manual_seed(1)) * 2 - 1).numpy().copy()
+    out64 = np.zeros_like(p64)
+    hc.hc_preprocess_f64(C.byref(fr), _p(p64), _p(out64), C.c_int64(500))
+    want64 = geodesy.preprocess_horizontal(torch.from_numpy(p64)[None], scene.frame)[0].numpy()
+    assert np.abs(out64 - want64).max() < 1e-11
+
+
+@pytest.mark.parametrize("dims,key", [(3, "encoding"), (2, "surface_encoding")])
+def test_host_build_of_hash_indexing_is_bit_exact(dims, key):
+    from atmonr.native import lib as L
+    cfg = ngp_config()["instant_ngp"][key]
+    if dims == 2:
+        cfg = cfg["nested"][0]
+    grid = L.grid_layout(dims, cfg)
+    orc = tcnn_spec.HashGrid(dims, cfg)
+    g = torch.Generator().manual_seed(4)
+    x = torch.rand(3000, dims, generator=g)
+    x[:6] = torch.tensor([0.0, 1.0, 0.5, 0.999999, 1e-7, 0.125])[:, None]
+    xn = x.numpy().copy()
+    idx = np.zeros((3000, 16, 1 << dims), np.uint32)
+    w = np.zeros((3000, 16, 1 << dims), np.float32)
+    _hc().hc_hashgrid_indices(C.byref(grid), _p(xn), dims, C.c_int64(3000), _p(idx), _p(w))
+    assert np.array_equal(idx.astype(np.int64), orc.all_indices(x).numpy())
+    for lvl in (0, 7, 15):
+        _, wo = tcnn_spec.grid_corner_indices(x, orc.levels, lvl)
+        assert np.array_equal(w[:, lvl], wo.numpy())
+
+
+def test_philox_uniforms():
+    out = np.zeros((64, 256), np.float32)
+    _hc().hc_philox(C.c_uint64(123), C.c_uint64(0), C.c_int64(64), 256, _p(out))
+    assert out.min() >= 0 and out.max() < 1
+    assert abs(out.mean() - 0.5) < 0.01 and abs(out.var() - 1 / 12) < 0.005
+    assert len(np.unique(out)) > 0.99 * out.size
+    out2 = np.zeros((32, 256), np.float32)
+    _hc().hc_philox(C.c_uint64(123), C.c_uint64(32), C.c_int64(32), 256, _p(out2))
+    assert np.array_equal(out2, out[32:])   # the draw depends only on (seed, global ray, bin)
+
+
+def test_pipeline_surface_on_cpu():
+    """Construction, state-dict layout and optimizer groups of the pipelines need no GPU."""
+    from helpers import FakeDataset
+    from atmonr.pipelines.factory import get_pipeline
+    from atmonr.utils import load_config
+    cfg = load_config(os.path.join(ROOT, "configs", "instant_ngp.json"))
+    scene = tiny_scene(h=3, w=3, n_views=3)
+    pipe = get_pipeline(cfg["pipeline"], FakeDataset(scene))
+    sd = pipe.state_dict()
+    assert list(sd) == ["pos_encoder", "pos_mlp", "dir_encoder", "dir_mlp", "surf_encoder", "surf_mlp"]
+    sizes = {k: v["params"].numel() for k, v in sd.items()}
+    assert sizes == {"pos_encoder": 42283392, "pos_mlp": 1536, "dir_encoder": 0, "dir_mlp": 2560,
+                     "surf_encoder": 5522000, "surf_mlp": 3072}
+    assert pipe.fused_state is not None
+    opt = pipe.get_optimizer(cfg["trainer"]["optimizer"])
+    assert [g["weight_decay"] for g in opt.param_groups] == [0, 1e-2]
+    assert sum(p.numel() for g in opt.param_groups for p in g["params"]) == 47812560
+    pipe.load_state_dict(sd); pipe.eval(); pipe.train()
+    with pytest.raises(NotImplementedError):
+        get_pipeline({"type": "nope"}, FakeDataset(scene))
+    ncfg = load_config(os.path.join(ROOT, "configs", "nerf.json"))
+    npipe = get_pipeline(ncfg["pipeline"], FakeDataset(scene))
+    assert set(npipe.state_dict()) == {"coarse", "fine"}
+    assert npipe.nerf["coarse"].fc1.in_features == 76 and npipe.nerf["fine"].fc9.out_features == 260

@@ -1,0 +1,346 @@
+"""GPU parity: every kernel of libatmonr_b200 (called through its C ABI via atmonr.native) against
+the CPU oracle on identical inputs and identical random draws."""
+
+import numpy as np
+import pytest
+import torch
+
+from helpers import FakeDataset, load_params, ngp_config, random_params, take, tiny_scene, to_cuda
+from oracle import geodesy, nerf as onerf, rendering, sampling, tcnn_spec
+from oracle.ngp import NGPOracle
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.fixture(scope="module")
+def scene():
+    return tiny_scene()
+
+
+def _native():
+    from atmonr.native import lib as L, ops
+    L.load()
+    return L, ops
+
+
+def rel_err(a, b):
+    a, b = a.double().cpu(), b.double().cpu()
+    return float((a - b).abs().max() / (b.abs().max() + 1e-30))
+
+
+# ------------------------------------------------------------------ sampler + preprocessor
+def test_sample_uniform_bit_exact(scene):
+    L, ops = _native()
+    b = take(scene.batch, slice(0, 200))
+    g = torch.Generator().manual_seed(3)
+    for n in (16, 64, 100):
+        u = torch.rand(200, n, generator=g)
+        pts_o, z_o = sampling.sample_uniform(b["origin"], b["dir"], b["len"], n, u)
+        pts, z = ops.sample_uniform(b["origin"].cuda(), b["dir"].cuda(), b["len"].cuda(), n, u=u.cuda())
+        assert torch.equal(z.cpu(), z_o) and torch.equal(pts.cpu(), pts_o)
+        pts_o, z_o = sampling.sample_uniform(b["origin"], b["dir"], b["len"], n, None)
+        pts, z = ops.sample_uniform(b["origin"].cuda(), b["dir"].cuda(), b["len"].cuda(), n, random=False)
+        assert torch.allclose(z.cpu(), z_o, rtol=0, atol=1e-7) and torch.allclose(pts.cpu(), pts_o, rtol=0, atol=1e-6)
+
+
+def test_philox_sampler_statistics(scene):
+    L, ops = _native()
+    b = take(scene.batch, slice(0, 256))
+    n = 64
+    _, z = ops.sample_uniform(b["origin"].cuda(), b["dir"].cuda(), b["len"].cuda(), n, random=True, seed=7)
+    _, z2 = ops.sample_uniform(b["origin"].cuda(), b["dir"].cuda(), b["len"].cuda(), n, random=True, seed=7)
+    _, z3 = ops.sample_uniform(b["origin"].cuda(), b["dir"].cuda(), b["len"].cuda(), n, random=True, seed=8)
+    assert torch.equal(z, z2) and not torch.equal(z, z3)
+    t = (z.cpu() / b["len"][:, None]) * n - torch.arange(n)[None]   # position inside the bin
+    assert (t >= -1e-4).all() and (t <= 1 + 1e-4).all()
+    assert abs(float(t.mean()) - 0.5) < 0.01 and abs(float(t.var()) - 1 / 12) < 0.005
+    # partition invariance: rays 128.. drawn alone with ray_index_base=128 give the same z
+    _, zp = ops.sample_uniform(b["origin"][128:].cuda(), b["dir"][128:].cuda(), b["len"][128:].cuda(), n,
+                               random=True, seed=7, ray_index_base=128)
+    assert torch.equal(zp, z[128:])
+
+
+def test_preprocess_matches_oracle(scene):
+    L, ops = _native()
+    b = take(scene.batch, slice(0, 300))
+    pts, _ = sampling.sample_uniform(b["origin"], b["dir"], b["len"], 32, torch.rand(300, 32, generator=torch.Generator().manual_seed(1)))
+    want32 = geodesy.preprocess_horizontal(pts, scene.frame)
+    pre = FakeDataset(scene).get_point_preprocessor("horizontal")
+    got32 = pre(pts.cuda()).cpu()
+    assert got32.dtype == torch.float32
+    # float32 output of a float64 computation: identical up to the rare last-bit rounding flip
+    assert torch.allclose(got32, want32, rtol=0, atol=2.5e-7)
+    assert (got32 != want32).float().mean() < 1e-3
+    p64 = pts.double().view(-1, 3)
+    want64 = geodesy.preprocess_horizontal(p64[None], scene.frame)[0]
+    got64 = pre(p64.cuda()).cpu()
+    assert got64.dtype == torch.float64 and torch.allclose(got64, want64, rtol=0, atol=1e-11)
+
+
+def test_ngp_sample_points_matches_oracle(scene):
+    L, ops = _native()
+    cfg = ngp_config(64)
+    orc = NGPOracle(cfg, scene.frame, scene.max_i)
+    b = take(scene.batch, slice(0, 128))
+    u = torch.rand(128, 64, generator=torch.Generator().manual_seed(2))
+    res = orc.forward(b, orc.init_params(0), u)
+    pre = FakeDataset(scene).get_point_preprocessor("horizontal")
+    x01, z = ops.ngp_sample_points(pre.frame, b["origin"].cuda(), b["dir"].cuda(), b["len"].cuda(), 64, 8.0, u=u.cuda())
+    assert torch.equal(z.cpu(), res["z_vals_fine"])
+    assert torch.allclose(x01.cpu(), res["pts01"], rtol=0, atol=1.5e-7)
+
+
+# ------------------------------------------------------------------ hash grid
+@pytest.mark.parametrize("dims,key", [(3, "encoding"), (2, "surface_encoding")])
+def test_hashgrid_indices_bit_exact_and_features(dims, key):
+    L, ops = _native()
+    cfg = ngp_config()["instant_ngp"][key]
+    if dims == 2:
+        cfg = cfg["nested"][0]
+    grid_o = tcnn_spec.HashGrid(dims, cfg)
+    grid = L.grid_layout(dims, cfg)
+    g = torch.Generator().manual_seed(5)
+    x = torch.rand(4096, dims, generator=g)
+    x[:8] = torch.tensor([0.0, 1.0, 0.5, 0.25, 0.999999, 1e-7, 0.125, 0.75])[:, None]  # edges
+    if dims == 3:
+        x[:, 2] *= 0.125   # compressed altitude range
+    idx = ops.hashgrid_indices(grid, x.cuda()).cpu().to(torch.int64) & 0xFFFFFFFF
+    assert torch.equal(idx, grid_o.all_indices(x))
+    params = (torch.rand(grid_o.n_params, generator=g) * 2 - 1) * 0.5
+    want = grid_o.forward(x, params, fp16=True)
+    p = params.cuda().requires_grad_()
+    got = ops.HashGridFn.apply(x.cuda(), p, p.detach().half(), grid)
+    # interpolation is fp32 FMA on fp16 table values, result rounded to fp16: allow one fp16 ulp
+    assert torch.allclose(got.cpu(), want, rtol=1e-3, atol=1e-6)
+    want32 = grid_o.forward(x, params, fp16=False)
+    assert rel_err(got, want32) < 2e-3
+    # backward: gradient of sum(out * r) w.r.t. the table
+    r = torch.randn(4096, grid_o.n_output_dims, generator=g)
+    pc = params.clone().requires_grad_()
+    (grid_o.forward(x, pc, fp16=True) * r).sum().backward()
+    (got * r.cuda()).sum().backward()
+    assert torch.allclose(p.grad.cpu(), pc.grad, rtol=1e-4, atol=1e-5)
+
+
+# ------------------------------------------------------------------ MLPs
+@pytest.mark.parametrize("n_in,n_out,key", [(32, 16, "network"), (19, 4, "rgb_network"), (36, 4, "surface_network")])
+def test_mlp_forward_backward(n_in, n_out, key):
+    L, ops = _native()
+    cfg = ngp_config()["instant_ngp"][key]
+    net_o = tcnn_spec.Network(n_in, n_out, cfg)
+    g = torch.Generator().manual_seed(11)
+    params = net_o.init_params(g)
+    m = 1000  # not a multiple of the 128-row tile
+    x = torch.randn(m, n_in, generator=g)
+    r = torch.randn(m, n_out, generator=g)
+    pc, xc = params.clone().requires_grad_(), x.clone().requires_grad_()
+    want = net_o.forward(xc, pc, fp16=True)
+    (want * r).sum().backward()
+    shape = L.mlp_shape(n_in, n_out, cfg)
+    p, xg = params.cuda().requires_grad_(), x.cuda().requires_grad_()
+    got = ops.MlpFn.apply(xg, p, p.detach().half(), shape)
+    (got * r.cuda()).sum().backward()
+    assert rel_err(got, want) < 1e-4
+    assert rel_err(p.grad, pc.grad) < 1e-4
+    assert rel_err(xg.grad, xc.grad) < 1e-4
+    assert rel_err(got, net_o.forward(x, params, fp16=False)) < 5e-3   # vs pure fp32
+
+
+# ------------------------------------------------------------------ compositing + loss
+@pytest.mark.parametrize("k,v,surf", [(4, 1, True), (4, 4, True), (4, 1, False), (2, 2, False), (3, 1, True)])
+def test_composite_forward_backward(k, v, surf):
+    L, ops = _native()
+    g = torch.Generator().manual_seed(21)
+    b, n = 37, 77   # ragged: not a multiple of the warp size
+    z = torch.sort(torch.rand(b, n, generator=g) * 25, dim=1)[0]
+    col = (torch.rand(b, n, k, generator=g) - 0.2)   # raw values, some negative -> exercised by relu
+    sig = (torch.rand(b, n, v, generator=g) - 0.3) * 0.5
+    cs = torch.rand(b, k, generator=g) - 0.1 if surf else None
+    ra, rs = torch.randn(b, k, generator=g), torch.randn(b, k, generator=g)
+    for relu in (True, False):
+        zc, cc, sc = z.clone().requires_grad_(), col.clone().requires_grad_(), (sig if relu else sig.abs()).clone().requires_grad_()
+        csc = cs.clone().requires_grad_() if surf else None
+        act = torch.relu if relu else (lambda t: t)
+        if surf:
+            cm, al, w, ca, csf = rendering.composite_with_surface(zc, act(cc), act(sc), act(csc))
+            loss = (ca * ra).sum() + (csf * rs).sum() + cm.sum()
+        else:
+            cm, al, w = rendering.composite(zc, act(cc), act(sc))
+            loss = (cm * ra).sum()
+        loss.backward()
+        zg, cg, sg = z.cuda().requires_grad_(), col.cuda().requires_grad_(), (sig if relu else sig.abs()).cuda().requires_grad_()
+        csg = cs.cuda().requires_grad_() if surf else None
+        gm, ga, gs, gw, gal = ops.CompositeFn.apply(zg, cg, sg, csg, 1.0, relu)
+        if surf:
+            lg = (ga * ra.cuda()).sum() + (gs * rs.cuda()).sum() + gm.sum()
+        else:
+            lg = (gm * ra.cuda()).sum()
+        lg.backward()
+        assert rel_err(gm, cm) < 1e-5 and rel_err(gw, w) < 1e-5 and rel_err(gal, al) < 1e-5
+        assert rel_err(cg.grad, cc.grad) < 1e-4
+        assert rel_err(sg.grad, sc.grad) < 1e-4
+        assert rel_err(zg.grad, zc.grad) < 1e-3
+        if surf:
+            assert rel_err(csg.grad, csc.grad) < 1e-5
+
+
+def test_composite_edge_cases():
+    L, ops = _native()
+    # single sample per ray, zero density, saturated density
+    z = torch.tensor([[0.7], [1.3]]).cuda()
+    col = torch.ones(2, 1, 4).cuda()
+    sig = torch.tensor([[[0.0]], [[1e4]]]).cuda()
+    cm, ca, cs, w, a = ops.CompositeFn.apply(z, col, sig, torch.ones(2, 4).cuda(), 1.0, False)
+    want = rendering.composite_with_surface(z.cpu(), col.cpu(), sig.cpu(), torch.ones(2, 4))
+    assert torch.allclose(cm.cpu(), want[0]) and torch.allclose(w.cpu(), want[2])
+    # empty batch
+    e = ops.CompositeFn.apply(torch.zeros(0, 8).cuda(), torch.zeros(0, 8, 4).cuda(), torch.zeros(0, 8, 1).cuda(), None, 1.0, True)
+    assert e[0].shape == (0, 4)
+
+
+@pytest.mark.parametrize("kind", list(rendering.LOSSES))
+def test_band_loss(kind):
+    L, ops = _native()
+    g = torch.Generator().manual_seed(31)
+    b = 1234
+    cm = (torch.rand(b, 4, generator=g) * 0.4).requires_grad_()
+    band = torch.randint(0, 4, (b,), generator=g)
+    rad = torch.rand(b, generator=g) * 0.4
+    want = rendering.LOSSES[kind](rendering.band_select(cm, band), rad, 0.37)
+    want.backward()
+    cg = cm.detach().cuda().requires_grad_()
+    got = ops.band_loss(cg, band.cuda(), rad.cuda(), 0.37, kind)
+    got.backward()
+    assert rel_err(got, want) < 1e-5
+    assert rel_err(cg.grad, cm.grad) < 1e-4
+
+
+# ------------------------------------------------------------------ optimizer
+def test_fused_adamw_matches_torch():
+    from atmonr.optim import FusedAdamW
+    g = torch.Generator().manual_seed(41)
+    n = 100003
+    p0 = torch.randn(n, generator=g)
+    ref = torch.nn.Parameter(p0.clone())
+    mine = torch.nn.Parameter(p0.clone().cuda())
+    kw = dict(lr=1e-2, betas=(0.9, 0.99), eps=1e-15, weight_decay=1e-2)
+    o_ref = torch.optim.AdamW([ref], foreach=False, **kw)
+    o_mine = FusedAdamW([mine], **kw)
+    for step in range(5):
+        gr = torch.randn(n, generator=g) * (0.1 if step != 2 else 0.0)   # a zero-gradient step too
+        ref.grad, mine.grad = gr.clone(), gr.clone().cuda()
+        o_ref.step(); o_mine.step()
+        assert torch.allclose(mine.detach().cpu(), ref.detach(), rtol=1e-6, atol=1e-7), step
+    from atmonr.native.modules import shadow_of
+    assert torch.equal(shadow_of(mine).cpu(), mine.detach().cpu().half())
+    sd = o_mine.state_dict()
+    assert set(sd["state"][0]) == {"step", "exp_avg", "exp_avg_sq"}
+
+
+# ------------------------------------------------------------------ the whole NGP step
+def _pipeline(scene, cfg):
+    from atmonr.pipelines.instant_ngp import InstantNGPPipeline
+    pipe = InstantNGPPipeline(cfg, FakeDataset(scene))
+    pipe.send_tensors_to(0)
+    return pipe
+
+
+def test_ngp_pipeline_forward_loss_gradients_vs_oracle(scene):
+    cfg = ngp_config(64)
+    orc16 = NGPOracle(cfg, scene.frame, scene.max_i, fp16=True)
+    orc32 = NGPOracle(cfg, scene.frame, scene.max_i, fp16=False)
+    params = random_params(orc16, seed=0, table_scale=2e3)
+    b = take(scene.batch, slice(0, 96))
+    u = torch.rand(96, 64, generator=torch.Generator().manual_seed(9))
+    res = orc16.forward(b, params, u)
+    loss = orc16.loss(b, res)
+    loss.backward()
+    pipe = _pipeline(scene, cfg)
+    assert pipe.fused_state is not None
+    load_params(pipe, params)
+    bc = to_cuda(b)
+    out = pipe.forward(bc, u=u.cuda())
+    lg = pipe.compute_loss(bc, out)
+    lg.backward()
+    for key in ("color_map_fine", "color_map_atmo", "color_map_surf"):
+        assert rel_err(out[key], res[key]) < 1e-3, key                      # native rounding points emulated
+    res32 = orc32.forward(b, params, u)
+    assert rel_err(out["color_map_fine"], res32["color_map_fine"]) < 1e-2   # vs pure fp32 (fp16 table/MLP path)
+    assert rel_err(lg, loss) < 1e-3
+    for key in ("weights_fine", "sigma_fine", "color_fine", "z_vals_fine", "color_surf"):
+        assert rel_err(out[key], res[key]) < 2e-3, key
+    for name in ("pos_mlp", "dir_mlp", "surf_mlp", "pos_encoder", "surf_encoder"):
+        got = getattr(pipe, name).params.grad
+        assert rel_err(got, params[name].grad) < 2e-3, name
+    # modular (operator-by-operator) path agrees with the fused path
+    pipe.fused_state = None
+    out_m = pipe.forward(bc, u=u.cuda())
+    assert rel_err(out_m["color_map_fine"], out["color_map_fine"]) < 1e-5
+
+
+def test_ngp_training_tracks_oracle(scene):
+    """Same initial parameters, same batches, same uniform draws: the native loss curve follows
+    the oracle's (torch AdamW on the fp16-emulating restatement)."""
+    cfg = ngp_config(32)
+    orc = NGPOracle(cfg, scene.frame, scene.max_i, fp16=True)
+    params = random_params(orc, seed=1, table_scale=1.0)
+    opt_cfg = {"lr": 1e-2, "betas": [0.9, 0.99], "eps": 1e-15, "weight_decay": 1e-2}
+    opt = orc.make_optimizer(params, opt_cfg)
+    pipe = _pipeline(scene, cfg)
+    load_params(pipe, params)
+    opt_n = pipe.get_optimizer(opt_cfg)
+    g = torch.Generator().manual_seed(77)
+    lo, ln = [], []
+    n_rays = scene.batch["origin"].shape[0]
+    for step in range(30):
+        sel = torch.randperm(n_rays, generator=g)[:64]
+        b = take(scene.batch, sel)
+        u = torch.rand(64, 32, generator=g)
+        l_o, _ = orc.train_step(b, params, opt, u)
+        bc = to_cuda(b)
+        out = pipe.forward(bc, u=u.cuda())
+        l_n = pipe.compute_loss(bc, out)
+        opt_n.zero_grad(); l_n.backward(); opt_n.step()
+        lo.append(float(l_o)); ln.append(float(l_n))
+    lo, ln = np.array(lo), np.array(ln)
+    assert ln[-1] < ln[0]                                  # it trains
+    assert np.max(np.abs(ln - lo) / lo) < 0.05, (lo, ln)   # and tracks the oracle step by step
+
+
+def test_extract_matches_oracle(scene):
+    cfg = ngp_config(16)
+    orc = NGPOracle(cfg, scene.frame, scene.max_i, fp16=True)
+    params = random_params(orc, seed=2, table_scale=5e3)
+    g = torch.Generator().manual_seed(3)
+    pts = (torch.rand(5000, 3, generator=g, dtype=torch.float64) * 2 - 1) * 0.9
+    want = orc.extract(pts, params)
+    pipe = _pipeline(scene, cfg)
+    load_params(pipe, params)
+    pipe.eval()
+    with torch.no_grad():
+        got = pipe.extract(pts.cuda())
+    assert got.shape == (5000, 1) and (got >= 0).all()
+    assert rel_err(got, want) < 2e-3
+    assert float((want > 0).float().mean()) > 0.05          # not trivially all zeros
+
+
+# ------------------------------------------------------------------ NeRF helpers
+def test_positional_encoding_and_sample_pdf():
+    L, ops = _native()
+    from atmonr.encoders import positional_encoding
+    g = torch.Generator().manual_seed(51)
+    p = torch.rand(50, 7, 3, generator=g) * 2 - 1
+    got = positional_encoding(p.cuda(), [14, 14, 10]).cpu()
+    want = onerf.pe_per_axis(p, [14, 14, 10])
+    assert got.shape == want.shape and torch.allclose(got, want, atol=2e-3)   # sin/cos of arguments up to 2^13*pi
+    assert torch.allclose(got[..., :4], want[..., :4], atol=1e-6)
+    got = positional_encoding(p.cuda(), 4).cpu()
+    assert torch.allclose(got, onerf.pe_interleaved(p, 4), atol=1e-5)
+    w = torch.rand(40, 64, 1, generator=g)
+    zc = torch.sort(torch.rand(40, 64, generator=g), dim=1)[0]
+    u = torch.rand(40, 128, generator=g)
+    z_o, inds_o = sampling.inverse_cdf_z(w, zc, u)
+    z, inds = ops.sample_pdf_z(w[..., 0].cuda(), zc.cuda(), u.cuda())
+    assert (torch.diff(z, dim=1) >= 0).all()
+    assert torch.allclose(z.cpu(), z_o, atol=1e-5)
+    assert (inds.cpu() == inds_o).float().mean() > 0.999      # identical except u within an ulp of a CDF edge
