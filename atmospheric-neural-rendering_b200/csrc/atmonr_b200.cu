@@ -1110,8 +1110,8 @@ int atmonr_composite_fwd(const float* z, const float* color, const float* sigma,
                          float z_scale, int64_t B, int N, int K, int V, int relu, float* color_map,
                          float* color_map_atmo, float* color_map_surf, float* trans_surf, float* weights,
                          float* alpha, void* stream) {
-  ATM_REQUIRE(color_map, "atmonr_composite_fwd", "null color_map");
   if (B == 0) return 0;
+  ATM_REQUIRE(color_map, "atmonr_composite_fwd", "null color_map");
   const int grid = grid_for(B * 32, 128);
 #define CALL(KK, VV)                                                                                      \
   k_composite_fwd<KK, VV><<<grid, 128, 0, S(stream)>>>(z, color, sigma, color_surf, z_scale, B, N, relu,   \
@@ -1127,9 +1127,9 @@ int atmonr_composite_bwd(const float* z, const float* color, const float* sigma,
                          const float* color_map_atmo, const float* trans_surf, const float* d_atmo,
                          const float* d_surf, float z_scale, int64_t B, int N, int K, int V, int relu,
                          float* dcolor, float* dsigma, float* dcolor_surf, float* ddelta, void* stream) {
+  if (B == 0) return 0;
   ATM_REQUIRE(color_map_atmo && d_atmo && dcolor && dsigma, "atmonr_composite_bwd", "null argument");
   ATM_REQUIRE(!color_surf || trans_surf, "atmonr_composite_bwd", "trans_surf required with a surface");
-  if (B == 0) return 0;
   const int grid = grid_for(B * 32, 128);
 #define CALL(KK, VV)                                                                                         \
   k_composite_bwd<KK, VV><<<grid, 128, 0, S(stream)>>>(z, color, sigma, color_surf, color_map_atmo, trans_surf, \

@@ -190,6 +190,14 @@ int atmonr_positional_encoding(const float* pts, int64_t M, int C, const int32_t
 int atmonr_sample_pdf(const float* weights, const float* z_coarse, const float* u, int64_t B,
                       int Nc, int Nf, float* z_sorted, int64_t* inds, void* stream);
 
+/* ---- tensor-core self test -------------------------------------------------------------------
+ * One 128-row tile through the three tcgen05 operand configurations of the fused kernels.
+ * a, b: (128, 32) fp16 row-major; d: (128, 32) float32.
+ *   mode 0: d = a @ b[:32].T   (forward layer: A and B K-major)
+ *   mode 1: d = a @ b[:32]     (input gradient: B read MN-major)
+ *   mode 2: d[:32] = a.T @ b   (weight gradient: A and B MN-major, K = 128 rows) */
+int atmonr_tc_probe(const void* a_f16, const void* b_f16, int mode, float* d, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

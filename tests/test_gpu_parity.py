@@ -344,3 +344,24 @@ def test_positional_encoding_and_sample_pdf():
     assert (torch.diff(z, dim=1) >= 0).all()
     assert torch.allclose(z.cpu(), z_o, atol=1e-5)
     assert (inds.cpu() == inds_o).float().mean() > 0.999      # identical except u within an ulp of a CDF edge
+
+
+# ------------------------------------------------------------------ tensor-core operand layouts
+@pytest.mark.parametrize("mode", [0, 1, 2])
+def test_tcgen05_probe(mode):
+    L, ops = _native()
+    g = torch.Generator().manual_seed(61 + mode)
+    a = torch.randn(128, 32, generator=g).half()
+    b = torch.randn(128, 32, generator=g).half()
+    d = torch.full((128, 32), float("nan"), device="cuda")
+    ag, bg = a.cuda(), b.cuda()   # keep both alive: a temporary's block would be reused
+    L.call("atmonr_tc_probe", L.ptr(ag), L.ptr(bg), mode, L.ptr(d), L.stream())
+    torch.cuda.synchronize()
+    af, bf = a.float(), b.float()
+    if mode == 0:
+        want, got = af @ bf[:32].T, d.cpu()
+    elif mode == 1:
+        want, got = af @ bf[:32], d.cpu()
+    else:
+        want, got = af.T @ bf, d.cpu()[:32]
+    assert torch.allclose(got, want, rtol=1e-3, atol=1e-3), float((got - want).abs().max())
