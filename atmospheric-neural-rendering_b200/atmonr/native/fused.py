@@ -15,6 +15,7 @@ when somebody reads them (LazyResults).
 from __future__ import annotations
 
 import ctypes as C
+import os
 from dataclasses import dataclass, field
 
 import torch
@@ -23,6 +24,12 @@ from atmonr.native import lib as L
 from atmonr.native import ops
 
 _f32 = torch.float32
+
+# "tc": dense layers on tcgen05 tensor cores (default); "simt": the thread-per-sample FMA kernels
+# (same arithmetic contract; kept as the cross-check of the tensor-core path).
+FIELD_IMPL = os.environ.get("ATMONR_FIELD_IMPL", "tc")
+# keep the encoded features of the forward pass for the backward pass when they fit in this many bytes
+ENC_CACHE_BYTES = int(float(os.environ.get("ATMONR_ENC_CACHE_GB", "40")) * (1 << 30))
 
 
 @dataclass
@@ -45,13 +52,22 @@ class NGPState:
     last: dict = field(default_factory=dict)
 
 
-def field_forward(st: NGPState, table16, pos_w16, dir_w16, x01, dirs, b, n):
+def field_forward(st: NGPState, table16, pos_w16, dir_w16, x01, dirs, b, n, want_enc=False):
+    """-> (sigma_raw (M,), color_raw (M,4), enc (M,32) fp16 | None)."""
     sigma_raw = torch.empty(b * n, device=x01.device, dtype=_f32)
     color_raw = torch.empty((b * n, 4), device=x01.device, dtype=_f32)
-    L.call("atmonr_ngp_field_fwd", C.byref(st.grid3), L.ptr(table16), C.byref(st.pos_mlp), L.ptr(pos_w16),
+    if FIELD_IMPL == "simt":
+        L.call("atmonr_ngp_field_fwd", C.byref(st.grid3), L.ptr(table16), C.byref(st.pos_mlp), L.ptr(pos_w16),
+               C.byref(st.dir_mlp), L.ptr(dir_w16), L.ptr(x01), L.ptr(dirs), b, n, L.ptr(sigma_raw), L.ptr(color_raw),
+               L.stream())
+        return sigma_raw, color_raw, None
+    enc = None
+    if want_enc and b * n * 64 <= ENC_CACHE_BYTES:
+        enc = torch.empty((b * n, 32), device=x01.device, dtype=torch.float16)
+    L.call("atmonr_ngp_field_fwd_tc", C.byref(st.grid3), L.ptr(table16), C.byref(st.pos_mlp), L.ptr(pos_w16),
            C.byref(st.dir_mlp), L.ptr(dir_w16), L.ptr(x01), L.ptr(dirs), b, n, L.ptr(sigma_raw), L.ptr(color_raw),
-           L.stream())
-    return sigma_raw, color_raw
+           L.ptr(enc), L.stream())
+    return sigma_raw, color_raw, enc
 
 
 def surface_forward(st: NGPState, table16, w16, origin, direction, length):
@@ -75,7 +91,7 @@ class NGPRenderFn(torch.autograd.Function):
         seed = (st.seed * 0x9E3779B97F4A7C15 + st.step) & 0xFFFFFFFFFFFFFFFF
         x01, z = ops.ngp_sample_points(st.frame, origin, direction, length, n, st.alt_compress, u=u, random=True,
                                        seed=seed, ray_index_base=st.ray_index_base, bins=st.bins)
-        sigma_raw, color_raw = field_forward(st, t16, pw16, dw16, x01, direction, b, n)
+        sigma_raw, color_raw, enc = field_forward(st, t16, pw16, dw16, x01, direction, b, n, want_enc=False)
         cs_raw = surface_forward(st, s16, sw16, origin, direction, length)
         cmap, catmo, csurf, tsurf, _, _ = ops.composite_forward(
             z, color_raw.view(b, n, 4), sigma_raw.view(b, n, 1), cs_raw, st.z_scale, relu=True,

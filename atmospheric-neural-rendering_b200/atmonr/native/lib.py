@@ -77,6 +77,7 @@ SIGNATURES = {
     "atmonr_positional_encoding": [P, I64, I32, C.POINTER(C.c_int32), I32, P, P],
     "atmonr_sample_pdf": [P, P, P, I64, I32, I32, P, P, P],
     "atmonr_tc_probe": [P, P, I32, P, P],
+    "atmonr_ngp_field_fwd_tc": [GP, P, MP, P, MP, P, P, P, I64, I32, P, P, P, P],
 }
 
 _lib = None

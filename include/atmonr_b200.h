@@ -124,6 +124,17 @@ int atmonr_ngp_field_bwd(const atmonr_grid_t* grid_host, const void* table_f16,
                          const float* dcolor_raw, int64_t B, int N, float* dtable, float* dpos_w,
                          float* ddir_w, void* stream);
 
+/* tcgen05 implementations of the two calls above (same contract; dense layers on the 5th-gen
+ * tensor cores, accumulators in TMEM). enc (optional, (M,32) fp16): the forward stores the encoded
+ * features there, the backward reads them instead of re-gathering the table. grad_absmax: device
+ * scalar holding max|dsigma_raw|,|dcolor_raw| (as produced by atmonr_composite_bwd); it sets the
+ * power-of-two scale under which the fp16 gradient operands are formed. */
+int atmonr_ngp_field_fwd_tc(const atmonr_grid_t* grid_host, const void* table_f16,
+                            const atmonr_mlp_t* pos_mlp_host, const void* pos_w_f16,
+                            const atmonr_mlp_t* dir_mlp_host, const void* dir_w_f16,
+                            const float* x01, const float* dirs, int64_t B, int N,
+                            float* sigma_raw, float* color_raw, void* enc_f16, void* stream);
+
 /* ---- surface branch, per ray: [hash2d(pts_surf.xy) | SH2(dir)] -> surf_mlp ----------------
  * instant_ngp.py:140,150,173-174. color_surf_raw (B,4) pre-ReLU. */
 int atmonr_ngp_surface_fwd(const atmonr_grid_t* grid2d_host, const void* table_f16,
