@@ -91,12 +91,14 @@ class NGPRenderFn(torch.autograd.Function):
         seed = (st.seed * 0x9E3779B97F4A7C15 + st.step) & 0xFFFFFFFFFFFFFFFF
         x01, z = ops.ngp_sample_points(st.frame, origin, direction, length, n, st.alt_compress, u=u, random=True,
                                        seed=seed, ray_index_base=st.ray_index_base, bins=st.bins)
-        sigma_raw, color_raw, enc = field_forward(st, t16, pw16, dw16, x01, direction, b, n, want_enc=False)
+        needs_grad = torch.is_grad_enabled() and any(t.requires_grad for t in (pos_table, pos_w, dir_w))
+        sigma_raw, color_raw, enc = field_forward(st, t16, pw16, dw16, x01, direction, b, n, want_enc=needs_grad)
         cs_raw = surface_forward(st, s16, sw16, origin, direction, length)
         cmap, catmo, csurf, tsurf, _, _ = ops.composite_forward(
             z, color_raw.view(b, n, 4), sigma_raw.view(b, n, 1), cs_raw, st.z_scale, relu=True,
             want_weights=False, want_alpha=False)
         ctx.st = st
+        ctx.enc = enc
         ctx.save_for_backward(t16, pw16, dw16, s16, sw16, origin, direction, length, x01, z, sigma_raw, color_raw,
                               cs_raw, catmo, tsurf)
         ctx.sizes = (pos_table.numel(), pos_w.numel(), dir_w.numel(), surf_table.numel(), surf_w.numel())
@@ -114,18 +116,25 @@ class NGPRenderFn(torch.autograd.Function):
         g_map = torch.zeros_like(catmo) if g_map is None else g_map
         d_atmo = (g_map + g_atmo if g_atmo is not None else g_map).contiguous().float()
         d_surf = (g_map + g_surf if g_surf is not None else g_map).contiguous().float()
+        absmax = torch.zeros(1, device=dev, dtype=_f32) if FIELD_IMPL != "simt" else None
         dcolor, dsigma, dcs = ops.composite_backward(
             z, color_raw.view(b, n, 4), sigma_raw.view(b, n, 1), cs_raw, catmo, tsurf, d_atmo, d_surf,
-            st.z_scale, relu=True)
+            st.z_scale, relu=True, grad_absmax=absmax)
         n_t, n_pw, n_dw, n_s, n_sw = ctx.sizes
         d_table = torch.zeros(n_t, device=dev, dtype=_f32)
         d_pw = torch.zeros(n_pw, device=dev, dtype=_f32)
         d_dw = torch.zeros(n_dw, device=dev, dtype=_f32)
         d_s = torch.zeros(n_s, device=dev, dtype=_f32)
         d_sw = torch.zeros(n_sw, device=dev, dtype=_f32)
-        L.call("atmonr_ngp_field_bwd", C.byref(st.grid3), L.ptr(t16), C.byref(st.pos_mlp), L.ptr(pw16),
-               C.byref(st.dir_mlp), L.ptr(dw16), L.ptr(x01), L.ptr(direction), L.ptr(dsigma), L.ptr(dcolor), b, n,
-               L.ptr(d_table), L.ptr(d_pw), L.ptr(d_dw), L.stream())
+        if FIELD_IMPL == "simt":
+            L.call("atmonr_ngp_field_bwd", C.byref(st.grid3), L.ptr(t16), C.byref(st.pos_mlp), L.ptr(pw16),
+                   C.byref(st.dir_mlp), L.ptr(dw16), L.ptr(x01), L.ptr(direction), L.ptr(dsigma), L.ptr(dcolor), b, n,
+                   L.ptr(d_table), L.ptr(d_pw), L.ptr(d_dw), L.stream())
+        else:
+            L.call("atmonr_ngp_field_bwd_tc", C.byref(st.grid3), L.ptr(t16), C.byref(st.pos_mlp), L.ptr(pw16),
+                   C.byref(st.dir_mlp), L.ptr(dw16), L.ptr(x01), L.ptr(direction), L.ptr(ctx.enc), L.ptr(dsigma),
+                   L.ptr(dcolor), L.ptr(absmax), b, n, L.ptr(d_table), L.ptr(d_pw), L.ptr(d_dw), L.stream())
+            ctx.enc = None
         L.call("atmonr_ngp_surface_bwd", C.byref(st.grid2), L.ptr(s16), C.byref(st.surf_mlp), L.ptr(sw16),
                L.ptr(origin), L.ptr(direction), L.ptr(length), L.ptr(dcs), b, L.ptr(d_s), L.ptr(d_sw), L.stream())
         return d_table, d_pw, d_dw, d_s, d_sw, None, None, None, None, None, None

@@ -156,7 +156,8 @@ def composite_forward(z, color, sigma, color_surf, z_scale, relu, want_weights=T
     return cmap, catmo, csurf, tsurf, weights, alpha
 
 
-def composite_backward(z, color, sigma, color_surf, catmo, tsurf, d_atmo, d_surf, z_scale, relu, want_dz=False):
+def composite_backward(z, color, sigma, color_surf, catmo, tsurf, d_atmo, d_surf, z_scale, relu, want_dz=False,
+                       grad_absmax=None):
     b, n = z.shape
     k, v = color.shape[-1], sigma.shape[-1]
     dcolor = torch.empty_like(color)
@@ -165,7 +166,7 @@ def composite_backward(z, color, sigma, color_surf, catmo, tsurf, d_atmo, d_surf
     ddelta = torch.empty_like(z) if want_dz else None
     L.call("atmonr_composite_bwd", L.ptr(z), L.ptr(color), L.ptr(sigma), L.ptr(color_surf), L.ptr(catmo), L.ptr(tsurf),
            L.ptr(d_atmo), L.ptr(d_surf), float(z_scale), b, n, k, v, int(relu), L.ptr(dcolor), L.ptr(dsigma),
-           L.ptr(dcs), L.ptr(ddelta), L.stream())
+           L.ptr(dcs), L.ptr(ddelta), L.ptr(grad_absmax), L.stream())
     if not want_dz:
         return dcolor, dsigma, dcs
     # delta_i = hi_i - lo_i with hi_i = (z_i+z_{i+1})/2 (last: z_{N-1}), lo_i = (z_{i-1}+z_i)/2 (first: 0)

@@ -507,7 +507,7 @@ k_composite_bwd(const float* __restrict__ z, const float* __restrict__ color, co
                 const float* __restrict__ tsurf, const float* __restrict__ g_atmo,
                 const float* __restrict__ g_surf, float zs, int64_t B, int N, int relu,
                 float* __restrict__ dcolor, float* __restrict__ dsigma, float* __restrict__ dcolor_surf,
-                float* __restrict__ ddelta) {
+                float* __restrict__ ddelta, float* __restrict__ grad_absmax) {
   const int lane = threadIdx.x & 31;
   const int64_t ray = (blockIdx.x * (int64_t)blockDim.x + threadIdx.x) >> 5;
   if (ray >= B) return;
@@ -532,6 +532,7 @@ k_composite_bwd(const float* __restrict__ z, const float* __restrict__ color, co
       if (lane == 0 && dcolor_surf) dcolor_surf[ray * K + k] = (relu && !(raw > 0.0f)) ? 0.0f : gs[k] * S;
     }
   }
+  float amax = 0.0f;  // largest |gradient| written by this lane (for the fp16 scale of field_bwd_tc)
   for (int base = 0; base < N; base += 32) {
     const int i = base + lane;
     const bool in = i < N;
@@ -574,14 +575,23 @@ k_composite_bwd(const float* __restrict__ z, const float* __restrict__ color, co
       float ds = delta * core;
       dd += s * core;
       if (relu && !(raw > 0.0f)) ds = 0.0f;
-      if (in) dsigma[(ray * N + i) * V + v] = ds;
+      if (in) dsigma[(ray * N + i) * V + v] = ds, amax = fmaxf(amax, fabsf(ds));
     }
     if (in && ddelta) ddelta[ray * N + i] = dd;
     if (in) {
 #pragma unroll
-      for (int k = 0; k < K; ++k)
-        dcolor[(ray * N + i) * K + k] = (relu && !(craw[k] > 0.0f)) ? 0.0f : dc[k];
+      for (int k = 0; k < K; ++k) {
+        const float d = (relu && !(craw[k] > 0.0f)) ? 0.0f : dc[k];
+        dcolor[(ray * N + i) * K + k] = d;
+        amax = fmaxf(amax, fabsf(d));
+      }
     }
+  }
+  if (grad_absmax) {
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) amax = fmaxf(amax, __shfl_xor_sync(0xffffffffu, amax, o));
+    // non-negative floats order like their bit patterns
+    if (lane == 0 && amax > 0.0f && amax < INFINITY) atomicMax(reinterpret_cast<int*>(grad_absmax), __float_as_int(amax));
   }
 }
 
@@ -1126,7 +1136,8 @@ int atmonr_composite_fwd(const float* z, const float* color, const float* sigma,
 int atmonr_composite_bwd(const float* z, const float* color, const float* sigma, const float* color_surf,
                          const float* color_map_atmo, const float* trans_surf, const float* d_atmo,
                          const float* d_surf, float z_scale, int64_t B, int N, int K, int V, int relu,
-                         float* dcolor, float* dsigma, float* dcolor_surf, float* ddelta, void* stream) {
+                         float* dcolor, float* dsigma, float* dcolor_surf, float* ddelta, float* grad_absmax,
+                         void* stream) {
   if (B == 0) return 0;
   ATM_REQUIRE(color_map_atmo && d_atmo && dcolor && dsigma, "atmonr_composite_bwd", "null argument");
   ATM_REQUIRE(!color_surf || trans_surf, "atmonr_composite_bwd", "trans_surf required with a surface");
@@ -1134,7 +1145,7 @@ int atmonr_composite_bwd(const float* z, const float* color, const float* sigma,
 #define CALL(KK, VV)                                                                                         \
   k_composite_bwd<KK, VV><<<grid, 128, 0, S(stream)>>>(z, color, sigma, color_surf, color_map_atmo, trans_surf, \
                                                       d_atmo, d_surf, z_scale, B, N, relu, dcolor, dsigma,    \
-                                                      dcolor_surf, ddelta)
+                                                      dcolor_surf, ddelta, grad_absmax)
   ATM_KV_DISPATCH(K, V, CALL)
 #undef CALL
   ATM_CHECK_LAUNCH("atmonr_composite_bwd");

@@ -245,6 +245,262 @@ k_field_fwd_tc(atmonr_grid_t g, const __half2* __restrict__ table, const __half*
   if (warp == 0) tmem_dealloc<fwd::kTmemCols>(tmem);
 }
 
+
+// =========================================================================================
+// fused radiance field, backward
+// =========================================================================================
+namespace bwd {
+// shared-memory map (bytes); the 16-column tiles come first and a pad closes the map so that the
+// 128-row MN-major reads of the weight-gradient MMAs (which run past a 16/32-column tile) stay
+// inside the allocation.
+constexpr int kW = 0;                 // the five weight tiles, same order as fwd:: (8192 B)
+constexpr int kDO = 8192;             // dL/d(dir_mlp out)  [128][16]
+constexpr int kDP = kDO + 4096;       // dL/d(pos_mlp out)  [128][16]
+constexpr int kENC = kDP + 4096;      // activations [128][32] ...
+constexpr int kH = kENC + 8192;
+constexpr int kDIN = kH + 8192;
+constexpr int kH1 = kDIN + 8192;
+constexpr int kH2 = kH1 + 8192;
+constexpr int kDA = kH2 + 8192;       // delta tiles [128][32]
+constexpr int kDB = kDA + 8192;
+constexpr int kPad = kDB + 8192;
+constexpr int kBar = kPad + 2048;
+constexpr int kTmemPtr = kBar + 8;
+constexpr int kBytes = kTmemPtr + 8;
+constexpr uint32_t kTmemCols = 256;
+// TMEM columns
+constexpr int cAcc32 = 0, cAcc16 = 32, cDWd3 = 64, cDWd2 = 96, cDWd1 = 128, cDW2p = 160, cDW1p = 192;
+}  // namespace bwd
+
+// delta[128][KD] (K-major A) times W (read MN-major: rows = K = out, cols = N = in = 32) -> acc32
+template <int KD>
+__device__ __forceinline__ void issue_dinput(uint32_t acc, uint32_t d_tile, uint32_t w_tile) {
+  constexpr uint32_t idesc = make_idesc(128, 32, 0, 1);
+#pragma unroll
+  for (int k = 0; k < KD / 16; ++k)
+    umma_f16(acc, desc_k_major(d_tile + k * 2 * kCore, KD), desc_mn_major(w_tile + k * 2 * 4 * kCore, 32), idesc, k);
+}
+// dW[o][i] += sum_s delta[s][o] * act[s][i]: both tiles read MN-major, K = 128 samples
+template <int KD>
+__device__ __forceinline__ void issue_dweight(uint32_t acc, uint32_t d_tile, uint32_t a_tile, uint32_t accumulate) {
+  constexpr uint32_t idesc = make_idesc(128, 32, 1, 1);
+#pragma unroll
+  for (int k = 0; k < 8; ++k)
+    umma_f16(acc, desc_mn_major(d_tile + k * 2 * (KD / 8) * kCore, KD), desc_mn_major(a_tile + k * 2 * 4 * kCore, 32),
+             idesc, accumulate | (uint32_t)(k > 0));
+}
+
+// zero the entries of v whose activation (this thread's row of `tile`) is not positive
+__device__ __forceinline__ void relu_mask_row(const uint8_t* tile, int r, float (&v)[32]) {
+#pragma unroll
+  for (int cc = 0; cc < 4; ++cc) {
+    const uint4 q = ld_chunk(tile, r, cc, 32);
+    const __half2* h = reinterpret_cast<const __half2*>(&q);
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      const float2 f = __half22float2(h[j]);
+      if (!(f.x > 0.0f)) v[cc * 8 + 2 * j] = 0.0f;
+      if (!(f.y > 0.0f)) v[cc * 8 + 2 * j + 1] = 0.0f;
+    }
+  }
+}
+
+__device__ __forceinline__ void store_row16(uint8_t* tile, int r, const float (&v)[16]) {
+#pragma unroll
+  for (int cc = 0; cc < 2; ++cc) {
+    uint4 q;
+    uint32_t* qp = reinterpret_cast<uint32_t*>(&q);
+#pragma unroll
+    for (int j = 0; j < 4; ++j) qp[j] = pack_h2(v[cc * 8 + 2 * j], v[cc * 8 + 2 * j + 1]);
+    st_chunk(tile, r, cc, 16, q);
+  }
+}
+
+__global__ void __launch_bounds__(128, 2)
+k_field_bwd_tc(atmonr_grid_t g, const __half2* __restrict__ table, const __half* __restrict__ pos_w,
+               const __half* __restrict__ dir_w, const float* __restrict__ x01, const float* __restrict__ dirs,
+               const __half* __restrict__ enc_in, const float* __restrict__ dsigma_raw,
+               const float* __restrict__ dcolor_raw, const float* __restrict__ grad_absmax, int64_t M, int N,
+               float* __restrict__ dtable, float* __restrict__ dpos_w, float* __restrict__ ddir_w) {
+  extern __shared__ __align__(128) uint8_t smem[];
+  uint64_t* bar = reinterpret_cast<uint64_t*>(smem + bwd::kBar);
+  uint32_t* tmem_ptr = reinterpret_cast<uint32_t*>(smem + bwd::kTmemPtr);
+  const int tid = threadIdx.x, warp = tid >> 5;
+  // the pad is read (as don't-care rows) by the weight-gradient MMAs: keep it finite
+  for (int i = tid; i < 2048 / 16; i += 128) reinterpret_cast<uint4*>(smem + bwd::kPad)[i] = make_uint4(0, 0, 0, 0);
+  load_field_weights(smem + bwd::kW, pos_w, dir_w);
+  if (warp == 0) tmem_alloc<bwd::kTmemCols>(tmem_ptr);
+  if (tid == 0) {
+    mbar_init(bar, 1);
+    fence_mbar_init();
+  }
+  publish_and_sync();
+  tc_fence_after();
+  const uint32_t tmem = *tmem_ptr;
+  const uint32_t my32 = tmem_addr(tmem, warp, bwd::cAcc32), my16 = tmem_addr(tmem, warp, bwd::cAcc16);
+  const uint32_t sb = smem_u32(smem);
+  // power-of-two scale that lifts the incoming gradients into fp16 range
+  float S = 1.0f;
+  if (grad_absmax) {
+    const float amax = *grad_absmax;
+    if (amax > 0.0f && amax < INFINITY) S = exp2f(fminf(fmaxf(floorf(log2f(2048.0f / amax)), -60.0f), 60.0f));
+  }
+  const float invS = 1.0f / S;
+  uint32_t phase = 0, seen_tile = 0;
+
+  for (int64_t tile = blockIdx.x; tile * kTile < M; tile += gridDim.x, seen_tile = 1) {
+    const int64_t i = tile * kTile + tid;
+    const bool valid = i < M;
+    const int64_t j = valid ? i : M - 1;
+    const float p[3] = {x01[3 * j], x01[3 * j + 1], x01[3 * j + 2]};
+    // ---------------- recompute the activations ----------------
+    if (enc_in) {
+      const uint4* src = reinterpret_cast<const uint4*>(enc_in + j * 32);
+#pragma unroll
+      for (int cc = 0; cc < 4; ++cc) st_chunk(smem + bwd::kENC, tid, cc, 32, src[cc]);
+    } else {
+      __half2 enc[16];
+      hash_encode_fast<3>(g, table, p, enc);
+      store_row32_h2(smem + bwd::kENC, tid, enc);
+    }
+    publish_and_sync();
+    if (tid == 0) issue_layer<32>(tmem + bwd::cAcc32, sb + bwd::kENC, sb + bwd::kW + fwd::kW1P, bar);
+    mbar_wait(bar, phase), phase ^= 1;
+    tc_fence_after();
+    float v[32];
+    tmem_ld32(my32, v);
+    store_row32<true>(smem + bwd::kH, tid, v);
+    publish_and_sync();
+    if (tid == 0) issue_layer<16>(tmem + bwd::cAcc16, sb + bwd::kH, sb + bwd::kW + fwd::kW2P, bar);
+    mbar_wait(bar, phase), phase ^= 1;
+    tc_fence_after();
+    {
+      float po[16];
+      tmem_ld16(my16, po);
+      dir_input_row(dirs + (j / N) * 3, po, v);
+    }
+    store_row32<false>(smem + bwd::kDIN, tid, v);
+    publish_and_sync();
+    if (tid == 0) issue_layer<32>(tmem + bwd::cAcc32, sb + bwd::kDIN, sb + bwd::kW + fwd::kWD1, bar);
+    mbar_wait(bar, phase), phase ^= 1;
+    tc_fence_after();
+    tmem_ld32(my32, v);
+    store_row32<true>(smem + bwd::kH1, tid, v);
+    publish_and_sync();
+    if (tid == 0) issue_layer<32>(tmem + bwd::cAcc32, sb + bwd::kH1, sb + bwd::kW + fwd::kWD2, bar);
+    mbar_wait(bar, phase), phase ^= 1;
+    tc_fence_after();
+    tmem_ld32(my32, v);
+    store_row32<true>(smem + bwd::kH2, tid, v);
+    // ---------------- backward ----------------
+    {
+      float dout[16];
+#pragma unroll
+      for (int k = 0; k < 16; ++k) dout[k] = 0.0f;
+      if (valid) {
+        const float4 dc = *reinterpret_cast<const float4*>(dcolor_raw + 4 * i);
+        dout[0] = dc.x * S, dout[1] = dc.y * S, dout[2] = dc.z * S, dout[3] = dc.w * S;
+      }
+      store_row16(smem + bwd::kDO, tid, dout);
+    }
+    publish_and_sync();
+    if (tid == 0) {
+      tc_fence_after();
+      issue_dinput<16>(tmem + bwd::cAcc32, sb + bwd::kDO, sb + bwd::kW + fwd::kWD3);
+      issue_dweight<16>(tmem + bwd::cDWd3, sb + bwd::kDO, sb + bwd::kH2, seen_tile);
+      umma_commit(bar);
+    }
+    mbar_wait(bar, phase), phase ^= 1;
+    tc_fence_after();
+    tmem_ld32(my32, v);
+    relu_mask_row(smem + bwd::kH2, tid, v);
+    store_row32<false>(smem + bwd::kDA, tid, v);
+    publish_and_sync();
+    if (tid == 0) {
+      tc_fence_after();
+      issue_dinput<32>(tmem + bwd::cAcc32, sb + bwd::kDA, sb + bwd::kW + fwd::kWD2);
+      issue_dweight<32>(tmem + bwd::cDWd2, sb + bwd::kDA, sb + bwd::kH1, seen_tile);
+      umma_commit(bar);
+    }
+    mbar_wait(bar, phase), phase ^= 1;
+    tc_fence_after();
+    tmem_ld32(my32, v);
+    relu_mask_row(smem + bwd::kH1, tid, v);
+    store_row32<false>(smem + bwd::kDB, tid, v);
+    publish_and_sync();
+    if (tid == 0) {
+      tc_fence_after();
+      issue_dinput<32>(tmem + bwd::cAcc32, sb + bwd::kDB, sb + bwd::kW + fwd::kWD1);
+      issue_dweight<32>(tmem + bwd::cDWd1, sb + bwd::kDB, sb + bwd::kDIN, seen_tile);
+      umma_commit(bar);
+    }
+    mbar_wait(bar, phase), phase ^= 1;
+    tc_fence_after();
+    tmem_ld32(my32, v);   // dL/d(dir_mlp input): columns 4..18 are the pos_mlp features
+    {
+      float dpo[16];
+      dpo[0] = valid ? dsigma_raw[i] * S : 0.0f;
+#pragma unroll
+      for (int k = 1; k < 16; ++k) dpo[k] = v[3 + k];
+      store_row16(smem + bwd::kDP, tid, dpo);
+    }
+    publish_and_sync();
+    if (tid == 0) {
+      tc_fence_after();
+      issue_dinput<16>(tmem + bwd::cAcc32, sb + bwd::kDP, sb + bwd::kW + fwd::kW2P);
+      issue_dweight<16>(tmem + bwd::cDW2p, sb + bwd::kDP, sb + bwd::kH, seen_tile);
+      umma_commit(bar);
+    }
+    mbar_wait(bar, phase), phase ^= 1;
+    tc_fence_after();
+    tmem_ld32(my32, v);
+    relu_mask_row(smem + bwd::kH, tid, v);
+    store_row32<false>(smem + bwd::kDA, tid, v);
+    publish_and_sync();
+    if (tid == 0) {
+      tc_fence_after();
+      issue_dinput<32>(tmem + bwd::cAcc32, sb + bwd::kDA, sb + bwd::kW + fwd::kW1P);
+      issue_dweight<32>(tmem + bwd::cDW1p, sb + bwd::kDA, sb + bwd::kENC, seen_tile);
+      umma_commit(bar);
+    }
+    mbar_wait(bar, phase), phase ^= 1;
+    tc_fence_after();
+    tmem_ld32(my32, v);   // dL/d(encoded features), scaled by S
+    if (valid) hash_scatter_fast<3>(g, dtable, p, v, invS);
+  }
+
+  // ---------------- flush the weight gradients (TMEM lanes = output neuron) ----------------
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  if (warp == 0 && seen_tile) {
+    const int o = tid;  // lane = row of the weight matrix
+    float w[32];
+    tmem_ld32(tmem_addr(tmem, 0, bwd::cDW1p), w);
+#pragma unroll
+    for (int c = 0; c < 32; ++c) atomicAdd(dpos_w + o * 32 + c, w[c] * invS);
+    tmem_ld32(tmem_addr(tmem, 0, bwd::cDW2p), w);
+    if (o < 16) {
+#pragma unroll
+      for (int c = 0; c < 32; ++c) atomicAdd(dpos_w + 1024 + o * 32 + c, w[c] * invS);
+    }
+    tmem_ld32(tmem_addr(tmem, 0, bwd::cDWd1), w);
+#pragma unroll
+    for (int c = 0; c < 32; ++c) atomicAdd(ddir_w + o * 32 + c, w[c] * invS);
+    tmem_ld32(tmem_addr(tmem, 0, bwd::cDWd2), w);
+#pragma unroll
+    for (int c = 0; c < 32; ++c) atomicAdd(ddir_w + 1024 + o * 32 + c, w[c] * invS);
+    tmem_ld32(tmem_addr(tmem, 0, bwd::cDWd3), w);
+    if (o < 16) {
+#pragma unroll
+      for (int c = 0; c < 32; ++c) atomicAdd(ddir_w + 2048 + o * 32 + c, w[c] * invS);
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 0) tmem_dealloc<bwd::kTmemCols>(tmem);
+}
+
 }  // namespace atm
 
 using namespace atm;
@@ -292,6 +548,28 @@ int atmonr_ngp_field_fwd_tc(const atmonr_grid_t* g, const void* table, const atm
       *g, (const __half2*)table, (const __half*)pos_w, (const __half*)dir_w, x01, dirs, M, N, sigma_raw, color_raw,
       (__half*)enc_out);
   ATM_CHECK_LAUNCH("atmonr_ngp_field_fwd_tc");
+  return 0;
+}
+
+
+// Same contract as atmonr_ngp_field_bwd. enc (optional): features saved by the forward pass;
+// grad_absmax (optional device scalar): max |incoming gradient|, sets the fp16 operand scale.
+int atmonr_ngp_field_bwd_tc(const atmonr_grid_t* g, const void* table, const atmonr_mlp_t* pm, const void* pos_w,
+                            const atmonr_mlp_t* dm, const void* dir_w, const float* x01, const float* dirs,
+                            const void* enc, const float* dsigma_raw, const float* dcolor_raw,
+                            const float* grad_absmax, int64_t B, int N, float* dtable, float* dpos_w, float* ddir_w,
+                            void* stream) {
+  if (check_field_shapes(g, pm, dm, "atmonr_ngp_field_bwd_tc")) return -1;
+  const int64_t M = B * N;
+  if (M == 0) return 0;
+  cudaError_t e = cudaFuncSetAttribute(k_field_bwd_tc, cudaFuncAttributeMaxDynamicSharedMemorySize, bwd::kBytes);
+  if (e != cudaSuccess) return fail("atmonr_ngp_field_bwd_tc", cudaGetErrorString(e));
+  const int64_t tiles = (M + kTile - 1) / kTile;
+  const int grid = (int)(tiles < (int64_t)tc_num_sms() * 2 ? tiles : (int64_t)tc_num_sms() * 2);
+  k_field_bwd_tc<<<grid, kTile, bwd::kBytes, reinterpret_cast<cudaStream_t>(stream)>>>(
+      *g, (const __half2*)table, (const __half*)pos_w, (const __half*)dir_w, x01, dirs, (const __half*)enc, dsigma_raw,
+      dcolor_raw, grad_absmax, M, N, dtable, dpos_w, ddir_w);
+  ATM_CHECK_LAUNCH("atmonr_ngp_field_bwd_tc");
   return 0;
 }
 

@@ -134,6 +134,13 @@ int atmonr_ngp_field_fwd_tc(const atmonr_grid_t* grid_host, const void* table_f1
                             const atmonr_mlp_t* dir_mlp_host, const void* dir_w_f16,
                             const float* x01, const float* dirs, int64_t B, int N,
                             float* sigma_raw, float* color_raw, void* enc_f16, void* stream);
+int atmonr_ngp_field_bwd_tc(const atmonr_grid_t* grid_host, const void* table_f16,
+                            const atmonr_mlp_t* pos_mlp_host, const void* pos_w_f16,
+                            const atmonr_mlp_t* dir_mlp_host, const void* dir_w_f16,
+                            const float* x01, const float* dirs, const void* enc_f16,
+                            const float* dsigma_raw, const float* dcolor_raw,
+                            const float* grad_absmax, int64_t B, int N, float* dtable,
+                            float* dpos_w, float* ddir_w, void* stream);
 
 /* ---- surface branch, per ray: [hash2d(pts_surf.xy) | SH2(dir)] -> surf_mlp ----------------
  * instant_ngp.py:140,150,173-174. color_surf_raw (B,4) pre-ReLU. */
@@ -160,12 +167,14 @@ int atmonr_composite_fwd(const float* z, const float* color, const float* sigma,
 /* Backward given dL/dcolor_map_atmo (B,K) and dL/dcolor_map_surf (B,K). Produces dcolor
  * (B,N,K), dsigma (B,N,V) and dcolor_surf (B,K) w.r.t. the RAW inputs when relu != 0, and
  * optionally ddelta (B,N) = dL/d(Voronoi cell width in km) for callers that differentiate
- * through the sample distances (NeRF fine pass, samplers.py:96 keeps that path alive). */
+ * through the sample distances (NeRF fine pass, samplers.py:96 keeps that path alive), and
+ * optionally grad_absmax (1 float, zero-initialised by the caller) = max |dcolor|, |dsigma|. */
 int atmonr_composite_bwd(const float* z, const float* color, const float* sigma,
                          const float* color_surf, const float* color_map_atmo,
                          const float* trans_surf, const float* d_atmo, const float* d_surf,
                          float z_scale, int64_t B, int N, int K, int V, int relu, float* dcolor,
-                         float* dsigma, float* dcolor_surf, float* ddelta, void* stream);
+                         float* dsigma, float* dcolor_surf, float* ddelta, float* grad_absmax,
+                         void* stream);
 
 /* ---- per-band loss and its gradient (instant_ngp.py:249-263, losses.py:5-33) ---------------
  * kind: 0 dark, 1 hdr, 2 l1, 3 l1_plus_hdr, 4 mse, 5 mse_plus_hdr. color_map (B,K); band

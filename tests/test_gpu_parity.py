@@ -245,7 +245,12 @@ def _pipeline(scene, cfg):
     return pipe
 
 
-def test_ngp_pipeline_forward_loss_gradients_vs_oracle(scene):
+@pytest.mark.parametrize("impl", ["tc", "simt"])
+def test_ngp_pipeline_forward_loss_gradients_vs_oracle(scene, impl, monkeypatch):
+    """impl = tc: dense layers on tcgen05 (fp16 gradient operands under a power-of-two scale);
+    impl = simt: thread-per-sample FMA kernels (fp32 gradients)."""
+    from atmonr.native import fused
+    monkeypatch.setattr(fused, "FIELD_IMPL", impl)
     cfg = ngp_config(64)
     orc16 = NGPOracle(cfg, scene.frame, scene.max_i, fp16=True)
     orc32 = NGPOracle(cfg, scene.frame, scene.max_i, fp16=False)
@@ -269,9 +274,11 @@ def test_ngp_pipeline_forward_loss_gradients_vs_oracle(scene):
     assert rel_err(lg, loss) < 1e-3
     for key in ("weights_fine", "sigma_fine", "color_fine", "z_vals_fine", "color_surf"):
         assert rel_err(out[key], res[key]) < 2e-3, key
+    # tc: every gradient operand of the MLP backward is rounded to fp16 (relative 2^-11) once
+    grad_tol = 2e-3 if impl == "simt" else 4e-3
     for name in ("pos_mlp", "dir_mlp", "surf_mlp", "pos_encoder", "surf_encoder"):
         got = getattr(pipe, name).params.grad
-        assert rel_err(got, params[name].grad) < 2e-3, name
+        assert rel_err(got, params[name].grad) < grad_tol, name
     # modular (operator-by-operator) path agrees with the fused path
     pipe.fused_state = None
     out_m = pipe.forward(bc, u=u.cuda())
