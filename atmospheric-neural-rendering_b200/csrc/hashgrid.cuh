@@ -149,6 +149,126 @@ __device__ __forceinline__ void hash_scatter_fast(const atmonr_grid_t& g, float*
   }
 }
 
+// ---- rolled-loop variants (small code footprint) ------------------------------------------------
+// The fully unrolled 16-level loops above cost 100+ KB of SASS per kernel and make the fused
+// kernels instruction-fetch bound. These variants keep the level loop rolled: per-level constants
+// come from a shared-memory copy of the level table (dynamic index), features are written straight
+// into the activation tile / read straight from TMEM instead of living in a register array.
+// rare path of the index reduction (coordinates outside [0,1]); kept out of line on purpose
+static __device__ __noinline__ uint32_t index_mod_slow(uint32_t idx, uint32_t size) { return idx % size; }
+
+struct LevelRow {
+  float scale;
+  uint32_t res, size, offset, hashed;  // hashed: bit0 = level hashes, bit1 = size is a power of two
+  uint32_t stride1, stride2, pad;      // res, res*res (dense index strides)
+};
+
+__device__ __forceinline__ void load_level_table(const atmonr_grid_t& g, LevelRow* rows) {
+  if (threadIdx.x < ATMONR_MAX_LEVELS) {
+    const int l = threadIdx.x;
+    LevelRow r;
+    r.scale = g.scale[l];
+    r.res = g.res[l];
+    r.size = g.size[l];
+    r.offset = g.offset[l];
+    uint64_t dense = 1;
+    for (int k = 0; k < g.n_dims; ++k) dense *= r.res;
+    r.hashed = (dense > (uint64_t)r.size ? 1u : 0u) | (((r.size & (r.size - 1u)) == 0u) ? 2u : 0u);
+    r.stride1 = r.res;
+    r.stride2 = r.res * r.res;
+    r.pad = 0;
+    rows[l] = r;
+  }
+}
+
+// corner entries + weights of one level from a LevelRow (3-D); bit-identical to level_corners<3>
+__device__ __forceinline__ void level_corners3(const LevelRow& lv, const float (&x)[3], uint32_t (&e)[8],
+                                               float (&w)[8], uint32_t (&cell)[3]) {
+  float frac[3];
+  grid_cell<3>(x, lv.scale, cell, frac);
+  const bool hashed = lv.hashed & 1u;
+  uint32_t t0[3], t1[3];
+  if (hashed) {
+    t0[0] = cell[0], t1[0] = cell[0] + 1u;
+    t0[1] = cell[1] * 2654435761u, t1[1] = t0[1] + 2654435761u;
+    t0[2] = cell[2] * 805459861u, t1[2] = t0[2] + 805459861u;
+  } else {
+    t0[0] = cell[0], t1[0] = cell[0] + 1u;
+    t0[1] = cell[1] * lv.stride1, t1[1] = t0[1] + lv.stride1;
+    t0[2] = cell[2] * lv.stride2, t1[2] = t0[2] + lv.stride2;
+  }
+  const float wx[2] = {1.0f - frac[0], frac[0]};
+  const float wy[2] = {1.0f - frac[1], frac[1]};
+  const float wz[2] = {1.0f - frac[2], frac[2]};
+  const uint32_t mask = lv.size - 1u;
+  const bool fast_hash = lv.hashed == 3u;
+#pragma unroll
+  for (int c = 0; c < 8; ++c) {
+    const int ix = c & 1, iy = (c >> 1) & 1, iz = c >> 2;
+    const uint32_t a = ix ? t1[0] : t0[0], b = iy ? t1[1] : t0[1], d = iz ? t1[2] : t0[2];
+    uint32_t idx = hashed ? (a ^ b ^ d) : (a + b + d);
+    if (fast_hash) {
+      idx &= mask;
+    } else if (idx >= lv.size) {
+      idx = (idx - lv.size < lv.size) ? idx - lv.size : index_mod_slow(idx, lv.size);
+    }
+    e[c] = idx;
+    w[c] = (wx[ix] * wy[iy]) * wz[iz];
+  }
+}
+
+__device__ __forceinline__ void level_corners3(const LevelRow& lv, const float (&x)[3], uint32_t (&e)[8],
+                                               float (&w)[8]) {
+  uint32_t cell[3];
+  level_corners3(lv, x, e, w, cell);
+}
+
+// Warp-aggregated scatter of one level. The 32 lanes of a warp hold consecutive samples of a ray,
+// so lanes that fall into the same grid cell form contiguous runs; the 8 corner contributions
+// (2 features each) of a run are summed with a segmented shuffle reduction and written by the
+// run's first lane with one vector RED per corner. When the warp has little duplication the
+// plain per-lane REDs are cheaper and are used instead. Must be called by all 32 lanes.
+__device__ __forceinline__ void scatter_level_aggregated(const LevelRow& lv, float* __restrict__ dtable,
+                                                         const float (&x)[3], float d0, float d1, bool valid) {
+  constexpr uint32_t full = 0xffffffffu;
+  const int lane = threadIdx.x & 31;
+  uint32_t e[8], cell[3];
+  float w[8];
+  level_corners3(lv, x, e, w, cell);
+  if (!valid) d0 = 0.0f, d1 = 0.0f;
+  const uint32_t p0 = __shfl_up_sync(full, cell[0], 1), p1 = __shfl_up_sync(full, cell[1], 1),
+                 p2 = __shfl_up_sync(full, cell[2], 1);
+  const bool head = lane == 0 || p0 != cell[0] || p1 != cell[1] || p2 != cell[2];
+  const uint32_t heads = __ballot_sync(full, head);
+  float* base = dtable + 2 * (size_t)lv.offset;
+  if (__popc(heads) > 16) {  // mostly distinct cells: no gain from aggregation
+    if (d0 != 0.0f || d1 != 0.0f) {
+#pragma unroll
+      for (int c = 0; c < 8; ++c) red_add_f32x2(base + 2 * (size_t)e[c], w[c] * d0, w[c] * d1);
+    }
+    return;
+  }
+  const uint32_t above = lane == 31 ? 0u : (heads & ~((2u << lane) - 1u));
+  const int run_end = above ? (__ffs(above) - 2) : 31;
+  float v[16];
+#pragma unroll
+  for (int c = 0; c < 8; ++c) v[2 * c] = w[c] * d0, v[2 * c + 1] = w[c] * d1;
+#pragma unroll
+  for (int o = 1; o < 32; o <<= 1) {
+    const bool take = lane + o <= run_end;
+#pragma unroll
+    for (int i = 0; i < 16; ++i) {
+      const float t = __shfl_down_sync(full, v[i], o);
+      if (take) v[i] += t;
+    }
+  }
+  if (head) {
+#pragma unroll
+    for (int c = 0; c < 8; ++c)
+      if (v[2 * c] != 0.0f || v[2 * c + 1] != 0.0f) red_add_f32x2(base + 2 * (size_t)e[c], v[2 * c], v[2 * c + 1]);
+  }
+}
+
 // Scatter dL/d(features) of one point into the fp32 gradient table.
 template <int D>
 __device__ __forceinline__ void hash_scatter(const atmonr_grid_t& g, float* __restrict__ dtable,

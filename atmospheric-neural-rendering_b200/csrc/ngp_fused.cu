@@ -89,7 +89,8 @@ constexpr int kWD2 = kWD1 + 2048;   // dir_mlp layer 1  [32][32]
 constexpr int kWD3 = kWD2 + 2048;   // dir_mlp output   [16][32]
 constexpr int kA0 = kWD3 + 1024;    // activation tile  [128][32]
 constexpr int kA1 = kA0 + 8192;     // activation tile  [128][32]
-constexpr int kBar = kA1 + 8192;
+constexpr int kLv = kA1 + 8192;     // level table, 16 x 32 B
+constexpr int kBar = kLv + 512;
 constexpr int kTmemPtr = kBar + 8;
 constexpr int kBytes = kTmemPtr + 8;
 constexpr uint32_t kTmemCols = 64;  // [0,32): hidden accumulator, [32,48): 16-wide outputs
@@ -132,6 +133,30 @@ __device__ __forceinline__ void store_row32_h2(uint8_t* tile, int r, const __hal
   }
 }
 
+// Hash-grid encoding of one point written straight into row r of an activation tile (rolled level
+// loop, see hashgrid.cuh). Same arithmetic as hash_encode().
+__device__ __forceinline__ void encode_to_tile(const LevelRow* __restrict__ lv, const __half2* __restrict__ table,
+                                               const float (&p)[3], uint8_t* tile, int r) {
+#pragma unroll 4
+  for (int l = 0; l < ATMONR_MAX_LEVELS; ++l) {
+    uint32_t e[8];
+    float w[8];
+    level_corners3(lv[l], p, e, w);
+    const __half2* base = table + lv[l].offset;
+    __half2 v[8];
+#pragma unroll
+    for (int c = 0; c < 8; ++c) v[c] = __ldg(base + e[c]);
+    float a0 = 0.0f, a1 = 0.0f;
+#pragma unroll
+    for (int c = 0; c < 8; ++c) {
+      const float2 f = __half22float2(v[c]);
+      a0 = fmaf(w[c], f.x, a0);
+      a1 = fmaf(w[c], f.y, a1);
+    }
+    *reinterpret_cast<uint32_t*>(tile + tile_off(r, 2 * l, 32)) = pack_h2(a0, a1);
+  }
+}
+
 // dir_mlp input row: [SH2(dir) | pos_out[1..15] | 1.0 x 13] (instant_ngp.py:165-169 + tcnn padding)
 __device__ __forceinline__ void dir_input_row(const float* __restrict__ dir, const float (&po)[16], float (&v)[32]) {
   float sh[4];
@@ -163,7 +188,7 @@ __device__ __forceinline__ void publish_and_sync() {
   __syncthreads();
 }
 
-__global__ void __launch_bounds__(128, 4)
+__global__ void __launch_bounds__(128, 8)
 k_field_fwd_tc(atmonr_grid_t g, const __half2* __restrict__ table, const __half* __restrict__ pos_w,
                const __half* __restrict__ dir_w, const float* __restrict__ x01, const float* __restrict__ dirs,
                int64_t M, int N, float* __restrict__ sigma_raw, float* __restrict__ color_raw,
@@ -172,6 +197,8 @@ k_field_fwd_tc(atmonr_grid_t g, const __half2* __restrict__ table, const __half*
   uint64_t* bar = reinterpret_cast<uint64_t*>(smem + fwd::kBar);
   uint32_t* tmem_ptr = reinterpret_cast<uint32_t*>(smem + fwd::kTmemPtr);
   const int tid = threadIdx.x, warp = tid >> 5;
+  LevelRow* lv = reinterpret_cast<LevelRow*>(smem + fwd::kLv);
+  load_level_table(g, lv);
   load_field_weights(smem, pos_w, dir_w);
   if (warp == 0) tmem_alloc<fwd::kTmemCols>(tmem_ptr);
   if (tid == 0) {
@@ -195,9 +222,7 @@ k_field_fwd_tc(atmonr_grid_t g, const __half2* __restrict__ table, const __half*
     // ---- hash-grid encoding -> A0
     {
       const float p[3] = {x01[3 * j], x01[3 * j + 1], x01[3 * j + 2]};
-      __half2 enc[16];
-      hash_encode_fast<3>(g, table, p, enc);
-      store_row32_h2(A0, tid, enc);
+      encode_to_tile(lv, table, p, A0, tid);
       if (enc_out && valid) {
         uint4* dst = reinterpret_cast<uint4*>(enc_out + i * 32);
 #pragma unroll
@@ -218,7 +243,7 @@ k_field_fwd_tc(atmonr_grid_t g, const __half2* __restrict__ table, const __half*
     float po[16];
     tmem_ld16(my16, po);
     if (valid) sigma_raw[i] = po[0];
-    dir_input_row(dirs + (j / N) * 3, po, v);
+    dir_input_row(dirs + (size_t)((uint32_t)j / (uint32_t)N) * 3, po, v);
     store_row32<false>(A0, tid, v);
     publish_and_sync();
     if (tid == 0) issue_layer<32>(acc32, sbase + fwd::kA0, sbase + fwd::kWD1, bar);
@@ -264,8 +289,10 @@ constexpr int kH2 = kH1 + 8192;
 constexpr int kDA = kH2 + 8192;       // delta tiles [128][32]
 constexpr int kDB = kDA + 8192;
 constexpr int kPad = kDB + 8192;
-constexpr int kBar = kPad + 2048;
-constexpr int kTmemPtr = kBar + 8;
+constexpr int kLv = kPad + 2048;      // level table
+constexpr int kBar = kLv + 512;
+constexpr int kBar2 = kBar + 8;
+constexpr int kTmemPtr = kBar2 + 8;
 constexpr int kBytes = kTmemPtr + 8;
 constexpr uint32_t kTmemCols = 256;
 // TMEM columns
@@ -324,20 +351,25 @@ k_field_bwd_tc(atmonr_grid_t g, const __half2* __restrict__ table, const __half*
                float* __restrict__ dtable, float* __restrict__ dpos_w, float* __restrict__ ddir_w) {
   extern __shared__ __align__(128) uint8_t smem[];
   uint64_t* bar = reinterpret_cast<uint64_t*>(smem + bwd::kBar);
+  uint64_t* bar2 = reinterpret_cast<uint64_t*>(smem + bwd::kBar2);
   uint32_t* tmem_ptr = reinterpret_cast<uint32_t*>(smem + bwd::kTmemPtr);
   const int tid = threadIdx.x, warp = tid >> 5;
+  LevelRow* lv = reinterpret_cast<LevelRow*>(smem + bwd::kLv);
+  load_level_table(g, lv);
   // the pad is read (as don't-care rows) by the weight-gradient MMAs: keep it finite
   for (int i = tid; i < 2048 / 16; i += 128) reinterpret_cast<uint4*>(smem + bwd::kPad)[i] = make_uint4(0, 0, 0, 0);
   load_field_weights(smem + bwd::kW, pos_w, dir_w);
   if (warp == 0) tmem_alloc<bwd::kTmemCols>(tmem_ptr);
   if (tid == 0) {
     mbar_init(bar, 1);
+    mbar_init(bar2, 1);
     fence_mbar_init();
   }
   publish_and_sync();
   tc_fence_after();
   const uint32_t tmem = *tmem_ptr;
   const uint32_t my32 = tmem_addr(tmem, warp, bwd::cAcc32), my16 = tmem_addr(tmem, warp, bwd::cAcc16);
+  uint32_t phase2 = 0;
   const uint32_t sb = smem_u32(smem);
   // power-of-two scale that lifts the incoming gradients into fp16 range
   float S = 1.0f;
@@ -353,15 +385,15 @@ k_field_bwd_tc(atmonr_grid_t g, const __half2* __restrict__ table, const __half*
     const bool valid = i < M;
     const int64_t j = valid ? i : M - 1;
     const float p[3] = {x01[3 * j], x01[3 * j + 1], x01[3 * j + 2]};
+    // the previous tile's weight-gradient MMAs still read its buffers: wait before overwriting
+    if (seen_tile) mbar_wait(bar2, phase2), phase2 ^= 1;
     // ---------------- recompute the activations ----------------
     if (enc_in) {
       const uint4* src = reinterpret_cast<const uint4*>(enc_in + j * 32);
 #pragma unroll
       for (int cc = 0; cc < 4; ++cc) st_chunk(smem + bwd::kENC, tid, cc, 32, src[cc]);
     } else {
-      __half2 enc[16];
-      hash_encode_fast<3>(g, table, p, enc);
-      store_row32_h2(smem + bwd::kENC, tid, enc);
+      encode_to_tile(lv, table, p, smem + bwd::kENC, tid);
     }
     publish_and_sync();
     if (tid == 0) issue_layer<32>(tmem + bwd::cAcc32, sb + bwd::kENC, sb + bwd::kW + fwd::kW1P, bar);
@@ -377,7 +409,7 @@ k_field_bwd_tc(atmonr_grid_t g, const __half2* __restrict__ table, const __half*
     {
       float po[16];
       tmem_ld16(my16, po);
-      dir_input_row(dirs + (j / N) * 3, po, v);
+      dir_input_row(dirs + (size_t)((uint32_t)j / (uint32_t)N) * 3, po, v);
     }
     store_row32<false>(smem + bwd::kDIN, tid, v);
     publish_and_sync();
@@ -407,8 +439,8 @@ k_field_bwd_tc(atmonr_grid_t g, const __half2* __restrict__ table, const __half*
     if (tid == 0) {
       tc_fence_after();
       issue_dinput<16>(tmem + bwd::cAcc32, sb + bwd::kDO, sb + bwd::kW + fwd::kWD3);
-      issue_dweight<16>(tmem + bwd::cDWd3, sb + bwd::kDO, sb + bwd::kH2, seen_tile);
-      umma_commit(bar);
+      umma_commit(bar);  // the next epilogue only waits for the input gradient ...
+      issue_dweight<16>(tmem + bwd::cDWd3, sb + bwd::kDO, sb + bwd::kH2, seen_tile);  // ... this overlaps it
     }
     mbar_wait(bar, phase), phase ^= 1;
     tc_fence_after();
@@ -419,8 +451,8 @@ k_field_bwd_tc(atmonr_grid_t g, const __half2* __restrict__ table, const __half*
     if (tid == 0) {
       tc_fence_after();
       issue_dinput<32>(tmem + bwd::cAcc32, sb + bwd::kDA, sb + bwd::kW + fwd::kWD2);
-      issue_dweight<32>(tmem + bwd::cDWd2, sb + bwd::kDA, sb + bwd::kH1, seen_tile);
-      umma_commit(bar);
+      umma_commit(bar);  // the next epilogue only waits for the input gradient ...
+      issue_dweight<32>(tmem + bwd::cDWd2, sb + bwd::kDA, sb + bwd::kH1, seen_tile);  // ... this overlaps it
     }
     mbar_wait(bar, phase), phase ^= 1;
     tc_fence_after();
@@ -431,8 +463,8 @@ k_field_bwd_tc(atmonr_grid_t g, const __half2* __restrict__ table, const __half*
     if (tid == 0) {
       tc_fence_after();
       issue_dinput<32>(tmem + bwd::cAcc32, sb + bwd::kDB, sb + bwd::kW + fwd::kWD1);
-      issue_dweight<32>(tmem + bwd::cDWd1, sb + bwd::kDB, sb + bwd::kDIN, seen_tile);
-      umma_commit(bar);
+      umma_commit(bar);  // the next epilogue only waits for the input gradient ...
+      issue_dweight<32>(tmem + bwd::cDWd1, sb + bwd::kDB, sb + bwd::kDIN, seen_tile);  // ... this overlaps it
     }
     mbar_wait(bar, phase), phase ^= 1;
     tc_fence_after();
@@ -448,8 +480,8 @@ k_field_bwd_tc(atmonr_grid_t g, const __half2* __restrict__ table, const __half*
     if (tid == 0) {
       tc_fence_after();
       issue_dinput<16>(tmem + bwd::cAcc32, sb + bwd::kDP, sb + bwd::kW + fwd::kW2P);
-      issue_dweight<16>(tmem + bwd::cDW2p, sb + bwd::kDP, sb + bwd::kH, seen_tile);
-      umma_commit(bar);
+      umma_commit(bar);  // the next epilogue only waits for the input gradient ...
+      issue_dweight<16>(tmem + bwd::cDW2p, sb + bwd::kDP, sb + bwd::kH, seen_tile);  // ... this overlaps it
     }
     mbar_wait(bar, phase), phase ^= 1;
     tc_fence_after();
@@ -460,16 +492,35 @@ k_field_bwd_tc(atmonr_grid_t g, const __half2* __restrict__ table, const __half*
     if (tid == 0) {
       tc_fence_after();
       issue_dinput<32>(tmem + bwd::cAcc32, sb + bwd::kDA, sb + bwd::kW + fwd::kW1P);
-      issue_dweight<32>(tmem + bwd::cDW1p, sb + bwd::kDA, sb + bwd::kENC, seen_tile);
-      umma_commit(bar);
+      umma_commit(bar);  // the next epilogue only waits for the input gradient ...
+      issue_dweight<32>(tmem + bwd::cDW1p, sb + bwd::kDA, sb + bwd::kENC, seen_tile);  // ... this overlaps it
+      umma_commit(bar2);  // tile boundary: every MMA that reads this tile's buffers
     }
     mbar_wait(bar, phase), phase ^= 1;
     tc_fence_after();
-    tmem_ld32(my32, v);   // dL/d(encoded features), scaled by S
-    if (valid) hash_scatter_fast<3>(g, dtable, p, v, invS);
+    // dL/d(encoded features) (scaled by S) sits in TMEM columns [0,32): scatter level by level
+#pragma unroll 2
+    for (int l = 0; l < ATMONR_MAX_LEVELS; ++l) {
+      float d[2];
+      tmem_ld2(my32 + 2 * l, d);
+      const float d0 = d[0] * invS, d1 = d[1] * invS;
+#ifdef ATM_SCATTER_AGGREGATED
+      scatter_level_aggregated(lv[l], dtable, p, d0, d1, valid);
+#else
+      if (valid && (d0 != 0.0f || d1 != 0.0f)) {
+        uint32_t e[8];
+        float w[8];
+        level_corners3(lv[l], p, e, w);
+        float* base = dtable + 2 * (size_t)lv[l].offset;
+#pragma unroll
+        for (int c = 0; c < 8; ++c) red_add_f32x2(base + 2 * (size_t)e[c], w[c] * d0, w[c] * d1);
+      }
+#endif
+    }
   }
 
   // ---------------- flush the weight gradients (TMEM lanes = output neuron) ----------------
+  if (seen_tile) mbar_wait(bar2, phase2);
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
@@ -542,8 +593,10 @@ int atmonr_ngp_field_fwd_tc(const atmonr_grid_t* g, const void* table, const atm
   if (check_field_shapes(g, pm, dm, "atmonr_ngp_field_fwd_tc")) return -1;
   const int64_t M = B * N;
   if (M == 0) return 0;
+  ATM_REQUIRE(M < ((int64_t)1 << 31), "atmonr_ngp_field_fwd_tc", "B*N must be below 2^31 per call (chunk the batch)");
   const int64_t tiles = (M + kTile - 1) / kTile;
-  const int grid = (int)(tiles < (int64_t)tc_num_sms() * 4 ? tiles : (int64_t)tc_num_sms() * 4);
+  const int64_t max_ctas = (int64_t)tc_num_sms() * 8;
+  const int grid = (int)(tiles < max_ctas ? tiles : max_ctas);
   k_field_fwd_tc<<<grid, kTile, fwd::kBytes, reinterpret_cast<cudaStream_t>(stream)>>>(
       *g, (const __half2*)table, (const __half*)pos_w, (const __half*)dir_w, x01, dirs, M, N, sigma_raw, color_raw,
       (__half*)enc_out);
@@ -562,6 +615,7 @@ int atmonr_ngp_field_bwd_tc(const atmonr_grid_t* g, const void* table, const atm
   if (check_field_shapes(g, pm, dm, "atmonr_ngp_field_bwd_tc")) return -1;
   const int64_t M = B * N;
   if (M == 0) return 0;
+  ATM_REQUIRE(M < ((int64_t)1 << 31), "atmonr_ngp_field_bwd_tc", "B*N must be below 2^31 per call (chunk the batch)");
   cudaError_t e = cudaFuncSetAttribute(k_field_bwd_tc, cudaFuncAttributeMaxDynamicSharedMemorySize, bwd::kBytes);
   if (e != cudaSuccess) return fail("atmonr_ngp_field_bwd_tc", cudaGetErrorString(e));
   const int64_t tiles = (M + kTile - 1) / kTile;

@@ -119,6 +119,14 @@ __device__ __forceinline__ void umma_commit(uint64_t* bar) {
 // ---- TMEM -> registers (each thread reads its own lane: 32 lanes per warp, N consecutive columns)
 __device__ __forceinline__ void tmem_ld_wait() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
 
+__device__ __forceinline__ void tmem_ld2(uint32_t taddr, float (&v)[2]) {
+  uint32_t r[2];
+  asm volatile("tcgen05.ld.sync.aligned.32x32b.x2.b32 {%0,%1}, [%2];" : "=r"(r[0]), "=r"(r[1]) : "r"(taddr));
+  tmem_ld_wait();
+  v[0] = __uint_as_float(r[0]);
+  v[1] = __uint_as_float(r[1]);
+}
+
 __device__ __forceinline__ void tmem_ld4(uint32_t taddr, float (&v)[4]) {
   uint32_t r[4];
   asm volatile("tcgen05.ld.sync.aligned.32x32b.x4.b32 {%0,%1,%2,%3}, [%4];"
