@@ -91,7 +91,7 @@ class NGPRenderFn(torch.autograd.Function):
         seed = (st.seed * 0x9E3779B97F4A7C15 + st.step) & 0xFFFFFFFFFFFFFFFF
         x01, z = ops.ngp_sample_points(st.frame, origin, direction, length, n, st.alt_compress, u=u, random=True,
                                        seed=seed, ray_index_base=st.ray_index_base, bins=st.bins)
-        needs_grad = torch.is_grad_enabled() and any(t.requires_grad for t in (pos_table, pos_w, dir_w))
+        needs_grad = any(ctx.needs_input_grad[:3])  # (grad mode is off inside Function.forward)
         sigma_raw, color_raw, enc = field_forward(st, t16, pw16, dw16, x01, direction, b, n, want_enc=needs_grad)
         cs_raw = surface_forward(st, s16, sw16, origin, direction, length)
         cmap, catmo, csurf, tsurf, _, _ = ops.composite_forward(

@@ -12,9 +12,23 @@
 // Thread/row mapping: CTA = 128 threads = one 128-sample tile; thread t owns sample row t, which
 // is TMEM lane t of every accumulator, so the epilogue between two layers (ReLU, fp16 pack,
 // store as the next layer's A operand) is thread-local.
+#include <stdlib.h>
+
 #include "common.cuh"
 #include "hashgrid.cuh"
 #include "tc_common.cuh"
+
+// debug switches for timing experiments (never defined in the shipped build)
+#ifdef ATM_DEBUG_NO_DW
+#define ATM_DW if (false)
+#else
+#define ATM_DW
+#endif
+#ifdef ATM_DEBUG_NO_SCATTER
+#define ATM_SCATTER_ON (d0 == 123456.0f)
+#else
+#define ATM_SCATTER_ON true
+#endif
 
 namespace atm {
 
@@ -552,6 +566,333 @@ k_field_bwd_tc(atmonr_grid_t g, const __half2* __restrict__ table, const __half*
   if (warp == 0) tmem_dealloc<bwd::kTmemCols>(tmem);
 }
 
+
+// =========================================================================================
+// fused radiance field, backward, 256-row tiles (two 128-row MMA halves per CTA)
+// =========================================================================================
+// Same arithmetic as k_field_bwd_tc. Differences: 256 threads own 256 sample rows, so each
+// barrier / MMA round trip serves twice the samples and 16 warps per SM are resident (2 CTAs);
+// shared memory is reused along the backward chain so that two CTAs fit:
+//   X   : encoded features (until layer 0 is done)  -> dL/dh2
+//   H   : pos_mlp hidden
+//   DIN : dir_mlp input                              -> encoded features again (re-read from
+//                                                        the forward's cache for dW of layer 0)
+//   H1  : dir_mlp hidden 0                           -> dL/dh
+//   H2  : dir_mlp hidden 1                           -> dL/dh1
+//   DO  : dL/d(dir_mlp out)                          -> dL/d(pos_mlp out)
+// A buffer is only overwritten after the mbarrier wait that proves its last MMA reader is done
+// (tcgen05.commit covers every MMA issued before it).
+namespace bwd2 {
+constexpr int kRows = 256;
+constexpr int kX = 0;
+constexpr int kH = kX + 16384;
+constexpr int kDIN = kH + 16384;
+constexpr int kH1 = kDIN + 16384;
+constexpr int kH2 = kH1 + 16384;
+constexpr int kDO = kH2 + 16384;      // [256][16]
+constexpr int kW = kDO + 8192;        // weights last: they also absorb the 128-row over-reads
+constexpr int kLv = kW + 8192;
+constexpr int kBar = kLv + 512;
+constexpr int kBar2 = kBar + 8;
+constexpr int kTmemPtr = kBar2 + 8;
+constexpr int kBytes = kTmemPtr + 8;
+constexpr uint32_t kTmemCols = 256;
+constexpr int cHalf = 48;             // per-half accumulators: [0,32) 32-wide, [32,48) 16-wide
+constexpr int cDWd3 = 96, cDWd2 = 128, cDWd1 = 160, cDW2p = 192, cDW1p = 224;
+}  // namespace bwd2
+
+template <int N>
+__device__ __forceinline__ void issue_layer2(uint32_t tmem, int col, uint32_t a_tile, uint32_t w_tile) {
+  constexpr uint32_t idesc = make_idesc(128, N, 0, 0);
+#pragma unroll
+  for (int h = 0; h < 2; ++h)
+#pragma unroll
+    for (int k = 0; k < 2; ++k)
+      umma_f16(tmem + h * bwd2::cHalf + col, desc_k_major(a_tile + h * 8192 + k * 2 * kCore, 32),
+               desc_k_major(w_tile + k * 2 * kCore, 32), idesc, k);
+}
+template <int KD>
+__device__ __forceinline__ void issue_dinput2(uint32_t tmem, uint32_t d_tile, uint32_t w_tile) {
+  constexpr uint32_t idesc = make_idesc(128, 32, 0, 1);
+#pragma unroll
+  for (int h = 0; h < 2; ++h)
+#pragma unroll
+    for (int k = 0; k < KD / 16; ++k)
+      umma_f16(tmem + h * bwd2::cHalf, desc_k_major(d_tile + h * 16 * (KD / 8) * kCore + k * 2 * kCore, KD),
+               desc_mn_major(w_tile + k * 2 * 4 * kCore, 32), idesc, k);
+}
+template <int KD>
+__device__ __forceinline__ void issue_dweight2(uint32_t acc, uint32_t d_tile, uint32_t a_tile, uint32_t accumulate) {
+  constexpr uint32_t idesc = make_idesc(128, 32, 1, 1);
+#pragma unroll
+  for (int k = 0; k < 16; ++k)
+    umma_f16(acc, desc_mn_major(d_tile + k * 2 * (KD / 8) * kCore, KD), desc_mn_major(a_tile + k * 2 * 4 * kCore, 32),
+             idesc, accumulate | (uint32_t)(k > 0));
+}
+
+__global__ void __launch_bounds__(256, 2)
+k_field_bwd_tc2(atmonr_grid_t g, const __half* __restrict__ pos_w, const __half* __restrict__ dir_w,
+                const float* __restrict__ x01, const float* __restrict__ dirs, const __half* __restrict__ enc_in,
+                const float* __restrict__ dsigma_raw, const float* __restrict__ dcolor_raw,
+                const float* __restrict__ grad_absmax, int64_t M, int N, float* __restrict__ dtable,
+                float* __restrict__ dpos_w, float* __restrict__ ddir_w) {
+  extern __shared__ __align__(128) uint8_t smem[];
+  uint64_t* bar = reinterpret_cast<uint64_t*>(smem + bwd2::kBar);
+  uint64_t* bar2 = reinterpret_cast<uint64_t*>(smem + bwd2::kBar2);
+  uint32_t* tmem_ptr = reinterpret_cast<uint32_t*>(smem + bwd2::kTmemPtr);
+  const int tid = threadIdx.x, warp = tid >> 5;
+  LevelRow* lv = reinterpret_cast<LevelRow*>(smem + bwd2::kLv);
+  load_level_table(g, lv);
+  load_field_weights(smem + bwd2::kW, pos_w, dir_w);
+  if (warp == 0) tmem_alloc<bwd2::kTmemCols>(tmem_ptr);
+  if (tid == 0) {
+    mbar_init(bar, 1);
+    mbar_init(bar2, 1);
+    fence_mbar_init();
+  }
+  publish_and_sync();
+  tc_fence_after();
+  const uint32_t tmem = *tmem_ptr;
+  const uint32_t my32 = tmem_addr(tmem, warp, (warp >> 2) * bwd2::cHalf), my16 = my32 + 32;
+  const uint32_t sb = smem_u32(smem), sw = sb + bwd2::kW;
+  uint8_t* X = smem + bwd2::kX;
+  uint8_t* H = smem + bwd2::kH;
+  uint8_t* DIN = smem + bwd2::kDIN;
+  uint8_t* H1 = smem + bwd2::kH1;
+  uint8_t* H2 = smem + bwd2::kH2;
+  uint8_t* DO = smem + bwd2::kDO;
+  float S = 1.0f;
+  if (grad_absmax) {
+    const float amax = *grad_absmax;
+    if (amax > 0.0f && amax < INFINITY) S = exp2f(fminf(fmaxf(floorf(log2f(2048.0f / amax)), -60.0f), 60.0f));
+  }
+  const float invS = 1.0f / S;
+  uint32_t phase = 0, phase2 = 0, seen_tile = 0;
+
+  for (int64_t tile = blockIdx.x; tile * bwd2::kRows < M; tile += gridDim.x, seen_tile = 1) {
+    const int64_t i = tile * bwd2::kRows + tid;
+    const bool valid = i < M;
+    const int64_t j = valid ? i : M - 1;
+    if (seen_tile) mbar_wait(bar2, phase2), phase2 ^= 1;
+    const uint4* enc_row = reinterpret_cast<const uint4*>(enc_in + j * 32);
+    // ---------------- recompute the activations ----------------
+#pragma unroll
+    for (int cc = 0; cc < 4; ++cc) st_chunk(X, tid, cc, 32, enc_row[cc]);
+    publish_and_sync();
+    if (tid == 0) {
+      tc_fence_after();
+      issue_layer2<32>(tmem, 0, sb + bwd2::kX, sw + fwd::kW1P);
+      umma_commit(bar);
+    }
+    mbar_wait(bar, phase), phase ^= 1;
+    tc_fence_after();
+    float v[32];
+    tmem_ld32(my32, v);
+    store_row32<true>(H, tid, v);
+    publish_and_sync();
+    if (tid == 0) {
+      tc_fence_after();
+      issue_layer2<16>(tmem, 32, sb + bwd2::kH, sw + fwd::kW2P);
+      umma_commit(bar);
+    }
+    mbar_wait(bar, phase), phase ^= 1;
+    tc_fence_after();
+    {
+      float po[16];
+      tmem_ld16(my16, po);
+      dir_input_row(dirs + (size_t)((uint32_t)j / (uint32_t)N) * 3, po, v);
+    }
+    store_row32<false>(DIN, tid, v);
+    publish_and_sync();
+    if (tid == 0) {
+      tc_fence_after();
+      issue_layer2<32>(tmem, 0, sb + bwd2::kDIN, sw + fwd::kWD1);
+      umma_commit(bar);
+    }
+    mbar_wait(bar, phase), phase ^= 1;
+    tc_fence_after();
+    tmem_ld32(my32, v);
+    store_row32<true>(H1, tid, v);
+    publish_and_sync();
+    if (tid == 0) {
+      tc_fence_after();
+      issue_layer2<32>(tmem, 0, sb + bwd2::kH1, sw + fwd::kWD2);
+      umma_commit(bar);
+    }
+    mbar_wait(bar, phase), phase ^= 1;
+    tc_fence_after();
+    tmem_ld32(my32, v);
+    store_row32<true>(H2, tid, v);
+    // ---------------- backward ----------------
+    {
+      float dout[16];
+#pragma unroll
+      for (int k = 0; k < 16; ++k) dout[k] = 0.0f;
+      if (valid) {
+        const float4 dc = *reinterpret_cast<const float4*>(dcolor_raw + 4 * i);
+        dout[0] = dc.x * S, dout[1] = dc.y * S, dout[2] = dc.z * S, dout[3] = dc.w * S;
+      }
+      store_row16(DO, tid, dout);
+    }
+    publish_and_sync();
+    if (tid == 0) {  // S0
+      tc_fence_after();
+      issue_dinput2<16>(tmem, sb + bwd2::kDO, sw + fwd::kWD3);
+      umma_commit(bar);
+      ATM_DW issue_dweight2<16>(tmem + bwd2::cDWd3, sb + bwd2::kDO, sb + bwd2::kH2, seen_tile);
+    }
+    mbar_wait(bar, phase), phase ^= 1;
+    tc_fence_after();
+    tmem_ld32(my32, v);
+    relu_mask_row(H2, tid, v);
+    store_row32<false>(X, tid, v);  // dL/dh2 -> X (layer 0 finished with the encoded features)
+    publish_and_sync();
+    if (tid == 0) {  // S1
+      tc_fence_after();
+      issue_dinput2<32>(tmem, sb + bwd2::kX, sw + fwd::kWD2);
+      umma_commit(bar);
+      ATM_DW issue_dweight2<32>(tmem + bwd2::cDWd2, sb + bwd2::kX, sb + bwd2::kH1, seen_tile);
+    }
+    mbar_wait(bar, phase), phase ^= 1;  // covers dW(d3): DO and H2 are free
+    tc_fence_after();
+    tmem_ld32(my32, v);
+    relu_mask_row(H1, tid, v);
+    store_row32<false>(H2, tid, v);  // dL/dh1 -> H2
+    publish_and_sync();
+    if (tid == 0) {  // S2
+      tc_fence_after();
+      issue_dinput2<32>(tmem, sb + bwd2::kH2, sw + fwd::kWD1);
+      umma_commit(bar);
+      ATM_DW issue_dweight2<32>(tmem + bwd2::cDWd1, sb + bwd2::kH2, sb + bwd2::kDIN, seen_tile);
+    }
+    mbar_wait(bar, phase), phase ^= 1;  // covers dW(d2): X and H1 are free
+    tc_fence_after();
+    tmem_ld32(my32, v);
+    {
+      float dpo[16];
+      dpo[0] = valid ? dsigma_raw[i] * S : 0.0f;
+#pragma unroll
+      for (int k = 1; k < 16; ++k) dpo[k] = v[3 + k];
+      store_row16(DO, tid, dpo);  // dL/d(pos_mlp out) -> DO
+    }
+    publish_and_sync();
+    if (tid == 0) {  // S3
+      tc_fence_after();
+      issue_dinput2<16>(tmem, sb + bwd2::kDO, sw + fwd::kW2P);
+      umma_commit(bar);
+      ATM_DW issue_dweight2<16>(tmem + bwd2::cDW2p, sb + bwd2::kDO, sb + bwd2::kH, seen_tile);
+    }
+    mbar_wait(bar, phase), phase ^= 1;  // covers dW(d1): H2 and DIN are free
+    tc_fence_after();
+    tmem_ld32(my32, v);
+    relu_mask_row(H, tid, v);
+    store_row32<false>(H1, tid, v);  // dL/dh -> H1
+#pragma unroll
+    for (int cc = 0; cc < 4; ++cc) st_chunk(DIN, tid, cc, 32, enc_row[cc]);  // encoded features again -> DIN
+    publish_and_sync();
+    if (tid == 0) {  // S4
+      tc_fence_after();
+      issue_dinput2<32>(tmem, sb + bwd2::kH1, sw + fwd::kW1P);
+      umma_commit(bar);
+      ATM_DW issue_dweight2<32>(tmem + bwd2::cDW1p, sb + bwd2::kH1, sb + bwd2::kDIN, seen_tile);
+      umma_commit(bar2);
+    }
+    mbar_wait(bar, phase), phase ^= 1;
+    tc_fence_after();
+    // ---- table-gradient scatter with run-length merging --------------------------------------
+    // dL/d(encoded features) of the whole tile is staged in shared memory (fp32, X..H are free
+    // now), then the work is re-mapped: thread (g, q) walks the 16 CONSECUTIVE samples
+    // 16g..16g+15 of level q. Consecutive samples of a ray mostly stay in the same grid cell,
+    // so their 8 corner contributions are merged in registers and written with one vector RED
+    // per corner per cell run instead of one per sample (the REDs were the kernel's bottleneck:
+    // ~1.3 cycles per lane-RED per SM).
+    tmem_ld32(my32, v);
+    {
+      float* srow = reinterpret_cast<float*>(smem + bwd2::kX) + tid * 32;
+#pragma unroll
+      for (int k = 0; k < 8; ++k)   // 16-byte chunks, XOR-swizzled by the row to spread banks
+        *reinterpret_cast<float4*>(srow + ((k ^ (tid & 7)) << 2)) =
+            make_float4(v[4 * k] * invS, v[4 * k + 1] * invS, v[4 * k + 2] * invS, v[4 * k + 3] * invS);
+    }
+    __syncthreads();
+    {
+      const int grp = tid >> 4, lvl = tid & 15;
+      const LevelRow L = lv[lvl];
+      float* base = dtable + 2 * (size_t)L.offset;
+      const float* stage = reinterpret_cast<const float*>(smem + bwd2::kX);
+      const int64_t row0 = tile * bwd2::kRows + grp * 16;
+      float acc[16];
+      uint32_t e_run[8], c_run[3] = {0xffffffffu, 0xffffffffu, 0xffffffffu};
+      bool open = false;
+#pragma unroll
+      for (int c = 0; c < 16; ++c) acc[c] = 0.0f;
+#pragma unroll 1
+      for (int r = 0; r < 16; ++r) {
+        const int64_t gi = row0 + r;
+        if (gi >= M) break;
+        const int row = grp * 16 + r;
+        const float2 d = *reinterpret_cast<const float2*>(stage + row * 32 + ((((lvl >> 1) ^ (row & 7)) << 2) | ((lvl & 1) << 1)));
+        if (!ATM_SCATTER_ON) continue;
+        if (d.x == 0.0f && d.y == 0.0f) continue;
+        const float p[3] = {x01[3 * gi], x01[3 * gi + 1], x01[3 * gi + 2]};
+        uint32_t e[8], cell[3];
+        float w[8];
+        level_corners3(L, p, e, w, cell);
+        if (open && (cell[0] != c_run[0] || cell[1] != c_run[1] || cell[2] != c_run[2])) {
+#pragma unroll
+          for (int c = 0; c < 8; ++c) red_add_f32x2(base + 2 * (size_t)e_run[c], acc[2 * c], acc[2 * c + 1]);
+#pragma unroll
+          for (int c = 0; c < 16; ++c) acc[c] = 0.0f;
+        }
+#pragma unroll
+        for (int c = 0; c < 8; ++c) {
+          acc[2 * c] = fmaf(w[c], d.x, acc[2 * c]);
+          acc[2 * c + 1] = fmaf(w[c], d.y, acc[2 * c + 1]);
+          e_run[c] = e[c];
+        }
+        c_run[0] = cell[0], c_run[1] = cell[1], c_run[2] = cell[2];
+        open = true;
+      }
+      if (open) {
+#pragma unroll
+        for (int c = 0; c < 8; ++c) red_add_f32x2(base + 2 * (size_t)e_run[c], acc[2 * c], acc[2 * c + 1]);
+      }
+    }
+    __syncthreads();  // the staging area is the next tile's X/H
+  }
+
+  if (seen_tile) mbar_wait(bar2, phase2);
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  if (warp == 0 && seen_tile) {
+    const int o = tid;
+    float w[32];
+    tmem_ld32(tmem_addr(tmem, 0, bwd2::cDW1p), w);
+#pragma unroll
+    for (int c = 0; c < 32; ++c) atomicAdd(dpos_w + o * 32 + c, w[c] * invS);
+    tmem_ld32(tmem_addr(tmem, 0, bwd2::cDW2p), w);
+    if (o < 16) {
+#pragma unroll
+      for (int c = 0; c < 32; ++c) atomicAdd(dpos_w + 1024 + o * 32 + c, w[c] * invS);
+    }
+    tmem_ld32(tmem_addr(tmem, 0, bwd2::cDWd1), w);
+#pragma unroll
+    for (int c = 0; c < 32; ++c) atomicAdd(ddir_w + o * 32 + c, w[c] * invS);
+    tmem_ld32(tmem_addr(tmem, 0, bwd2::cDWd2), w);
+#pragma unroll
+    for (int c = 0; c < 32; ++c) atomicAdd(ddir_w + 1024 + o * 32 + c, w[c] * invS);
+    tmem_ld32(tmem_addr(tmem, 0, bwd2::cDWd3), w);
+    if (o < 16) {
+#pragma unroll
+      for (int c = 0; c < 32; ++c) atomicAdd(ddir_w + 2048 + o * 32 + c, w[c] * invS);
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 0) tmem_dealloc<bwd2::kTmemCols>(tmem);
+}
+
 }  // namespace atm
 
 using namespace atm;
@@ -616,6 +957,18 @@ int atmonr_ngp_field_bwd_tc(const atmonr_grid_t* g, const void* table, const atm
   const int64_t M = B * N;
   if (M == 0) return 0;
   ATM_REQUIRE(M < ((int64_t)1 << 31), "atmonr_ngp_field_bwd_tc", "B*N must be below 2^31 per call (chunk the batch)");
+  static const bool use_wide = getenv("ATMONR_BWD_NARROW") == nullptr;
+  if (enc && use_wide) {
+    cudaError_t e2 = cudaFuncSetAttribute(k_field_bwd_tc2, cudaFuncAttributeMaxDynamicSharedMemorySize, bwd2::kBytes);
+    if (e2 != cudaSuccess) return fail("atmonr_ngp_field_bwd_tc", cudaGetErrorString(e2));
+    const int64_t tiles2 = (M + bwd2::kRows - 1) / bwd2::kRows;
+    const int grid2 = (int)(tiles2 < (int64_t)tc_num_sms() * 2 ? tiles2 : (int64_t)tc_num_sms() * 2);
+    k_field_bwd_tc2<<<grid2, bwd2::kRows, bwd2::kBytes, reinterpret_cast<cudaStream_t>(stream)>>>(
+        *g, (const __half*)pos_w, (const __half*)dir_w, x01, dirs, (const __half*)enc, dsigma_raw, dcolor_raw,
+        grad_absmax, M, N, dtable, dpos_w, ddir_w);
+    ATM_CHECK_LAUNCH("atmonr_ngp_field_bwd_tc");
+    return 0;
+  }
   cudaError_t e = cudaFuncSetAttribute(k_field_bwd_tc, cudaFuncAttributeMaxDynamicSharedMemorySize, bwd::kBytes);
   if (e != cudaSuccess) return fail("atmonr_ngp_field_bwd_tc", cudaGetErrorString(e));
   const int64_t tiles = (M + kTile - 1) / kTile;
