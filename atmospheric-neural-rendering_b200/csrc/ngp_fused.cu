@@ -893,6 +893,163 @@ k_field_bwd_tc2(atmonr_grid_t g, const __half* __restrict__ pos_w, const __half*
   if (warp == 0) tmem_dealloc<bwd2::kTmemCols>(tmem);
 }
 
+
+// =========================================================================================
+// fused radiance field, forward, 256-row tiles with run-length merged gathers
+// =========================================================================================
+// Encoding phase: thread (g, q) encodes the 16 CONSECUTIVE samples 16g..16g+15 at level q. While
+// consecutive samples of the ray stay in the same grid cell the 8 corner entries are kept in
+// registers, so the table is gathered once per cell run (not once per sample) and the entry
+// indices are only recomputed when the cell changes. The features go straight into the A tile.
+// MLP phase: thread t owns sample row t (TMEM lane t & 127 of half t >> 7), as in k_field_fwd_tc.
+namespace fwd2 {
+constexpr int kRows = 256;
+constexpr int kA0 = 0;                 // [256][32]
+constexpr int kA1 = kA0 + 16384;       // [256][32]
+constexpr int kW = kA1 + 16384;
+constexpr int kLv = kW + 8192;
+constexpr int kBar = kLv + 512;
+constexpr int kTmemPtr = kBar + 8;
+constexpr int kBytes = kTmemPtr + 8;
+constexpr uint32_t kTmemCols = 128;    // two halves x ([0,32) hidden, [32,48) 16-wide)
+}  // namespace fwd2
+
+__global__ void __launch_bounds__(256, 4)
+k_field_fwd_tc2(atmonr_grid_t g, const __half2* __restrict__ table, const __half* __restrict__ pos_w,
+                const __half* __restrict__ dir_w, const float* __restrict__ x01, const float* __restrict__ dirs,
+                int64_t M, int N, float* __restrict__ sigma_raw, float* __restrict__ color_raw,
+                __half* __restrict__ enc_out) {
+  extern __shared__ __align__(128) uint8_t smem[];
+  uint64_t* bar = reinterpret_cast<uint64_t*>(smem + fwd2::kBar);
+  uint32_t* tmem_ptr = reinterpret_cast<uint32_t*>(smem + fwd2::kTmemPtr);
+  const int tid = threadIdx.x, warp = tid >> 5;
+  LevelRow* lv = reinterpret_cast<LevelRow*>(smem + fwd2::kLv);
+  load_level_table(g, lv);
+  load_field_weights(smem + fwd2::kW, pos_w, dir_w);
+  if (warp == 0) tmem_alloc<fwd2::kTmemCols>(tmem_ptr);
+  if (tid == 0) {
+    mbar_init(bar, 1);
+    fence_mbar_init();
+  }
+  publish_and_sync();
+  tc_fence_after();
+  const uint32_t tmem = *tmem_ptr;
+  const uint32_t my32 = tmem_addr(tmem, warp, (warp >> 2) * bwd2::cHalf), my16 = my32 + 32;
+  const uint32_t sb = smem_u32(smem), sw = sb + fwd2::kW;
+  uint8_t* A0 = smem + fwd2::kA0;
+  uint8_t* A1 = smem + fwd2::kA1;
+  uint32_t phase = 0;
+  const int grp = tid >> 4, lvl = tid & 15;
+  const LevelRow L = lv[lvl];
+  const __half2* lbase = table + L.offset;
+
+  for (int64_t tile = blockIdx.x; tile * fwd2::kRows < M; tile += gridDim.x) {
+    const int64_t i = tile * fwd2::kRows + tid;
+    const bool valid = i < M;
+    const int64_t j = valid ? i : M - 1;
+    // ---- encoding: 16 consecutive samples of one level per thread ----
+    {
+      const int64_t row0 = tile * fwd2::kRows + grp * 16;
+      uint32_t c_run[3] = {0xffffffffu, 0xffffffffu, 0xffffffffu};
+      float2 f[8];
+#pragma unroll
+      for (int c = 0; c < 8; ++c) f[c] = make_float2(0.0f, 0.0f);
+#pragma unroll 2
+      for (int r = 0; r < 16; ++r) {
+        int64_t gi = row0 + r;
+        if (gi >= M) gi = M - 1;
+        const float p[3] = {x01[3 * gi], x01[3 * gi + 1], x01[3 * gi + 2]};
+        uint32_t cell[3];
+        float frac[3];
+        grid_cell<3>(p, L.scale, cell, frac);
+        if (cell[0] != c_run[0] || cell[1] != c_run[1] || cell[2] != c_run[2]) {
+          uint32_t e[8];
+          float wdummy[8];
+          level_corners3(L, p, e, wdummy, cell);
+#pragma unroll
+          for (int c = 0; c < 8; ++c) f[c] = __half22float2(__ldg(lbase + e[c]));
+          c_run[0] = cell[0], c_run[1] = cell[1], c_run[2] = cell[2];
+        }
+        const float wx[2] = {1.0f - frac[0], frac[0]};
+        const float wy[2] = {1.0f - frac[1], frac[1]};
+        const float wz[2] = {1.0f - frac[2], frac[2]};
+        float a0 = 0.0f, a1 = 0.0f;
+#pragma unroll
+        for (int c = 0; c < 8; ++c) {
+          const float w = (wx[c & 1] * wy[(c >> 1) & 1]) * wz[c >> 2];
+          a0 = fmaf(w, f[c].x, a0);
+          a1 = fmaf(w, f[c].y, a1);
+        }
+        *reinterpret_cast<uint32_t*>(A0 + tile_off(grp * 16 + r, 2 * lvl, 32)) = pack_h2(a0, a1);
+      }
+    }
+    publish_and_sync();
+    if (enc_out && valid) {  // own row, complete after the barrier
+      uint4* dst = reinterpret_cast<uint4*>(enc_out + i * 32);
+#pragma unroll
+      for (int cc = 0; cc < 4; ++cc) dst[cc] = ld_chunk(A0, tid, cc, 32);
+    }
+    if (tid == 0) {
+      tc_fence_after();
+      issue_layer2<32>(tmem, 0, sb + fwd2::kA0, sw + fwd::kW1P);
+      umma_commit(bar);
+    }
+    mbar_wait(bar, phase), phase ^= 1;
+    tc_fence_after();
+    float v[32];
+    tmem_ld32(my32, v);
+    store_row32<true>(A1, tid, v);
+    publish_and_sync();
+    if (tid == 0) {
+      tc_fence_after();
+      issue_layer2<16>(tmem, 32, sb + fwd2::kA1, sw + fwd::kW2P);
+      umma_commit(bar);
+    }
+    mbar_wait(bar, phase), phase ^= 1;
+    tc_fence_after();
+    float po[16];
+    tmem_ld16(my16, po);
+    if (valid) sigma_raw[i] = po[0];
+    dir_input_row(dirs + (size_t)((uint32_t)j / (uint32_t)N) * 3, po, v);
+    store_row32<false>(A0, tid, v);
+    publish_and_sync();
+    if (tid == 0) {
+      tc_fence_after();
+      issue_layer2<32>(tmem, 0, sb + fwd2::kA0, sw + fwd::kWD1);
+      umma_commit(bar);
+    }
+    mbar_wait(bar, phase), phase ^= 1;
+    tc_fence_after();
+    tmem_ld32(my32, v);
+    store_row32<true>(A1, tid, v);
+    publish_and_sync();
+    if (tid == 0) {
+      tc_fence_after();
+      issue_layer2<32>(tmem, 0, sb + fwd2::kA1, sw + fwd::kWD2);
+      umma_commit(bar);
+    }
+    mbar_wait(bar, phase), phase ^= 1;
+    tc_fence_after();
+    tmem_ld32(my32, v);
+    store_row32<true>(A0, tid, v);
+    publish_and_sync();
+    if (tid == 0) {
+      tc_fence_after();
+      issue_layer2<16>(tmem, 32, sb + fwd2::kA0, sw + fwd::kWD3);
+      umma_commit(bar);
+    }
+    mbar_wait(bar, phase), phase ^= 1;
+    tc_fence_after();
+    float c[4];
+    tmem_ld4(my16, c);
+    if (valid) *reinterpret_cast<float4*>(color_raw + 4 * i) = make_float4(c[0], c[1], c[2], c[3]);
+    // the next tile's encoding writes A0, which the last layer's MMA has finished reading (waited above)
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 0) tmem_dealloc<fwd2::kTmemCols>(tmem);
+}
+
 }  // namespace atm
 
 using namespace atm;
@@ -935,6 +1092,21 @@ int atmonr_ngp_field_fwd_tc(const atmonr_grid_t* g, const void* table, const atm
   const int64_t M = B * N;
   if (M == 0) return 0;
   ATM_REQUIRE(M < ((int64_t)1 << 31), "atmonr_ngp_field_fwd_tc", "B*N must be below 2^31 per call (chunk the batch)");
+  // the 256-row variant merges gathers over runs of samples in one cell; its serial per-thread
+  // gather chain currently loses to the 128-row kernel (44 vs 33 ms at 2^18 rays): opt-in only
+  static const bool use_wide = getenv("ATMONR_FWD_WIDE") != nullptr;
+  if (use_wide) {
+    cudaError_t e2 = cudaFuncSetAttribute(k_field_fwd_tc2, cudaFuncAttributeMaxDynamicSharedMemorySize, fwd2::kBytes);
+    if (e2 != cudaSuccess) return fail("atmonr_ngp_field_fwd_tc", cudaGetErrorString(e2));
+    const int64_t tiles2 = (M + fwd2::kRows - 1) / fwd2::kRows;
+    const int64_t cap2 = (int64_t)tc_num_sms() * 4;
+    k_field_fwd_tc2<<<(int)(tiles2 < cap2 ? tiles2 : cap2), fwd2::kRows, fwd2::kBytes,
+                      reinterpret_cast<cudaStream_t>(stream)>>>(*g, (const __half2*)table, (const __half*)pos_w,
+                                                                (const __half*)dir_w, x01, dirs, M, N, sigma_raw,
+                                                                color_raw, (__half*)enc_out);
+    ATM_CHECK_LAUNCH("atmonr_ngp_field_fwd_tc");
+    return 0;
+  }
   const int64_t tiles = (M + kTile - 1) / kTile;
   const int64_t max_ctas = (int64_t)tc_num_sms() * 8;
   const int grid = (int)(tiles < max_ctas ? tiles : max_ctas);
