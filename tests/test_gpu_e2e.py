@@ -1,0 +1,97 @@
+"""GPU end-to-end: the train / extract scripts on a synthetic granule, and the NeRF pipeline
+against the (reference-pinned) NeRF oracle on identical draws."""
+
+import json
+import os
+import subprocess
+import sys
+
+import numpy as np
+import pytest
+import torch
+
+from helpers import ROOT, FakeDataset, take, tiny_scene, to_cuda
+from oracle import nerf as onerf
+
+pytestmark = pytest.mark.gpu
+
+
+def test_train_and_extract_scripts(tmp_path):
+    cfg = json.load(open(os.path.join(ROOT, "configs", "instant_ngp.json")))
+    cfg["pipeline"]["num_samples_per_ray"] = 64
+    cfg["trainer"].update(batch_size=2048, num_iters=10, print_frequency=2)
+    cfg_path = tmp_path / "cfg.json"
+    cfg_path.write_text(json.dumps(cfg))
+    env = dict(os.environ, PYTHONPATH="")
+    run = lambda *a: subprocess.run([sys.executable, *a], cwd=tmp_path, env=env, capture_output=True, text=True, timeout=600)
+    r = run(os.path.join(ROOT, "scripts", "train.py"), "--exp-name", "t0", "--config-path", str(cfg_path),
+            "--scene-filename", "synthetic:H=12,W=12,seed=3", "--overwrite")
+    assert r.returncode == 0, r.stderr[-2000:]
+    out = tmp_path / "data" / "output" / "t0"
+    ckpts = sorted(out.glob("epoch_*.pt"))
+    assert ckpts and (out / "args.json").exists() and (out / "config.json").exists()
+    ck = torch.load(ckpts[-1], weights_only=False)
+    assert set(ck) == {"pipeline", "optimizer", "scheduler", "tensorboard_dir", "epoch_idx", "iter_count"}
+    assert list(ck["pipeline"]) == ["pos_encoder", "pos_mlp", "dir_encoder", "dir_mlp", "surf_encoder", "surf_mlp"]
+    assert ck["pipeline"]["pos_encoder"]["params"].numel() == 42283392 and ck["iter_count"] == 10
+    assert "PSNR_mean" in r.stdout
+    # resume for a few more iterations
+    cfg["trainer"]["num_iters"] = 14
+    cfg_path.write_text(json.dumps(cfg))
+    r = run(os.path.join(ROOT, "scripts", "train.py"), "--exp-name", "t0", "--config-path", str(cfg_path),
+            "--scene-filename", "synthetic:H=12,W=12,seed=3", "--resume")
+    assert r.returncode == 0, r.stderr[-2000:]
+    # extraction over the voxel grid
+    r = run(os.path.join(ROOT, "scripts", "extract.py"), "--exp-name", "t0", "--coord-mode", "voxelgrid",
+            "--extract-filename", "ext.nc", "--horizontal-step", "60000", "--alt-step", "1000", "--batch-size", "16")
+    assert r.returncode == 0, r.stderr[-2000:]
+    z = np.load(out / "ext.npz")
+    ext = z["extinction_coefficient"]
+    assert ext.ndim == 4 and ext.shape[2] == 21 and ext.shape[3] == 1 and np.isfinite(ext).all() and (ext >= 0).all()
+    r = run(os.path.join(ROOT, "scripts", "extract.py"), "--exp-name", "t0", "--coord-mode", "globalgrid", "--extract-filename", "x.nc")
+    assert r.returncode != 0 and "NotImplementedError" in r.stderr
+
+
+def test_nerf_pipeline_matches_oracle(monkeypatch):
+    from atmonr.pipelines.nerf import NeRFPipeline
+    scene = tiny_scene()
+    cfg = {"type": "NeRF", "include_height": False, "point_preprocessor": "horizontal", "num_bands": 4,
+           "ray_origin_height": 20000, "sampler": {"N_c": 8, "N_f": 16}, "encoder": {"L_x": [14, 14, 10], "L_d": 4},
+           "mlp_hidden_dim": 32}
+    orc = onerf.NeRFOracle(cfg, scene.frame)
+    params = orc.init_params(seed=3)
+    pipe = NeRFPipeline(cfg, FakeDataset(scene))
+    pipe.load_state_dict({m: {k: v.detach().clone() for k, v in params[m].items()} for m in ("coarse", "fine")})
+    pipe.send_tensors_to(0)
+    pipe.eval()   # no density noise: deterministic given the two uniform draws
+    b = take(scene.batch, slice(0, 40))
+    g = torch.Generator().manual_seed(8)
+    u_c, u_f = torch.rand(40, 8, generator=g), torch.rand(40, 16, generator=g)
+    draws = [u_c, u_f]
+    real_rand = torch.rand
+    monkeypatch.setattr(torch, "rand", lambda *a, **k: draws.pop(0).to(k.get("device", "cpu")) if draws else real_rand(*a, **k))
+    res_o = orc.forward(b, params, u_c, u_f)
+    loss_o = orc.loss(b, res_o)
+    loss_o.backward()
+    bc = to_cuda(b)
+    res = pipe.forward(bc)
+    loss = pipe.compute_loss(bc, res)
+    loss.backward()
+    rel = lambda a, c: float((a.detach().double().cpu() - c.detach().double()).abs().max() / (c.detach().double().abs().max() + 1e-30))
+    assert rel(res["z_vals_coarse"], res_o["z_vals_coarse"]) < 1e-6
+    assert rel(res["z_vals_fine"], res_o["z_vals_fine"]) < 1e-4
+    for k in ("color_map_coarse", "color_map_fine", "weights_coarse", "weights_fine", "sigma_fine"):
+        assert rel(res[k], res_o[k]) < 2e-3, k      # fp32 path: north_star tolerance 1e-3 on radiances
+    assert rel(res["color_map_fine"], res_o["color_map_fine"]) < 1e-3
+    assert rel(loss, loss_o) < 1e-3
+    for mode in ("coarse", "fine"):   # the coarse gradients include the path through sample_pdf
+        for name in ("fc1.weight", "fc11.weight"):
+            layer, attr = name.split(".")
+            got = getattr(getattr(pipe.nerf[mode], layer), attr).grad
+            assert rel(got, params[mode][name].grad) < 2e-2, (mode, name)
+    assert torch.equal(res["color_map_atmo"], res["color_map_fine"]) and float(res["color_map_surf"].abs().max()) == 0
+    with torch.no_grad():
+        pts = (torch.rand(100, 3, dtype=torch.float64) * 2 - 1) * 0.9
+        want = orc.extract(pts, params)
+        got = pipe.extract(pts.cuda())
+    assert rel(got, want) < 2e-3
