@@ -219,14 +219,22 @@ def run_native(args) -> None:
             torch.distributed.all_reduce(ms, op=torch.distributed.ReduceOp.MAX)
         return float(ms.item())
 
-    # ---- warm-up, then the device-resident measurement (inputs cycle through > L2 of data) ----
+    # ---- settle (allocator pools, lazy module loading: the first ~6 steps of a process run up to
+    # 1.6x slower), then the W warm-up steps, then the device-resident measurement ----
+    for i in range(4):
+        step(batches[i % len(batches)])
     for i in range(W):
         step(batches[i % len(batches)])
     clocks = ClockSampler(local)
     if rank == 0:
         clocks.start()
     L.STATS = L.CallStats(timed=False)
+    profile_range = os.environ.get("ATMONR_CUDA_PROFILER_RANGE") == "1"  # ncu --profile-from-start off
+    if profile_range:
+        torch.cuda.profiler.start()
     ms_total = timed(K, lambda i: step(batches[i % len(batches)]))
+    if profile_range:
+        torch.cuda.profiler.stop()
     launches = L.STATS.launches
     L.STATS = None
     clock_info = clocks.stop() if rank == 0 else {}
@@ -243,21 +251,32 @@ def run_native(args) -> None:
     per_step = {k: sum(v) / min(K, 3) for k, v in dur.items()}
     top = max(per_step, key=per_step.get)
     M = B * args.samples
-    alg_bytes = {  # 512 B gathered / 512 B scattered per sample; AdamW 28 B + 2 B shadow per param
+    # SURVEY 8d per-unit figures: 512 B gathered (fwd) / 512 B scattered (bwd) per sample -- the
+    # backward reads the forward's cached features (64 B/sample) instead of re-gathering the table;
+    # AdamW 28 B + 2 B fp16 shadow per parameter.
+    alg_bytes = {
         "atmonr_ngp_field_fwd": 512 * M, "atmonr_ngp_field_bwd": 1024 * M,
+        "atmonr_ngp_field_fwd_tc": 512 * M, "atmonr_ngp_field_bwd_tc": 512 * M,
         "atmonr_adamw_step": 30 * N_PARAMS, "atmonr_ngp_sample_points": 16 * M + 28 * B,
         "atmonr_composite_fwd": 24 * M, "atmonr_composite_bwd": 44 * M,
     }
+    traffic_file = os.path.join(ROOT, "profiles", "ncu_dram_traffic.json")
+    traffic = json.load(open(traffic_file)) if os.path.exists(traffic_file) else {}
     peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json"))) if os.path.exists(os.path.join(ROOT, "MEASURED_PEAKS.json")) else {}
     hbm_peak = float(peaks.get("hbm_gbs", 6650.0))
     n_top = max(1, calls.get(top, 1) // min(K, 3))
     achieved = alg_bytes.get(top, 0) / (per_step[top] / n_top * 1e-3) / 1e9 if top in alg_bytes else None
     roofline = {
         "kernel": top, "bound": "hbm", "achieved": achieved, "peak": hbm_peak, "unit": "GB/s",
-        "frac": (achieved / hbm_peak) if achieved else None, "traffic": None,
+        "frac": (achieved / hbm_peak) if achieved else None,
+        "traffic": traffic.get(top, {}).get("dram_bytes_per_launch") if traffic.get("rays") == B else None,
+        "algorithmic_bytes_per_launch": alg_bytes.get(top),
         "peak_source": "MEASURED_PEAKS.json hbm_gbs" if peaks else "fallback 6650 GB/s (B200_PROFILING.md)",
-        "note": "algorithmic bytes = table gathers (+ gradient scatters) per SURVEY 8d; the fp16 table is "
-                "L2-resident, so this is table traffic served by L2, quoted against the HBM copy peak",
+        "note": "algorithmic bytes = table gathers / gradient scatters per SURVEY 8d (each 2-feature RED counted as "
+                "4 B like the reference's half2 atomics); this traffic is served by L2 (the table and most of its "
+                "gradient are L2-resident), so frac is table traffic quoted against the HBM copy peak",
+        "achieved_gbs_by_kernel": {k: round(alg_bytes[k] / (per_step[k] / max(1, calls.get(k, 1) // min(K, 3)) * 1e-3) / 1e9, 1)
+                                   for k in per_step if k in alg_bytes},
         "ms_per_step_by_kernel": {k: round(v, 3) for k, v in sorted(per_step.items(), key=lambda kv: -kv[1])},
     }
 
@@ -272,6 +291,19 @@ def run_native(args) -> None:
     e2e = {"value": world * B * 1e3 / ms_e2e, "unit": UNIT, "h2d_bytes_per_step": h2d_bytes, "d2h_bytes_per_step": 4,
            "ms_per_step": ms_e2e}
 
+    # ---- extraction: voxel queries/s (BASELINE.json metric, second half), inputs resident in HBM ----
+    n_vox = 32768 * 81
+    gen = torch.Generator(device=dev).manual_seed(rank)
+    vox = (torch.rand((n_vox, 3), device=dev, dtype=torch.float64, generator=gen) * 2 - 1) * 0.95
+    pipe.eval()
+    with torch.no_grad():
+        for _ in range(2):
+            pipe.extract(vox)
+        ms_ext = timed(5, lambda i: pipe.extract(vox)) / 5
+    pipe.train()
+    extract = {"value": world * n_vox * 1e3 / ms_ext, "unit": "voxels/s", "voxels_per_call_per_gpu": n_vox,
+               "ms_per_call": ms_ext}
+
     if rank != 0:
         return
     cpu = None if args.no_cpu_baseline else cpu_step_rate(args.samples, args.cpu_rays, 2, 1)
@@ -285,7 +317,7 @@ def run_native(args) -> None:
             "rays_per_gpu": B, "samples_per_ray": args.samples, "parallelism": f"dp{world}",
             "l2": "inputs larger than L2: per-step working set (x01, sigma, colour, gradients) is several GB",
         },
-        "clocks": clock_info, "e2e": e2e, "gpu_launches": launches, "roofline": roofline,
+        "clocks": clock_info, "e2e": e2e, "gpu_launches": launches, "roofline": roofline, "extract": extract,
         "cpu_baseline": {k: cpu[k] for k in ("value", "unit", "cores", "kind", "sample")} if cpu else None,
     }
     print(json.dumps(line))
