@@ -64,18 +64,31 @@ ATM_HD float stratified_z(float bin_lo, float t, int n_bins, float len) {
 
 ATM_HD void ecef_to_geodetic(double x, double y, double z, double& lat_deg, double& lon_deg,
                              double& alt) {
+  // Same quantities as the reference, with the sines / cosines of the two auxiliary angles taken
+  // algebraically instead of through atan2 -> sin/cos:
+  //   u   = atan2(z/d, a/b)  is only used as sin(u), cos(u)       = p/h, q/h with h = hypot(p, q)
+  //   phi = atan2(num, den)  is returned, and used as sin/cos(phi) = num/g, den/g
+  //   cos(lam) = x / d
+  // This removes one atan2 and five sin/cos evaluations per sample (the kernel is bound by the
+  // FP64 pipe); the results agree with the literal form to a few float64 ulps.
   const double A = ATM_WGS_A, B = ATM_WGS_B;
   const double E_SQ = (A * A - B * B) / (A * A);
   const double EP_SQ = (A * A - B * B) / (B * B);
   const double PI = 3.141592653589793;
   const double lam = atan2(y, x);
   const double d = sqrt(x * x + y * y);
-  const double u = atan2(z / d, 0.0 + A / B);
-  const double su = sin(u), cu = cos(u);
-  const double phi = atan2(z + (EP_SQ * B) * ((su * su) * su), d - (E_SQ * A) * ((cu * cu) * cu));
-  const double sp = sin(phi);
+  const double p = z / d, q = A / B;
+  const double h = sqrt(p * p + q * q);
+  const double su = p / h, cu = q / h;
+  const double num = z + (EP_SQ * B) * ((su * su) * su);
+  const double den = d - (E_SQ * A) * ((cu * cu) * cu);
+  const double phi = atan2(num, den);
+  const double g = sqrt(num * num + den * den);
+  const double sp = num / g, cp = den / g;
   const double n = A / sqrt(1.0 - (E_SQ * (sp * sp)));
-  alt = x / (cos(phi) * cos(lam)) - n;
+  // x == 0 is the reference's singular meridian (cos(lam) ~ 6e-17): keep its literal behaviour
+  const double cl = x != 0.0 ? x / d : cos(lam);
+  alt = x / (cp * cl) - n;
   lat_deg = phi * 180.0 / PI;
   lon_deg = lam * 180.0 / PI;
 }

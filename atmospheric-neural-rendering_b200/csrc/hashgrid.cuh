@@ -223,6 +223,40 @@ __device__ __forceinline__ void level_corners3(const LevelRow& lv, const float (
   level_corners3(lv, x, e, w, cell);
 }
 
+// the two halves of level_corners3, for callers that need the entries only once per cell run
+__device__ __forceinline__ void corner_weights3(const float (&frac)[3], float (&w)[8]) {
+  const float wx[2] = {1.0f - frac[0], frac[0]};
+  const float wy[2] = {1.0f - frac[1], frac[1]};
+  const float wz[2] = {1.0f - frac[2], frac[2]};
+#pragma unroll
+  for (int c = 0; c < 8; ++c) w[c] = (wx[c & 1] * wy[(c >> 1) & 1]) * wz[c >> 2];
+}
+__device__ __forceinline__ void corner_entries3(const LevelRow& lv, const uint32_t (&cell)[3], uint32_t (&e)[8]) {
+  const bool hashed = lv.hashed & 1u;
+  uint32_t t0[3], t1[3];
+  t0[0] = cell[0], t1[0] = cell[0] + 1u;
+  if (hashed) {
+    t0[1] = cell[1] * 2654435761u, t1[1] = t0[1] + 2654435761u;
+    t0[2] = cell[2] * 805459861u, t1[2] = t0[2] + 805459861u;
+  } else {
+    t0[1] = cell[1] * lv.stride1, t1[1] = t0[1] + lv.stride1;
+    t0[2] = cell[2] * lv.stride2, t1[2] = t0[2] + lv.stride2;
+  }
+  const uint32_t mask = lv.size - 1u;
+  const bool fast_hash = lv.hashed == 3u;
+#pragma unroll
+  for (int c = 0; c < 8; ++c) {
+    const uint32_t a = (c & 1) ? t1[0] : t0[0], b = (c & 2) ? t1[1] : t0[1], d = (c & 4) ? t1[2] : t0[2];
+    uint32_t idx = hashed ? (a ^ b ^ d) : (a + b + d);
+    if (fast_hash) {
+      idx &= mask;
+    } else if (idx >= lv.size) {
+      idx = (idx - lv.size < lv.size) ? idx - lv.size : index_mod_slow(idx, lv.size);
+    }
+    e[c] = idx;
+  }
+}
+
 // Warp-aggregated scatter of one level. The 32 lanes of a warp hold consecutive samples of a ray,
 // so lanes that fall into the same grid cell form contiguous runs; the 8 corner contributions
 // (2 features each) of a run are summed with a segmented shuffle reduction and written by the

@@ -822,10 +822,16 @@ k_field_bwd_tc2(atmonr_grid_t g, const __half* __restrict__ pos_w, const __half*
       const float* stage = reinterpret_cast<const float*>(smem + bwd2::kX);
       const int64_t row0 = tile * bwd2::kRows + grp * 16;
       float acc[16];
-      uint32_t e_run[8], c_run[3] = {0xffffffffu, 0xffffffffu, 0xffffffffu};
+      uint32_t c_run[3] = {0xffffffffu, 0xffffffffu, 0xffffffffu};
       bool open = false;
 #pragma unroll
       for (int c = 0; c < 16; ++c) acc[c] = 0.0f;
+      auto flush = [&]() {  // entries are only needed here, once per run of samples in one cell
+        uint32_t e[8];
+        corner_entries3(L, c_run, e);
+#pragma unroll
+        for (int c = 0; c < 8; ++c) red_add_f32x2(base + 2 * (size_t)e[c], acc[2 * c], acc[2 * c + 1]);
+      };
 #pragma unroll 1
       for (int r = 0; r < 16; ++r) {
         const int64_t gi = row0 + r;
@@ -835,12 +841,12 @@ k_field_bwd_tc2(atmonr_grid_t g, const __half* __restrict__ pos_w, const __half*
         if (!ATM_SCATTER_ON) continue;
         if (d.x == 0.0f && d.y == 0.0f) continue;
         const float p[3] = {x01[3 * gi], x01[3 * gi + 1], x01[3 * gi + 2]};
-        uint32_t e[8], cell[3];
-        float w[8];
-        level_corners3(L, p, e, w, cell);
+        uint32_t cell[3];
+        float frac[3], w[8];
+        grid_cell<3>(p, L.scale, cell, frac);
+        corner_weights3(frac, w);
         if (open && (cell[0] != c_run[0] || cell[1] != c_run[1] || cell[2] != c_run[2])) {
-#pragma unroll
-          for (int c = 0; c < 8; ++c) red_add_f32x2(base + 2 * (size_t)e_run[c], acc[2 * c], acc[2 * c + 1]);
+          flush();
 #pragma unroll
           for (int c = 0; c < 16; ++c) acc[c] = 0.0f;
         }
@@ -848,15 +854,11 @@ k_field_bwd_tc2(atmonr_grid_t g, const __half* __restrict__ pos_w, const __half*
         for (int c = 0; c < 8; ++c) {
           acc[2 * c] = fmaf(w[c], d.x, acc[2 * c]);
           acc[2 * c + 1] = fmaf(w[c], d.y, acc[2 * c + 1]);
-          e_run[c] = e[c];
         }
         c_run[0] = cell[0], c_run[1] = cell[1], c_run[2] = cell[2];
         open = true;
       }
-      if (open) {
-#pragma unroll
-        for (int c = 0; c < 8; ++c) red_add_f32x2(base + 2 * (size_t)e_run[c], acc[2 * c], acc[2 * c + 1]);
-      }
+      if (open) flush();
     }
     __syncthreads();  // the staging area is the next tile's X/H
   }

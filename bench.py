@@ -329,6 +329,8 @@ def main():
         run_reference(args)
     else:
         run_native(args)
+    if torch.distributed.is_available() and torch.distributed.is_initialized():
+        torch.distributed.destroy_process_group()
 
 
 if __name__ == "__main__":
