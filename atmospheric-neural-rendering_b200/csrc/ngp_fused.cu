@@ -1096,7 +1096,7 @@ int atmonr_ngp_field_fwd_tc(const atmonr_grid_t* g, const void* table, const atm
   ATM_REQUIRE(M < ((int64_t)1 << 31), "atmonr_ngp_field_fwd_tc", "B*N must be below 2^31 per call (chunk the batch)");
   // the 256-row variant merges gathers over runs of samples in one cell; its serial per-thread
   // gather chain currently loses to the 128-row kernel (44 vs 33 ms at 2^18 rays): opt-in only
-  static const bool use_wide = getenv("ATMONR_FWD_WIDE") != nullptr;
+  const bool use_wide = getenv("ATMONR_FWD_WIDE") != nullptr;  // read per call: tests toggle it
   if (use_wide) {
     cudaError_t e2 = cudaFuncSetAttribute(k_field_fwd_tc2, cudaFuncAttributeMaxDynamicSharedMemorySize, fwd2::kBytes);
     if (e2 != cudaSuccess) return fail("atmonr_ngp_field_fwd_tc", cudaGetErrorString(e2));
@@ -1131,7 +1131,7 @@ int atmonr_ngp_field_bwd_tc(const atmonr_grid_t* g, const void* table, const atm
   const int64_t M = B * N;
   if (M == 0) return 0;
   ATM_REQUIRE(M < ((int64_t)1 << 31), "atmonr_ngp_field_bwd_tc", "B*N must be below 2^31 per call (chunk the batch)");
-  static const bool use_wide = getenv("ATMONR_BWD_NARROW") == nullptr;
+  const bool use_wide = getenv("ATMONR_BWD_NARROW") == nullptr;  // read per call: tests toggle it
   if (enc && use_wide) {
     cudaError_t e2 = cudaFuncSetAttribute(k_field_bwd_tc2, cudaFuncAttributeMaxDynamicSharedMemorySize, bwd2::kBytes);
     if (e2 != cudaSuccess) return fail("atmonr_ngp_field_bwd_tc", cudaGetErrorString(e2));

@@ -133,6 +133,78 @@ def cpu_step_rate(samples: int, rays: int, steps: int, warmup: int) -> dict:
             "ms_per_step": sec * 1e3}
 
 
+def nerf_config() -> dict:
+    return json.load(open(os.path.join(ROOT, "configs", "nerf.json")))
+
+
+def cpu_nerf_rate(rays: int = 1024, steps: int = 2, warmup: int = 1) -> dict:
+    """the reference's pure-PyTorch NeRF path on the host cores. The
+    reference tree is not present on the GPU box, so its pinned restatement (oracle/nerf.py,
+    bit-checked against the reference's NeRFPipeline in tests/test_oracle_golden.py) is timed:
+    forward + loss + backward + Adam, configs/nerf.json pipeline section (N_c 64, N_f 128,
+    hidden 256), B = `rays`, density noise on (training mode)."""
+    from helpers import take, tiny_scene
+    from oracle.nerf import NeRFOracle
+
+    torch.set_num_threads(os.cpu_count() or 1)
+    scene = tiny_scene(h=16, w=16, n_views=9)
+    cfg = nerf_config()["pipeline"]
+    orc = NeRFOracle(cfg, scene.frame)
+    params = orc.init_params(0)
+    opt = torch.optim.Adam([p for m in params.values() for p in m.values()], lr=5e-4)
+    g = torch.Generator().manual_seed(0)
+    n = scene.batch["origin"].shape[0]
+    nc, nf = cfg["sampler"]["N_c"], cfg["sampler"]["N_f"]
+    times = []
+    for it in range(warmup + steps):
+        batch = take(scene.batch, torch.randint(0, n, (rays,), generator=g))
+        u_c, u_f = torch.rand(rays, nc, generator=g), torch.rand(rays, nf, generator=g)
+        noise_c = torch.randn(rays * nc, 1, generator=g)
+        noise_f = torch.randn(rays * (nc + nf), cfg["num_bands"], generator=g)
+        t0 = time.perf_counter()
+        res = orc.forward(batch, params, u_c, u_f, noise_c, noise_f)
+        loss = orc.loss(batch, res)
+        opt.zero_grad()
+        loss.backward()
+        opt.step()
+        if it >= warmup:
+            times.append(time.perf_counter() - t0)
+    sec = sum(times) / len(times)
+    return {"value": rays / sec, "unit": UNIT, "cores": torch.get_num_threads(), "kind": "port",
+            "sample": f"{steps} steps x {rays} rays x ({nc}+{nc + nf}) samples, oracle/nerf.py (torch CPU fp32), {sec:.2f} s/step"}
+
+
+def gpu_nerf_rate(dataset, dev, rays: int = 4096, steps: int = 5) -> dict:
+    """The native NeRF pipeline (configs/nerf.json) on this GPU: rays/s of fwd + loss + bwd + Adam."""
+    from atmonr.batch_loader import BatchLoader
+    from atmonr.pipelines.factory import get_pipeline
+
+    cfg = nerf_config()
+    pipe = get_pipeline(cfg["pipeline"], dataset)
+    pipe.send_tensors_to(dev.index)
+    opt = pipe.get_optimizer(cfg["trainer"]["optimizer"])
+    batch = next(iter(BatchLoader(dataset, batch_size=rays, shuffle=True, seed=7)))
+
+    def step():
+        loss = pipe.compute_loss(batch, pipe.forward(batch))
+        opt.zero_grad()
+        loss.backward()
+        opt.step()
+
+    for _ in range(3):
+        step()
+    torch.cuda.synchronize()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(steps):
+        step()
+    e1.record()
+    torch.cuda.synchronize()
+    ms = e0.elapsed_time(e1) / steps
+    return {"value": rays * 1e3 / ms, "unit": UNIT, "rays_per_step": rays, "ms_per_step": ms,
+            "note": "configs/nerf.json, coarse 64 + fine 192 samples, hidden 256; MLP layers are cuBLAS fp32 GEMMs"}
+
+
 def run_reference(args) -> None:
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
@@ -306,7 +378,9 @@ def run_native(args) -> None:
 
     if rank != 0:
         return
+    nerf = gpu_nerf_rate(dataset, dev)
     cpu = None if args.no_cpu_baseline else cpu_step_rate(args.samples, args.cpu_rays, 2, 1)
+    cpu_nerf = None if args.no_cpu_baseline else cpu_nerf_rate()
     line = {
         "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": K, "warmup": W,
         "ms_per_step": ms_step, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
@@ -319,6 +393,7 @@ def run_native(args) -> None:
         },
         "clocks": clock_info, "e2e": e2e, "gpu_launches": launches, "roofline": roofline, "extract": extract,
         "cpu_baseline": {k: cpu[k] for k in ("value", "unit", "cores", "kind", "sample")} if cpu else None,
+        "nerf": nerf, "cpu_baseline_nerf": cpu_nerf,
     }
     print(json.dumps(line))
 
