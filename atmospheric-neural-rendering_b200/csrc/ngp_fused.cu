@@ -809,14 +809,17 @@ k_field_bwd_tc2(atmonr_grid_t g, const __half* __restrict__ pos_w, const __half*
     tmem_ld32(my32, v);
     {
       float* srow = reinterpret_cast<float*>(smem + bwd2::kX) + tid * 32;
+      const int swz = (tid ^ (tid >> 4)) & 7;
 #pragma unroll
       for (int k = 0; k < 8; ++k)   // 16-byte chunks, XOR-swizzled by the row to spread banks
-        *reinterpret_cast<float4*>(srow + ((k ^ (tid & 7)) << 2)) =
+        *reinterpret_cast<float4*>(srow + ((k ^ swz) << 2)) =
             make_float4(v[4 * k] * invS, v[4 * k + 1] * invS, v[4 * k + 2] * invS, v[4 * k + 3] * invS);
     }
     __syncthreads();
     {
-      const int grp = tid >> 4, lvl = tid & 15;
+      // a warp holds 2 levels x 16 sample groups: cell runs of one level end at similar rates,
+      // so coarse-level warps almost never execute the flush path
+      const int grp = tid & 15, lvl = tid >> 4;
       const LevelRow L = lv[lvl];
       float* base = dtable + 2 * (size_t)L.offset;
       const float* stage = reinterpret_cast<const float*>(smem + bwd2::kX);
@@ -837,7 +840,8 @@ k_field_bwd_tc2(atmonr_grid_t g, const __half* __restrict__ pos_w, const __half*
         const int64_t gi = row0 + r;
         if (gi >= M) break;
         const int row = grp * 16 + r;
-        const float2 d = *reinterpret_cast<const float2*>(stage + row * 32 + ((((lvl >> 1) ^ (row & 7)) << 2) | ((lvl & 1) << 1)));
+        const float2 d = *reinterpret_cast<const float2*>(
+            stage + row * 32 + ((((lvl >> 1) ^ ((row ^ (row >> 4)) & 7)) << 2) | ((lvl & 1) << 1)));
         if (!ATM_SCATTER_ON) continue;
         if (d.x == 0.0f && d.y == 0.0f) continue;
         const float p[3] = {x01[3 * gi], x01[3 * gi + 1], x01[3 * gi + 2]};
