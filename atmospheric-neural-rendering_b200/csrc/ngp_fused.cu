@@ -25,7 +25,7 @@
 #define ATM_DW
 #endif
 #ifdef ATM_DEBUG_NO_SCATTER
-#define ATM_SCATTER_ON (d0 == 123456.0f)
+#define ATM_SCATTER_ON (d.x == 123456.0f)
 #else
 #define ATM_SCATTER_ON true
 #endif
@@ -592,7 +592,8 @@ constexpr int kH2 = kH1 + 16384;
 constexpr int kDO = kH2 + 16384;      // [256][16]
 constexpr int kW = kDO + 8192;        // weights last: they also absorb the 128-row over-reads
 constexpr int kLv = kW + 8192;
-constexpr int kBar = kLv + 512;
+constexpr int kPos = kLv + 512;       // sample positions of the tile, 3 x 272 floats (skewed rows)
+constexpr int kBar = kPos + 3 * 272 * 4;
 constexpr int kBar2 = kBar + 8;
 constexpr int kTmemPtr = kBar2 + 8;
 constexpr int kBytes = kTmemPtr + 8;
@@ -675,6 +676,14 @@ k_field_bwd_tc2(atmonr_grid_t g, const __half* __restrict__ pos_w, const __half*
     const int64_t j = valid ? i : M - 1;
     if (seen_tile) mbar_wait(bar2, phase2), phase2 ^= 1;
     const uint4* enc_row = reinterpret_cast<const uint4*>(enc_in + j * 32);
+    // this row's position: needed only by the scatter at the end of the tile; fetched now so the
+    // global-load latency hides behind the whole MLP phase (row index skewed by row/16 so that the
+    // scatter's 16-rows-apart reads hit distinct banks)
+    {
+      float* pos = reinterpret_cast<float*>(smem + bwd2::kPos);
+      const int at = tid + (tid >> 4);
+      pos[at] = x01[3 * j], pos[272 + at] = x01[3 * j + 1], pos[544 + at] = x01[3 * j + 2];
+    }
     // ---------------- recompute the activations ----------------
 #pragma unroll
     for (int cc = 0; cc < 4; ++cc) st_chunk(X, tid, cc, 32, enc_row[cc]);
@@ -844,7 +853,8 @@ k_field_bwd_tc2(atmonr_grid_t g, const __half* __restrict__ pos_w, const __half*
             stage + row * 32 + ((((lvl >> 1) ^ ((row ^ (row >> 4)) & 7)) << 2) | ((lvl & 1) << 1)));
         if (!ATM_SCATTER_ON) continue;
         if (d.x == 0.0f && d.y == 0.0f) continue;
-        const float p[3] = {x01[3 * gi], x01[3 * gi + 1], x01[3 * gi + 2]};
+        const float* pos = reinterpret_cast<const float*>(smem + bwd2::kPos) + row + (row >> 4);
+        const float p[3] = {pos[0], pos[272], pos[544]};
         uint32_t cell[3];
         float frac[3], w[8];
         grid_cell<3>(p, L.scale, cell, frac);
