@@ -181,80 +181,82 @@ __device__ __forceinline__ void load_level_table(const atmonr_grid_t& g, LevelRo
   }
 }
 
-// corner entries + weights of one level from a LevelRow (3-D); bit-identical to level_corners<3>
-__device__ __forceinline__ void level_corners3(const LevelRow& lv, const float (&x)[3], uint32_t (&e)[8],
-                                               float (&w)[8], uint32_t (&cell)[3]) {
-  float frac[3];
-  grid_cell<3>(x, lv.scale, cell, frac);
-  const bool hashed = lv.hashed & 1u;
-  uint32_t t0[3], t1[3];
-  if (hashed) {
-    t0[0] = cell[0], t1[0] = cell[0] + 1u;
-    t0[1] = cell[1] * 2654435761u, t1[1] = t0[1] + 2654435761u;
-    t0[2] = cell[2] * 805459861u, t1[2] = t0[2] + 805459861u;
-  } else {
-    t0[0] = cell[0], t1[0] = cell[0] + 1u;
-    t0[1] = cell[1] * lv.stride1, t1[1] = t0[1] + lv.stride1;
-    t0[2] = cell[2] * lv.stride2, t1[2] = t0[2] + lv.stride2;
-  }
-  const float wx[2] = {1.0f - frac[0], frac[0]};
-  const float wy[2] = {1.0f - frac[1], frac[1]};
-  const float wz[2] = {1.0f - frac[2], frac[2]};
-  const uint32_t mask = lv.size - 1u;
-  const bool fast_hash = lv.hashed == 3u;
-#pragma unroll
-  for (int c = 0; c < 8; ++c) {
-    const int ix = c & 1, iy = (c >> 1) & 1, iz = c >> 2;
-    const uint32_t a = ix ? t1[0] : t0[0], b = iy ? t1[1] : t0[1], d = iz ? t1[2] : t0[2];
-    uint32_t idx = hashed ? (a ^ b ^ d) : (a + b + d);
-    if (fast_hash) {
-      idx &= mask;
-    } else if (idx >= lv.size) {
-      idx = (idx - lv.size < lv.size) ? idx - lv.size : index_mod_slow(idx, lv.size);
-    }
-    e[c] = idx;
-    w[c] = (wx[ix] * wy[iy]) * wz[iz];
-  }
-}
-
-__device__ __forceinline__ void level_corners3(const LevelRow& lv, const float (&x)[3], uint32_t (&e)[8],
-                                               float (&w)[8]) {
-  uint32_t cell[3];
-  level_corners3(lv, x, e, w, cell);
-}
-
 // the two halves of level_corners3, for callers that need the entries only once per cell run
 __device__ __forceinline__ void corner_weights3(const float (&frac)[3], float (&w)[8]) {
   const float wx[2] = {1.0f - frac[0], frac[0]};
   const float wy[2] = {1.0f - frac[1], frac[1]};
   const float wz[2] = {1.0f - frac[2], frac[2]};
+  const float wxy[4] = {wx[0] * wy[0], wx[1] * wy[0], wx[0] * wy[1], wx[1] * wy[1]};
 #pragma unroll
-  for (int c = 0; c < 8; ++c) w[c] = (wx[c & 1] * wy[(c >> 1) & 1]) * wz[c >> 2];
+  for (int c = 0; c < 8; ++c) w[c] = wxy[c & 3] * wz[c >> 2];
+}
+
+// Entries of the 8 corners of `cell`, bit-identical to grid_entry() of every corner. Two tight
+// paths cover a regular table: hashed levels with a power-of-two size (three-input XORs and one
+// mask per corner) and dense levels whose 8 corners lie inside the level (one three-input add per
+// corner: the corner with all +1 is the largest, so one compare proves that no modulo is needed).
+// Anything else (coordinates outside [0,1], wrap at the upper boundary, odd sizes) takes the
+// general path.
+__device__ __forceinline__ uint32_t xor_and(uint32_t a, uint32_t b, uint32_t mask) {  // (a ^ b) & mask, one LOP3
+  uint32_t r;
+  asm("lop3.b32 %0, %1, %2, %3, 0x28;" : "=r"(r) : "r"(a), "r"(b), "r"(mask));
+  return r;
+}
+__device__ __forceinline__ uint32_t xor2(uint32_t a, uint32_t b) {  // kept opaque so the pair terms are shared
+  uint32_t r;
+  asm("xor.b32 %0, %1, %2;" : "=r"(r) : "r"(a), "r"(b));
+  return r;
 }
 __device__ __forceinline__ void corner_entries3(const LevelRow& lv, const uint32_t (&cell)[3], uint32_t (&e)[8]) {
-  const bool hashed = lv.hashed & 1u;
-  uint32_t t0[3], t1[3];
-  t0[0] = cell[0], t1[0] = cell[0] + 1u;
-  if (hashed) {
-    t0[1] = cell[1] * 2654435761u, t1[1] = t0[1] + 2654435761u;
-    t0[2] = cell[2] * 805459861u, t1[2] = t0[2] + 805459861u;
-  } else {
-    t0[1] = cell[1] * lv.stride1, t1[1] = t0[1] + lv.stride1;
-    t0[2] = cell[2] * lv.stride2, t1[2] = t0[2] + lv.stride2;
-  }
-  const uint32_t mask = lv.size - 1u;
-  const bool fast_hash = lv.hashed == 3u;
+  const uint32_t x[2] = {cell[0], cell[0] + 1u};
+  if (lv.hashed == 3u) {  // hashed, power-of-two size
+    const uint32_t y0 = cell[1] * 2654435761u, y1 = y0 + 2654435761u;
+    const uint32_t z0 = cell[2] * 805459861u, z1 = z0 + 805459861u;
+    const uint32_t yz[4] = {xor2(y0, z0), xor2(y1, z0), xor2(y0, z1), xor2(y1, z1)};
+    const uint32_t mask = lv.size - 1u;
 #pragma unroll
-  for (int c = 0; c < 8; ++c) {
-    const uint32_t a = (c & 1) ? t1[0] : t0[0], b = (c & 2) ? t1[1] : t0[1], d = (c & 4) ? t1[2] : t0[2];
-    uint32_t idx = hashed ? (a ^ b ^ d) : (a + b + d);
-    if (fast_hash) {
-      idx &= mask;
-    } else if (idx >= lv.size) {
-      idx = (idx - lv.size < lv.size) ? idx - lv.size : index_mod_slow(idx, lv.size);
+    for (int c = 0; c < 8; ++c) e[c] = xor_and(x[c & 1], yz[c >> 1], mask);
+  } else if (lv.hashed & 1u) {  // hashed, any size (not produced by atmonr_grid_layout)
+    const uint32_t y0 = cell[1] * 2654435761u, z0 = cell[2] * 805459861u;
+    const uint32_t y[2] = {y0, y0 + 2654435761u}, z[2] = {z0, z0 + 805459861u};
+#pragma unroll
+    for (int c = 0; c < 8; ++c) e[c] = index_mod_slow(x[c & 1] ^ y[(c >> 1) & 1] ^ z[c >> 2], lv.size);
+  } else {  // dense
+    const uint32_t y0 = cell[1] * lv.stride1, y1 = y0 + lv.stride1;
+    const uint32_t z0 = cell[2] * lv.stride2, z1 = z0 + lv.stride2;
+    const uint32_t yz[4] = {y0 + z0, y1 + z0, y0 + z1, y1 + z1};
+#pragma unroll
+    for (int c = 0; c < 8; ++c) e[c] = x[c & 1] + yz[c >> 1];
+    // cells below 2^16 cannot wrap uint32 (res^3 of a dense level fits 32 bits), so e[7] is the largest
+    if ((cell[0] | cell[1] | cell[2]) >= 65536u || e[7] >= lv.size) {
+#pragma unroll
+      for (int c = 0; c < 8; ++c)
+        if (e[c] >= lv.size) e[c] = (e[c] - lv.size < lv.size) ? e[c] - lv.size : index_mod_slow(e[c], lv.size);
     }
-    e[c] = idx;
   }
+}
+
+// &table[entry] with one 32x32+64-bit multiply-add (the compiler otherwise spends four
+// instructions per corner on 64-bit address arithmetic)
+template <typename T>
+__device__ __forceinline__ T* entry_ptr(T* base, uint32_t entry) {
+  T* p;
+  asm("mad.wide.u32 %0, %1, %2, %3;" : "=l"(p) : "r"(entry), "n"(sizeof(T)), "l"(base));
+  return p;
+}
+
+// corner entries + weights of one level from a LevelRow (3-D); bit-identical to level_corners<3>
+__device__ __forceinline__ void level_corners3(const LevelRow& lv, const float (&x)[3], uint32_t (&e)[8],
+                                               float (&w)[8], uint32_t (&cell)[3]) {
+  float frac[3];
+  grid_cell<3>(x, lv.scale, cell, frac);
+  corner_entries3(lv, cell, e);
+  corner_weights3(frac, w);
+}
+__device__ __forceinline__ void level_corners3(const LevelRow& lv, const float (&x)[3], uint32_t (&e)[8],
+                                               float (&w)[8]) {
+  uint32_t cell[3];
+  level_corners3(lv, x, e, w, cell);
 }
 
 // Warp-aggregated scatter of one level. The 32 lanes of a warp hold consecutive samples of a ray,

@@ -101,13 +101,18 @@ constexpr int kW2P = kW1P + 2048;   // pos_mlp output   [16][32]
 constexpr int kWD1 = kW2P + 1024;   // dir_mlp layer 0  [32][32]
 constexpr int kWD2 = kWD1 + 2048;   // dir_mlp layer 1  [32][32]
 constexpr int kWD3 = kWD2 + 2048;   // dir_mlp output   [16][32]
-constexpr int kA0 = kWD3 + 1024;    // activation tile  [128][32]
-constexpr int kA1 = kA0 + 8192;     // activation tile  [128][32]
-constexpr int kLv = kA1 + 8192;     // level table, 16 x 32 B
+constexpr int kA = kWD3 + 1024;     // activation tile  [128][32], rewritten in place layer after layer
+constexpr int kLv = kA + 8192;      // level table, 16 x 32 B
 constexpr int kBar = kLv + 512;
 constexpr int kTmemPtr = kBar + 8;
 constexpr int kBytes = kTmemPtr + 8;
-constexpr uint32_t kTmemCols = 64;  // [0,32): hidden accumulator, [32,48): 16-wide outputs
+// one 32-column accumulator; the 16-wide outputs reuse its first columns (a layer's accumulator
+// has been read by every thread before the next layer is issued)
+constexpr uint32_t kTmemCols = 32;
+#ifndef ATM_FWD_CTAS
+#define ATM_FWD_CTAS 10
+#endif
+constexpr int kCtasPerSm = ATM_FWD_CTAS;  // 10 x 4 warps per SM at <= 48 registers; smem 17 KB and 32 TMEM columns per CTA
 }  // namespace fwd
 
 // all five weight matrices -> tile layout
@@ -120,6 +125,17 @@ __device__ __forceinline__ void load_field_weights(uint8_t* smem, const __half* 
   load_matrix_tile(dir_w + 2048, smem + fwd::kWD3, 16, 32);
 }
 
+// two fp32 -> packed fp16 pair (low half = a), optionally through ReLU, in one instruction
+template <bool RELU>
+__device__ __forceinline__ uint32_t pack_h2_act(float a, float b) {
+  uint32_t r;
+  if (RELU)
+    asm("cvt.rn.relu.f16x2.f32 %0, %1, %2;" : "=r"(r) : "f"(b), "f"(a));
+  else
+    asm("cvt.rn.f16x2.f32 %0, %1, %2;" : "=r"(r) : "f"(b), "f"(a));
+  return r;
+}
+
 // store one 32-wide fp16 row (optionally after ReLU) into an activation tile
 template <bool RELU>
 __device__ __forceinline__ void store_row32(uint8_t* tile, int r, const float (&v)[32]) {
@@ -128,46 +144,74 @@ __device__ __forceinline__ void store_row32(uint8_t* tile, int r, const float (&
     uint4 q;
     uint32_t* qp = reinterpret_cast<uint32_t*>(&q);
 #pragma unroll
-    for (int j = 0; j < 4; ++j) {
-      float a = v[cc * 8 + 2 * j], b = v[cc * 8 + 2 * j + 1];
-      if (RELU) a = fmaxf(a, 0.0f), b = fmaxf(b, 0.0f);
-      qp[j] = pack_h2(a, b);
-    }
-    st_chunk(tile, r, cc, 32, q);
-  }
-}
-__device__ __forceinline__ void store_row32_h2(uint8_t* tile, int r, const __half2 (&h)[16]) {
-#pragma unroll
-  for (int cc = 0; cc < 4; ++cc) {
-    uint4 q;
-    uint32_t* qp = reinterpret_cast<uint32_t*>(&q);
-#pragma unroll
-    for (int j = 0; j < 4; ++j) qp[j] = *reinterpret_cast<const uint32_t*>(&h[cc * 4 + j]);
+    for (int j = 0; j < 4; ++j) qp[j] = pack_h2_act<RELU>(v[cc * 8 + 2 * j], v[cc * 8 + 2 * j + 1]);
     st_chunk(tile, r, cc, 32, q);
   }
 }
 
-// Hash-grid encoding of one point written straight into row r of an activation tile (rolled level
-// loop, see hashgrid.cuh). Same arithmetic as hash_encode().
+// columns [16*half, 16*half+16) of row r
+template <bool RELU>
+__device__ __forceinline__ void store_half16(uint8_t* tile, int r, int half, const float (&v)[16]) {
+#pragma unroll
+  for (int cc = 0; cc < 2; ++cc) {
+    uint4 q;
+    uint32_t* qp = reinterpret_cast<uint32_t*>(&q);
+#pragma unroll
+    for (int j = 0; j < 4; ++j) qp[j] = pack_h2_act<RELU>(v[cc * 8 + 2 * j], v[cc * 8 + 2 * j + 1]);
+    st_chunk(tile, r, 2 * half + cc, 32, q);
+  }
+}
+// hidden-layer epilogue: this thread's 32 accumulator columns -> ReLU -> fp16 row of the tile, in
+// two 16-column halves (a 32-column tcgen05.ld would pin 32 registers at once)
+__device__ __forceinline__ void relu_acc_to_tile(uint32_t taddr, uint8_t* tile, int r) {
+  float h[16];
+  tmem_ld16(taddr, h);
+  store_half16<true>(tile, r, 0, h);
+  tmem_ld16(taddr + 16, h);
+  store_half16<true>(tile, r, 1, h);
+}
+
+// ---- hash-grid encoding of one point, software-pipelined over the levels ------------------------
+// level_issue() computes the 8 corner entries of a level and issues the 8 table gathers;
+// level_finish() interpolates. The loop issues level l+1 before it consumes level l, so a thread
+// always has 8-16 gathers in flight. Same arithmetic as hash_encode().
+__device__ __forceinline__ void level_issue(const LevelRow& L, const __half2* __restrict__ table, const float (&p)[3],
+                                            uint32_t (&v)[8], float (&frac)[3]) {
+  uint32_t cell[3], e[8];
+  grid_cell<3>(p, L.scale, cell, frac);
+  corner_entries3(L, cell, e);
+  const uint32_t* base = reinterpret_cast<const uint32_t*>(table + L.offset);
+#pragma unroll
+  for (int c = 0; c < 8; ++c) v[c] = __ldg(entry_ptr(base, e[c]));
+}
+__device__ __forceinline__ uint32_t level_finish(const uint32_t (&v)[8], const float (&frac)[3]) {
+  float w[8];
+  corner_weights3(frac, w);
+  float a0 = 0.0f, a1 = 0.0f;
+#pragma unroll
+  for (int c = 0; c < 8; ++c) {
+    const float2 f = __half22float2(*reinterpret_cast<const __half2*>(&v[c]));
+    a0 = fmaf(w[c], f.x, a0);
+    a1 = fmaf(w[c], f.y, a1);
+  }
+  return pack_h2_act<false>(a0, a1);
+}
 __device__ __forceinline__ void encode_to_tile(const LevelRow* __restrict__ lv, const __half2* __restrict__ table,
                                                const float (&p)[3], uint8_t* tile, int r) {
-#pragma unroll 4
+  uint32_t vn[8];
+  float fn[3];
+  level_issue(lv[0], table, p, vn, fn);
+  uint8_t* row = tile + tile_off(r, 0, 32);
+#pragma unroll 2
   for (int l = 0; l < ATMONR_MAX_LEVELS; ++l) {
-    uint32_t e[8];
-    float w[8];
-    level_corners3(lv[l], p, e, w);
-    const __half2* base = table + lv[l].offset;
-    __half2 v[8];
+    uint32_t vc[8];
+    float fc[3];
 #pragma unroll
-    for (int c = 0; c < 8; ++c) v[c] = __ldg(base + e[c]);
-    float a0 = 0.0f, a1 = 0.0f;
-#pragma unroll
-    for (int c = 0; c < 8; ++c) {
-      const float2 f = __half22float2(v[c]);
-      a0 = fmaf(w[c], f.x, a0);
-      a1 = fmaf(w[c], f.y, a1);
-    }
-    *reinterpret_cast<uint32_t*>(tile + tile_off(r, 2 * l, 32)) = pack_h2(a0, a1);
+    for (int c = 0; c < 8; ++c) vc[c] = vn[c];
+    fc[0] = fn[0], fc[1] = fn[1], fc[2] = fn[2];
+    if (l + 1 < ATMONR_MAX_LEVELS) level_issue(lv[l + 1], table, p, vn, fn);
+    // features 2l, 2l+1 of row r: chunk l/4 (128 B apart), 4 bytes per level inside the chunk
+    *reinterpret_cast<uint32_t*>(row + (l >> 2) * kCore + (l & 3) * 4) = level_finish(vc, fc);
   }
 }
 
@@ -202,7 +246,7 @@ __device__ __forceinline__ void publish_and_sync() {
   __syncthreads();
 }
 
-__global__ void __launch_bounds__(128, 8)
+__global__ void __launch_bounds__(128, fwd::kCtasPerSm)
 k_field_fwd_tc(atmonr_grid_t g, const __half2* __restrict__ table, const __half* __restrict__ pos_w,
                const __half* __restrict__ dir_w, const float* __restrict__ x01, const float* __restrict__ dirs,
                int64_t M, int N, float* __restrict__ sigma_raw, float* __restrict__ color_raw,
@@ -221,67 +265,75 @@ k_field_fwd_tc(atmonr_grid_t g, const __half2* __restrict__ table, const __half*
   }
   publish_and_sync();
   tc_fence_after();
-  const uint32_t tmem = *tmem_ptr;
-  const uint32_t acc32 = tmem, acc16 = tmem + 32;
-  const uint32_t my32 = tmem_addr(tmem, warp, 0), my16 = tmem_addr(tmem, warp, 32);
-  const uint32_t sbase = smem_u32(smem);
-  uint8_t* A0 = smem + fwd::kA0;
-  uint8_t* A1 = smem + fwd::kA1;
+  const uint32_t acc = *tmem_ptr;
+  const uint32_t mine = tmem_addr(acc, warp, 0);
+  const uint32_t sbase = smem_u32(smem), sa = sbase + fwd::kA;
+  uint8_t* A = smem + fwd::kA;
   uint32_t phase = 0;
 
   for (int64_t tile = blockIdx.x; tile * kTile < M; tile += gridDim.x) {
     const int64_t i = tile * kTile + tid;
     const bool valid = i < M;
     const int64_t j = valid ? i : M - 1;
-    // ---- hash-grid encoding -> A0
+    // ---- hash-grid encoding -> A (the previous tile's last MMA has been waited for)
     {
       const float p[3] = {x01[3 * j], x01[3 * j + 1], x01[3 * j + 2]};
-      encode_to_tile(lv, table, p, A0, tid);
+      encode_to_tile(lv, table, p, A, tid);
       if (enc_out && valid) {
         uint4* dst = reinterpret_cast<uint4*>(enc_out + i * 32);
 #pragma unroll
-        for (int cc = 0; cc < 4; ++cc) dst[cc] = ld_chunk(A0, tid, cc, 32);
+        for (int cc = 0; cc < 4; ++cc) dst[cc] = ld_chunk(A, tid, cc, 32);
       }
     }
     publish_and_sync();
-    if (tid == 0) issue_layer<32>(acc32, sbase + fwd::kA0, sbase + fwd::kW1P, bar);
+    if (tid == 0) issue_layer<32>(acc, sa, sbase + fwd::kW1P, bar);
     mbar_wait(bar, phase), phase ^= 1;
     tc_fence_after();
-    float v[32];
-    tmem_ld32(my32, v);
-    store_row32<true>(A1, tid, v);
+    relu_acc_to_tile(mine, A, tid);
     publish_and_sync();
-    if (tid == 0) issue_layer<16>(acc16, sbase + fwd::kA1, sbase + fwd::kW2P, bar);
+    if (tid == 0) issue_layer<16>(acc, sa, sbase + fwd::kW2P, bar);
     mbar_wait(bar, phase), phase ^= 1;
     tc_fence_after();
-    float po[16];
-    tmem_ld16(my16, po);
-    if (valid) sigma_raw[i] = po[0];
-    dir_input_row(dirs + (size_t)((uint32_t)j / (uint32_t)N) * 3, po, v);
-    store_row32<false>(A0, tid, v);
+    {
+      // dir_mlp input row: [SH2(dir) | pos_out[1..15] | 1.0 x 13] (instant_ngp.py:165-169 + tcnn padding)
+      float po[16], h[16];
+      tmem_ld16(mine, po);
+      if (valid) sigma_raw[i] = po[0];
+      const float* dir = dirs + (size_t)((uint32_t)j / (uint32_t)N) * 3;
+      float sh[4];
+      sh_degree2(dir[0], dir[1], dir[2], sh);
+#pragma unroll
+      for (int k = 0; k < 4; ++k) h[k] = sh[k];
+#pragma unroll
+      for (int k = 4; k < 16; ++k) h[k] = po[k - 3];
+      store_half16<false>(A, tid, 0, h);
+#pragma unroll
+      for (int k = 0; k < 3; ++k) h[k] = po[13 + k];
+#pragma unroll
+      for (int k = 3; k < 16; ++k) h[k] = 1.0f;
+      store_half16<false>(A, tid, 1, h);
+    }
     publish_and_sync();
-    if (tid == 0) issue_layer<32>(acc32, sbase + fwd::kA0, sbase + fwd::kWD1, bar);
+    if (tid == 0) issue_layer<32>(acc, sa, sbase + fwd::kWD1, bar);
     mbar_wait(bar, phase), phase ^= 1;
     tc_fence_after();
-    tmem_ld32(my32, v);
-    store_row32<true>(A1, tid, v);
+    relu_acc_to_tile(mine, A, tid);
     publish_and_sync();
-    if (tid == 0) issue_layer<32>(acc32, sbase + fwd::kA1, sbase + fwd::kWD2, bar);
+    if (tid == 0) issue_layer<32>(acc, sa, sbase + fwd::kWD2, bar);
     mbar_wait(bar, phase), phase ^= 1;
     tc_fence_after();
-    tmem_ld32(my32, v);
-    store_row32<true>(A0, tid, v);
+    relu_acc_to_tile(mine, A, tid);
     publish_and_sync();
-    if (tid == 0) issue_layer<16>(acc16, sbase + fwd::kA0, sbase + fwd::kWD3, bar);
+    if (tid == 0) issue_layer<16>(acc, sa, sbase + fwd::kWD3, bar);
     mbar_wait(bar, phase), phase ^= 1;
     tc_fence_after();
     float c[4];
-    tmem_ld4(my16, c);
+    tmem_ld4(mine, c);
     if (valid) *reinterpret_cast<float4*>(color_raw + 4 * i) = make_float4(c[0], c[1], c[2], c[3]);
   }
   tc_fence_before();
   __syncthreads();
-  if (warp == 0) tmem_dealloc<fwd::kTmemCols>(tmem);
+  if (warp == 0) tmem_dealloc<fwd::kTmemCols>(acc);
 }
 
 
@@ -331,18 +383,21 @@ __device__ __forceinline__ void issue_dweight(uint32_t acc, uint32_t d_tile, uin
              idesc, accumulate | (uint32_t)(k > 0));
 }
 
-// zero the entries of v whose activation (this thread's row of `tile`) is not positive
-__device__ __forceinline__ void relu_mask_row(const uint8_t* tile, int r, float (&v)[32]) {
+// dst row r = fp16(v) where this thread's row of the activation tile `act` is positive, else 0:
+// the ReLU derivative applied in the packed-half domain (one convert, one compare-to-mask and one
+// AND per pair of values; the values equal "mask in fp32, then round")
+__device__ __forceinline__ void store_row32_masked(uint8_t* dst, const uint8_t* act, int r, const float (&v)[32]) {
+  const __half2 zero = __floats2half2_rn(0.0f, 0.0f);
 #pragma unroll
   for (int cc = 0; cc < 4; ++cc) {
-    const uint4 q = ld_chunk(tile, r, cc, 32);
-    const __half2* h = reinterpret_cast<const __half2*>(&q);
+    const uint4 a = ld_chunk(act, r, cc, 32);
+    const __half2* ah = reinterpret_cast<const __half2*>(&a);
+    uint4 q;
+    uint32_t* qp = reinterpret_cast<uint32_t*>(&q);
 #pragma unroll
-    for (int j = 0; j < 4; ++j) {
-      const float2 f = __half22float2(h[j]);
-      if (!(f.x > 0.0f)) v[cc * 8 + 2 * j] = 0.0f;
-      if (!(f.y > 0.0f)) v[cc * 8 + 2 * j + 1] = 0.0f;
-    }
+    for (int j = 0; j < 4; ++j)
+      qp[j] = pack_h2_act<false>(v[cc * 8 + 2 * j], v[cc * 8 + 2 * j + 1]) & __hgt2_mask(ah[j], zero);
+    st_chunk(dst, r, cc, 32, q);
   }
 }
 
@@ -459,8 +514,7 @@ k_field_bwd_tc(atmonr_grid_t g, const __half2* __restrict__ table, const __half*
     mbar_wait(bar, phase), phase ^= 1;
     tc_fence_after();
     tmem_ld32(my32, v);
-    relu_mask_row(smem + bwd::kH2, tid, v);
-    store_row32<false>(smem + bwd::kDA, tid, v);
+    store_row32_masked(smem + bwd::kDA, smem + bwd::kH2, tid, v);
     publish_and_sync();
     if (tid == 0) {
       tc_fence_after();
@@ -471,8 +525,7 @@ k_field_bwd_tc(atmonr_grid_t g, const __half2* __restrict__ table, const __half*
     mbar_wait(bar, phase), phase ^= 1;
     tc_fence_after();
     tmem_ld32(my32, v);
-    relu_mask_row(smem + bwd::kH1, tid, v);
-    store_row32<false>(smem + bwd::kDB, tid, v);
+    store_row32_masked(smem + bwd::kDB, smem + bwd::kH1, tid, v);
     publish_and_sync();
     if (tid == 0) {
       tc_fence_after();
@@ -500,8 +553,7 @@ k_field_bwd_tc(atmonr_grid_t g, const __half2* __restrict__ table, const __half*
     mbar_wait(bar, phase), phase ^= 1;
     tc_fence_after();
     tmem_ld32(my32, v);
-    relu_mask_row(smem + bwd::kH, tid, v);
-    store_row32<false>(smem + bwd::kDA, tid, v);
+    store_row32_masked(smem + bwd::kDA, smem + bwd::kH, tid, v);
     publish_and_sync();
     if (tid == 0) {
       tc_fence_after();
@@ -753,8 +805,7 @@ k_field_bwd_tc2(atmonr_grid_t g, const __half* __restrict__ pos_w, const __half*
     mbar_wait(bar, phase), phase ^= 1;
     tc_fence_after();
     tmem_ld32(my32, v);
-    relu_mask_row(H2, tid, v);
-    store_row32<false>(X, tid, v);  // dL/dh2 -> X (layer 0 finished with the encoded features)
+    store_row32_masked(X, H2, tid, v);  // dL/dh2 -> X (layer 0 finished with the encoded features)
     publish_and_sync();
     if (tid == 0) {  // S1
       tc_fence_after();
@@ -765,8 +816,7 @@ k_field_bwd_tc2(atmonr_grid_t g, const __half* __restrict__ pos_w, const __half*
     mbar_wait(bar, phase), phase ^= 1;  // covers dW(d3): DO and H2 are free
     tc_fence_after();
     tmem_ld32(my32, v);
-    relu_mask_row(H1, tid, v);
-    store_row32<false>(H2, tid, v);  // dL/dh1 -> H2
+    store_row32_masked(H2, H1, tid, v);  // dL/dh1 -> H2
     publish_and_sync();
     if (tid == 0) {  // S2
       tc_fence_after();
@@ -794,8 +844,7 @@ k_field_bwd_tc2(atmonr_grid_t g, const __half* __restrict__ pos_w, const __half*
     mbar_wait(bar, phase), phase ^= 1;  // covers dW(d1): H2 and DIN are free
     tc_fence_after();
     tmem_ld32(my32, v);
-    relu_mask_row(H, tid, v);
-    store_row32<false>(H1, tid, v);  // dL/dh -> H1
+    store_row32_masked(H1, H, tid, v);  // dL/dh -> H1
 #pragma unroll
     for (int cc = 0; cc < 4; ++cc) st_chunk(DIN, tid, cc, 32, enc_row[cc]);  // encoded features again -> DIN
     publish_and_sync();
@@ -830,7 +879,7 @@ k_field_bwd_tc2(atmonr_grid_t g, const __half* __restrict__ pos_w, const __half*
       // so coarse-level warps almost never execute the flush path
       const int grp = tid & 15, lvl = tid >> 4;
       const LevelRow L = lv[lvl];
-      float* base = dtable + 2 * (size_t)L.offset;
+      float2* base = reinterpret_cast<float2*>(dtable) + L.offset;
       const float* stage = reinterpret_cast<const float*>(smem + bwd2::kX);
       const int64_t row0 = tile * bwd2::kRows + grp * 16;
       float acc[16];
@@ -842,7 +891,7 @@ k_field_bwd_tc2(atmonr_grid_t g, const __half* __restrict__ pos_w, const __half*
         uint32_t e[8];
         corner_entries3(L, c_run, e);
 #pragma unroll
-        for (int c = 0; c < 8; ++c) red_add_f32x2(base + 2 * (size_t)e[c], acc[2 * c], acc[2 * c + 1]);
+        for (int c = 0; c < 8; ++c) red_add_f32x2(reinterpret_cast<float*>(entry_ptr(base, e[c])), acc[2 * c], acc[2 * c + 1]);
       };
 #pragma unroll 1
       for (int r = 0; r < 16; ++r) {
@@ -910,162 +959,6 @@ k_field_bwd_tc2(atmonr_grid_t g, const __half* __restrict__ pos_w, const __half*
 }
 
 
-// =========================================================================================
-// fused radiance field, forward, 256-row tiles with run-length merged gathers
-// =========================================================================================
-// Encoding phase: thread (g, q) encodes the 16 CONSECUTIVE samples 16g..16g+15 at level q. While
-// consecutive samples of the ray stay in the same grid cell the 8 corner entries are kept in
-// registers, so the table is gathered once per cell run (not once per sample) and the entry
-// indices are only recomputed when the cell changes. The features go straight into the A tile.
-// MLP phase: thread t owns sample row t (TMEM lane t & 127 of half t >> 7), as in k_field_fwd_tc.
-namespace fwd2 {
-constexpr int kRows = 256;
-constexpr int kA0 = 0;                 // [256][32]
-constexpr int kA1 = kA0 + 16384;       // [256][32]
-constexpr int kW = kA1 + 16384;
-constexpr int kLv = kW + 8192;
-constexpr int kBar = kLv + 512;
-constexpr int kTmemPtr = kBar + 8;
-constexpr int kBytes = kTmemPtr + 8;
-constexpr uint32_t kTmemCols = 128;    // two halves x ([0,32) hidden, [32,48) 16-wide)
-}  // namespace fwd2
-
-__global__ void __launch_bounds__(256, 4)
-k_field_fwd_tc2(atmonr_grid_t g, const __half2* __restrict__ table, const __half* __restrict__ pos_w,
-                const __half* __restrict__ dir_w, const float* __restrict__ x01, const float* __restrict__ dirs,
-                int64_t M, int N, float* __restrict__ sigma_raw, float* __restrict__ color_raw,
-                __half* __restrict__ enc_out) {
-  extern __shared__ __align__(128) uint8_t smem[];
-  uint64_t* bar = reinterpret_cast<uint64_t*>(smem + fwd2::kBar);
-  uint32_t* tmem_ptr = reinterpret_cast<uint32_t*>(smem + fwd2::kTmemPtr);
-  const int tid = threadIdx.x, warp = tid >> 5;
-  LevelRow* lv = reinterpret_cast<LevelRow*>(smem + fwd2::kLv);
-  load_level_table(g, lv);
-  load_field_weights(smem + fwd2::kW, pos_w, dir_w);
-  if (warp == 0) tmem_alloc<fwd2::kTmemCols>(tmem_ptr);
-  if (tid == 0) {
-    mbar_init(bar, 1);
-    fence_mbar_init();
-  }
-  publish_and_sync();
-  tc_fence_after();
-  const uint32_t tmem = *tmem_ptr;
-  const uint32_t my32 = tmem_addr(tmem, warp, (warp >> 2) * bwd2::cHalf), my16 = my32 + 32;
-  const uint32_t sb = smem_u32(smem), sw = sb + fwd2::kW;
-  uint8_t* A0 = smem + fwd2::kA0;
-  uint8_t* A1 = smem + fwd2::kA1;
-  uint32_t phase = 0;
-  const int grp = tid >> 4, lvl = tid & 15;
-  const LevelRow L = lv[lvl];
-  const __half2* lbase = table + L.offset;
-
-  for (int64_t tile = blockIdx.x; tile * fwd2::kRows < M; tile += gridDim.x) {
-    const int64_t i = tile * fwd2::kRows + tid;
-    const bool valid = i < M;
-    const int64_t j = valid ? i : M - 1;
-    // ---- encoding: 16 consecutive samples of one level per thread ----
-    {
-      const int64_t row0 = tile * fwd2::kRows + grp * 16;
-      uint32_t c_run[3] = {0xffffffffu, 0xffffffffu, 0xffffffffu};
-      float2 f[8];
-#pragma unroll
-      for (int c = 0; c < 8; ++c) f[c] = make_float2(0.0f, 0.0f);
-#pragma unroll 2
-      for (int r = 0; r < 16; ++r) {
-        int64_t gi = row0 + r;
-        if (gi >= M) gi = M - 1;
-        const float p[3] = {x01[3 * gi], x01[3 * gi + 1], x01[3 * gi + 2]};
-        uint32_t cell[3];
-        float frac[3];
-        grid_cell<3>(p, L.scale, cell, frac);
-        if (cell[0] != c_run[0] || cell[1] != c_run[1] || cell[2] != c_run[2]) {
-          uint32_t e[8];
-          float wdummy[8];
-          level_corners3(L, p, e, wdummy, cell);
-#pragma unroll
-          for (int c = 0; c < 8; ++c) f[c] = __half22float2(__ldg(lbase + e[c]));
-          c_run[0] = cell[0], c_run[1] = cell[1], c_run[2] = cell[2];
-        }
-        const float wx[2] = {1.0f - frac[0], frac[0]};
-        const float wy[2] = {1.0f - frac[1], frac[1]};
-        const float wz[2] = {1.0f - frac[2], frac[2]};
-        float a0 = 0.0f, a1 = 0.0f;
-#pragma unroll
-        for (int c = 0; c < 8; ++c) {
-          const float w = (wx[c & 1] * wy[(c >> 1) & 1]) * wz[c >> 2];
-          a0 = fmaf(w, f[c].x, a0);
-          a1 = fmaf(w, f[c].y, a1);
-        }
-        *reinterpret_cast<uint32_t*>(A0 + tile_off(grp * 16 + r, 2 * lvl, 32)) = pack_h2(a0, a1);
-      }
-    }
-    publish_and_sync();
-    if (enc_out && valid) {  // own row, complete after the barrier
-      uint4* dst = reinterpret_cast<uint4*>(enc_out + i * 32);
-#pragma unroll
-      for (int cc = 0; cc < 4; ++cc) dst[cc] = ld_chunk(A0, tid, cc, 32);
-    }
-    if (tid == 0) {
-      tc_fence_after();
-      issue_layer2<32>(tmem, 0, sb + fwd2::kA0, sw + fwd::kW1P);
-      umma_commit(bar);
-    }
-    mbar_wait(bar, phase), phase ^= 1;
-    tc_fence_after();
-    float v[32];
-    tmem_ld32(my32, v);
-    store_row32<true>(A1, tid, v);
-    publish_and_sync();
-    if (tid == 0) {
-      tc_fence_after();
-      issue_layer2<16>(tmem, 32, sb + fwd2::kA1, sw + fwd::kW2P);
-      umma_commit(bar);
-    }
-    mbar_wait(bar, phase), phase ^= 1;
-    tc_fence_after();
-    float po[16];
-    tmem_ld16(my16, po);
-    if (valid) sigma_raw[i] = po[0];
-    dir_input_row(dirs + (size_t)((uint32_t)j / (uint32_t)N) * 3, po, v);
-    store_row32<false>(A0, tid, v);
-    publish_and_sync();
-    if (tid == 0) {
-      tc_fence_after();
-      issue_layer2<32>(tmem, 0, sb + fwd2::kA0, sw + fwd::kWD1);
-      umma_commit(bar);
-    }
-    mbar_wait(bar, phase), phase ^= 1;
-    tc_fence_after();
-    tmem_ld32(my32, v);
-    store_row32<true>(A1, tid, v);
-    publish_and_sync();
-    if (tid == 0) {
-      tc_fence_after();
-      issue_layer2<32>(tmem, 0, sb + fwd2::kA1, sw + fwd::kWD2);
-      umma_commit(bar);
-    }
-    mbar_wait(bar, phase), phase ^= 1;
-    tc_fence_after();
-    tmem_ld32(my32, v);
-    store_row32<true>(A0, tid, v);
-    publish_and_sync();
-    if (tid == 0) {
-      tc_fence_after();
-      issue_layer2<16>(tmem, 32, sb + fwd2::kA0, sw + fwd::kWD3);
-      umma_commit(bar);
-    }
-    mbar_wait(bar, phase), phase ^= 1;
-    tc_fence_after();
-    float c[4];
-    tmem_ld4(my16, c);
-    if (valid) *reinterpret_cast<float4*>(color_raw + 4 * i) = make_float4(c[0], c[1], c[2], c[3]);
-    // the next tile's encoding writes A0, which the last layer's MMA has finished reading (waited above)
-  }
-  tc_fence_before();
-  __syncthreads();
-  if (warp == 0) tmem_dealloc<fwd2::kTmemCols>(tmem);
-}
-
 }  // namespace atm
 
 using namespace atm;
@@ -1108,23 +1001,8 @@ int atmonr_ngp_field_fwd_tc(const atmonr_grid_t* g, const void* table, const atm
   const int64_t M = B * N;
   if (M == 0) return 0;
   ATM_REQUIRE(M < ((int64_t)1 << 31), "atmonr_ngp_field_fwd_tc", "B*N must be below 2^31 per call (chunk the batch)");
-  // the 256-row variant merges gathers over runs of samples in one cell; its serial per-thread
-  // gather chain currently loses to the 128-row kernel (44 vs 33 ms at 2^18 rays): opt-in only
-  const bool use_wide = getenv("ATMONR_FWD_WIDE") != nullptr;  // read per call: tests toggle it
-  if (use_wide) {
-    cudaError_t e2 = cudaFuncSetAttribute(k_field_fwd_tc2, cudaFuncAttributeMaxDynamicSharedMemorySize, fwd2::kBytes);
-    if (e2 != cudaSuccess) return fail("atmonr_ngp_field_fwd_tc", cudaGetErrorString(e2));
-    const int64_t tiles2 = (M + fwd2::kRows - 1) / fwd2::kRows;
-    const int64_t cap2 = (int64_t)tc_num_sms() * 4;
-    k_field_fwd_tc2<<<(int)(tiles2 < cap2 ? tiles2 : cap2), fwd2::kRows, fwd2::kBytes,
-                      reinterpret_cast<cudaStream_t>(stream)>>>(*g, (const __half2*)table, (const __half*)pos_w,
-                                                                (const __half*)dir_w, x01, dirs, M, N, sigma_raw,
-                                                                color_raw, (__half*)enc_out);
-    ATM_CHECK_LAUNCH("atmonr_ngp_field_fwd_tc");
-    return 0;
-  }
   const int64_t tiles = (M + kTile - 1) / kTile;
-  const int64_t max_ctas = (int64_t)tc_num_sms() * 8;
+  const int64_t max_ctas = (int64_t)tc_num_sms() * fwd::kCtasPerSm;
   const int grid = (int)(tiles < max_ctas ? tiles : max_ctas);
   k_field_fwd_tc<<<grid, kTile, fwd::kBytes, reinterpret_cast<cudaStream_t>(stream)>>>(
       *g, (const __half2*)table, (const __half*)pos_w, (const __half*)dir_w, x01, dirs, M, N, sigma_raw, color_raw,

@@ -245,12 +245,12 @@ def _pipeline(scene, cfg):
     return pipe
 
 
-@pytest.mark.parametrize("impl", ["tc", "simt", "tc-nocache", "tc-narrow-bwd", "tc-wide-fwd"])
+@pytest.mark.parametrize("impl", ["tc", "simt", "tc-nocache", "tc-narrow-bwd"])
 def test_ngp_pipeline_forward_loss_gradients_vs_oracle(scene, impl, monkeypatch):
     """impl = tc: dense layers on tcgen05 (fp16 gradient operands under a power-of-two scale), 128-row
     forward tiles, 256-row backward tiles reading the forward's cached encoding;
     tc-nocache: no encoding cache -> 128-row backward that re-gathers the table;
-    tc-narrow-bwd / tc-wide-fwd: the alternative tile widths; simt: thread-per-sample FMA kernels
+    tc-narrow-bwd: the 128-row backward with the cache; simt: thread-per-sample FMA kernels
     (fp32 gradients)."""
     from atmonr.native import fused
     monkeypatch.setattr(fused, "FIELD_IMPL", "simt" if impl == "simt" else "tc")
@@ -258,8 +258,6 @@ def test_ngp_pipeline_forward_loss_gradients_vs_oracle(scene, impl, monkeypatch)
         monkeypatch.setattr(fused, "ENC_CACHE_BYTES", 0)
     if impl == "tc-narrow-bwd":
         monkeypatch.setenv("ATMONR_BWD_NARROW", "1")
-    if impl == "tc-wide-fwd":
-        monkeypatch.setenv("ATMONR_FWD_WIDE", "1")
     cfg = ngp_config(64)
     orc16 = NGPOracle(cfg, scene.frame, scene.max_i, fp16=True)
     orc32 = NGPOracle(cfg, scene.frame, scene.max_i, fp16=False)
