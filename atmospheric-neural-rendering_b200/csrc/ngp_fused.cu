@@ -636,6 +636,7 @@ k_field_bwd_tc(atmonr_grid_t g, const __half2* __restrict__ table, const __half*
 // (tcgen05.commit covers every MMA issued before it).
 namespace bwd2 {
 constexpr int kRows = 256;
+constexpr int kThreads = 288;            // 8 epilogue warps (one sample row per thread) + the MMA-issuer warp
 constexpr int kX = 0;
 constexpr int kH = kX + 16384;
 constexpr int kDIN = kH + 16384;
@@ -683,7 +684,20 @@ __device__ __forceinline__ void issue_dweight2(uint32_t acc, uint32_t d_tile, ui
              idesc, accumulate | (uint32_t)(k > 0));
 }
 
-__global__ void __launch_bounds__(256, 2)
+// named barrier 1: epilogue warps arrive (non-blocking) when their rows of a stage's operand tile
+// are written, the issuer warp waits on it; named barrier 2: the 256 epilogue threads only
+__device__ __forceinline__ void stage_arrive() {
+  fence_async_smem();
+  tc_fence_before();
+  asm volatile("bar.arrive 1, 288;" ::: "memory");
+}
+__device__ __forceinline__ void stage_wait() {
+  asm volatile("bar.sync 1, 288;" ::: "memory");
+  tc_fence_after();
+}
+__device__ __forceinline__ void epilogue_sync() { asm volatile("bar.sync 2, 256;" ::: "memory"); }
+
+__global__ void __launch_bounds__(bwd2::kThreads, 2)
 k_field_bwd_tc2(atmonr_grid_t g, const __half* __restrict__ pos_w, const __half* __restrict__ dir_w,
                 const float* __restrict__ x01, const float* __restrict__ dirs, const __half* __restrict__ enc_in,
                 const float* __restrict__ dsigma_raw, const float* __restrict__ dcolor_raw,
@@ -706,20 +720,85 @@ k_field_bwd_tc2(atmonr_grid_t g, const __half* __restrict__ pos_w, const __half*
   publish_and_sync();
   tc_fence_after();
   const uint32_t tmem = *tmem_ptr;
-  const uint32_t my32 = tmem_addr(tmem, warp, (warp >> 2) * bwd2::cHalf), my16 = my32 + 32;
   const uint32_t sb = smem_u32(smem), sw = sb + bwd2::kW;
-  uint8_t* X = smem + bwd2::kX;
-  uint8_t* H = smem + bwd2::kH;
-  uint8_t* DIN = smem + bwd2::kDIN;
-  uint8_t* H1 = smem + bwd2::kH1;
-  uint8_t* H2 = smem + bwd2::kH2;
-  uint8_t* DO = smem + bwd2::kDO;
   float S = 1.0f;
   if (grad_absmax) {
     const float amax = *grad_absmax;
     if (amax > 0.0f && amax < INFINITY) S = exp2f(fminf(fmaxf(floorf(log2f(2048.0f / amax)), -60.0f), 60.0f));
   }
   const float invS = 1.0f / S;
+  const bool cta_has_work = (int64_t)blockIdx.x * bwd2::kRows < M;
+
+  if (warp == 8) {
+    // ------------------------------- MMA issuer warp ----------------------------------------
+    // Every tcgen05.mma of the CTA is issued here, so the epilogue warps never stall behind the
+    // (long) weight-gradient issue sequences: a stage's input-gradient MMAs are committed first,
+    // its weight-gradient MMAs are issued while the epilogue warps already work on the result.
+    const bool leader = (tid & 31) == 0;
+    uint32_t seen_tile = 0;
+    for (int64_t tile = blockIdx.x; tile * bwd2::kRows < M; tile += gridDim.x, seen_tile = 1) {
+      stage_wait();  // X = encoded features
+      if (leader) {
+        issue_layer2<32>(tmem, 0, sb + bwd2::kX, sw + fwd::kW1P);
+        umma_commit(bar);
+      }
+      stage_wait();  // H
+      if (leader) {
+        issue_layer2<16>(tmem, 32, sb + bwd2::kH, sw + fwd::kW2P);
+        umma_commit(bar);
+      }
+      stage_wait();  // DIN
+      if (leader) {
+        issue_layer2<32>(tmem, 0, sb + bwd2::kDIN, sw + fwd::kWD1);
+        umma_commit(bar);
+      }
+      stage_wait();  // H1
+      if (leader) {
+        issue_layer2<32>(tmem, 0, sb + bwd2::kH1, sw + fwd::kWD2);
+        umma_commit(bar);
+      }
+      stage_wait();  // S0: DO = dL/d(dir_mlp out), H2
+      if (leader) {
+        issue_dinput2<16>(tmem, sb + bwd2::kDO, sw + fwd::kWD3);
+        umma_commit(bar);
+        ATM_DW issue_dweight2<16>(tmem + bwd2::cDWd3, sb + bwd2::kDO, sb + bwd2::kH2, seen_tile);
+      }
+      stage_wait();  // S1: X = dL/dh2
+      if (leader) {
+        issue_dinput2<32>(tmem, sb + bwd2::kX, sw + fwd::kWD2);
+        umma_commit(bar);
+        ATM_DW issue_dweight2<32>(tmem + bwd2::cDWd2, sb + bwd2::kX, sb + bwd2::kH1, seen_tile);
+      }
+      stage_wait();  // S2: H2 = dL/dh1
+      if (leader) {
+        issue_dinput2<32>(tmem, sb + bwd2::kH2, sw + fwd::kWD1);
+        umma_commit(bar);
+        ATM_DW issue_dweight2<32>(tmem + bwd2::cDWd1, sb + bwd2::kH2, sb + bwd2::kDIN, seen_tile);
+      }
+      stage_wait();  // S3: DO = dL/d(pos_mlp out)
+      if (leader) {
+        issue_dinput2<16>(tmem, sb + bwd2::kDO, sw + fwd::kW2P);
+        umma_commit(bar);
+        ATM_DW issue_dweight2<16>(tmem + bwd2::cDW2p, sb + bwd2::kDO, sb + bwd2::kH, seen_tile);
+      }
+      stage_wait();  // S4: H1 = dL/dh, DIN = encoded features again
+      if (leader) {
+        issue_dinput2<32>(tmem, sb + bwd2::kH1, sw + fwd::kW1P);
+        umma_commit(bar);
+        ATM_DW issue_dweight2<32>(tmem + bwd2::cDW1p, sb + bwd2::kH1, sb + bwd2::kDIN, seen_tile);
+        umma_commit(bar2);  // tile boundary: every MMA that reads this tile's buffers
+      }
+      __syncwarp();
+    }
+  } else {
+  // ------------------------------- epilogue warps ---------------------------------------------
+  const uint32_t my32 = tmem_addr(tmem, warp, (warp >> 2) * bwd2::cHalf), my16 = my32 + 32;
+  uint8_t* X = smem + bwd2::kX;
+  uint8_t* H = smem + bwd2::kH;
+  uint8_t* DIN = smem + bwd2::kDIN;
+  uint8_t* H1 = smem + bwd2::kH1;
+  uint8_t* H2 = smem + bwd2::kH2;
+  uint8_t* DO = smem + bwd2::kDO;
   uint32_t phase = 0, phase2 = 0, seen_tile = 0;
 
   for (int64_t tile = blockIdx.x; tile * bwd2::kRows < M; tile += gridDim.x, seen_tile = 1) {
@@ -739,23 +818,13 @@ k_field_bwd_tc2(atmonr_grid_t g, const __half* __restrict__ pos_w, const __half*
     // ---------------- recompute the activations ----------------
 #pragma unroll
     for (int cc = 0; cc < 4; ++cc) st_chunk(X, tid, cc, 32, enc_row[cc]);
-    publish_and_sync();
-    if (tid == 0) {
-      tc_fence_after();
-      issue_layer2<32>(tmem, 0, sb + bwd2::kX, sw + fwd::kW1P);
-      umma_commit(bar);
-    }
+    stage_arrive();
     mbar_wait(bar, phase), phase ^= 1;
     tc_fence_after();
     float v[32];
     tmem_ld32(my32, v);
     store_row32<true>(H, tid, v);
-    publish_and_sync();
-    if (tid == 0) {
-      tc_fence_after();
-      issue_layer2<16>(tmem, 32, sb + bwd2::kH, sw + fwd::kW2P);
-      umma_commit(bar);
-    }
+    stage_arrive();
     mbar_wait(bar, phase), phase ^= 1;
     tc_fence_after();
     {
@@ -764,22 +833,12 @@ k_field_bwd_tc2(atmonr_grid_t g, const __half* __restrict__ pos_w, const __half*
       dir_input_row(dirs + (size_t)((uint32_t)j / (uint32_t)N) * 3, po, v);
     }
     store_row32<false>(DIN, tid, v);
-    publish_and_sync();
-    if (tid == 0) {
-      tc_fence_after();
-      issue_layer2<32>(tmem, 0, sb + bwd2::kDIN, sw + fwd::kWD1);
-      umma_commit(bar);
-    }
+    stage_arrive();
     mbar_wait(bar, phase), phase ^= 1;
     tc_fence_after();
     tmem_ld32(my32, v);
     store_row32<true>(H1, tid, v);
-    publish_and_sync();
-    if (tid == 0) {
-      tc_fence_after();
-      issue_layer2<32>(tmem, 0, sb + bwd2::kH1, sw + fwd::kWD2);
-      umma_commit(bar);
-    }
+    stage_arrive();
     mbar_wait(bar, phase), phase ^= 1;
     tc_fence_after();
     tmem_ld32(my32, v);
@@ -795,35 +854,17 @@ k_field_bwd_tc2(atmonr_grid_t g, const __half* __restrict__ pos_w, const __half*
       }
       store_row16(DO, tid, dout);
     }
-    publish_and_sync();
-    if (tid == 0) {  // S0
-      tc_fence_after();
-      issue_dinput2<16>(tmem, sb + bwd2::kDO, sw + fwd::kWD3);
-      umma_commit(bar);
-      ATM_DW issue_dweight2<16>(tmem + bwd2::cDWd3, sb + bwd2::kDO, sb + bwd2::kH2, seen_tile);
-    }
+    stage_arrive();  // S0
     mbar_wait(bar, phase), phase ^= 1;
     tc_fence_after();
     tmem_ld32(my32, v);
     store_row32_masked(X, H2, tid, v);  // dL/dh2 -> X (layer 0 finished with the encoded features)
-    publish_and_sync();
-    if (tid == 0) {  // S1
-      tc_fence_after();
-      issue_dinput2<32>(tmem, sb + bwd2::kX, sw + fwd::kWD2);
-      umma_commit(bar);
-      ATM_DW issue_dweight2<32>(tmem + bwd2::cDWd2, sb + bwd2::kX, sb + bwd2::kH1, seen_tile);
-    }
+    stage_arrive();  // S1
     mbar_wait(bar, phase), phase ^= 1;  // covers dW(d3): DO and H2 are free
     tc_fence_after();
     tmem_ld32(my32, v);
     store_row32_masked(H2, H1, tid, v);  // dL/dh1 -> H2
-    publish_and_sync();
-    if (tid == 0) {  // S2
-      tc_fence_after();
-      issue_dinput2<32>(tmem, sb + bwd2::kH2, sw + fwd::kWD1);
-      umma_commit(bar);
-      ATM_DW issue_dweight2<32>(tmem + bwd2::cDWd1, sb + bwd2::kH2, sb + bwd2::kDIN, seen_tile);
-    }
+    stage_arrive();  // S2
     mbar_wait(bar, phase), phase ^= 1;  // covers dW(d2): X and H1 are free
     tc_fence_after();
     tmem_ld32(my32, v);
@@ -834,27 +875,14 @@ k_field_bwd_tc2(atmonr_grid_t g, const __half* __restrict__ pos_w, const __half*
       for (int k = 1; k < 16; ++k) dpo[k] = v[3 + k];
       store_row16(DO, tid, dpo);  // dL/d(pos_mlp out) -> DO
     }
-    publish_and_sync();
-    if (tid == 0) {  // S3
-      tc_fence_after();
-      issue_dinput2<16>(tmem, sb + bwd2::kDO, sw + fwd::kW2P);
-      umma_commit(bar);
-      ATM_DW issue_dweight2<16>(tmem + bwd2::cDW2p, sb + bwd2::kDO, sb + bwd2::kH, seen_tile);
-    }
+    stage_arrive();  // S3
     mbar_wait(bar, phase), phase ^= 1;  // covers dW(d1): H2 and DIN are free
     tc_fence_after();
     tmem_ld32(my32, v);
     store_row32_masked(H1, H, tid, v);  // dL/dh -> H1
 #pragma unroll
     for (int cc = 0; cc < 4; ++cc) st_chunk(DIN, tid, cc, 32, enc_row[cc]);  // encoded features again -> DIN
-    publish_and_sync();
-    if (tid == 0) {  // S4
-      tc_fence_after();
-      issue_dinput2<32>(tmem, sb + bwd2::kH1, sw + fwd::kW1P);
-      umma_commit(bar);
-      ATM_DW issue_dweight2<32>(tmem + bwd2::cDW1p, sb + bwd2::kH1, sb + bwd2::kDIN, seen_tile);
-      umma_commit(bar2);
-    }
+    stage_arrive();  // S4
     mbar_wait(bar, phase), phase ^= 1;
     tc_fence_after();
     // ---- table-gradient scatter with run-length merging --------------------------------------
@@ -865,6 +893,7 @@ k_field_bwd_tc2(atmonr_grid_t g, const __half* __restrict__ pos_w, const __half*
     // per corner per cell run instead of one per sample (the REDs were the kernel's bottleneck:
     // ~1.3 cycles per lane-RED per SM).
     tmem_ld32(my32, v);
+    tc_fence_before();
     {
       float* srow = reinterpret_cast<float*>(smem + bwd2::kX) + tid * 32;
       const int swz = (tid ^ (tid >> 4)) & 7;
@@ -873,7 +902,7 @@ k_field_bwd_tc2(atmonr_grid_t g, const __half* __restrict__ pos_w, const __half*
         *reinterpret_cast<float4*>(srow + ((k ^ swz) << 2)) =
             make_float4(v[4 * k] * invS, v[4 * k + 1] * invS, v[4 * k + 2] * invS, v[4 * k + 3] * invS);
     }
-    __syncthreads();
+    epilogue_sync();
     {
       // a warp holds 2 levels x 16 sample groups: cell runs of one level end at similar rates,
       // so coarse-level warps almost never execute the flush path
@@ -923,14 +952,19 @@ k_field_bwd_tc2(atmonr_grid_t g, const __half* __restrict__ pos_w, const __half*
       }
       if (open) flush();
     }
-    __syncthreads();  // the staging area is the next tile's X/H
+    epilogue_sync();  // the staging area is the next tile's X/H
   }
+  }  // epilogue warps
 
-  if (seen_tile) mbar_wait(bar2, phase2);
+  // the last tile's weight-gradient MMAs: its bar2 completion has not been consumed by anybody
+  if (cta_has_work) {
+    const int64_t my_tiles = ((M + bwd2::kRows - 1) / bwd2::kRows - blockIdx.x + gridDim.x - 1) / gridDim.x;
+    mbar_wait(bar2, (uint32_t)((my_tiles - 1) & 1));
+  }
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
-  if (warp == 0 && seen_tile) {
+  if (warp == 0 && cta_has_work) {
     const int o = tid;
     float w[32];
     tmem_ld32(tmem_addr(tmem, 0, bwd2::cDW1p), w);
@@ -957,6 +991,7 @@ k_field_bwd_tc2(atmonr_grid_t g, const __half* __restrict__ pos_w, const __half*
   __syncthreads();
   if (warp == 0) tmem_dealloc<bwd2::kTmemCols>(tmem);
 }
+
 
 
 }  // namespace atm
@@ -1029,7 +1064,7 @@ int atmonr_ngp_field_bwd_tc(const atmonr_grid_t* g, const void* table, const atm
     if (e2 != cudaSuccess) return fail("atmonr_ngp_field_bwd_tc", cudaGetErrorString(e2));
     const int64_t tiles2 = (M + bwd2::kRows - 1) / bwd2::kRows;
     const int grid2 = (int)(tiles2 < (int64_t)tc_num_sms() * 2 ? tiles2 : (int64_t)tc_num_sms() * 2);
-    k_field_bwd_tc2<<<grid2, bwd2::kRows, bwd2::kBytes, reinterpret_cast<cudaStream_t>(stream)>>>(
+    k_field_bwd_tc2<<<grid2, bwd2::kThreads, bwd2::kBytes, reinterpret_cast<cudaStream_t>(stream)>>>(
         *g, (const __half*)pos_w, (const __half*)dir_w, x01, dirs, (const __half*)enc, dsigma_raw, dcolor_raw,
         grad_absmax, M, N, dtable, dpos_w, ddir_w);
     ATM_CHECK_LAUNCH("atmonr_ngp_field_bwd_tc");
