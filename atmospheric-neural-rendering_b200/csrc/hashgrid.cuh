@@ -236,6 +236,44 @@ __device__ __forceinline__ void corner_entries3(const LevelRow& lv, const uint32
   }
 }
 
+// L2 eviction policies: the table (and its gradient) should stay L2-resident while tens of GB of
+// per-sample data stream through the same cache every step.
+__device__ __forceinline__ uint64_t l2_policy_keep() {
+  uint64_t p;
+  asm("createpolicy.fractional.L2::evict_last.b64 %0, 1.0;" : "=l"(p));
+  return p;
+}
+__device__ __forceinline__ uint64_t l2_policy_stream() {
+  uint64_t p;
+  asm("createpolicy.fractional.L2::evict_first.b64 %0, 1.0;" : "=l"(p));
+  return p;
+}
+__device__ __forceinline__ uint32_t ldg_u32_hint(const uint32_t* ptr, uint64_t policy) {
+  uint32_t v;
+  asm("ld.global.nc.L2::cache_hint.b32 %0, [%1], %2;" : "=r"(v) : "l"(ptr), "l"(policy));
+  return v;
+}
+__device__ __forceinline__ float ldg_f32_hint(const float* ptr, uint64_t policy) {
+  float v;
+  asm("ld.global.nc.L2::cache_hint.f32 %0, [%1], %2;" : "=f"(v) : "l"(ptr), "l"(policy));
+  return v;
+}
+__device__ __forceinline__ uint4 ldg_u128_hint(const uint4* ptr, uint64_t policy) {
+  uint4 v;
+  asm("ld.global.nc.L2::cache_hint.v4.b32 {%0,%1,%2,%3}, [%4], %5;"
+      : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w)
+      : "l"(ptr), "l"(policy));
+  return v;
+}
+__device__ __forceinline__ void stg_u128_hint(uint4* ptr, uint4 v, uint64_t policy) {
+  asm volatile("st.global.L2::cache_hint.v4.b32 [%0], {%1,%2,%3,%4}, %5;" ::"l"(ptr), "r"(v.x), "r"(v.y), "r"(v.z),
+               "r"(v.w), "l"(policy)
+               : "memory");
+}
+__device__ __forceinline__ void stg_f32_hint(float* ptr, float v, uint64_t policy) {
+  asm volatile("st.global.L2::cache_hint.f32 [%0], %1, %2;" ::"l"(ptr), "f"(v), "l"(policy) : "memory");
+}
+
 // &table[entry] with one 32x32+64-bit multiply-add (the compiler otherwise spends four
 // instructions per corner on 64-bit address arithmetic)
 template <typename T>

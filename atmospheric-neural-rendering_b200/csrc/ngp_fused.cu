@@ -61,7 +61,7 @@ __global__ void __launch_bounds__(128) k_tc_probe(const __half* __restrict__ A, 
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem = tmem_base_s;
-  if (tid == 0) {
+  if (warp == 0) {
     const uint32_t a0 = smem_u32(sA), b0 = smem_u32(sB);
     if (mode == 0) {  // D = A[128x32] * W[32x32]^T : both K-major, K = 32
       const uint32_t idesc = make_idesc(128, 32, 0, 0);
@@ -176,13 +176,19 @@ __device__ __forceinline__ void relu_acc_to_tile(uint32_t taddr, uint8_t* tile, 
 // level_finish() interpolates. The loop issues level l+1 before it consumes level l, so a thread
 // always has 8-16 gathers in flight. Same arithmetic as hash_encode().
 __device__ __forceinline__ void level_issue(const LevelRow& L, const __half2* __restrict__ table, const float (&p)[3],
-                                            uint32_t (&v)[8], float (&frac)[3]) {
+                                            uint32_t (&v)[8], float (&frac)[3], uint64_t keep) {
   uint32_t cell[3], e[8];
   grid_cell<3>(p, L.scale, cell, frac);
   corner_entries3(L, cell, e);
   const uint32_t* base = reinterpret_cast<const uint32_t*>(table + L.offset);
 #pragma unroll
-  for (int c = 0; c < 8; ++c) v[c] = __ldg(entry_ptr(base, e[c]));
+  for (int c = 0; c < 8; ++c) {
+#ifdef ATM_L2_HINTS
+    v[c] = ldg_u32_hint(entry_ptr(base, e[c]), keep);
+#else
+    v[c] = __ldg(entry_ptr(base, e[c]));
+#endif
+  }
 }
 __device__ __forceinline__ uint32_t level_finish(const uint32_t (&v)[8], const float (&frac)[3]) {
   float w[8];
@@ -197,11 +203,12 @@ __device__ __forceinline__ uint32_t level_finish(const uint32_t (&v)[8], const f
   return pack_h2_act<false>(a0, a1);
 }
 __device__ __forceinline__ void encode_to_tile(const LevelRow* __restrict__ lv, const __half2* __restrict__ table,
-                                               const float (&p)[3], uint8_t* tile, int r) {
+                                               const float (&p)[3], uint8_t* tile, int r, uint64_t keep) {
   uint32_t vn[8];
   float fn[3];
-  level_issue(lv[0], table, p, vn, fn);
+  level_issue(lv[0], table, p, vn, fn, keep);
   uint8_t* row = tile + tile_off(r, 0, 32);
+  // (an explicit two-register-set version of this loop measured 4 % slower than the copies below)
 #pragma unroll 2
   for (int l = 0; l < ATMONR_MAX_LEVELS; ++l) {
     uint32_t vc[8];
@@ -209,7 +216,7 @@ __device__ __forceinline__ void encode_to_tile(const LevelRow* __restrict__ lv, 
 #pragma unroll
     for (int c = 0; c < 8; ++c) vc[c] = vn[c];
     fc[0] = fn[0], fc[1] = fn[1], fc[2] = fn[2];
-    if (l + 1 < ATMONR_MAX_LEVELS) level_issue(lv[l + 1], table, p, vn, fn);
+    if (l + 1 < ATMONR_MAX_LEVELS) level_issue(lv[l + 1], table, p, vn, fn, keep);
     // features 2l, 2l+1 of row r: chunk l/4 (128 B apart), 4 bytes per level inside the chunk
     *reinterpret_cast<uint32_t*>(row + (l >> 2) * kCore + (l & 3) * 4) = level_finish(vc, fc);
   }
@@ -270,6 +277,7 @@ k_field_fwd_tc(atmonr_grid_t g, const __half2* __restrict__ table, const __half*
   const uint32_t sbase = smem_u32(smem), sa = sbase + fwd::kA;
   uint8_t* A = smem + fwd::kA;
   uint32_t phase = 0;
+  const uint64_t keep_pol = l2_policy_keep(), stream_pol = l2_policy_stream();
 
   for (int64_t tile = blockIdx.x; tile * kTile < M; tile += gridDim.x) {
     const int64_t i = tile * kTile + tid;
@@ -277,21 +285,32 @@ k_field_fwd_tc(atmonr_grid_t g, const __half2* __restrict__ table, const __half*
     const int64_t j = valid ? i : M - 1;
     // ---- hash-grid encoding -> A (the previous tile's last MMA has been waited for)
     {
+#ifdef ATM_L2_HINTS
+      const float p[3] = {ldg_f32_hint(x01 + 3 * j, stream_pol), ldg_f32_hint(x01 + 3 * j + 1, stream_pol),
+                          ldg_f32_hint(x01 + 3 * j + 2, stream_pol)};
+#else
       const float p[3] = {x01[3 * j], x01[3 * j + 1], x01[3 * j + 2]};
-      encode_to_tile(lv, table, p, A, tid);
+#endif
+      encode_to_tile(lv, table, p, A, tid, keep_pol);
       if (enc_out && valid) {
         uint4* dst = reinterpret_cast<uint4*>(enc_out + i * 32);
 #pragma unroll
-        for (int cc = 0; cc < 4; ++cc) dst[cc] = ld_chunk(A, tid, cc, 32);
+        for (int cc = 0; cc < 4; ++cc) {
+#ifdef ATM_L2_HINTS
+          stg_u128_hint(dst + cc, ld_chunk(A, tid, cc, 32), stream_pol);
+#else
+          dst[cc] = ld_chunk(A, tid, cc, 32);
+#endif
+        }
       }
     }
     publish_and_sync();
-    if (tid == 0) issue_layer<32>(acc, sa, sbase + fwd::kW1P, bar);
+    if (warp == 0) issue_layer<32>(acc, sa, sbase + fwd::kW1P, bar);
     mbar_wait(bar, phase), phase ^= 1;
     tc_fence_after();
     relu_acc_to_tile(mine, A, tid);
     publish_and_sync();
-    if (tid == 0) issue_layer<16>(acc, sa, sbase + fwd::kW2P, bar);
+    if (warp == 0) issue_layer<16>(acc, sa, sbase + fwd::kW2P, bar);
     mbar_wait(bar, phase), phase ^= 1;
     tc_fence_after();
     {
@@ -314,17 +333,17 @@ k_field_fwd_tc(atmonr_grid_t g, const __half2* __restrict__ table, const __half*
       store_half16<false>(A, tid, 1, h);
     }
     publish_and_sync();
-    if (tid == 0) issue_layer<32>(acc, sa, sbase + fwd::kWD1, bar);
+    if (warp == 0) issue_layer<32>(acc, sa, sbase + fwd::kWD1, bar);
     mbar_wait(bar, phase), phase ^= 1;
     tc_fence_after();
     relu_acc_to_tile(mine, A, tid);
     publish_and_sync();
-    if (tid == 0) issue_layer<32>(acc, sa, sbase + fwd::kWD2, bar);
+    if (warp == 0) issue_layer<32>(acc, sa, sbase + fwd::kWD2, bar);
     mbar_wait(bar, phase), phase ^= 1;
     tc_fence_after();
     relu_acc_to_tile(mine, A, tid);
     publish_and_sync();
-    if (tid == 0) issue_layer<16>(acc, sa, sbase + fwd::kWD3, bar);
+    if (warp == 0) issue_layer<16>(acc, sa, sbase + fwd::kWD3, bar);
     mbar_wait(bar, phase), phase ^= 1;
     tc_fence_after();
     float c[4];
@@ -462,17 +481,17 @@ k_field_bwd_tc(atmonr_grid_t g, const __half2* __restrict__ table, const __half*
 #pragma unroll
       for (int cc = 0; cc < 4; ++cc) st_chunk(smem + bwd::kENC, tid, cc, 32, src[cc]);
     } else {
-      encode_to_tile(lv, table, p, smem + bwd::kENC, tid);
+      encode_to_tile(lv, table, p, smem + bwd::kENC, tid, l2_policy_keep());
     }
     publish_and_sync();
-    if (tid == 0) issue_layer<32>(tmem + bwd::cAcc32, sb + bwd::kENC, sb + bwd::kW + fwd::kW1P, bar);
+    if (warp == 0) issue_layer<32>(tmem + bwd::cAcc32, sb + bwd::kENC, sb + bwd::kW + fwd::kW1P, bar);
     mbar_wait(bar, phase), phase ^= 1;
     tc_fence_after();
     float v[32];
     tmem_ld32(my32, v);
     store_row32<true>(smem + bwd::kH, tid, v);
     publish_and_sync();
-    if (tid == 0) issue_layer<16>(tmem + bwd::cAcc16, sb + bwd::kH, sb + bwd::kW + fwd::kW2P, bar);
+    if (warp == 0) issue_layer<16>(tmem + bwd::cAcc16, sb + bwd::kH, sb + bwd::kW + fwd::kW2P, bar);
     mbar_wait(bar, phase), phase ^= 1;
     tc_fence_after();
     {
@@ -482,13 +501,13 @@ k_field_bwd_tc(atmonr_grid_t g, const __half2* __restrict__ table, const __half*
     }
     store_row32<false>(smem + bwd::kDIN, tid, v);
     publish_and_sync();
-    if (tid == 0) issue_layer<32>(tmem + bwd::cAcc32, sb + bwd::kDIN, sb + bwd::kW + fwd::kWD1, bar);
+    if (warp == 0) issue_layer<32>(tmem + bwd::cAcc32, sb + bwd::kDIN, sb + bwd::kW + fwd::kWD1, bar);
     mbar_wait(bar, phase), phase ^= 1;
     tc_fence_after();
     tmem_ld32(my32, v);
     store_row32<true>(smem + bwd::kH1, tid, v);
     publish_and_sync();
-    if (tid == 0) issue_layer<32>(tmem + bwd::cAcc32, sb + bwd::kH1, sb + bwd::kW + fwd::kWD2, bar);
+    if (warp == 0) issue_layer<32>(tmem + bwd::cAcc32, sb + bwd::kH1, sb + bwd::kW + fwd::kWD2, bar);
     mbar_wait(bar, phase), phase ^= 1;
     tc_fence_after();
     tmem_ld32(my32, v);
@@ -505,7 +524,7 @@ k_field_bwd_tc(atmonr_grid_t g, const __half2* __restrict__ table, const __half*
       store_row16(smem + bwd::kDO, tid, dout);
     }
     publish_and_sync();
-    if (tid == 0) {
+    if (warp == 0) {
       tc_fence_after();
       issue_dinput<16>(tmem + bwd::cAcc32, sb + bwd::kDO, sb + bwd::kW + fwd::kWD3);
       umma_commit(bar);  // the next epilogue only waits for the input gradient ...
@@ -516,7 +535,7 @@ k_field_bwd_tc(atmonr_grid_t g, const __half2* __restrict__ table, const __half*
     tmem_ld32(my32, v);
     store_row32_masked(smem + bwd::kDA, smem + bwd::kH2, tid, v);
     publish_and_sync();
-    if (tid == 0) {
+    if (warp == 0) {
       tc_fence_after();
       issue_dinput<32>(tmem + bwd::cAcc32, sb + bwd::kDA, sb + bwd::kW + fwd::kWD2);
       umma_commit(bar);  // the next epilogue only waits for the input gradient ...
@@ -527,7 +546,7 @@ k_field_bwd_tc(atmonr_grid_t g, const __half2* __restrict__ table, const __half*
     tmem_ld32(my32, v);
     store_row32_masked(smem + bwd::kDB, smem + bwd::kH1, tid, v);
     publish_and_sync();
-    if (tid == 0) {
+    if (warp == 0) {
       tc_fence_after();
       issue_dinput<32>(tmem + bwd::cAcc32, sb + bwd::kDB, sb + bwd::kW + fwd::kWD1);
       umma_commit(bar);  // the next epilogue only waits for the input gradient ...
@@ -544,7 +563,7 @@ k_field_bwd_tc(atmonr_grid_t g, const __half2* __restrict__ table, const __half*
       store_row16(smem + bwd::kDP, tid, dpo);
     }
     publish_and_sync();
-    if (tid == 0) {
+    if (warp == 0) {
       tc_fence_after();
       issue_dinput<16>(tmem + bwd::cAcc32, sb + bwd::kDP, sb + bwd::kW + fwd::kW2P);
       umma_commit(bar);  // the next epilogue only waits for the input gradient ...
@@ -555,7 +574,7 @@ k_field_bwd_tc(atmonr_grid_t g, const __half2* __restrict__ table, const __half*
     tmem_ld32(my32, v);
     store_row32_masked(smem + bwd::kDA, smem + bwd::kH, tid, v);
     publish_and_sync();
-    if (tid == 0) {
+    if (warp == 0) {
       tc_fence_after();
       issue_dinput<32>(tmem + bwd::cAcc32, sb + bwd::kDA, sb + bwd::kW + fwd::kW1P);
       umma_commit(bar);  // the next epilogue only waits for the input gradient ...
@@ -731,58 +750,58 @@ k_field_bwd_tc2(atmonr_grid_t g, const __half* __restrict__ pos_w, const __half*
 
   if (warp == 8) {
     // ------------------------------- MMA issuer warp ----------------------------------------
+    // (all 32 lanes run this code converged; umma_f16 / umma_commit elect the issuing lane)
     // Every tcgen05.mma of the CTA is issued here, so the epilogue warps never stall behind the
     // (long) weight-gradient issue sequences: a stage's input-gradient MMAs are committed first,
     // its weight-gradient MMAs are issued while the epilogue warps already work on the result.
-    const bool leader = (tid & 31) == 0;
     uint32_t seen_tile = 0;
     for (int64_t tile = blockIdx.x; tile * bwd2::kRows < M; tile += gridDim.x, seen_tile = 1) {
       stage_wait();  // X = encoded features
-      if (leader) {
+      {
         issue_layer2<32>(tmem, 0, sb + bwd2::kX, sw + fwd::kW1P);
         umma_commit(bar);
       }
       stage_wait();  // H
-      if (leader) {
+      {
         issue_layer2<16>(tmem, 32, sb + bwd2::kH, sw + fwd::kW2P);
         umma_commit(bar);
       }
       stage_wait();  // DIN
-      if (leader) {
+      {
         issue_layer2<32>(tmem, 0, sb + bwd2::kDIN, sw + fwd::kWD1);
         umma_commit(bar);
       }
       stage_wait();  // H1
-      if (leader) {
+      {
         issue_layer2<32>(tmem, 0, sb + bwd2::kH1, sw + fwd::kWD2);
         umma_commit(bar);
       }
       stage_wait();  // S0: DO = dL/d(dir_mlp out), H2
-      if (leader) {
+      {
         issue_dinput2<16>(tmem, sb + bwd2::kDO, sw + fwd::kWD3);
         umma_commit(bar);
         ATM_DW issue_dweight2<16>(tmem + bwd2::cDWd3, sb + bwd2::kDO, sb + bwd2::kH2, seen_tile);
       }
       stage_wait();  // S1: X = dL/dh2
-      if (leader) {
+      {
         issue_dinput2<32>(tmem, sb + bwd2::kX, sw + fwd::kWD2);
         umma_commit(bar);
         ATM_DW issue_dweight2<32>(tmem + bwd2::cDWd2, sb + bwd2::kX, sb + bwd2::kH1, seen_tile);
       }
       stage_wait();  // S2: H2 = dL/dh1
-      if (leader) {
+      {
         issue_dinput2<32>(tmem, sb + bwd2::kH2, sw + fwd::kWD1);
         umma_commit(bar);
         ATM_DW issue_dweight2<32>(tmem + bwd2::cDWd1, sb + bwd2::kH2, sb + bwd2::kDIN, seen_tile);
       }
       stage_wait();  // S3: DO = dL/d(pos_mlp out)
-      if (leader) {
+      {
         issue_dinput2<16>(tmem, sb + bwd2::kDO, sw + fwd::kW2P);
         umma_commit(bar);
         ATM_DW issue_dweight2<16>(tmem + bwd2::cDW2p, sb + bwd2::kDO, sb + bwd2::kH, seen_tile);
       }
       stage_wait();  // S4: H1 = dL/dh, DIN = encoded features again
-      if (leader) {
+      {
         issue_dinput2<32>(tmem, sb + bwd2::kH1, sw + fwd::kW1P);
         umma_commit(bar);
         ATM_DW issue_dweight2<32>(tmem + bwd2::cDW1p, sb + bwd2::kH1, sb + bwd2::kDIN, seen_tile);

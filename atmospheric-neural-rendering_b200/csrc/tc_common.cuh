@@ -33,21 +33,20 @@ __device__ __forceinline__ uint32_t tile_off(int r, int c, int C) {
 // ---- descriptors ------------------------------------------------------------------------
 // Shared-memory matrix descriptor (cute::UMMA::SmemDescriptor): start address, leading and
 // stride byte offsets in 16-byte units, descriptor version 1 (Blackwell), no swizzle.
-__device__ __forceinline__ uint64_t make_smem_desc(uint32_t saddr, uint32_t lbo_bytes, uint32_t sbo_bytes) {
-  uint64_t d = 0;
-  d |= (uint64_t)((saddr >> 4) & 0x3FFF);
-  d |= (uint64_t)((lbo_bytes >> 4) & 0x3FFF) << 16;
-  d |= (uint64_t)((sbo_bytes >> 4) & 0x3FFF) << 32;
-  d |= (uint64_t)1 << 46;
-  return d;
+// Every tile address here is a multiple of 16 below 256 KB, so the address field is simply
+// saddr >> 4: descriptors of neighbouring tiles / K steps differ by a compile-time constant and
+// the issuing warp forms each one with a single add.
+__host__ __device__ constexpr uint64_t desc_fields(uint32_t lbo_bytes, uint32_t sbo_bytes) {
+  return ((uint64_t)((lbo_bytes >> 4) & 0x3FFF) << 16) | ((uint64_t)((sbo_bytes >> 4) & 0x3FFF) << 32) |
+         ((uint64_t)1 << 46);
 }
-// K-major operand: rows = M/N (groups of 8 rows are `row_group_bytes` apart), K chunks 128 B apart.
+// K-major operand: rows = M/N (groups of 8 rows are (C/8)*128 B apart), K chunks 128 B apart.
 __device__ __forceinline__ uint64_t desc_k_major(uint32_t saddr, int C) {
-  return make_smem_desc(saddr, kCore, (uint32_t)(C >> 3) * kCore);
+  return desc_fields(kCore, (uint32_t)(C >> 3) * kCore) | (uint64_t)(saddr >> 4);
 }
 // MN-major operand over the same bytes: rows = K, columns = M/N.
 __device__ __forceinline__ uint64_t desc_mn_major(uint32_t saddr, int C) {
-  return make_smem_desc(saddr, (uint32_t)(C >> 3) * kCore, kCore);
+  return desc_fields((uint32_t)(C >> 3) * kCore, kCore) | (uint64_t)(saddr >> 4);
 }
 
 // Instruction descriptor (cute::UMMA::InstrDescriptor) for kind::f16: fp16 A and B, fp32 D.
@@ -98,22 +97,33 @@ __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
 }
 
 // ---- MMA ---------------------------------------------------------------------------------
-// D[tmem] (+)= A[smem] * B[smem]^T, issued by ONE thread.
+// D[tmem] (+)= A[smem] * B[smem]^T. Called by ALL 32 lanes of one converged warp with identical
+// (warp-uniform) operands; elect.sync picks the lane that issues. Predicating the instruction on
+// the elect predicate (instead of branching on a lane id around it) lets ptxas keep descriptors in
+// uniform registers and emit one UTCHMMA; inside a divergent `if (tid == 0)` it wraps every
+// UTCHMMA in an elect-and-retry loop that costs ~150 cycles per MMA (measured, scratch/ubench).
 __device__ __forceinline__ void umma_f16(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t idesc,
                                          uint32_t accumulate) {
   asm volatile(
       "{\n\t"
-      ".reg .pred p;\n\t"
+      ".reg .pred p, q;\n\t"
       "setp.ne.b32 p, %4, 0;\n\t"
-      "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t"
+      "elect.sync _|q, 0xffffffff;\n\t"
+      "@q tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t"
       "}" ::"r"(tmem_d),
       "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate)
       : "memory");
 }
-// Make the mbarrier track completion of all MMAs issued so far by this thread.
+// Make the mbarrier track completion of all MMAs issued so far by the elected lane (same calling
+// convention as umma_f16: the whole converged warp).
 __device__ __forceinline__ void umma_commit(uint64_t* bar) {
-  asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(bar))
-               : "memory");
+  asm volatile(
+      "{\n\t"
+      ".reg .pred q;\n\t"
+      "elect.sync _|q, 0xffffffff;\n\t"
+      "@q tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];\n\t"
+      "}" ::"r"(smem_u32(bar))
+      : "memory");
 }
 
 // ---- TMEM -> registers (each thread reads its own lane: 32 lanes per warp, N consecutive columns)
