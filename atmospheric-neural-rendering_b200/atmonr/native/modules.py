@@ -65,8 +65,8 @@ class Encoding(nn.Module):
             kind = sub["otype"]
             grid = None
             if kind == "HashGrid":
-                if n not in (2, 3):
-                    raise NotImplementedError("HashGrid over 2 or 3 dims only (include_height / 4-D grids: SURVEY 8f-4)")
+                if n not in (2, 3, 4):  # 4: positions + height (`include_height`)
+                    raise NotImplementedError("HashGrid over 2, 3 or 4 dims")
                 grid = L.grid_layout(n, sub)
             elif kind == "SphericalHarmonics":
                 if int(sub["degree"]) != 2 or n != 3:

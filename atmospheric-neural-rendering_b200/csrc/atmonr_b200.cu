@@ -870,7 +870,7 @@ static int set_smem(Kern k, size_t bytes, const char* name) {
 
 static bool mlp_supported(const atmonr_mlp_t* m) {
   return m && m->width == kWidth && m->out_pad == kOutPad && (m->n_hidden == 1 || m->n_hidden == 2) &&
-         (m->in_pad == 32 || m->in_pad == 48) && m->n_in <= m->in_pad && m->n_out <= m->out_pad;
+         (m->in_pad == 16 || m->in_pad == 32 || m->in_pad == 48) && m->n_in <= m->in_pad && m->n_out <= m->out_pad;
 }
 static bool is_shape(const atmonr_mlp_t* m, int in_pad, int nh) {
   return mlp_supported(m) && m->in_pad == in_pad && m->n_hidden == nh;
@@ -909,7 +909,7 @@ const char* atmonr_last_error(void) { return g_last_error; }
 int atmonr_grid_layout(int n_dims, int n_levels, int log2_hashmap_size, int base_resolution,
                        float per_level_scale, atmonr_grid_t* out) {
   ATM_REQUIRE(out, "atmonr_grid_layout", "null output");
-  ATM_REQUIRE(n_dims == 2 || n_dims == 3, "atmonr_grid_layout", "n_dims must be 2 or 3");
+  ATM_REQUIRE(n_dims >= 2 && n_dims <= 4, "atmonr_grid_layout", "n_dims must be 2, 3 or 4");
   ATM_REQUIRE(n_levels >= 1 && n_levels <= ATMONR_MAX_LEVELS, "atmonr_grid_layout", "n_levels out of range");
   ATM_REQUIRE(log2_hashmap_size >= 3 && log2_hashmap_size <= 30, "atmonr_grid_layout", "log2_hashmap_size out of range");
   memset(out, 0, sizeof(*out));
@@ -976,16 +976,19 @@ int atmonr_ngp_sample_points(const atmonr_frame_t* f, const float* origin, const
   return 0;
 }
 
-#define ATM_GRID_DISPATCH(g, CALL2, CALL3)          \
-  if ((g)->n_dims == 2) { CALL2; } else { CALL3; }
+// one instantiation per grid dimensionality: 2 (surface), 3 (positions), 4 (positions + height,
+// `include_height`, samplers.py:168-195)
+#define ATM_GRID_DISPATCH(g, KERNEL, ...)                           \
+  if ((g)->n_dims == 2) { KERNEL<2> __VA_ARGS__; }                  \
+  else if ((g)->n_dims == 3) { KERNEL<3> __VA_ARGS__; }             \
+  else { KERNEL<4> __VA_ARGS__; }
 
 int atmonr_hashgrid_fwd(const atmonr_grid_t* g, const float* x, int xs, const void* table, int64_t M, float* out,
                         void* stream) {
   ATM_REQUIRE(g && g->n_feat == 2, "atmonr_hashgrid_fwd", "bad grid");
   if (M == 0) return 0;
   const int grid = grid_for(M, 128);
-  ATM_GRID_DISPATCH(g, (k_hashgrid_fwd<2><<<grid, 128, 0, S(stream)>>>(*g, x, xs, (const __half2*)table, M, out)),
-                    (k_hashgrid_fwd<3><<<grid, 128, 0, S(stream)>>>(*g, x, xs, (const __half2*)table, M, out)));
+  ATM_GRID_DISPATCH(g, k_hashgrid_fwd, <<<grid, 128, 0, S(stream)>>>(*g, x, xs, (const __half2*)table, M, out));
   ATM_CHECK_LAUNCH("atmonr_hashgrid_fwd");
   return 0;
 }
@@ -995,8 +998,7 @@ int atmonr_hashgrid_bwd(const atmonr_grid_t* g, const float* x, int xs, const fl
   ATM_REQUIRE(g && g->n_feat == 2, "atmonr_hashgrid_bwd", "bad grid");
   if (M == 0) return 0;
   const int grid = grid_for(M, 128);
-  ATM_GRID_DISPATCH(g, (k_hashgrid_bwd<2><<<grid, 128, 0, S(stream)>>>(*g, x, xs, dout, M, dtable)),
-                    (k_hashgrid_bwd<3><<<grid, 128, 0, S(stream)>>>(*g, x, xs, dout, M, dtable)));
+  ATM_GRID_DISPATCH(g, k_hashgrid_bwd, <<<grid, 128, 0, S(stream)>>>(*g, x, xs, dout, M, dtable));
   ATM_CHECK_LAUNCH("atmonr_hashgrid_bwd");
   return 0;
 }
@@ -1006,8 +1008,7 @@ int atmonr_hashgrid_indices(const atmonr_grid_t* g, const float* x, int xs, int6
   ATM_REQUIRE(g, "atmonr_hashgrid_indices", "bad grid");
   if (M == 0) return 0;
   const int grid = grid_for(M, 128);
-  ATM_GRID_DISPATCH(g, (k_hashgrid_indices<2><<<grid, 128, 0, S(stream)>>>(*g, x, xs, M, idx)),
-                    (k_hashgrid_indices<3><<<grid, 128, 0, S(stream)>>>(*g, x, xs, M, idx)));
+  ATM_GRID_DISPATCH(g, k_hashgrid_indices, <<<grid, 128, 0, S(stream)>>>(*g, x, xs, M, idx));
   ATM_CHECK_LAUNCH("atmonr_hashgrid_indices");
   return 0;
 }
@@ -1015,8 +1016,10 @@ int atmonr_hashgrid_indices(const atmonr_grid_t* g, const float* x, int xs, int6
 #endif  // ATM_PART_BASIC
 #if ATM_PART_MLP
 int atmonr_mlp_fwd(const atmonr_mlp_t* m, const void* w, const float* x, int64_t M, float* out, void* stream) {
-  ATM_REQUIRE(mlp_supported(m), "atmonr_mlp_fwd", "unsupported MLP shape (width 32, in_pad 32|48, 1|2 hidden layers)");
+  ATM_REQUIRE(mlp_supported(m), "atmonr_mlp_fwd", "unsupported MLP shape (width 32, in_pad 16|32|48, 1|2 hidden layers)");
   if (M == 0) return 0;
+  if (m->in_pad == 16 && m->n_hidden == 1) return launch_mlp_fwd<16, 1>(m, w, x, M, out, stream);
+  if (m->in_pad == 16 && m->n_hidden == 2) return launch_mlp_fwd<16, 2>(m, w, x, M, out, stream);
   if (m->in_pad == 32 && m->n_hidden == 1) return launch_mlp_fwd<32, 1>(m, w, x, M, out, stream);
   if (m->in_pad == 32 && m->n_hidden == 2) return launch_mlp_fwd<32, 2>(m, w, x, M, out, stream);
   if (m->in_pad == 48 && m->n_hidden == 1) return launch_mlp_fwd<48, 1>(m, w, x, M, out, stream);
@@ -1025,9 +1028,11 @@ int atmonr_mlp_fwd(const atmonr_mlp_t* m, const void* w, const float* x, int64_t
 
 int atmonr_mlp_bwd(const atmonr_mlp_t* m, const void* w, const float* x, const float* dout, int64_t M, float* dx,
                    float* dw, void* stream) {
-  ATM_REQUIRE(mlp_supported(m), "atmonr_mlp_bwd", "unsupported MLP shape (width 32, in_pad 32|48, 1|2 hidden layers)");
+  ATM_REQUIRE(mlp_supported(m), "atmonr_mlp_bwd", "unsupported MLP shape (width 32, in_pad 16|32|48, 1|2 hidden layers)");
   ATM_REQUIRE(dw, "atmonr_mlp_bwd", "null dw");
   if (M == 0) return 0;
+  if (m->in_pad == 16 && m->n_hidden == 1) return launch_mlp_bwd<16, 1>(m, w, x, dout, M, dx, dw, stream);
+  if (m->in_pad == 16 && m->n_hidden == 2) return launch_mlp_bwd<16, 2>(m, w, x, dout, M, dx, dw, stream);
   if (m->in_pad == 32 && m->n_hidden == 1) return launch_mlp_bwd<32, 1>(m, w, x, dout, M, dx, dw, stream);
   if (m->in_pad == 32 && m->n_hidden == 2) return launch_mlp_bwd<32, 2>(m, w, x, dout, M, dx, dw, stream);
   if (m->in_pad == 48 && m->n_hidden == 1) return launch_mlp_bwd<48, 1>(m, w, x, dout, M, dx, dw, stream);

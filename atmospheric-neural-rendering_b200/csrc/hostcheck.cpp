@@ -58,7 +58,8 @@ void hc_ngp_sample_points(const atmonr_frame_t* f, const float* o, const float* 
 
 void hc_hashgrid_indices(const atmonr_grid_t* g, const float* x, int xs, int64_t M, uint32_t* idx, float* w) {
   if (g->n_dims == 2) indices_impl<2>(g, x, xs, M, idx, w);
-  else indices_impl<3>(g, x, xs, M, idx, w);
+  else if (g->n_dims == 3) indices_impl<3>(g, x, xs, M, idx, w);
+  else indices_impl<4>(g, x, xs, M, idx, w);
 }
 
 void hc_philox(uint64_t seed, uint64_t ray0, int64_t B, int N, float* out) {

@@ -165,7 +165,8 @@ __device__ __forceinline__ void stage_float(float* s, int ld, const float (&v)[N
 // Shared-memory scratch of the backward tile: activations and deltas.
 template <int IN>
 struct BwdScratch {
-  static constexpr int kFloats = kTile * (IN + 4) + kTile * (kWidth + 4);
+  static constexpr int kActCols = (IN > kWidth ? IN : kWidth) + 4;  // the activation area also stages hidden rows
+  static constexpr int kFloats = kTile * kActCols + kTile * (kWidth + 4);
 };
 
 // Backward through one MLP for the CTA's tile. Every thread of the CTA must call it (it
@@ -181,7 +182,7 @@ __device__ __forceinline__ void mlp_backward(const float* __restrict__ W, float*
                                              const float (&dout)[kOutPad], float (&dx)[IN]) {
   using S = MlpShape<IN, NH>;
   float* sA = scratch;
-  float* sD = scratch + kTile * (IN + 4);
+  float* sD = scratch + kTile * BwdScratch<IN>::kActCols;
   float dh[kWidth];
 
   // output layer: dW_out += dout^T h_last ; dh = W_out^T dout, masked by the ReLU

@@ -23,13 +23,18 @@ MODULES = ("pos_encoder", "pos_mlp", "dir_encoder", "dir_mlp", "surf_encoder", "
 
 
 class NGPOracle:
-    def __init__(self, cfg: dict, frame: HorizontalFrame | None, max_i: float, fp16: bool = False):
-        """cfg is the "pipeline" section of configs/instant_ngp.json."""
+    def __init__(self, cfg: dict, frame: HorizontalFrame | None, max_i: float, fp16: bool = False, geo=None):
+        """cfg is the "pipeline" section of configs/instant_ngp.json. `frame` is the granule frame of
+        the 'horizontal' point preprocessor (None when the config has no preprocessor); `geo` =
+        (scale, offset (3,) float64 tensor, ray_origin_height) is what pipeline.py:30-58 captures
+        from the dataset, needed without a frame (`include_height`, and z in km)."""
         self.cfg, self.frame, self.max_i, self.fp16 = cfg, frame, float(max_i), fp16
+        self.geo = geo
+        assert not (cfg["include_height"] and frame is not None)  # pipeline.py:30-32
         ngp = cfg["instant_ngp"]
         self.n_sigma = cfg["num_bands"] if cfg["multi_band_extinction"] else 1
-        assert not cfg["include_height"], "oracle covers the shipped configs (include_height=false)"
-        self.pos_encoder = tcnn_spec.make_encoding(3, ngp["encoding"])
+        self.n_pos = 4 if cfg["include_height"] else 3
+        self.pos_encoder = tcnn_spec.make_encoding(self.n_pos, ngp["encoding"])
         self.pos_mlp = tcnn_spec.Network(self.pos_encoder.n_output_dims, 16, ngp["network"])
         self.dir_encoder = tcnn_spec.make_encoding(3 + 16 - self.n_sigma, ngp["dir_encoding"])
         self.dir_mlp = tcnn_spec.Network(self.dir_encoder.n_output_dims, cfg["num_bands"], ngp["rgb_network"])
@@ -52,9 +57,12 @@ class NGPOracle:
             pts = preprocess_horizontal(pts, self.frame)
         pts = (pts + 1) / 2
         pts_surf = (pts_surf + 1) / 2
+        if cfg["include_height"]:  # instant_ngp.py:152-154 (applied to the [0,1] points, like the reference)
+            scale, offset, height = self.geo
+            pts = sampling.append_heights(pts, height, scale, offset)
         dirs = batch["dir"][:, None].repeat(1, n, 1)
-        pts = torch.cat([pts[..., :2], pts[..., 2:] / cfg["alt_compress_factor"]], dim=-1)
-        x = pts.view(b * n, 3)
+        pts = torch.cat([pts[..., :2], pts[..., 2:3] / cfg["alt_compress_factor"], pts[..., 3:]], dim=-1)
+        x = pts.view(b * n, self.n_pos)
         pos_out = self.pos_mlp.forward(
             self.pos_encoder.forward(x, params["pos_encoder"], self.fp16), params["pos_mlp"], self.fp16
         )
@@ -69,7 +77,7 @@ class NGPOracle:
         sigma = pos_out[:, : self.n_sigma].view(b, n, -1)
         color, color_surf, sigma = torch.relu(color), torch.relu(color_surf), torch.relu(sigma)
         c, _, w, c_atmo, c_surf = rendering.composite_with_surface(
-            z * (self.frame.scale / 1000 if self.frame else batch["scale"] / 1000), color, sigma, color_surf
+            z * ((self.frame.scale if self.frame else self.geo[0]) / 1000), color, sigma, color_surf
         )
         return {
             "color_fine": color[:, :-1], "color_surf": color_surf, "color_map_surf": c_surf,

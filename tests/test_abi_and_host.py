@@ -56,7 +56,7 @@ def test_bad_arguments_report_errors():
         L.call("atmonr_grid_layout", 3, 17, 19, 16, 1.5, C.byref(g))
 
 
-@pytest.mark.parametrize("dims,key", [(3, "encoding"), (2, "surface_encoding")])
+@pytest.mark.parametrize("dims,key", [(3, "encoding"), (2, "surface_encoding"), (4, "encoding")])
 def test_grid_layout_matches_oracle_bit_for_bit(dims, key):
     from atmonr.native import lib as L
     cfg = ngp_config()["instant_ngp"][key]
@@ -67,7 +67,8 @@ def test_grid_layout_matches_oracle_bit_for_bit(dims, key):
     assert np.array_equal(np.array(g.scale[:16], dtype=np.float32).view(np.uint32), lv["scale"].view(np.uint32))
     assert list(g.res[:16]) == lv["res"].tolist() and list(g.size[:16]) == lv["size"].tolist()
     assert list(g.offset[:17]) == lv["offset"].tolist()
-    assert g.n_entries == (21141696 if dims == 3 else 2761000)
+    if dims < 4:  # 4 = positions + height (`include_height`)
+        assert g.n_entries == (21141696 if dims == 3 else 2761000)
 
 
 def _hc():
@@ -108,7 +109,7 @@ def test_host_build_of_kernel_math_matches_oracle():
     assert np.abs(out64 - want64).max() < 1e-11
 
 
-@pytest.mark.parametrize("dims,key", [(3, "encoding"), (2, "surface_encoding")])
+@pytest.mark.parametrize("dims,key", [(3, "encoding"), (2, "surface_encoding"), (4, "encoding")])
 def test_host_build_of_hash_indexing_is_bit_exact(dims, key):
     from atmonr.native import lib as L
     cfg = ngp_config()["instant_ngp"][key]

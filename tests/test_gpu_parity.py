@@ -91,7 +91,7 @@ def test_ngp_sample_points_matches_oracle(scene):
 
 
 # ------------------------------------------------------------------ hash grid
-@pytest.mark.parametrize("dims,key", [(3, "encoding"), (2, "surface_encoding")])
+@pytest.mark.parametrize("dims,key", [(3, "encoding"), (2, "surface_encoding"), (4, "encoding")])
 def test_hashgrid_indices_bit_exact_and_features(dims, key):
     L, ops = _native()
     cfg = ngp_config()["instant_ngp"][key]
@@ -102,7 +102,7 @@ def test_hashgrid_indices_bit_exact_and_features(dims, key):
     g = torch.Generator().manual_seed(5)
     x = torch.rand(4096, dims, generator=g)
     x[:8] = torch.tensor([0.0, 1.0, 0.5, 0.25, 0.999999, 1e-7, 0.125, 0.75])[:, None]  # edges
-    if dims == 3:
+    if dims >= 3:
         x[:, 2] *= 0.125   # compressed altitude range
     idx = ops.hashgrid_indices(grid, x.cuda()).cpu().to(torch.int64) & 0xFFFFFFFF
     assert torch.equal(idx, grid_o.all_indices(x))
@@ -123,7 +123,7 @@ def test_hashgrid_indices_bit_exact_and_features(dims, key):
 
 
 # ------------------------------------------------------------------ MLPs
-@pytest.mark.parametrize("n_in,n_out,key", [(32, 16, "network"), (19, 4, "rgb_network"), (36, 4, "surface_network")])
+@pytest.mark.parametrize("n_in,n_out,key", [(32, 16, "network"), (19, 4, "rgb_network"), (36, 4, "surface_network"), (16, 4, "rgb_network")])
 def test_mlp_forward_backward(n_in, n_out, key):
     L, ops = _native()
     cfg = ngp_config()["instant_ngp"][key]
@@ -292,6 +292,43 @@ def test_ngp_pipeline_forward_loss_gradients_vs_oracle(scene, impl, monkeypatch)
     assert rel_err(out_m["color_map_fine"], out["color_map_fine"]) < 1e-5
 
 
+@pytest.mark.parametrize("height,multi_band", [(True, False), (False, True), (True, True)])
+def test_ngp_optional_inputs_vs_oracle(scene, height, multi_band):
+    """`include_height` (4-D hash grid over [x, y, z/8, h], samplers.py:168-195) and
+    `multi_band_extinction` (one density per band): off in the shipped configs, served by the
+    operator-by-operator path. include_height excludes the 'horizontal' preprocessor
+    (pipeline.py:30-32)."""
+    cfg = ngp_config(24)
+    cfg["include_height"], cfg["multi_band_extinction"] = height, multi_band
+    if height:
+        cfg["point_preprocessor"] = ""
+    geo = (scene.scale, scene.offset, 20000.0)
+    orc = NGPOracle(cfg, None if height else scene.frame, scene.max_i, fp16=True, geo=geo)
+    params = random_params(orc, seed=3, table_scale=2e3)
+    b = take(scene.batch, slice(0, 40))
+    u = torch.rand(40, 24, generator=torch.Generator().manual_seed(4))
+    res = orc.forward(b, params, u)
+    loss = orc.loss(b, res)
+    loss.backward()
+    ds = FakeDataset(scene)
+    ds.offset = scene.offset.cuda()
+    from atmonr.pipelines.instant_ngp import InstantNGPPipeline
+    pipe = InstantNGPPipeline(cfg, ds)
+    pipe.send_tensors_to(0)
+    assert pipe.fused_state is None          # not the fused kernels' configuration
+    load_params(pipe, params)
+    bc = to_cuda(b)
+    out = pipe.forward(bc, u=u.cuda())
+    lg = pipe.compute_loss(bc, out)
+    lg.backward()
+    assert out["sigma_fine"].shape[-1] == (4 if multi_band else 1)
+    for key in ("color_map_fine", "color_map_atmo", "color_map_surf", "sigma_fine", "color_fine"):
+        assert rel_err(out[key], res[key]) < 2e-3, key
+    assert rel_err(lg, loss) < 1e-3
+    for name in ("pos_mlp", "dir_mlp", "surf_mlp", "pos_encoder", "surf_encoder"):
+        assert rel_err(getattr(pipe, name).params.grad, params[name].grad) < 4e-3, name
+
+
 def test_ngp_training_tracks_oracle(scene):
     """Same initial parameters, same batches, same uniform draws: the native loss curve follows
     the oracle's (torch AdamW on the fp16-emulating restatement)."""
@@ -381,11 +418,11 @@ def test_tcgen05_probe(mode):
     assert torch.allclose(got, want, rtol=1e-3, atol=1e-3), float((got - want).abs().max())
 
 
-@pytest.mark.parametrize("impl", ["simt", "tc"])
-def test_ngp_loss_curve_tracks_oracle_300_steps(scene, impl, monkeypatch):
-    """north_star: 'loss curves tracking the reference'. 300 optimisation steps with identical
-    initial parameters, batches and uniform draws; small hash tables (log2 T = 12) keep the CPU
-    oracle's dense AdamW cheap.
+@pytest.mark.parametrize("impl,n_steps", [("simt", 300), ("tc", 300), ("tc", 2000)])
+def test_ngp_loss_curve_tracks_oracle(scene, impl, n_steps, monkeypatch):
+    """north_star: 'loss curves tracking the reference over 2k steps'. 300 / 2000 optimisation
+    steps with identical initial parameters, batches and uniform draws; small hash tables
+    (log2 T = 12) keep the CPU oracle's dense AdamW cheap.
 
     AdamW with eps = 1e-15 (configs/instant_ngp.json:94) normalises every non-zero gradient to a
     full-size step, so trajectories of two correct implementations separate chaotically after a
@@ -410,7 +447,7 @@ def test_ngp_loss_curve_tracks_oracle_300_steps(scene, impl, monkeypatch):
     g = torch.Generator().manual_seed(123)
     n_rays = scene.batch["origin"].shape[0]
     lo, ln = [], []
-    for step in range(300):
+    for step in range(n_steps):
         sel = torch.randperm(n_rays, generator=g)[:48]
         b = take(scene.batch, sel)
         u = torch.rand(48, 32, generator=g)
@@ -420,15 +457,16 @@ def test_ngp_loss_curve_tracks_oracle_300_steps(scene, impl, monkeypatch):
         opt_n.zero_grad(); l_n.backward(); opt_n.step()
         lo.append(float(l_o)); ln.append(float(l_n))
     lo, ln = np.array(lo), np.array(ln)
-    smooth = lambda a: np.convolve(a, np.ones(40) / 40, mode="valid")
+    win = max(40, n_steps // 10)   # the 48-ray batches make single losses noisy: compare running means
+    smooth = lambda a: np.convolve(a, np.ones(win) / win, mode="valid")
     so, sn = smooth(lo), smooth(ln)
     dev = np.abs(sn - so) / so
     print(f"[{impl}] first/last smoothed loss: oracle {so[0]:.4f}/{so[-1]:.4f} native {sn[0]:.4f}/{sn[-1]:.4f}; "
           f"max dev {dev.max():.3f} mean dev {dev.mean():.3f}; first 10 steps max dev {np.max(np.abs(ln[:10]-lo[:10])/lo[:10]):.4f}")
     assert np.max(np.abs(ln[:10] - lo[:10]) / lo[:10]) < 0.05   # step-by-step while trajectories are close
     assert sn[-1] < 0.2 * sn[0] and so[-1] < 0.2 * so[0]        # both make the same real progress
-    print("  smoothed oracle", np.round(so[::20], 4).tolist())
-    print("  smoothed native", np.round(sn[::20], 4).tolist())
+    print("  smoothed oracle", np.round(so[:: n_steps // 15], 4).tolist())
+    print("  smoothed native", np.round(sn[:: n_steps // 15], 4).tolist())
     ratio = sn / so
     assert 0.5 < ratio.min() and ratio.max() < 2.0               # same curve (chaotic bumps stay within a band)
     assert 0.6 < sn[-1] / so[-1] < 1.5                           # and the same final loss level
