@@ -35,6 +35,47 @@ namespace atm {
 using namespace tc;
 
 // =========================================================================================
+// weight-gradient MMAs with sample-group concatenation
+// =========================================================================================
+// dW[o][i] = sum_s delta[s][o] * act[s][i] has a tiny output (<= 32 x 32) and a huge K (samples),
+// while a tcgen05.mma of M = 128 costs ~40 cycles whatever N <= 64 is (scratch/ubench): the cost
+// is the number of MMAs. Both operands are read MN-major from [rows][C] tiles whose 8-row groups
+// are contiguous blocks of (C/8)*128 bytes, so column group C/8 + j of row group g IS column
+// group j of row group g + 1: reading "too many" columns concatenates the following row groups
+// for free. With the MMA's two K row groups WAYS groups apart,
+//     A = act tile  (M = 128: row groups g .. g+3 side by side, 32 columns each),
+//     B = delta tile (N = WAYS * KD: row groups g .. g+WAYS-1 side by side),
+// D[32 q + i][KD q' + o] = sum over the rows of groups {g+q, g+WAYS+q} x {g+q', g+WAYS+q'}; the
+// diagonal blocks q = q' < WAYS hold the gradient of 16 * WAYS samples per MMA (the off-diagonal
+// blocks are ignored). The flush sums the diagonal blocks: dW[o][i] = sum_q D[32 q + i][KD q + o].
+template <int KD, int WAYS, int ROWS>
+__device__ __forceinline__ void issue_dweight_t(uint32_t acc, uint32_t act_tile, uint32_t d_tile, uint32_t accumulate) {
+  constexpr uint32_t idesc = make_idesc(128, WAYS * KD, 1, 1);
+  constexpr int kGroupsPerMma = 2 * WAYS;
+#pragma unroll
+  for (int j = 0; j < ROWS / (8 * kGroupsPerMma); ++j)
+    umma_f16(acc, desc_mn_major_strided(act_tile + j * kGroupsPerMma * 4 * kCore, 32, WAYS),
+             desc_mn_major_strided(d_tile + j * kGroupsPerMma * (KD / 8) * kCore, KD, WAYS), idesc,
+             accumulate | (uint32_t)(j > 0));
+}
+// Add the diagonal blocks of one accumulator into dW (row-major [KD_real rows][32]); called by the
+// first WAYS warps of the CTA (warp q owns TMEM lanes 32 q ..).
+template <int KD, int WAYS>
+__device__ __forceinline__ void flush_dweight_t(uint32_t tmem, int col, int warp, int lane, int rows, float scale,
+                                                float* __restrict__ dW) {
+  if (warp >= WAYS) return;
+  float v[KD];
+  if constexpr (KD == 32) {
+    tmem_ld32(tmem_addr(tmem, warp, col + KD * warp), v);
+  } else {
+    tmem_ld16(tmem_addr(tmem, warp, col + KD * warp), v);
+  }
+#pragma unroll
+  for (int o = 0; o < KD; ++o)
+    if (o < rows) atomicAdd(dW + o * 32 + lane, v[o] * scale);
+}
+
+// =========================================================================================
 // probe
 // =========================================================================================
 __global__ void __launch_bounds__(128) k_tc_probe(const __half* __restrict__ A, const __half* __restrict__ B,
@@ -50,8 +91,13 @@ __global__ void __launch_bounds__(128) k_tc_probe(const __half* __restrict__ A, 
   }
   __syncthreads();
   load_matrix_tile(A, sA, 128, 32);
-  load_matrix_tile(B, sB, 128, 32);
-  if (warp == 0) tmem_alloc<32>(&tmem_base_s);
+  if (mode == 4) {  // [128][16] tile from the first 16 columns of B
+    for (int i = tid; i < 128 * 2; i += 128)
+      st_chunk(sB, i >> 1, i & 1, 16, *reinterpret_cast<const uint4*>(B + (i >> 1) * 32 + (i & 1) * 8));
+  } else {
+    load_matrix_tile(B, sB, 128, 32);
+  }
+  if (warp == 0) tmem_alloc<64>(&tmem_base_s);
   if (tid == 0) {
     mbar_init(&bar, 1);
     fence_mbar_init();
@@ -71,11 +117,15 @@ __global__ void __launch_bounds__(128) k_tc_probe(const __half* __restrict__ A, 
       const uint32_t idesc = make_idesc(128, 32, 0, 1);
       for (int k = 0; k < 2; ++k)
         umma_f16(tmem, desc_k_major(a0 + k * 2 * kCore, 32), desc_mn_major(b0 + k * 2 * 4 * kCore, 32), idesc, k > 0);
-    } else {  // D[m][n] = sum_s A[s][m] * B[s][n] : both MN-major, K = 128 samples
+    } else if (mode == 2) {  // D[m][n] = sum_s A[s][m] * B[s][n] : both MN-major, K = 128 samples
       const uint32_t idesc = make_idesc(128, 32, 1, 1);
       for (int k = 0; k < 8; ++k)
         umma_f16(tmem, desc_mn_major(a0 + k * 2 * 4 * kCore, 32), desc_mn_major(b0 + k * 2 * 4 * kCore, 32), idesc,
                  k > 0);
+    } else if (mode == 3) {  // sample-group concatenation, 32-column delta tile (B), two ways
+      issue_dweight_t<32, 2, 128>(tmem, a0, b0, 0);
+    } else {                 // the same with a 16-column delta tile: B holds [128][16] (b[:, :16] repacked)
+      issue_dweight_t<16, 2, 128>(tmem, a0, b0, 0);
     }
     umma_commit(&bar);
   }
@@ -84,10 +134,15 @@ __global__ void __launch_bounds__(128) k_tc_probe(const __half* __restrict__ A, 
   float v[32];
   tmem_ld32(tmem_addr(tmem, warp, 0), v);
 #pragma unroll
-  for (int j = 0; j < 32; ++j) D[tid * 32 + j] = v[j];
+  for (int j = 0; j < 32; ++j) D[tid * (mode >= 3 ? 64 : 32) + j] = v[j];
+  if (mode >= 3) {
+    tmem_ld32(tmem_addr(tmem, warp, 32), v);
+#pragma unroll
+    for (int j = 0; j < 32; ++j) D[tid * 64 + 32 + j] = v[j];
+  }
   tc_fence_before();
   __syncthreads();
-  if (warp == 0) tmem_dealloc<32>(tmem);
+  if (warp == 0) tmem_dealloc<64>(tmem);
 }
 
 
@@ -670,8 +725,10 @@ constexpr int kBar2 = kBar + 8;
 constexpr int kTmemPtr = kBar2 + 8;
 constexpr int kBytes = kTmemPtr + 8;
 constexpr uint32_t kTmemCols = 256;
-constexpr int cHalf = 48;             // per-half accumulators: [0,32) 32-wide, [32,48) 16-wide
-constexpr int cDWd3 = 96, cDWd2 = 128, cDWd1 = 160, cDW2p = 192, cDW1p = 224;
+constexpr int cHalf = 32;             // per-half accumulator (the 16-wide results use its first columns)
+// weight-gradient accumulators (issue_dweight_t): the two 16-column layers and one 32-column
+// layer concatenate two sample groups per MMA, the other two layers take the columns that are left
+constexpr int cDWd3 = 64, cDW2p = 96, cDWd2 = 128, cDWd1 = 192, cDW1p = 224;
 }  // namespace bwd2
 
 template <int N>
@@ -694,15 +751,6 @@ __device__ __forceinline__ void issue_dinput2(uint32_t tmem, uint32_t d_tile, ui
       umma_f16(tmem + h * bwd2::cHalf, desc_k_major(d_tile + h * 16 * (KD / 8) * kCore + k * 2 * kCore, KD),
                desc_mn_major(w_tile + k * 2 * 4 * kCore, 32), idesc, k);
 }
-template <int KD>
-__device__ __forceinline__ void issue_dweight2(uint32_t acc, uint32_t d_tile, uint32_t a_tile, uint32_t accumulate) {
-  constexpr uint32_t idesc = make_idesc(128, 32, 1, 1);
-#pragma unroll
-  for (int k = 0; k < 16; ++k)
-    umma_f16(acc, desc_mn_major(d_tile + k * 2 * (KD / 8) * kCore, KD), desc_mn_major(a_tile + k * 2 * 4 * kCore, 32),
-             idesc, accumulate | (uint32_t)(k > 0));
-}
-
 // named barrier 1: epilogue warps arrive (non-blocking) when their rows of a stage's operand tile
 // are written, the issuer warp waits on it; named barrier 2: the 256 epilogue threads only
 __device__ __forceinline__ void stage_arrive() {
@@ -763,7 +811,7 @@ k_field_bwd_tc2(atmonr_grid_t g, const __half* __restrict__ pos_w, const __half*
       }
       stage_wait();  // H
       {
-        issue_layer2<16>(tmem, 32, sb + bwd2::kH, sw + fwd::kW2P);
+        issue_layer2<16>(tmem, 0, sb + bwd2::kH, sw + fwd::kW2P);
         umma_commit(bar);
       }
       stage_wait();  // DIN
@@ -780,38 +828,38 @@ k_field_bwd_tc2(atmonr_grid_t g, const __half* __restrict__ pos_w, const __half*
       {
         issue_dinput2<16>(tmem, sb + bwd2::kDO, sw + fwd::kWD3);
         umma_commit(bar);
-        ATM_DW issue_dweight2<16>(tmem + bwd2::cDWd3, sb + bwd2::kDO, sb + bwd2::kH2, seen_tile);
+        ATM_DW issue_dweight_t<16, 2, 256>(tmem + bwd2::cDWd3, sb + bwd2::kH2, sb + bwd2::kDO, seen_tile);
       }
       stage_wait();  // S1: X = dL/dh2
       {
         issue_dinput2<32>(tmem, sb + bwd2::kX, sw + fwd::kWD2);
         umma_commit(bar);
-        ATM_DW issue_dweight2<32>(tmem + bwd2::cDWd2, sb + bwd2::kX, sb + bwd2::kH1, seen_tile);
+        ATM_DW issue_dweight_t<32, 2, 256>(tmem + bwd2::cDWd2, sb + bwd2::kH1, sb + bwd2::kX, seen_tile);
       }
       stage_wait();  // S2: H2 = dL/dh1
       {
         issue_dinput2<32>(tmem, sb + bwd2::kH2, sw + fwd::kWD1);
         umma_commit(bar);
-        ATM_DW issue_dweight2<32>(tmem + bwd2::cDWd1, sb + bwd2::kH2, sb + bwd2::kDIN, seen_tile);
+        ATM_DW issue_dweight_t<32, 1, 256>(tmem + bwd2::cDWd1, sb + bwd2::kDIN, sb + bwd2::kH2, seen_tile);
       }
       stage_wait();  // S3: DO = dL/d(pos_mlp out)
       {
         issue_dinput2<16>(tmem, sb + bwd2::kDO, sw + fwd::kW2P);
         umma_commit(bar);
-        ATM_DW issue_dweight2<16>(tmem + bwd2::cDW2p, sb + bwd2::kDO, sb + bwd2::kH, seen_tile);
+        ATM_DW issue_dweight_t<16, 2, 256>(tmem + bwd2::cDW2p, sb + bwd2::kH, sb + bwd2::kDO, seen_tile);
       }
       stage_wait();  // S4: H1 = dL/dh, DIN = encoded features again
       {
         issue_dinput2<32>(tmem, sb + bwd2::kH1, sw + fwd::kW1P);
         umma_commit(bar);
-        ATM_DW issue_dweight2<32>(tmem + bwd2::cDW1p, sb + bwd2::kH1, sb + bwd2::kDIN, seen_tile);
+        ATM_DW issue_dweight_t<32, 1, 256>(tmem + bwd2::cDW1p, sb + bwd2::kDIN, sb + bwd2::kH1, seen_tile);
         umma_commit(bar2);  // tile boundary: every MMA that reads this tile's buffers
       }
       __syncwarp();
     }
   } else {
   // ------------------------------- epilogue warps ---------------------------------------------
-  const uint32_t my32 = tmem_addr(tmem, warp, (warp >> 2) * bwd2::cHalf), my16 = my32 + 32;
+  const uint32_t my32 = tmem_addr(tmem, warp, (warp >> 2) * bwd2::cHalf), my16 = my32;
   uint8_t* X = smem + bwd2::kX;
   uint8_t* H = smem + bwd2::kH;
   uint8_t* DIN = smem + bwd2::kDIN;
@@ -983,28 +1031,13 @@ k_field_bwd_tc2(atmonr_grid_t g, const __half* __restrict__ pos_w, const __half*
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
-  if (warp == 0 && cta_has_work) {
-    const int o = tid;
-    float w[32];
-    tmem_ld32(tmem_addr(tmem, 0, bwd2::cDW1p), w);
-#pragma unroll
-    for (int c = 0; c < 32; ++c) atomicAdd(dpos_w + o * 32 + c, w[c] * invS);
-    tmem_ld32(tmem_addr(tmem, 0, bwd2::cDW2p), w);
-    if (o < 16) {
-#pragma unroll
-      for (int c = 0; c < 32; ++c) atomicAdd(dpos_w + 1024 + o * 32 + c, w[c] * invS);
-    }
-    tmem_ld32(tmem_addr(tmem, 0, bwd2::cDWd1), w);
-#pragma unroll
-    for (int c = 0; c < 32; ++c) atomicAdd(ddir_w + o * 32 + c, w[c] * invS);
-    tmem_ld32(tmem_addr(tmem, 0, bwd2::cDWd2), w);
-#pragma unroll
-    for (int c = 0; c < 32; ++c) atomicAdd(ddir_w + 1024 + o * 32 + c, w[c] * invS);
-    tmem_ld32(tmem_addr(tmem, 0, bwd2::cDWd3), w);
-    if (o < 16) {
-#pragma unroll
-      for (int c = 0; c < 32; ++c) atomicAdd(ddir_w + 2048 + o * 32 + c, w[c] * invS);
-    }
+  if (warp < 2 && cta_has_work) {
+    const int lane = tid & 31;
+    flush_dweight_t<32, 1>(tmem, bwd2::cDW1p, warp, lane, 32, invS, dpos_w);
+    flush_dweight_t<16, 2>(tmem, bwd2::cDW2p, warp, lane, 16, invS, dpos_w + 1024);
+    flush_dweight_t<32, 1>(tmem, bwd2::cDWd1, warp, lane, 32, invS, ddir_w);
+    flush_dweight_t<32, 2>(tmem, bwd2::cDWd2, warp, lane, 32, invS, ddir_w + 1024);
+    flush_dweight_t<16, 2>(tmem, bwd2::cDWd3, warp, lane, 16, invS, ddir_w + 2048);
   }
   tc_fence_before();
   __syncthreads();
@@ -1021,7 +1054,7 @@ extern "C" {
 
 // Debug / parity entry point (declared in include/atmonr_b200.h).
 int atmonr_tc_probe(const void* a_f16, const void* b_f16, int mode, float* d, void* stream) {
-  ATM_REQUIRE(mode >= 0 && mode <= 2, "atmonr_tc_probe", "mode must be 0, 1 or 2");
+  ATM_REQUIRE(mode >= 0 && mode <= 4, "atmonr_tc_probe", "mode must be 0..4");
   k_tc_probe<<<1, 128, 0, reinterpret_cast<cudaStream_t>(stream)>>>((const __half*)a_f16, (const __half*)b_f16, mode, d);
   ATM_CHECK_LAUNCH("atmonr_tc_probe");
   return 0;

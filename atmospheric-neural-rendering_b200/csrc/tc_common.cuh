@@ -96,6 +96,12 @@ __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
       : "memory");
 }
 
+// MN-major operand whose K direction skips row groups: the two 8-row K groups of one MMA are
+// `k_group_stride` row groups apart (see issue_dweight_t in ngp_fused.cu).
+__device__ __forceinline__ uint64_t desc_mn_major_strided(uint32_t saddr, int C, int k_group_stride) {
+  return desc_fields((uint32_t)(C >> 3) * kCore * (uint32_t)k_group_stride, kCore) | (uint64_t)(saddr >> 4);
+}
+
 // ---- MMA ---------------------------------------------------------------------------------
 // D[tmem] (+)= A[smem] * B[smem]^T. Called by ALL 32 lanes of one converged warp with identical
 // (warp-uniform) operands; elect.sync picks the lane that issues. Predicating the instruction on

@@ -215,7 +215,9 @@ int atmonr_sample_pdf(const float* weights, const float* z_coarse, const float* 
  * a, b: (128, 32) fp16 row-major; d: (128, 32) float32.
  *   mode 0: d = a @ b[:32].T   (forward layer: A and B K-major)
  *   mode 1: d = a @ b[:32]     (input gradient: B read MN-major)
- *   mode 2: d[:32] = a.T @ b   (weight gradient: A and B MN-major, K = 128 rows) */
+ *   mode 2: d[:32] = a.T @ b   (weight gradient: A and B MN-major, K = 128 rows)
+ *   mode 3: d is (128, 64); d[:32, :32] + d[32:64, 32:64] = a.T @ b            (weight gradient with two
+ *   mode 4: d is (128, 64); d[:32, :16] + d[32:64, 16:32] = a.T @ b[:, :16]     sample groups per MMA) */
 int atmonr_tc_probe(const void* a_f16, const void* b_f16, int mode, float* d, void* stream);
 
 #ifdef __cplusplus

@@ -398,13 +398,13 @@ def test_positional_encoding_and_sample_pdf():
 
 
 # ------------------------------------------------------------------ tensor-core operand layouts
-@pytest.mark.parametrize("mode", [0, 1, 2])
+@pytest.mark.parametrize("mode", [0, 1, 2, 3, 4])
 def test_tcgen05_probe(mode):
     L, ops = _native()
     g = torch.Generator().manual_seed(61 + mode)
     a = torch.randn(128, 32, generator=g).half()
     b = torch.randn(128, 32, generator=g).half()
-    d = torch.full((128, 32), float("nan"), device="cuda")
+    d = torch.full((128, 64 if mode >= 3 else 32), float("nan"), device="cuda")
     ag, bg = a.cuda(), b.cuda()   # keep both alive: a temporary's block would be reused
     L.call("atmonr_tc_probe", L.ptr(ag), L.ptr(bg), mode, L.ptr(d), L.stream())
     torch.cuda.synchronize()
@@ -413,8 +413,14 @@ def test_tcgen05_probe(mode):
         want, got = af @ bf[:32].T, d.cpu()
     elif mode == 1:
         want, got = af @ bf[:32], d.cpu()
-    else:
+    elif mode == 2:
         want, got = af.T @ bf, d.cpu()[:32]
+    elif mode == 3:   # two sample groups per MMA: the gradient is the sum of the diagonal blocks
+        dc = d.cpu()
+        want, got = af.T @ bf, dc[:32, :32] + dc[32:64, 32:64]
+    else:
+        dc = d.cpu()
+        want, got = af.T @ bf[:, :16], dc[:32, :16] + dc[32:64, 16:32]
     assert torch.allclose(got, want, rtol=1e-3, atol=1e-3), float((got - want).abs().max())
 
 
