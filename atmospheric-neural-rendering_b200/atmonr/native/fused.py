@@ -50,6 +50,81 @@ class NGPState:
     ray_index_base: int = 0   # global index of the first ray of this rank's shard
     bins: torch.Tensor | None = None
     last: dict = field(default_factory=dict)
+    pending: list = field(default_factory=list)   # sample points of announced batches (schedule_prefetch)
+    side_stream: torch.cuda.Stream | None = None
+
+
+def _sample_seed(st: NGPState) -> int:
+    """New stratified draws for every sampler invocation (the kernel's generator is counter-based)."""
+    st.step += 1
+    return (st.seed * 0x9E3779B97F4A7C15 + st.step) & 0xFFFFFFFFFFFFFFFF
+
+
+def _rays_f32(origin, direction, length):
+    return origin.contiguous().float(), direction.contiguous().float(), length.contiguous().float()
+
+
+def schedule_prefetch(st: NGPState, origin, direction, length) -> None:
+    """Announce the NEXT batch (call it before the current step's forward is enqueued).
+
+    The sampler depends on the rays only, not on the parameters, and is bound by the FP64 pipe,
+    while the field backward leaves most issue slots idle. So the next batch's
+    sample points are computed on a side stream underneath the current step's backward:
+    this call allocates the outputs and records "rays ready" on the current stream; the kernel
+    itself is launched by `launch_prefetch` right after the field backward has been enqueued
+    (its persistent CTAs are placed first, the sampler's CTAs fill what is left of each SM).
+    """
+    o, d, ln = _rays_f32(origin, direction, length)
+    b, n = o.shape[0], st.n_samples
+    if st.bins is None or st.bins.device != o.device or st.bins.numel() != n:
+        st.bins = ops.linspace_bins(n, o.device)
+    x01 = torch.empty((b * n, 3), device=o.device, dtype=_f32)
+    z = torch.empty((b, n), device=o.device, dtype=_f32)
+    ready = torch.cuda.Event()
+    ready.record()
+    st.pending.append({"key": (origin.data_ptr(), tuple(origin.shape)), "src": origin, "rays": (o, d, ln),
+                       "x01": x01, "z": z, "seed": _sample_seed(st), "ready": ready, "done": None,
+                       "ray_index_base": st.ray_index_base})
+    del st.pending[:-2]  # the batch about to run and the one after it; anything older was never used
+
+
+def launch_prefetch(st: NGPState, on_side_stream: bool = True) -> None:
+    for p in st.pending:
+        if p["done"] is None:
+            _launch_one(st, p, on_side_stream)
+
+
+def _launch_one(st: NGPState, p: dict, on_side_stream: bool) -> None:
+    o, d, ln = p["rays"]
+    cur = torch.cuda.current_stream()
+    if on_side_stream:
+        if st.side_stream is None or st.side_stream.device != o.device:
+            st.side_stream = torch.cuda.Stream(device=o.device)
+        run_on = st.side_stream
+        run_on.wait_event(p["ready"])
+    else:
+        run_on = cur
+    with torch.cuda.stream(run_on):
+        ops.ngp_sample_points(st.frame, o, d, ln, st.n_samples, st.alt_compress, random=True, seed=p["seed"],
+                              ray_index_base=p["ray_index_base"], bins=st.bins, out=(p["x01"], p["z"]))
+        p["done"] = torch.cuda.Event()
+        p["done"].record()
+
+
+def take_prefetched(st: NGPState, origin):
+    """-> (x01, z) of a batch announced with schedule_prefetch, or None."""
+    key = (origin.data_ptr(), tuple(origin.shape))
+    for k, p in enumerate(st.pending):
+        if p["key"] == key:
+            break
+    else:
+        return None
+    if p["done"] is None:            # no backward ran in between (first step, evaluation): sample in line
+        _launch_one(st, p, on_side_stream=False)
+    else:
+        torch.cuda.current_stream().wait_event(p["done"])
+    del st.pending[:k + 1]
+    return p["x01"], p["z"]
 
 
 def field_forward(st: NGPState, table16, pos_w16, dir_w16, x01, dirs, b, n, want_enc=False):
@@ -82,15 +157,16 @@ class NGPRenderFn(torch.autograd.Function):
     @staticmethod
     def forward(ctx, pos_table, pos_w, dir_w, surf_table, surf_w, st: NGPState, shadows, origin, direction, length, u):
         t16, pw16, dw16, s16, sw16 = shadows
-        origin = origin.contiguous().float()
-        direction = direction.contiguous().float()
-        length = length.contiguous().float()
+        pre = take_prefetched(st, origin) if u is None else None
+        origin, direction, length = _rays_f32(origin, direction, length)
         b, n = origin.shape[0], st.n_samples
-        if st.bins is None or st.bins.device != origin.device or st.bins.numel() != n:
-            st.bins = ops.linspace_bins(n, origin.device)
-        seed = (st.seed * 0x9E3779B97F4A7C15 + st.step) & 0xFFFFFFFFFFFFFFFF
-        x01, z = ops.ngp_sample_points(st.frame, origin, direction, length, n, st.alt_compress, u=u, random=True,
-                                       seed=seed, ray_index_base=st.ray_index_base, bins=st.bins)
+        if pre is not None:
+            x01, z = pre
+        else:
+            if st.bins is None or st.bins.device != origin.device or st.bins.numel() != n:
+                st.bins = ops.linspace_bins(n, origin.device)
+            x01, z = ops.ngp_sample_points(st.frame, origin, direction, length, n, st.alt_compress, u=u, random=True,
+                                           seed=_sample_seed(st), ray_index_base=st.ray_index_base, bins=st.bins)
         needs_grad = any(ctx.needs_input_grad[:3])  # (grad mode is off inside Function.forward)
         sigma_raw, color_raw, enc = field_forward(st, t16, pw16, dw16, x01, direction, b, n, want_enc=needs_grad)
         cs_raw = surface_forward(st, s16, sw16, origin, direction, length)
@@ -135,6 +211,7 @@ class NGPRenderFn(torch.autograd.Function):
                    C.byref(st.dir_mlp), L.ptr(dw16), L.ptr(x01), L.ptr(direction), L.ptr(ctx.enc), L.ptr(dsigma),
                    L.ptr(dcolor), L.ptr(absmax), b, n, L.ptr(d_table), L.ptr(d_pw), L.ptr(d_dw), L.stream())
             ctx.enc = None
+        launch_prefetch(st)  # next batch's sample points, underneath the field backward
         L.call("atmonr_ngp_surface_bwd", C.byref(st.grid2), L.ptr(s16), C.byref(st.surf_mlp), L.ptr(sw16),
                L.ptr(origin), L.ptr(direction), L.ptr(length), L.ptr(dcs), b, L.ptr(d_s), L.ptr(d_sw), L.stream())
         return d_table, d_pw, d_dw, d_s, d_sw, None, None, None, None, None, None

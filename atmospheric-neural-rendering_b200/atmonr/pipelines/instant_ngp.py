@@ -99,8 +99,6 @@ class InstantNGPPipeline(Pipeline):
         if self.fused_state is None:
             return self._forward_modular(ray_batch, u)
         st = self.fused_state
-        st.step += 1
-        st.ray_index_base = 0
         shadows = (self.pos_encoder.table_f16(), self.pos_mlp.weights_f16(), self.dir_mlp.weights_f16(),
                    self.surf_encoder.table_f16(), self.surf_mlp.weights_f16())
         cmap, catmo, csurf = fused.NGPRenderFn.apply(
@@ -108,6 +106,15 @@ class InstantNGPPipeline(Pipeline):
             self.surf_mlp.params, st, shadows, ray_batch["origin"], ray_batch["dir"], ray_batch["len"], u)
         return fused.LazyResults(
             {"color_map_fine": cmap, "color_map_atmo": catmo, "color_map_surf": csurf}, st)
+
+    def prefetch(self, ray_batch: Mapping[str, torch.Tensor]) -> None:
+        """Optional: announce the NEXT training batch before running the current step. Its sample
+        points (the parameter-independent, FP64-bound part of forward) are then computed on a side
+        stream underneath the current step's backward (atmonr.native.fused.schedule_prefetch).
+        forward() picks them up when it is given the same `origin` tensor; results are those of
+        an in-line sampler call with the same draw counter."""
+        if self.fused_state is not None and self.training:
+            fused.schedule_prefetch(self.fused_state, ray_batch["origin"], ray_batch["dir"], ray_batch["len"])
 
     def _forward_modular(self, ray_batch, u=None):
         """instant_ngp.py:129-206 operator by operator (non-default configurations)."""

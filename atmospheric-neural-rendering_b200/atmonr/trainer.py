@@ -35,6 +35,20 @@ def _make_writer(log_dir):
         return _NullWriter()
 
 
+def _with_lookahead(loader):
+    """(batch, next batch or None) pairs: the next batch is gathered one step early so that the
+    pipeline can compute its sample points underneath the current step (Pipeline.prefetch)."""
+    it = iter(loader)
+    try:
+        cur = next(it)
+    except StopIteration:
+        return
+    for nxt in it:
+        yield cur, nxt
+        cur = nxt
+    yield cur, None
+
+
 class Trainer:
     def __init__(self, config: dict, dataset, pipeline, exp_name: str) -> None:
         self.config, self.dataset, self.pipeline = config, dataset, pipeline
@@ -81,11 +95,13 @@ class Trainer:
         last_len, running = 0, []
         sched = self.config["scheduler"]
         while self.iter_count < self.config["num_iters"]:
-            for batch in self.dataloader:
+            for batch, upcoming in _with_lookahead(self.dataloader):
                 if prof:
                     prof.step()
                 if not self.config["all_gpu"]:
                     batch = dict_to(batch, self.device)
+                elif upcoming is not None and hasattr(self.pipeline, "prefetch"):
+                    self.pipeline.prefetch(upcoming)
                 results, loss = self.train_step(batch)
                 loss_val = loss.item()
                 self.writer.add_scalar("Loss", loss_val, self.iter_count)

@@ -46,6 +46,8 @@ def parse():
     ap.add_argument("--granule", default="synthetic:H=256,W=256,seed=0")
     ap.add_argument("--cpu-rays", type=int, default=256, help="rays per step of the CPU baseline sample")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-prefetch", action="store_true",
+                    help="sample every batch in line instead of underneath the previous step's backward")
     return ap.parse_args()
 
 
@@ -263,7 +265,13 @@ def run_native(args) -> None:
     host = [{k: v.cpu().pin_memory() for k, v in b.items()} for b in batches]
     h2d_bytes = sum(v.numel() * v.element_size() for v in host[0].values())
 
-    def step(batch):
+    prefetch = not args.no_prefetch
+
+    def step(batch, upcoming=None):
+        # the NEXT batch is announced first: its sample points are computed on a side stream
+        # underneath this step's backward (InstantNGPPipeline.prefetch); one sampler launch per step
+        if prefetch and upcoming is not None:
+            pipe.prefetch(upcoming)
         res = pipe.forward(batch)
         loss = pipe.compute_loss(batch, res)
         opt.zero_grad()
@@ -293,10 +301,11 @@ def run_native(args) -> None:
 
     # ---- settle (allocator pools, lazy module loading: the first ~6 steps of a process run up to
     # 1.6x slower), then the W warm-up steps, then the device-resident measurement ----
+    nb = len(batches)
     for i in range(4):
-        step(batches[i % len(batches)])
+        step(batches[i % nb], batches[(i + 1) % nb])
     for i in range(W):
-        step(batches[i % len(batches)])
+        step(batches[i % nb], batches[(i + 1) % nb])
     clocks = ClockSampler(local)
     if rank == 0:
         clocks.start()
@@ -304,7 +313,7 @@ def run_native(args) -> None:
     profile_range = os.environ.get("ATMONR_CUDA_PROFILER_RANGE") == "1"  # ncu --profile-from-start off
     if profile_range:
         torch.cuda.profiler.start()
-    ms_total = timed(K, lambda i: step(batches[i % len(batches)]))
+    ms_total = timed(K, lambda i: step(batches[i % nb], batches[(i + 1) % nb]))
     if profile_range:
         torch.cuda.profiler.stop()
     launches = L.STATS.launches
@@ -316,7 +325,7 @@ def run_native(args) -> None:
     # ---- per-kernel durations (CUDA events around every C-ABI call, separate pass) ----
     L.STATS = L.CallStats(timed=True)
     for i in range(min(K, 3)):
-        step(batches[i % len(batches)])
+        step(batches[i % nb], batches[(i + 1) % nb])
     dur = L.STATS.durations_ms()
     calls = dict(L.STATS.calls)
     L.STATS = None
@@ -353,13 +362,26 @@ def run_native(args) -> None:
     }
 
     # ---- end to end through the pipeline API with host buffers ----
-    def e2e_step(i):
-        hb = host[i % len(host)]
-        batch = {k: v.to(dev, non_blocking=True) for k, v in hb.items()}
-        return step(batch).item()
+    # Every step copies ONE batch from pinned host memory (the next step's, double-buffered like the
+    # sample points) and reads the loss back.
+    staged = {}
 
-    e2e_step(0)
+    def h2d(i):
+        return {k: v.to(dev, non_blocking=True) for k, v in host[i % len(host)].items()}
+
+    def e2e_step(i):
+        batch = staged.pop(i, None) or h2d(i)
+        if prefetch:
+            staged[i + 1] = h2d(i + 1)
+        return step(batch, staged.get(i + 1)).item()
+
+    e2e_step(-1)
+    staged.clear()
+    staged[0] = h2d(0)
+    if prefetch:
+        pipe.prefetch(staged[0])
     ms_e2e = timed(K, e2e_step) / K
+    staged.clear()
     e2e = {"value": world * B * 1e3 / ms_e2e, "unit": UNIT, "h2d_bytes_per_step": h2d_bytes, "d2h_bytes_per_step": 4,
            "ms_per_step": ms_e2e}
 
