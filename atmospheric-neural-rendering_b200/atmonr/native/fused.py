@@ -29,6 +29,10 @@ _f32 = torch.float32
 # (same arithmetic contract; kept as the cross-check of the tensor-core path).
 FIELD_IMPL = os.environ.get("ATMONR_FIELD_IMPL", "tc")
 # keep the encoded features of the forward pass for the backward pass when they fit in this many bytes
+# how a prefetched batch's sampler is released: "free" = as soon as its rays are ready (it runs
+# underneath whatever the device executes then); "bwd" = together with the field backward, which is
+# moved to a high-priority stream
+PREFETCH_MODE = os.environ.get("ATMONR_PREFETCH_MODE", "free")
 ENC_CACHE_BYTES = int(float(os.environ.get("ATMONR_ENC_CACHE_GB", "40")) * (1 << 30))
 
 
@@ -52,6 +56,7 @@ class NGPState:
     last: dict = field(default_factory=dict)
     pending: list = field(default_factory=list)   # sample points of announced batches (schedule_prefetch)
     side_stream: torch.cuda.Stream | None = None
+    bwd_stream: torch.cuda.Stream | None = None   # high priority: the field backward while a prefetch runs
 
 
 def _sample_seed(st: NGPState) -> int:
@@ -88,13 +93,19 @@ def schedule_prefetch(st: NGPState, origin, direction, length) -> None:
     del st.pending[:-2]  # the batch about to run and the one after it; anything older was never used
 
 
-def launch_prefetch(st: NGPState, on_side_stream: bool = True) -> None:
+def has_unlaunched_prefetch(st: NGPState) -> bool:
+    return any(p["done"] is None for p in st.pending)
+
+
+def launch_prefetch(st: NGPState, after: torch.cuda.Event | None = None) -> None:
+    """Launch the announced batches' samplers on the side stream, not before `after` (the host runs
+    ahead of the device: without it the kernel would start at once, underneath whatever runs then)."""
     for p in st.pending:
         if p["done"] is None:
-            _launch_one(st, p, on_side_stream)
+            _launch_one(st, p, True, after)
 
 
-def _launch_one(st: NGPState, p: dict, on_side_stream: bool) -> None:
+def _launch_one(st: NGPState, p: dict, on_side_stream: bool, after=None) -> None:
     o, d, ln = p["rays"]
     cur = torch.cuda.current_stream()
     if on_side_stream:
@@ -102,6 +113,8 @@ def _launch_one(st: NGPState, p: dict, on_side_stream: bool) -> None:
             st.side_stream = torch.cuda.Stream(device=o.device)
         run_on = st.side_stream
         run_on.wait_event(p["ready"])
+        if after is not None:
+            run_on.wait_event(after)
     else:
         run_on = cur
     with torch.cuda.stream(run_on):
@@ -120,7 +133,7 @@ def take_prefetched(st: NGPState, origin):
     else:
         return None
     if p["done"] is None:            # no backward ran in between (first step, evaluation): sample in line
-        _launch_one(st, p, on_side_stream=False)
+        _launch_one(st, p, False)
     else:
         torch.cuda.current_stream().wait_event(p["done"])
     del st.pending[:k + 1]
@@ -207,11 +220,33 @@ class NGPRenderFn(torch.autograd.Function):
                    C.byref(st.dir_mlp), L.ptr(dw16), L.ptr(x01), L.ptr(direction), L.ptr(dsigma), L.ptr(dcolor), b, n,
                    L.ptr(d_table), L.ptr(d_pw), L.ptr(d_dw), L.stream())
         else:
-            L.call("atmonr_ngp_field_bwd_tc", C.byref(st.grid3), L.ptr(t16), C.byref(st.pos_mlp), L.ptr(pw16),
-                   C.byref(st.dir_mlp), L.ptr(dw16), L.ptr(x01), L.ptr(direction), L.ptr(ctx.enc), L.ptr(dsigma),
-                   L.ptr(dcolor), L.ptr(absmax), b, n, L.ptr(d_table), L.ptr(d_pw), L.ptr(d_dw), L.stream())
+            # With a batch announced (schedule_prefetch) the field backward runs on a high-priority
+            # stream and the next batch's sampler on the (default-priority) side stream, both released
+            # by the same event: the block scheduler places the backward's persistent CTAs first and
+            # fills what is left of each SM (registers for one more CTA) with sampler CTAs.
+            overlap = PREFETCH_MODE == "bwd" and has_unlaunched_prefetch(st)
+            cur = torch.cuda.current_stream()
+            run_on = cur
+            if overlap:
+                if st.bwd_stream is None or st.bwd_stream.device != dev:
+                    st.bwd_stream = torch.cuda.Stream(device=dev, priority=-1)
+                fork = torch.cuda.Event()
+                fork.record()
+                run_on = st.bwd_stream
+                run_on.wait_event(fork)
+            with torch.cuda.stream(run_on):
+                L.call("atmonr_ngp_field_bwd_tc", C.byref(st.grid3), L.ptr(t16), C.byref(st.pos_mlp), L.ptr(pw16),
+                       C.byref(st.dir_mlp), L.ptr(dw16), L.ptr(x01), L.ptr(direction), L.ptr(ctx.enc), L.ptr(dsigma),
+                       L.ptr(dcolor), L.ptr(absmax), b, n, L.ptr(d_table), L.ptr(d_pw), L.ptr(d_dw), L.stream())
+                if overlap:
+                    join = torch.cuda.Event()
+                    join.record()
+            if overlap:
+                launch_prefetch(st, after=fork)
+                cur.wait_event(join)
+            else:
+                launch_prefetch(st)
             ctx.enc = None
-        launch_prefetch(st)  # next batch's sample points, underneath the field backward
         L.call("atmonr_ngp_surface_bwd", C.byref(st.grid2), L.ptr(s16), C.byref(st.surf_mlp), L.ptr(sw16),
                L.ptr(origin), L.ptr(direction), L.ptr(length), L.ptr(dcs), b, L.ptr(d_s), L.ptr(d_sw), L.stream())
         return d_table, d_pw, d_dw, d_s, d_sw, None, None, None, None, None, None

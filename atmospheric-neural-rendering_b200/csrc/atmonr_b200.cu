@@ -54,22 +54,22 @@ __global__ void k_sample_uniform(const float* __restrict__ o, const float* __res
 }
 
 // harp2.py:372-386
-__global__ void k_preprocess_f32(atmonr_frame_t f, const float* __restrict__ p, float* __restrict__ out,
-                                 int64_t n) {
+__global__ void k_preprocess_f32(atmonr_frame_t f, GeoFrame gf, const float* __restrict__ p,
+                                 float* __restrict__ out, int64_t n) {
   const int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
   if (i >= n) return;
   float a, b, c;
-  preprocess_f32(f, p[3 * i], p[3 * i + 1], p[3 * i + 2], a, b, c);
+  preprocess_f32(f, gf, p[3 * i], p[3 * i + 1], p[3 * i + 2], a, b, c);
   out[3 * i] = a;
   out[3 * i + 1] = b;
   out[3 * i + 2] = c;
 }
-__global__ void k_preprocess_f64(atmonr_frame_t f, const double* __restrict__ p, double* __restrict__ out,
-                                 int64_t n) {
+__global__ void k_preprocess_f64(atmonr_frame_t f, GeoFrame gf, const double* __restrict__ p,
+                                 double* __restrict__ out, int64_t n) {
   const int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
   if (i >= n) return;
   double a, b, c;
-  preprocess_f64(f, p[3 * i], p[3 * i + 1], p[3 * i + 2], a, b, c);
+  preprocess_f64(f, gf, p[3 * i], p[3 * i + 1], p[3 * i + 2], a, b, c);
   out[3 * i] = a;
   out[3 * i + 1] = b;
   out[3 * i + 2] = c;
@@ -77,7 +77,8 @@ __global__ void k_preprocess_f64(atmonr_frame_t f, const double* __restrict__ p,
 
 // instant_ngp.py:139-160 in one pass: stratified sample -> ECEF -> geodetic -> [0,1]^3 with
 // compressed altitude. One thread per sample; consecutive threads walk along a ray.
-__global__ void k_ngp_sample_points(atmonr_frame_t f, const float* __restrict__ o,
+// (General form: any N, any pointer alignment. The training path uses k_ngp_sample_points4.)
+__global__ void k_ngp_sample_points(atmonr_frame_t f, GeoFrame gf, const float* __restrict__ o,
                                     const float* __restrict__ d, const float* __restrict__ len,
                                     const float* __restrict__ u, const float* __restrict__ bins,
                                     int64_t total, int N, int mode, uint64_t seed, uint64_t base,
@@ -94,12 +95,62 @@ __global__ void k_ngp_sample_points(atmonr_frame_t f, const float* __restrict__ 
 #pragma unroll
   for (int k = 0; k < 3; ++k) p[k] = o[ray * 3 + k] + d[ray * 3 + k] * zz;
   float c0 = p[0], c1 = p[1], c2 = p[2];
-  if (f.enabled) preprocess_f32(f, p[0], p[1], p[2], c0, c1, c2);
+  if (f.enabled) preprocess_f32(f, gf, p[0], p[1], p[2], c0, c1, c2);
   float x0, x1, x2;
   to_unit_cube(c0, c1, c2, alt_compress, x0, x1, x2);
   x01[idx * 3] = x0;
   x01[idx * 3 + 1] = x1;
   x01[idx * 3 + 2] = x2;
+}
+
+// Same arithmetic, one thread per aligned group of FOUR consecutive bins of a ray (N % 4 == 0,
+// 16-byte aligned buffers): one Philox block, one index division and one load of the ray per
+// four samples, 16-byte loads/stores, and four independent FP64 chains per thread to hide the
+// latency of the FP64 pipe. The kernel is bound by FP64 issue, not by its 16 B/sample of HBM writes.
+__global__ void __launch_bounds__(128)
+k_ngp_sample_points4(atmonr_frame_t f, GeoFrame gf, const float* __restrict__ o, const float* __restrict__ d,
+                     const float* __restrict__ len, const float* __restrict__ u, const float* __restrict__ bins,
+                     int64_t groups, int N4, int mode, uint64_t seed, uint64_t base, float alt_compress,
+                     float* __restrict__ x01, float* __restrict__ z) {
+  const int64_t q = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+  if (q >= groups) return;
+  int64_t ray;
+  if (groups <= 0xffffffffll) ray = (int64_t)((uint32_t)q / (uint32_t)N4);
+  else ray = q / N4;
+  const int g4 = (int)(q - ray * N4);
+  const int N = N4 * 4, i0 = g4 * 4;
+  float t[4] = {0.5f, 0.5f, 0.5f, 0.5f};
+  if (mode == 1) {
+    const float4 uu = reinterpret_cast<const float4*>(u)[q];
+    t[0] = uu.x, t[1] = uu.y, t[2] = uu.z, t[3] = uu.w;
+  } else if (mode == 2) {
+    philox_uniform4(seed, base + (uint64_t)ray, (uint32_t)g4, t);
+  }
+  float lo[4];
+  if (bins) {
+    const float4 bb = reinterpret_cast<const float4*>(bins)[g4];
+    lo[0] = bb.x, lo[1] = bb.y, lo[2] = bb.z, lo[3] = bb.w;
+  } else {
+#pragma unroll
+    for (int k = 0; k < 4; ++k) lo[k] = (float)(i0 + k) / (float)N;
+  }
+  const float ln = len[ray];
+  const float ox = o[ray * 3], oy = o[ray * 3 + 1], oz = o[ray * 3 + 2];
+  const float dx = d[ray * 3], dy = d[ray * 3 + 1], dz = d[ray * 3 + 2];
+  float zz[4], out[12];
+#pragma unroll
+  for (int k = 0; k < 4; ++k) {
+    zz[k] = stratified_z(lo[k], t[k], N, ln);
+    const float px = ox + dx * zz[k], py = oy + dy * zz[k], pz = oz + dz * zz[k];
+    float c0 = px, c1 = py, c2 = pz;
+    if (f.enabled) preprocess_f32(f, gf, px, py, pz, c0, c1, c2);
+    to_unit_cube(c0, c1, c2, alt_compress, out[3 * k], out[3 * k + 1], out[3 * k + 2]);
+  }
+  reinterpret_cast<float4*>(z)[q] = make_float4(zz[0], zz[1], zz[2], zz[3]);
+  float4* xo = reinterpret_cast<float4*>(x01) + 3 * q;
+  xo[0] = make_float4(out[0], out[1], out[2], out[3]);
+  xo[1] = make_float4(out[4], out[5], out[6], out[7]);
+  xo[2] = make_float4(out[8], out[9], out[10], out[11]);
 }
 
 // =========================================================================================
@@ -722,7 +773,7 @@ k_adamw(float* __restrict__ p, float* __restrict__ g, float* __restrict__ m, flo
 // Extraction: float64 point -> preprocess -> hash -> pos_mlp -> max(sigma, 0)
 // =========================================================================================
 __global__ void __launch_bounds__(kTile)
-k_extract_sigma(atmonr_frame_t f, atmonr_grid_t g, const __half2* __restrict__ table,
+k_extract_sigma(atmonr_frame_t f, GeoFrame gf, atmonr_grid_t g, const __half2* __restrict__ table,
                 const __half* __restrict__ pos_w, const double* __restrict__ pts, int64_t n,
                 float alt_compress, float* __restrict__ sigma) {
   __shared__ __align__(16) float sW[PosMlp::kNumWeights];
@@ -732,7 +783,7 @@ k_extract_sigma(atmonr_frame_t f, atmonr_grid_t g, const __half2* __restrict__ t
     const int64_t i = tile * kTile + threadIdx.x;
     if (i >= n) continue;
     double c0 = pts[3 * i], c1 = pts[3 * i + 1], c2 = pts[3 * i + 2];
-    if (f.enabled) preprocess_f64(f, c0, c1, c2, c0, c1, c2);
+    if (f.enabled) preprocess_f64(f, gf, c0, c1, c2, c0, c1, c2);
     // instant_ngp.py:224-233 stay in float64; tcnn casts its input to float32
     const float p[3] = {(float)((c0 + 1.0) / 2.0), (float)((c1 + 1.0) / 2.0),
                         (float)(((c2 + 1.0) / 2.0) / (double)alt_compress)};
@@ -956,10 +1007,11 @@ int atmonr_preprocess_horizontal(const atmonr_frame_t* f, const void* pts, void*
                                  void* stream) {
   ATM_REQUIRE(f && f->enabled, "atmonr_preprocess_horizontal", "frame missing or disabled");
   if (n == 0) return 0;
+  const GeoFrame gf = make_geo_frame(*f);
   if (is_f64)
-    k_preprocess_f64<<<grid_for(n, 256), 256, 0, S(stream)>>>(*f, (const double*)pts, (double*)out, n);
+    k_preprocess_f64<<<grid_for(n, 256), 256, 0, S(stream)>>>(*f, gf, (const double*)pts, (double*)out, n);
   else
-    k_preprocess_f32<<<grid_for(n, 256), 256, 0, S(stream)>>>(*f, (const float*)pts, (float*)out, n);
+    k_preprocess_f32<<<grid_for(n, 256), 256, 0, S(stream)>>>(*f, gf, (const float*)pts, (float*)out, n);
   ATM_CHECK_LAUNCH("atmonr_preprocess_horizontal");
   return 0;
 }
@@ -970,8 +1022,14 @@ int atmonr_ngp_sample_points(const atmonr_frame_t* f, const float* origin, const
   ATM_REQUIRE(f, "atmonr_ngp_sample_points", "null frame");
   ATM_REQUIRE(mode >= 0 && mode <= 2 && (mode != 1 || u), "atmonr_ngp_sample_points", "bad mode / missing u");
   if (B * N == 0) return 0;
-  k_ngp_sample_points<<<grid_for(B * N, 256), 256, 0, S(stream)>>>(*f, origin, dir, len, u, bins, B * N, N, mode,
-                                                                  seed, ray_index_base, alt_compress, x01, z);
+  const GeoFrame gf = make_geo_frame(*f);
+  auto aligned16 = [](const void* p) { return (reinterpret_cast<uintptr_t>(p) & 15u) == 0; };
+  if (N % 4 == 0 && aligned16(x01) && aligned16(z) && aligned16(u) && aligned16(bins) && B * (int64_t)(N / 4) < (1ll << 37))
+    k_ngp_sample_points4<<<grid_for(B * (N / 4), 128), 128, 0, S(stream)>>>(
+        *f, gf, origin, dir, len, u, bins, B * (N / 4), N / 4, mode, seed, ray_index_base, alt_compress, x01, z);
+  else
+    k_ngp_sample_points<<<grid_for(B * N, 256), 256, 0, S(stream)>>>(*f, gf, origin, dir, len, u, bins, B * N, N, mode,
+                                                                    seed, ray_index_base, alt_compress, x01, z);
   ATM_CHECK_LAUNCH("atmonr_ngp_sample_points");
   return 0;
 }
@@ -1199,7 +1257,7 @@ int atmonr_extract_sigma(const atmonr_frame_t* f, const atmonr_grid_t* g, const 
   ATM_REQUIRE(is_shape(pm, 32, 1) && pm->n_in == 32, "atmonr_extract_sigma", "pos_mlp must be 32 -> [32] -> 16");
   if (n == 0) return 0;
   const int grid = grid_for((n + kTile - 1) / kTile, 1, num_sms() * 16);
-  k_extract_sigma<<<grid, kTile, 0, S(stream)>>>(*f, *g, (const __half2*)table, (const __half*)pos_w, pts, n,
+  k_extract_sigma<<<grid, kTile, 0, S(stream)>>>(*f, make_geo_frame(*f), *g, (const __half2*)table, (const __half*)pos_w, pts, n,
                                                 alt_compress, sigma);
   ATM_CHECK_LAUNCH("atmonr_extract_sigma");
   return 0;

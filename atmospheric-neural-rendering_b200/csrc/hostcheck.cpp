@@ -29,18 +29,21 @@ static void indices_impl(const atmonr_grid_t* g, const float* x, int xs, int64_t
 extern "C" {
 
 void hc_preprocess_f32(const atmonr_frame_t* f, const float* p, float* out, int64_t n) {
+  const atm::GeoFrame gf = atm::make_geo_frame(*f);
   for (int64_t i = 0; i < n; ++i)
-    atm::preprocess_f32(*f, p[3 * i], p[3 * i + 1], p[3 * i + 2], out[3 * i], out[3 * i + 1], out[3 * i + 2]);
+    atm::preprocess_f32(*f, gf, p[3 * i], p[3 * i + 1], p[3 * i + 2], out[3 * i], out[3 * i + 1], out[3 * i + 2]);
 }
 
 void hc_preprocess_f64(const atmonr_frame_t* f, const double* p, double* out, int64_t n) {
+  const atm::GeoFrame gf = atm::make_geo_frame(*f);
   for (int64_t i = 0; i < n; ++i)
-    atm::preprocess_f64(*f, p[3 * i], p[3 * i + 1], p[3 * i + 2], out[3 * i], out[3 * i + 1], out[3 * i + 2]);
+    atm::preprocess_f64(*f, gf, p[3 * i], p[3 * i + 1], p[3 * i + 2], out[3 * i], out[3 * i + 1], out[3 * i + 2]);
 }
 
 void hc_ngp_sample_points(const atmonr_frame_t* f, const float* o, const float* d, const float* len,
                           const float* u, const float* bins, int64_t B, int N, int mode, uint64_t seed,
                           uint64_t base, float alt_compress, float* x01, float* z) {
+  const atm::GeoFrame gf = atm::make_geo_frame(*f);
   for (int64_t ray = 0; ray < B; ++ray)
     for (int i = 0; i < N; ++i) {
       const int64_t idx = ray * N + i;
@@ -51,7 +54,7 @@ void hc_ngp_sample_points(const atmonr_frame_t* f, const float* o, const float* 
       float p[3];
       for (int k = 0; k < 3; ++k) p[k] = o[ray * 3 + k] + d[ray * 3 + k] * zz;
       float c0 = p[0], c1 = p[1], c2 = p[2];
-      if (f->enabled) atm::preprocess_f32(*f, p[0], p[1], p[2], c0, c1, c2);
+      if (f->enabled) atm::preprocess_f32(*f, gf, p[0], p[1], p[2], c0, c1, c2);
       atm::to_unit_cube(c0, c1, c2, alt_compress, x01[idx * 3], x01[idx * 3 + 1], x01[idx * 3 + 2]);
     }
 }

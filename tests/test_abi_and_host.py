@@ -109,6 +109,41 @@ def test_host_build_of_kernel_math_matches_oracle():
     assert np.abs(out64 - want64).max() < 1e-11
 
 
+@pytest.mark.parametrize("lat0,lon0,dlat,dlon,shift", [
+    (32.5, -72.5, 5, 5, False),     # the bench granule
+    (-60.0, 179.5, 4, 6, True),     # across the dateline (harp2.py:366-370)
+    (75.0, 100.0, 8, 19, False),    # wide swath at high latitude: partly outside the small-angle window
+    (10.0, -120.0, 30, 40, False),  # mostly outside it: literal atan2 form
+])
+def test_local_angle_geodesy_matches_literal_form(lat0, lon0, dlat, dlon, shift):
+    """device_math.cuh:ecef_to_geodetic_local (angles relative to the granule centre, asin series,
+    reciprocals) against the oracle's literal cartesian_to_horizontal, float64 and float32."""
+    n = 20000
+    g = torch.Generator().manual_seed(3)
+    lat = lat0 + (torch.rand(n, generator=g, dtype=torch.float64) - 0.5) * dlat
+    lon = (lon0 + (torch.rand(n, generator=g, dtype=torch.float64) - 0.5) * dlon + 180) % 360 - 180
+    alt = torch.rand(n, generator=g, dtype=torch.float64) * 20000
+    xyz = torch.stack(geodesy.geodetic_to_ecef(lat, lon, alt), -1)
+    offset = xyz.mean(0)
+    scale = float((xyz - offset).abs().max())
+    pn = (xyz - offset) / scale
+    lon_s = lon % 360 - 180 if shift else lon
+    fr = geodesy.HorizontalFrame(scale=scale, offset=tuple(offset.tolist()), lat_min=float(lat.min()),
+                                 lat_range=float(lat.max() - lat.min()), lon_min=float(lon_s.min()),
+                                 lon_range=float(lon_s.max() - lon_s.min()), origin_height=20000.0, shift_lon=shift)
+    hc, frs = _hc(), _frame_struct(fr)
+    p64 = pn.numpy().copy()
+    out64 = np.zeros_like(p64)
+    hc.hc_preprocess_f64(C.byref(frs), _p(p64), _p(out64), C.c_int64(n))
+    want64 = geodesy.preprocess_horizontal(pn[None], fr)[0].numpy()
+    assert np.abs(out64 - want64).max() < 1e-11
+    p32 = pn.float().numpy().copy()
+    out32 = np.zeros_like(p32)
+    hc.hc_preprocess_f32(C.byref(frs), _p(p32), _p(out32), C.c_int64(n))
+    want32 = geodesy.preprocess_horizontal(pn.float()[None], fr)[0].numpy()
+    assert np.abs(out32 - want32).max() < 1.5e-7 and (out32 != want32).mean() < 1e-3
+
+
 @pytest.mark.parametrize("dims,key", [(3, "encoding"), (2, "surface_encoding"), (4, "encoding")])
 def test_host_build_of_hash_indexing_is_bit_exact(dims, key):
     from atmonr.native import lib as L
