@@ -472,6 +472,45 @@ __device__ __forceinline__ float voronoi_delta(const float* __restrict__ zr, int
   return hi - lo;
 }
 
+// Raw inputs of one sample. The compositing kernels walk a ray 32 samples at a time with a serial
+// dependence (the scan carry), so the loads of the following chunks are issued two chunks ahead
+// (register prefetch): the kernels are bound by HBM latency x bytes in flight otherwise.
+template <int K, int V>
+struct RawSample {
+  float zm, zi, zp;  // z[i-1], z[i], z[i+1] (normalised)
+  float c[K];
+  float s[V];
+};
+
+template <int K, int V>
+__device__ __forceinline__ RawSample<K, V> load_raw(const float* __restrict__ zr, const float* __restrict__ color,
+                                                    const float* __restrict__ sigma, int64_t row0, int i, int N) {
+  RawSample<K, V> r;
+  const bool in = i < N;
+  r.zi = in ? zr[i] : 0.0f;
+  r.zm = (in && i > 0) ? zr[i - 1] : 0.0f;
+  r.zp = (in && i < N - 1) ? zr[i + 1] : 0.0f;
+  if (K == 4) {
+    const float4 cc = in ? *reinterpret_cast<const float4*>(color + (row0 + i) * 4) : make_float4(0.f, 0.f, 0.f, 0.f);
+    r.c[0] = cc.x, r.c[1 % K] = cc.y, r.c[2 % K] = cc.z, r.c[3 % K] = cc.w;
+  } else {
+#pragma unroll
+    for (int k = 0; k < K; ++k) r.c[k] = in ? color[(row0 + i) * K + k] : 0.0f;
+  }
+#pragma unroll
+  for (int v = 0; v < V; ++v) r.s[v] = in ? sigma[(row0 + i) * V + v] : 0.0f;
+  return r;
+}
+
+// same arithmetic as voronoi_delta, from prefetched neighbours
+template <int K, int V>
+__device__ __forceinline__ float raw_delta(const RawSample<K, V>& r, int i, int N, float zs) {
+  const float zi = r.zi * zs;
+  const float lo = i == 0 ? zi * 0.0f : (r.zm * zs + zi) / 2.0f;
+  const float hi = i == N - 1 ? zi : (zi + r.zp * zs) / 2.0f;
+  return hi - lo;
+}
+
 template <int K, int V>
 __global__ void __launch_bounds__(128)
 k_composite_fwd(const float* __restrict__ z, const float* __restrict__ color, const float* __restrict__ sigma,
@@ -487,19 +526,24 @@ k_composite_fwd(const float* __restrict__ z, const float* __restrict__ color, co
   for (int v = 0; v < V; ++v) carry[v] = 1.0f, surf[v] = 1.0f;
 #pragma unroll
   for (int k = 0; k < K; ++k) acc[k] = 0.0f;
+  RawSample<K, V> r0 = load_raw<K, V>(zr, color, sigma, ray * N, lane, N);
+  RawSample<K, V> r1 = load_raw<K, V>(zr, color, sigma, ray * N, 32 + lane, N);
   for (int base = 0; base < N; base += 32) {
     const int i = base + lane;
     const bool in = i < N;
-    const float delta = in ? voronoi_delta(zr, i, N, zs) : 0.0f;
+    const RawSample<K, V> r2 = load_raw<K, V>(zr, color, sigma, ray * N, i + 64, N);
+    const float delta = in ? raw_delta(r0, i, N, zs) : 0.0f;
     float c[K];
 #pragma unroll
-    for (int k = 0; k < K; ++k) {
-      const float raw = in ? color[(ray * N + i) * K + k] : 0.0f;
-      c[k] = relu ? fmaxf(raw, 0.0f) : raw;
-    }
+    for (int k = 0; k < K; ++k) c[k] = relu ? fmaxf(r0.c[k], 0.0f) : r0.c[k];
+    float sraw[V];
+#pragma unroll
+    for (int v = 0; v < V; ++v) sraw[v] = r0.s[v];
+    r0 = r1;
+    r1 = r2;
 #pragma unroll
     for (int v = 0; v < V; ++v) {
-      const float raw = in ? sigma[(ray * N + i) * V + v] : 0.0f;
+      const float raw = sraw[v];
       const float s = relu ? fmaxf(raw, 0.0f) : raw;
       const float a = 1.0f - expf(-s * delta);
       const float t = in ? (1.0f - a) + 1e-10f : 1.0f;
@@ -584,23 +628,30 @@ k_composite_bwd(const float* __restrict__ z, const float* __restrict__ color, co
     }
   }
   float amax = 0.0f;  // largest |gradient| written by this lane (for the fp16 scale of field_bwd_tc)
+  RawSample<K, V> r0 = load_raw<K, V>(zr, color, sigma, ray * N, lane, N);
+  RawSample<K, V> r1 = load_raw<K, V>(zr, color, sigma, ray * N, 32 + lane, N);
   for (int base = 0; base < N; base += 32) {
     const int i = base + lane;
     const bool in = i < N;
-    const float delta = in ? voronoi_delta(zr, i, N, zs) : 0.0f;
-    float c[K], craw[K];
+    const RawSample<K, V> r2 = load_raw<K, V>(zr, color, sigma, ray * N, i + 64, N);
+    const float delta = in ? raw_delta(r0, i, N, zs) : 0.0f;
+    float c[K], craw[K], sraw[V];
 #pragma unroll
     for (int k = 0; k < K; ++k) {
-      craw[k] = in ? color[(ray * N + i) * K + k] : 0.0f;
+      craw[k] = r0.c[k];
       c[k] = relu ? fmaxf(craw[k], 0.0f) : craw[k];
     }
+#pragma unroll
+    for (int v = 0; v < V; ++v) sraw[v] = r0.s[v];
+    r0 = r1;
+    r1 = r2;
     float dc[K];
     float dd = 0.0f;  // dL/d(delta_i), summed over density channels
 #pragma unroll
     for (int k = 0; k < K; ++k) dc[k] = 0.0f;
 #pragma unroll
     for (int v = 0; v < V; ++v) {
-      const float raw = in ? sigma[(ray * N + i) * V + v] : 0.0f;
+      const float raw = sraw[v];
       const float s = relu ? fmaxf(raw, 0.0f) : raw;
       const float e = expf(-s * delta);
       const float a = 1.0f - e;
@@ -630,11 +681,17 @@ k_composite_bwd(const float* __restrict__ z, const float* __restrict__ color, co
     }
     if (in && ddelta) ddelta[ray * N + i] = dd;
     if (in) {
+      float dk[K];
 #pragma unroll
       for (int k = 0; k < K; ++k) {
-        const float d = (relu && !(craw[k] > 0.0f)) ? 0.0f : dc[k];
-        dcolor[(ray * N + i) * K + k] = d;
-        amax = fmaxf(amax, fabsf(d));
+        dk[k] = (relu && !(craw[k] > 0.0f)) ? 0.0f : dc[k];
+        amax = fmaxf(amax, fabsf(dk[k]));
+      }
+      if (K == 4) {
+        *reinterpret_cast<float4*>(dcolor + (ray * N + i) * 4) = make_float4(dk[0], dk[1 % K], dk[2 % K], dk[3 % K]);
+      } else {
+#pragma unroll
+        for (int k = 0; k < K; ++k) dcolor[(ray * N + i) * K + k] = dk[k];
       }
     }
   }
@@ -1185,6 +1242,7 @@ int atmonr_composite_fwd(const float* z, const float* color, const float* sigma,
                          float* alpha, void* stream) {
   if (B == 0) return 0;
   ATM_REQUIRE(color_map, "atmonr_composite_fwd", "null color_map");
+  ATM_REQUIRE(K != 4 || (reinterpret_cast<uintptr_t>(color) & 15u) == 0, "atmonr_composite_fwd", "color must be 16-byte aligned");
   const int grid = grid_for(B * 32, 128);
 #define CALL(KK, VV)                                                                                      \
   k_composite_fwd<KK, VV><<<grid, 128, 0, S(stream)>>>(z, color, sigma, color_surf, z_scale, B, N, relu,   \
@@ -1204,6 +1262,8 @@ int atmonr_composite_bwd(const float* z, const float* color, const float* sigma,
   if (B == 0) return 0;
   ATM_REQUIRE(color_map_atmo && d_atmo && dcolor && dsigma, "atmonr_composite_bwd", "null argument");
   ATM_REQUIRE(!color_surf || trans_surf, "atmonr_composite_bwd", "trans_surf required with a surface");
+  ATM_REQUIRE(K != 4 || ((reinterpret_cast<uintptr_t>(color) | reinterpret_cast<uintptr_t>(dcolor)) & 15u) == 0,
+              "atmonr_composite_bwd", "color and dcolor must be 16-byte aligned");
   const int grid = grid_for(B * 32, 128);
 #define CALL(KK, VV)                                                                                         \
   k_composite_bwd<KK, VV><<<grid, 128, 0, S(stream)>>>(z, color, sigma, color_surf, color_map_atmo, trans_surf, \

@@ -10,7 +10,20 @@
 
 namespace atm {
 
-// Encode one point: out[2*l], out[2*l+1] = fp16-rounded interpolated features of level l.
+// N-linear interpolation of one level, tiny-cuda-nn's arithmetic (grid.h kernel_grid,
+// upstream-recalled; SURVEY 8c "tcnn accumulates in fp16"): the fp32 corner weight is rounded to
+// fp16 and the two features of the entry are accumulated with ONE packed half-precision FMA per
+// corner, corners in index order (bit k of the corner id = +1 in dimension k), starting from 0.
+// (Also the cheapest form: 2 instructions per corner instead of 2 converts + 2 FFMA.)
+template <int NC>
+__device__ __forceinline__ __half2 interp_corners(const __half2 (&v)[NC], const float (&w)[NC]) {
+  __half2 acc = __floats2half2_rn(0.0f, 0.0f);
+#pragma unroll
+  for (int c = 0; c < NC; ++c) acc = __hfma2(__float2half2_rn(w[c]), v[c], acc);
+  return acc;
+}
+
+// Encode one point: out[l] = the two interpolated fp16 features of level l.
 template <int D>
 __device__ __forceinline__ void hash_encode(const atmonr_grid_t& g, const __half2* __restrict__ table,
                                             const float (&x)[D], __half2 (&out)[ATMONR_MAX_LEVELS]) {
@@ -29,14 +42,7 @@ __device__ __forceinline__ void hash_encode(const atmonr_grid_t& g, const __half
         grid_corner<D>(cell, frac, c, g.res[l], g.size[l], e, w[c]);
         v[c] = __ldg(lvl + e);
       }
-      float a0 = 0.0f, a1 = 0.0f;
-#pragma unroll
-      for (int c = 0; c < (1 << D); ++c) {
-        const float2 f = __half22float2(v[c]);
-        a0 = fmaf(w[c], f.x, a0);
-        a1 = fmaf(w[c], f.y, a1);
-      }
-      out[l] = __floats2half2_rn(a0, a1);
+      out[l] = interp_corners<(1 << D)>(v, w);
     } else {
       out[l] = __floats2half2_rn(0.0f, 0.0f);
     }
@@ -116,14 +122,7 @@ __device__ __forceinline__ void hash_encode_fast(const atmonr_grid_t& g, const _
       __half2 v[1 << D];
 #pragma unroll
       for (int c = 0; c < (1 << D); ++c) v[c] = __ldg(lvl + e[c]);
-      float a0 = 0.0f, a1 = 0.0f;
-#pragma unroll
-      for (int c = 0; c < (1 << D); ++c) {
-        const float2 f = __half22float2(v[c]);
-        a0 = fmaf(w[c], f.x, a0);
-        a1 = fmaf(w[c], f.y, a1);
-      }
-      out[l] = __floats2half2_rn(a0, a1);
+      out[l] = interp_corners<(1 << D)>(v, w);
     } else {
       out[l] = __floats2half2_rn(0.0f, 0.0f);
     }

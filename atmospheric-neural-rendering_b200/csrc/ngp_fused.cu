@@ -248,14 +248,11 @@ __device__ __forceinline__ void level_issue(const LevelRow& L, const __half2* __
 __device__ __forceinline__ uint32_t level_finish(const uint32_t (&v)[8], const float (&frac)[3]) {
   float w[8];
   corner_weights3(frac, w);
-  float a0 = 0.0f, a1 = 0.0f;
+  __half2 h[8];
 #pragma unroll
-  for (int c = 0; c < 8; ++c) {
-    const float2 f = __half22float2(*reinterpret_cast<const __half2*>(&v[c]));
-    a0 = fmaf(w[c], f.x, a0);
-    a1 = fmaf(w[c], f.y, a1);
-  }
-  return pack_h2_act<false>(a0, a1);
+  for (int c = 0; c < 8; ++c) h[c] = *reinterpret_cast<const __half2*>(&v[c]);
+  const __half2 acc = interp_corners<8>(h, w);
+  return *reinterpret_cast<const uint32_t*>(&acc);
 }
 __device__ __forceinline__ void encode_to_tile(const LevelRow* __restrict__ lv, const __half2* __restrict__ table,
                                                const float (&p)[3], uint8_t* tile, int r, uint64_t keep) {

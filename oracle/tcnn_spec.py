@@ -12,7 +12,9 @@ src/atmonr/pipelines/instant_ngp.py:60-85 (construction), :163-174 (training for
 Two numeric modes:
   * ``fp16=False``: everything in float32 -- the ground truth of the tolerance tests.
   * ``fp16=True`` : emulates the rounding points of the native sm_100a path (table entries,
-    MLP weights, encoder outputs and hidden activations rounded to fp16; fp32 accumulate),
+    MLP weights, encoder outputs and hidden activations rounded to fp16; fp32 accumulate in the
+    MLPs; the hash-grid interpolation accumulates in fp16 with one fused multiply-add per corner,
+    as tiny-cuda-nn does),
     with straight-through gradients, so the CUDA kernels can be checked tightly.
 """
 
@@ -138,9 +140,22 @@ class HashGrid:
             acc = torch.zeros(x01.shape[0], self.n_feat, dtype=torch.float32)
             for c in range(idx.shape[1]):
                 acc = acc + w[:, c, None] * tab[base + idx[:, c]]
+            if fp16:
+                # [upstream-recalled] tcnn grid.h: result = fma((half)weight, entry, result), all in
+                # fp16, corners in index order. One rounding per corner: the product of two fp16
+                # values and its sum with an fp16 accumulator are exact in float64.
+                # (numpy rounds float64 -> float16 once; torch goes through float32, a double rounding)
+                chain = np.zeros((x01.shape[0], self.n_feat), np.float16)
+                with torch.no_grad():
+                    w16 = w.numpy().astype(np.float16).astype(np.float64)
+                    t64 = tab.detach().numpy().astype(np.float64)
+                    for c in range(idx.shape[1]):
+                        prod = w16[:, c, None] * t64[base + idx[:, c].numpy()]
+                        chain = (chain.astype(np.float64) + prod).astype(np.float16)
+                chain = torch.from_numpy(chain.astype(np.float32))
+                acc = chain + (acc - acc.detach())   # value: the fp16 chain, exactly; gradient: straight through
             outs.append(acc)
-        out = torch.cat(outs, dim=1)
-        return _ste_half(out) if fp16 else out
+        return torch.cat(outs, dim=1)
 
     def all_indices(self, x01):
         """Global entry index of every (sample, level, corner): (M, L, 2^D) int64."""

@@ -110,8 +110,8 @@ def test_hashgrid_indices_bit_exact_and_features(dims, key):
     want = grid_o.forward(x, params, fp16=True)
     p = params.cuda().requires_grad_()
     got = ops.HashGridFn.apply(x.cuda(), p, p.detach().half(), grid)
-    # interpolation is fp32 FMA on fp16 table values, result rounded to fp16: allow one fp16 ulp
-    assert torch.allclose(got.cpu(), want, rtol=1e-3, atol=1e-6)
+    # interpolation = one fp16 FMA per corner in corner order (tcnn's arithmetic): reproduced exactly
+    assert torch.equal(got.cpu(), want)
     want32 = grid_o.forward(x, params, fp16=False)
     assert rel_err(got, want32) < 2e-3
     # backward: gradient of sum(out * r) w.r.t. the table
@@ -289,7 +289,9 @@ def test_ngp_pipeline_forward_loss_gradients_vs_oracle(scene, impl, monkeypatch)
     # modular (operator-by-operator) path agrees with the fused path
     pipe.fused_state = None
     out_m = pipe.forward(bc, u=u.cuda())
-    assert rel_err(out_m["color_map_fine"], out["color_map_fine"]) < 1e-5
+    # (same encodings bit for bit; the dense layers accumulate in a different order, which can flip the
+    # fp16 rounding of a hidden activation)
+    assert rel_err(out_m["color_map_fine"], out["color_map_fine"]) < 1e-4
 
 
 @pytest.mark.parametrize("height,multi_band", [(True, False), (False, True), (True, True)])
