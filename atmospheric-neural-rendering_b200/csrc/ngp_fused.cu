@@ -864,6 +864,20 @@ k_field_bwd_tc2(atmonr_grid_t g, const __half* __restrict__ pos_w, const __half*
   uint8_t* H2 = smem + bwd2::kH2;
   uint8_t* DO = smem + bwd2::kDO;
   uint32_t phase = 0, phase2 = 0, seen_tile = 0;
+  // This thread's inputs of the NEXT tile (encoded features, position) are loaded into registers
+  // before the scatter phase of the current tile, so a tile never starts with an exposed global
+  // load (that wait was 15 % of the epilogue warps' time).
+  uint4 nx[4];
+  float npos[3];
+  auto fetch_inputs = [&](int64_t t) {
+    const int64_t ii = t * bwd2::kRows + tid;
+    const int64_t jj = ii < M ? ii : M - 1;
+    const uint4* src = reinterpret_cast<const uint4*>(enc_in + jj * 32);
+#pragma unroll
+    for (int cc = 0; cc < 4; ++cc) nx[cc] = __ldg(src + cc);
+    npos[0] = __ldg(x01 + 3 * jj), npos[1] = __ldg(x01 + 3 * jj + 1), npos[2] = __ldg(x01 + 3 * jj + 2);
+  };
+  if (cta_has_work) fetch_inputs(blockIdx.x);
 
   for (int64_t tile = blockIdx.x; tile * bwd2::kRows < M; tile += gridDim.x, seen_tile = 1) {
     const int64_t i = tile * bwd2::kRows + tid;
@@ -871,18 +885,21 @@ k_field_bwd_tc2(atmonr_grid_t g, const __half* __restrict__ pos_w, const __half*
     const int64_t j = valid ? i : M - 1;
     if (seen_tile) mbar_wait(bar2, phase2), phase2 ^= 1;
     const uint4* enc_row = reinterpret_cast<const uint4*>(enc_in + j * 32);
-    // this row's position: needed only by the scatter at the end of the tile; fetched now so the
-    // global-load latency hides behind the whole MLP phase (row index skewed by row/16 so that the
-    // scatter's 16-rows-apart reads hit distinct banks)
+    // ---------------- recompute the activations ----------------
+#pragma unroll
+    for (int cc = 0; cc < 4; ++cc) st_chunk(X, tid, cc, 32, nx[cc]);
+    stage_arrive();
+    // this row's position: needed only by the scatter at the end of the tile (row index skewed by
+    // row/16 so that the scatter's 16-rows-apart reads hit distinct banks)
     {
       float* pos = reinterpret_cast<float*>(smem + bwd2::kPos);
       const int at = tid + (tid >> 4);
-      pos[at] = x01[3 * j], pos[272 + at] = x01[3 * j + 1], pos[544 + at] = x01[3 * j + 2];
+      pos[at] = npos[0], pos[272 + at] = npos[1], pos[544 + at] = npos[2];
     }
-    // ---------------- recompute the activations ----------------
-#pragma unroll
-    for (int cc = 0; cc < 4; ++cc) st_chunk(X, tid, cc, 32, enc_row[cc]);
-    stage_arrive();
+    // incoming gradients of this row: needed at stages S0 / S3, requested now
+    float4 dc_in = make_float4(0.0f, 0.0f, 0.0f, 0.0f);
+    float ds_in = 0.0f;
+    if (valid) dc_in = __ldg(reinterpret_cast<const float4*>(dcolor_raw + 4 * i)), ds_in = __ldg(dsigma_raw + i);
     mbar_wait(bar, phase), phase ^= 1;
     tc_fence_after();
     float v[32];
@@ -912,10 +929,7 @@ k_field_bwd_tc2(atmonr_grid_t g, const __half* __restrict__ pos_w, const __half*
       float dout[16];
 #pragma unroll
       for (int k = 0; k < 16; ++k) dout[k] = 0.0f;
-      if (valid) {
-        const float4 dc = *reinterpret_cast<const float4*>(dcolor_raw + 4 * i);
-        dout[0] = dc.x * S, dout[1] = dc.y * S, dout[2] = dc.z * S, dout[3] = dc.w * S;
-      }
+      dout[0] = dc_in.x * S, dout[1] = dc_in.y * S, dout[2] = dc_in.z * S, dout[3] = dc_in.w * S;
       store_row16(DO, tid, dout);
     }
     stage_arrive();  // S0
@@ -934,7 +948,7 @@ k_field_bwd_tc2(atmonr_grid_t g, const __half* __restrict__ pos_w, const __half*
     tmem_ld32(my32, v);
     {
       float dpo[16];
-      dpo[0] = valid ? dsigma_raw[i] * S : 0.0f;
+      dpo[0] = ds_in * S;
 #pragma unroll
       for (int k = 1; k < 16; ++k) dpo[k] = v[3 + k];
       store_row16(DO, tid, dpo);  // dL/d(pos_mlp out) -> DO
@@ -967,6 +981,7 @@ k_field_bwd_tc2(atmonr_grid_t g, const __half* __restrict__ pos_w, const __half*
             make_float4(v[4 * k] * invS, v[4 * k + 1] * invS, v[4 * k + 2] * invS, v[4 * k + 3] * invS);
     }
     epilogue_sync();
+    if ((tile + gridDim.x) * bwd2::kRows < M) fetch_inputs(tile + gridDim.x);
     {
       // a warp holds 2 levels x 16 sample groups: cell runs of one level end at similar rates,
       // so coarse-level warps almost never execute the flush path
@@ -975,6 +990,18 @@ k_field_bwd_tc2(atmonr_grid_t g, const __half* __restrict__ pos_w, const __half*
       float2* base = reinterpret_cast<float2*>(dtable) + L.offset;
       const float* stage = reinterpret_cast<const float*>(smem + bwd2::kX);
       const int64_t row0 = tile * bwd2::kRows + grp * 16;
+      // Most samples carry NO gradient (empty space: density <= 0 kills both dL/dsigma and the
+      // compositing weight), so the rows with a non-zero dL/d(features) are found first, with 16
+      // independent shared-memory reads in flight, and only those are walked.
+      const float* srow0 = stage + grp * 16 * 32 + ((lvl & 1) << 1);
+      uint32_t nz = 0;
+#pragma unroll
+      for (int r = 0; r < 16; ++r) {
+        const float2 d = *reinterpret_cast<const float2*>(srow0 + r * 32 + ((((lvl >> 1) ^ ((r ^ grp) & 7))) << 2));
+        nz |= (d.x != 0.0f || d.y != 0.0f) ? (1u << r) : 0u;
+      }
+      if (row0 + 16 > M) nz &= row0 < M ? (1u << (int)(M - row0)) - 1u : 0u;
+      if (!ATM_SCATTER_ON) nz = 0;
       float acc[16];
       uint32_t c_run[3] = {0xffffffffu, 0xffffffffu, 0xffffffffu};
       bool open = false;
@@ -987,14 +1014,11 @@ k_field_bwd_tc2(atmonr_grid_t g, const __half* __restrict__ pos_w, const __half*
         for (int c = 0; c < 8; ++c) red_add_f32x2(reinterpret_cast<float*>(entry_ptr(base, e[c])), acc[2 * c], acc[2 * c + 1]);
       };
 #pragma unroll 1
-      for (int r = 0; r < 16; ++r) {
-        const int64_t gi = row0 + r;
-        if (gi >= M) break;
+      while (nz) {
+        const int r = __ffs(nz) - 1;
+        nz &= nz - 1u;
         const int row = grp * 16 + r;
-        const float2 d = *reinterpret_cast<const float2*>(
-            stage + row * 32 + ((((lvl >> 1) ^ ((row ^ (row >> 4)) & 7)) << 2) | ((lvl & 1) << 1)));
-        if (!ATM_SCATTER_ON) continue;
-        if (d.x == 0.0f && d.y == 0.0f) continue;
+        const float2 d = *reinterpret_cast<const float2*>(srow0 + r * 32 + ((((lvl >> 1) ^ ((r ^ grp) & 7))) << 2));
         const float* pos = reinterpret_cast<const float*>(smem + bwd2::kPos) + row + (row >> 4);
         const float p[3] = {pos[0], pos[272], pos[544]};
         uint32_t cell[3];
