@@ -29,6 +29,9 @@ _f32 = torch.float32
 # (same arithmetic contract; kept as the cross-check of the tensor-core path).
 FIELD_IMPL = os.environ.get("ATMONR_FIELD_IMPL", "tc")
 # keep the encoded features of the forward pass for the backward pass when they fit in this many bytes
+# the field backward visits only the samples whose incoming gradient can be non-zero (exact; see
+# atmonr_composite_bwd_compact). "0" = dense backward over every sample.
+COMPACT_BWD = os.environ.get("ATMONR_COMPACT_BWD", "1") != "0"
 ENC_CACHE_BYTES = int(float(os.environ.get("ATMONR_ENC_CACHE_GB", "40")) * (1 << 30))
 
 
@@ -195,9 +198,16 @@ class NGPRenderFn(torch.autograd.Function):
         d_atmo = (g_map + g_atmo if g_atmo is not None else g_map).contiguous().float()
         d_surf = (g_map + g_surf if g_surf is not None else g_map).contiguous().float()
         absmax = torch.zeros(1, device=dev, dtype=_f32) if FIELD_IMPL != "simt" else None
-        dcolor, dsigma, dcs = ops.composite_backward(
-            z, color_raw.view(b, n, 4), sigma_raw.view(b, n, 1), cs_raw, catmo, tsurf, d_atmo, d_surf,
-            st.z_scale, relu=True, grad_absmax=absmax)
+        compact = COMPACT_BWD and FIELD_IMPL != "simt" and ctx.enc is not None and os.environ.get("ATMONR_BWD_NARROW") is None
+        if compact:
+            act_idx, n_act, dcolor, dsigma, dcs = ops.composite_backward_compact(
+                z, color_raw.view(b, n, 4), sigma_raw.view(b, n, 1), cs_raw, catmo, tsurf, d_atmo, d_surf,
+                st.z_scale, relu=True, grad_absmax=absmax)
+            st.last["n_active"] = n_act
+        else:
+            dcolor, dsigma, dcs = ops.composite_backward(
+                z, color_raw.view(b, n, 4), sigma_raw.view(b, n, 1), cs_raw, catmo, tsurf, d_atmo, d_surf,
+                st.z_scale, relu=True, grad_absmax=absmax)
         n_t, n_pw, n_dw, n_s, n_sw = ctx.sizes
         d_table = torch.zeros(n_t, device=dev, dtype=_f32)
         d_pw = torch.zeros(n_pw, device=dev, dtype=_f32)
@@ -208,6 +218,13 @@ class NGPRenderFn(torch.autograd.Function):
             L.call("atmonr_ngp_field_bwd", C.byref(st.grid3), L.ptr(t16), C.byref(st.pos_mlp), L.ptr(pw16),
                    C.byref(st.dir_mlp), L.ptr(dw16), L.ptr(x01), L.ptr(direction), L.ptr(dsigma), L.ptr(dcolor), b, n,
                    L.ptr(d_table), L.ptr(d_pw), L.ptr(d_dw), L.stream())
+        elif compact:
+            L.call("atmonr_ngp_field_bwd_tc_compact", C.byref(st.grid3), C.byref(st.pos_mlp), L.ptr(pw16),
+                   C.byref(st.dir_mlp), L.ptr(dw16), L.ptr(x01), L.ptr(direction), L.ptr(ctx.enc), L.ptr(act_idx),
+                   L.ptr(n_act), L.ptr(dsigma), L.ptr(dcolor), L.ptr(absmax), b, n, L.ptr(d_table), L.ptr(d_pw),
+                   L.ptr(d_dw), L.stream())
+            launch_prefetch(st)
+            ctx.enc = None
         else:
             L.call("atmonr_ngp_field_bwd_tc", C.byref(st.grid3), L.ptr(t16), C.byref(st.pos_mlp), L.ptr(pw16),
                    C.byref(st.dir_mlp), L.ptr(dw16), L.ptr(x01), L.ptr(direction), L.ptr(ctx.enc), L.ptr(dsigma),

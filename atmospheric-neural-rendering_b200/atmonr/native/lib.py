@@ -71,6 +71,7 @@ SIGNATURES = {
     "atmonr_ngp_surface_bwd": [GP, P, MP, P, P, P, P, P, I64, P, P, P],
     "atmonr_composite_fwd": [P, P, P, P, F32, I64, I32, I32, I32, I32, P, P, P, P, P, P, P],
     "atmonr_composite_bwd": [P, P, P, P, P, P, P, P, F32, I64, I32, I32, I32, I32, P, P, P, P, P, P],
+    "atmonr_composite_bwd_compact": [P, P, P, P, P, P, P, P, F32, I64, I32, I32, I32, I32, P, P, P, P, P, P, P],
     "atmonr_band_loss": [P, P, P, F32, I32, I64, I32, F32, P, P, P, P],
     "atmonr_adamw_step": [P, P, P, P, P, I64, F64, F64, F64, F64, F64, I64, F64, I32, P],
     "atmonr_extract_sigma": [FP, GP, P, MP, P, P, I64, F32, P, P],
@@ -79,6 +80,7 @@ SIGNATURES = {
     "atmonr_tc_probe": [P, P, I32, P, P],
     "atmonr_ngp_field_fwd_tc": [GP, P, MP, P, MP, P, P, P, I64, I32, P, P, P, P],
     "atmonr_ngp_field_bwd_tc": [GP, P, MP, P, MP, P, P, P, P, P, P, P, I64, I32, P, P, P, P],
+    "atmonr_ngp_field_bwd_tc_compact": [GP, MP, P, MP, P, P, P, P, P, P, P, P, P, I64, I32, P, P, P, P],
 }
 
 _lib = None

@@ -183,6 +183,25 @@ def composite_backward(z, color, sigma, color_surf, catmo, tsurf, d_atmo, d_surf
     return dcolor, dsigma, dcs, dz * z_scale
 
 
+def composite_backward_compact(z, color, sigma, color_surf, catmo, tsurf, d_atmo, d_surf, z_scale, relu,
+                               grad_absmax=None):
+    """atmonr_composite_bwd_compact: gradients of the samples that can carry one, as a list.
+    -> (active_idx (M,) int32 [first n valid], n_active (1,) int32 on the device, dcolor_c (M,K), dsigma_c (M,V),
+    dcolor_surf)."""
+    b, n = z.shape
+    k, v = color.shape[-1], sigma.shape[-1]
+    m = b * n
+    active_idx = torch.empty(m, device=z.device, dtype=torch.int32)
+    n_active = torch.zeros(1, device=z.device, dtype=torch.int32)
+    dcolor_c = torch.empty((m, k), device=z.device, dtype=_f32)
+    dsigma_c = torch.empty((m, v), device=z.device, dtype=_f32)
+    dcs = torch.empty_like(color_surf) if color_surf is not None else None
+    L.call("atmonr_composite_bwd_compact", L.ptr(z), L.ptr(color), L.ptr(sigma), L.ptr(color_surf), L.ptr(catmo),
+           L.ptr(tsurf), L.ptr(d_atmo), L.ptr(d_surf), float(z_scale), b, n, k, v, int(relu), L.ptr(active_idx),
+           L.ptr(n_active), L.ptr(dcolor_c), L.ptr(dsigma_c), L.ptr(dcs), L.ptr(grad_absmax), L.stream())
+    return active_idx, n_active, dcolor_c, dsigma_c, dcs
+
+
 class CompositeFn(torch.autograd.Function):
     """graphics_utils.py render / render_with_surface, differentiable w.r.t. colour, density,
     surface colour and (NeRF fine pass) the sample distances z."""

@@ -595,18 +595,41 @@ k_composite_fwd(const float* __restrict__ z, const float* __restrict__ color, co
 //   dL/dsig_v = delta_i * ( e_i * (T_i q_i - (Q_v - Qpre_i) / t_i) - S_v G_v )
 // with e = exp(-sig delta), t = (1-a)+1e-10, Q_v = sum_i w_i q_i (= g_atmo . C_atmo),
 // Qpre the inclusive prefix of w q, S_v = prod(1-a), G_v = sum_k g_surf[k] c_surf[k].
-template <int K, int V>
+// COMPACT: dsigma / dcolor are written as a dense LIST of the samples that can carry a gradient
+// (with the ReLUs of instant_ngp.py:178-184 a sample whose raw density is <= 0 has alpha = 0, hence
+// weight 0, hence dL/dcolour = 0, and the ReLU zeroes dL/dsigma), their sample indices go to
+// active_idx and the list length to *n_active (zeroed by the caller). A ray's samples stay
+// consecutive and in order (one atomicAdd per ray reserves its block). Empty space costs the field
+// backward nothing that way.
+template <int K, int V, bool COMPACT>
 __global__ void __launch_bounds__(128)
 k_composite_bwd(const float* __restrict__ z, const float* __restrict__ color, const float* __restrict__ sigma,
                 const float* __restrict__ color_surf, const float* __restrict__ catmo,
                 const float* __restrict__ tsurf, const float* __restrict__ g_atmo,
                 const float* __restrict__ g_surf, float zs, int64_t B, int N, int relu,
                 float* __restrict__ dcolor, float* __restrict__ dsigma, float* __restrict__ dcolor_surf,
-                float* __restrict__ ddelta, float* __restrict__ grad_absmax) {
+                float* __restrict__ ddelta, float* __restrict__ grad_absmax, uint32_t* __restrict__ active_idx,
+                uint32_t* __restrict__ n_active) {
   const int lane = threadIdx.x & 31;
   const int64_t ray = (blockIdx.x * (int64_t)blockDim.x + threadIdx.x) >> 5;
   if (ray >= B) return;
   const float* zr = z + ray * N;
+  uint32_t list_at = 0;  // COMPACT: next free position of this ray's block of the list
+  if (COMPACT) {
+    uint32_t cnt = 0;
+    for (int base = 0; base < N; base += 32) {
+      const int i = base + lane;
+      bool act = i < N;
+      if (act && relu) {
+        act = false;
+#pragma unroll
+        for (int v = 0; v < V; ++v) act = act || sigma[(ray * N + i) * V + v] > 0.0f;
+      }
+      cnt += __popc(__ballot_sync(0xffffffffu, act));
+    }
+    if (lane == 0) list_at = atomicAdd(n_active, cnt);
+    list_at = __shfl_sync(0xffffffffu, list_at, 0);
+  }
   float ga[K], gs[K], Qtot[V], SG[V], carryT[V], carryQ[V];
 #pragma unroll
   for (int k = 0; k < K; ++k) {
@@ -645,6 +668,20 @@ k_composite_bwd(const float* __restrict__ z, const float* __restrict__ color, co
     for (int v = 0; v < V; ++v) sraw[v] = r0.s[v];
     r0 = r1;
     r1 = r2;
+    uint32_t at = 0;  // COMPACT: this sample's list position
+    bool listed = false;
+    if (COMPACT) {
+      listed = in;
+      if (in && relu) {
+        listed = false;
+#pragma unroll
+        for (int v = 0; v < V; ++v) listed = listed || sraw[v] > 0.0f;
+      }
+      const uint32_t m = __ballot_sync(0xffffffffu, listed);
+      at = list_at + __popc(m & ((1u << lane) - 1u));
+      list_at += __popc(m);
+      if (listed) active_idx[at] = (uint32_t)(ray * N + i);
+    }
     float dc[K];
     float dd = 0.0f;  // dL/d(delta_i), summed over density channels
 #pragma unroll
@@ -677,10 +714,15 @@ k_composite_bwd(const float* __restrict__ z, const float* __restrict__ color, co
       float ds = delta * core;
       dd += s * core;
       if (relu && !(raw > 0.0f)) ds = 0.0f;
-      if (in) dsigma[(ray * N + i) * V + v] = ds, amax = fmaxf(amax, fabsf(ds));
+      if (COMPACT) {
+        if (listed) dsigma[(size_t)at * V + v] = ds, amax = fmaxf(amax, fabsf(ds));
+      } else if (in) {
+        dsigma[(ray * N + i) * V + v] = ds, amax = fmaxf(amax, fabsf(ds));
+      }
     }
     if (in && ddelta) ddelta[ray * N + i] = dd;
-    if (in) {
+    if (COMPACT ? listed : in) {
+      const size_t orow = COMPACT ? (size_t)at : (size_t)(ray * N + i);
       float dk[K];
 #pragma unroll
       for (int k = 0; k < K; ++k) {
@@ -688,10 +730,10 @@ k_composite_bwd(const float* __restrict__ z, const float* __restrict__ color, co
         amax = fmaxf(amax, fabsf(dk[k]));
       }
       if (K == 4) {
-        *reinterpret_cast<float4*>(dcolor + (ray * N + i) * 4) = make_float4(dk[0], dk[1 % K], dk[2 % K], dk[3 % K]);
+        *reinterpret_cast<float4*>(dcolor + orow * 4) = make_float4(dk[0], dk[1 % K], dk[2 % K], dk[3 % K]);
       } else {
 #pragma unroll
-        for (int k = 0; k < K; ++k) dcolor[(ray * N + i) * K + k] = dk[k];
+        for (int k = 0; k < K; ++k) dcolor[orow * K + k] = dk[k];
       }
     }
   }
@@ -1265,13 +1307,36 @@ int atmonr_composite_bwd(const float* z, const float* color, const float* sigma,
   ATM_REQUIRE(K != 4 || ((reinterpret_cast<uintptr_t>(color) | reinterpret_cast<uintptr_t>(dcolor)) & 15u) == 0,
               "atmonr_composite_bwd", "color and dcolor must be 16-byte aligned");
   const int grid = grid_for(B * 32, 128);
-#define CALL(KK, VV)                                                                                         \
-  k_composite_bwd<KK, VV><<<grid, 128, 0, S(stream)>>>(z, color, sigma, color_surf, color_map_atmo, trans_surf, \
-                                                      d_atmo, d_surf, z_scale, B, N, relu, dcolor, dsigma,    \
-                                                      dcolor_surf, ddelta, grad_absmax)
+#define CALL(KK, VV)                                                                                                \
+  k_composite_bwd<KK, VV, false><<<grid, 128, 0, S(stream)>>>(z, color, sigma, color_surf, color_map_atmo, trans_surf, \
+                                                             d_atmo, d_surf, z_scale, B, N, relu, dcolor, dsigma,    \
+                                                             dcolor_surf, ddelta, grad_absmax, nullptr, nullptr)
   ATM_KV_DISPATCH(K, V, CALL)
 #undef CALL
   ATM_CHECK_LAUNCH("atmonr_composite_bwd");
+  return 0;
+}
+
+int atmonr_composite_bwd_compact(const float* z, const float* color, const float* sigma, const float* color_surf,
+                                 const float* color_map_atmo, const float* trans_surf, const float* d_atmo,
+                                 const float* d_surf, float z_scale, int64_t B, int N, int K, int V, int relu,
+                                 uint32_t* active_idx, uint32_t* n_active, float* dcolor_c, float* dsigma_c,
+                                 float* dcolor_surf, float* grad_absmax, void* stream) {
+  if (B == 0) return 0;
+  ATM_REQUIRE(color_map_atmo && d_atmo && dcolor_c && dsigma_c && active_idx && n_active, "atmonr_composite_bwd_compact",
+              "null argument");
+  ATM_REQUIRE(!color_surf || trans_surf, "atmonr_composite_bwd_compact", "trans_surf required with a surface");
+  ATM_REQUIRE(B * (int64_t)N < ((int64_t)1 << 32), "atmonr_composite_bwd_compact", "B*N must be below 2^32");
+  ATM_REQUIRE(K != 4 || ((reinterpret_cast<uintptr_t>(color) | reinterpret_cast<uintptr_t>(dcolor_c)) & 15u) == 0,
+              "atmonr_composite_bwd_compact", "color and dcolor_c must be 16-byte aligned");
+  const int grid = grid_for(B * 32, 128);
+#define CALL(KK, VV)                                                                                               \
+  k_composite_bwd<KK, VV, true><<<grid, 128, 0, S(stream)>>>(z, color, sigma, color_surf, color_map_atmo, trans_surf, \
+                                                            d_atmo, d_surf, z_scale, B, N, relu, dcolor_c, dsigma_c, \
+                                                            dcolor_surf, nullptr, grad_absmax, active_idx, n_active)
+  ATM_KV_DISPATCH(K, V, CALL)
+#undef CALL
+  ATM_CHECK_LAUNCH("atmonr_composite_bwd_compact");
   return 0;
 }
 

@@ -761,12 +761,20 @@ __device__ __forceinline__ void stage_wait() {
 }
 __device__ __forceinline__ void epilogue_sync() { asm volatile("bar.sync 2, 256;" ::: "memory"); }
 
+// COMPACT: the rows are not samples 0..M-1 but the `*n_active` samples listed in active_idx (the
+// ones whose incoming gradient can be non-zero, written by k_composite_bwd in compact mode together
+// with their gradients dsigma_raw / dcolor_raw, which are then indexed by ROW, not by sample).
+// A sample with a zero incoming gradient contributes exactly zero to every output of this kernel,
+// so leaving it out changes nothing but the time.
+template <bool COMPACT>
 __global__ void __launch_bounds__(bwd2::kThreads, 2)
 k_field_bwd_tc2(atmonr_grid_t g, const __half* __restrict__ pos_w, const __half* __restrict__ dir_w,
                 const float* __restrict__ x01, const float* __restrict__ dirs, const __half* __restrict__ enc_in,
                 const float* __restrict__ dsigma_raw, const float* __restrict__ dcolor_raw,
-                const float* __restrict__ grad_absmax, int64_t M, int N, float* __restrict__ dtable,
-                float* __restrict__ dpos_w, float* __restrict__ ddir_w) {
+                const float* __restrict__ grad_absmax, int64_t M_samples, int N, float* __restrict__ dtable,
+                float* __restrict__ dpos_w, float* __restrict__ ddir_w, const uint32_t* __restrict__ active_idx,
+                const uint32_t* __restrict__ n_active) {
+  const int64_t M = COMPACT ? (int64_t)*n_active : M_samples;  // rows
   extern __shared__ __align__(128) uint8_t smem[];
   uint64_t* bar = reinterpret_cast<uint64_t*>(smem + bwd2::kBar);
   uint64_t* bar2 = reinterpret_cast<uint64_t*>(smem + bwd2::kBar2);
@@ -869,9 +877,12 @@ k_field_bwd_tc2(atmonr_grid_t g, const __half* __restrict__ pos_w, const __half*
   // load (that wait was 15 % of the epilogue warps' time).
   uint4 nx[4];
   float npos[3];
+  int64_t nsample = 0;  // sample index of the next tile's row
   auto fetch_inputs = [&](int64_t t) {
     const int64_t ii = t * bwd2::kRows + tid;
-    const int64_t jj = ii < M ? ii : M - 1;
+    int64_t jj = ii < M ? ii : M - 1;
+    if (COMPACT) jj = (int64_t)__ldg(active_idx + jj);
+    nsample = jj;
     const uint4* src = reinterpret_cast<const uint4*>(enc_in + jj * 32);
 #pragma unroll
     for (int cc = 0; cc < 4; ++cc) nx[cc] = __ldg(src + cc);
@@ -880,9 +891,9 @@ k_field_bwd_tc2(atmonr_grid_t g, const __half* __restrict__ pos_w, const __half*
   if (cta_has_work) fetch_inputs(blockIdx.x);
 
   for (int64_t tile = blockIdx.x; tile * bwd2::kRows < M; tile += gridDim.x, seen_tile = 1) {
-    const int64_t i = tile * bwd2::kRows + tid;
+    const int64_t i = tile * bwd2::kRows + tid;  // row (indexes the incoming gradients)
     const bool valid = i < M;
-    const int64_t j = valid ? i : M - 1;
+    const int64_t j = nsample;                   // sample (indexes enc_in, x01, dirs)
     if (seen_tile) mbar_wait(bar2, phase2), phase2 ^= 1;
     const uint4* enc_row = reinterpret_cast<const uint4*>(enc_in + j * 32);
     // ---------------- recompute the activations ----------------
@@ -900,6 +911,8 @@ k_field_bwd_tc2(atmonr_grid_t g, const __half* __restrict__ pos_w, const __half*
     float4 dc_in = make_float4(0.0f, 0.0f, 0.0f, 0.0f);
     float ds_in = 0.0f;
     if (valid) dc_in = __ldg(reinterpret_cast<const float4*>(dcolor_raw + 4 * i)), ds_in = __ldg(dsigma_raw + i);
+    const float* dptr = dirs + (size_t)((uint32_t)j / (uint32_t)N) * 3;  // the ray's direction (dir_mlp input)
+    const float dr[3] = {__ldg(dptr), __ldg(dptr + 1), __ldg(dptr + 2)};
     mbar_wait(bar, phase), phase ^= 1;
     tc_fence_after();
     float v[32];
@@ -911,7 +924,7 @@ k_field_bwd_tc2(atmonr_grid_t g, const __half* __restrict__ pos_w, const __half*
     {
       float po[16];
       tmem_ld16(my16, po);
-      dir_input_row(dirs + (size_t)((uint32_t)j / (uint32_t)N) * 3, po, v);
+      dir_input_row(dr, po, v);
     }
     store_row32<false>(DIN, tid, v);
     stage_arrive();
@@ -1133,13 +1146,13 @@ int atmonr_ngp_field_bwd_tc(const atmonr_grid_t* g, const void* table, const atm
   ATM_REQUIRE(M < ((int64_t)1 << 31), "atmonr_ngp_field_bwd_tc", "B*N must be below 2^31 per call (chunk the batch)");
   const bool use_wide = getenv("ATMONR_BWD_NARROW") == nullptr;  // read per call: tests toggle it
   if (enc && use_wide) {
-    cudaError_t e2 = cudaFuncSetAttribute(k_field_bwd_tc2, cudaFuncAttributeMaxDynamicSharedMemorySize, bwd2::kBytes);
+    cudaError_t e2 = cudaFuncSetAttribute(k_field_bwd_tc2<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, bwd2::kBytes);
     if (e2 != cudaSuccess) return fail("atmonr_ngp_field_bwd_tc", cudaGetErrorString(e2));
     const int64_t tiles2 = (M + bwd2::kRows - 1) / bwd2::kRows;
     const int grid2 = (int)(tiles2 < (int64_t)tc_num_sms() * 2 ? tiles2 : (int64_t)tc_num_sms() * 2);
-    k_field_bwd_tc2<<<grid2, bwd2::kThreads, bwd2::kBytes, reinterpret_cast<cudaStream_t>(stream)>>>(
+    k_field_bwd_tc2<false><<<grid2, bwd2::kThreads, bwd2::kBytes, reinterpret_cast<cudaStream_t>(stream)>>>(
         *g, (const __half*)pos_w, (const __half*)dir_w, x01, dirs, (const __half*)enc, dsigma_raw, dcolor_raw,
-        grad_absmax, M, N, dtable, dpos_w, ddir_w);
+        grad_absmax, M, N, dtable, dpos_w, ddir_w, nullptr, nullptr);
     ATM_CHECK_LAUNCH("atmonr_ngp_field_bwd_tc");
     return 0;
   }
@@ -1151,6 +1164,30 @@ int atmonr_ngp_field_bwd_tc(const atmonr_grid_t* g, const void* table, const atm
       *g, (const __half2*)table, (const __half*)pos_w, (const __half*)dir_w, x01, dirs, (const __half*)enc, dsigma_raw,
       dcolor_raw, grad_absmax, M, N, dtable, dpos_w, ddir_w);
   ATM_CHECK_LAUNCH("atmonr_ngp_field_bwd_tc");
+  return 0;
+}
+
+// The same backward over the samples listed in active_idx only (atmonr_composite_bwd_compact):
+// dsigma_c (n_active,) and dcolor_c (n_active, 4) are indexed by list position, *n_active is read
+// on the device (no host synchronisation). enc (the forward's cached features) is required.
+int atmonr_ngp_field_bwd_tc_compact(const atmonr_grid_t* g, const atmonr_mlp_t* pm, const void* pos_w,
+                                    const atmonr_mlp_t* dm, const void* dir_w, const float* x01, const float* dirs,
+                                    const void* enc, const uint32_t* active_idx, const uint32_t* n_active,
+                                    const float* dsigma_c, const float* dcolor_c, const float* grad_absmax, int64_t B,
+                                    int N, float* dtable, float* dpos_w, float* ddir_w, void* stream) {
+  if (check_field_shapes(g, pm, dm, "atmonr_ngp_field_bwd_tc_compact")) return -1;
+  const int64_t M = B * N;
+  if (M == 0) return 0;
+  ATM_REQUIRE(M < ((int64_t)1 << 31), "atmonr_ngp_field_bwd_tc_compact", "B*N must be below 2^31 per call (chunk the batch)");
+  ATM_REQUIRE(enc && active_idx && n_active && dsigma_c && dcolor_c, "atmonr_ngp_field_bwd_tc_compact", "null argument");
+  cudaError_t e2 = cudaFuncSetAttribute(k_field_bwd_tc2<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, bwd2::kBytes);
+  if (e2 != cudaSuccess) return fail("atmonr_ngp_field_bwd_tc_compact", cudaGetErrorString(e2));
+  const int64_t tiles2 = (M + bwd2::kRows - 1) / bwd2::kRows;  // upper bound: the list length is only known on the device
+  const int grid2 = (int)(tiles2 < (int64_t)tc_num_sms() * 2 ? tiles2 : (int64_t)tc_num_sms() * 2);
+  k_field_bwd_tc2<true><<<grid2, bwd2::kThreads, bwd2::kBytes, reinterpret_cast<cudaStream_t>(stream)>>>(
+      *g, (const __half*)pos_w, (const __half*)dir_w, x01, dirs, (const __half*)enc, dsigma_c, dcolor_c, grad_absmax, M,
+      N, dtable, dpos_w, ddir_w, active_idx, n_active);
+  ATM_CHECK_LAUNCH("atmonr_ngp_field_bwd_tc_compact");
   return 0;
 }
 

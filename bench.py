@@ -46,6 +46,8 @@ def parse():
     ap.add_argument("--granule", default="synthetic:H=256,W=256,seed=0")
     ap.add_argument("--cpu-rays", type=int, default=256, help="rays per step of the CPU baseline sample")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--dense-backward", action="store_true",
+                    help="field backward over every sample instead of the samples that carry a gradient")
     ap.add_argument("--no-prefetch", action="store_true",
                     help="sample every batch in line instead of underneath the previous step's backward")
     return ap.parse_args()
@@ -266,6 +268,9 @@ def run_native(args) -> None:
     h2d_bytes = sum(v.numel() * v.element_size() for v in host[0].values())
 
     prefetch = not args.no_prefetch
+    from atmonr.native import fused as _fused
+    if args.dense_backward:
+        _fused.COMPACT_BWD = False
 
     def step(batch, upcoming=None):
         # the NEXT batch is announced first: its sample points are computed on a side stream
@@ -318,6 +323,8 @@ def run_native(args) -> None:
         torch.cuda.profiler.stop()
     launches = L.STATS.launches
     L.STATS = None
+    n_act = pipe.fused_state.last.get("n_active") if pipe.fused_state is not None else None
+    active_fraction = float(n_act.item()) / (B * args.samples) if n_act is not None else 1.0
     clock_info = clocks.stop() if rank == 0 else {}
     ms_step = ms_total / K
     value = world * B * 1e3 / ms_step
@@ -338,6 +345,9 @@ def run_native(args) -> None:
     alg_bytes = {
         "atmonr_ngp_field_fwd": 512 * M, "atmonr_ngp_field_bwd": 1024 * M,
         "atmonr_ngp_field_fwd_tc": 512 * M, "atmonr_ngp_field_bwd_tc": 512 * M,
+        # the compact backward scatters for the listed samples only: count those
+        "atmonr_ngp_field_bwd_tc_compact": int(512 * M * active_fraction),
+        "atmonr_composite_bwd_compact": int((28 + 24 * active_fraction) * M),
         "atmonr_adamw_step": 30 * N_PARAMS, "atmonr_ngp_sample_points": 16 * M + 28 * B,
         "atmonr_composite_fwd": 24 * M, "atmonr_composite_bwd": 44 * M,
     }
@@ -411,6 +421,8 @@ def run_native(args) -> None:
             "workload": f"Instant-NGP (configs/instant_ngp.json) train step, {B} rays/GPU x {args.samples} samples/ray, "
                         f"{args.granule} HARP2-shaped granule, 4 bands 10/10/60/10 views",
             "rays_per_gpu": B, "samples_per_ray": args.samples, "parallelism": f"dp{world}",
+            "backward": ("dense" if args.dense_backward else
+                         f"samples with a non-zero incoming gradient only ({active_fraction:.3f} of all samples in the last step; exact)"),
             "l2": "inputs larger than L2: per-step working set (x01, sigma, colour, gradients) is several GB",
         },
         "clocks": clock_info, "e2e": e2e, "gpu_launches": launches, "roofline": roofline, "extract": extract,

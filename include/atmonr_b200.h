@@ -142,6 +142,20 @@ int atmonr_ngp_field_bwd_tc(const atmonr_grid_t* grid_host, const void* table_f1
                             const float* grad_absmax, int64_t B, int N, float* dtable,
                             float* dpos_w, float* ddir_w, void* stream);
 
+/* The tcgen05 backward over a LIST of samples (those whose incoming gradient can be non-zero; see
+ * atmonr_composite_bwd_compact): active_idx (n,) sample indices, *n_active = n on the device,
+ * dsigma_c (n,) / dcolor_c (n,4) indexed by list position. A sample with zero incoming gradient
+ * contributes exactly zero to dtable / dpos_w / ddir_w, so the outputs equal those of
+ * atmonr_ngp_field_bwd_tc on the dense arrays (up to the order of the fp32 atomics). enc_f16 is
+ * required. */
+int atmonr_ngp_field_bwd_tc_compact(const atmonr_grid_t* grid_host, const atmonr_mlp_t* pos_mlp_host,
+                                    const void* pos_w_f16, const atmonr_mlp_t* dir_mlp_host,
+                                    const void* dir_w_f16, const float* x01, const float* dirs,
+                                    const void* enc_f16, const uint32_t* active_idx,
+                                    const uint32_t* n_active, const float* dsigma_c,
+                                    const float* dcolor_c, const float* grad_absmax, int64_t B, int N,
+                                    float* dtable, float* dpos_w, float* ddir_w, void* stream);
+
 /* ---- surface branch, per ray: [hash2d(pts_surf.xy) | SH2(dir)] -> surf_mlp ----------------
  * instant_ngp.py:140,150,173-174. color_surf_raw (B,4) pre-ReLU. */
 int atmonr_ngp_surface_fwd(const atmonr_grid_t* grid2d_host, const void* table_f16,
@@ -175,6 +189,20 @@ int atmonr_composite_bwd(const float* z, const float* color, const float* sigma,
                          float z_scale, int64_t B, int N, int K, int V, int relu, float* dcolor,
                          float* dsigma, float* dcolor_surf, float* ddelta, float* grad_absmax,
                          void* stream);
+
+/* The same backward, writing dcolor / dsigma only for the samples that can carry a gradient, as a
+ * list: active_idx (capacity B*N) receives their sample indices (a ray's samples stay consecutive
+ * and ordered), dcolor_c (capacity B*N, K) and dsigma_c (capacity B*N, V) their gradients by list
+ * position, *n_active (device, zeroed by the caller) the list length. With relu != 0 a sample is
+ * listed iff one of its raw densities is > 0 (otherwise alpha = 0 => weight 0 => dcolor = 0, and the
+ * ReLU zeroes dsigma); with relu == 0 every sample is listed. */
+int atmonr_composite_bwd_compact(const float* z, const float* color, const float* sigma,
+                                 const float* color_surf, const float* color_map_atmo,
+                                 const float* trans_surf, const float* d_atmo, const float* d_surf,
+                                 float z_scale, int64_t B, int N, int K, int V, int relu,
+                                 uint32_t* active_idx, uint32_t* n_active, float* dcolor_c,
+                                 float* dsigma_c, float* dcolor_surf, float* grad_absmax,
+                                 void* stream);
 
 /* ---- per-band loss and its gradient (instant_ngp.py:249-263, losses.py:5-33) ---------------
  * kind: 0 dark, 1 hdr, 2 l1, 3 l1_plus_hdr, 4 mse, 5 mse_plus_hdr. color_map (B,K); band
