@@ -617,15 +617,30 @@ k_composite_bwd(const float* __restrict__ z, const float* __restrict__ color, co
   uint32_t list_at = 0;  // COMPACT: next free position of this ray's block of the list
   if (COMPACT) {
     uint32_t cnt = 0;
-    for (int base = 0; base < N; base += 32) {
-      const int i = base + lane;
-      bool act = i < N;
-      if (act && relu) {
-        act = false;
-#pragma unroll
-        for (int v = 0; v < V; ++v) act = act || sigma[(ray * N + i) * V + v] > 0.0f;
+    if (!relu) {
+      cnt = (uint32_t)N;
+    } else if (V == 1 && (N & 3) == 0 && (reinterpret_cast<uintptr_t>(sigma) & 15u) == 0) {
+      // 16-byte loads, four in flight per lane: the count costs one memory round trip per ray
+      const float4* s4 = reinterpret_cast<const float4*>(sigma + ray * N);
+      uint32_t mine = 0;
+#pragma unroll 4
+      for (int q = lane; q < (N >> 2); q += 32) {
+        const float4 sv = s4[q];
+        mine += (sv.x > 0.0f) + (sv.y > 0.0f) + (sv.z > 0.0f) + (sv.w > 0.0f);
       }
-      cnt += __popc(__ballot_sync(0xffffffffu, act));
+#pragma unroll
+      for (int o = 16; o > 0; o >>= 1) mine += __shfl_xor_sync(0xffffffffu, mine, o);
+      cnt = mine;
+    } else {
+      for (int base = 0; base < N; base += 32) {
+        const int i = base + lane;
+        bool act = false;
+        if (i < N) {
+#pragma unroll
+          for (int v = 0; v < V; ++v) act = act || sigma[(ray * N + i) * V + v] > 0.0f;
+        }
+        cnt += __popc(__ballot_sync(0xffffffffu, act));
+      }
     }
     if (lane == 0) list_at = atomicAdd(n_active, cnt);
     list_at = __shfl_sync(0xffffffffu, list_at, 0);

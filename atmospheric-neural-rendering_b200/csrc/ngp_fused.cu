@@ -877,11 +877,22 @@ k_field_bwd_tc2(atmonr_grid_t g, const __half* __restrict__ pos_w, const __half*
   // load (that wait was 15 % of the epilogue warps' time).
   uint4 nx[4];
   float npos[3];
-  int64_t nsample = 0;  // sample index of the next tile's row
+  int64_t nsample = 0;     // sample index of the next tile's row
+  uint32_t idx_ahead = 0;  // COMPACT: list entry of this thread's row one tile further (so that the row
+                           // loads below never wait for the index load)
+  auto load_idx = [&](int64_t t) -> uint32_t {
+    if (!COMPACT || t * bwd2::kRows >= M) return 0u;
+    const int64_t ii = t * bwd2::kRows + tid;
+    return __ldg(active_idx + (ii < M ? ii : M - 1));
+  };
+  if (cta_has_work) idx_ahead = load_idx(blockIdx.x);
   auto fetch_inputs = [&](int64_t t) {
     const int64_t ii = t * bwd2::kRows + tid;
     int64_t jj = ii < M ? ii : M - 1;
-    if (COMPACT) jj = (int64_t)__ldg(active_idx + jj);
+    if (COMPACT) {
+      jj = (int64_t)idx_ahead;
+      idx_ahead = load_idx(t + gridDim.x);
+    }
     nsample = jj;
     const uint4* src = reinterpret_cast<const uint4*>(enc_in + jj * 32);
 #pragma unroll
