@@ -46,8 +46,8 @@ def parse():
     ap.add_argument("--granule", default="synthetic:H=256,W=256,seed=0")
     ap.add_argument("--cpu-rays", type=int, default=256, help="rays per step of the CPU baseline sample")
     ap.add_argument("--no-cpu-baseline", action="store_true")
-    ap.add_argument("--dense-backward", action="store_true",
-                    help="field backward over every sample instead of the samples that carry a gradient")
+    ap.add_argument("--compact-backward", action="store_true",
+                    help="field backward over the samples that carry a gradient only (exact; pays off on sparse scenes)")
     ap.add_argument("--no-prefetch", action="store_true",
                     help="sample every batch in line instead of underneath the previous step's backward")
     return ap.parse_args()
@@ -269,8 +269,8 @@ def run_native(args) -> None:
 
     prefetch = not args.no_prefetch
     from atmonr.native import fused as _fused
-    if args.dense_backward:
-        _fused.COMPACT_BWD = False
+    if args.compact_backward:
+        _fused.COMPACT_BWD = True
 
     def step(batch, upcoming=None):
         # the NEXT batch is announced first: its sample points are computed on a side stream
@@ -421,8 +421,8 @@ def run_native(args) -> None:
             "workload": f"Instant-NGP (configs/instant_ngp.json) train step, {B} rays/GPU x {args.samples} samples/ray, "
                         f"{args.granule} HARP2-shaped granule, 4 bands 10/10/60/10 views",
             "rays_per_gpu": B, "samples_per_ray": args.samples, "parallelism": f"dp{world}",
-            "backward": ("dense" if args.dense_backward else
-                         f"samples with a non-zero incoming gradient only ({active_fraction:.3f} of all samples in the last step; exact)"),
+            "backward": (f"samples with a non-zero incoming gradient only ({active_fraction:.3f} of all samples in the last step; exact)"
+                         if _fused.COMPACT_BWD else "dense (every sample)"),
             "l2": "inputs larger than L2: per-step working set (x01, sigma, colour, gradients) is several GB",
         },
         "clocks": clock_info, "e2e": e2e, "gpu_launches": launches, "roofline": roofline, "extract": extract,

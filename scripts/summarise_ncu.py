@@ -1,0 +1,148 @@
+"""Turn the ncu artefacts a gpurun call brought back into the tracked summaries under profiles/.
+
+    python scripts/summarise_ncu.py --tag r2 --full gpurun_out/X_prof_full.ncu-rep \\
+        --launches gpurun_out/X_launches.csv --bench gpurun_out/X_bench.json --cmd-full "..." --cmd-launch "..."
+
+Writes profiles/<tag>_ncu_full_summary.md (selected counters + warp-stall split per kernel),
+profiles/<tag>_ncu_launch_list.md/.csv (per-kernel totals and shares next to the live CUDA-event
+split of the bench line) and refreshes profiles/ncu_dram_traffic.json (read by bench.py for
+roofline.traffic). Needs `ncu` on PATH (it only READS reports here; nothing is profiled).
+"""
+
+from __future__ import annotations
+
+import argparse
+import csv
+import io
+import json
+import os
+import subprocess
+from collections import defaultdict
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+METRICS = [
+    "gpu__time_duration.sum", "dram__bytes_read.sum", "dram__bytes_write.sum",
+    "gpu__dram_throughput.avg.pct_of_peak_sustained_elapsed", "lts__throughput.avg.pct_of_peak_sustained_elapsed",
+    "lts__t_sector_hit_rate.pct", "lts__t_sectors_srcunit_tex_op_read.sum", "lts__t_sectors_srcunit_tex_op_red.sum",
+    "l1tex__t_sector_hit_rate.pct", "l1tex__t_sectors_pipe_lsu_mem_global_op_ld.sum",
+    "launch__grid_size", "launch__block_size", "launch__registers_per_thread",
+    "sm__throughput.avg.pct_of_peak_sustained_elapsed", "sm__warps_active.avg.pct_of_peak_sustained_active",
+    "smsp__issue_active.avg.pct_of_peak_sustained_active", "smsp__inst_executed.sum",
+    "smsp__inst_executed_op_global_red.sum", "sm__pipe_fp64_cycles_active.avg.pct_of_peak_sustained_active",
+    "sm__pipe_tensor_cycles_active.avg.pct_of_peak_sustained_active",
+    "sm__inst_executed_pipe_tensor.sum",
+]
+# kernel name prefix -> C-ABI entry point (the keys bench.py uses)
+ENTRY = {
+    "k_ngp_sample_points": "atmonr_ngp_sample_points", "k_field_fwd_tc": "atmonr_ngp_field_fwd_tc",
+    "k_composite_fwd": "atmonr_composite_fwd", "k_composite_bwd": "atmonr_composite_bwd",
+    "k_field_bwd_tc2": "atmonr_ngp_field_bwd_tc",
+}
+
+
+def short(name: str) -> str:
+    name = name.replace("void ", "").replace("atm::", "")
+    return name.split("(")[0]
+
+
+def entry_of(kernel: str) -> str | None:
+    for k, v in ENTRY.items():
+        if kernel.startswith(k):
+            # the last template argument of k_field_bwd_tc2<COMPACT> / k_composite_bwd<K, V, COMPACT>
+            args = kernel[kernel.index("<") + 1:kernel.rindex(">")].split(",") if "<" in kernel else []
+            compact = bool(args) and args[-1].strip() in ("1", "true") and (
+                (k == "k_field_bwd_tc2") or (k == "k_composite_bwd" and len(args) == 3))
+            return v + ("_compact" if compact else "")
+    return None
+
+
+def full_summary(rep: str, tag: str, cmd: str, rays: int) -> None:
+    raw = subprocess.run(["ncu", "-i", rep, "--page", "raw", "--csv"], capture_output=True, text=True, check=True).stdout
+    rows = list(csv.reader(io.StringIO(raw)))
+    head, units, data = rows[0], rows[1], rows[2:]
+    ki = head.index("Kernel Name")
+    stall_cols = [i for i, c in enumerate(head) if c.startswith("smsp__pcsamp_warps_issue_stalled") and "not_issued" not in c]
+    out = [f"# ncu --set full, {tag}, bench.py default configuration (2^18 rays x 1024 samples)", "", f"`{cmd}`", "",
+           "Durations under ncu are serialised, cache-flushed replays (longer than the live CUDA-event times of "
+           "the bench line); counters are per launch. `stalls` = warp-state sampling split (pc sampling).", ""]
+    traffic = {"rays": rays, "source": f"profiles/{tag}_ncu_full_summary.md (ncu --set full, dram__bytes_read.sum + "
+                                        "dram__bytes_write.sum per launch)"}
+    for r in data:
+        name = short(r[ki])
+        out += [f"## {name}", "```"]
+        vals = {}
+        for m in METRICS:
+            if m in head:
+                i = head.index(m)
+                vals[m] = (r[i], units[i])
+                out.append(f"{m:<78} {r[i]:>18} {units[i]}")
+        tot = sum(float(r[i].replace(",", "") or 0) for i in stall_cols) or 1.0
+        split = sorted(((float(r[i].replace(",", "") or 0) / tot, head[i][len("smsp__pcsamp_warps_issue_stalled_"):]) for i in stall_cols), reverse=True)
+        out.append("stalls: " + ", ".join(f"{n} {100 * f:.1f}%" for f, n in split[:8]))
+        out.append("```")
+        out.append("")
+        ent = entry_of(name)
+        if ent and "dram__bytes_read.sum" in vals:
+            def to_bytes(v, u):
+                scale = {"byte": 1, "Kbyte": 1e3, "Mbyte": 1e6, "Gbyte": 1e9, "Tbyte": 1e12}[u]
+                return float(v.replace(",", "")) * scale
+            traffic[ent] = {"dram_bytes_per_launch": to_bytes(*vals["dram__bytes_read.sum"]) + to_bytes(*vals["dram__bytes_write.sum"])}
+    open(os.path.join(ROOT, "profiles", f"{tag}_ncu_full_summary.md"), "w").write("\n".join(out))
+    json.dump(traffic, open(os.path.join(ROOT, "profiles", "ncu_dram_traffic.json"), "w"), indent=1)
+
+
+def launch_list(path: str, tag: str, cmd: str, bench: dict | None) -> None:
+    lines = [l for l in open(path) if not l.startswith("==")]
+    rows = list(csv.DictReader(io.StringIO("".join(lines))))
+    tot, cnt = defaultdict(float), defaultdict(int)
+    for r in rows:
+        if r.get("Metric Name") != "gpu__time_duration.sum":
+            continue
+        v = float(r["Metric Value"].replace(",", ""))
+        unit = r.get("Metric Unit", "ns")
+        ms = v * {"ns": 1e-6, "us": 1e-3, "ms": 1.0, "s": 1e3}.get(unit, 1e-6)
+        k = short(r["Kernel Name"])
+        tot[k] += ms
+        cnt[k] += 1
+    total = sum(tot.values()) or 1.0
+    live = (bench or {}).get("roofline", {}).get("ms_per_step_by_kernel", {})
+    live_total = sum(live.values()) or 1.0
+    out = [f"# ncu launch list, {tag} (steady state, own kernels only)", "", f"`{cmd}`", "",
+           f"{sum(cnt.values())} consecutive launches of the library's kernels after the set-up and settle steps; 2^18 rays x "
+           "1024 samples per step. Times under ncu are serialised and cold-cache: compare SHARES with the live "
+           "CUDA-event split of the same command without ncu (right-hand columns, the bench line of the same call).", "",
+           "| kernel | launches | ncu total ms | ncu share | live ms/step | live share |", "|---|---|---|---|---|---|"]
+    for k in sorted(tot, key=lambda k: -tot[k]):
+        ent = entry_of(k)
+        lv = live.get(ent) if ent else None
+        if lv is None:
+            lv = {"k_surface_bwd": live.get("atmonr_ngp_surface_bwd"), "k_surface_fwd": live.get("atmonr_ngp_surface_fwd"),
+                  "k_adamw": live.get("atmonr_adamw_step"), "k_band_loss": live.get("atmonr_band_loss")}.get(k)
+        out.append(f"| `{k}` | {cnt[k]} | {tot[k]:.3f} | {100 * tot[k] / total:.1f}% | "
+                   + (f"{lv:.3f} | {100 * lv / live_total:.1f}% |" if lv is not None else " | |"))
+    open(os.path.join(ROOT, "profiles", f"{tag}_ncu_launch_list.md"), "w").write("\n".join(out) + "\n")
+    open(os.path.join(ROOT, "profiles", f"{tag}_ncu_launch_list.csv"), "w").write("".join(lines))
+
+
+def main() -> None:
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--tag", required=True)
+    ap.add_argument("--full")
+    ap.add_argument("--launches")
+    ap.add_argument("--bench")
+    ap.add_argument("--cmd-full", default="")
+    ap.add_argument("--cmd-launch", default="")
+    ap.add_argument("--rays", type=int, default=1 << 18)
+    a = ap.parse_args()
+    bench = json.loads(open(a.bench).read().strip().splitlines()[-1]) if a.bench else None
+    if a.full:
+        full_summary(a.full, a.tag, a.cmd_full, a.rays)
+    if a.launches:
+        launch_list(a.launches, a.tag, a.cmd_launch, bench)
+    if bench:
+        json.dump(bench, open(os.path.join(ROOT, "profiles", f"{a.tag}_bench_n1.json"), "w"))
+
+
+if __name__ == "__main__":
+    main()

@@ -245,7 +245,7 @@ def _pipeline(scene, cfg):
     return pipe
 
 
-@pytest.mark.parametrize("impl", ["tc", "tc-dense-bwd", "simt", "tc-nocache", "tc-narrow-bwd"])
+@pytest.mark.parametrize("impl", ["tc", "tc-compact-bwd", "simt", "tc-nocache", "tc-narrow-bwd"])
 def test_ngp_pipeline_forward_loss_gradients_vs_oracle(scene, impl, monkeypatch):
     """impl = tc: dense layers on tcgen05 (fp16 gradient operands under a power-of-two scale), 128-row
     forward tiles, 256-row backward tiles reading the forward's cached encoding;
@@ -254,8 +254,8 @@ def test_ngp_pipeline_forward_loss_gradients_vs_oracle(scene, impl, monkeypatch)
     (fp32 gradients)."""
     from atmonr.native import fused
     monkeypatch.setattr(fused, "FIELD_IMPL", "simt" if impl == "simt" else "tc")
-    if impl == "tc-dense-bwd":   # default "tc": the backward visits only the samples that carry a gradient
-        monkeypatch.setattr(fused, "COMPACT_BWD", False)
+    if impl == "tc-compact-bwd":   # the backward visits only the samples that carry a gradient
+        monkeypatch.setattr(fused, "COMPACT_BWD", True)
     if impl == "tc-nocache":
         monkeypatch.setattr(fused, "ENC_CACHE_BYTES", 0)
     if impl == "tc-narrow-bwd":
