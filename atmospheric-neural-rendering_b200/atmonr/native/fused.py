@@ -286,6 +286,6 @@ def extract_sigma(st: NGPState, table16, pos_w16, pts: torch.Tensor) -> torch.Te
     p = pts.contiguous().double()
     n = p.shape[0]
     out = torch.empty(n, device=p.device, dtype=_f32)
-    L.call("atmonr_extract_sigma", C.byref(st.frame), C.byref(st.grid3), L.ptr(table16), C.byref(st.pos_mlp),
+    L.call("atmonr_extract_sigma" if FIELD_IMPL == "simt" else "atmonr_extract_sigma_tc", C.byref(st.frame), C.byref(st.grid3), L.ptr(table16), C.byref(st.pos_mlp),
            L.ptr(pos_w16), L.ptr(p), n, float(st.alt_compress), L.ptr(out), L.stream())
     return out.view(n, 1)

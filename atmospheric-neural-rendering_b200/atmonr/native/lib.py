@@ -75,6 +75,7 @@ SIGNATURES = {
     "atmonr_band_loss": [P, P, P, F32, I32, I64, I32, F32, P, P, P, P],
     "atmonr_adamw_step": [P, P, P, P, P, I64, F64, F64, F64, F64, F64, I64, F64, I32, P],
     "atmonr_extract_sigma": [FP, GP, P, MP, P, P, I64, F32, P, P],
+    "atmonr_extract_sigma_tc": [FP, GP, P, MP, P, P, I64, F32, P, P],
     "atmonr_positional_encoding": [P, I64, I32, C.POINTER(C.c_int32), I32, P, P],
     "atmonr_sample_pdf": [P, P, P, I64, I32, I32, P, P, P],
     "atmonr_tc_probe": [P, P, I32, P, P],

@@ -409,6 +409,67 @@ k_field_fwd_tc(atmonr_grid_t g, const __half2* __restrict__ table, const __half*
 
 
 // =========================================================================================
+// extraction: float64 scene point -> geodetic preprocessing -> hash grid -> pos_mlp -> max(sigma, 0)
+// =========================================================================================
+// instant_ngp.py:208-247 with the two dense layers of pos_mlp on tcgen05: the forward kernel above
+// without the colour branch, fed from float64 points (scripts/extract.py:205) through the float64
+// flavour of the preprocessor. Same shared-memory map; 6 CTAs per SM (the FP64 chain needs registers).
+__global__ void __launch_bounds__(128, 6)
+k_extract_sigma_tc(atmonr_frame_t f, GeoFrame gf, atmonr_grid_t g, const __half2* __restrict__ table,
+                   const __half* __restrict__ pos_w, const double* __restrict__ pts, int64_t n,
+                   float alt_compress, float* __restrict__ sigma) {
+  extern __shared__ __align__(128) uint8_t smem[];
+  uint64_t* bar = reinterpret_cast<uint64_t*>(smem + fwd::kBar);
+  uint32_t* tmem_ptr = reinterpret_cast<uint32_t*>(smem + fwd::kTmemPtr);
+  const int tid = threadIdx.x, warp = tid >> 5;
+  LevelRow* lv = reinterpret_cast<LevelRow*>(smem + fwd::kLv);
+  load_level_table(g, lv);
+  load_matrix_tile(pos_w, smem + fwd::kW1P, 32, 32);
+  load_matrix_tile(pos_w + 1024, smem + fwd::kW2P, 16, 32);
+  if (warp == 0) tmem_alloc<fwd::kTmemCols>(tmem_ptr);
+  if (tid == 0) {
+    mbar_init(bar, 1);
+    fence_mbar_init();
+  }
+  publish_and_sync();
+  tc_fence_after();
+  const uint32_t acc = *tmem_ptr;
+  const uint32_t mine = tmem_addr(acc, warp, 0);
+  const uint32_t sbase = smem_u32(smem), sa = sbase + fwd::kA;
+  uint8_t* A = smem + fwd::kA;
+  uint32_t phase = 0;
+  const uint64_t keep_pol = l2_policy_keep();
+  for (int64_t tile = blockIdx.x; tile * kTile < n; tile += gridDim.x) {
+    const int64_t i = tile * kTile + tid;
+    const bool valid = i < n;
+    const int64_t j = valid ? i : n - 1;
+    {
+      double c0 = pts[3 * j], c1 = pts[3 * j + 1], c2 = pts[3 * j + 2];
+      if (f.enabled) preprocess_f64(f, gf, c0, c1, c2, c0, c1, c2);
+      // instant_ngp.py:224-233 stay in float64; tcnn casts its input to float32
+      const float p[3] = {(float)((c0 + 1.0) / 2.0), (float)((c1 + 1.0) / 2.0),
+                          (float)(((c2 + 1.0) / 2.0) / (double)alt_compress)};
+      encode_to_tile(lv, table, p, A, tid, keep_pol);
+    }
+    publish_and_sync();
+    if (warp == 0) issue_layer<32>(acc, sa, sbase + fwd::kW1P, bar);
+    mbar_wait(bar, phase), phase ^= 1;
+    tc_fence_after();
+    relu_acc_to_tile(mine, A, tid);
+    publish_and_sync();
+    if (warp == 0) issue_layer<16>(acc, sa, sbase + fwd::kW2P, bar);
+    mbar_wait(bar, phase), phase ^= 1;
+    tc_fence_after();
+    float po[4];
+    tmem_ld4(mine, po);
+    if (valid) sigma[i] = fmaxf(po[0], 0.0f);
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 0) tmem_dealloc<fwd::kTmemCols>(acc);
+}
+
+// =========================================================================================
 // fused radiance field, backward
 // =========================================================================================
 namespace bwd {
@@ -1143,6 +1204,23 @@ int atmonr_ngp_field_fwd_tc(const atmonr_grid_t* g, const void* table, const atm
   return 0;
 }
 
+
+// atmonr_extract_sigma on the tensor-core path (declared in include/atmonr_b200.h).
+int atmonr_extract_sigma_tc(const atmonr_frame_t* f, const atmonr_grid_t* g, const void* table, const atmonr_mlp_t* pm,
+                            const void* pos_w, const double* pts, int64_t n, float alt_compress, float* sigma,
+                            void* stream) {
+  ATM_REQUIRE(f && g && g->n_dims == 3 && g->n_feat == 2 && g->n_levels == 16, "atmonr_extract_sigma_tc", "bad frame/grid");
+  ATM_REQUIRE(pm && pm->in_pad == 32 && pm->width == 32 && pm->n_hidden == 1 && pm->n_out == 16, "atmonr_extract_sigma_tc",
+              "pos_mlp must be 32 -> [32] -> 16");
+  if (n == 0) return 0;
+  const int64_t tiles = (n + kTile - 1) / kTile;
+  const int64_t max_ctas = (int64_t)tc_num_sms() * 6;
+  const int grid = (int)(tiles < max_ctas ? tiles : max_ctas);
+  k_extract_sigma_tc<<<grid, kTile, fwd::kBytes, reinterpret_cast<cudaStream_t>(stream)>>>(
+      *f, make_geo_frame(*f), *g, (const __half2*)table, (const __half*)pos_w, pts, n, alt_compress, sigma);
+  ATM_CHECK_LAUNCH("atmonr_extract_sigma_tc");
+  return 0;
+}
 
 // Same contract as atmonr_ngp_field_bwd. enc (optional): features saved by the forward pass;
 // grad_absmax (optional device scalar): max |incoming gradient|, sets the fp16 operand scale.

@@ -226,6 +226,12 @@ int atmonr_extract_sigma(const atmonr_frame_t* frame_host, const atmonr_grid_t* 
                          const void* table_f16, const atmonr_mlp_t* pos_mlp_host,
                          const void* pos_w_f16, const double* pts, int64_t n, float alt_compress,
                          float* sigma, void* stream);
+/* The same query with the two dense layers on tcgen05 (the training forward kernel without its
+ * colour branch); same arguments, same results up to the accumulation order of the dense layers. */
+int atmonr_extract_sigma_tc(const atmonr_frame_t* frame_host, const atmonr_grid_t* grid_host,
+                         const void* table_f16, const atmonr_mlp_t* pos_mlp_host,
+                         const void* pos_w_f16, const double* pts, int64_t n, float alt_compress,
+                         float* sigma, void* stream);
 
 /* ---- NeRF path helpers ----------------------------------------------------------------------
  * encoders.py:4-28 positional_encoding; list variant (per-axis frequency counts, layout

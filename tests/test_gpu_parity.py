@@ -362,7 +362,12 @@ def test_ngp_training_tracks_oracle(scene):
     assert np.max(np.abs(ln - lo) / lo) < 0.05, (lo, ln)   # and tracks the oracle step by step
 
 
-def test_extract_matches_oracle(scene):
+@pytest.mark.parametrize("impl", ["tc", "simt"])
+def test_extract_matches_oracle(scene, impl, monkeypatch):
+    """instant_ngp.py:208-247. tc: k_extract_sigma_tc (dense layers on tcgen05, the default);
+    simt: the thread-per-voxel kernel kept as its cross-check. 5000 voxels = 39 full tiles + a ragged one."""
+    from atmonr.native import fused
+    monkeypatch.setattr(fused, "FIELD_IMPL", impl)
     cfg = ngp_config(16)
     orc = NGPOracle(cfg, scene.frame, scene.max_i, fp16=True)
     params = random_params(orc, seed=2, table_scale=5e3)
