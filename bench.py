@@ -14,6 +14,7 @@ region). Scaling is weak: every rank processes `--rays` rays per step.
 from __future__ import annotations
 
 import argparse
+import math
 import json
 import os
 import subprocess
@@ -397,9 +398,21 @@ def run_native(args) -> None:
            "ms_per_step": ms_e2e}
 
     # ---- extraction: voxel queries/s (BASELINE.json metric, second half), inputs resident in HBM ----
+    # SURVEY 8d workload: a dense grid of voxel columns over the granule x 81 altitudes (0..20 km, step
+    # 250 m), float64 ECEF points normalised like scripts/extract.py:81, one call = 32768 columns x 81.
+    # Each rank queries its own slab of columns (no communication).
+    from atmonr.datasets.harp2_extract import HARP2VoxelGridExtractDataset
     n_vox = 32768 * 81
-    gen = torch.Generator(device=dev).manual_seed(rank)
-    vox = (torch.rand((n_vox, 3), device=dev, dtype=torch.float64, generator=gen) * 2 - 1) * 0.95
+    lat_span_m = math.radians(float(dataset.lat[~dataset.lat.isnan()].max() - dataset.lat[~dataset.lat.isnan()].min())) * 6378137.0
+    h_step = lat_span_m / 620.0   # ~620 x ~500 columns over the 5 x 5 degree granule: > 4 x 32768 columns
+    grid_ds = HARP2VoxelGridExtractDataset(dataset, horizontal_step=h_step, alt_step=250.0)
+    n_alt = int(grid_ds.sample_alt.shape[0])
+    n_cols = len(grid_ds) // n_alt
+    per_call = min(32768, n_cols // max(world, 1))
+    lo = (rank * per_call) % max(n_cols - per_call + 1, 1)
+    n_vox = per_call * n_alt
+    vox = ((grid_ds.xyz[lo * n_alt:(lo + per_call) * n_alt].to(dev) - dataset.offset.to(dev)) / dataset.scale).contiguous()
+    assert vox.dtype == torch.float64 and vox.shape == (n_vox, 3)
     pipe.eval()
     with torch.no_grad():
         for _ in range(2):
@@ -407,7 +420,8 @@ def run_native(args) -> None:
         ms_ext = timed(5, lambda i: pipe.extract(vox)) / 5
     pipe.train()
     extract = {"value": world * n_vox * 1e3 / ms_ext, "unit": "voxels/s", "voxels_per_call_per_gpu": n_vox,
-               "ms_per_call": ms_ext}
+               "ms_per_call": ms_ext,
+               "workload": f"voxel grid, {per_call} columns x {n_alt} altitudes per call, float64 points (scripts/extract.py voxelgrid mode)"}
 
     if rank != 0:
         return
