@@ -313,7 +313,7 @@ def run_native(args) -> None:
     for i in range(W):
         step(batches[i % nb], batches[(i + 1) % nb])
     clocks = ClockSampler(local)
-    if rank == 0:
+    if rank == 0 and os.environ.get("ATMONR_BENCH_NO_CLOCKS") != "1":
         clocks.start()
     L.STATS = L.CallStats(timed=False)
     profile_range = os.environ.get("ATMONR_CUDA_PROFILER_RANGE") == "1"  # ncu --profile-from-start off

@@ -200,3 +200,11 @@ def test_pipeline_surface_on_cpu():
     npipe = get_pipeline(ncfg["pipeline"], FakeDataset(scene))
     assert set(npipe.state_dict()) == {"coarse", "fine"}
     assert npipe.nerf["coarse"].fc1.in_features == 76 and npipe.nerf["fine"].fc9.out_features == 260
+
+
+def test_trainer_lookahead_pairs():
+    """Trainer announces the NEXT batch to the pipeline one step early (Pipeline.prefetch)."""
+    from atmonr.trainer import _with_lookahead
+    assert list(_with_lookahead([])) == []
+    assert list(_with_lookahead(["a"])) == [("a", None)]
+    assert list(_with_lookahead(iter("abc"))) == [("a", "b"), ("b", "c"), ("c", None)]
