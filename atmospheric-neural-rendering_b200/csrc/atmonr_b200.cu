@@ -107,50 +107,9 @@ __global__ void k_ngp_sample_points(atmonr_frame_t f, GeoFrame gf, const float* 
 // 16-byte aligned buffers): one Philox block, one index division and one load of the ray per
 // four samples, 16-byte loads/stores, and four independent FP64 chains per thread to hide the
 // latency of the FP64 pipe. The kernel is bound by FP64 issue, not by its 16 B/sample of HBM writes.
-__global__ void __launch_bounds__(128)
-k_ngp_sample_points4(atmonr_frame_t f, GeoFrame gf, const float* __restrict__ o, const float* __restrict__ d,
-                     const float* __restrict__ len, const float* __restrict__ u, const float* __restrict__ bins,
-                     int64_t groups, int N4, int mode, uint64_t seed, uint64_t base, float alt_compress,
-                     float* __restrict__ x01, float* __restrict__ z) {
+__global__ void __launch_bounds__(128) k_ngp_sample_points4(SamplerJob job) {
   const int64_t q = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
-  if (q >= groups) return;
-  int64_t ray;
-  if (groups <= 0xffffffffll) ray = (int64_t)((uint32_t)q / (uint32_t)N4);
-  else ray = q / N4;
-  const int g4 = (int)(q - ray * N4);
-  const int N = N4 * 4, i0 = g4 * 4;
-  float t[4] = {0.5f, 0.5f, 0.5f, 0.5f};
-  if (mode == 1) {
-    const float4 uu = reinterpret_cast<const float4*>(u)[q];
-    t[0] = uu.x, t[1] = uu.y, t[2] = uu.z, t[3] = uu.w;
-  } else if (mode == 2) {
-    philox_uniform4(seed, base + (uint64_t)ray, (uint32_t)g4, t);
-  }
-  float lo[4];
-  if (bins) {
-    const float4 bb = reinterpret_cast<const float4*>(bins)[g4];
-    lo[0] = bb.x, lo[1] = bb.y, lo[2] = bb.z, lo[3] = bb.w;
-  } else {
-#pragma unroll
-    for (int k = 0; k < 4; ++k) lo[k] = (float)(i0 + k) / (float)N;
-  }
-  const float ln = len[ray];
-  const float ox = o[ray * 3], oy = o[ray * 3 + 1], oz = o[ray * 3 + 2];
-  const float dx = d[ray * 3], dy = d[ray * 3 + 1], dz = d[ray * 3 + 2];
-  float zz[4], out[12];
-#pragma unroll
-  for (int k = 0; k < 4; ++k) {
-    zz[k] = stratified_z(lo[k], t[k], N, ln);
-    const float px = ox + dx * zz[k], py = oy + dy * zz[k], pz = oz + dz * zz[k];
-    float c0 = px, c1 = py, c2 = pz;
-    if (f.enabled) preprocess_f32(f, gf, px, py, pz, c0, c1, c2);
-    to_unit_cube(c0, c1, c2, alt_compress, out[3 * k], out[3 * k + 1], out[3 * k + 2]);
-  }
-  reinterpret_cast<float4*>(z)[q] = make_float4(zz[0], zz[1], zz[2], zz[3]);
-  float4* xo = reinterpret_cast<float4*>(x01) + 3 * q;
-  xo[0] = make_float4(out[0], out[1], out[2], out[3]);
-  xo[1] = make_float4(out[4], out[5], out[6], out[7]);
-  xo[2] = make_float4(out[8], out[9], out[10], out[11]);
+  if (q < job.groups) sample_group4(job, q);
 }
 
 // =========================================================================================
@@ -1136,14 +1095,13 @@ int atmonr_ngp_sample_points(const atmonr_frame_t* f, const float* origin, const
   ATM_REQUIRE(f, "atmonr_ngp_sample_points", "null frame");
   ATM_REQUIRE(mode >= 0 && mode <= 2 && (mode != 1 || u), "atmonr_ngp_sample_points", "bad mode / missing u");
   if (B * N == 0) return 0;
-  const GeoFrame gf = make_geo_frame(*f);
-  auto aligned16 = [](const void* p) { return (reinterpret_cast<uintptr_t>(p) & 15u) == 0; };
-  if (N % 4 == 0 && aligned16(x01) && aligned16(z) && aligned16(u) && aligned16(bins) && B * (int64_t)(N / 4) < (1ll << 37))
-    k_ngp_sample_points4<<<grid_for(B * (N / 4), 128), 128, 0, S(stream)>>>(
-        *f, gf, origin, dir, len, u, bins, B * (N / 4), N / 4, mode, seed, ray_index_base, alt_compress, x01, z);
+  SamplerJob job;
+  if (make_sampler_job(job, f, origin, dir, len, u, bins, B, N, mode, seed, ray_index_base, alt_compress, x01, z))
+    k_ngp_sample_points4<<<grid_for(job.groups, 128), 128, 0, S(stream)>>>(job);
   else
-    k_ngp_sample_points<<<grid_for(B * N, 256), 256, 0, S(stream)>>>(*f, gf, origin, dir, len, u, bins, B * N, N, mode,
-                                                                    seed, ray_index_base, alt_compress, x01, z);
+    k_ngp_sample_points<<<grid_for(B * N, 256), 256, 0, S(stream)>>>(*f, make_geo_frame(*f), origin, dir, len, u, bins,
+                                                                    B * N, N, mode, seed, ray_index_base, alt_compress,
+                                                                    x01, z);
   ATM_CHECK_LAUNCH("atmonr_ngp_sample_points");
   return 0;
 }
