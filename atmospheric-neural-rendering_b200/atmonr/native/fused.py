@@ -34,10 +34,6 @@ FIELD_IMPL = os.environ.get("ATMONR_FIELD_IMPL", "tc")
 # mostly empty; on the benchmark's randomly initialised field 82 % of the samples are listed and the
 # list costs about what it saves (device-resident step -1.5 %, end-to-end step +3 %), so it is opt-in.
 COMPACT_BWD = os.environ.get("ATMONR_COMPACT_BWD", "0") != "0"
-# Where an announced batch's sampler runs: "bwd" = on the spare (tenth) warp of every CTA of the field
-# backward kernel of the current step (atmonr_ngp_field_bwd_tc_sampling; costs the step nothing);
-# "stream" = as its own kernel on a side stream.
-PREFETCH_IN = os.environ.get("ATMONR_PREFETCH_IN", "bwd")
 ENC_CACHE_BYTES = int(float(os.environ.get("ATMONR_ENC_CACHE_GB", "40")) * (1 << 30))
 
 
@@ -120,26 +116,6 @@ def _launch_one(st: NGPState, p: dict, on_side_stream: bool) -> None:
                               ray_index_base=p["ray_index_base"], bins=st.bins, out=(p["x01"], p["z"]))
         p["done"] = torch.cuda.Event()
         p["done"].record()
-
-
-def _sampler_job_for_backward(st: NGPState):
-    """The first announced, not yet sampled batch as an atmonr_sampler_job_t for the field backward's
-    sampler warp, or None (nothing announced / in-kernel sampling not applicable)."""
-    if PREFETCH_IN != "bwd" or st.n_samples % 4 != 0:
-        return None
-    for p in st.pending:
-        if p["done"] is None:
-            o, d, ln = p["rays"]
-            jt = L.SamplerJobT()
-            jt.frame = C.pointer(st.frame)
-            jt.origin, jt.dir, jt.len, jt.bins = L.ptr(o), L.ptr(d), L.ptr(ln), L.ptr(st.bins)
-            jt.B, jt.N = o.shape[0], st.n_samples
-            jt.seed, jt.ray_index_base = p["seed"], p["ray_index_base"]
-            jt.alt_compress = float(st.alt_compress)
-            jt.x01, jt.z = L.ptr(p["x01"]), L.ptr(p["z"])
-            # (the rays were produced on this stream before the event `ready`, i.e. before this call)
-            return p, jt
-    return None
 
 
 def take_prefetched(st: NGPState, origin):
@@ -252,24 +228,16 @@ class NGPRenderFn(torch.autograd.Function):
             launch_prefetch(st)
             ctx.enc = None
         else:
-            job = _sampler_job_for_backward(st) if (ctx.enc is not None and os.environ.get("ATMONR_BWD_NARROW") is None) else None
-            if job is not None:
-                p, jt = job
-                torch.cuda.current_stream().wait_event(p["ready"])   # the rays (a no-op on the announcing stream)
-                L.call("atmonr_ngp_field_bwd_tc_sampling", C.byref(st.grid3), L.ptr(t16), C.byref(st.pos_mlp),
-                       L.ptr(pw16), C.byref(st.dir_mlp), L.ptr(dw16), L.ptr(x01), L.ptr(direction), L.ptr(ctx.enc),
-                       L.ptr(dsigma), L.ptr(dcolor), L.ptr(absmax), b, n, L.ptr(d_table), L.ptr(d_pw), L.ptr(d_dw),
-                       C.byref(jt), L.stream())
-                p["done"] = torch.cuda.Event()
-                p["done"].record()
-            else:
-                L.call("atmonr_ngp_field_bwd_tc", C.byref(st.grid3), L.ptr(t16), C.byref(st.pos_mlp), L.ptr(pw16),
-                       C.byref(st.dir_mlp), L.ptr(dw16), L.ptr(x01), L.ptr(direction), L.ptr(ctx.enc), L.ptr(dsigma),
-                       L.ptr(dcolor), L.ptr(absmax), b, n, L.ptr(d_table), L.ptr(d_pw), L.ptr(d_dw), L.stream())
+            L.call("atmonr_ngp_field_bwd_tc", C.byref(st.grid3), L.ptr(t16), C.byref(st.pos_mlp), L.ptr(pw16),
+                   C.byref(st.dir_mlp), L.ptr(dw16), L.ptr(x01), L.ptr(direction), L.ptr(ctx.enc), L.ptr(dsigma),
+                   L.ptr(dcolor), L.ptr(absmax), b, n, L.ptr(d_table), L.ptr(d_pw), L.ptr(d_dw), L.stream())
             # announced batches: their samplers go to the side stream now. (Releasing them together
             # with the backward from a common event, the backward on a high-priority stream, was
             # measured too: the sampler's CTAs do not fit next to two backward CTAs -- the register
-            # file of each SM sub-partition is full -- so it only ran after the backward.)
+            # file of each SM sub-partition is full -- so it only ran after the backward. Running the
+            # sampler on a tenth warp INSIDE the backward kernel fits the register file but made the
+            # step 2-4 ms slower: its ~1600 FP64 instructions share the instruction cache with the
+            # backward's 3900.)
             launch_prefetch(st)
             ctx.enc = None
         L.call("atmonr_ngp_surface_bwd", C.byref(st.grid2), L.ptr(s16), C.byref(st.surf_mlp), L.ptr(sw16),

@@ -49,17 +49,6 @@ class MlpT(C.Structure):
         return self.width * self.in_pad + (self.n_hidden - 1) * self.width * self.width + self.out_pad * self.width
 
 
-class SamplerJobT(C.Structure):
-    """atmonr_sampler_job_t: the atmonr_ngp_sample_points call whose outputs the field backward's
-    sampler warp produces (next batch)."""
-    _fields_ = [
-        ("frame", C.POINTER(FrameT)), ("origin", C.c_void_p), ("dir", C.c_void_p), ("len", C.c_void_p),
-        ("bins", C.c_void_p), ("B", C.c_int64), ("N", C.c_int32), ("reserved", C.c_int32),
-        ("seed", C.c_uint64), ("ray_index_base", C.c_uint64), ("alt_compress", C.c_float),
-        ("reserved_f", C.c_float), ("x01", C.c_void_p), ("z", C.c_void_p),
-    ]
-
-
 P, I64, I32, U64, F32, F64 = C.c_void_p, C.c_int64, C.c_int, C.c_uint64, C.c_float, C.c_double
 GP, FP, MP = C.POINTER(GridT), C.POINTER(FrameT), C.POINTER(MlpT)
 
@@ -92,7 +81,6 @@ SIGNATURES = {
     "atmonr_tc_probe": [P, P, I32, P, P],
     "atmonr_ngp_field_fwd_tc": [GP, P, MP, P, MP, P, P, P, I64, I32, P, P, P, P],
     "atmonr_ngp_field_bwd_tc": [GP, P, MP, P, MP, P, P, P, P, P, P, P, I64, I32, P, P, P, P],
-    "atmonr_ngp_field_bwd_tc_sampling": [GP, P, MP, P, MP, P, P, P, P, P, P, P, I64, I32, P, P, P, C.POINTER(SamplerJobT), P],
     "atmonr_ngp_field_bwd_tc_compact": [GP, MP, P, MP, P, P, P, P, P, P, P, P, P, I64, I32, P, P, P, P],
 }
 

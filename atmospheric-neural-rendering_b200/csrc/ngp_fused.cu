@@ -769,7 +769,6 @@ k_field_bwd_tc(atmonr_grid_t g, const __half2* __restrict__ table, const __half*
 namespace bwd2 {
 constexpr int kRows = 256;
 constexpr int kThreads = 288;            // 8 epilogue warps (one sample row per thread) + the MMA-issuer warp
-constexpr int kLaunchThreads = 320;      // + the sampler warp (next batch's sample points; idle without a job)
 constexpr int kX = 0;
 constexpr int kH = kX + 16384;
 constexpr int kDIN = kH + 16384;
@@ -828,19 +827,14 @@ __device__ __forceinline__ void epilogue_sync() { asm volatile("bar.sync 2, 256;
 // with their gradients dsigma_raw / dcolor_raw, which are then indexed by ROW, not by sample).
 // A sample with a zero incoming gradient contributes exactly zero to every output of this kernel,
 // so leaving it out changes nothing but the time.
-// Warp 9 is the SAMPLER warp: the sample points of the NEXT training batch depend on its rays only,
-// their float64 geodesy is bound by the FP64 pipe, and this kernel leaves 70 % of the issue slots
-// and the whole FP64 pipe idle. The tenth warp fits in the register file for free (2 CTAs x 10 warps
-// = 5 warps per SM sub-partition, which two of the four sub-partitions hold already), so the
-// sampler runs inside the backward of the previous step and costs the step nothing.
 template <bool COMPACT>
-__global__ void __launch_bounds__(bwd2::kLaunchThreads, 2)
+__global__ void __launch_bounds__(bwd2::kThreads, 2)
 k_field_bwd_tc2(atmonr_grid_t g, const __half* __restrict__ pos_w, const __half* __restrict__ dir_w,
                 const float* __restrict__ x01, const float* __restrict__ dirs, const __half* __restrict__ enc_in,
                 const float* __restrict__ dsigma_raw, const float* __restrict__ dcolor_raw,
                 const float* __restrict__ grad_absmax, int64_t M_samples, int N, float* __restrict__ dtable,
                 float* __restrict__ dpos_w, float* __restrict__ ddir_w, const uint32_t* __restrict__ active_idx,
-                const uint32_t* __restrict__ n_active, const SamplerJob job) {
+                const uint32_t* __restrict__ n_active) {
   const int64_t M = COMPACT ? (int64_t)*n_active : M_samples;  // rows
   extern __shared__ __align__(128) uint8_t smem[];
   uint64_t* bar = reinterpret_cast<uint64_t*>(smem + bwd2::kBar);
@@ -929,10 +923,6 @@ k_field_bwd_tc2(atmonr_grid_t g, const __half* __restrict__ pos_w, const __half*
       }
       __syncwarp();
     }
-  } else if (warp == 9) {
-    // ------------------------------- sampler warp ---------------------------------------------
-    const int lane = tid & 31;
-    for (int64_t q = (int64_t)blockIdx.x * 32 + lane; q < job.groups; q += (int64_t)gridDim.x * 32) sample_group4(job, q);
   } else {
   // ------------------------------- epilogue warps ---------------------------------------------
   const uint32_t my32 = tmem_addr(tmem, warp, (warp >> 2) * bwd2::cHalf), my16 = my32;
@@ -1234,11 +1224,11 @@ int atmonr_extract_sigma_tc(const atmonr_frame_t* f, const atmonr_grid_t* g, con
 
 // Same contract as atmonr_ngp_field_bwd. enc (optional): features saved by the forward pass;
 // grad_absmax (optional device scalar): max |incoming gradient|, sets the fp16 operand scale.
-static int field_bwd_tc_impl(const atmonr_grid_t* g, const void* table, const atmonr_mlp_t* pm, const void* pos_w,
-                             const atmonr_mlp_t* dm, const void* dir_w, const float* x01, const float* dirs,
-                             const void* enc, const float* dsigma_raw, const float* dcolor_raw,
-                             const float* grad_absmax, int64_t B, int N, float* dtable, float* dpos_w, float* ddir_w,
-                             const SamplerJob* next_job, void* stream) {
+int atmonr_ngp_field_bwd_tc(const atmonr_grid_t* g, const void* table, const atmonr_mlp_t* pm, const void* pos_w,
+                            const atmonr_mlp_t* dm, const void* dir_w, const float* x01, const float* dirs,
+                            const void* enc, const float* dsigma_raw, const float* dcolor_raw,
+                            const float* grad_absmax, int64_t B, int N, float* dtable, float* dpos_w, float* ddir_w,
+                            void* stream) {
   if (check_field_shapes(g, pm, dm, "atmonr_ngp_field_bwd_tc")) return -1;
   const int64_t M = B * N;
   if (M == 0) return 0;
@@ -1249,14 +1239,12 @@ static int field_bwd_tc_impl(const atmonr_grid_t* g, const void* table, const at
     if (e2 != cudaSuccess) return fail("atmonr_ngp_field_bwd_tc", cudaGetErrorString(e2));
     const int64_t tiles2 = (M + bwd2::kRows - 1) / bwd2::kRows;
     const int grid2 = (int)(tiles2 < (int64_t)tc_num_sms() * 2 ? tiles2 : (int64_t)tc_num_sms() * 2);
-    SamplerJob none{};
-    k_field_bwd_tc2<false><<<grid2, bwd2::kLaunchThreads, bwd2::kBytes, reinterpret_cast<cudaStream_t>(stream)>>>(
+    k_field_bwd_tc2<false><<<grid2, bwd2::kThreads, bwd2::kBytes, reinterpret_cast<cudaStream_t>(stream)>>>(
         *g, (const __half*)pos_w, (const __half*)dir_w, x01, dirs, (const __half*)enc, dsigma_raw, dcolor_raw,
-        grad_absmax, M, N, dtable, dpos_w, ddir_w, nullptr, nullptr, next_job ? *next_job : none);
+        grad_absmax, M, N, dtable, dpos_w, ddir_w, nullptr, nullptr);
     ATM_CHECK_LAUNCH("atmonr_ngp_field_bwd_tc");
     return 0;
   }
-  ATM_REQUIRE(!next_job, "atmonr_ngp_field_bwd_tc_sampling", "the sampler warp needs the 256-row backward (enc given, ATMONR_BWD_NARROW unset)");
   cudaError_t e = cudaFuncSetAttribute(k_field_bwd_tc, cudaFuncAttributeMaxDynamicSharedMemorySize, bwd::kBytes);
   if (e != cudaSuccess) return fail("atmonr_ngp_field_bwd_tc", cudaGetErrorString(e));
   const int64_t tiles = (M + kTile - 1) / kTile;
@@ -1266,33 +1254,6 @@ static int field_bwd_tc_impl(const atmonr_grid_t* g, const void* table, const at
       dcolor_raw, grad_absmax, M, N, dtable, dpos_w, ddir_w);
   ATM_CHECK_LAUNCH("atmonr_ngp_field_bwd_tc");
   return 0;
-}
-
-int atmonr_ngp_field_bwd_tc(const atmonr_grid_t* g, const void* table, const atmonr_mlp_t* pm, const void* pos_w,
-                            const atmonr_mlp_t* dm, const void* dir_w, const float* x01, const float* dirs,
-                            const void* enc, const float* dsigma_raw, const float* dcolor_raw,
-                            const float* grad_absmax, int64_t B, int N, float* dtable, float* dpos_w, float* ddir_w,
-                            void* stream) {
-  return field_bwd_tc_impl(g, table, pm, pos_w, dm, dir_w, x01, dirs, enc, dsigma_raw, dcolor_raw, grad_absmax, B, N,
-                           dtable, dpos_w, ddir_w, nullptr, stream);
-}
-
-// atmonr_ngp_field_bwd_tc that ALSO computes the sample points of the next batch (what
-// atmonr_ngp_sample_points would write for `next`, in-kernel Philox draws) on a spare warp of every CTA.
-// Returns -2 (nothing launched) when the job does not fit the fast sampler (N % 4, alignment).
-int atmonr_ngp_field_bwd_tc_sampling(const atmonr_grid_t* g, const void* table, const atmonr_mlp_t* pm,
-                                     const void* pos_w, const atmonr_mlp_t* dm, const void* dir_w, const float* x01,
-                                     const float* dirs, const void* enc, const float* dsigma_raw,
-                                     const float* dcolor_raw, const float* grad_absmax, int64_t B, int N, float* dtable,
-                                     float* dpos_w, float* ddir_w, const atmonr_sampler_job_t* next, void* stream) {
-  ATM_REQUIRE(next && next->frame && next->x01 && next->z, "atmonr_ngp_field_bwd_tc_sampling", "null job");
-  ATM_REQUIRE(enc && B * (int64_t)N > 0, "atmonr_ngp_field_bwd_tc_sampling", "needs the forward's cached features and a non-empty batch");
-  SamplerJob job;
-  if (!make_sampler_job(job, next->frame, next->origin, next->dir, next->len, nullptr, next->bins, next->B, next->N, 2,
-                        next->seed, next->ray_index_base, next->alt_compress, next->x01, next->z))
-    return -2;
-  return field_bwd_tc_impl(g, table, pm, pos_w, dm, dir_w, x01, dirs, enc, dsigma_raw, dcolor_raw, grad_absmax, B, N,
-                           dtable, dpos_w, ddir_w, &job, stream);
 }
 
 // The same backward over the samples listed in active_idx only (atmonr_composite_bwd_compact):
@@ -1312,10 +1273,9 @@ int atmonr_ngp_field_bwd_tc_compact(const atmonr_grid_t* g, const atmonr_mlp_t* 
   if (e2 != cudaSuccess) return fail("atmonr_ngp_field_bwd_tc_compact", cudaGetErrorString(e2));
   const int64_t tiles2 = (M + bwd2::kRows - 1) / bwd2::kRows;  // upper bound: the list length is only known on the device
   const int grid2 = (int)(tiles2 < (int64_t)tc_num_sms() * 2 ? tiles2 : (int64_t)tc_num_sms() * 2);
-  SamplerJob none{};
-  k_field_bwd_tc2<true><<<grid2, bwd2::kLaunchThreads, bwd2::kBytes, reinterpret_cast<cudaStream_t>(stream)>>>(
+  k_field_bwd_tc2<true><<<grid2, bwd2::kThreads, bwd2::kBytes, reinterpret_cast<cudaStream_t>(stream)>>>(
       *g, (const __half*)pos_w, (const __half*)dir_w, x01, dirs, (const __half*)enc, dsigma_c, dcolor_c, grad_absmax, M,
-      N, dtable, dpos_w, ddir_w, active_idx, n_active, none);
+      N, dtable, dpos_w, ddir_w, active_idx, n_active);
   ATM_CHECK_LAUNCH("atmonr_ngp_field_bwd_tc_compact");
   return 0;
 }

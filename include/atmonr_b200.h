@@ -142,37 +142,6 @@ int atmonr_ngp_field_bwd_tc(const atmonr_grid_t* grid_host, const void* table_f1
                             const float* grad_absmax, int64_t B, int N, float* dtable,
                             float* dpos_w, float* ddir_w, void* stream);
 
-/* atmonr_ngp_field_bwd_tc that also computes the sample points of the NEXT batch on a spare warp of
- * every CTA: the sampler needs the rays only, is bound by the FP64 pipe, and the backward kernel
- * leaves that pipe and most issue slots idle. `next` describes the call
- * atmonr_ngp_sample_points(frame, origin, dir, len, NULL, bins, B, N, 2, seed, ray_index_base,
- * alt_compress, x01, z) whose outputs are produced. Returns -2 without launching when N % 4 != 0
- * or a buffer is not 16-byte aligned (call the two functions separately then). */
-typedef struct {
-  const atmonr_frame_t* frame;
-  const float* origin;
-  const float* dir;
-  const float* len;
-  const float* bins;
-  int64_t B;
-  int32_t N;
-  int32_t reserved;
-  uint64_t seed;
-  uint64_t ray_index_base;
-  float alt_compress;
-  float reserved_f;
-  float* x01;
-  float* z;
-} atmonr_sampler_job_t;
-int atmonr_ngp_field_bwd_tc_sampling(const atmonr_grid_t* grid_host, const void* table_f16,
-                                     const atmonr_mlp_t* pos_mlp_host, const void* pos_w_f16,
-                                     const atmonr_mlp_t* dir_mlp_host, const void* dir_w_f16,
-                                     const float* x01, const float* dirs, const void* enc_f16,
-                                     const float* dsigma_raw, const float* dcolor_raw,
-                                     const float* grad_absmax, int64_t B, int N, float* dtable,
-                                     float* dpos_w, float* ddir_w, const atmonr_sampler_job_t* next,
-                                     void* stream);
-
 /* The tcgen05 backward over a LIST of samples (those whose incoming gradient can be non-zero; see
  * atmonr_composite_bwd_compact): active_idx (n,) sample indices, *n_active = n on the device,
  * dsigma_c (n,) / dcolor_c (n,4) indexed by list position. A sample with zero incoming gradient
