@@ -32,9 +32,12 @@ class BatchLoader:
     def __iter__(self) -> Iterator[dict[str, torch.Tensor]]:
         n = self.idx.shape[0]
         order = torch.randperm(n, generator=self.generator) if self.shuffle else torch.arange(n)
+        # ONE host->device copy of the permutation per epoch; every batch index is a device-side slice
+        # of it (a per-batch copy from pageable memory blocks the host until the device has caught up)
+        order = order.to(self.idx.device)
         for b in range(len(self)):
             idx = order[b * self.batch_size:(b + 1) * self.batch_size]
             if self.world_size > 1:
                 per = -(-idx.shape[0] // self.world_size)
                 idx = idx[self.rank * per:(self.rank + 1) * per]
-            yield self.dataset.__getbatch__(idx.to(self.idx.device))
+            yield self.dataset.__getbatch__(idx)

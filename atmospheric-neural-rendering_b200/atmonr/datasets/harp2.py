@@ -141,7 +141,9 @@ class HARP2Dataset(Dataset):
         self.ray_len_norm = self.ray_len / self.scale
         band_of_view = torch.from_numpy(self.irgb_idx).to(device=keep.device)
         self.ray_irgb_idx = band_of_view[torch.where(keep.view((-1, n_view)))[1]]
-        self.ray_idx = torch.arange(self.ray_origin_norm.shape[0], dtype=torch.int32)
+        # (the reference keeps ray_idx on the host, harp2.py:254, which costs a blocking copy per batch;
+        # here it lives with the ray tables, and the trainer scatters with it on the device)
+        self.ray_idx = torch.arange(self.ray_origin_norm.shape[0], dtype=torch.int32, device=self.ray_origin_norm.device)
 
     # ---- harp2.py:259-349 ------------------------------------------------------------------
     def get_progress_tracker(self) -> ProgressTracker:

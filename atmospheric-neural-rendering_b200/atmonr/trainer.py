@@ -94,6 +94,25 @@ class Trainer:
         progress = self.dataset.get_progress_tracker()
         last_len, running = 0, []
         sched = self.config["scheduler"]
+        # The reference reads the loss and three pixel vectors back to the host EVERY step
+        # (trainer.py:108-140: two .item() and three device->host copies), which serialises host and
+        # device. Same observable behaviour without the per-step synchronisation: losses
+        # are read back in groups of `print_frequency` steps (the writer gets every step's value with
+        # its own step index), and the progress pixels are scattered into a device buffer that is
+        # copied into the host-side ProgressTracker once per epoch, before it is used.
+        dev_pix = None           # (3, n_rays) on the device: total / surface / atmosphere predictions
+        waiting: list = []       # (iteration, loss tensor) not yet read back
+
+        def flush_losses():
+            nonlocal running
+            if not waiting:
+                return
+            vals = torch.stack([t for _, t in waiting]).float().cpu().tolist()
+            for (it, _), v in zip(waiting, vals):
+                self.writer.add_scalar("Loss", v, it)
+            running = (running + vals)[-self.config["print_frequency"]:]
+            waiting.clear()
+
         while self.iter_count < self.config["num_iters"]:
             for batch, upcoming in _with_lookahead(self.dataloader):
                 if prof:
@@ -103,27 +122,32 @@ class Trainer:
                 elif upcoming is not None and hasattr(self.pipeline, "prefetch"):
                     self.pipeline.prefetch(upcoming)
                 results, loss = self.train_step(batch)
-                loss_val = loss.item()
-                self.writer.add_scalar("Loss", loss_val, self.iter_count)
-                running = running[-self.config["print_frequency"]:] + [loss_val]
+                waiting.append((self.iter_count, loss.detach()))
                 self.iter_count += 1
                 if (sched["type"] == "fixed" and self.iter_count % sched["decay_interval"] == 0
                         and self.iter_count > sched["decay_start"]):
                     self.scheduler.step()
-                # progress tracker: one gather on the device, one copy to the host (trainer.py:123-140)
+                # progress tracker (trainer.py:123-140): one gather + one scatter on the device
                 band = batch["irgb_idx"][:, None]
                 maps = torch.stack([results["color_map_fine"], results["color_map_surf"], results["color_map_atmo"]])
-                pix = torch.take_along_dim(maps.detach(), band[None].expand(3, -1, -1), dim=2)[..., 0].float().cpu().numpy()
-                where = batch["idx"].cpu().numpy()
-                progress.pred_pixels[where] = pix[0]
-                progress.pred_pixels_surf[where] = pix[1]
-                progress.pred_pixels_atmo[where] = pix[2]
+                pix = torch.take_along_dim(maps.detach(), band[None].expand(3, -1, -1), dim=2)[..., 0].float()
+                if dev_pix is None:
+                    dev_pix = torch.zeros((3, progress.pred_pixels.shape[0]), device=pix.device)
+                    for k, name in enumerate(("pred_pixels", "pred_pixels_surf", "pred_pixels_atmo")):
+                        dev_pix[k] = torch.from_numpy(getattr(progress, name)).to(pix.device)
+                dev_pix.index_copy_(1, batch["idx"].to(pix.device, torch.long), pix)
                 if self.iter_count >= self.config["num_iters"]:
                     break
-                if self.iter_count % self.config["print_frequency"] == 0 and self.rank == 0:
-                    line = f"{self.iter_count}/{self.config['num_iters']} | Loss: {sum(running) / len(running):.5f}"
-                    print(line + max(0, last_len - len(line)) * " ", end="\r")
-                    last_len = len(line)
+                if self.iter_count % self.config["print_frequency"] == 0:
+                    flush_losses()
+                    if self.rank == 0:
+                        line = f"{self.iter_count}/{self.config['num_iters']} | Loss: {sum(running) / len(running):.5f}"
+                        print(line + max(0, last_len - len(line)) * " ", end="\r")
+                        last_len = len(line)
+            flush_losses()
+            if dev_pix is not None:
+                host_pix = dev_pix.cpu().numpy()
+                progress.pred_pixels[:], progress.pred_pixels_surf[:], progress.pred_pixels_atmo[:] = host_pix
             self._end_of_epoch(progress, output_path, last_len)
             if prof:
                 prof.stop()
