@@ -37,7 +37,7 @@ METRICS = [
 ENTRY = {
     "k_ngp_sample_points": "atmonr_ngp_sample_points", "k_field_fwd_tc": "atmonr_ngp_field_fwd_tc",
     "k_composite_fwd": "atmonr_composite_fwd", "k_composite_bwd": "atmonr_composite_bwd",
-    "k_field_bwd_tc2": "atmonr_ngp_field_bwd_tc",
+    "k_field_bwd_tc2": "atmonr_ngp_field_bwd_tc", "k_extract_sigma_tc": "atmonr_extract_sigma_tc",
 }
 
 
@@ -57,13 +57,13 @@ def entry_of(kernel: str) -> str | None:
     return None
 
 
-def full_summary(rep: str, tag: str, cmd: str, rays: int) -> None:
+def full_summary(rep: str, tag: str, cmd: str, rays: int, write_traffic: bool = True) -> None:
     raw = subprocess.run(["ncu", "-i", rep, "--page", "raw", "--csv"], capture_output=True, text=True, check=True).stdout
     rows = list(csv.reader(io.StringIO(raw)))
     head, units, data = rows[0], rows[1], rows[2:]
     ki = head.index("Kernel Name")
     stall_cols = [i for i, c in enumerate(head) if c.startswith("smsp__pcsamp_warps_issue_stalled") and "not_issued" not in c]
-    out = [f"# ncu --set full, {tag}, bench.py default configuration (2^18 rays x 1024 samples)", "", f"`{cmd}`", "",
+    out = [f"# ncu --set full, {tag}, bench.py default configuration", "", f"`{cmd}`", "",
            "Durations under ncu are serialised, cache-flushed replays (longer than the live CUDA-event times of "
            "the bench line); counters are per launch. `stalls` = warp-state sampling split (pc sampling).", ""]
     traffic = {"rays": rays, "source": f"profiles/{tag}_ncu_full_summary.md (ncu --set full, dram__bytes_read.sum + "
@@ -89,7 +89,8 @@ def full_summary(rep: str, tag: str, cmd: str, rays: int) -> None:
                 return float(v.replace(",", "")) * scale
             traffic[ent] = {"dram_bytes_per_launch": to_bytes(*vals["dram__bytes_read.sum"]) + to_bytes(*vals["dram__bytes_write.sum"])}
     open(os.path.join(ROOT, "profiles", f"{tag}_ncu_full_summary.md"), "w").write("\n".join(out))
-    json.dump(traffic, open(os.path.join(ROOT, "profiles", "ncu_dram_traffic.json"), "w"), indent=1)
+    if write_traffic:
+        json.dump(traffic, open(os.path.join(ROOT, "profiles", "ncu_dram_traffic.json"), "w"), indent=1)
 
 
 def launch_list(path: str, tag: str, cmd: str, bench: dict | None) -> None:
@@ -134,10 +135,11 @@ def main() -> None:
     ap.add_argument("--cmd-full", default="")
     ap.add_argument("--cmd-launch", default="")
     ap.add_argument("--rays", type=int, default=1 << 18)
+    ap.add_argument("--no-traffic", action="store_true", help="do not rewrite profiles/ncu_dram_traffic.json")
     a = ap.parse_args()
     bench = json.loads(open(a.bench).read().strip().splitlines()[-1]) if a.bench else None
     if a.full:
-        full_summary(a.full, a.tag, a.cmd_full, a.rays)
+        full_summary(a.full, a.tag, a.cmd_full, a.rays, not a.no_traffic)
     if a.launches:
         launch_list(a.launches, a.tag, a.cmd_launch, bench)
     if bench:
