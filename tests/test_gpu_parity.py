@@ -596,3 +596,65 @@ def test_compact_backward_equals_dense_backward(scene, monkeypatch):
     dead = torch.ones(bb * nn, dtype=torch.bool, device=z.device)
     dead[idx] = False
     assert float(dcol.view(-1, 4)[dead].abs().max()) == 0.0 and float(dsig.view(-1)[dead].abs().max()) == 0.0
+
+
+@pytest.mark.parametrize("case", ["none-listed", "all-listed", "ragged"])
+def test_compact_backward_edge_cases(scene, case):
+    """The list is empty (every raw density <= 0: the field backward must do nothing and return),
+    holds every sample (relu == 0 lists all), or ends in the middle of a 256-row tile."""
+    L, ops = _native()
+    import ctypes as C
+    from atmonr.native import fused
+    cfg = ngp_config(64)
+    orc = NGPOracle(cfg, scene.frame, scene.max_i, fp16=True)
+    params = random_params(orc, seed=1, table_scale=2e3)
+    pipe = _pipeline(scene, cfg)
+    load_params(pipe, params)
+    b = to_cuda(take(scene.batch, slice(0, 37)))      # 37 x 64 = 2368 samples = 9.25 tiles
+    u = torch.rand(37, 64, generator=torch.Generator().manual_seed(3)).cuda()
+    out = pipe.forward(b, u=u)
+    st = pipe.fused_state
+    z, col, cs = st.last["z"], st.last["color_raw"], st.last["color_surf_raw"]
+    sig = st.last["sigma_raw"].clone()
+    relu = True
+    if case == "none-listed":
+        sig = -sig.abs() - 1e-3
+    elif case == "all-listed":
+        relu = False
+    bb, nn = z.shape
+    cmap, catmo, csurf, tsurf, _, _ = ops.composite_forward(z, col, sig, cs, st.z_scale, relu=relu, want_weights=False, want_alpha=False)
+    g = torch.randn(bb, 4, generator=torch.Generator().manual_seed(5)).cuda()
+    absmax = torch.zeros(1, device="cuda")
+    idx, n_act, dcol_c, dsig_c, _ = ops.composite_backward_compact(z, col, sig, cs, catmo, tsurf, g, g, st.z_scale, relu=relu, grad_absmax=absmax)
+    n = int(n_act)
+    assert n == {"none-listed": 0, "all-listed": bb * nn}.get(case, int((sig > 0).sum()))
+    if case == "ragged":
+        assert n % 256 != 0
+    # the field backward over the list against the dense field backward on the scattered gradients
+    x01 = st.last["x01"]
+    dense_col = torch.zeros(bb * nn, 4, device="cuda")
+    dense_sig = torch.zeros(bb * nn, device="cuda")
+    dense_col[idx[:n].long()] = dcol_c[:n]
+    dense_sig[idx[:n].long()] = dsig_c[:n, 0]
+    t16, pw16, dw16 = pipe.pos_encoder.table_f16(), pipe.pos_mlp.weights_f16(), pipe.dir_mlp.weights_f16()
+    _, _, enc = fused.field_forward(st, t16, pw16, dw16, x01, b["dir"].contiguous(), bb, nn, want_enc=True)
+    outs = {}
+    for mode in ("compact", "dense"):
+        d_t = torch.zeros(pipe.pos_encoder.params.numel(), device="cuda")
+        d_pw = torch.zeros(pipe.pos_mlp.params.numel(), device="cuda")
+        d_dw = torch.zeros(pipe.dir_mlp.params.numel(), device="cuda")
+        if mode == "compact":
+            L.call("atmonr_ngp_field_bwd_tc_compact", C.byref(st.grid3), C.byref(st.pos_mlp), L.ptr(pw16), C.byref(st.dir_mlp),
+                   L.ptr(dw16), L.ptr(x01), L.ptr(b["dir"].contiguous()), L.ptr(enc), L.ptr(idx), L.ptr(n_act), L.ptr(dsig_c),
+                   L.ptr(dcol_c), L.ptr(absmax), bb, nn, L.ptr(d_t), L.ptr(d_pw), L.ptr(d_dw), L.stream())
+        else:
+            L.call("atmonr_ngp_field_bwd_tc", C.byref(st.grid3), L.ptr(t16), C.byref(st.pos_mlp), L.ptr(pw16), C.byref(st.dir_mlp),
+                   L.ptr(dw16), L.ptr(x01), L.ptr(b["dir"].contiguous()), L.ptr(enc), L.ptr(dense_sig), L.ptr(dense_col),
+                   L.ptr(absmax), bb, nn, L.ptr(d_t), L.ptr(d_pw), L.ptr(d_dw), L.stream())
+        torch.cuda.synchronize()
+        outs[mode] = (d_t, d_pw, d_dw)
+    for a, c in zip(outs["compact"], outs["dense"]):
+        if case == "none-listed":
+            assert float(a.abs().max()) == 0.0 and float(c.abs().max()) == 0.0
+        else:
+            assert rel_err(a, c) < 1e-5
