@@ -10,6 +10,7 @@ generator (`--scene-filename synthetic:H=64,W=64,seed=0`), see datasets/granule.
 
 from __future__ import annotations
 
+import os
 from pathlib import Path
 from typing import Callable
 
@@ -205,7 +206,15 @@ class HARP2Dataset(Dataset):
         }
 
     def __getbatch__(self, idx: torch.Tensor) -> dict[str, torch.Tensor]:
+        # ATMONR_NATIVE_GATHER=1: the seven gathers in one launch (atmonr_gather_batch, csrc/rays.cu)
+        if os.environ.get("ATMONR_NATIVE_GATHER") == "1" and self.ray_origin_norm.is_cuda and torch.is_tensor(idx) \
+                and idx.dtype == torch.int64 and idx.dim() == 1:
+            return ops.gather_batch(self._ray_tables(), idx.to(self.ray_origin_norm.device))
         return self[idx]
+
+    def _ray_tables(self) -> dict[str, torch.Tensor]:
+        return {"origin": self.ray_origin_norm, "dir": self.ray_dir, "alt": self.ray_alt, "rad": self.ray_rad,
+                "len": self.ray_len_norm, "idx": self.ray_idx, "irgb_idx": self.ray_irgb_idx}
 
     def __len__(self) -> int:
         return self.ray_origin_norm.shape[0]

@@ -10,6 +10,7 @@ preprocessor) does NOT go through this module: it is fused into the sm_100a samp
 from __future__ import annotations
 
 import math
+import os
 
 import torch
 
@@ -101,7 +102,13 @@ def compose_dirs_and_surface_normals(dirs, lat, lon):
 
 def get_rays(lat, lon, alt, thetav, phiv, ray_origin_height, tol: float = 10.0, max_iters: int = 20):
     """Ray entry (top of the shell at `ray_origin_height`) and exit (surface) for every
-    pixel/view. wgs_84.py:223-290. Returns origins (P*A,3), directions (P*A,3), lengths (P*A,)."""
+    pixel/view. wgs_84.py:223-290. Returns origins (P*A,3), directions (P*A,3), lengths (P*A,).
+
+    With ATMONR_NATIVE_RAYS=1 and CUDA inputs the chunk is computed by the library's ray-setup
+    kernels (`atmonr_get_rays`, csrc/rays.cu: same dtype flow, same chunk-wide refinement loop)."""
+    if os.environ.get("ATMONR_NATIVE_RAYS") == "1" and lat.is_cuda:
+        from atmonr.native import ops
+        return ops.get_rays(lat, lon, alt, thetav, phiv, ray_origin_height, tol, max_iters)
     x, y, z = horizontal_to_cartesian(lat.double(), lon.double(), alt.double())
     surface = torch.stack([x, y, z], dim=-1).float()
     local = horizontal_coords_to_dirvecs(thetav.double(), phiv.double())

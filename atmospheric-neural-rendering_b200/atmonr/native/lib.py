@@ -57,6 +57,8 @@ SIGNATURES = {
     "atmonr_abi_version": [],
     "atmonr_last_error": [],
     "atmonr_grid_layout": [I32, I32, I32, I32, F32, GP],
+    "atmonr_get_rays": [P, P, P, P, P, I64, F32, F64, I32, P, P, P, P, C.POINTER(C.c_int), P],
+    "atmonr_gather_batch": [P, P, P, P, P, P, P, P, I64, I64, P, P, P, P, P, P, P, P, P],
     "atmonr_sample_uniform": [P, P, P, P, P, I64, I32, I32, U64, U64, P, P, P],
     "atmonr_preprocess_horizontal": [FP, P, P, I64, I32, P],
     "atmonr_ngp_sample_points": [FP, P, P, P, P, P, I64, I32, I32, U64, U64, F32, P, P, P],

@@ -83,6 +83,58 @@ def ngp_sample_points(frame, origin, direction, length, n, alt_compress, u=None,
 
 
 # ------------------------------------------------------------------------------------------
+# ray table and batch gather (dataset side of the path)
+# ------------------------------------------------------------------------------------------
+def get_rays(lat, lon, alt, thetav, phiv, ray_origin_height, tol: float = 10.0, max_iters: int = 20):
+    """wgs_84.py:223-290 for one chunk of pixels: (P,A) float32 inputs -> origins (P*A,3),
+    directions (P*A,3), lengths (P*A,), all float32. Synchronises the current stream."""
+    lat, lon, alt, thetav, phiv = (_c(t, _f32) for t in (lat, lon, alt, thetav, phiv))
+    if not (lat.shape == lon.shape == alt.shape == thetav.shape == phiv.shape):
+        raise ValueError("lat, lon, alt, thetav, phiv must share a shape")
+    n = lat.numel()
+    dev = lat.device
+    origin = torch.empty((n, 3), device=dev, dtype=_f32)
+    direction = torch.empty((n, 3), device=dev, dtype=_f32)
+    length = torch.empty((n,), device=dev, dtype=_f32)
+    work = torch.empty((2 * n + 1,), device=dev, dtype=torch.float64)
+    iters = C.c_int(0)
+    L.call("atmonr_get_rays", L.ptr(lat), L.ptr(lon), L.ptr(alt), L.ptr(thetav), L.ptr(phiv), n,
+           float(ray_origin_height), float(tol), int(max_iters), L.ptr(origin), L.ptr(direction), L.ptr(length),
+           L.ptr(work), C.byref(iters), L.stream())
+    get_rays.last_iters = iters.value
+    return origin, direction, length
+
+
+def gather_batch(tables: dict, index: torch.Tensor) -> dict:
+    """harp2.py:392-420: the per-ray tables {origin, dir, alt, rad, len, idx, irgb_idx} gathered at
+    `index` (int64, negative values count from the end) in one launch. An out-of-range index raises
+    IndexError when `gather_batch.check` is set (costs a device->host read per batch); the kernel never
+    reads out of bounds either way."""
+    index = _c(index, torch.int64)
+    if index.dim() != 1:
+        raise ValueError("batch index must be 1-D")
+    b, r = index.shape[0], tables["origin"].shape[0]
+    dev = index.device
+    want = {"origin": (_f32, (r, 3)), "dir": (_f32, (r, 3)), "alt": (_f32, (r,)), "rad": (_f32, (r,)),
+            "len": (_f32, (r,)), "idx": (torch.int32, (r,)), "irgb_idx": (torch.int64, (r,))}
+    for k, (dt, shp) in want.items():
+        t = tables[k]
+        if t.dtype != dt or tuple(t.shape) != shp or not t.is_contiguous():
+            raise L.NativeLibraryError(f"gather_batch: table {k!r} must be contiguous {dt} of shape {shp}")
+    out = {k: torch.empty((b,) + shp[1:], device=dev, dtype=dt) for k, (dt, shp) in want.items()}
+    bad = torch.zeros(1, device=dev, dtype=torch.int32)
+    L.call("atmonr_gather_batch", *(L.ptr(tables[k]) for k in ("origin", "dir", "alt", "rad", "len", "idx", "irgb_idx")),
+           L.ptr(index), b, r, *(L.ptr(out[k]) for k in ("origin", "dir", "alt", "rad", "len", "idx", "irgb_idx")),
+           L.ptr(bad), L.stream())
+    if gather_batch.check and int(bad.item()):
+        raise IndexError("batch index out of range for the ray table")
+    return out
+
+
+gather_batch.check = False
+
+
+# ------------------------------------------------------------------------------------------
 # hash grid
 # ------------------------------------------------------------------------------------------
 def hashgrid_indices(grid: L.GridT, x: torch.Tensor) -> torch.Tensor:

@@ -37,6 +37,7 @@ UNITS = [
     ("field", "atmonr_b200.cu", ["-DATM_PART=2"]),
     ("surf", "atmonr_b200.cu", ["-DATM_PART=3"]),
     ("fused", "ngp_fused.cu", []),
+    ("rays", "rays.cu", []),
 ]
 
 

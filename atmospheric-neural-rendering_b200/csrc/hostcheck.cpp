@@ -3,7 +3,10 @@
 // NOT a CPU fallback: nothing in the product imports this library. The CPU test-suite uses
 // it to check, without a GPU, that the exact code the kernels execute (indexing, geodesy,
 // Philox, stratified sampling) agrees with the oracle bit for bit / within tolerance.
+#include <vector>
+
 #include "device_math.cuh"
+#include "ray_setup.cuh"
 
 template <int D>
 static void indices_impl(const atmonr_grid_t* g, const float* x, int xs, int64_t M, uint32_t* idx, float* w) {
@@ -68,6 +71,34 @@ void hc_hashgrid_indices(const atmonr_grid_t* g, const float* x, int xs, int64_t
 void hc_philox(uint64_t seed, uint64_t ray0, int64_t B, int N, float* out) {
   for (int64_t r = 0; r < B; ++r)
     for (int i = 0; i < N; ++i) out[r * N + i] = atm::philox_uniform(seed, ray0 + r, (uint32_t)i);
+}
+
+// wgs_84.py:223-290 with the loop structure of atmonr_get_rays (every ray of the call refined
+// while any ray is out of tolerance); returns the number of refinements
+int hc_get_rays(const float* lat, const float* lon, const float* alt, const float* thetav, const float* phiv,
+                int64_t n, float origin_height, double tol, int max_iters, float* origin, float* dir, float* len) {
+  std::vector<atm::RaySetup> rs(n);
+  std::vector<double> cur(n), height(n);
+  const double H = (double)origin_height;
+  bool any = false;
+  for (int64_t i = 0; i < n; ++i) {
+    atm::ray_setup(lat[i], lon[i], alt[i], thetav[i], phiv[i], origin_height, rs[i]);
+    cur[i] = rs[i].len0;
+    height[i] = atm::ray_height(rs[i], cur[i]);
+    any = any || fabs(H - height[i]) > tol;
+  }
+  int iters = 0;
+  while (iters < max_iters && any) {
+    any = false;
+    for (int64_t i = 0; i < n; ++i) {
+      cur[i] = cur[i] * H / height[i];
+      height[i] = atm::ray_height(rs[i], cur[i]);
+      any = any || fabs(H - height[i]) > tol;
+    }
+    ++iters;
+  }
+  for (int64_t i = 0; i < n; ++i) atm::ray_outputs(rs[i], cur[i], origin + 3 * i, dir + 3 * i, len[i]);
+  return iters;
 }
 
 }  // extern "C"

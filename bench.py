@@ -425,9 +425,12 @@ def run_native(args) -> None:
 
     if rank != 0:
         return
-    nerf = gpu_nerf_rate(dataset, dev)
-    cpu = None if args.no_cpu_baseline else cpu_step_rate(args.samples, args.cpu_rays, 2, 1)
-    cpu_nerf = None if args.no_cpu_baseline else cpu_nerf_rate()
+    # the NeRF line and the CPU baselines belong to the N = 1 run (rank 0 would otherwise keep the
+    # other ranks' GPUs idle for ~20 s of host work in every run of the scaling sweep)
+    solo = world == 1
+    nerf = gpu_nerf_rate(dataset, dev) if solo else None
+    cpu = cpu_step_rate(args.samples, args.cpu_rays, 2, 1) if solo and not args.no_cpu_baseline else None
+    cpu_nerf = cpu_nerf_rate() if solo and not args.no_cpu_baseline else None
     line = {
         "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": K, "warmup": W,
         "ms_per_step": ms_step, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,

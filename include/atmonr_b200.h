@@ -67,6 +67,34 @@ const char* atmonr_last_error(void);
 int atmonr_grid_layout(int n_dims, int n_levels, int log2_hashmap_size, int base_resolution,
                        float per_level_scale, atmonr_grid_t* out_host);
 
+/* ---- geospatial/wgs_84.py:223-290 get_rays (once per run, per chunk of pixels) ----------------
+ * The ray table of a granule: for each of the n = P*A pixel/view pairs (lat, lon, alt, thetav,
+ * phiv: float32, degrees / metres) the surface point, the direction from the top of the shell to
+ * the surface, and the length for which the ray's upper end lies at ray_origin_height above the
+ * ellipsoid, found by the reference's fixed point `len *= H / height(len)`: every ray of the call
+ * is refined for as long as ANY ray of the call is further than tol metres from the shell, at
+ * most max_iters times (so a call = one chunk of datasets/harp2.py:219-239). Outputs origin (n,3),
+ * dir (n,3), len (n) float32. work: (2n + 1) * 8 bytes of device scratch. The iteration count
+ * goes to *n_iters_host (may be NULL). NaN inputs give NaN rays (filtered by the caller,
+ * wgs_84.py:293-313). UNLIKE the other calls this one synchronises `stream` (it reads the
+ * convergence flag after every refinement). */
+int atmonr_get_rays(const float* lat, const float* lon, const float* alt, const float* thetav,
+                    const float* phiv, int64_t n, float ray_origin_height, double tol,
+                    int max_iters, float* origin, float* dir, float* len, void* work,
+                    int* n_iters_host, void* stream);
+
+/* ---- datasets/harp2.py:392-420 __getitem__ / __getbatch__ (every step) ----------------------
+ * The seven advanced-index gathers of a batch in one launch. Tables of R rays: origin (R,3),
+ * dir (R,3), alt (R), rad (R), len (R) float32, ray_idx (R) int32, band (R) int64 (irgb_idx);
+ * index (B) int64, negative values count from the end. alt / ray_idx and their outputs may be
+ * NULL. *bad_index (device int, zeroed by the caller) is set when an index is out of range (the
+ * entry is then read from ray 0). */
+int atmonr_gather_batch(const float* origin, const float* dir, const float* alt, const float* rad,
+                        const float* len, const int32_t* ray_idx, const int64_t* band,
+                        const int64_t* index, int64_t B, int64_t R, float* out_origin,
+                        float* out_dir, float* out_alt, float* out_rad, float* out_len,
+                        int32_t* out_ray_idx, int64_t* out_band, int* bad_index, void* stream);
+
 /* ---- samplers.py:8-47 sample_uniform_bins ------------------------------------------------
  * mode 0: bin mid-points (random=False); 1: uniforms read from u (B,N); 2: in-kernel Philox
  * keyed by (seed, ray_index_base + ray, bin). bins: N floats = linspace(0,1,N+1)[:-1] or NULL

@@ -54,6 +54,33 @@ def test_bad_arguments_report_errors():
         L.call("atmonr_grid_layout", 5, 16, 19, 16, 1.5, C.byref(g))
     with pytest.raises(L.NativeLibraryError, match="n_levels"):
         L.call("atmonr_grid_layout", 3, 17, 19, 16, 1.5, C.byref(g))
+    # argument checks of the dataset-side entry points happen before any CUDA call
+    with pytest.raises(L.NativeLibraryError, match="atmonr_get_rays: null pointer"):
+        L.call("atmonr_get_rays", None, None, None, None, None, 4, 20000.0, 10.0, 20, None, None, None, None, None, None)
+    with pytest.raises(L.NativeLibraryError, match="atmonr_gather_batch"):
+        L.call("atmonr_gather_batch", *([None] * 8), 4, 0, *([None] * 9))
+    L.call("atmonr_get_rays", None, None, None, None, None, 0, 20000.0, 10.0, 20, None, None, None, None, None, None)   # empty chunk
+    L.call("atmonr_gather_batch", *([None] * 8), 0, 10, *([None] * 9))                                                 # empty batch
+
+
+def test_native_ray_dispatch_needs_cuda_tensors(monkeypatch):
+    """ATMONR_NATIVE_RAYS only reroutes CUDA inputs; CPU tensors keep the torch expressions (dataset
+    construction without a GPU, e.g. this test-suite), and the operator itself refuses CPU tensors."""
+    from atmonr.geospatial.wgs_84 import get_rays
+    from atmonr.native import lib as L, ops
+    t = lambda v: torch.tensor([[v]], dtype=torch.float32)
+    args = (t(35.0), t(-75.0), t(0.0), t(10.0), t(0.0))
+    want = get_rays(*args, 20000.0)
+    monkeypatch.setenv("ATMONR_NATIVE_RAYS", "1")
+    got = get_rays(*args, 20000.0)
+    assert all(torch.equal(a, b) for a, b in zip(want, got))
+    with pytest.raises(L.NativeLibraryError):
+        ops.get_rays(*args, 20000.0)
+    with pytest.raises(L.NativeLibraryError):
+        ops.gather_batch({k: torch.zeros(2, 3) if k in ("origin", "dir") else torch.zeros(2, dtype=d)
+                          for k, d in (("origin", None), ("dir", None), ("alt", torch.float32), ("rad", torch.float32),
+                                       ("len", torch.float32), ("idx", torch.int32), ("irgb_idx", torch.int64))},
+                         torch.tensor([0]))
 
 
 @pytest.mark.parametrize("dims,key", [(3, "encoding"), (2, "surface_encoding"), (4, "encoding")])
@@ -208,3 +235,61 @@ def test_trainer_lookahead_pairs():
     assert list(_with_lookahead([])) == []
     assert list(_with_lookahead(["a"])) == [("a", None)]
     assert list(_with_lookahead(iter("abc"))) == [("a", "b"), ("b", "c"), ("c", None)]
+
+
+# ---------------------------------------------------------------- ray table (csrc/ray_setup.cuh)
+def _hc_get_rays(lat, lon, alt, thetav, phiv, height=20000.0, tol=10.0, max_iters=20):
+    arrs = [np.ascontiguousarray(a, dtype=np.float32).ravel() for a in (lat, lon, alt, thetav, phiv)]
+    n = arrs[0].size
+    o, d, ln = np.zeros((n, 3), np.float32), np.zeros((n, 3), np.float32), np.zeros(n, np.float32)
+    hc = _hc()
+    hc.hc_get_rays.restype = C.c_int
+    iters = hc.hc_get_rays(*map(_p, arrs), C.c_int64(n), C.c_float(height), C.c_double(tol), max_iters, _p(o), _p(d), _p(ln))
+    return o, d, ln, iters
+
+
+def test_host_build_of_ray_setup_matches_reference_vectors():
+    """The code of atmonr_get_rays (csrc/ray_setup.cuh, built for the host) against the rays the
+    REFERENCE's get_rays produced (tests/golden/reference_vectors.npz). glibc's float32/float64
+    sin/cos/atan2 are the ones torch-CPU used when the vectors were made, so the agreement is to the
+    last bit except where a fused multiply-add inside torch's matmul rounds differently."""
+    G = np.load(os.path.join(ROOT, "tests", "golden", "reference_vectors.npz"))
+    o, d, ln, iters = _hc_get_rays(G["rays_lat"], G["rays_lon"], G["rays_alt"], G["rays_thetav"], G["rays_phiv"])
+    assert 0 <= iters <= 20
+    assert np.abs(d - G["rays_dir"]).max() <= 1.2e-7          # one float32 ulp of a unit vector's component
+    assert np.abs(ln - G["rays_len"]).max() <= 4e-3           # float32 ulp at 3e4 m is 2e-3
+    assert np.abs(o - G["rays_origin"]).max() <= 0.5          # float32 ulp at 6.4e6 m is 0.5
+    assert (o == G["rays_origin"]).mean() > 0.9 and (ln == G["rays_len"]).mean() > 0.9
+
+
+def test_host_build_of_ray_setup_matches_oracle_chunk_semantics():
+    """Same, against the oracle on a HARP2-shaped chunk, including the chunk-wide refinement rule:
+    a steep view forces extra refinements that the nadir rays of the same chunk must take too."""
+    scene_rng = np.random.default_rng(3)
+    p, a = 40, 9
+    lat = (30 + 5 * scene_rng.random((p, 1)) + np.zeros((1, a))).astype(np.float32)
+    lon = (179.0 + 2 * scene_rng.random((p, 1)) + np.zeros((1, a))).astype(np.float32)   # across the dateline
+    lon = np.where(lon > 180, lon - 360, lon).astype(np.float32)
+    alt = (scene_rng.random((p, a)) * 3000).astype(np.float32)
+    thetav = np.abs(np.linspace(-60, 60, a, dtype=np.float32))[None, :] + scene_rng.random((p, a)).astype(np.float32)
+    phiv = (scene_rng.random((p, a)) * 360 - 180).astype(np.float32)
+    t = lambda x: torch.from_numpy(np.ascontiguousarray(x, dtype=np.float32))
+    for sl in (slice(None), slice(0, 1)):   # the whole chunk; one pixel alone (fewer refinements)
+        args = [x[sl] for x in (lat, lon, alt, thetav, phiv)]
+        want_o, want_d, want_l = geodesy.build_rays(*map(t, args), 20000.0)
+        o, d, ln, iters = _hc_get_rays(*args)
+        assert np.abs(d - want_d.numpy()).max() <= 1.2e-7
+        assert (np.abs(ln - want_l.numpy()) / want_l.numpy()).max() <= 4e-7   # three float32 ulps (60 degree views: 4e4 m)
+        assert np.abs(o - want_o.numpy()).max() <= 0.5
+    # the shell is reached within the tolerance: |altitude(origin) - H| <= tol (+ float32 rounding of the origin)
+    la, lo, al = geodesy.ecef_to_geodetic(*(torch.from_numpy(o.astype(np.float64))[:, k] for k in range(3)))
+    assert float((al - 20000.0).abs().max()) <= 10.0 + 1.0
+    # NaN geometry stays NaN (filtered later by filter_rays) and does not stall the loop
+    lat2 = lat.copy(); lat2[0, 0] = np.nan
+    o, d, ln, iters = _hc_get_rays(lat2, lon, alt, thetav, phiv)
+    assert np.isnan(o[0]).all() and np.isfinite(o[1:]).all() and iters <= 20
+    # max_iters = 0: the first guess is returned
+    _, _, ln0, it0 = _hc_get_rays(lat, lon, alt, thetav, phiv, max_iters=0)
+    assert it0 == 0
+    want0 = ((20000.0 - alt) / np.cos(np.deg2rad(thetav.astype(np.float64)))).ravel()
+    assert np.abs(ln0 - want0).max() <= 2e-2

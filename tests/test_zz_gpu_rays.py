@@ -1,0 +1,127 @@
+"""GPU parity of the dataset-side kernels (csrc/rays.cu): atmonr_get_rays against the oracle's
+build_rays (pinned bit for bit to the reference's get_rays) and the host build of the same code,
+atmonr_gather_batch against torch indexing (bit-exact). The file sorts last on purpose: these two
+entry points are opt-in (ATMONR_NATIVE_RAYS / ATMONR_NATIVE_GATHER) until they have been green on
+a B200 once."""
+
+import ctypes as C
+
+import numpy as np
+import pytest
+import torch
+
+from oracle import geodesy
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.fixture(scope="module", autouse=True)
+def built():
+    import __graft_entry__ as ge
+    ge.build()
+    assert torch.cuda.is_available()
+
+
+def _geometry(p=300, a=9, seed=5, dateline=False):
+    rng = np.random.default_rng(seed)
+    lat = (30 + 5 * rng.random((p, 1)) + np.zeros((1, a))).astype(np.float32)
+    lon = ((179.0 if dateline else -75.0) + 3 * rng.random((p, 1)) + np.zeros((1, a))).astype(np.float32)
+    lon = np.where(lon > 180, lon - 360, lon).astype(np.float32)
+    alt = (rng.random((p, a)) * 3000).astype(np.float32)
+    thetav = (np.abs(np.linspace(-60, 60, a, dtype=np.float32))[None, :] + rng.random((p, a))).astype(np.float32)
+    phiv = (rng.random((p, a)) * 360 - 180).astype(np.float32)
+    return [torch.from_numpy(x) for x in (lat, lon, alt, thetav, phiv)]
+
+
+@pytest.mark.parametrize("dateline", [False, True])
+def test_get_rays_matches_oracle(dateline):
+    from atmonr.native import ops
+    args = _geometry(dateline=dateline)
+    want_o, want_d, want_l = geodesy.build_rays(*args, 20000.0)
+    o, d, ln = ops.get_rays(*(t.cuda() for t in args), 20000.0)
+    assert 0 <= ops.get_rays.last_iters <= 20
+    o, d, ln = o.cpu(), d.cpu(), ln.cpu()
+    # device sin/cos/atan2 differ from glibc's in the last place: a float32 ulp or two of each output
+    assert float((d - want_d).abs().max()) <= 2.4e-7
+    assert float(((ln - want_l).abs() / want_l).max()) <= 6e-7
+    assert float((o - want_o).abs().max()) <= 1.0          # float32 ulp at 6.4e6 m is 0.5
+    assert float((o == want_o).float().mean()) > 0.5
+    # the upper end of every ray lies on the shell
+    al = geodesy.ecef_to_geodetic(*(o.double()[:, k] for k in range(3)))[2]
+    assert float((al - 20000.0).abs().max()) <= 11.0
+
+
+def test_get_rays_edge_cases():
+    from atmonr.native import ops
+    args = _geometry(p=33, a=3)
+    # empty chunk
+    e = [t[:0].cuda() for t in args]
+    o, d, ln = ops.get_rays(*e, 20000.0)
+    assert o.shape == (0, 3) and d.shape == (0, 3) and ln.shape == (0,)
+    # NaN geometry stays NaN and does not keep the chunk iterating
+    args[0][0, 0] = float("nan")
+    o, d, ln = ops.get_rays(*(t.cuda() for t in args), 20000.0)
+    assert bool(o[0].isnan().all()) and bool(o[1:].isfinite().all()) and ops.get_rays.last_iters <= 20
+    # max_iters = 0 returns the first guess; a one-ray chunk needs no more refinements than the full chunk
+    args = _geometry(p=33, a=3)
+    _, _, l0 = ops.get_rays(*(t.cuda() for t in args), 20000.0, max_iters=0)
+    assert ops.get_rays.last_iters == 0
+    want0 = (20000.0 - args[2].double()) / torch.cos(torch.deg2rad(args[3].double()))
+    assert float((l0.cpu().double() - want0.flatten()).abs().max()) <= 2e-2
+    ops.get_rays(*(t.cuda() for t in args), 20000.0)
+    full = ops.get_rays.last_iters
+    ops.get_rays(*(t[:1, :1].cuda() for t in args), 20000.0)
+    assert ops.get_rays.last_iters <= full
+
+
+def test_get_rays_dispatch_builds_the_same_dataset(monkeypatch):
+    """HARP2Dataset built with ATMONR_NATIVE_RAYS=1 against the default (torch expressions on the GPU)."""
+    import json, os
+    from helpers import ROOT
+    from atmonr.datasets.factory import get_dataset
+    cfg = json.load(open(os.path.join(ROOT, "configs", "instant_ngp.json")))["dataset"]
+    base = get_dataset(cfg, "synthetic:H=24,W=20,seed=2")
+    monkeypatch.setenv("ATMONR_NATIVE_RAYS", "1")
+    nat = get_dataset(cfg, "synthetic:H=24,W=20,seed=2")
+    assert torch.equal(base.ray_filter, nat.ray_filter)
+    assert float((base.ray_dir - nat.ray_dir).abs().max()) <= 2.4e-7
+    assert float(((base.ray_len - nat.ray_len).abs() / base.ray_len).max()) <= 6e-7
+    assert abs(base.scale - nat.scale) <= 1e-6 * base.scale
+    assert float((base.ray_origin_norm - nat.ray_origin_norm).abs().max()) <= 1e-5
+
+
+def test_gather_batch_is_bit_exact(monkeypatch):
+    import json, os
+    from helpers import ROOT
+    from atmonr.batch_loader import BatchLoader
+    from atmonr.datasets.factory import get_dataset
+    from atmonr.native import lib as L, ops
+    cfg = json.load(open(os.path.join(ROOT, "configs", "instant_ngp.json")))["dataset"]
+    ds = get_dataset(cfg, "synthetic:H=24,W=20,seed=2")
+    r = len(ds)
+    g = torch.Generator().manual_seed(0)
+    for b in (0, 1, 257, 4096):
+        idx = torch.randint(-r, r, (b,), generator=g).cuda()
+        want = ds[idx]
+        got = ops.gather_batch(ds._ray_tables(), idx)
+        assert set(got) == set(want)
+        for k in want:
+            assert got[k].dtype == want[k].dtype and got[k].shape == want[k].shape, k
+            assert torch.equal(got[k], want[k]), k
+    # out-of-range index: reported, nothing read out of bounds
+    ops.gather_batch.check = True
+    try:
+        with pytest.raises(IndexError):
+            ops.gather_batch(ds._ray_tables(), torch.tensor([0, r], device="cuda"))
+    finally:
+        ops.gather_batch.check = False
+    with pytest.raises(L.NativeLibraryError):
+        ops.gather_batch({**ds._ray_tables(), "rad": ds.ray_rad.double()}, torch.tensor([0], device="cuda"))
+    # the loader path: same batches with and without the fused gather
+    a = [b for b in BatchLoader(ds, batch_size=1000, shuffle=True, seed=3)]
+    monkeypatch.setenv("ATMONR_NATIVE_GATHER", "1")
+    c = [b for b in BatchLoader(ds, batch_size=1000, shuffle=True, seed=3)]
+    assert len(a) == len(c)
+    for x, y in zip(a, c):
+        for k in x:
+            assert torch.equal(x[k], y[k]), k
