@@ -2,12 +2,16 @@
 
 Eleven biased linear layers, width `hidden_dim`, a skip connection that re-injects the encoded
 position at layer 6, a density head on layer 9 (with unit Gaussian noise while training) and a
-direction-conditioned colour head. The layers are torch.nn.Linear (cuBLAS GEMMs -- plain library
-GEMMs; the hand-written tcgen05 path of this build targets the Instant-NGP MLPs). Parameter names
-(`fc1`..`fc11`) match the reference so checkpoints interchange.
+direction-conditioned colour head. The layers are torch.nn.Linear modules, so parameter names
+(`fc1`..`fc11`) match the reference and checkpoints interchange. By default they run as library
+float32 GEMMs; with ATMONR_NERF_TC=1 (opt-in until validated on a B200) forward and input gradient
+of every layer run on tcgen05 through `atmonr_linear_fwd_tc` (csrc/linear_tc.cu: float32 operands
+split into three bfloat16 terms, six partial products, float32 accumulation in TMEM).
 """
 
 from __future__ import annotations
+
+import os
 
 import torch
 import torch.nn as nn
@@ -28,15 +32,22 @@ class AtmoNeRF(nn.Module):
             nn.init.kaiming_normal_(layer.weight, mode="fan_out")
             setattr(self, f"fc{k}", layer)
 
+    def _layer(self, k: int, x: torch.Tensor, relu: bool) -> torch.Tensor:
+        fc = getattr(self, f"fc{k}")
+        if x.is_cuda and os.environ.get("ATMONR_NERF_TC") == "1":
+            from atmonr.native import ops
+            return ops.linear_tc(x, fc.weight, fc.bias, relu)
+        return F.relu(fc(x)) if relu else fc(x)
+
     def forward_pos_only(self, x_pos: torch.Tensor):
         """Trunk up to the density head. models/nerf.py:48-73."""
         x = x_pos
         for k in range(1, 6):
-            x = F.relu(getattr(self, f"fc{k}")(x))
-        x = F.relu(self.fc6(torch.cat([x, x_pos], dim=1)))
-        x = F.relu(self.fc7(x))
-        x = F.relu(self.fc8(x))
-        x = self.fc9(x)
+            x = self._layer(k, x, True)
+        x = self._layer(6, torch.cat([x, x_pos], dim=1), True)
+        x = self._layer(7, x, True)
+        x = self._layer(8, x, True)
+        x = self._layer(9, x, False)
         sigma = x[:, self.hidden_dim:]
         if self.training:
             sigma = sigma + torch.randn(sigma.shape, device=sigma.device)
@@ -46,8 +57,8 @@ class AtmoNeRF(nn.Module):
         """models/nerf.py:75-93 -> (colour in (0,1), density >= 0)."""
         x_pos, d = x[:, : self.pos_channels], x[:, self.pos_channels:]
         feat, sigma = self.forward_pos_only(x_pos)
-        hid = F.relu(self.fc10(torch.cat([feat[:, : self.hidden_dim], d], dim=1)))
-        return torch.sigmoid(self.fc11(hid)), sigma
+        hid = self._layer(10, torch.cat([feat[:, : self.hidden_dim], d], dim=1), True)
+        return torch.sigmoid(self._layer(11, hid, False)), sigma
 
 
 def get_model(hidden_dim: int, N_lambda: int, L_x, L_d: int, include_height: bool):

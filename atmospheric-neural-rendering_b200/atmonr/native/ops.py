@@ -135,6 +135,64 @@ gather_batch.check = False
 
 
 # ------------------------------------------------------------------------------------------
+# AtmoNeRF dense layers on tcgen05 (float32-accurate bf16x3 split), csrc/linear_tc.cu
+# ------------------------------------------------------------------------------------------
+def linear_planes_bytes(n_out: int, k_in: int) -> int:
+    """Size of the split copy of a (n_out, k_in) matrix (include/atmonr_b200.h: atmonr_linear_prep)."""
+    return -(-n_out // 256) * -(-k_in // 32) * 3 * 16384
+
+
+def linear_forward(x: torch.Tensor, weight: torch.Tensor, bias, relu: bool, transpose: bool = False) -> torch.Tensor:
+    """act(x @ B.T + bias) with B = weight (n_out, k_in), or B = weight.T when `transpose`
+    (then weight is (k_in, n_out)). x may be a column slice of a wider float32 tensor."""
+    if not (x.is_cuda and weight.is_cuda):
+        raise L.NativeLibraryError("libatmonr_b200 operates on CUDA tensors only (no CPU fallback)")
+    if x.dtype != _f32 or x.dim() != 2 or x.stride(1) != 1 or (x.shape[0] > 1 and x.stride(0) < x.shape[1]):
+        x = x.to(_f32).contiguous()
+    weight = _c(weight.detach(), _f32)
+    n_out, k_in = (weight.shape[1], weight.shape[0]) if transpose else (weight.shape[0], weight.shape[1])
+    if x.shape[1] != k_in:
+        raise ValueError(f"linear_forward: x has {x.shape[1]} columns, the matrix expects {k_in}")
+    m = x.shape[0]
+    ldx = x.stride(0) if m > 1 else max(k_in, x.stride(0))
+    planes = torch.empty(linear_planes_bytes(n_out, k_in), device=x.device, dtype=torch.uint8)
+    y = torch.empty((m, n_out), device=x.device, dtype=_f32)
+    L.call("atmonr_linear_prep", L.ptr(weight), n_out, k_in, int(transpose), L.ptr(planes), L.stream())
+    b = None if bias is None else _c(bias.detach(), _f32)
+    L.call("atmonr_linear_fwd_tc", x.data_ptr(), ldx, L.ptr(planes), L.ptr(b), m, n_out, k_in, int(relu),
+           L.ptr(y), n_out, L.stream())
+    return y
+
+
+class LinearTcFn(torch.autograd.Function):
+    """torch.nn.functional.linear (+ optional ReLU) on the tensor cores. Forward and input gradient
+    are atmonr_linear_fwd_tc products; the weight gradient dY^T X (a reduction over all rows) and the
+    bias gradient are library float32 reductions for now."""
+
+    @staticmethod
+    def forward(ctx, x, weight, bias, relu):
+        y = linear_forward(x, weight, bias, relu)
+        ctx.relu, ctx.has_bias = relu, bias is not None
+        ctx.save_for_backward(x, weight, y if relu else None)
+        return y
+
+    @staticmethod
+    def backward(ctx, dy):
+        x, weight, y = ctx.saved_tensors
+        dy = _c(dy, _f32)
+        if ctx.relu:
+            dy = dy * (y > 0)
+        dx = linear_forward(dy, weight, None, False, transpose=True) if ctx.needs_input_grad[0] else None
+        dw = dy.t() @ x if ctx.needs_input_grad[1] else None
+        db = dy.sum(dim=0) if ctx.has_bias and ctx.needs_input_grad[2] else None
+        return dx, dw, db, None
+
+
+def linear_tc(x, weight, bias=None, relu: bool = False):
+    return LinearTcFn.apply(x, weight, bias, relu)
+
+
+# ------------------------------------------------------------------------------------------
 # hash grid
 # ------------------------------------------------------------------------------------------
 def hashgrid_indices(grid: L.GridT, x: torch.Tensor) -> torch.Tensor:

@@ -38,6 +38,7 @@ UNITS = [
     ("surf", "atmonr_b200.cu", ["-DATM_PART=3"]),
     ("fused", "ngp_fused.cu", []),
     ("rays", "rays.cu", []),
+    ("linear", "linear_tc.cu", []),
 ]
 
 

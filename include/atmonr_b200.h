@@ -272,6 +272,22 @@ int atmonr_positional_encoding(const float* pts, int64_t M, int C, const int32_t
 int atmonr_sample_pdf(const float* weights, const float* z_coarse, const float* u, int64_t B,
                       int Nc, int Nf, float* z_sorted, int64_t* inds, void* stream);
 
+/* ---- AtmoNeRF dense layers (models/nerf.py:6-93: eleven biased nn.Linear) on tcgen05 -----------
+ * Y (M, n_out) = act(X (M, k_in) * B (n_out, k_in)^T + bias), float32 in and out, float32-accurate:
+ * every operand is split into three bfloat16 terms and the product is assembled from the six
+ * significant partial products on the tensor cores (float32 accumulation in TMEM).
+ * atmonr_linear_prep splits B once per step into `planes`:
+ *     ceil(n_out / 256) * ceil(k_in / 32) * 3 * 16384 bytes
+ * B = w (n_out, k_in) row-major, or, with transpose != 0, the transpose of w (k_in, n_out)
+ * row-major (the input-gradient product dX = dY * W runs atmonr_linear_fwd_tc on the planes of
+ * W^T). ldx / ldy: row strides of x / y in elements (column slices of wider tensors are fine).
+ * bias (n_out) may be NULL; act: 0 none, 1 ReLU. */
+int atmonr_linear_prep(const float* w, int n_out, int k_in, int transpose, void* planes,
+                       void* stream);
+int atmonr_linear_fwd_tc(const float* x, int64_t ldx, const void* planes, const float* bias,
+                         int64_t M, int n_out, int k_in, int act, float* y, int64_t ldy,
+                         void* stream);
+
 /* ---- tensor-core self test -------------------------------------------------------------------
  * One 128-row tile through the three tcgen05 operand configurations of the fused kernels.
  * a, b: (128, 32) fp16 row-major; d: (128, 32) float32.

@@ -293,3 +293,68 @@ def test_host_build_of_ray_setup_matches_oracle_chunk_semantics():
     assert it0 == 0
     want0 = ((20000.0 - alt) / np.cos(np.deg2rad(thetav.astype(np.float64)))).ravel()
     assert np.abs(ln0 - want0).max() <= 2e-2
+
+
+# ---------------------------------------------------------------- dense layer on tcgen05 (csrc/linear_tc.cu)
+def _bf16_round(a):
+    """float32 -> nearest-even bfloat16, returned as float32 (numpy has no bfloat16)."""
+    b = np.ascontiguousarray(a, dtype=np.float32).view(np.uint32).astype(np.uint64)
+    b = ((b + 0x7FFF + ((b >> 16) & 1)) >> 16) << 16
+    return b.astype(np.uint32).view(np.float32)
+
+
+def test_bf16_triple_split_is_float32_accurate():
+    """The arithmetic of atmonr_linear_fwd_tc, emulated: three bfloat16 terms per float32 operand,
+    the six partial products hh, hm, mh, mm, hl, lh accumulated in float32 (here float64, to isolate
+    the error of the split itself). Single-pass bf16 is ~3e-3, the six-product form float32-grade."""
+    rng = np.random.default_rng(0)
+    x = rng.standard_normal((64, 332)).astype(np.float32)
+    w = (rng.standard_normal((48, 332)) / 18).astype(np.float32)
+
+    def split(v):
+        hi = _bf16_round(v)
+        mid = _bf16_round(v - hi)
+        lo = _bf16_round(v - hi - mid)
+        assert np.all((v - hi) - mid == v - hi - mid)          # the residuals are exact in float32
+        return hi.astype(np.float64), mid.astype(np.float64), lo.astype(np.float64)
+
+    (xh, xm, xl), (wh, wm, wl) = split(x), split(w)
+    assert np.abs(x - (xh + xm + xl)).max() <= 2.0 ** -24 * np.abs(x).max()
+    want = x.astype(np.float64) @ w.astype(np.float64).T
+    six = xh @ wh.T + xh @ wm.T + xm @ wh.T + xm @ wm.T + xh @ wl.T + xl @ wh.T
+    one = xh @ wh.T
+    scale = np.abs(want).max()
+    assert np.abs(six - want).max() / scale <= 2e-7
+    assert np.abs(one - want).max() / scale >= 1e-4
+    f32 = (x @ w.T).astype(np.float64)                          # a float32 GEMM, for scale
+    assert np.abs(six - want).max() <= 4 * np.abs(f32 - want).max() + 1e-7 * scale
+
+
+def test_linear_tc_host_side():
+    from atmonr.native import lib as L, ops
+    assert ops.linear_planes_bytes(256, 256) == 8 * 3 * 16384
+    assert ops.linear_planes_bytes(257, 76) == 2 * 3 * 3 * 16384
+    assert ops.linear_planes_bytes(4, 128) == 4 * 3 * 16384
+    with pytest.raises(L.NativeLibraryError):
+        ops.linear_forward(torch.zeros(4, 8), torch.zeros(3, 8), None, False)
+    with pytest.raises(L.NativeLibraryError, match="act must be"):
+        L.call("atmonr_linear_fwd_tc", None, 8, None, None, 4, 3, 8, 2, None, 3, None)
+    with pytest.raises(L.NativeLibraryError, match="null pointer"):
+        L.call("atmonr_linear_fwd_tc", None, 8, None, None, 4, 3, 8, 0, None, 3, None)
+    with pytest.raises(L.NativeLibraryError, match="null pointer"):
+        L.call("atmonr_linear_prep", None, 3, 8, 0, None, None)
+    L.call("atmonr_linear_fwd_tc", None, 8, None, None, 0, 3, 8, 0, None, 3, None)   # no rows: nothing to do
+
+
+def test_nerf_model_default_path_is_unchanged_on_cpu(monkeypatch):
+    """ATMONR_NERF_TC only reroutes CUDA activations; the CPU model (used by nothing in the product,
+    but by this suite's shape checks) keeps its torch layers."""
+    from atmonr.models.nerf import get_model
+    torch.manual_seed(0)
+    coarse, fine = get_model(32, 4, [4, 4, 2], 2, False)
+    x = torch.rand(10, 2 * 10 + 12)
+    coarse.eval()
+    want = coarse(x)
+    monkeypatch.setenv("ATMONR_NERF_TC", "1")
+    got = coarse(x)
+    assert torch.equal(want[0], got[0]) and torch.equal(want[1], got[1])

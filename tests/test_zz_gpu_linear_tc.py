@@ -1,0 +1,112 @@
+"""GPU parity of the tcgen05 dense layer of the AtmoNeRF MLP (csrc/linear_tc.cu) against float64
+matrix products, torch autograd and the default (library GEMM) NeRF pipeline.
+
+The kernel was written after this round's GPU budget was spent and has NOT run on a B200 yet. A
+tensor-core kernel with an mbarrier pipeline can hang when a descriptor or a phase is wrong, so
+these tests only run when ATMONR_RUN_UNVERIFIED=1 (the first thing to do with a GPU: run them under
+`timeout`), and the model only uses the kernel with ATMONR_NERF_TC=1."""
+
+import os
+
+import pytest
+import torch
+
+pytestmark = [pytest.mark.gpu,
+              pytest.mark.skipif(os.environ.get("ATMONR_RUN_UNVERIFIED") != "1",
+                                 reason="linear_tc has not been validated on hardware yet (set ATMONR_RUN_UNVERIFIED=1)")]
+
+
+@pytest.fixture(scope="module", autouse=True)
+def built():
+    import __graft_entry__ as ge
+    ge.build()
+    assert torch.cuda.is_available()
+
+
+SHAPES = [  # (M, k_in, n_out, relu, bias): the layer shapes of configs/nerf.json + ragged edges
+    (300, 76, 256, True, True),      # fc1 (K tail: 76 = 2 chunks + 12)
+    (1000, 256, 256, True, True),    # fc2-5, fc7-8
+    (129, 332, 256, True, True),     # fc6 (skip connection)
+    (257, 256, 257, False, True),    # fc9 coarse: 256 + 1 outputs -> second column tile of 16
+    (64, 256, 260, False, True),     # fc9 fine
+    (500, 280, 128, True, True),     # fc10
+    (333, 128, 4, False, True),      # fc11
+    (1, 32, 16, False, False), (128, 7, 3, True, False), (4096, 256, 256, False, False),
+]
+
+
+def _ref(x, w, b, relu):
+    y = x.double() @ w.double().t() + (0 if b is None else b.double())
+    return torch.relu(y) if relu else y
+
+
+@pytest.mark.parametrize("m,k,n,relu,bias", SHAPES)
+def test_linear_forward_matches_float64(m, k, n, relu, bias):
+    from atmonr.native import ops
+    g = torch.Generator().manual_seed(m + k + n)
+    x = torch.randn(m, k, generator=g).cuda()
+    w = (torch.randn(n, k, generator=g) / k ** 0.5).cuda()
+    b = torch.randn(n, generator=g).cuda() if bias else None
+    want = _ref(x, w, b, relu)
+    got = ops.linear_forward(x, w, b, relu)
+    scale = float(want.abs().max())
+    err = float((got.double() - want).abs().max()) / scale
+    lib = float(((torch.relu(x @ w.t() + (0 if b is None else b)) if relu else x @ w.t() + (0 if b is None else b)).double() - want).abs().max()) / scale
+    assert err <= 2e-6, (err, lib)         # float32-grade: the library's float32 GEMM is at `lib`
+    # input-gradient form: dY (m, n) * W (n, k) through the planes of W^T
+    dy = torch.randn(m, n, generator=g).cuda()
+    dx = ops.linear_forward(dy, w, None, False, transpose=True)
+    want_dx = dy.double() @ w.double()
+    assert float((dx.double() - want_dx).abs().max()) / float(want_dx.abs().max()) <= 2e-6
+
+
+def test_linear_on_a_column_slice_and_autograd():
+    from atmonr.native import ops
+    g = torch.Generator().manual_seed(0)
+    wide = torch.randn(700, 100, generator=g).cuda()
+    x = wide[:, :76]                                   # models/nerf.py: x_pos = x[:, :pos_channels]
+    w = (torch.randn(256, 76, generator=g) / 9).cuda().requires_grad_()
+    b = torch.randn(256, generator=g).cuda().requires_grad_()
+    xr = x.clone().requires_grad_()
+    y = ops.linear_tc(xr, w, b, relu=True)
+    y.backward(torch.ones_like(y))
+    xd, wd, bd = (t.detach().double().requires_grad_() for t in (x, w, b))
+    yd = torch.relu(xd @ wd.t() + bd)
+    yd.backward(torch.ones_like(yd))
+    assert float((y.double() - yd).abs().max()) <= 2e-6 * float(yd.abs().max())
+    same = ops.linear_forward(x, w, b, True)           # strided input, no copy
+    assert torch.equal(same, y.detach())
+    for got, want in ((xr.grad, xd.grad), (w.grad, wd.grad), (b.grad, bd.grad)):
+        assert float((got.double() - want).abs().max()) <= 1e-5 * float(want.abs().max())
+
+
+def test_nerf_pipeline_with_tensor_core_layers(monkeypatch):
+    """configs/nerf.json forward + loss + backward with ATMONR_NERF_TC=1 against the default path:
+    same parameters, same draws (eval mode: no density noise; the sampler's Philox stream is keyed by
+    the step counter, which both runs start from zero)."""
+    import json
+    from helpers import ROOT
+    from atmonr.batch_loader import BatchLoader
+    from atmonr.datasets.factory import get_dataset
+    from atmonr.pipelines.factory import get_pipeline
+    cfg = json.load(open(os.path.join(ROOT, "configs", "nerf.json")))
+    ds = get_dataset(cfg["dataset"], "synthetic:H=12,W=12,seed=3")
+    batch = next(iter(BatchLoader(ds, batch_size=512, shuffle=True, seed=7)))
+    outs = {}
+    for mode in ("lib", "tc"):
+        monkeypatch.setenv("ATMONR_NERF_TC", "1" if mode == "tc" else "0")
+        torch.manual_seed(0)
+        pipe = get_pipeline(cfg["pipeline"], ds)
+        pipe.send_tensors_to(0)
+        pipe.eval()
+        torch.manual_seed(1)
+        res = pipe.forward(batch)
+        loss = pipe.compute_loss(batch, res)
+        loss.backward()
+        grads = torch.cat([p.grad.flatten() for net in pipe.nerf.values() for p in net.parameters()])
+        outs[mode] = (res["color_map_fine"].detach(), res["color_map_coarse"].detach(), float(loss), grads)
+    a, b = outs["lib"], outs["tc"]
+    for x, y in ((a[0], b[0]), (a[1], b[1])):
+        assert float((x - y).abs().max()) <= 1e-4 * float(x.abs().max())      # north_star: 1e-3 relative
+    assert abs(a[2] - b[2]) <= 1e-4 * abs(a[2])
+    assert float((a[3] - b[3]).abs().max()) <= 1e-3 * float(a[3].abs().max())
