@@ -142,32 +142,67 @@ def linear_planes_bytes(n_out: int, k_in: int) -> int:
     return -(-n_out // 256) * -(-k_in // 32) * 3 * 16384
 
 
-def linear_forward(x: torch.Tensor, weight: torch.Tensor, bias, relu: bool, transpose: bool = False) -> torch.Tensor:
-    """act(x @ B.T + bias) with B = weight (n_out, k_in), or B = weight.T when `transpose`
-    (then weight is (k_in, n_out)). x may be a column slice of a wider float32 tensor."""
-    if not (x.is_cuda and weight.is_cuda):
+def _rows(t: torch.Tensor):
+    """(tensor, row stride in elements) of a 2-D float32 CUDA tensor whose rows are contiguous; a
+    copy is made only when the layout does not allow that."""
+    if not t.is_cuda:
         raise L.NativeLibraryError("libatmonr_b200 operates on CUDA tensors only (no CPU fallback)")
-    if x.dtype != _f32 or x.dim() != 2 or x.stride(1) != 1 or (x.shape[0] > 1 and x.stride(0) < x.shape[1]):
-        x = x.to(_f32).contiguous()
+    if t.dtype != _f32 or t.dim() != 2 or t.stride(1) != 1 or (t.shape[0] > 1 and t.stride(0) < t.shape[1]):
+        t = t.to(_f32).contiguous()
+    return t, (t.stride(0) if t.shape[0] > 1 else max(t.shape[1], t.stride(0)))
+
+
+def linear_forward(x: torch.Tensor, weight: torch.Tensor, bias, relu: bool, transpose: bool = False,
+                   mask: torch.Tensor | None = None) -> torch.Tensor:
+    """act(x' @ B.T + bias) with B = weight (n_out, k_in), or B = weight.T when `transpose` (then
+    weight is (k_in, n_out)); x' = x, or x where mask > 0 and 0 elsewhere. x and mask may be column
+    slices of wider float32 tensors."""
+    if not weight.is_cuda:
+        raise L.NativeLibraryError("libatmonr_b200 operates on CUDA tensors only (no CPU fallback)")
+    x, ldx = _rows(x)
     weight = _c(weight.detach(), _f32)
     n_out, k_in = (weight.shape[1], weight.shape[0]) if transpose else (weight.shape[0], weight.shape[1])
     if x.shape[1] != k_in:
         raise ValueError(f"linear_forward: x has {x.shape[1]} columns, the matrix expects {k_in}")
     m = x.shape[0]
-    ldx = x.stride(0) if m > 1 else max(k_in, x.stride(0))
+    mp, ldm = None, 0
+    if mask is not None:
+        mask, ldm = _rows(mask)
+        if mask.shape != x.shape:
+            raise ValueError("linear_forward: mask and x must have the same shape")
+        mp = mask.data_ptr()
     planes = torch.empty(linear_planes_bytes(n_out, k_in), device=x.device, dtype=torch.uint8)
     y = torch.empty((m, n_out), device=x.device, dtype=_f32)
     L.call("atmonr_linear_prep", L.ptr(weight), n_out, k_in, int(transpose), L.ptr(planes), L.stream())
     b = None if bias is None else _c(bias.detach(), _f32)
-    L.call("atmonr_linear_fwd_tc", x.data_ptr(), ldx, L.ptr(planes), L.ptr(b), m, n_out, k_in, int(relu),
+    L.call("atmonr_linear_fwd_tc", x.data_ptr(), ldx, mp, ldm, L.ptr(planes), L.ptr(b), m, n_out, k_in, int(relu),
            L.ptr(y), n_out, L.stream())
     return y
 
 
+def linear_weight_grad(dy: torch.Tensor, x: torch.Tensor, mask: torch.Tensor | None = None) -> torch.Tensor:
+    """dW (n_out, k_in) = dy'.T @ x over all rows; dy' = dy where mask > 0 (mask: the layer's output)."""
+    dy, ldy = _rows(dy)
+    x, ldx = _rows(x)
+    if dy.shape[0] != x.shape[0]:
+        raise ValueError("linear_weight_grad: dy and x must have the same number of rows")
+    mp, ldm = None, 0
+    if mask is not None:
+        mask, ldm = _rows(mask)
+        if mask.shape != dy.shape:
+            raise ValueError("linear_weight_grad: mask and dy must have the same shape")
+        mp = mask.data_ptr()
+    n_out, k_in = dy.shape[1], x.shape[1]
+    dw = torch.zeros((n_out, k_in), device=x.device, dtype=_f32)
+    L.call("atmonr_linear_dw_tc", dy.data_ptr(), ldy, mp, ldm, x.data_ptr(), ldx, x.shape[0], n_out, k_in, L.ptr(dw),
+           L.stream())
+    return dw
+
+
 class LinearTcFn(torch.autograd.Function):
-    """torch.nn.functional.linear (+ optional ReLU) on the tensor cores. Forward and input gradient
-    are atmonr_linear_fwd_tc products; the weight gradient dY^T X (a reduction over all rows) and the
-    bias gradient are library float32 reductions for now."""
+    """torch.nn.functional.linear (+ optional ReLU) on the tensor cores: forward, input gradient and
+    weight gradient are tcgen05 products (the ReLU derivative is applied to the incoming gradient while
+    it is staged); the bias gradient is a column sum."""
 
     @staticmethod
     def forward(ctx, x, weight, bias, relu):
@@ -180,11 +215,11 @@ class LinearTcFn(torch.autograd.Function):
     def backward(ctx, dy):
         x, weight, y = ctx.saved_tensors
         dy = _c(dy, _f32)
-        if ctx.relu:
-            dy = dy * (y > 0)
-        dx = linear_forward(dy, weight, None, False, transpose=True) if ctx.needs_input_grad[0] else None
-        dw = dy.t() @ x if ctx.needs_input_grad[1] else None
-        db = dy.sum(dim=0) if ctx.has_bias and ctx.needs_input_grad[2] else None
+        dx = linear_forward(dy, weight, None, False, transpose=True, mask=y) if ctx.needs_input_grad[0] else None
+        dw = linear_weight_grad(dy, x, mask=y) if ctx.needs_input_grad[1] else None
+        db = None
+        if ctx.has_bias and ctx.needs_input_grad[2]:
+            db = (torch.where(y > 0, dy, torch.zeros_like(dy)) if ctx.relu else dy).sum(dim=0)
         return dx, dw, db, None
 
 

@@ -64,6 +64,28 @@ __device__ __forceinline__ void split8(const float (&v)[8], uint4& hi, uint4& mi
   }
 }
 
+// eight consecutive float32 of a row (`left` = columns left in the row; fewer than 8 -> zero fill),
+// optionally zeroed where the matching entry of `m` is not positive (the ReLU derivative of the
+// layer's output, applied while the gradient operand is staged)
+__device__ __forceinline__ void load8(const float* __restrict__ src, const float* __restrict__ m, int left, bool vec_ok,
+                                      float (&v)[8]) {
+  if (vec_ok && left >= 8) {
+    const float4 p = *reinterpret_cast<const float4*>(src), q = *reinterpret_cast<const float4*>(src + 4);
+    v[0] = p.x, v[1] = p.y, v[2] = p.z, v[3] = p.w, v[4] = q.x, v[5] = q.y, v[6] = q.z, v[7] = q.w;
+    if (m) {
+      const float4 a = *reinterpret_cast<const float4*>(m), b = *reinterpret_cast<const float4*>(m + 4);
+      const float mm[8] = {a.x, a.y, a.z, a.w, b.x, b.y, b.z, b.w};
+#pragma unroll
+      for (int j = 0; j < 8; ++j)
+        if (!(mm[j] > 0.0f)) v[j] = 0.0f;
+    }
+  } else {
+#pragma unroll
+    for (int j = 0; j < 8; ++j)
+      if (j < left) v[j] = (m && !(m[j] > 0.0f)) ? 0.0f : src[j];
+  }
+}
+
 // B (n_out, k_in) float32 row-major, or its transpose when `transpose` (then the source is
 // (k_in, n_out) row-major) -> planes[(tile * k_chunks + chunk) * 3 + plane][256 x 32 bf16, tile layout]
 __global__ void k_linear_prep(const float* __restrict__ w, int n_out, int k_in, int transpose, int k_chunks,
@@ -91,9 +113,9 @@ __global__ void k_linear_prep(const float* __restrict__ w, int n_out, int k_in, 
 }
 
 __global__ void __launch_bounds__(lin::kThreads, 1)
-k_linear_tc(const float* __restrict__ x, int64_t ldx, const uint8_t* __restrict__ planes,
-            const float* __restrict__ bias, int64_t M, int n_out, int k_in, int k_chunks, int act,
-            float* __restrict__ y, int64_t ldy) {
+k_linear_tc(const float* __restrict__ x, int64_t ldx, const float* __restrict__ mask, int64_t ldm,
+            const uint8_t* __restrict__ planes, const float* __restrict__ bias, int64_t M, int n_out, int k_in,
+            int k_chunks, int act, float* __restrict__ y, int64_t ldy) {
   extern __shared__ __align__(128) uint8_t smem[];
   uint64_t* bar = reinterpret_cast<uint64_t*>(smem + lin::kBar);          // bar[s]: MMAs that read stage s are done
   uint32_t* tmem_ptr = reinterpret_cast<uint32_t*>(smem + lin::kTmemPtr);
@@ -116,7 +138,8 @@ k_linear_tc(const float* __restrict__ x, int64_t ldx, const uint8_t* __restrict_
   const int n_cols = min(lin::kCols, ((n_out + 15) / 16) * 16 - n0);       // MMA N (multiple of 16)
   const uint32_t idesc = make_idesc_bf16(lin::kRows, n_cols);
   const uint8_t* b_src = planes + (size_t)blockIdx.y * k_chunks * 3 * lin::kBTile;
-  const bool vec_ok = (ldx & 3) == 0 && (reinterpret_cast<uintptr_t>(x) & 15) == 0;
+  const bool vec_ok = (ldx & 3) == 0 && (reinterpret_cast<uintptr_t>(x) & 15) == 0 &&
+                      (!mask || ((ldm & 3) == 0 && (reinterpret_cast<uintptr_t>(mask) & 15) == 0));
 
   for (int c = 0; c < k_chunks; ++c) {
     const int s = c & 1;
@@ -126,8 +149,9 @@ k_linear_tc(const float* __restrict__ x, int64_t ldx, const uint8_t* __restrict_
     // ---- X chunk: 128 rows x 32 columns float32 -> three bf16 planes (2 groups of 8 values per thread)
 #pragma unroll
     for (int it = 0; it < 2; ++it) {
-      const int item = tid + it * lin::kThreads;        // 512 items = 128 rows x 4 groups
-      const int r = item >> 2, cc = item & 3;
+      // a quarter warp (8 lanes) writes the 8 rows of ONE core matrix = 128 contiguous bytes of shared
+      // memory (no bank conflicts); in global memory the warp reads 8 rows x 128 contiguous bytes
+      const int r = ((warp + it * (lin::kThreads / 32)) << 3) | (tid & 7), cc = (tid >> 3) & 3;
       const int64_t row = row0 + r;
       const int k0 = c * lin::kChunk + cc * 8;
       float v[8];
@@ -135,14 +159,7 @@ k_linear_tc(const float* __restrict__ x, int64_t ldx, const uint8_t* __restrict_
       for (int j = 0; j < 8; ++j) v[j] = 0.0f;
       if (row < M) {
         const float* src = x + row * ldx + k0;
-        if (vec_ok && k0 + 8 <= k_in) {
-          const float4 p = *reinterpret_cast<const float4*>(src), q = *reinterpret_cast<const float4*>(src + 4);
-          v[0] = p.x, v[1] = p.y, v[2] = p.z, v[3] = p.w, v[4] = q.x, v[5] = q.y, v[6] = q.z, v[7] = q.w;
-        } else {
-#pragma unroll
-          for (int j = 0; j < 8; ++j)
-            if (k0 + j < k_in) v[j] = src[j];
-        }
+        load8(src, mask ? mask + row * ldm + k0 : nullptr, k_in - k0, vec_ok, v);
       }
       uint4 hi, mid, lo;
       split8(v, hi, mid, lo);
@@ -215,6 +232,141 @@ k_linear_tc(const float* __restrict__ x, int64_t ldx, const uint8_t* __restrict_
   if (warp == 0) tmem_dealloc<lin::kTmemCols>(acc);
 }
 
+// =========================================================================================
+// weight gradient: dW[n_out, k_in] += sum over rows m of dY[m, n_out] * X[m, k_in]
+// =========================================================================================
+// The reduction runs over the ROWS, so both operands are read MN-major straight from their
+// row-major chunks (32 rows per stage; tc_common.cuh: the same bytes serve both views). A CTA owns a
+// contiguous slab of rows, accumulates a 256 x 256 block of dW in TMEM (two M = 128 accumulators,
+// all 512 columns) and adds it to dW with float32 REDs at the end; grid.y / grid.z walk wider
+// layers in blocks of 256 (fc9: n_out = 256 + V, fc6: k_in = 256 + 76). Same six-product bf16
+// split as the forward; the ReLU derivative is applied to dY while it is staged (`mask` = the
+// layer's output).
+namespace ldw {
+constexpr int kChunk = 32;                         // rows per stage (the MMA K dimension)
+constexpr int kWide = 256;                         // columns of a staged operand block
+constexpr int kThreads = 256;
+constexpr int kTile = kChunk * kWide * 2;          // 16 KB: one bf16 plane of one operand
+constexpr int kStage = 6 * kTile;                  // 96 KB
+constexpr int kBar = 2 * kStage;
+constexpr int kTmemPtr = kBar + 16;
+constexpr int kBytes = kTmemPtr + 16;
+constexpr uint32_t kTmemCols = 512;
+}  // namespace ldw
+
+// rows [row_lo, row_lo + 32) x columns [c0, c0 + 256) of a row-major float32 matrix -> three bf16
+// planes in the [32][256] tile layout (zero outside the matrix)
+__device__ __forceinline__ void stage_rows(const float* __restrict__ src, int64_t ld, const float* __restrict__ mask,
+                                           int64_t ldm, int64_t row_lo, int64_t M, int c0, int cols, bool vec_ok,
+                                           uint8_t* tile, int tid) {
+  const int warp = tid >> 5, lane = tid & 31;
+#pragma unroll
+  for (int it = 0; it < 4; ++it) {
+    const int wi = warp + it * (ldw::kThreads / 32);             // 32 warp items: 4 row groups x 8 column blocks
+    const int r = ((wi >> 3) << 3) | (lane & 7), cc = ((wi & 7) << 2) | (lane >> 3);
+    const int64_t row = row_lo + r;
+    const int k0 = c0 + cc * 8;
+    float v[8];
+#pragma unroll
+    for (int j = 0; j < 8; ++j) v[j] = 0.0f;
+    if (row < M && k0 < cols) load8(src + row * ld + k0, mask ? mask + row * ldm + k0 : nullptr, cols - k0, vec_ok, v);
+    uint4 hi, mid, lo;
+    split8(v, hi, mid, lo);
+    st_chunk(tile, r, cc, ldw::kWide, hi);
+    st_chunk(tile + ldw::kTile, r, cc, ldw::kWide, mid);
+    st_chunk(tile + 2 * ldw::kTile, r, cc, ldw::kWide, lo);
+  }
+}
+
+__global__ void __launch_bounds__(ldw::kThreads, 1)
+k_linear_dw_tc(const float* __restrict__ dy, int64_t ldy, const float* __restrict__ mask, int64_t ldm,
+               const float* __restrict__ x, int64_t ldx, int64_t M, int n_out, int k_in, float* __restrict__ dw) {
+  extern __shared__ __align__(128) uint8_t smem[];
+  uint64_t* bar = reinterpret_cast<uint64_t*>(smem + ldw::kBar);
+  uint32_t* tmem_ptr = reinterpret_cast<uint32_t*>(smem + ldw::kTmemPtr);
+  const int tid = threadIdx.x, warp = tid >> 5;
+  // this CTA's slab of 32-row chunks
+  const int64_t chunks = (M + ldw::kChunk - 1) / ldw::kChunk;
+  const int64_t per = (chunks + gridDim.x - 1) / gridDim.x;
+  const int64_t c_lo = (int64_t)blockIdx.x * per, c_hi = min(chunks, c_lo + per);
+  if (c_lo >= c_hi) return;                                      // uniform: nothing allocated yet
+  if (warp == 0) tmem_alloc<ldw::kTmemCols>(tmem_ptr);
+  if (tid == 0) {
+    mbar_init(bar, 1);
+    mbar_init(bar + 1, 1);
+    fence_mbar_init();
+  }
+  fence_async_smem();
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t acc = *tmem_ptr;
+  const uint32_t sbase = smem_u32(smem);
+  const int n0 = blockIdx.y * ldw::kWide, k0 = blockIdx.z * ldw::kWide;     // block of dW owned by this CTA
+  const int m_halves = (min(n_out - n0, ldw::kWide) + 127) / 128;           // M = 128 accumulators in use
+  const int n_cols = min(ldw::kWide, ((k_in - k0 + 15) / 16) * 16);         // MMA N
+  const uint32_t idesc = make_idesc_bf16(128, n_cols) | (1u << 15) | (1u << 16);   // A and B MN-major
+  const bool vy = (ldy & 3) == 0 && (reinterpret_cast<uintptr_t>(dy) & 15) == 0 &&
+                  (!mask || ((ldm & 3) == 0 && (reinterpret_cast<uintptr_t>(mask) & 15) == 0));
+  const bool vx = (ldx & 3) == 0 && (reinterpret_cast<uintptr_t>(x) & 15) == 0;
+
+  int it = 0;
+  for (int64_t c = c_lo; c < c_hi; ++c, ++it) {
+    const int s = it & 1;
+    uint8_t* stage = smem + s * ldw::kStage;
+    if (it >= 2) mbar_wait(bar + s, (uint32_t)(((it >> 1) - 1) & 1));
+    stage_rows(dy, ldy, mask, ldm, c * ldw::kChunk, M, n0, n_out, vy, stage, tid);
+    stage_rows(x, ldx, nullptr, 0, c * ldw::kChunk, M, k0, k_in, vx, stage + 3 * ldw::kTile, tid);
+    fence_async_smem();
+    tc_fence_before();
+    __syncthreads();
+    if (warp == 0) {
+      tc_fence_after();
+      const uint32_t a0 = sbase + s * ldw::kStage, b0 = a0 + 3 * ldw::kTile;
+      const int pa[6] = {0, 0, 1, 1, 0, 2}, pb[6] = {0, 1, 0, 1, 2, 0};
+      for (int h = 0; h < m_halves; ++h) {
+#pragma unroll
+        for (int k = 0; k < ldw::kChunk / 16; ++k) {
+#pragma unroll
+          for (int t = 0; t < 6; ++t) {
+            // two 8-row groups per K step; columns 128 h .. of dY are 16 h core matrices further on
+            const uint32_t koff = k * 2 * (ldw::kWide / 8) * kCore;
+            const uint64_t ad = desc_mn_major(a0 + pa[t] * ldw::kTile + koff + h * 16 * kCore, ldw::kWide);
+            const uint64_t bd = desc_mn_major(b0 + pb[t] * ldw::kTile + koff, ldw::kWide);
+            umma_f16(acc + h * 256, ad, bd, idesc, (it | k | t) != 0 ? 1u : 0u);
+          }
+        }
+      }
+      umma_commit(bar + s);
+    }
+  }
+  {
+    const int last = it - 1;
+    mbar_wait(bar + (last & 1), (uint32_t)((last >> 1) & 1));
+    tc_fence_after();
+  }
+  // ---- epilogue: accumulator h, lane = row (n_out index), columns = k_in index
+  for (int h = 0; h < m_halves; ++h) {
+    const int n = n0 + h * 128 + (warp & 3) * 32 + (tid & 31);
+    const int col_lo = (warp >> 2) * 128;
+#pragma unroll 1
+    for (int cb = 0; cb < 128; cb += 16) {
+      const int col = col_lo + cb;
+      if (col >= n_cols) break;                                  // warp-uniform
+      float v[16];
+      tmem_ld16(tmem_addr(acc, warp, h * 256 + col), v);
+      if (n < n_out) {
+#pragma unroll
+        for (int j = 0; j < 16; ++j)
+          if (k0 + col + j < k_in) atomicAdd(dw + (size_t)n * k_in + k0 + col + j, v[j]);
+      }
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 0) tmem_dealloc<ldw::kTmemCols>(acc);
+}
+
 }  // namespace atm
 
 using namespace atm;
@@ -233,21 +385,44 @@ int atmonr_linear_prep(const float* w, int n_out, int k_in, int transpose, void*
   return 0;
 }
 
-int atmonr_linear_fwd_tc(const float* x, int64_t ldx, const void* planes, const float* bias, int64_t M, int n_out,
-                         int k_in, int act, float* y, int64_t ldy, void* stream) {
+int atmonr_linear_fwd_tc(const float* x, int64_t ldx, const float* mask, int64_t ldm, const void* planes,
+                         const float* bias, int64_t M, int n_out, int k_in, int act, float* y, int64_t ldy,
+                         void* stream) {
   ATM_REQUIRE(M >= 0 && n_out > 0 && k_in > 0, "atmonr_linear_fwd_tc", "bad shape");
   ATM_REQUIRE(act == 0 || act == 1, "atmonr_linear_fwd_tc", "act must be 0 (none) or 1 (ReLU)");
   if (M == 0) return 0;
   ATM_REQUIRE(x && planes && y, "atmonr_linear_fwd_tc", "null pointer");
-  ATM_REQUIRE(ldx >= k_in && ldy >= n_out, "atmonr_linear_fwd_tc", "row stride smaller than the row");
+  ATM_REQUIRE(ldx >= k_in && ldy >= n_out && (!mask || ldm >= k_in), "atmonr_linear_fwd_tc", "row stride smaller than the row");
   ATM_REQUIRE((M + lin::kRows - 1) / lin::kRows < (1ll << 31), "atmonr_linear_fwd_tc", "too many rows");
   cudaError_t e = cudaFuncSetAttribute(k_linear_tc, cudaFuncAttributeMaxDynamicSharedMemorySize, lin::kBytes);
   if (e != cudaSuccess) return fail("atmonr_linear_fwd_tc", cudaGetErrorString(e));
   const int n_tiles = (n_out + lin::kCols - 1) / lin::kCols, k_chunks = (k_in + lin::kChunk - 1) / lin::kChunk;
   dim3 grid((unsigned)((M + lin::kRows - 1) / lin::kRows), (unsigned)n_tiles);
-  k_linear_tc<<<grid, lin::kThreads, lin::kBytes, S(stream)>>>(x, ldx, reinterpret_cast<const uint8_t*>(planes), bias, M,
-                                                               n_out, k_in, k_chunks, act, y, ldy);
+  k_linear_tc<<<grid, lin::kThreads, lin::kBytes, S(stream)>>>(x, ldx, mask, ldm, reinterpret_cast<const uint8_t*>(planes),
+                                                               bias, M, n_out, k_in, k_chunks, act, y, ldy);
   ATM_CHECK_LAUNCH("atmonr_linear_fwd_tc");
+  return 0;
+}
+
+int atmonr_linear_dw_tc(const float* dy, int64_t ldy, const float* mask, int64_t ldm, const float* x, int64_t ldx,
+                        int64_t M, int n_out, int k_in, float* dw, void* stream) {
+  ATM_REQUIRE(M >= 0 && n_out > 0 && k_in > 0, "atmonr_linear_dw_tc", "bad shape");
+  if (M == 0) return 0;
+  ATM_REQUIRE(dy && x && dw, "atmonr_linear_dw_tc", "null pointer");
+  ATM_REQUIRE(ldy >= n_out && ldx >= k_in && (!mask || ldm >= n_out), "atmonr_linear_dw_tc", "row stride smaller than the row");
+  cudaError_t e = cudaFuncSetAttribute(k_linear_dw_tc, cudaFuncAttributeMaxDynamicSharedMemorySize, ldw::kBytes);
+  if (e != cudaSuccess) return fail("atmonr_linear_dw_tc", cudaGetErrorString(e));
+  int dev = 0, sms = 0;
+  if (cudaGetDevice(&dev) != cudaSuccess || cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess)
+    return fail("atmonr_linear_dw_tc", "cannot query the device");
+  const int ny = (n_out + ldw::kWide - 1) / ldw::kWide, nz = (k_in + ldw::kWide - 1) / ldw::kWide;
+  const int64_t chunks = (M + ldw::kChunk - 1) / ldw::kChunk;
+  int64_t slabs = sms / (ny * nz);           // one CTA per SM over all blocks of dW
+  if (slabs < 1) slabs = 1;
+  if (slabs > chunks) slabs = chunks;
+  dim3 grid((unsigned)slabs, (unsigned)ny, (unsigned)nz);
+  k_linear_dw_tc<<<grid, ldw::kThreads, ldw::kBytes, S(stream)>>>(dy, ldy, mask, ldm, x, ldx, M, n_out, k_in, dw);
+  ATM_CHECK_LAUNCH("atmonr_linear_dw_tc");
   return 0;
 }
 

@@ -273,20 +273,28 @@ int atmonr_sample_pdf(const float* weights, const float* z_coarse, const float* 
                       int Nc, int Nf, float* z_sorted, int64_t* inds, void* stream);
 
 /* ---- AtmoNeRF dense layers (models/nerf.py:6-93: eleven biased nn.Linear) on tcgen05 -----------
- * Y (M, n_out) = act(X (M, k_in) * B (n_out, k_in)^T + bias), float32 in and out, float32-accurate:
- * every operand is split into three bfloat16 terms and the product is assembled from the six
- * significant partial products on the tensor cores (float32 accumulation in TMEM).
- * atmonr_linear_prep splits B once per step into `planes`:
- *     ceil(n_out / 256) * ceil(k_in / 32) * 3 * 16384 bytes
- * B = w (n_out, k_in) row-major, or, with transpose != 0, the transpose of w (k_in, n_out)
- * row-major (the input-gradient product dX = dY * W runs atmonr_linear_fwd_tc on the planes of
- * W^T). ldx / ldy: row strides of x / y in elements (column slices of wider tensors are fine).
- * bias (n_out) may be NULL; act: 0 none, 1 ReLU. */
+ * Float32 in and out, float32-accurate: every operand is split into three bfloat16 terms and each
+ * product is assembled from the six significant partial products on the tensor cores (float32
+ * accumulation in TMEM). ld*: row strides in elements (column slices of wider tensors are fine).
+ *
+ * atmonr_linear_fwd_tc:  Y (M, n_out) = act(X' (M, k_in) * B (n_out, k_in)^T + bias)
+ *   X' = X, or, with mask != NULL, X where mask (M, k_in) > 0 and 0 elsewhere (the ReLU
+ *   derivative of a layer's output applied to the incoming gradient while it is staged).
+ *   B is given as `planes`, produced once per step by atmonr_linear_prep from w (n_out, k_in)
+ *   row-major, or, with transpose != 0, from the transpose of w (k_in, n_out) row-major (the
+ *   input-gradient product dX = dY * W is this call on the planes of W^T). planes:
+ *       ceil(n_out / 256) * ceil(k_in / 32) * 3 * 16384 bytes.
+ *   bias (n_out) may be NULL; act: 0 none, 1 ReLU.
+ * atmonr_linear_dw_tc:   dW (n_out, k_in) += dY' (M, n_out)^T * X (M, k_in)   (dW contiguous,
+ *   zeroed or pre-loaded by the caller; mask (M, n_out) as above, applied to dY). */
 int atmonr_linear_prep(const float* w, int n_out, int k_in, int transpose, void* planes,
                        void* stream);
-int atmonr_linear_fwd_tc(const float* x, int64_t ldx, const void* planes, const float* bias,
-                         int64_t M, int n_out, int k_in, int act, float* y, int64_t ldy,
-                         void* stream);
+int atmonr_linear_fwd_tc(const float* x, int64_t ldx, const float* mask, int64_t ldm,
+                         const void* planes, const float* bias, int64_t M, int n_out, int k_in,
+                         int act, float* y, int64_t ldy, void* stream);
+int atmonr_linear_dw_tc(const float* dy, int64_t ldy, const float* mask, int64_t ldm,
+                        const float* x, int64_t ldx, int64_t M, int n_out, int k_in, float* dw,
+                        void* stream);
 
 /* ---- tensor-core self test -------------------------------------------------------------------
  * One 128-row tile through the three tcgen05 operand configurations of the fused kernels.

@@ -32,6 +32,7 @@ SHAPES = [  # (M, k_in, n_out, relu, bias): the layer shapes of configs/nerf.jso
     (500, 280, 128, True, True),     # fc10
     (333, 128, 4, False, True),      # fc11
     (1, 32, 16, False, False), (128, 7, 3, True, False), (4096, 256, 256, False, False),
+    (40000, 332, 260, True, True),   # more 32-row chunks than SMs: several chunks per CTA in the weight gradient
 ]
 
 
@@ -58,6 +59,16 @@ def test_linear_forward_matches_float64(m, k, n, relu, bias):
     dx = ops.linear_forward(dy, w, None, False, transpose=True)
     want_dx = dy.double() @ w.double()
     assert float((dx.double() - want_dx).abs().max()) / float(want_dx.abs().max()) <= 2e-6
+    # the same with the ReLU derivative of the layer's output applied while dY is staged
+    keep = (got > 0) if relu else torch.ones_like(got, dtype=torch.bool)
+    dx = ops.linear_forward(dy, w, None, False, transpose=True, mask=got if relu else None)
+    want_dx = (dy * keep).double() @ w.double()
+    assert float((dx.double() - want_dx).abs().max()) / float(want_dx.abs().max() + 1e-30) <= 2e-6
+    # weight gradient: a reduction over all rows (split over the CTAs, float32 REDs at the end)
+    dw = ops.linear_weight_grad(dy, x, mask=got if relu else None)
+    want_dw = (dy * keep).double().t() @ x.double()
+    assert dw.shape == (n, k)
+    assert float((dw.double() - want_dw).abs().max()) / float(want_dw.abs().max() + 1e-30) <= 4e-6
 
 
 def test_linear_on_a_column_slice_and_autograd():
