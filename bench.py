@@ -207,7 +207,9 @@ def gpu_nerf_rate(dataset, dev, rays: int = 4096, steps: int = 5) -> dict:
     torch.cuda.synchronize()
     ms = e0.elapsed_time(e1) / steps
     return {"value": rays * 1e3 / ms, "unit": UNIT, "rays_per_step": rays, "ms_per_step": ms,
-            "note": "configs/nerf.json, coarse 64 + fine 192 samples, hidden 256; MLP layers are cuBLAS fp32 GEMMs"}
+            "note": "configs/nerf.json, coarse 64 + fine 192 samples, hidden 256; MLP layers are "
+                    + ("tcgen05 bf16x3-split products (csrc/linear_tc.cu)" if os.environ.get("ATMONR_NERF_TC") == "1"
+                       else "cuBLAS fp32 GEMMs")}
 
 
 def run_reference(args) -> None:
