@@ -86,8 +86,9 @@ def test_get_rays_dispatch_builds_the_same_dataset(monkeypatch):
     assert torch.equal(base.ray_filter, nat.ray_filter)
     assert float((base.ray_dir - nat.ray_dir).abs().max()) <= 2.4e-7
     assert float(((base.ray_len - nat.ray_len).abs() / base.ray_len).max()) <= 6e-7
-    assert abs(base.scale - nat.scale) <= 1e-6 * base.scale
-    assert float((base.ray_origin_norm - nat.ray_origin_norm).abs().max()) <= 1e-5
+    # one float32 ulp of an ECEF coordinate (0.5 m) moves the bounding box by 2e-6 of its size
+    assert abs(base.scale - nat.scale) <= 1e-5 * base.scale
+    assert float((base.ray_origin_norm - nat.ray_origin_norm).abs().max()) <= 3e-5
 
 
 def test_gather_batch_is_bit_exact(monkeypatch):
