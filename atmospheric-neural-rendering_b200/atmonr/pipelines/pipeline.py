@@ -51,6 +51,14 @@ class Pipeline:
     def load_state_dict(self, state_dict: dict) -> None:
         raise NotImplementedError
 
+    def parameters(self):
+        """Every trainable tensor of the pipeline (not part of the reference interface: the
+        data-parallel launchers broadcast rank 0's initial values through it)."""
+        for name in getattr(self, "module_names", []):
+            yield from getattr(self, name).parameters()
+        for net in getattr(self, "nerf", {}).values():
+            yield from net.parameters()
+
     def train(self) -> None:
         raise NotImplementedError
 

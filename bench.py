@@ -253,7 +253,7 @@ def run_native(args) -> None:
     dataset = get_dataset(cfg["dataset"], args.granule)
     pipe = get_pipeline(cfg["pipeline"], dataset)
     pipe.send_tensors_to(local)
-    dist.broadcast_parameters(p for name in pipe.module_names for p in getattr(pipe, name).parameters())
+    dist.broadcast_parameters(pipe.parameters())
     opt = pipe.get_optimizer(OPT_CFG)
     B, K, W = args.rays, args.steps, args.warmup
 

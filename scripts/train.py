@@ -60,7 +60,7 @@ def main() -> None:
     pipeline = get_pipeline(config["pipeline"], dataset)
     pipeline.send_tensors_to(device)
     if world > 1:
-        dist.broadcast_parameters(p for m in getattr(pipeline, "module_names", []) for p in getattr(pipeline, m).parameters())
+        dist.broadcast_parameters(pipeline.parameters())
     trainer = Trainer(config["trainer"], dataset, pipeline, args.exp_name)
     if args.resume:
         trainer.load(output_path)

@@ -45,7 +45,22 @@ def _worker(rank, world, port, out):
     loss = ((p[0] * first["x"] + p[1]) ** 2).mean()
     loss.backward()
     dist.all_reduce_gradients(opt)
-    torch.save({"seen": seen, "grad": p.grad.clone(), "first": first["idx"].clone()}, out.format(rank))
+    # rank 0's initial parameters reach every rank, for both pipeline families (the NeRF nets are plain
+    # torch modules, so this part of the launcher logic runs on CPU)
+    sys.path.insert(0, os.path.join(root, "tests"))
+    sys.path.insert(0, root)
+    from helpers import FakeDataset, tiny_scene
+    import json
+    from atmonr.pipelines.factory import get_pipeline
+    torch.manual_seed(100 + rank)                      # different initial values per rank on purpose
+    cfg = json.load(open(os.path.join(root, "configs", "nerf.json")))["pipeline"]
+    cfg["mlp_hidden_dim"] = 16
+    pipe = get_pipeline(cfg, FakeDataset(tiny_scene(h=2, w=2, n_views=3)))
+    before = torch.cat([q.detach().flatten() for q in pipe.parameters()]).clone()
+    dist.broadcast_parameters(pipe.parameters())
+    after = torch.cat([q.detach().flatten() for q in pipe.parameters()]).clone()
+    torch.save({"seen": seen, "grad": p.grad.clone(), "first": first["idx"].clone(), "nerf_before": before,
+                "nerf_after": after}, out.format(rank))
     td.destroy_process_group()
 
 
@@ -64,6 +79,9 @@ def test_ray_sharding_and_gradient_allreduce(tmp_path):
     p = torch.nn.Parameter(torch.tensor([0.5, -1.5]))
     ((p[0] * x + p[1]) ** 2).mean().backward()
     assert torch.allclose(r0["grad"], p.grad, rtol=1e-5)
+    # parameter broadcast: the ranks started from different values and end with rank 0's
+    assert r0["nerf_before"].numel() > 1000 and not torch.equal(r0["nerf_before"], r1["nerf_before"])
+    assert torch.equal(r0["nerf_after"], r0["nerf_before"]) and torch.equal(r1["nerf_after"], r0["nerf_before"])
 
 
 def test_shard_slice_partitions():
