@@ -1,0 +1,47 @@
+"""More golden vectors from the REFERENCE's own code (same rules as make_golden.py: run in the build
+container only, outputs committed): the two sampler-side functions that are off the default configs
+(SURVEY 8f-4), `sample_biased_bins` and `append_heights`.
+
+    python tests/golden/make_golden_extra.py   ->   tests/golden/reference_vectors_extra.npz
+"""
+
+import sys
+from pathlib import Path
+
+import numpy as np
+import torch
+
+HERE = Path(__file__).resolve().parent
+sys.path.insert(0, str(HERE))
+from make_golden import import_reference, synthetic_geometry  # noqa: E402
+
+
+def main():
+    import_reference()
+    from atmonr import samplers
+    from atmonr.geospatial import wgs_84
+
+    out = {}
+    lat, lon, alt, thetav, phiv = synthetic_geometry()
+    origins, dirs, lens = wgs_84.get_rays(lat, lon, alt, thetav, phiv, 20000.0)
+    origins_n, scale, offset = wgs_84.normalize_rays(origins, dirs, lens)
+    batch = {"origin": origins_n[:40], "dir": dirs[:40], "len": lens[:40] / scale}
+    for tag, alpha in (("a0", 0.0), ("a35", 0.35), ("a9", 0.9)):
+        torch.manual_seed(11)
+        pts, z = samplers.sample_biased_bins(batch, 24, 20000.0, alpha)
+        out[f"bias_{tag}_pts"], out[f"bias_{tag}_z"] = pts.numpy(), z.numpy()
+    torch.manual_seed(11)
+    out["bias_u"] = torch.rand((40, 24)).numpy()          # the draws the calls above consumed
+    for k, v in batch.items():
+        out["bias_" + k] = v.numpy()
+    torch.manual_seed(12)
+    pts, _ = samplers.sample_uniform_bins(batch, n_bins=16)
+    out["ah_pts"] = pts.numpy()
+    out["ah_out"] = samplers.append_heights(pts, 20000.0, scale, offset).numpy()
+    out["ah_scale"], out["ah_offset"] = np.float64(scale), offset.numpy()
+    np.savez_compressed(HERE / "reference_vectors_extra.npz", **out)
+    print({k: v.shape for k, v in out.items()})
+
+
+if __name__ == "__main__":
+    main()

@@ -177,3 +177,34 @@ def test_nerf_pipeline_matches_reference_forward_and_grads():
     for mode in ("coarse", "fine"):  # the coarse grads include the path through sample_pdf
         close(params[mode]["fc1.weight"].grad, T(f"nerf_{mode}_grad_fc1"), rtol=1e-4, atol=1e-7)
         close(params[mode]["fc11.weight"].grad, T(f"nerf_{mode}_grad_fc11"), rtol=1e-4, atol=1e-7)
+
+
+# ---------------------------------------------------------------- off-default sampler functions
+GX = np.load(os.path.join(os.path.dirname(__file__), "golden", "reference_vectors_extra.npz"))
+TX = lambda k: torch.from_numpy(GX[k])
+
+
+@pytest.mark.parametrize("tag,alpha", [("a0", 0.0), ("a35", 0.35), ("a9", 0.9)])
+def test_sample_biased_bins_matches_reference(tag, alpha):
+    """atmonr.samplers.sample_biased_bins (a torch expression in this package: it is off both shipped
+    configs) against the reference's samplers.py:106-165 on the same CPU generator state."""
+    import sys
+    sys.path.insert(0, os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "atmospheric-neural-rendering_b200"))
+    from atmonr import samplers
+    batch = {"origin": TX("bias_origin"), "dir": TX("bias_dir"), "len": TX("bias_len")}
+    torch.manual_seed(11)
+    pts, z = samplers.sample_biased_bins(batch, 24, 20000.0, alpha)
+    close(z, TX(f"bias_{tag}_z"), rtol=2e-7)
+    close(pts, TX(f"bias_{tag}_pts"), atol=2e-7)
+    # stratification survives the warp: samples of a ray are increasing and stay inside the ray
+    assert bool((z[:, 1:] >= z[:, :-1]).all()) and bool((z <= batch["len"][:, None] * (1 + 1e-6)).all())
+
+
+def test_append_heights_matches_reference():
+    import sys
+    sys.path.insert(0, os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "atmospheric-neural-rendering_b200"))
+    from atmonr import samplers
+    got = samplers.append_heights(TX("ah_pts"), 20000.0, float(GX["ah_scale"]), TX("ah_offset"))
+    close(got, TX("ah_out"))
+    want = sampling.append_heights(TX("ah_pts"), 20000.0, float(GX["ah_scale"]), TX("ah_offset"))
+    close(want, TX("ah_out"))
