@@ -32,11 +32,14 @@ class AtmoNeRF(nn.Module):
             nn.init.kaiming_normal_(layer.weight, mode="fan_out")
             setattr(self, f"fc{k}", layer)
 
-    def _layer(self, k: int, x: torch.Tensor, relu: bool) -> torch.Tensor:
+    def _layer(self, k: int, x: torch.Tensor, relu: bool, x2: torch.Tensor | None = None) -> torch.Tensor:
+        """relu?(fc_k(cat([x, x2]))); on the tensor-core path the concatenation is never materialised."""
         fc = getattr(self, f"fc{k}")
         if x.is_cuda and os.environ.get("ATMONR_NERF_TC") == "1":
             from atmonr.native import ops
-            return ops.linear_tc(x, fc.weight, fc.bias, relu)
+            return ops.linear_tc(x, fc.weight, fc.bias, relu, x2=x2)
+        if x2 is not None:
+            x = torch.cat([x, x2], dim=1)
         return F.relu(fc(x)) if relu else fc(x)
 
     def forward_pos_only(self, x_pos: torch.Tensor):
@@ -44,7 +47,7 @@ class AtmoNeRF(nn.Module):
         x = x_pos
         for k in range(1, 6):
             x = self._layer(k, x, True)
-        x = self._layer(6, torch.cat([x, x_pos], dim=1), True)
+        x = self._layer(6, x, True, x2=x_pos)
         x = self._layer(7, x, True)
         x = self._layer(8, x, True)
         x = self._layer(9, x, False)
@@ -57,7 +60,7 @@ class AtmoNeRF(nn.Module):
         """models/nerf.py:75-93 -> (colour in (0,1), density >= 0)."""
         x_pos, d = x[:, : self.pos_channels], x[:, self.pos_channels:]
         feat, sigma = self.forward_pos_only(x_pos)
-        hid = self._layer(10, torch.cat([feat[:, : self.hidden_dim], d], dim=1), True)
+        hid = self._layer(10, feat[:, : self.hidden_dim], True, x2=d)
         return torch.sigmoid(self._layer(11, hid, False)), sigma
 
 

@@ -152,38 +152,55 @@ def _rows(t: torch.Tensor):
     return t, (t.stride(0) if t.shape[0] > 1 else max(t.shape[1], t.stride(0)))
 
 
+def _segments(x: torch.Tensor, x2):
+    """(x, ldx, x2 pointer, ldx2, k_split, k_in) for an input given as one tensor or as two column
+    blocks [x | x2] that the kernels read in place (no torch.cat)."""
+    x, ldx = _rows(x)
+    if x2 is None:
+        return x, ldx, None, None, 0, x.shape[1], x.shape[1]
+    x2, ldx2 = _rows(x2)
+    if x2.shape[0] != x.shape[0]:
+        raise ValueError("the two input blocks must have the same number of rows")
+    if x.shape[1] % 8:                                   # the kernels split on a multiple of 8 columns
+        x, x2 = torch.cat([x, x2], dim=1), None
+        return x, x.stride(0), None, None, 0, x.shape[1], x.shape[1]
+    return x, ldx, x2, x2.data_ptr(), ldx2, x.shape[1], x.shape[1] + x2.shape[1]
+
+
 def linear_forward(x: torch.Tensor, weight: torch.Tensor, bias, relu: bool, transpose: bool = False,
-                   mask: torch.Tensor | None = None) -> torch.Tensor:
-    """act(x' @ B.T + bias) with B = weight (n_out, k_in), or B = weight.T when `transpose` (then
-    weight is (k_in, n_out)); x' = x, or x where mask > 0 and 0 elsewhere. x and mask may be column
-    slices of wider float32 tensors."""
+                   mask: torch.Tensor | None = None, x2: torch.Tensor | None = None) -> torch.Tensor:
+    """act(X' @ B.T + bias) with B = weight (n_out, k_in), or B = weight.T when `transpose` (then
+    weight is (k_in, n_out)); X = x or [x | x2]; X' = X where mask > 0 and 0 elsewhere when a mask is
+    given. x, x2 and mask may be column slices of wider float32 tensors."""
     if not weight.is_cuda:
         raise L.NativeLibraryError("libatmonr_b200 operates on CUDA tensors only (no CPU fallback)")
-    x, ldx = _rows(x)
+    x, ldx, x2, x2p, ldx2, k_split, k_cols = _segments(x, x2)
     weight = _c(weight.detach(), _f32)
     n_out, k_in = (weight.shape[1], weight.shape[0]) if transpose else (weight.shape[0], weight.shape[1])
-    if x.shape[1] != k_in:
-        raise ValueError(f"linear_forward: x has {x.shape[1]} columns, the matrix expects {k_in}")
+    if k_cols != k_in:
+        raise ValueError(f"linear_forward: the input has {k_cols} columns, the matrix expects {k_in}")
     m = x.shape[0]
     mp, ldm = None, 0
     if mask is not None:
         mask, ldm = _rows(mask)
-        if mask.shape != x.shape:
-            raise ValueError("linear_forward: mask and x must have the same shape")
+        if tuple(mask.shape) != (m, k_in):
+            raise ValueError("linear_forward: mask and input must have the same shape")
         mp = mask.data_ptr()
     planes = torch.empty(linear_planes_bytes(n_out, k_in), device=x.device, dtype=torch.uint8)
     y = torch.empty((m, n_out), device=x.device, dtype=_f32)
     L.call("atmonr_linear_prep", L.ptr(weight), n_out, k_in, int(transpose), L.ptr(planes), L.stream())
     b = None if bias is None else _c(bias.detach(), _f32)
-    L.call("atmonr_linear_fwd_tc", x.data_ptr(), ldx, mp, ldm, L.ptr(planes), L.ptr(b), m, n_out, k_in, int(relu),
-           L.ptr(y), n_out, L.stream())
+    L.call("atmonr_linear_fwd_tc", x.data_ptr(), ldx, x2p, ldx2, k_split, mp, ldm, L.ptr(planes), L.ptr(b), m, n_out,
+           k_in, int(relu), L.ptr(y), n_out, L.stream())
     return y
 
 
-def linear_weight_grad(dy: torch.Tensor, x: torch.Tensor, mask: torch.Tensor | None = None) -> torch.Tensor:
-    """dW (n_out, k_in) = dy'.T @ x over all rows; dy' = dy where mask > 0 (mask: the layer's output)."""
+def linear_weight_grad(dy: torch.Tensor, x: torch.Tensor, mask: torch.Tensor | None = None,
+                       x2: torch.Tensor | None = None) -> torch.Tensor:
+    """dW (n_out, k_in) = dy'.T @ X over all rows; X = x or [x | x2]; dy' = dy where mask > 0 (mask: the
+    layer's output)."""
     dy, ldy = _rows(dy)
-    x, ldx = _rows(x)
+    x, ldx, x2, x2p, ldx2, k_split, k_in = _segments(x, x2)
     if dy.shape[0] != x.shape[0]:
         raise ValueError("linear_weight_grad: dy and x must have the same number of rows")
     mp, ldm = None, 0
@@ -192,39 +209,45 @@ def linear_weight_grad(dy: torch.Tensor, x: torch.Tensor, mask: torch.Tensor | N
         if mask.shape != dy.shape:
             raise ValueError("linear_weight_grad: mask and dy must have the same shape")
         mp = mask.data_ptr()
-    n_out, k_in = dy.shape[1], x.shape[1]
+    n_out = dy.shape[1]
     dw = torch.zeros((n_out, k_in), device=x.device, dtype=_f32)
-    L.call("atmonr_linear_dw_tc", dy.data_ptr(), ldy, mp, ldm, x.data_ptr(), ldx, x.shape[0], n_out, k_in, L.ptr(dw),
-           L.stream())
+    L.call("atmonr_linear_dw_tc", dy.data_ptr(), ldy, mp, ldm, x.data_ptr(), ldx, x2p, ldx2, k_split, x.shape[0], n_out,
+           k_in, L.ptr(dw), L.stream())
     return dw
 
 
 class LinearTcFn(torch.autograd.Function):
-    """torch.nn.functional.linear (+ optional ReLU) on the tensor cores: forward, input gradient and
-    weight gradient are tcgen05 products (the ReLU derivative is applied to the incoming gradient while
-    it is staged); the bias gradient is a column sum."""
+    """torch.nn.functional.linear (+ optional ReLU) of x or of [x | x2] on the tensor cores: forward,
+    input gradient and weight gradient are tcgen05 products (the ReLU derivative is applied to the
+    incoming gradient while it is staged); the bias gradient is a column sum."""
 
     @staticmethod
-    def forward(ctx, x, weight, bias, relu):
-        y = linear_forward(x, weight, bias, relu)
-        ctx.relu, ctx.has_bias = relu, bias is not None
-        ctx.save_for_backward(x, weight, y if relu else None)
+    def forward(ctx, x, x2, weight, bias, relu):
+        y = linear_forward(x, weight, bias, relu, x2=x2)
+        ctx.relu, ctx.has_bias, ctx.k1 = relu, bias is not None, x.shape[1]
+        ctx.save_for_backward(x, x2, weight, y if relu else None)
         return y
 
     @staticmethod
     def backward(ctx, dy):
-        x, weight, y = ctx.saved_tensors
+        x, x2, weight, y = ctx.saved_tensors
         dy = _c(dy, _f32)
-        dx = linear_forward(dy, weight, None, False, transpose=True, mask=y) if ctx.needs_input_grad[0] else None
-        dw = linear_weight_grad(dy, x, mask=y) if ctx.needs_input_grad[1] else None
+        need_x = ctx.needs_input_grad[0] or (x2 is not None and ctx.needs_input_grad[1])
+        dx = linear_forward(dy, weight, None, False, transpose=True, mask=y) if need_x else None
+        dx1 = dx2 = None
+        if dx is not None:
+            dx1 = (dx if x2 is None else dx[:, : ctx.k1]) if ctx.needs_input_grad[0] else None
+            dx2 = dx[:, ctx.k1:] if (x2 is not None and ctx.needs_input_grad[1]) else None
+        dw = linear_weight_grad(dy, x, mask=y, x2=x2) if ctx.needs_input_grad[2] else None
         db = None
-        if ctx.has_bias and ctx.needs_input_grad[2]:
+        if ctx.has_bias and ctx.needs_input_grad[3]:
             db = (torch.where(y > 0, dy, torch.zeros_like(dy)) if ctx.relu else dy).sum(dim=0)
-        return dx, dw, db, None
+        return dx1, dx2, dw, db, None
 
 
-def linear_tc(x, weight, bias=None, relu: bool = False):
-    return LinearTcFn.apply(x, weight, bias, relu)
+def linear_tc(x, weight, bias=None, relu: bool = False, x2=None):
+    """relu?(cat([x, x2]) @ weight.T + bias) without materialising the concatenation."""
+    return LinearTcFn.apply(x, x2, weight, bias, relu)
 
 
 # ------------------------------------------------------------------------------------------

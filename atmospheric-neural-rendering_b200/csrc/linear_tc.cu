@@ -113,8 +113,8 @@ __global__ void k_linear_prep(const float* __restrict__ w, int n_out, int k_in, 
 }
 
 __global__ void __launch_bounds__(lin::kThreads, 1)
-k_linear_tc(const float* __restrict__ x, int64_t ldx, const float* __restrict__ mask, int64_t ldm,
-            const uint8_t* __restrict__ planes, const float* __restrict__ bias, int64_t M, int n_out, int k_in,
+k_linear_tc(const float* __restrict__ x, int64_t ldx, const float* __restrict__ x2, int64_t ldx2, int k_split,
+            const float* __restrict__ mask, int64_t ldm, const uint8_t* __restrict__ planes, const float* __restrict__ bias, int64_t M, int n_out, int k_in,
             int k_chunks, int act, float* __restrict__ y, int64_t ldy) {
   extern __shared__ __align__(128) uint8_t smem[];
   uint64_t* bar = reinterpret_cast<uint64_t*>(smem + lin::kBar);          // bar[s]: MMAs that read stage s are done
@@ -139,7 +139,8 @@ k_linear_tc(const float* __restrict__ x, int64_t ldx, const float* __restrict__ 
   const uint32_t idesc = make_idesc_bf16(lin::kRows, n_cols);
   const uint8_t* b_src = planes + (size_t)blockIdx.y * k_chunks * 3 * lin::kBTile;
   const bool vec_ok = (ldx & 3) == 0 && (reinterpret_cast<uintptr_t>(x) & 15) == 0 &&
-                      (!mask || ((ldm & 3) == 0 && (reinterpret_cast<uintptr_t>(mask) & 15) == 0));
+                      (!mask || ((ldm & 3) == 0 && (reinterpret_cast<uintptr_t>(mask) & 15) == 0)) &&
+                      (!x2 || ((ldx2 & 3) == 0 && (reinterpret_cast<uintptr_t>(x2) & 15) == 0));
 
   for (int c = 0; c < k_chunks; ++c) {
     const int s = c & 1;
@@ -158,8 +159,11 @@ k_linear_tc(const float* __restrict__ x, int64_t ldx, const float* __restrict__ 
 #pragma unroll
       for (int j = 0; j < 8; ++j) v[j] = 0.0f;
       if (row < M) {
-        const float* src = x + row * ldx + k0;
-        load8(src, mask ? mask + row * ldm + k0 : nullptr, k_in - k0, vec_ok, v);
+        // columns [0, k_split) come from x, [k_split, k_in) from x2 (k_split is a multiple of 8: a group
+        // of 8 never straddles the two)
+        const bool second = k0 >= k_split;
+        const float* src = second ? x2 + row * ldx2 + (k0 - k_split) : x + row * ldx + k0;
+        load8(src, mask ? mask + row * ldm + k0 : nullptr, (second ? k_in : k_split) - k0, vec_ok, v);
       }
       uint4 hi, mid, lo;
       split8(v, hi, mid, lo);
@@ -256,9 +260,10 @@ constexpr uint32_t kTmemCols = 512;
 
 // rows [row_lo, row_lo + 32) x columns [c0, c0 + 256) of a row-major float32 matrix -> three bf16
 // planes in the [32][256] tile layout (zero outside the matrix)
-__device__ __forceinline__ void stage_rows(const float* __restrict__ src, int64_t ld, const float* __restrict__ mask,
-                                           int64_t ldm, int64_t row_lo, int64_t M, int c0, int cols, bool vec_ok,
-                                           uint8_t* tile, int tid) {
+__device__ __forceinline__ void stage_rows(const float* __restrict__ src, int64_t ld, const float* __restrict__ src2,
+                                           int64_t ld2, int split, const float* __restrict__ mask, int64_t ldm,
+                                           int64_t row_lo, int64_t M, int c0, int cols, bool vec_ok, uint8_t* tile,
+                                           int tid) {
   const int warp = tid >> 5, lane = tid & 31;
 #pragma unroll
   for (int it = 0; it < 4; ++it) {
@@ -269,7 +274,11 @@ __device__ __forceinline__ void stage_rows(const float* __restrict__ src, int64_
     float v[8];
 #pragma unroll
     for (int j = 0; j < 8; ++j) v[j] = 0.0f;
-    if (row < M && k0 < cols) load8(src + row * ld + k0, mask ? mask + row * ldm + k0 : nullptr, cols - k0, vec_ok, v);
+    if (row < M && k0 < cols) {
+      const bool second = k0 >= split;   // columns [split, cols) live in src2
+      load8(second ? src2 + row * ld2 + (k0 - split) : src + row * ld + k0, mask ? mask + row * ldm + k0 : nullptr,
+            (second ? cols : split) - k0, vec_ok, v);
+    }
     uint4 hi, mid, lo;
     split8(v, hi, mid, lo);
     st_chunk(tile, r, cc, ldw::kWide, hi);
@@ -280,7 +289,8 @@ __device__ __forceinline__ void stage_rows(const float* __restrict__ src, int64_
 
 __global__ void __launch_bounds__(ldw::kThreads, 1)
 k_linear_dw_tc(const float* __restrict__ dy, int64_t ldy, const float* __restrict__ mask, int64_t ldm,
-               const float* __restrict__ x, int64_t ldx, int64_t M, int n_out, int k_in, float* __restrict__ dw) {
+               const float* __restrict__ x, int64_t ldx, const float* __restrict__ x2, int64_t ldx2, int k_split,
+               int64_t M, int n_out, int k_in, float* __restrict__ dw) {
   extern __shared__ __align__(128) uint8_t smem[];
   uint64_t* bar = reinterpret_cast<uint64_t*>(smem + ldw::kBar);
   uint32_t* tmem_ptr = reinterpret_cast<uint32_t*>(smem + ldw::kTmemPtr);
@@ -308,15 +318,16 @@ k_linear_dw_tc(const float* __restrict__ dy, int64_t ldy, const float* __restric
   const uint32_t idesc = make_idesc_bf16(128, n_cols) | (1u << 15) | (1u << 16);   // A and B MN-major
   const bool vy = (ldy & 3) == 0 && (reinterpret_cast<uintptr_t>(dy) & 15) == 0 &&
                   (!mask || ((ldm & 3) == 0 && (reinterpret_cast<uintptr_t>(mask) & 15) == 0));
-  const bool vx = (ldx & 3) == 0 && (reinterpret_cast<uintptr_t>(x) & 15) == 0;
+  const bool vx = (ldx & 3) == 0 && (reinterpret_cast<uintptr_t>(x) & 15) == 0 &&
+                  (!x2 || ((ldx2 & 3) == 0 && (reinterpret_cast<uintptr_t>(x2) & 15) == 0));
 
   int it = 0;
   for (int64_t c = c_lo; c < c_hi; ++c, ++it) {
     const int s = it & 1;
     uint8_t* stage = smem + s * ldw::kStage;
     if (it >= 2) mbar_wait(bar + s, (uint32_t)(((it >> 1) - 1) & 1));
-    stage_rows(dy, ldy, mask, ldm, c * ldw::kChunk, M, n0, n_out, vy, stage, tid);
-    stage_rows(x, ldx, nullptr, 0, c * ldw::kChunk, M, k0, k_in, vx, stage + 3 * ldw::kTile, tid);
+    stage_rows(dy, ldy, nullptr, 0, n_out, mask, ldm, c * ldw::kChunk, M, n0, n_out, vy, stage, tid);
+    stage_rows(x, ldx, x2, ldx2, k_split, nullptr, 0, c * ldw::kChunk, M, k0, k_in, vx, stage + 3 * ldw::kTile, tid);
     fence_async_smem();
     tc_fence_before();
     __syncthreads();
@@ -385,31 +396,41 @@ int atmonr_linear_prep(const float* w, int n_out, int k_in, int transpose, void*
   return 0;
 }
 
-int atmonr_linear_fwd_tc(const float* x, int64_t ldx, const float* mask, int64_t ldm, const void* planes,
-                         const float* bias, int64_t M, int n_out, int k_in, int act, float* y, int64_t ldy,
-                         void* stream) {
+int atmonr_linear_fwd_tc(const float* x, int64_t ldx, const float* x2, int64_t ldx2, int k_split, const float* mask,
+                         int64_t ldm, const void* planes, const float* bias, int64_t M, int n_out, int k_in, int act,
+                         float* y, int64_t ldy, void* stream) {
   ATM_REQUIRE(M >= 0 && n_out > 0 && k_in > 0, "atmonr_linear_fwd_tc", "bad shape");
   ATM_REQUIRE(act == 0 || act == 1, "atmonr_linear_fwd_tc", "act must be 0 (none) or 1 (ReLU)");
   if (M == 0) return 0;
   ATM_REQUIRE(x && planes && y, "atmonr_linear_fwd_tc", "null pointer");
-  ATM_REQUIRE(ldx >= k_in && ldy >= n_out && (!mask || ldm >= k_in), "atmonr_linear_fwd_tc", "row stride smaller than the row");
+  if (!x2) k_split = k_in;
+  ATM_REQUIRE(k_split > 0 && k_split <= k_in && (k_split == k_in || k_split % 8 == 0), "atmonr_linear_fwd_tc",
+              "k_split must be a multiple of 8 inside (0, k_in]");
+  ATM_REQUIRE(ldx >= k_split && (!x2 || ldx2 >= k_in - k_split) && ldy >= n_out && (!mask || ldm >= k_in),
+              "atmonr_linear_fwd_tc", "row stride smaller than the row");
   ATM_REQUIRE((M + lin::kRows - 1) / lin::kRows < (1ll << 31), "atmonr_linear_fwd_tc", "too many rows");
   cudaError_t e = cudaFuncSetAttribute(k_linear_tc, cudaFuncAttributeMaxDynamicSharedMemorySize, lin::kBytes);
   if (e != cudaSuccess) return fail("atmonr_linear_fwd_tc", cudaGetErrorString(e));
   const int n_tiles = (n_out + lin::kCols - 1) / lin::kCols, k_chunks = (k_in + lin::kChunk - 1) / lin::kChunk;
   dim3 grid((unsigned)((M + lin::kRows - 1) / lin::kRows), (unsigned)n_tiles);
-  k_linear_tc<<<grid, lin::kThreads, lin::kBytes, S(stream)>>>(x, ldx, mask, ldm, reinterpret_cast<const uint8_t*>(planes),
-                                                               bias, M, n_out, k_in, k_chunks, act, y, ldy);
+  k_linear_tc<<<grid, lin::kThreads, lin::kBytes, S(stream)>>>(x, ldx, x2, ldx2, k_split, mask, ldm,
+                                                               reinterpret_cast<const uint8_t*>(planes), bias, M, n_out,
+                                                               k_in, k_chunks, act, y, ldy);
   ATM_CHECK_LAUNCH("atmonr_linear_fwd_tc");
   return 0;
 }
 
 int atmonr_linear_dw_tc(const float* dy, int64_t ldy, const float* mask, int64_t ldm, const float* x, int64_t ldx,
-                        int64_t M, int n_out, int k_in, float* dw, void* stream) {
+                        const float* x2, int64_t ldx2, int k_split, int64_t M, int n_out, int k_in, float* dw,
+                        void* stream) {
   ATM_REQUIRE(M >= 0 && n_out > 0 && k_in > 0, "atmonr_linear_dw_tc", "bad shape");
   if (M == 0) return 0;
   ATM_REQUIRE(dy && x && dw, "atmonr_linear_dw_tc", "null pointer");
-  ATM_REQUIRE(ldy >= n_out && ldx >= k_in && (!mask || ldm >= n_out), "atmonr_linear_dw_tc", "row stride smaller than the row");
+  if (!x2) k_split = k_in;
+  ATM_REQUIRE(k_split > 0 && k_split <= k_in && (k_split == k_in || k_split % 8 == 0), "atmonr_linear_dw_tc",
+              "k_split must be a multiple of 8 inside (0, k_in]");
+  ATM_REQUIRE(ldy >= n_out && ldx >= k_split && (!x2 || ldx2 >= k_in - k_split) && (!mask || ldm >= n_out),
+              "atmonr_linear_dw_tc", "row stride smaller than the row");
   cudaError_t e = cudaFuncSetAttribute(k_linear_dw_tc, cudaFuncAttributeMaxDynamicSharedMemorySize, ldw::kBytes);
   if (e != cudaSuccess) return fail("atmonr_linear_dw_tc", cudaGetErrorString(e));
   int dev = 0, sms = 0;
@@ -421,7 +442,8 @@ int atmonr_linear_dw_tc(const float* dy, int64_t ldy, const float* mask, int64_t
   if (slabs < 1) slabs = 1;
   if (slabs > chunks) slabs = chunks;
   dim3 grid((unsigned)slabs, (unsigned)ny, (unsigned)nz);
-  k_linear_dw_tc<<<grid, ldw::kThreads, ldw::kBytes, S(stream)>>>(dy, ldy, mask, ldm, x, ldx, M, n_out, k_in, dw);
+  k_linear_dw_tc<<<grid, ldw::kThreads, ldw::kBytes, S(stream)>>>(dy, ldy, mask, ldm, x, ldx, x2, ldx2, k_split, M, n_out,
+                                                                  k_in, dw);
   ATM_CHECK_LAUNCH("atmonr_linear_dw_tc");
   return 0;
 }

@@ -278,6 +278,8 @@ int atmonr_sample_pdf(const float* weights, const float* z_coarse, const float* 
  * accumulation in TMEM). ld*: row strides in elements (column slices of wider tensors are fine).
  *
  * atmonr_linear_fwd_tc:  Y (M, n_out) = act(X' (M, k_in) * B (n_out, k_in)^T + bias)
+ *   X = x, or, with x2 != NULL, the concatenation [x (M, k_split) | x2 (M, k_in - k_split)] read
+ *   in place (models/nerf.py:62,86 `torch.cat([x, x_pos])`; k_split a multiple of 8).
  *   X' = X, or, with mask != NULL, X where mask (M, k_in) > 0 and 0 elsewhere (the ReLU
  *   derivative of a layer's output applied to the incoming gradient while it is staged).
  *   B is given as `planes`, produced once per step by atmonr_linear_prep from w (n_out, k_in)
@@ -286,15 +288,17 @@ int atmonr_sample_pdf(const float* weights, const float* z_coarse, const float* 
  *       ceil(n_out / 256) * ceil(k_in / 32) * 3 * 16384 bytes.
  *   bias (n_out) may be NULL; act: 0 none, 1 ReLU.
  * atmonr_linear_dw_tc:   dW (n_out, k_in) += dY' (M, n_out)^T * X (M, k_in)   (dW contiguous,
- *   zeroed or pre-loaded by the caller; mask (M, n_out) as above, applied to dY). */
+ *   zeroed or pre-loaded by the caller; mask (M, n_out) as above, applied to dY; x / x2 / k_split
+ *   as above). */
 int atmonr_linear_prep(const float* w, int n_out, int k_in, int transpose, void* planes,
                        void* stream);
-int atmonr_linear_fwd_tc(const float* x, int64_t ldx, const float* mask, int64_t ldm,
-                         const void* planes, const float* bias, int64_t M, int n_out, int k_in,
-                         int act, float* y, int64_t ldy, void* stream);
+int atmonr_linear_fwd_tc(const float* x, int64_t ldx, const float* x2, int64_t ldx2, int k_split,
+                         const float* mask, int64_t ldm, const void* planes, const float* bias,
+                         int64_t M, int n_out, int k_in, int act, float* y, int64_t ldy,
+                         void* stream);
 int atmonr_linear_dw_tc(const float* dy, int64_t ldy, const float* mask, int64_t ldm,
-                        const float* x, int64_t ldx, int64_t M, int n_out, int k_in, float* dw,
-                        void* stream);
+                        const float* x, int64_t ldx, const float* x2, int64_t ldx2, int k_split,
+                        int64_t M, int n_out, int k_in, float* dw, void* stream);
 
 /* ---- tensor-core self test -------------------------------------------------------------------
  * One 128-row tile through the three tcgen05 operand configurations of the fused kernels.

@@ -86,9 +86,10 @@ def prep(w, n_out, k_in, transpose):
     return planes
 
 
-def linear_cta(x, mask, planes, bias, M, n_out, k_in, act, bx, by, y):
+def linear_cta(x, mask, planes, bias, M, n_out, k_in, act, bx, by, y, x2=None, k_split=None):
     """One CTA of k_linear_tc."""
     k_chunks = -(-k_in // CHUNK)
+    k_split = k_in if x2 is None else k_split
     row0, n0 = bx * ROWS, by * COLS
     n_cols = min(COLS, -(-n_out // 16) * 16 - n0)
     b_src = by * k_chunks * 3 * B_TILE
@@ -105,9 +106,12 @@ def linear_cta(x, mask, planes, bias, M, n_out, k_in, act, bx, by, y):
                 row, k0 = row0 + r, c * CHUNK + cc * 8
                 v = np.zeros(8, np.float32)
                 if row < M:
+                    second = k0 >= k_split
+                    left = (k_in if second else k_split) - k0
                     for j in range(8):
-                        if j < k_in - k0:
-                            v[j] = 0.0 if (mask is not None and not mask[row, k0 + j] > 0) else x[row, k0 + j]
+                        if j < left:
+                            val = x2[row, k0 - k_split + j] if second else x[row, k0 + j]
+                            v[j] = 0.0 if (mask is not None and not mask[row, k0 + j] > 0) else val
                 hi, mid, lo = split8(v)
                 st_chunk(smem, stage, r, cc, CHUNK, hi)
                 st_chunk(smem, stage + A_TILE, r, cc, CHUNK, mid)
@@ -162,6 +166,20 @@ def test_forward_kernel_model(m, k_in, n_out, transpose, masked):
     assert np.abs(y - want).max() <= 3e-7 * np.abs(want).max()
 
 
+def test_forward_kernel_model_two_input_blocks():
+    """[x | x2] read in place (fc6: 256 + 76 columns; here 40 + 20 with a ragged tail in each block)."""
+    rng = np.random.default_rng(9)
+    m, k1, k2, n_out = 20, 40, 20, 24
+    x1 = rng.standard_normal((m, k1)).astype(np.float32)
+    x2 = rng.standard_normal((m, k2)).astype(np.float32)
+    w = rng.standard_normal((n_out, k1 + k2)).astype(np.float32)
+    planes = prep(w, n_out, k1 + k2, False)
+    y = np.full((m, n_out), np.nan)
+    linear_cta(x1, None, planes, None, m, n_out, k1 + k2, False, 0, 0, y, x2=x2, k_split=k1)
+    want = np.concatenate([x1, x2], 1).astype(np.float64) @ w.astype(np.float64).T
+    assert np.abs(y - want).max() <= 3e-7 * np.abs(want).max()
+
+
 # ------------------------------------------------------------------------------------------
 # weight-gradient kernel
 # ------------------------------------------------------------------------------------------
@@ -170,7 +188,7 @@ DW_TILE = DW_CHUNK * WIDE * 2
 DW_STAGE = 6 * DW_TILE
 
 
-def stage_rows(smem, tile, src, mask, row_lo, M, c0, cols):
+def stage_rows(smem, tile, src, mask, row_lo, M, c0, cols, src2=None, split=None):
     for tid in range(THREADS):
         warp, lane = tid >> 5, tid & 31
         for it in range(4):
@@ -180,16 +198,20 @@ def stage_rows(smem, tile, src, mask, row_lo, M, c0, cols):
             row, k0 = row_lo + r, c0 + cc * 8
             v = np.zeros(8, np.float32)
             if row < M and k0 < cols:
+                sp = cols if src2 is None else split
+                second = k0 >= sp
+                left = (cols if second else sp) - k0
                 for j in range(8):
-                    if j < cols - k0:
-                        v[j] = 0.0 if (mask is not None and not mask[row, k0 + j] > 0) else src[row, k0 + j]
+                    if j < left:
+                        val = src2[row, k0 - sp + j] if second else src[row, k0 + j]
+                        v[j] = 0.0 if (mask is not None and not mask[row, k0 + j] > 0) else val
             hi, mid, lo = split8(v)
             st_chunk(smem, tile, r, cc, WIDE, hi)
             st_chunk(smem, tile + DW_TILE, r, cc, WIDE, mid)
             st_chunk(smem, tile + 2 * DW_TILE, r, cc, WIDE, lo)
 
 
-def dw_cta(dy, mask, x, M, n_out, k_in, bx, gx, by, bz, dw):
+def dw_cta(dy, mask, x, M, n_out, k_in, bx, gx, by, bz, dw, x2=None, k_split=None):
     chunks = -(-M // DW_CHUNK)
     per = -(-chunks // gx)
     c_lo, c_hi = bx * per, min(chunks, bx * per + per)
@@ -203,7 +225,7 @@ def dw_cta(dy, mask, x, M, n_out, k_in, bx, gx, by, bz, dw):
     for it, c in enumerate(range(c_lo, c_hi)):
         stage = (it & 1) * DW_STAGE
         stage_rows(smem, stage, dy, mask, c * DW_CHUNK, M, n0, n_out)
-        stage_rows(smem, stage + 3 * DW_TILE, x, None, c * DW_CHUNK, M, k0, k_in)
+        stage_rows(smem, stage + 3 * DW_TILE, x, None, c * DW_CHUNK, M, k0, k_in, x2, k_split)
         a0, b0 = stage, stage + 3 * DW_TILE
         for h in range(m_halves):
             for k in range(DW_CHUNK // 16):
@@ -244,4 +266,18 @@ def test_weight_gradient_kernel_model(m, n_out, k_in, gx, masked):
                 dw_cta(dy, mask, x, m, n_out, k_in, bx, gx, by, bz, dw)
     dye = dy if mask is None else np.where(mask > 0, dy, 0)
     want = dye.astype(np.float64).T @ x.astype(np.float64)
+    assert np.abs(dw - want).max() <= 3e-7 * np.abs(want).max()
+
+
+def test_weight_gradient_kernel_model_two_input_blocks():
+    """X = [x | x2] with the split inside the second 256-column block (fc6: 256 + 76)."""
+    rng = np.random.default_rng(4)
+    m, n_out, k1, k2 = 40, 12, 264, 20
+    dy = rng.standard_normal((m, n_out)).astype(np.float32)
+    x1 = rng.standard_normal((m, k1)).astype(np.float32)
+    x2 = rng.standard_normal((m, k2)).astype(np.float32)
+    dw = np.zeros((n_out, k1 + k2))
+    for bz in range(2):
+        dw_cta(dy, None, x1, m, n_out, k1 + k2, 0, 1, 0, bz, dw, x2=x2, k_split=k1)
+    want = dy.astype(np.float64).T @ np.concatenate([x1, x2], 1).astype(np.float64)
     assert np.abs(dw - want).max() <= 3e-7 * np.abs(want).max()

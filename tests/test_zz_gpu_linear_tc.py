@@ -91,6 +91,28 @@ def test_linear_on_a_column_slice_and_autograd():
         assert float((got.double() - want).abs().max()) <= 1e-5 * float(want.abs().max())
 
 
+def test_linear_on_two_input_blocks():
+    """fc6 / fc10: relu(fc(cat([x, x2]))) with the concatenation read in place, forward and backward."""
+    from atmonr.native import ops
+    g = torch.Generator().manual_seed(2)
+    for k1, k2, n in ((256, 76, 256), (256, 24, 128), (20, 12, 8)):   # the last one is not a multiple of 8: cat fallback
+        feat = torch.randn(900, k1 + 4, generator=g).cuda()
+        x1 = feat[:, :k1].detach().requires_grad_()                   # a column slice, like feat[:, :hidden_dim]
+        x2 = torch.randn(900, k2, generator=g).cuda().requires_grad_()
+        w = (torch.randn(n, k1 + k2, generator=g) / 16).cuda().requires_grad_()
+        b = torch.randn(n, generator=g).cuda().requires_grad_()
+        y = ops.linear_tc(x1, w, b, relu=True, x2=x2)
+        gy = torch.randn(900, n, generator=g).cuda()
+        y.backward(gy)
+        d = [t.detach().double().requires_grad_() for t in (x1, x2, w, b)]
+        yd = torch.relu(torch.cat([d[0], d[1]], 1) @ d[2].t() + d[3])
+        yd.backward(gy.double())
+        assert float((y.double() - yd).abs().max()) <= 2e-6 * float(yd.abs().max())
+        for got, want in zip((x1.grad, x2.grad, w.grad, b.grad), (t.grad for t in d)):
+            assert got.shape == want.shape
+            assert float((got.double() - want).abs().max()) <= 1e-5 * float(want.abs().max())
+
+
 def test_nerf_pipeline_with_tensor_core_layers(monkeypatch):
     """configs/nerf.json forward + loss + backward with ATMONR_NERF_TC=1 against the default path:
     same parameters, same draws (eval mode: no density noise; the sampler's Philox stream is keyed by
