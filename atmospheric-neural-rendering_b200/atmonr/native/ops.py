@@ -196,9 +196,9 @@ def linear_forward(x: torch.Tensor, weight: torch.Tensor, bias, relu: bool, tran
 
 
 def linear_weight_grad(dy: torch.Tensor, x: torch.Tensor, mask: torch.Tensor | None = None,
-                       x2: torch.Tensor | None = None) -> torch.Tensor:
+                       x2: torch.Tensor | None = None, want_bias: bool = False):
     """dW (n_out, k_in) = dy'.T @ X over all rows; X = x or [x | x2]; dy' = dy where mask > 0 (mask: the
-    layer's output)."""
+    layer's output). With want_bias also db (n_out) = column sums of dy', from the same pass: (dW, db)."""
     dy, ldy = _rows(dy)
     x, ldx, x2, x2p, ldx2, k_split, k_in = _segments(x, x2)
     if dy.shape[0] != x.shape[0]:
@@ -211,15 +211,16 @@ def linear_weight_grad(dy: torch.Tensor, x: torch.Tensor, mask: torch.Tensor | N
         mp = mask.data_ptr()
     n_out = dy.shape[1]
     dw = torch.zeros((n_out, k_in), device=x.device, dtype=_f32)
+    db = torch.zeros((n_out,), device=x.device, dtype=_f32) if want_bias else None
     L.call("atmonr_linear_dw_tc", dy.data_ptr(), ldy, mp, ldm, x.data_ptr(), ldx, x2p, ldx2, k_split, x.shape[0], n_out,
-           k_in, L.ptr(dw), L.stream())
-    return dw
+           k_in, L.ptr(dw), L.ptr(db), L.stream())
+    return (dw, db) if want_bias else dw
 
 
 class LinearTcFn(torch.autograd.Function):
     """torch.nn.functional.linear (+ optional ReLU) of x or of [x | x2] on the tensor cores: forward,
     input gradient and weight gradient are tcgen05 products (the ReLU derivative is applied to the
-    incoming gradient while it is staged); the bias gradient is a column sum."""
+    incoming gradient while it is staged); the bias gradient comes out of the weight-gradient kernel."""
 
     @staticmethod
     def forward(ctx, x, x2, weight, bias, relu):
@@ -238,11 +239,11 @@ class LinearTcFn(torch.autograd.Function):
         if dx is not None:
             dx1 = (dx if x2 is None else dx[:, : ctx.k1]) if ctx.needs_input_grad[0] else None
             dx2 = dx[:, ctx.k1:] if (x2 is not None and ctx.needs_input_grad[1]) else None
-        dw = linear_weight_grad(dy, x, mask=y, x2=x2) if ctx.needs_input_grad[2] else None
-        db = None
-        if ctx.has_bias and ctx.needs_input_grad[3]:
-            db = (torch.where(y > 0, dy, torch.zeros_like(dy)) if ctx.relu else dy).sum(dim=0)
-        return dx1, dx2, dw, db, None
+        want_db = ctx.has_bias and ctx.needs_input_grad[3]
+        dw = db = None
+        if ctx.needs_input_grad[2] or want_db:
+            dw, db = linear_weight_grad(dy, x, mask=y, x2=x2, want_bias=True)
+        return dx1, dx2, (dw if ctx.needs_input_grad[2] else None), (db if want_db else None), None
 
 
 def linear_tc(x, weight, bias=None, relu: bool = False, x2=None):

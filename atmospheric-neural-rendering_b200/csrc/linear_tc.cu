@@ -263,7 +263,7 @@ constexpr uint32_t kTmemCols = 512;
 __device__ __forceinline__ void stage_rows(const float* __restrict__ src, int64_t ld, const float* __restrict__ src2,
                                            int64_t ld2, int split, const float* __restrict__ mask, int64_t ldm,
                                            int64_t row_lo, int64_t M, int c0, int cols, bool vec_ok, uint8_t* tile,
-                                           int tid) {
+                                           int tid, float* colsum = nullptr) {
   const int warp = tid >> 5, lane = tid & 31;
 #pragma unroll
   for (int it = 0; it < 4; ++it) {
@@ -279,6 +279,10 @@ __device__ __forceinline__ void stage_rows(const float* __restrict__ src, int64_
       load8(second ? src2 + row * ld2 + (k0 - split) : src + row * ld + k0, mask ? mask + row * ldm + k0 : nullptr,
             (second ? cols : split) - k0, vec_ok, v);
     }
+    if (colsum) {  // a thread's column group cc is the same in every iteration and every chunk
+#pragma unroll
+      for (int j = 0; j < 8; ++j) colsum[j] += v[j];
+    }
     uint4 hi, mid, lo;
     split8(v, hi, mid, lo);
     st_chunk(tile, r, cc, ldw::kWide, hi);
@@ -290,7 +294,7 @@ __device__ __forceinline__ void stage_rows(const float* __restrict__ src, int64_
 __global__ void __launch_bounds__(ldw::kThreads, 1)
 k_linear_dw_tc(const float* __restrict__ dy, int64_t ldy, const float* __restrict__ mask, int64_t ldm,
                const float* __restrict__ x, int64_t ldx, const float* __restrict__ x2, int64_t ldx2, int k_split,
-               int64_t M, int n_out, int k_in, float* __restrict__ dw) {
+               int64_t M, int n_out, int k_in, float* __restrict__ dw, float* __restrict__ db) {
   extern __shared__ __align__(128) uint8_t smem[];
   uint64_t* bar = reinterpret_cast<uint64_t*>(smem + ldw::kBar);
   uint32_t* tmem_ptr = reinterpret_cast<uint32_t*>(smem + ldw::kTmemPtr);
@@ -321,12 +325,20 @@ k_linear_dw_tc(const float* __restrict__ dy, int64_t ldy, const float* __restric
   const bool vx = (ldx & 3) == 0 && (reinterpret_cast<uintptr_t>(x) & 15) == 0 &&
                   (!x2 || ((ldx2 & 3) == 0 && (reinterpret_cast<uintptr_t>(x2) & 15) == 0));
 
+  // bias gradient = column sums of the (masked) dY: the staging threads see every value anyway; the
+  // CTAs of the first k_in block add theirs
+  float colsum[8];
+#pragma unroll
+  for (int j = 0; j < 8; ++j) colsum[j] = 0.0f;
+  const bool want_db = db != nullptr && blockIdx.z == 0;
+
   int it = 0;
   for (int64_t c = c_lo; c < c_hi; ++c, ++it) {
     const int s = it & 1;
     uint8_t* stage = smem + s * ldw::kStage;
     if (it >= 2) mbar_wait(bar + s, (uint32_t)(((it >> 1) - 1) & 1));
-    stage_rows(dy, ldy, nullptr, 0, n_out, mask, ldm, c * ldw::kChunk, M, n0, n_out, vy, stage, tid);
+    stage_rows(dy, ldy, nullptr, 0, n_out, mask, ldm, c * ldw::kChunk, M, n0, n_out, vy, stage, tid,
+               want_db ? colsum : nullptr);
     stage_rows(x, ldx, x2, ldx2, k_split, nullptr, 0, c * ldw::kChunk, M, k0, k_in, vx, stage + 3 * ldw::kTile, tid);
     fence_async_smem();
     tc_fence_before();
@@ -355,6 +367,17 @@ k_linear_dw_tc(const float* __restrict__ dy, int64_t ldy, const float* __restric
     const int last = it - 1;
     mbar_wait(bar + (last & 1), (uint32_t)((last >> 1) & 1));
     tc_fence_after();
+  }
+  if (want_db) {  // lanes l, l^1, l^2, l^4 hold the same 8 columns for different rows
+    const int lane = tid & 31, col0 = n0 + (((warp & 7) << 2) | (lane >> 3)) * 8;
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+      float v = colsum[j];
+      v += __shfl_xor_sync(0xffffffffu, v, 1);
+      v += __shfl_xor_sync(0xffffffffu, v, 2);
+      v += __shfl_xor_sync(0xffffffffu, v, 4);
+      if ((lane & 7) == 0 && col0 + j < n_out) atomicAdd(db + col0 + j, v);
+    }
   }
   // ---- epilogue: accumulator h, lane = row (n_out index), columns = k_in index
   for (int h = 0; h < m_halves; ++h) {
@@ -422,7 +445,7 @@ int atmonr_linear_fwd_tc(const float* x, int64_t ldx, const float* x2, int64_t l
 
 int atmonr_linear_dw_tc(const float* dy, int64_t ldy, const float* mask, int64_t ldm, const float* x, int64_t ldx,
                         const float* x2, int64_t ldx2, int k_split, int64_t M, int n_out, int k_in, float* dw,
-                        void* stream) {
+                        float* db, void* stream) {
   ATM_REQUIRE(M >= 0 && n_out > 0 && k_in > 0, "atmonr_linear_dw_tc", "bad shape");
   if (M == 0) return 0;
   ATM_REQUIRE(dy && x && dw, "atmonr_linear_dw_tc", "null pointer");
@@ -443,7 +466,7 @@ int atmonr_linear_dw_tc(const float* dy, int64_t ldy, const float* mask, int64_t
   if (slabs > chunks) slabs = chunks;
   dim3 grid((unsigned)slabs, (unsigned)ny, (unsigned)nz);
   k_linear_dw_tc<<<grid, ldw::kThreads, ldw::kBytes, S(stream)>>>(dy, ldy, mask, ldm, x, ldx, x2, ldx2, k_split, M, n_out,
-                                                                  k_in, dw);
+                                                                  k_in, dw, db);
   ATM_CHECK_LAUNCH("atmonr_linear_dw_tc");
   return 0;
 }

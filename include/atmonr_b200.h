@@ -289,7 +289,8 @@ int atmonr_sample_pdf(const float* weights, const float* z_coarse, const float* 
  *   bias (n_out) may be NULL; act: 0 none, 1 ReLU.
  * atmonr_linear_dw_tc:   dW (n_out, k_in) += dY' (M, n_out)^T * X (M, k_in)   (dW contiguous,
  *   zeroed or pre-loaded by the caller; mask (M, n_out) as above, applied to dY; x / x2 / k_split
- *   as above). */
+ *   as above). db (n_out, may be NULL) += column sums of dY' (the bias gradient, accumulated by
+ *   the threads that stage dY). */
 int atmonr_linear_prep(const float* w, int n_out, int k_in, int transpose, void* planes,
                        void* stream);
 int atmonr_linear_fwd_tc(const float* x, int64_t ldx, const float* x2, int64_t ldx2, int k_split,
@@ -298,7 +299,7 @@ int atmonr_linear_fwd_tc(const float* x, int64_t ldx, const float* x2, int64_t l
                          void* stream);
 int atmonr_linear_dw_tc(const float* dy, int64_t ldy, const float* mask, int64_t ldm,
                         const float* x, int64_t ldx, const float* x2, int64_t ldx2, int k_split,
-                        int64_t M, int n_out, int k_in, float* dw, void* stream);
+                        int64_t M, int n_out, int k_in, float* dw, float* db, void* stream);
 
 /* ---- tensor-core self test -------------------------------------------------------------------
  * One 128-row tile through the three tcgen05 operand configurations of the fused kernels.

@@ -342,8 +342,8 @@ def test_linear_tc_host_side():
     with pytest.raises(L.NativeLibraryError, match="null pointer"):
         L.call("atmonr_linear_fwd_tc", None, 8, None, 0, 0, None, 0, None, None, 4, 3, 8, 0, None, 3, None)
     with pytest.raises(L.NativeLibraryError, match="null pointer"):
-        L.call("atmonr_linear_dw_tc", None, 3, None, 0, None, 8, None, 0, 0, 4, 3, 8, None, None)
-    L.call("atmonr_linear_dw_tc", None, 3, None, 0, None, 8, None, 0, 0, 0, 3, 8, None, None)             # no rows
+        L.call("atmonr_linear_dw_tc", None, 3, None, 0, None, 8, None, 0, 0, 4, 3, 8, None, None, None)
+    L.call("atmonr_linear_dw_tc", None, 3, None, 0, None, 8, None, 0, 0, 0, 3, 8, None, None, None)             # no rows
     with pytest.raises(L.NativeLibraryError, match="null pointer"):
         L.call("atmonr_linear_prep", None, 3, 8, 0, None, None)
     L.call("atmonr_linear_fwd_tc", None, 8, None, 0, 0, None, 0, None, None, 0, 3, 8, 0, None, 3, None)   # no rows: nothing to do

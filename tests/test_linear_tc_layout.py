@@ -188,7 +188,7 @@ DW_TILE = DW_CHUNK * WIDE * 2
 DW_STAGE = 6 * DW_TILE
 
 
-def stage_rows(smem, tile, src, mask, row_lo, M, c0, cols, src2=None, split=None):
+def stage_rows(smem, tile, src, mask, row_lo, M, c0, cols, src2=None, split=None, colsum=None):
     for tid in range(THREADS):
         warp, lane = tid >> 5, tid & 31
         for it in range(4):
@@ -205,13 +205,15 @@ def stage_rows(smem, tile, src, mask, row_lo, M, c0, cols, src2=None, split=None
                     if j < left:
                         val = src2[row, k0 - sp + j] if second else src[row, k0 + j]
                         v[j] = 0.0 if (mask is not None and not mask[row, k0 + j] > 0) else val
+            if colsum is not None:
+                colsum[tid] += v
             hi, mid, lo = split8(v)
             st_chunk(smem, tile, r, cc, WIDE, hi)
             st_chunk(smem, tile + DW_TILE, r, cc, WIDE, mid)
             st_chunk(smem, tile + 2 * DW_TILE, r, cc, WIDE, lo)
 
 
-def dw_cta(dy, mask, x, M, n_out, k_in, bx, gx, by, bz, dw, x2=None, k_split=None):
+def dw_cta(dy, mask, x, M, n_out, k_in, bx, gx, by, bz, dw, x2=None, k_split=None, db=None):
     chunks = -(-M // DW_CHUNK)
     per = -(-chunks // gx)
     c_lo, c_hi = bx * per, min(chunks, bx * per + per)
@@ -222,9 +224,10 @@ def dw_cta(dy, mask, x, M, n_out, k_in, bx, gx, by, bz, dw, x2=None, k_split=Non
     n_cols = min(WIDE, -(-(k_in - k0) // 16) * 16)
     smem = np.full(2 * DW_STAGE // 2, 0x7FC0, np.uint16)
     acc = np.zeros((2, 128, n_cols), np.float64)
+    colsum = np.zeros((THREADS, 8)) if (db is not None and bz == 0) else None
     for it, c in enumerate(range(c_lo, c_hi)):
         stage = (it & 1) * DW_STAGE
-        stage_rows(smem, stage, dy, mask, c * DW_CHUNK, M, n0, n_out)
+        stage_rows(smem, stage, dy, mask, c * DW_CHUNK, M, n0, n_out, colsum=colsum)
         stage_rows(smem, stage + 3 * DW_TILE, x, None, c * DW_CHUNK, M, k0, k_in, x2, k_split)
         a0, b0 = stage, stage + 3 * DW_TILE
         for h in range(m_halves):
@@ -234,6 +237,16 @@ def dw_cta(dy, mask, x, M, n_out, k_in, bx, gx, by, bz, dw, x2=None, k_split=Non
                     a = fetch(smem, a0 + PA[t] * DW_TILE + koff + h * 16 * K_CORE, (WIDE >> 3) * K_CORE, K_CORE, True, 128)
                     b = fetch(smem, b0 + PB[t] * DW_TILE + koff, (WIDE >> 3) * K_CORE, K_CORE, True, n_cols)
                     acc[h] += a.astype(np.float64) @ b.astype(np.float64).T
+    if colsum is not None:
+        for tid in range(THREADS):
+            warp, lane = tid >> 5, tid & 31
+            if lane & 7:
+                continue
+            col0 = n0 + (((warp & 7) << 2) | (lane >> 3)) * 8
+            total = sum(colsum[tid ^ q] for q in range(8))        # the three xor-shuffles
+            for j in range(8):
+                if col0 + j < n_out:
+                    db[col0 + j] += total[j]
     for h in range(m_halves):
         for tid in range(THREADS):
             warp = tid >> 5
@@ -259,14 +272,15 @@ def test_weight_gradient_kernel_model(m, n_out, k_in, gx, masked):
     dy = rng.standard_normal((m, n_out)).astype(np.float32)
     x = rng.standard_normal((m, k_in)).astype(np.float32)
     mask = rng.standard_normal((m, n_out)).astype(np.float32) if masked else None
-    dw = np.zeros((n_out, k_in))
+    dw, db = np.zeros((n_out, k_in)), np.zeros(n_out)
     for bx in range(gx):
         for by in range(-(-n_out // WIDE)):
             for bz in range(-(-k_in // WIDE)):
-                dw_cta(dy, mask, x, m, n_out, k_in, bx, gx, by, bz, dw)
+                dw_cta(dy, mask, x, m, n_out, k_in, bx, gx, by, bz, dw, db=db)
     dye = dy if mask is None else np.where(mask > 0, dy, 0)
     want = dye.astype(np.float64).T @ x.astype(np.float64)
     assert np.abs(dw - want).max() <= 3e-7 * np.abs(want).max()
+    assert np.abs(db - dye.astype(np.float64).sum(0)).max() <= 1e-6 * np.abs(dye).sum(0).max()
 
 
 def test_weight_gradient_kernel_model_two_input_blocks():

@@ -65,10 +65,12 @@ def test_linear_forward_matches_float64(m, k, n, relu, bias):
     want_dx = (dy * keep).double() @ w.double()
     assert float((dx.double() - want_dx).abs().max()) / float(want_dx.abs().max() + 1e-30) <= 2e-6
     # weight gradient: a reduction over all rows (split over the CTAs, float32 REDs at the end)
-    dw = ops.linear_weight_grad(dy, x, mask=got if relu else None)
+    dw, db = ops.linear_weight_grad(dy, x, mask=got if relu else None, want_bias=True)
     want_dw = (dy * keep).double().t() @ x.double()
-    assert dw.shape == (n, k)
+    assert dw.shape == (n, k) and db.shape == (n,)
     assert float((dw.double() - want_dw).abs().max()) / float(want_dw.abs().max() + 1e-30) <= 4e-6
+    want_db = (dy * keep).double().sum(0)
+    assert float((db.double() - want_db).abs().max()) <= 2e-5 * float(want_db.abs().max() + 1e-30) + 1e-4
 
 
 def test_linear_on_a_column_slice_and_autograd():
