@@ -116,7 +116,9 @@ torch.save({"view_idx": ds.view_idx, "irgb_idx": ds.irgb_idx, "img_shp": tuple(d
             "ray_len_norm": ds.ray_len_norm, "ray_rad": ds.ray_rad, "ray_alt": ds.ray_alt,
             "ray_irgb_idx": ds.ray_irgb_idx, "scale": ds.scale, "offset": ds.offset, "len": len(ds),
             "batch": {k: v for k, v in batch.items()}, "idx": idx, "p32": p32, "p64": p64,
-            "pre32": pre(p32), "pre64": pre(p64)}, sys.argv[6])
+            "pre32": pre(p32), "pre64": pre(p64), "best_rgb_idx": [int(v) for v in ds.best_rgb_idx],
+            "tracker": {k: getattr(ds.get_progress_tracker(), k) for k in
+                        ("valid", "target_img", "target_img_rgb", "pred_img", "pred_pixels")}}, sys.argv[6])
 """
 
 
@@ -141,6 +143,13 @@ def test_dataset_matches_the_reference_dataset_on_the_synthetic_granule(tmp_path
     assert ds.scale == ref["scale"] and torch.equal(ds.offset, ref["offset"])
     for k in ("ray_origin_norm", "ray_dir", "ray_len_norm", "ray_rad", "ray_alt", "ray_irgb_idx"):
         assert torch.equal(getattr(ds, k), ref[k]), k          # same torch build, same operations: bit for bit
+    # visualisation side of the dataset (harp2.py:126-203, 259-349): RGB view choice and progress tracker
+    import numpy as np
+    assert [int(v) for v in ds.best_rgb_idx] == ref["best_rgb_idx"]
+    tracker = ds.get_progress_tracker()
+    for k, v in ref["tracker"].items():
+        got = getattr(tracker, k)
+        assert got.shape == v.shape and np.array_equal(got, v, equal_nan=True), k
     batch = ds[ref["idx"]]
     assert set(batch) == set(ref["batch"])
     for k, v in ref["batch"].items():
