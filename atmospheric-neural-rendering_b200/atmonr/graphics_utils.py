@@ -30,5 +30,40 @@ def render_with_surface(z_vals, color, sigma, color_surf):
     return cmap, alpha, weights, catmo, csurf
 
 
-def voxel_traversal(*args, **kwargs):
-    raise NotImplementedError("voxel_traversal (globalgrid extract mode) is outside the B200 hot-path build")
+def voxel_traversal(u: torch.Tensor, end: torch.Tensor, unique_only: bool = True) -> torch.Tensor:
+    """Voxels (unit grid, any dimension) crossed by the segments u[i] -> end[i]; graphics_utils.py:80-147
+    (Amanatides & Woo 1987), used by the global-grid extract layout (harp2_extract.py:858). Returns
+    int16 voxel indices, one row per visit (all start voxels first, then one row per step), or the
+    distinct rows when `unique_only`.
+
+    A batched DDA on whatever device the inputs live on: every segment still under way advances along
+    the axis whose next cell boundary is nearest; an axis that has reached the end voxel's index is
+    frozen (its boundary distance becomes infinite), so a walk ends exactly in the end voxel, or stops
+    as soon as some axis is past it. Plain torch: this runs once per extraction, not per step."""
+    if u.shape != end.shape or u.dim() != 2:
+        raise ValueError("u and end must both have shape (N, D)")
+    delta = end - u
+    direction = delta / torch.linalg.norm(delta, dim=-1, keepdim=True)
+    step = torch.sign(direction).to(torch.int16)
+    cell = torch.floor(u).to(torch.int16)
+    last = torch.floor(end).to(torch.int16)
+    # distance along the segment to the first boundary on each axis, and between boundaries
+    along = step.to(u.dtype) * u
+    t_next = torch.abs((torch.ceil(along) - along) / direction)
+    t_next = torch.where(t_next.isnan() | (cell == last), torch.full_like(t_next, torch.inf), t_next)
+    t_cell = torch.abs(1 / direction)
+    visits = [torch.unique(cell, dim=0, sorted=False)]
+    gap = (cell - last) * step                       # < 0: still short of the end index on that axis
+    walking = ~((gap == 0).all(dim=-1) | (gap > 0).any(dim=-1))
+    while bool(walking.any()):
+        rows = torch.nonzero(walking)[:, 0]
+        axis = torch.argmin(t_next[rows], dim=-1)
+        t_next[rows, axis] += t_cell[rows, axis]
+        cell[rows, axis] += step[rows, axis]
+        visits.append(cell[rows].clone())
+        gap = (cell[rows] - last[rows]) * step[rows]
+        reached = gap >= 0
+        t_next[rows] = torch.where(reached, torch.full_like(t_next[rows], torch.inf), t_next[rows])
+        walking[rows] = ~(reached.all(dim=-1) | (gap > 0).any(dim=-1))
+    out = torch.cat(visits, dim=0)
+    return torch.unique(out, dim=0, sorted=False) if unique_only else out

@@ -39,6 +39,20 @@ def main():
     out["ah_pts"] = pts.numpy()
     out["ah_out"] = samplers.append_heights(pts, 20000.0, scale, offset).numpy()
     out["ah_scale"], out["ah_offset"] = np.float64(scale), offset.numpy()
+    # graphics_utils.voxel_traversal: random segments in 2-D and 3-D, axis-aligned ones, and segments
+    # that start and end in one voxel; compared as SETS of visited voxels (sorted unique rows)
+    from atmonr import graphics_utils
+    g = torch.Generator().manual_seed(21)
+    for tag, dim in (("2d", 2), ("3d", 3)):
+        a = torch.rand(60, dim, generator=g) * 20 - 4
+        b = torch.rand(60, dim, generator=g) * 20 - 4
+        b[:6, 0] = a[:6, 0]                       # no motion along x
+        b[6:10] = a[6:10] + 0.01 * (torch.rand(4, dim, generator=g) - 0.5)   # (almost always) one voxel
+        reg = graphics_utils.voxel_traversal(a.clone(), b.clone(), unique_only=True)
+        out[f"vox_{tag}_u"], out[f"vox_{tag}_end"] = a.numpy(), b.numpy()
+        out[f"vox_{tag}_set"] = torch.unique(reg, dim=0).numpy()
+        full = graphics_utils.voxel_traversal(a.clone(), b.clone(), unique_only=False)
+        out[f"vox_{tag}_visits"] = np.int64(full.shape[0])
     np.savez_compressed(HERE / "reference_vectors_extra.npz", **out)
     print({k: v.shape for k, v in out.items()})
 

@@ -208,3 +208,24 @@ def test_append_heights_matches_reference():
     close(got, TX("ah_out"))
     want = sampling.append_heights(TX("ah_pts"), 20000.0, float(GX["ah_scale"]), TX("ah_offset"))
     close(want, TX("ah_out"))
+
+
+@pytest.mark.parametrize("tag", ["2d", "3d"])
+def test_voxel_traversal_matches_reference(tag):
+    """graphics_utils.voxel_traversal against the reference's graphics_utils.py:80-147: the same SET of
+    voxels and the same number of visits, on random, axis-aligned and single-voxel segments."""
+    import sys
+    sys.path.insert(0, os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "atmospheric-neural-rendering_b200"))
+    from atmonr import graphics_utils
+    u, end = TX(f"vox_{tag}_u"), TX(f"vox_{tag}_end")
+    reg = graphics_utils.voxel_traversal(u.clone(), end.clone(), unique_only=True)
+    assert reg.dtype == torch.int16
+    assert torch.equal(torch.unique(reg, dim=0), TX(f"vox_{tag}_set"))
+    full = graphics_utils.voxel_traversal(u.clone(), end.clone(), unique_only=False)
+    assert full.shape[0] == int(GX[f"vox_{tag}_visits"])
+    # every segment's start and end voxel are in the set
+    have = {tuple(r) for r in reg.tolist()}
+    for p in torch.cat([torch.floor(u), torch.floor(end)]).to(torch.int16).tolist():
+        assert tuple(p) in have
+    with pytest.raises(ValueError):
+        graphics_utils.voxel_traversal(u, end[:5])
