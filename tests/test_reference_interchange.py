@@ -160,3 +160,104 @@ def test_dataset_matches_the_reference_dataset_on_the_synthetic_granule(tmp_path
     frame = geodesy.HorizontalFrame.from_latlon(lat, lon, ds.scale, ds.offset, 20000.0)
     assert torch.equal(geodesy.preprocess_horizontal(ref["p32"], frame), ref["pre32"])
     assert float((geodesy.preprocess_horizontal(ref["p64"], frame) - ref["pre64"]).abs().max()) <= 1e-12
+
+
+# ------------------------------------------------------------------------------------------
+# the reference's InstantNGPPipeline around a stand-in tinycudann
+# ------------------------------------------------------------------------------------------
+NGP_CHILD = DATASET_CHILD.split("from atmonr.datasets.harp2 import HARP2Dataset")[0] + r"""
+# a stand-in `tinycudann`: the module API the reference uses (instant_ngp.py:60-85), with the
+# arithmetic of oracle/tcnn_spec.py in float32. What is under test is everything AROUND it.
+import types
+sys.path.insert(0, sys.argv[7])                      # repository root: the `oracle` package
+from oracle import tcnn_spec
+
+class _Mod(torch.nn.Module):
+    def __init__(self, impl):
+        super().__init__()
+        self.impl, self.n_output_dims = impl, impl.n_output_dims
+        self.params = torch.nn.Parameter(torch.zeros(impl.n_params))
+    def forward(self, x):
+        return self.impl.forward(x.float(), self.params, False)
+
+tcnn = types.ModuleType("tinycudann")
+tcnn.Encoding = lambda n_in, cfg, **kw: _Mod(tcnn_spec.make_encoding(n_in, cfg))
+tcnn.Network = lambda n_in, n_out, cfg, **kw: _Mod(tcnn_spec.Network(n_in, n_out, cfg))
+sys.modules["tinycudann"] = tcnn
+
+from atmonr.datasets.harp2 import HARP2Dataset
+from atmonr.pipelines.instant_ngp import InstantNGPPipeline
+cfg = json.loads(sys.argv[4])
+ds = HARP2Dataset(cfg["dataset"], "fake.nc")
+pipe = InstantNGPPipeline(cfg["pipeline"], ds)
+pipe.send_tensors_to(0)
+job = torch.load(sys.argv[8])
+for name, p in job["params"].items():
+    getattr(pipe, name).params.data.copy_(p)
+batch = ds[job["idx"]]
+torch.manual_seed(job["seed"])
+res = pipe.forward(batch)
+loss = pipe.compute_loss(batch, res)
+loss.backward()
+pipe.eval()
+sig = pipe.extract(job["pts"].clone())
+opt = pipe.get_optimizer(cfg["trainer"]["optimizer"])
+torch.save({"res": {k: v.detach() for k, v in res.items()}, "loss": loss.detach(),
+            "grads": {n: getattr(pipe, n).params.grad for n in job["params"] if getattr(pipe, n).params.grad is not None},
+            "extract": sig.detach(), "state_keys": {k: list(v) for k, v in pipe.state_dict().items()},
+            "groups": [(len(g["params"]), g["weight_decay"], g["lr"], tuple(g["betas"]), g["eps"]) for g in opt.param_groups]},
+           sys.argv[6])
+"""
+
+
+def test_ngp_glue_matches_the_reference_pipeline(tmp_path):
+    """instant_ngp.py:129-263 (sampling, preprocessing, remap, altitude compression, direction
+    conditioning, ReLUs, compositing with the surface, z in km, band selection and loss, extract) run
+    from the REFERENCE's own InstantNGPPipeline, with a stand-in for the absent tiny-cuda-nn that
+    evaluates oracle/tcnn_spec.py. The oracle pipeline (oracle/ngp.py) must reproduce its results and
+    parameter gradients: this pins the oracle's glue; only the tcnn arithmetic itself stays unpinned."""
+    from atmonr.datasets.harp2 import HARP2Dataset
+    from oracle import geodesy
+    from oracle.ngp import NGPOracle
+    spec = "synthetic:H=10,W=9,seed=4"
+    cfg = json.load(open(os.path.join(ROOT, "configs", "instant_ngp.json")))
+    cfg["pipeline"]["num_samples_per_ray"] = 24
+    for key in ("encoding", "surface_encoding"):
+        cfg["pipeline"]["instant_ngp"][key]["log2_hashmap_size"] = 12       # small tables: CPU-sized test
+    ds = HARP2Dataset(dict(cfg["dataset"]), spec, device=torch.device("cpu"))
+    lat, lon = ds.lat[~ds.lat.isnan()], ds.lon[~ds.lon.isnan()]
+    frame = geodesy.HorizontalFrame.from_latlon(lat, lon, ds.scale, ds.offset, 20000.0)
+    orc = NGPOracle(cfg["pipeline"], frame, ds.max_i, fp16=False)
+    params = orc.init_params(3)
+    with torch.no_grad():
+        for k in ("pos_encoder", "surf_encoder"):
+            params[k].mul_(3e3)                                             # non-trivial outputs
+    idx = torch.arange(5, len(ds), 211)[:40]
+    g = torch.Generator().manual_seed(6)
+    pts = torch.rand(64, 3, dtype=torch.float64, generator=g) * 1.6 - 0.8
+    job, out = str(tmp_path / "job.pt"), str(tmp_path / "ref_ngp.pt")
+    torch.save({"params": {k: v.detach() for k, v in params.items()}, "idx": idx, "seed": 17, "pts": pts}, job)
+    r = subprocess.run([sys.executable, "-c", NGP_CHILD, os.path.join(ROOT, "tests", "golden"),
+                        os.path.join(ROOT, "atmospheric-neural-rendering_b200", "atmonr", "datasets", "granule.py"),
+                        spec, json.dumps(cfg), str(tmp_path), out, ROOT, job], capture_output=True, text=True, timeout=900)
+    assert r.returncode == 0, r.stderr[-3000:]
+    ref = torch.load(out, weights_only=False)
+    batch = ds[idx]
+    torch.manual_seed(17)
+    u = torch.rand(idx.shape[0], 24)                                        # samplers.py:37 draws (B, n_bins)
+    res = orc.forward(batch, params, u)
+    loss = orc.loss(batch, res)
+    loss.backward()
+    assert set(ref["res"]) == set(res) - {"pts01"}                          # same result keys (instant_ngp.py:193-204)
+    for k, v in ref["res"].items():
+        assert res[k].shape == v.shape, k
+        assert torch.allclose(res[k].detach(), v, rtol=1e-6, atol=1e-9), (k, float((res[k].detach() - v).abs().max()))
+    assert abs(float(loss.detach()) - float(ref["loss"])) <= 1e-6 * abs(float(ref["loss"]))
+    for name, gref in ref["grads"].items():
+        got = params[name].grad
+        assert float((got - gref).abs().max()) <= 1e-5 * float(gref.abs().max() + 1e-30), name
+    sig = orc.extract(pts, params)
+    assert torch.allclose(sig.detach(), ref["extract"].float(), rtol=1e-6, atol=1e-9)
+    # checkpoint layout and optimizer groups of the reference (instant_ngp.py:107-127, 265-296)
+    assert ref["state_keys"] == {n: ["params"] for n in ("pos_encoder", "pos_mlp", "dir_encoder", "dir_mlp", "surf_encoder", "surf_mlp")}
+    assert [(g[1], g[2]) for g in ref["groups"]] == [(0, 0.01), (0.01, 0.01)]
