@@ -18,6 +18,10 @@ Pinning status
   checked against golden vectors produced by importing the reference's own Python modules
   from ``/root/reference/src`` (``tests/golden/make_golden.py``; vectors committed under
   ``tests/golden/``) and against the known-answer vectors listed in SURVEY.md section 8c.
+* ``ngp`` (the Instant-NGP glue, instant_ngp.py:129-263): PINNED to the reference's own
+  ``InstantNGPPipeline``, constructed in a child process on the reference's ``HARP2Dataset`` around a
+  stand-in ``tinycudann`` module that evaluates ``tcnn_spec`` (forward results, loss, parameter
+  gradients, extract; ``tests/test_reference_interchange.py``, build container only).
 * ``tcnn_spec`` (multiresolution hash grid, spherical harmonics, identity/composite
   encodings, bias-free fully fused MLP): **PARITY UNPINNED**.  That arithmetic lives in the
   third-party, un-vendored and un-pinned ``tiny-cuda-nn`` (reference README.md:19-22 installs

@@ -1,9 +1,11 @@
 """Oracle: the Instant-NGP pipeline of the reference, restated on CPU.
 
 TEST INFRASTRUCTURE (see oracle/__init__.py).  Glue restated from
-src/atmonr/pipelines/instant_ngp.py:33-263; the tiny-cuda-nn modules come from
-oracle/tcnn_spec.py (PARITY UNPINNED there); sampler / preprocessor / renderer / losses are
-the pinned restatements in oracle/{sampling,geodesy,rendering}.py.
+src/atmonr/pipelines/instant_ngp.py:33-263 and PINNED to it: the reference's own
+InstantNGPPipeline, run around a stand-in tinycudann that evaluates oracle/tcnn_spec.py, gives the
+same results, loss, gradients and extract (tests/test_reference_interchange.py). The tiny-cuda-nn
+modules themselves come from oracle/tcnn_spec.py (PARITY UNPINNED there); sampler / preprocessor /
+renderer / losses are the pinned restatements in oracle/{sampling,geodesy,rendering}.py.
 
 Differences from the reference that are deliberate and stated:
   * compositing and loss run in float32 (the reference inherits fp16 from tcnn's outputs,
