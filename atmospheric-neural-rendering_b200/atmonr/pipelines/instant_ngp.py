@@ -156,7 +156,9 @@ class InstantNGPPipeline(Pipeline):
         if self.point_preprocessor:
             pts = self.point_preprocessor(pts[None])[0]
         pts = (pts + 1) / 2
-        pts = torch.cat([pts[..., :2], pts[..., 2:3] / self.config["alt_compress_factor"]], dim=-1)
+        if self.config["include_height"]:  # instant_ngp.py:227-230: the 4-D grid needs its height column here too
+            pts = append_heights(pts[None], self.ray_origin_height, self.scale, self.offset)[0]
+        pts = torch.cat([pts[..., :2], pts[..., 2:3] / self.config["alt_compress_factor"], pts[..., 3:]], dim=-1)
         out = self.pos_mlp(self.pos_encoder(pts.float()))
         return torch.clip(out[..., : self.num_density_outputs], min=0)
 

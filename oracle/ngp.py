@@ -97,7 +97,10 @@ class NGPOracle:
         if self.frame is not None:
             pts = preprocess_horizontal(pts[None], self.frame)[0]
         pts = (pts + 1) / 2
-        pts = torch.cat([pts[..., :2], pts[..., 2:] / self.cfg["alt_compress_factor"]], dim=-1)
+        if self.cfg["include_height"]:  # instant_ngp.py:227-230
+            scale, offset, height = self.geo
+            pts = sampling.append_heights(pts[None], height, scale, offset)[0]
+        pts = torch.cat([pts[..., :2], pts[..., 2:3] / self.cfg["alt_compress_factor"], pts[..., 3:]], dim=-1)
         out = self.pos_mlp.forward(
             self.pos_encoder.forward(pts.float(), params["pos_encoder"], self.fp16), params["pos_mlp"], self.fp16
         )

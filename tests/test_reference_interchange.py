@@ -210,7 +210,8 @@ torch.save({"res": {k: v.detach() for k, v in res.items()}, "loss": loss.detach(
 """
 
 
-def test_ngp_glue_matches_the_reference_pipeline(tmp_path):
+@pytest.mark.parametrize("variant", ["default", "multi_band_extinction", "include_height", "l1_plus_hdr"])
+def test_ngp_glue_matches_the_reference_pipeline(tmp_path, variant):
     """instant_ngp.py:129-263 (sampling, preprocessing, remap, altitude compression, direction
     conditioning, ReLUs, compositing with the surface, z in km, band selection and loss, extract) run
     from the REFERENCE's own InstantNGPPipeline, with a stand-in for the absent tiny-cuda-nn that
@@ -224,10 +225,20 @@ def test_ngp_glue_matches_the_reference_pipeline(tmp_path):
     cfg["pipeline"]["num_samples_per_ray"] = 24
     for key in ("encoding", "surface_encoding"):
         cfg["pipeline"]["instant_ngp"][key]["log2_hashmap_size"] = 12       # small tables: CPU-sized test
+    if variant == "multi_band_extinction":                                  # one density per band
+        cfg["pipeline"]["multi_band_extinction"] = True
+    elif variant == "include_height":                                       # 4-D grid on raw scene coordinates
+        cfg["pipeline"]["include_height"], cfg["pipeline"]["point_preprocessor"] = True, ""
+        cfg["pipeline"]["encoder"] = {"L_x": 4}       # pipeline.py:36 reads this NeRF key whenever there is no preprocessor
+    elif variant == "l1_plus_hdr":
+        cfg["pipeline"]["loss"] = "l1_plus_hdr"
     ds = HARP2Dataset(dict(cfg["dataset"]), spec, device=torch.device("cpu"))
     lat, lon = ds.lat[~ds.lat.isnan()], ds.lon[~ds.lon.isnan()]
     frame = geodesy.HorizontalFrame.from_latlon(lat, lon, ds.scale, ds.offset, 20000.0)
-    orc = NGPOracle(cfg["pipeline"], frame, ds.max_i, fp16=False)
+    if variant == "include_height":
+        orc = NGPOracle(cfg["pipeline"], None, ds.max_i, fp16=False, geo=(ds.scale, ds.offset, 20000.0))
+    else:
+        orc = NGPOracle(cfg["pipeline"], frame, ds.max_i, fp16=False)
     params = orc.init_params(3)
     with torch.no_grad():
         for k in ("pos_encoder", "surf_encoder"):
@@ -248,6 +259,9 @@ def test_ngp_glue_matches_the_reference_pipeline(tmp_path):
     res = orc.forward(batch, params, u)
     loss = orc.loss(batch, res)
     loss.backward()
+    if variant == "include_height":
+        assert "norm_heights_fine" in ref["res"]                            # instant_ngp.py:205-206
+        ref["res"].pop("norm_heights_fine")
     assert set(ref["res"]) == set(res) - {"pts01"}                          # same result keys (instant_ngp.py:193-204)
     for k, v in ref["res"].items():
         assert res[k].shape == v.shape, k
