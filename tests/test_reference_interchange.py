@@ -202,7 +202,19 @@ loss.backward()
 pipe.eval()
 sig = pipe.extract(job["pts"].clone())
 opt = pipe.get_optimizer(cfg["trainer"]["optimizer"])
-torch.save({"res": {k: v.detach() for k, v in res.items()}, "loss": loss.detach(),
+curve = []
+if job.get("steps"):                                  # trainer.py:99-105, the reference's own step order
+    pipe.train()
+    for k in range(job["steps"]):
+        b = ds[job["idx"] + k]
+        torch.manual_seed(job["seed"] + 1 + k)
+        r_ = pipe.forward(b)
+        l_ = pipe.compute_loss(b, r_)
+        opt.zero_grad()
+        l_.backward()
+        opt.step()
+        curve.append(float(l_.detach()))
+torch.save({"curve": curve, "res": {k: v.detach() for k, v in res.items()}, "loss": loss.detach(),
             "grads": {n: getattr(pipe, n).params.grad for n in job["params"] if getattr(pipe, n).params.grad is not None},
             "extract": sig.detach(), "state_keys": {k: list(v) for k, v in pipe.state_dict().items()},
             "groups": [(len(g["params"]), g["weight_decay"], g["lr"], tuple(g["betas"]), g["eps"]) for g in opt.param_groups]},
@@ -275,3 +287,44 @@ def test_ngp_glue_matches_the_reference_pipeline(tmp_path, variant):
     # checkpoint layout and optimizer groups of the reference (instant_ngp.py:107-127, 265-296)
     assert ref["state_keys"] == {n: ["params"] for n in ("pos_encoder", "pos_mlp", "dir_encoder", "dir_mlp", "surf_encoder", "surf_mlp")}
     assert [(g[1], g[2]) for g in ref["groups"]] == [(0, 0.01), (0.01, 0.01)]
+
+
+def test_ngp_training_curve_matches_the_reference_pipeline(tmp_path):
+    """30 optimisation steps of the reference's own InstantNGPPipeline + its AdamW groups
+    (instant_ngp.py:107-127, trainer.py:99-105) around the stand-in tcnn, against the oracle's
+    `train_step` from the same parameters, batches and draws: the two loss curves coincide."""
+    from atmonr.datasets.harp2 import HARP2Dataset
+    from oracle import geodesy
+    from oracle.ngp import NGPOracle
+    spec = "synthetic:H=10,W=9,seed=4"
+    cfg = json.load(open(os.path.join(ROOT, "configs", "instant_ngp.json")))
+    cfg["pipeline"]["num_samples_per_ray"] = 24
+    for key in ("encoding", "surface_encoding"):
+        cfg["pipeline"]["instant_ngp"][key]["log2_hashmap_size"] = 12
+    ds = HARP2Dataset(dict(cfg["dataset"]), spec, device=torch.device("cpu"))
+    lat, lon = ds.lat[~ds.lat.isnan()], ds.lon[~ds.lon.isnan()]
+    frame = geodesy.HorizontalFrame.from_latlon(lat, lon, ds.scale, ds.offset, 20000.0)
+    orc = NGPOracle(cfg["pipeline"], frame, ds.max_i, fp16=False)
+    params = orc.init_params(5)
+    idx = torch.arange(5, len(ds), 211)[:40]
+    steps = 30
+    job, out = str(tmp_path / "job.pt"), str(tmp_path / "ref_ngp.pt")
+    torch.save({"params": {k: v.detach() for k, v in params.items()}, "idx": idx, "seed": 40,
+                "pts": torch.zeros(4, 3, dtype=torch.float64), "steps": steps}, job)
+    r = subprocess.run([sys.executable, "-c", NGP_CHILD, os.path.join(ROOT, "tests", "golden"),
+                        os.path.join(ROOT, "atmospheric-neural-rendering_b200", "atmonr", "datasets", "granule.py"),
+                        spec, json.dumps(cfg), str(tmp_path), out, ROOT, job], capture_output=True, text=True, timeout=900)
+    assert r.returncode == 0, r.stderr[-3000:]
+    ref_curve = torch.load(out, weights_only=False)["curve"]
+    # the child ran one forward/backward before the loop WITHOUT stepping: parameters are still the initial ones
+    opt = orc.make_optimizer(params, cfg["trainer"]["optimizer"])
+    curve = []
+    for k in range(steps):
+        torch.manual_seed(40 + 1 + k)
+        u = torch.rand(idx.shape[0], 24)
+        loss, _ = orc.train_step(ds[idx + k], params, opt, u)
+        curve.append(float(loss))
+    assert len(ref_curve) == steps
+    rel = max(abs(a - b) / abs(b) for a, b in zip(curve, ref_curve))
+    assert rel <= 1e-3, (rel, curve[-3:], ref_curve[-3:])
+    assert ref_curve[-1] < ref_curve[0]                     # and it does learn
