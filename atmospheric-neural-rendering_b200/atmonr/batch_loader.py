@@ -2,7 +2,8 @@
 
 Same constructor and iteration protocol. The reference builds every batch index from a Python
 list of B ints (batch_loader.py:45-49); here one permutation per epoch is drawn as a tensor
-(torch's generator, so seeding works the same way) and sliced, which removes the O(B) Python
+(torch's generators, drawn exactly like the reference's RandomSampler does, so `torch.manual_seed`
+reproduces the reference's batch order) and sliced, which removes the O(B) Python
 work per step. Under torch.distributed every rank draws the SAME permutation and
 takes its own contiguous slice of each global batch (data-parallel ray sharding).
 """
@@ -31,7 +32,17 @@ class BatchLoader:
 
     def __iter__(self) -> Iterator[dict[str, torch.Tensor]]:
         n = self.idx.shape[0]
-        order = torch.randperm(n, generator=self.generator) if self.shuffle else torch.arange(n)
+        if not self.shuffle:
+            order = torch.arange(n)
+        else:
+            gen = self.generator
+            if gen is None:
+                # what the reference's RandomSampler does (batch_loader.py:34-38 -> torch RandomSampler): one
+                # int64 from the global generator seeds a private one, so `torch.manual_seed(s)` gives the
+                # SAME batch order as the reference and consumes the global stream identically
+                gen = torch.Generator()
+                gen.manual_seed(int(torch.empty((), dtype=torch.int64).random_().item()))
+            order = torch.randperm(n, generator=gen)
         # ONE host->device copy of the permutation per epoch; every batch index is a device-side slice
         # of it (a per-batch copy from pageable memory blocks the host until the device has caught up)
         order = order.to(self.idx.device)

@@ -328,3 +328,44 @@ def test_ngp_training_curve_matches_the_reference_pipeline(tmp_path):
     rel = max(abs(a - b) / abs(b) for a, b in zip(curve, ref_curve))
     assert rel <= 1e-3, (rel, curve[-3:], ref_curve[-3:])
     assert ref_curve[-1] < ref_curve[0]                     # and it does learn
+
+
+LOADER_CHILD = DATASET_CHILD.split("idx = torch.arange(0, len(ds), 97)")[0] + r"""
+from atmonr.batch_loader import BatchLoader
+out = {}
+for tag, kw in (("plain", {}), ("drop", {"drop_last": True}), ("seq", {"shuffle": False})):
+    torch.manual_seed(123)
+    loader = BatchLoader(ds, batch_size=1000, **kw)
+    epochs = []
+    for _ in range(2):
+        epochs.append([b["idx"].clone() for b in loader])
+    out[tag] = {"len": len(loader), "epochs": epochs, "after": torch.rand(3)}
+torch.save(out, sys.argv[6])
+"""
+
+
+def test_batch_loader_reproduces_the_reference_order(tmp_path):
+    """Same `torch.manual_seed`, same batches as the reference's BatchLoader (batch_loader.py:11-60):
+    order within two epochs, the partial last batch, drop_last, the sequential mode, len(), and the
+    state the global generator is left in."""
+    from atmonr.batch_loader import BatchLoader
+    from atmonr.datasets.harp2 import HARP2Dataset
+    spec = "synthetic:H=10,W=9,seed=4"
+    cfg = json.load(open(os.path.join(ROOT, "configs", "instant_ngp.json")))["dataset"]
+    out = str(tmp_path / "ref_loader.pt")
+    r = subprocess.run([sys.executable, "-c", LOADER_CHILD, os.path.join(ROOT, "tests", "golden"),
+                        os.path.join(ROOT, "atmospheric-neural-rendering_b200", "atmonr", "datasets", "granule.py"),
+                        spec, json.dumps(cfg), str(tmp_path), out], capture_output=True, text=True, timeout=600)
+    assert r.returncode == 0, r.stderr[-3000:]
+    ref = torch.load(out, weights_only=False)
+    ds = HARP2Dataset(dict(cfg), spec, device=torch.device("cpu"))
+    for tag, kw in (("plain", {}), ("drop", {"drop_last": True}), ("seq", {"shuffle": False})):
+        torch.manual_seed(123)
+        loader = BatchLoader(ds, batch_size=1000, **kw)
+        assert len(loader) == ref[tag]["len"], tag
+        for want in ref[tag]["epochs"]:
+            got = [b["idx"] for b in loader]
+            assert len(got) == len(want), tag
+            for a, b in zip(got, want):
+                assert torch.equal(a.cpu(), b), tag
+        assert torch.equal(torch.rand(3), ref[tag]["after"]), tag
