@@ -79,6 +79,7 @@ SIGNATURES = {
     "atmonr_extract_sigma": [FP, GP, P, MP, P, P, I64, F32, P, P],
     "atmonr_extract_sigma_tc": [FP, GP, P, MP, P, P, I64, F32, P, P],
     "atmonr_positional_encoding": [P, I64, I32, C.POINTER(C.c_int32), I32, P, P],
+    "atmonr_positional_encoding_f64": [P, I64, I32, C.POINTER(C.c_int32), I32, P, P],
     "atmonr_sample_pdf": [P, P, P, I64, I32, I32, P, P, P],
     "atmonr_tc_probe": [P, P, I32, P, P],
     "atmonr_linear_prep": [P, I32, I32, I32, P, P],

@@ -442,13 +442,17 @@ def adamw_step(param, grad, exp_avg, exp_avg_sq, param_f16, lr, beta1, beta2, ep
 # NeRF helpers
 # ------------------------------------------------------------------------------------------
 def positional_encoding(pts: torch.Tensor, freqs, interleaved: bool) -> torch.Tensor:
-    p = _c(pts, _f32)
+    """encoders.py:4-28 -> float32 features. float64 points keep their precision through the phase
+    (the extract path, nerf.py:209-213); everything else is encoded in float32."""
+    f64 = pts.dtype == torch.float64
+    p = _c(pts, torch.float64 if f64 else _f32)
     c = p.shape[-1]
     flat = p.reshape(-1, c)
     fl = list(freqs) if not isinstance(freqs, int) else [freqs] * c
     arr = (C.c_int32 * len(fl))(*fl)
     out = torch.empty((flat.shape[0], 2 * sum(fl)), device=p.device, dtype=_f32)
-    L.call("atmonr_positional_encoding", L.ptr(flat), flat.shape[0], c, arr, int(interleaved), L.ptr(out), L.stream())
+    L.call("atmonr_positional_encoding_f64" if f64 else "atmonr_positional_encoding", L.ptr(flat), flat.shape[0], c,
+           arr, int(interleaved), L.ptr(out), L.stream())
     return out
 
 

@@ -114,7 +114,8 @@ class NeRFPipeline(Pipeline):
             pts = self.point_preprocessor(pts[None])[0]
         if self.config["include_height"]:
             pts = append_heights(pts[None], self.ray_origin_height, self.scale, self.offset)[0]
-        enc = positional_encoding(pts.float(), self.config["encoder"]["L_x"]).view(pts.shape[0], -1).float()
+        # float64 points (scripts/extract.py) are encoded in float64 and rounded once, like the reference
+        enc = positional_encoding(pts, self.config["encoder"]["L_x"]).view(pts.shape[0], -1).float()
         _, sigma = self.nerf["fine"].forward_pos_only(enc)
         return torch.clip(sigma, min=0)
 

@@ -877,23 +877,35 @@ struct PeCfg {
   int32_t C, width, interleaved;
 };
 
-__global__ void k_positional_encoding(const float* __restrict__ pts, int64_t M, PeCfg cfg, float* __restrict__ out) {
+// T = float: the training path (float32 points, float32 phases). T = double: the extract path, where
+// the reference keeps the float64 points of scripts/extract.py through the encoder (nerf.py:209-213):
+// the float32 factor 2^l * pi is widened, the phase and sin / cos are float64, the result is rounded
+// once to float32.
+template <typename T>
+__global__ void k_positional_encoding(const T* __restrict__ pts, int64_t M, PeCfg cfg, float* __restrict__ out) {
   const int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
   if (i >= M) return;
   const float PI_F = 3.14159265358979323846f;
   float* row = out + i * cfg.width;
   for (int a = 0; a < cfg.C; ++a) {
-    const float p = pts[i * cfg.C + a];
+    const T p = pts[i * cfg.C + a];
     const int L = cfg.freqs[a];
     float f = 1.0f;
     for (int l = 0; l < L; ++l) {
-      const float arg = (f * PI_F) * p;
-      if (cfg.interleaved) {
-        row[cfg.col0[a] + 2 * l] = sinf(arg);
-        row[cfg.col0[a] + 2 * l + 1] = cosf(arg);
+      float sn, cs;
+      if constexpr (sizeof(T) == 8) {
+        const double arg = (double)(f * PI_F) * p;
+        sn = (float)sin(arg), cs = (float)cos(arg);
       } else {
-        row[cfg.col0[a] + l] = sinf(arg);
-        row[cfg.col0[a] + L + l] = cosf(arg);
+        const float arg = (f * PI_F) * p;
+        sn = sinf(arg), cs = cosf(arg);
+      }
+      if (cfg.interleaved) {
+        row[cfg.col0[a] + 2 * l] = sn;
+        row[cfg.col0[a] + 2 * l + 1] = cs;
+      } else {
+        row[cfg.col0[a] + l] = sn;
+        row[cfg.col0[a] + L + l] = cs;
       }
       f *= 2.0f;
     }
@@ -1361,10 +1373,8 @@ int atmonr_extract_sigma(const atmonr_frame_t* f, const atmonr_grid_t* g, const 
   return 0;
 }
 
-int atmonr_positional_encoding(const float* pts, int64_t M, int C, const int32_t* freqs, int interleaved,
-                               float* out, void* stream) {
-  ATM_REQUIRE(C >= 1 && C <= 4 && freqs, "atmonr_positional_encoding", "C must be 1..4");
-  PeCfg cfg;
+static int pe_config(int C, const int32_t* freqs, int interleaved, PeCfg& cfg) {
+  if (!(C >= 1 && C <= 4 && freqs)) return -1;
   int col = 0;
   for (int a = 0; a < 4; ++a) {
     cfg.freqs[a] = a < C ? freqs[a] : 0;
@@ -1374,9 +1384,26 @@ int atmonr_positional_encoding(const float* pts, int64_t M, int C, const int32_t
   cfg.C = C;
   cfg.width = col;
   cfg.interleaved = interleaved;
+  return 0;
+}
+
+int atmonr_positional_encoding(const float* pts, int64_t M, int C, const int32_t* freqs, int interleaved,
+                               float* out, void* stream) {
+  PeCfg cfg;
+  ATM_REQUIRE(pe_config(C, freqs, interleaved, cfg) == 0, "atmonr_positional_encoding", "C must be 1..4");
   if (M == 0) return 0;
-  k_positional_encoding<<<grid_for(M, 256), 256, 0, S(stream)>>>(pts, M, cfg, out);
+  k_positional_encoding<float><<<grid_for(M, 256), 256, 0, S(stream)>>>(pts, M, cfg, out);
   ATM_CHECK_LAUNCH("atmonr_positional_encoding");
+  return 0;
+}
+
+int atmonr_positional_encoding_f64(const double* pts, int64_t M, int C, const int32_t* freqs, int interleaved,
+                                   float* out, void* stream) {
+  PeCfg cfg;
+  ATM_REQUIRE(pe_config(C, freqs, interleaved, cfg) == 0, "atmonr_positional_encoding_f64", "C must be 1..4");
+  if (M == 0) return 0;
+  k_positional_encoding<double><<<grid_for(M, 256), 256, 0, S(stream)>>>(pts, M, cfg, out);
+  ATM_CHECK_LAUNCH("atmonr_positional_encoding_f64");
   return 0;
 }
 

@@ -267,6 +267,11 @@ int atmonr_extract_sigma_tc(const atmonr_frame_t* frame_host, const atmonr_grid_
  * otherwise. pts (M,C) float32, C <= 4. */
 int atmonr_positional_encoding(const float* pts, int64_t M, int C, const int32_t* freqs_host,
                                int interleaved, float* out, void* stream);
+/* The same for float64 points (the extract path, pipelines/nerf.py:209-213: scripts/extract.py feeds
+ * float64 points and the reference encodes them before casting): phases and sin / cos in float64,
+ * output rounded once to float32. */
+int atmonr_positional_encoding_f64(const double* pts, int64_t M, int C, const int32_t* freqs_host,
+                                   int interleaved, float* out, void* stream);
 /* samplers.py:50-103 sample_pdf up to and including the sort: weights (B,Nc) (the V == 1
  * column), z_coarse (B,Nc), u (B,Nf) -> z_sorted (B,Nc+Nf), inds (B,Nf) int64. */
 int atmonr_sample_pdf(const float* weights, const float* z_coarse, const float* u, int64_t B,

@@ -157,3 +157,19 @@ def test_ngp_extract_with_optional_inputs_vs_oracle(height, multi_band):
     got = pipe.extract(pts.cuda()).detach().cpu()
     assert got.shape == want.shape == (700, 4 if multi_band else 1)
     assert float((got - want).abs().max()) <= 2e-3 * float(want.abs().max() + 1e-12)
+
+
+def test_positional_encoding_of_float64_points():
+    """encoders.py:4-28 on float64 points (the extract path): phases in float64, one rounding to float32.
+    At L = 14 a float32 phase is off by up to 2^13 * pi * 6e-8 = 1.5e-3 rad; the float64 flavour is not."""
+    from oracle import nerf as onerf
+    from atmonr.encoders import positional_encoding
+    g = torch.Generator().manual_seed(0)
+    p = torch.rand(513, 3, dtype=torch.float64, generator=g) * 2 - 1
+    for L in ([14, 14, 10], 4):
+        want = (onerf.pe_per_axis(p, L) if isinstance(L, list) else onerf.pe_interleaved(p, L)).float()
+        got = positional_encoding(p.cuda(), L).cpu()
+        assert got.dtype == torch.float32 and got.shape == want.shape
+        assert float((got - want).abs().max()) <= 2e-7
+        low = positional_encoding(p.float().cuda(), L).cpu()          # the float32 flavour is unchanged
+        assert float((low - want).abs().max()) <= (2e-3 if isinstance(L, list) else 4e-6)
