@@ -229,3 +229,27 @@ def test_voxel_traversal_matches_reference(tag):
         assert tuple(p) in have
     with pytest.raises(ValueError):
         graphics_utils.voxel_traversal(u, end[:5])
+
+
+def test_package_sample_pdf_differentiable_path_matches_reference():
+    """atmonr.samplers.sample_pdf on the differentiable path (the torch graph the NeRF coarse -> fine
+    gradient flows through; plain torch, so it runs here) against the reference's output for the same
+    generator state, and its gradients against the oracle's (pinned through the NeRF pipeline golden)."""
+    import sys
+    sys.path.insert(0, os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "atmospheric-neural-rendering_b200"))
+    from atmonr import samplers
+    o, d, ln = _batch()
+    batch = {"origin": o[:7], "dir": d[:7], "len": ln[:7]}
+    w = T("pdf_w").clone().requires_grad_()
+    zc = T("pdf_zc").clone().requires_grad_()
+    torch.manual_seed(77)
+    pts, z = samplers.sample_pdf(batch, w, zc, n_samples=24)
+    close(z.detach(), T("pdf_z")); close(pts.detach(), T("pdf_pts"))
+    g = torch.rand(z.shape, generator=torch.Generator().manual_seed(1))
+    (z * g).sum().backward()
+    w2 = T("pdf_w").clone().requires_grad_()
+    zc2 = T("pdf_zc").clone().requires_grad_()
+    _, z2, _ = sampling.sample_pdf(o[:7], d[:7], w2, zc2, T("pdf_u"))
+    (z2 * g).sum().backward()
+    close(w.grad, w2.grad, rtol=1e-6, atol=1e-9); close(zc.grad, zc2.grad, rtol=1e-6, atol=1e-9)
+    assert float(w.grad.abs().max()) > 0
