@@ -53,6 +53,13 @@ def main():
         out[f"vox_{tag}_set"] = torch.unique(reg, dim=0).numpy()
         full = graphics_utils.voxel_traversal(a.clone(), b.clone(), unique_only=False)
         out[f"vox_{tag}_visits"] = np.int64(full.shape[0])
+    # geospatial/spherical.py: the spherical-Earth helpers of the global-grid layout
+    from atmonr.geospatial import spherical
+    xyz = origins[:50].clone()
+    out["sph_in"] = xyz.numpy()
+    out["sph_fwd"] = spherical.wgs_84_to_spherical(xyz.clone()).numpy()
+    out["sph_back"] = spherical.spherical_to_wgs84(spherical.wgs_84_to_spherical(xyz.clone())).numpy()
+    out["sph_stretch"] = spherical.stretch_above_sea_level(spherical.wgs_84_to_spherical(xyz.clone()), 12.0).numpy()
     np.savez_compressed(HERE / "reference_vectors_extra.npz", **out)
     print({k: v.shape for k, v in out.items()})
 

@@ -253,3 +253,26 @@ def test_package_sample_pdf_differentiable_path_matches_reference():
     (z2 * g).sum().backward()
     close(w.grad, w2.grad, rtol=1e-6, atol=1e-9); close(zc.grad, zc2.grad, rtol=1e-6, atol=1e-9)
     assert float(w.grad.abs().max()) > 0
+
+
+def test_spherical_helpers_match_reference():
+    """geospatial/spherical.py (used by the global-grid extract layout): WGS-84 <-> spherical Earth and
+    the above-sea-level stretch."""
+    import sys
+    sys.path.insert(0, os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "atmospheric-neural-rendering_b200"))
+    from atmonr.geospatial import spherical
+    x = TX("sph_in")
+    close(spherical.wgs_84_to_spherical(x.clone()), TX("sph_fwd"))
+    close(spherical.spherical_to_wgs84(spherical.wgs_84_to_spherical(x.clone())), TX("sph_back"))
+    close(spherical.stretch_above_sea_level(spherical.wgs_84_to_spherical(x.clone()), 12.0), TX("sph_stretch"))
+
+
+def test_package_coarse_compositing_graph_matches_reference():
+    """pipelines/nerf.py: the coarse pass composites through a torch graph (its weights feed the fine
+    sampler's CDF); same numbers as the reference's render (golden) and the same weights."""
+    import sys
+    sys.path.insert(0, os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "atmospheric-neural-rendering_b200"))
+    from atmonr.pipelines.nerf import _composite_torch
+    for tag in ("1", "4"):
+        c, w = _composite_torch(T("r_z"), T("r_col"), T(f"r_sg{tag}"))
+        close(c, T(f"r_c{tag}"), rtol=1e-6, atol=1e-7); close(w, T(f"r_w{tag}"), rtol=1e-6, atol=1e-8)
