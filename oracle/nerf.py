@@ -77,11 +77,15 @@ def mlp_forward(sd, x_pos, x_dir, hidden, noise=None):
 
 
 class NeRFOracle:
-    def __init__(self, cfg, frame: HorizontalFrame | None):
-        self.cfg, self.frame = cfg, frame
+    def __init__(self, cfg, frame: HorizontalFrame | None, geo=None):
+        """`geo` = (scale, offset (3,) float64, ray_origin_height): what pipeline.py:30-58 captures from
+        the dataset; needed when there is no frame (no point preprocessor) or with `include_height`."""
+        self.cfg, self.frame, self.geo = cfg, frame, geo
         self.lx, self.ld = cfg["encoder"]["L_x"], cfg["encoder"]["L_d"]
         self.hidden = cfg["mlp_hidden_dim"]
-        pos_ch = sum(self.lx) * 2 if isinstance(self.lx, list) else self.lx * 6
+        self.height = bool(cfg.get("include_height", False))
+        n_pos = 4 if self.height else 3                                   # models/nerf.py:126-133
+        pos_ch = sum(self.lx) * 2 if isinstance(self.lx, list) else self.lx * 2 * n_pos
         self.shapes = {
             "coarse": mlp_shapes(pos_ch, self.ld * 6, cfg["num_bands"], 1, self.hidden),
             "fine": mlp_shapes(pos_ch, self.ld * 6, cfg["num_bands"], cfg["num_bands"], self.hidden),
@@ -102,13 +106,17 @@ class NeRFOracle:
         pts = sampling.points_on_rays(batch["origin"], batch["dir"], z)
         if self.frame is not None:
             pts = preprocess_horizontal(pts, self.frame)
+        if self.height:  # pipelines/nerf.py:127-128
+            scale, offset, h0 = self.geo
+            pts = sampling.append_heights(pts, h0, scale, offset)
         x_pos = self._encode_pos(pts).view(b * n, -1)
         dirs = batch["dir"][:, None].repeat(1, n, 1)
         x_dir = pe_interleaved(dirs, self.ld).view(b * n, -1)
         color, sigma = mlp_forward(sd, x_pos, x_dir, self.hidden, noise)
         color = torch.exp(torch.clamp(color.view(b, n, -1), max=11))
         sigma = torch.relu(sigma.view(b, n, -1))
-        c, _, w = rendering.composite(z * (self.frame.scale / 1000), color, sigma)
+        scale = self.frame.scale if self.frame is not None else self.geo[0]
+        c, _, w = rendering.composite(z * (scale / 1000), color, sigma)
         return {"color": color, "sigma": sigma, "color_map": c, "weights": w, "z_vals": z}
 
     def forward(self, batch, params, u_c, u_f, noise_c=None, noise_f=None):
@@ -134,6 +142,9 @@ class NeRFOracle:
         """pipelines/nerf.py:190-217."""
         if self.frame is not None:
             pts = preprocess_horizontal(pts[None], self.frame)[0]
+        if self.height:  # pipelines/nerf.py:205-208
+            scale, offset, h0 = self.geo
+            pts = sampling.append_heights(pts[None], h0, scale, offset)[0]
         x_pos = self._encode_pos(pts).view(pts.shape[0], -1).float()
         _, sigma = mlp_forward(params["fine"], x_pos, None, self.hidden)
         return torch.clip(sigma, min=0)

@@ -369,3 +369,73 @@ def test_batch_loader_reproduces_the_reference_order(tmp_path):
             for a, b in zip(got, want):
                 assert torch.equal(a.cpu(), b), tag
         assert torch.equal(torch.rand(3), ref[tag]["after"]), tag
+
+
+NERF_CHILD = r"""
+import sys, json, torch
+from types import SimpleNamespace
+sys.path.insert(0, sys.argv[1])
+from make_golden import import_reference
+import_reference()
+from atmonr.pipelines.nerf import NeRFPipeline
+cfg = json.loads(sys.argv[2])
+job = torch.load(sys.argv[3])
+ds = SimpleNamespace(config={"ray_origin_height": 20000}, scale=job["scale"], offset=job["offset"], max_i=0.3,
+                     get_point_preprocessor=lambda name: None)
+pipe = NeRFPipeline(cfg, ds)
+pipe.load_state_dict(job["params"])
+pipe.eval()                                            # no density noise: deterministic given the two draws
+torch.manual_seed(job["seed"])
+res = pipe.forward(job["batch"])
+loss = pipe.compute_loss(job["batch"], res)
+loss.backward()
+sig = pipe.extract(job["pts"].clone())
+torch.save({"res": {k: v.detach() for k, v in res.items()}, "loss": loss.detach(), "extract": sig.detach(),
+            "grads": {m: {n: p.grad for n, p in pipe.nerf[m].named_parameters() if p.grad is not None} for m in ("coarse", "fine")}},
+           sys.argv[4])
+"""
+
+
+@pytest.mark.parametrize("variant", ["int_L", "include_height"])
+def test_nerf_oracle_variants_match_the_reference_pipeline(tmp_path, variant):
+    """The NeRF configurations off the shipped config (pipelines/nerf.py:73-217): a scalar `L_x`
+    (interleaved encoding layout) without a point preprocessor, and `include_height` (4 encoded
+    coordinates): the reference's NeRFPipeline against oracle/nerf.py, forward, loss, gradients, extract."""
+    from atmonr.datasets.harp2 import HARP2Dataset
+    from oracle import nerf as onerf
+    cfgd = json.load(open(os.path.join(ROOT, "configs", "instant_ngp.json")))["dataset"]
+    ds = HARP2Dataset(dict(cfgd), "synthetic:H=10,W=9,seed=4", device=torch.device("cpu"))
+    cfg = json.load(open(os.path.join(ROOT, "configs", "nerf.json")))["pipeline"]
+    cfg.update(mlp_hidden_dim=32, point_preprocessor="", sampler={"N_c": 8, "N_f": 16})
+    if variant == "int_L":
+        cfg["encoder"] = {"L_x": 5, "L_d": 3}
+    else:
+        cfg["include_height"], cfg["encoder"] = True, {"L_x": [4, 4, 4, 3], "L_d": 3}
+    orc = onerf.NeRFOracle(cfg, None, geo=(ds.scale, ds.offset, 20000.0))
+    params = orc.init_params(2)
+    idx = torch.arange(3, len(ds), 301)[:20]
+    batch = {k: v for k, v in ds[idx].items()}
+    g = torch.Generator().manual_seed(1)
+    pts = torch.rand(30, 3, dtype=torch.float64, generator=g) * 0.2 + batch["origin"][:1].double()
+    job, out = str(tmp_path / "job.pt"), str(tmp_path / "ref.pt")
+    torch.save({"params": {m: {k: v.detach() for k, v in params[m].items()} for m in params}, "batch": batch,
+                "seed": 31, "pts": pts, "scale": ds.scale, "offset": ds.offset}, job)
+    r = subprocess.run([sys.executable, "-c", NERF_CHILD, os.path.join(ROOT, "tests", "golden"), json.dumps(cfg), job, out],
+                       capture_output=True, text=True, timeout=600)
+    assert r.returncode == 0, r.stderr[-3000:]
+    ref = torch.load(out, weights_only=False)
+    torch.manual_seed(31)
+    u_c, u_f = torch.rand(20, 8), torch.rand(20, 16)
+    res = orc.forward(batch, params, u_c, u_f)
+    loss = orc.loss(batch, res)
+    loss.backward()
+    for k, v in ref["res"].items():
+        if k.startswith("norm_heights"):
+            continue
+        assert torch.allclose(res[k].detach(), v, rtol=2e-5, atol=1e-7), (k, float((res[k].detach() - v).abs().max()))
+    assert abs(float(loss.detach()) - float(ref["loss"])) <= 1e-5 * abs(float(ref["loss"]))
+    for m in ("coarse", "fine"):
+        for n in ("fc1.weight", "fc6.weight", "fc11.weight"):
+            a, b = params[m][n].grad, ref["grads"][m][n]
+            assert float((a - b).abs().max()) <= 1e-4 * float(b.abs().max() + 1e-30), (m, n)
+    assert torch.allclose(orc.extract(pts, params).detach(), ref["extract"], rtol=2e-5, atol=1e-7)
