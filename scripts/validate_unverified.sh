@@ -10,7 +10,10 @@ mkdir -p gpurun_out
 python -c "import __graft_entry__ as g; g.build()" || exit 1
 timeout 300 python -m pytest tests/test_zz_gpu_rays.py -x -q > gpurun_out/unverified_rays.log 2>&1
 echo "rays: exit $?" | tee -a gpurun_out/unverified_summary.txt
-ATMONR_RUN_UNVERIFIED=1 timeout 300 python -m pytest tests/test_zz_gpu_linear_tc.py tests/test_zz_gpu_unverified_modes.py -x -q \
+ATMONR_RUN_UNVERIFIED=1 timeout 300 python -m pytest tests/test_zz_gpu_unverified_modes.py -q \
+  > gpurun_out/unverified_modes.log 2>&1
+echo "nerf modes: exit $?" | tee -a gpurun_out/unverified_summary.txt
+ATMONR_RUN_UNVERIFIED=1 timeout 300 python -m pytest tests/test_zz_gpu_linear_tc.py -x -q \
   > gpurun_out/unverified_linear_tc.log 2>&1
 rc=$?
 echo "linear_tc: exit $rc" | tee -a gpurun_out/unverified_summary.txt
