@@ -122,13 +122,16 @@ torch.save({"view_idx": ds.view_idx, "irgb_idx": ds.irgb_idx, "img_shp": tuple(d
 """
 
 
-def test_dataset_matches_the_reference_dataset_on_the_synthetic_granule(tmp_path):
+@pytest.mark.parametrize("variant", ["shipped", "most_pixels_rgb_30deg_no_nir"])
+def test_dataset_matches_the_reference_dataset_on_the_synthetic_granule(tmp_path, variant):
     """a1 + a2 + a3 + the `horizontal` closure through the reference's OWN HARP2Dataset
     (datasets/harp2.py:26-429), fed the synthetic granule through a stand-in for netCDF4.Dataset."""
     from atmonr.datasets.factory import get_dataset
     from atmonr.datasets.harp2 import HARP2Dataset
     spec = "synthetic:H=10,W=9,seed=4"
     cfg = json.load(open(os.path.join(ROOT, "configs", "instant_ngp.json")))["dataset"]
+    if variant != "shipped":      # the other RGB view choice, a tighter view-angle filter, a dropped band
+        cfg.update(rgb_mode="most_pixels", max_abs_view_angle=30.0, bands_to_keep=[1, 2, 3])
     out = str(tmp_path / "ref_ds.pt")
     r = subprocess.run([sys.executable, "-c", DATASET_CHILD, os.path.join(ROOT, "tests", "golden"),
                         os.path.join(ROOT, "atmospheric-neural-rendering_b200", "atmonr", "datasets", "granule.py"),
