@@ -17,18 +17,19 @@ HARP2_BANDS = ((440.0, 10), (550.0, 10), (670.0, 60), (870.0, 10))
 
 
 class SyntheticGranule:
-    """`synthetic:H=64,W=64,seed=0[,nan=0.02]` -- geometry of a 5 x 5 degree scene off the US east
-    coast seen by 90 along-track views within +-45 degrees; intensities are a smooth function of
+    """`synthetic:H=64,W=64,seed=0[,nan=0.02][,lat0=30][,lon0=-75]` -- geometry of a 5 x 5 degree scene
+    (south-west corner lat0, lon0; default off the US east coast; longitudes wrap at the dateline) seen
+    by 90 along-track views within +-45 degrees; intensities are a smooth function of
     position, band and view angle plus noise, with a fraction of NaN pixels."""
 
     processing_level = "L1B"
 
     def __init__(self, spec: str):
-        opts = {"H": 64, "W": 64, "seed": 0, "nan": 0.02}
+        opts = {"H": 64, "W": 64, "seed": 0, "nan": 0.02, "lat0": 30.0, "lon0": -75.0}
         body = spec.split(":", 1)[1] if ":" in spec else ""
         for item in filter(None, body.split(",")):
             k, v = item.split("=")
-            opts[k] = float(v) if k == "nan" else int(v)
+            opts[k] = float(v) if k in ("nan", "lat0", "lon0") else int(v)
         h, w = int(opts["H"]), int(opts["W"])
         rng = np.random.default_rng(int(opts["seed"]))
         wl, ang = [], []
@@ -39,8 +40,10 @@ class SyntheticGranule:
         self.view_angles = np.asarray(ang, dtype=np.float32)
         v = len(wl)
         # image rows run south -> north in the file (HARP2Dataset flips them so north is up)
-        lat = np.linspace(30.0, 35.0, h, dtype=np.float32)[:, None] + np.zeros((1, w), np.float32)
-        lon = np.linspace(-75.0, -70.0, w, dtype=np.float32)[None, :] + np.zeros((h, 1), np.float32)
+        lat0, lon0 = float(opts["lat0"]), float(opts["lon0"])
+        lat = np.linspace(lat0, lat0 + 5.0, h, dtype=np.float32)[:, None] + np.zeros((1, w), np.float32)
+        lon = np.linspace(lon0, lon0 + 5.0, w, dtype=np.float32)[None, :] + np.zeros((h, 1), np.float32)
+        lon = np.where(lon > 180.0, lon - 360.0, lon).astype(np.float32)
         self._fields = {
             "latitude": np.broadcast_to(lat, (v, h, w)).copy(),
             "longitude": np.broadcast_to(lon, (v, h, w)).copy(),

@@ -122,7 +122,7 @@ torch.save({"view_idx": ds.view_idx, "irgb_idx": ds.irgb_idx, "img_shp": tuple(d
 """
 
 
-@pytest.mark.parametrize("variant", ["shipped", "most_pixels_rgb_30deg_no_nir"])
+@pytest.mark.parametrize("variant", ["shipped", "most_pixels_rgb_30deg_no_nir", "dateline"])
 def test_dataset_matches_the_reference_dataset_on_the_synthetic_granule(tmp_path, variant):
     """a1 + a2 + a3 + the `horizontal` closure through the reference's OWN HARP2Dataset
     (datasets/harp2.py:26-429), fed the synthetic granule through a stand-in for netCDF4.Dataset."""
@@ -130,7 +130,9 @@ def test_dataset_matches_the_reference_dataset_on_the_synthetic_granule(tmp_path
     from atmonr.datasets.harp2 import HARP2Dataset
     spec = "synthetic:H=10,W=9,seed=4"
     cfg = json.load(open(os.path.join(ROOT, "configs", "instant_ngp.json")))["dataset"]
-    if variant != "shipped":      # the other RGB view choice, a tighter view-angle filter, a dropped band
+    if variant == "dateline":     # a granule across the dateline: the lon-shift branch of harp2.py:366-370
+        spec = "synthetic:H=10,W=9,seed=4,lat0=-62,lon0=177.5"
+    elif variant != "shipped":    # the other RGB view choice, a tighter view-angle filter, a dropped band
         cfg.update(rgb_mode="most_pixels", max_abs_view_angle=30.0, bands_to_keep=[1, 2, 3])
     out = str(tmp_path / "ref_ds.pt")
     r = subprocess.run([sys.executable, "-c", DATASET_CHILD, os.path.join(ROOT, "tests", "golden"),
@@ -161,6 +163,13 @@ def test_dataset_matches_the_reference_dataset_on_the_synthetic_granule(tmp_path
     from oracle import geodesy
     lat, lon = ds.lat[~ds.lat.isnan()], ds.lon[~ds.lon.isnan()]
     frame = geodesy.HorizontalFrame.from_latlon(lat, lon, ds.scale, ds.offset, 20000.0)
+    assert frame.shift_lon == (variant == "dateline")
+    # the constants this package hands to the sampler kernel are the closure's
+    fr = ds.get_point_preprocessor("horizontal").frame
+    assert bool(fr.shift_lon) == frame.shift_lon and fr.enabled == 1
+    for name in ("scale", "lat_min", "lat_range", "lon_min", "lon_range", "origin_height"):
+        assert getattr(fr, name) == getattr(frame, name), name
+    assert tuple(fr.offset) == tuple(frame.offset)
     assert torch.equal(geodesy.preprocess_horizontal(ref["p32"], frame), ref["pre32"])
     assert float((geodesy.preprocess_horizontal(ref["p64"], frame) - ref["pre64"]).abs().max()) <= 1e-12
 
