@@ -451,3 +451,143 @@ def test_nerf_oracle_variants_match_the_reference_pipeline(tmp_path, variant):
             a, b = params[m][n].grad, ref["grads"][m][n]
             assert float((a - b).abs().max()) <= 1e-4 * float(b.abs().max() + 1e-30), (m, n)
     assert torch.allclose(orc.extract(pts, params).detach(), ref["extract"], rtol=2e-5, atol=1e-7)
+
+
+# ------------------------------------------------------------------------------------------
+# the reference's Trainer, end to end, against this package's Trainer
+# ------------------------------------------------------------------------------------------
+TRAINER_CHILD = NGP_CHILD.split("from atmonr.datasets.harp2 import HARP2Dataset\nfrom atmonr.pipelines.instant_ngp import InstantNGPPipeline")[0] + r"""
+import numpy as np
+torch.cuda.current_device = lambda: 0
+from atmonr.datasets import harp2 as ref_harp2
+from atmonr.datasets.harp2 import HARP2Dataset
+from atmonr.pipelines.instant_ngp import InstantNGPPipeline
+from atmonr import trainer as ref_trainer
+
+def _psnr(pred, target, dim, reduction, data_range):      # torchmetrics' definition, for the stub
+    return 10 * torch.log10(data_range ** 2 / ((pred - target) ** 2).mean(dim=dim))
+ref_harp2.peak_signal_noise_ratio = _psnr
+ref_harp2.structural_similarity_index_measure = lambda p, t, reduction: torch.zeros(p.shape[0])
+
+class Recorder:
+    def __init__(self, *a, **k): self.scalars, self.images = [], []
+    def add_scalar(self, tag, val, step): self.scalars.append((tag, float(val), int(step)))
+    def add_image(self, tag, img): self.images.append((tag, np.array(img)))
+ref_trainer.SummaryWriter = Recorder
+
+cfg = json.loads(sys.argv[4])
+ds = HARP2Dataset(cfg["dataset"], "fake.nc")
+pipe = InstantNGPPipeline(cfg["pipeline"], ds)
+pipe.send_tensors_to("cpu")
+job = torch.load(sys.argv[8])
+for name, p in job["params"].items():
+    getattr(pipe, name).params.data.copy_(p)
+torch.manual_seed(job["seed"])
+tr = ref_trainer.Trainer(cfg["trainer"], ds, pipe, "t")
+outdir = Path(sys.argv[5]) / "ref_run"
+outdir.mkdir()
+tr.train(outdir)
+ck = sorted(outdir.glob("epoch_*.pt"))
+last = torch.load(ck[-1], weights_only=False)
+torch.save({"scalars": tr.writer.scalars, "images": tr.writer.images, "lr": tr.optimizer.param_groups[0]["lr"],
+            "iter_count": tr.iter_count, "epoch_idx": tr.epoch_idx, "num_epochs": tr.num_epochs,
+            "ckpts": [c.name for c in ck], "ck_keys": sorted(last), "ck_pipeline": last["pipeline"],
+            "params": {n: getattr(pipe, n).params.detach().clone() for n in job["params"]}}, sys.argv[6])
+"""
+
+
+class _OracleBackedPipeline:
+    """Test-only adapter: the Pipeline surface this package's Trainer talks to, computed by the oracle
+    (the native pipeline needs a GPU; the Trainer's own logic does not)."""
+
+    def __init__(self, orc, params):
+        self.orc, self.params, self.device = orc, params, "cpu"
+
+    def get_optimizer(self, cfg):
+        return self.orc.make_optimizer(self.params, cfg)
+
+    def forward(self, batch):
+        u = torch.rand((batch["origin"].shape[0], self.orc.cfg["num_samples_per_ray"]))   # samplers.py:37
+        return self.orc.forward(batch, self.params, u)
+
+    def compute_loss(self, batch, results):
+        return self.orc.loss(batch, results)
+
+    def state_dict(self):
+        return {k: {"params": v.detach().clone()} for k, v in self.params.items()}
+
+
+def test_trainer_matches_the_reference_trainer(tmp_path, monkeypatch):
+    """trainer.py:26-274 end to end: the reference's Trainer drives its InstantNGPPipeline (stand-in
+    tcnn) for two epochs; this package's Trainer drives the oracle from the same seed. Same batches in
+    the same order, same per-iteration losses under the same step indices, same learning-rate decays,
+    same PSNR and progress image at each epoch end, same checkpoints."""
+    from atmonr import trainer as T
+    from atmonr.datasets.harp2 import HARP2Dataset
+    from oracle import geodesy
+    from oracle.ngp import NGPOracle
+    spec = "synthetic:H=12,W=12,seed=2"
+    cfg = json.load(open(os.path.join(ROOT, "configs", "instant_ngp.json")))
+    cfg["pipeline"]["num_samples_per_ray"] = 8
+    for key in ("encoding", "surface_encoding"):
+        cfg["pipeline"]["instant_ngp"][key]["log2_hashmap_size"] = 10
+    cfg["trainer"].update(batch_size=4096, num_iters=7, print_frequency=3,
+                          scheduler={"type": "fixed", "gamma": 0.5, "decay_start": 2, "decay_interval": 2})
+    ds = HARP2Dataset(dict(cfg["dataset"]), spec, device=torch.device("cpu"))
+    lat, lon = ds.lat[~ds.lat.isnan()], ds.lon[~ds.lon.isnan()]
+    frame = geodesy.HorizontalFrame.from_latlon(lat, lon, ds.scale, ds.offset, 20000.0)
+    orc = NGPOracle(cfg["pipeline"], frame, ds.max_i, fp16=False)
+    params = orc.init_params(7)
+    with torch.no_grad():
+        for k in ("pos_encoder", "surf_encoder"):
+            params[k].mul_(3e3)
+    job, out = str(tmp_path / "job.pt"), str(tmp_path / "ref_trainer.pt")
+    torch.save({"params": {k: v.detach() for k, v in params.items()}, "seed": 99}, job)
+    r = subprocess.run([sys.executable, "-c", TRAINER_CHILD, os.path.join(ROOT, "tests", "golden"),
+                        os.path.join(ROOT, "atmospheric-neural-rendering_b200", "atmonr", "datasets", "granule.py"),
+                        spec, json.dumps(cfg), str(tmp_path), out, ROOT, job], capture_output=True, text=True, timeout=1200)
+    assert r.returncode == 0, r.stderr[-3000:]
+    ref = torch.load(out, weights_only=False)
+
+    class Recorder:
+        def __init__(self):
+            self.scalars, self.images = [], []
+
+        def add_scalar(self, tag, val, step):
+            self.scalars.append((tag, float(val), int(step)))
+
+        def add_image(self, tag, img):
+            self.images.append((tag, img))
+
+    monkeypatch.chdir(tmp_path)
+    monkeypatch.setattr(torch.cuda, "current_device", lambda: 0)
+    monkeypatch.setattr(T, "_make_writer", lambda d: Recorder())
+    pipe = _OracleBackedPipeline(orc, params)
+    torch.manual_seed(99)
+    tr = T.Trainer(cfg["trainer"], ds, pipe, "t")
+    outdir = tmp_path / "my_run"
+    outdir.mkdir()
+    tr.train(outdir)
+    assert (tr.iter_count, tr.epoch_idx, tr.num_epochs) == (ref["iter_count"], ref["epoch_idx"], ref["num_epochs"])
+    assert tr.optimizer.param_groups[0]["lr"] == pytest.approx(ref["lr"])
+    mine_loss = [(s, v) for t, v, s in tr.writer.scalars if t == "Loss"]
+    ref_loss = [(s, v) for t, v, s in ref["scalars"] if t == "Loss"]
+    assert [s for s, _ in mine_loss] == [s for s, _ in ref_loss] == list(range(7))
+    for (_, a), (_, b) in zip(mine_loss, ref_loss):
+        assert abs(a - b) <= 2e-4 * abs(b), (mine_loss, ref_loss)
+    mine_psnr = [v for t, v, s in tr.writer.scalars if t == "PSNR_mean"]
+    ref_psnr = [v for t, v, s in ref["scalars"] if t == "PSNR_mean"]
+    assert len(mine_psnr) == len(ref_psnr) == 2
+    assert all(abs(a - b) <= 1e-3 * abs(b) for a, b in zip(mine_psnr, ref_psnr))
+    assert [t for t, _ in tr.writer.images] == [t for t, _ in ref["images"]]
+    for (_, a), (_, b) in zip(tr.writer.images, ref["images"]):
+        assert a.shape == b.shape and abs(a - b).max() <= 1e-4
+    ck = sorted(outdir.glob("epoch_*.pt"))
+    assert [c.name for c in ck] == ref["ckpts"]
+    last = torch.load(ck[-1], weights_only=False)
+    assert sorted(last) == ref["ck_keys"]
+    for name, p in ref["params"].items():
+        assert params[name].shape == p.shape, name
+        if p.numel():                                       # dir_encoder has no parameters
+            assert float((params[name].detach() - p).abs().max()) <= 2e-4 * float(p.abs().max() + 1e-30), name
+        assert list(last["pipeline"][name]) == list(ref["ck_pipeline"][name]) == ["params"]
