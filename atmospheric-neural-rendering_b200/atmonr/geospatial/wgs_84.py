@@ -145,3 +145,100 @@ def normalize_rays(ray_origin, ray_dir, ray_len):
     scale = ((hi - lo).max() / 2).item()
     offset = (hi + lo) / 2
     return torch.clamp((ray_origin - offset) / scale, -1, 1).float(), scale, offset
+
+
+# ---- Vincenty's formulae on the WGS-84 ellipsoid (wgs_84.py:342-575) ------------------------------
+# Used by the reference's Vincenty voxel-grid layout (datasets/harp2_extract.py:189-348), which this
+# build replaces by a regular grid; the two functions keep the reference's conventions so that layout
+# code written against them keeps working: angles in degrees in, distances in metres, the inverse
+# problem returns both azimuths in DEGREES, the direct problem returns the destination in degrees
+# (longitude not wrapped) and the arrival azimuth in RADIANS, and a stalled iteration raises Warning.
+def _reduced(lat_deg):
+    """Reduced latitude U: tan U = (1 - f) tan(lat)."""
+    return torch.atan((1 - WGS_84_F) * torch.tan(lat_deg * torch.pi / 180))
+
+
+def _vincenty_series(cos2_alpha):
+    """Vincenty's A and B as functions of u^2 = cos^2(alpha) (a^2 - b^2) / b^2."""
+    u2 = cos2_alpha * (WGS_84_A**2 - WGS_84_B**2) / WGS_84_B**2
+    big_a = 1 + (u2 / 16384) * (4096 + u2 * (-768 + u2 * (320 - 175 * u2)))
+    big_b = (u2 / 1024) * (256 + u2 * (-128 + u2 * (74 - 47 * u2)))
+    return big_a, big_b
+
+
+def _delta_sigma(big_b, sin_s, cos_s, cos_2sm):
+    inner = cos_s * (-1 + 2 * cos_2sm**2) - (1 / 6) * big_b * cos_2sm * (-3 + 4 * sin_s**2) * (-3 + 4 * cos_2sm**2)
+    return big_b * sin_s * (cos_2sm + (1 / 4) * big_b * inner)
+
+
+def _longitude_term(sin_alpha, cos2_alpha, sigma, sin_s, cos_s, cos_2sm):
+    """(1 - C) f sin(alpha) [sigma + C sin(sigma) (cos 2sigma_m + C cos(sigma) (-1 + 2 cos^2 2sigma_m))]"""
+    c = (WGS_84_F / 16) * cos2_alpha * (4 + WGS_84_F * (4 - 3 * cos2_alpha))
+    return (1 - c) * WGS_84_F * sin_alpha * (sigma + c * sin_s * (cos_2sm + c * cos_s * (-1 + 2 * cos_2sm**2)))
+
+
+def vincenty_distance(latlon1, latlon2, tol: float = 1e-12, max_iters: int = 10):
+    """Inverse problem: geodesic distance (m) and the forward azimuths (degrees) at both ends.
+    latlon1 / latlon2: (lat, lon) tuples or (2, ...) tensors, degrees. wgs_84.py:342-449."""
+    if not isinstance(tol, float) or not isinstance(max_iters, int):
+        raise AssertionError("tol must be a float and max_iters an int")
+    u1, u2 = _reduced(latlon1[0]), _reduced(latlon2[0])
+    su1, cu1, su2, cu2 = torch.sin(u1), torch.cos(u1), torch.sin(u2), torch.cos(u2)
+    dlon = latlon2[1] * torch.pi / 180 - latlon1[1] * torch.pi / 180
+    lam, n_iter = dlon, 0
+    while True:
+        if n_iter > max_iters:
+            raise Warning(f"Exceeded {max_iters} iterations without lambda changing by less than {tol:.1e}")
+        sl, cl = torch.sin(lam), torch.cos(lam)
+        sin_s = torch.sqrt((cu2 * sl) ** 2 + (cu1 * su2 - su1 * cu2 * cl) ** 2)
+        cos_s = su1 * su2 + cu1 * cu2 * cl
+        sigma = torch.atan2(sin_s, cos_s)
+        sin_alpha = cu1 * cu2 * sl / sin_s
+        cos2_alpha = 1 - sin_alpha**2
+        cos_2sm = cos_s - (2 * su1 * su2) / cos2_alpha
+        new = dlon + _longitude_term(sin_alpha, cos2_alpha, sigma, sin_s, cos_s, cos_2sm)
+        step, lam, n_iter = new - lam, new, n_iter + 1
+        if not bool((torch.abs(step) > tol).any()):
+            break
+    big_a, big_b = _vincenty_series(cos2_alpha)
+    s = WGS_84_B * big_a * (sigma - _delta_sigma(big_b, sin_s, cos_s, cos_2sm))
+    sl, cl = torch.sin(lam), torch.cos(lam)
+    alpha1 = torch.atan2(cu2 * sl, cu1 * su2 - su1 * cu2 * cl)
+    alpha2 = torch.atan2(cu1 * sl, -su1 * cu2 + cu1 * su2 * cl)
+    return s, alpha1 * 180 / math.pi, alpha2 * 180 / math.pi
+
+
+def vincenty_point_along_geodesic(latlon1, alpha1, s, tol: float = 1e-6, max_iters: int = 10):
+    """Direct problem: the point `s` metres along the geodesic leaving latlon1 (degrees) at azimuth
+    alpha1 (degrees). Returns ((lat2, lon2) in degrees, same container kind as latlon1; arrival azimuth in
+    radians). wgs_84.py:452-575."""
+    if not isinstance(alpha1, torch.Tensor) or not isinstance(s, torch.Tensor):
+        raise AssertionError("alpha1 and s must be tensors")
+    if not isinstance(tol, float) or not isinstance(max_iters, int):
+        raise AssertionError("tol must be a float and max_iters an int")
+    lon1 = latlon1[1] * torch.pi / 180
+    az = alpha1 * torch.pi / 180
+    u1 = _reduced(latlon1[0])
+    su1, cu1, saz, caz = torch.sin(u1), torch.cos(u1), torch.sin(az), torch.cos(az)
+    sigma1 = torch.atan2(torch.tan(u1), caz)
+    sin_alpha = cu1 * saz
+    cos2_alpha = 1 - sin_alpha**2
+    big_a, big_b = _vincenty_series(cos2_alpha)
+    first = s / (WGS_84_B * big_a)
+    sigma, n_iter = first, 0
+    while True:
+        if n_iter > max_iters:
+            raise Warning(f"Exceeded {max_iters} iterations without sigma changing by less than {tol:.1e}")
+        cos_2sm = torch.cos(2 * sigma1 + sigma)
+        new = first + _delta_sigma(big_b, torch.sin(sigma), torch.cos(sigma), cos_2sm)
+        step, sigma, n_iter = new - sigma, new, n_iter + 1
+        if not bool((torch.abs(step) > tol).any()):
+            break
+    ss, cs = torch.sin(sigma), torch.cos(sigma)
+    lat2 = torch.atan2(su1 * cs + cu1 * ss * caz,
+                       (1 - WGS_84_F) * torch.sqrt(sin_alpha**2 + (su1 * ss - cu1 * cs * caz) ** 2))
+    lam = torch.atan2(ss * saz, cu1 * cs - su1 * ss * caz)
+    lon2 = lam - _longitude_term(sin_alpha, cos2_alpha, sigma, ss, cs, cos_2sm) + lon1
+    alpha2 = torch.atan2(sin_alpha, -su1 * ss + cu1 * cs * caz)
+    lat2, lon2 = lat2 * 180 / torch.pi, lon2 * 180 / torch.pi
+    return ((lat2, lon2) if isinstance(latlon1, tuple) else torch.stack([lat2, lon2])), alpha2

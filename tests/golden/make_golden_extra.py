@@ -60,6 +60,19 @@ def main():
     out["sph_fwd"] = spherical.wgs_84_to_spherical(xyz.clone()).numpy()
     out["sph_back"] = spherical.spherical_to_wgs84(spherical.wgs_84_to_spherical(xyz.clone())).numpy()
     out["sph_stretch"] = spherical.stretch_above_sea_level(spherical.wgs_84_to_spherical(xyz.clone()), 12.0).numpy()
+    # Vincenty inverse / direct problems (wgs_84.py:342-575), float64 inputs
+    g = torch.Generator().manual_seed(33)
+    la1 = torch.rand(40, generator=g, dtype=torch.float64) * 120 - 60
+    lo1 = torch.rand(40, generator=g, dtype=torch.float64) * 300 - 150
+    la2 = la1 + torch.rand(40, generator=g, dtype=torch.float64) * 8 - 4
+    lo2 = lo1 + torch.rand(40, generator=g, dtype=torch.float64) * 8 - 4
+    s_, a1, a2 = wgs_84.vincenty_distance((la1, lo1), (la2, lo2))
+    out["vin_ll1"], out["vin_ll2"] = torch.stack([la1, lo1]).numpy(), torch.stack([la2, lo2]).numpy()
+    out["vin_s"], out["vin_a1"], out["vin_a2"] = s_.numpy(), a1.numpy(), a2.numpy()
+    (la3, lo3), a3 = wgs_84.vincenty_point_along_geodesic((la1, lo1), a1, s_ * 0.37)
+    out["vin_d_lat"], out["vin_d_lon"], out["vin_d_a2"] = la3.numpy(), lo3.numpy(), a3.numpy()
+    ll4, _ = wgs_84.vincenty_point_along_geodesic(torch.stack([la1, lo1]), a1, s_)
+    out["vin_d_full"] = ll4.numpy()
     np.savez_compressed(HERE / "reference_vectors_extra.npz", **out)
     print({k: v.shape for k, v in out.items()})
 

@@ -276,3 +276,24 @@ def test_package_coarse_compositing_graph_matches_reference():
     for tag in ("1", "4"):
         c, w = _composite_torch(T("r_z"), T("r_col"), T(f"r_sg{tag}"))
         close(c, T(f"r_c{tag}"), rtol=1e-6, atol=1e-7); close(w, T(f"r_w{tag}"), rtol=1e-6, atol=1e-8)
+
+
+def test_vincenty_functions_match_reference():
+    """geospatial/wgs_84.py vincenty_distance / vincenty_point_along_geodesic (wgs_84.py:342-575):
+    distances, both azimuths, intermediate and end points, on 40 random geodesics of a few hundred km."""
+    import sys
+    sys.path.insert(0, os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "atmospheric-neural-rendering_b200"))
+    from atmonr.geospatial import wgs_84
+    ll1, ll2 = TX("vin_ll1"), TX("vin_ll2")
+    s, a1, a2 = wgs_84.vincenty_distance((ll1[0], ll1[1]), (ll2[0], ll2[1]))
+    close(s, TX("vin_s"), rtol=1e-12); close(a1, TX("vin_a1"), atol=1e-9); close(a2, TX("vin_a2"), atol=1e-9)
+    (la, lo), az = wgs_84.vincenty_point_along_geodesic((ll1[0], ll1[1]), a1, s * 0.37)
+    close(la, TX("vin_d_lat"), atol=1e-11); close(lo, TX("vin_d_lon"), atol=1e-11); close(az, TX("vin_d_a2"), atol=1e-11)
+    full, _ = wgs_84.vincenty_point_along_geodesic(ll1, a1, s)
+    assert isinstance(full, torch.Tensor) and full.shape == (2, 40)      # tensor in, stacked tensor out
+    close(full, TX("vin_d_full"), atol=1e-11)
+    close(full, ll2, atol=1e-7)                                          # direct(inverse) closes the loop (1 cm)
+    with pytest.raises(Warning):                                         # a stalled iteration raises, like the reference
+        wgs_84.vincenty_distance((ll1[0], ll1[1]), (ll2[0], ll2[1]), tol=1e-30, max_iters=2)
+    with pytest.raises(AssertionError):
+        wgs_84.vincenty_point_along_geodesic((ll1[0], ll1[1]), 10.0, s)
