@@ -591,3 +591,47 @@ def test_trainer_matches_the_reference_trainer(tmp_path, monkeypatch):
         if p.numel():                                       # dir_encoder has no parameters
             assert float((params[name].detach() - p).abs().max()) <= 2e-4 * float(p.abs().max() + 1e-30), name
         assert list(last["pipeline"][name]) == list(ref["ck_pipeline"][name]) == ["params"]
+
+
+GRID_CHILD = DATASET_CHILD.split("idx = torch.arange(0, len(ds), 97)")[0] + r"""
+from atmonr.datasets import harp2_extract as ref_ext
+ref_ext.HARP2VoxelGridExtractDataset._interp_dem_height = lambda self, dem, la, lo: torch.zeros_like(la)   # no DEM file
+kw = json.loads(sys.argv[7])
+grid = ref_ext.HARP2VoxelGridExtractDataset(ds, **kw)
+torch.save({"shp": tuple(grid.shp), "lat": grid.lat, "lon": grid.lon, "xyz": grid.xyz, "idx": grid.idx,
+            "sample_alt": grid.sample_alt, "batch": grid.__getbatch__(torch.arange(0, 50, 7))}, sys.argv[6])
+"""
+
+
+@pytest.mark.parametrize("spec,kw", [
+    ("synthetic:H=10,W=9,seed=4", {"horizontal_step": 30000.0, "alt_step": 1000.0}),
+    ("synthetic:H=10,W=9,seed=4,lat0=-62,lon0=177.5", {"horizontal_step": 21000.0, "alt_step": 2500.0, "min_alt": 500.0, "max_alt": 15000.0}),
+])
+def test_vincenty_voxel_grid_matches_the_reference_layout(tmp_path, spec, kw):
+    """HARP2VoxelGridExtractDataset(layout="vincenty") against the reference class
+    (harp2_extract.py:189-348; its DEM lookup, which only feeds the output file's `height`, stubbed):
+    same grid shape and altitude levels, voxel columns within a metre (the geodesic arithmetic is
+    float32 on both sides, in different operation orders), same index table and batch layout."""
+    from atmonr.datasets.harp2 import HARP2Dataset
+    from atmonr.datasets.harp2_extract import HARP2VoxelGridExtractDataset
+    cfg = json.load(open(os.path.join(ROOT, "configs", "instant_ngp.json")))["dataset"]
+    out = str(tmp_path / "ref_grid.pt")
+    r = subprocess.run([sys.executable, "-c", GRID_CHILD, os.path.join(ROOT, "tests", "golden"),
+                        os.path.join(ROOT, "atmospheric-neural-rendering_b200", "atmonr", "datasets", "granule.py"),
+                        spec, json.dumps(cfg), str(tmp_path), out, json.dumps(kw)], capture_output=True, text=True, timeout=600)
+    assert r.returncode == 0, r.stderr[-3000:]
+    ref = torch.load(out, weights_only=False)
+    ds = HARP2Dataset(dict(cfg), spec, device=torch.device("cpu"))
+    grid = HARP2VoxelGridExtractDataset(ds, layout="vincenty", **kw)
+    assert tuple(grid.shp) == ref["shp"] and torch.equal(grid.sample_alt, ref["sample_alt"])
+    assert torch.equal(grid.idx, ref["idx"]) and grid.xyz.dtype == ref["xyz"].dtype == torch.float64
+    dlon = (grid.lon - ref["lon"] + 180) % 360 - 180
+    assert float((grid.lat - ref["lat"]).abs().max()) <= 2e-5 and float(dlon.abs().max()) <= 2e-5     # ~2 m
+    assert float((grid.xyz - ref["xyz"]).norm(dim=1).max()) <= 3.0                                     # metres
+    b = grid.__getbatch__(torch.arange(0, 50, 7))
+    assert set(b) == set(ref["batch"]) and torch.equal(b["idx"], ref["batch"]["idx"])
+    # neighbouring columns are about `horizontal_step` apart: n stations span n steps (the reference's
+    # linspace), and the meridians converge towards the poleward edge (16 % over 5 degrees at 62 S)
+    xyz = grid.xyz.view(*grid.shp, 3)[:, :, 0]
+    step_ew = (xyz[:, 1:] - xyz[:, :-1]).norm(dim=-1)
+    assert float((step_ew / kw["horizontal_step"] - 1).abs().max()) < 0.25
