@@ -143,8 +143,10 @@ class HARP2VoxelGridExtractDataset:
             np.savez_compressed(path.with_suffix(".npz"), **fields)
             return
         with netCDF4.Dataset(path, "w") as nc:  # pragma: no cover - module absent here
-            for name, size in (("rows", rows), ("cols", cols), ("levels", n_alt), ("bands", ext.shape[-1])):
+            # dimension names of the reference's writer (harp2_extract.py:453-456)
+            along, across, vert, bands = "bins_along_track", "bins_across_track", "bins_vertical", "number_of_bands"
+            for name, size in ((along, rows), (across, cols), (vert, n_alt), (bands, ext.shape[-1])):
                 nc.createDimension(name, size)
-            dims = {4: ("rows", "cols", "levels", "bands"), 3: ("rows", "cols", "levels"), 2: ("rows", "cols"), 1: ("levels",)}
+            dims = {4: (along, across, vert, bands), 3: (along, across, vert), 2: (along, across), 1: (vert,)}
             for name, arr in fields.items():
                 nc.createVariable(name, arr.dtype, dims[arr.ndim])[:] = arr
