@@ -137,3 +137,34 @@ def test_progress_pixels_follow_the_predictions(monkeypatch, tmp_path):
     p = seen["p"]
     assert abs(p.pred_pixels - want).max() <= 1e-7
     assert abs(p.pred_pixels_surf - 0.25 * want).max() <= 1e-7 and abs(p.pred_pixels_atmo - 0.75 * want).max() <= 1e-7
+
+
+@pytest.mark.parametrize("layout", ["regular", "vincenty"])
+def test_extract_dataset_dump(tmp_path, layout):
+    """The extract grid's output file (harp2_extract.py:429-596): without netCDF4 an .npz with the
+    reference's variable names; shapes follow (along, across, vertical[, bands])."""
+    import numpy as np
+    from atmonr.datasets.factory import get_extract_dataset
+    from atmonr.datasets.harp2 import HARP2Dataset
+    cfg = json.load(open(os.path.join(ROOT, "configs", "instant_ngp.json")))["dataset"]
+    ds = HARP2Dataset(dict(cfg), "synthetic:H=10,W=9,seed=4", device=torch.device("cpu"))
+    grid = get_extract_dataset("voxelgrid", ds, horizontal_step=40000.0, alt_step=2000.0, layout=layout,
+                               coord_mode="voxelgrid", extract_filename="x.nc")          # extra CLI keys are ignored
+    rows, cols, n_alt = grid.shp
+    assert n_alt == 11 and len(grid) == rows * cols * n_alt
+    sigma = torch.rand(len(grid), 1)
+    grid.dump(tmp_path / "ext.nc", sigma)
+    try:
+        import netCDF4  # noqa: F401
+        return                                                   # the netCDF branch is exercised where the module exists
+    except ImportError:
+        pass
+    out = np.load(tmp_path / "ext.npz")
+    assert set(out.files) == {"extinction_coefficient", "latitude", "longitude", "height", "altitude",
+                              "x_wgs84", "y_wgs84", "z_wgs84"}
+    assert out["extinction_coefficient"].shape == (rows, cols, n_alt, 1)
+    assert np.array_equal(out["extinction_coefficient"][..., 0].ravel(), sigma[:, 0].numpy())
+    assert out["latitude"].shape == out["longitude"].shape == out["height"].shape == (rows, cols)
+    assert out["altitude"].shape == (n_alt,) and out["x_wgs84"].shape == (rows, cols, n_alt)
+    with pytest.raises(NotImplementedError):
+        get_extract_dataset("globalgrid", ds)
