@@ -1,7 +1,9 @@
-"""GPU parity of the native NeRF pipeline in the configurations off the shipped config: a scalar
+"""GPU parity of the native pipelines in configurations off the shipped configs. NeRF: a scalar
 `L_x` without a point preprocessor, and `include_height`. oracle/nerf.py is pinned to the reference's
 NeRFPipeline in both (tests/test_reference_interchange.py); the native side of these modes has not run
-on a B200 yet, so the tests are gated like tests/test_zz_gpu_linear_tc.py (ATMONR_RUN_UNVERIFIED=1)."""
+on a B200 yet, so the tests are gated like tests/test_zz_gpu_linear_tc.py (ATMONR_RUN_UNVERIFIED=1).
+Instant-NGP: `extract` with include_height / multi_band_extinction (the operator-by-operator extract path,
+which no earlier GPU test exercised, with this round's include_height fix)."""
 
 import os
 
@@ -61,3 +63,35 @@ def test_nerf_pipeline_variants_match_oracle(monkeypatch, variant):
     with torch.no_grad():
         pts = (b["origin"].double() + b["dir"].double() * (0.5 * b["len"].double()[:, None])).contiguous()
         assert rel(pipe.extract(pts.cuda()), orc.extract(pts, params)) < 2e-3
+
+
+@pytest.mark.parametrize("height,multi_band", [(True, False), (False, True), (True, True)])
+def test_ngp_extract_with_optional_inputs_vs_oracle(height, multi_band):
+    """`extract` in the off-default modes (instant_ngp.py:208-247 with include_height /
+    multi_band_extinction): the 4-D grid needs the height column in extract as well (the oracle and the
+    reference agree on this: tests/test_reference_interchange.py)."""
+    from helpers import FakeDataset, load_params, ngp_config, random_params, tiny_scene
+    from oracle.ngp import NGPOracle
+    from atmonr.pipelines.instant_ngp import InstantNGPPipeline
+    scene = tiny_scene()
+    cfg = ngp_config(24)
+    cfg["include_height"], cfg["multi_band_extinction"] = height, multi_band
+    if height:
+        cfg["point_preprocessor"] = ""
+    orc = NGPOracle(cfg, None if height else scene.frame, scene.max_i, fp16=True, geo=(scene.scale, scene.offset, 20000.0))
+    params = random_params(orc, seed=3, table_scale=2e3)
+    ds = FakeDataset(scene)
+    ds.offset = scene.offset.cuda()
+    pipe = InstantNGPPipeline(cfg, ds)
+    pipe.send_tensors_to(0)
+    load_params(pipe, params)
+    pipe.eval()
+    # query points inside the atmosphere shell (on the scene's rays), like a voxel grid's
+    b = scene.batch
+    t = torch.rand(b["origin"].shape[0], 1, dtype=torch.float64, generator=torch.Generator().manual_seed(9))
+    pts = (b["origin"].double() + b["dir"].double() * (t * b["len"].double()[:, None]))[:500].contiguous()
+    assert pts.shape == (500, 3)
+    want = orc.extract(pts, params).detach()
+    got = pipe.extract(pts.cuda()).detach().cpu()
+    assert got.shape == want.shape == (500, 4 if multi_band else 1)
+    assert float((got - want).abs().max()) <= 2e-3 * float(want.abs().max() + 1e-12)
