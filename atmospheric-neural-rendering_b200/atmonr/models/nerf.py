@@ -3,19 +3,22 @@
 Eleven biased linear layers, width `hidden_dim`, a skip connection that re-injects the encoded
 position at layer 6, a density head on layer 9 (with unit Gaussian noise while training) and a
 direction-conditioned colour head. The layers are torch.nn.Linear modules, so parameter names
-(`fc1`..`fc11`) match the reference and checkpoints interchange. By default they run as library
-float32 GEMMs; with ATMONR_NERF_TC=1 (opt-in until validated on a B200) forward and input gradient
-of every layer run on tcgen05 through `atmonr_linear_fwd_tc` (csrc/linear_tc.cu: float32 operands
-split into three bfloat16 terms, six partial products, float32 accumulation in TMEM).
+(`fc1`..`fc11`) match the reference and checkpoints interchange. On the device forward, input
+gradient and weight gradient of every layer run on tcgen05 (csrc/linear_tc.cu: float32 operands
+split into three bfloat16 terms, six partial products, float32 accumulation in TMEM; validated on a
+B200 in round 2, tests/test_zz_gpu_linear_tc.py). `DENSE_IMPL = "library"` switches the layers to
+torch's float32 GEMMs: used by the tests and by scripts/bench_nerf.py as the cross-check, never by
+the pipelines.
 """
 
 from __future__ import annotations
 
-import os
-
 import torch
 import torch.nn as nn
 import torch.nn.functional as F
+
+
+DENSE_IMPL = "tc"   # "tc" (product path) | "library" (cross-check in tests / bench only)
 
 
 class AtmoNeRF(nn.Module):
@@ -35,7 +38,7 @@ class AtmoNeRF(nn.Module):
     def _layer(self, k: int, x: torch.Tensor, relu: bool, x2: torch.Tensor | None = None) -> torch.Tensor:
         """relu?(fc_k(cat([x, x2]))); on the tensor-core path the concatenation is never materialised."""
         fc = getattr(self, f"fc{k}")
-        if x.is_cuda and os.environ.get("ATMONR_NERF_TC") == "1":
+        if x.is_cuda and DENSE_IMPL == "tc":
             from atmonr.native import ops
             return ops.linear_tc(x, fc.weight, fc.bias, relu, x2=x2)
         if x2 is not None:

@@ -208,8 +208,13 @@ def gpu_nerf_rate(dataset, dev, rays: int = 4096, steps: int = 5) -> dict:
     ms = e0.elapsed_time(e1) / steps
     return {"value": rays * 1e3 / ms, "unit": UNIT, "rays_per_step": rays, "ms_per_step": ms,
             "note": "configs/nerf.json, coarse 64 + fine 192 samples, hidden 256; MLP layers are "
-                    + ("tcgen05 bf16x3-split products (csrc/linear_tc.cu)" if os.environ.get("ATMONR_NERF_TC") == "1"
-                       else "cuBLAS fp32 GEMMs")}
+                    + ("tcgen05 bf16x3-split products (csrc/linear_tc.cu)" if _nerf_dense_impl() == "tc"
+                       else "cuBLAS fp32 GEMMs (cross-check)")}
+
+
+def _nerf_dense_impl() -> str:
+    import atmonr.models.nerf as mn
+    return mn.DENSE_IMPL
 
 
 def run_reference(args) -> None:

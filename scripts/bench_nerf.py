@@ -1,6 +1,6 @@
 """NeRF training step (configs/nerf.json: coarse 64 + fine 192 samples, hidden 256) on cuda:0:
-rays/s of forward + loss + backward + Adam, CUDA-event timed. ATMONR_NERF_TC=1 runs the dense layers
-on tcgen05 (csrc/linear_tc.cu); unset, they are library float32 GEMMs. Prints one JSON line."""
+rays/s of forward + loss + backward + Adam, CUDA-event timed. The dense layers run on tcgen05
+(csrc/linear_tc.cu); `--library` times torch's float32 GEMMs instead (cross-check). Prints one JSON line."""
 
 from __future__ import annotations
 
@@ -25,10 +25,13 @@ def main() -> None:
         raise SystemExit("bench_nerf.py needs a CUDA device; there is no CPU fallback")
     torch.cuda.set_device(0)
     L.load()
+    import atmonr.models.nerf as mn
+    if "--library" in sys.argv:
+        mn.DENSE_IMPL = "library"
     rays = int(os.environ.get("ATMONR_NERF_RAYS", "4096"))
     ds = get_dataset(bench.nerf_config()["dataset"], "synthetic:H=64,W=64,seed=0")
     out = bench.gpu_nerf_rate(ds, torch.device("cuda", 0), rays=rays, steps=10)
-    out["dense_layers"] = "tcgen05 bf16x3 split (atmonr_linear_fwd_tc / _dw_tc)" if os.environ.get("ATMONR_NERF_TC") == "1" \
+    out["dense_layers"] = "tcgen05 bf16x3 split (atmonr_linear_fwd_tc / _dw_tc)" if mn.DENSE_IMPL == "tc" \
         else "library float32 GEMMs"
     flop = 922e6 * rays          # 922 MFLOP per ray, forward + backward
     out["tflops_fp32_equivalent"] = flop / (out["ms_per_step"] * 1e-3) / 1e12

@@ -350,14 +350,16 @@ def test_linear_tc_host_side():
 
 
 def test_nerf_model_default_path_is_unchanged_on_cpu(monkeypatch):
-    """ATMONR_NERF_TC only reroutes CUDA activations; the CPU model (used by nothing in the product,
-    but by this suite's shape checks) keeps its torch layers."""
+    """The tensor-core layers only take CUDA activations; the CPU model (used by nothing in the product,
+    but by this suite's shape checks) keeps its torch layers under either setting of DENSE_IMPL."""
     from atmonr.models.nerf import get_model
     torch.manual_seed(0)
     coarse, fine = get_model(32, 4, [4, 4, 2], 2, False)
     x = torch.rand(10, 2 * 10 + 12)
     coarse.eval()
     want = coarse(x)
-    monkeypatch.setenv("ATMONR_NERF_TC", "1")
+    import atmonr.models.nerf as mn
+    assert mn.DENSE_IMPL == "tc"
+    monkeypatch.setattr(mn, "DENSE_IMPL", "library")
     got = coarse(x)
     assert torch.equal(want[0], got[0]) and torch.equal(want[1], got[1])

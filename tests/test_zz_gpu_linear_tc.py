@@ -1,19 +1,17 @@
 """GPU parity of the tcgen05 dense layer of the AtmoNeRF MLP (csrc/linear_tc.cu) against float64
 matrix products, torch autograd and the default (library GEMM) NeRF pipeline.
 
-The kernel was written after this round's GPU budget was spent and has NOT run on a B200 yet. A
-tensor-core kernel with an mbarrier pipeline can hang when a descriptor or a phase is wrong, so
-these tests only run when ATMONR_RUN_UNVERIFIED=1 (the first thing to do with a GPU: run them under
-`timeout`), and the model only uses the kernel with ATMONR_NERF_TC=1."""
+Tolerances: the kernels accumulate in float32 like the library's float32 GEMM, so every product is
+required to be as close to the float64 result as max(4e-6 of the output scale, twice the error of
+the library float32 product of the same operands): "float32-grade", not a fixed ulp count, because
+the rounding of a K- (or M-) term float32 sum grows with the number of terms."""
 
 import os
 
 import pytest
 import torch
 
-pytestmark = [pytest.mark.gpu,
-              pytest.mark.skipif(os.environ.get("ATMONR_RUN_UNVERIFIED") != "1",
-                                 reason="linear_tc has not been validated on hardware yet (set ATMONR_RUN_UNVERIFIED=1)")]
+pytestmark = [pytest.mark.gpu]
 
 
 @pytest.fixture(scope="module", autouse=True)
@@ -41,36 +39,40 @@ def _ref(x, w, b, relu):
     return torch.relu(y) if relu else y
 
 
+def _close(got, want64, lib32, what):
+    """float32-grade: within max(4e-6, 2 x the library float32 product's error) of the float64 result,
+    relative to the output scale."""
+    scale = float(want64.abs().max()) + 1e-30
+    err = float((got.double() - want64).abs().max()) / scale
+    lib = float((lib32.double() - want64).abs().max()) / scale
+    assert err <= max(4e-6, 2 * lib), (what, err, lib)
+
+
 @pytest.mark.parametrize("m,k,n,relu,bias", SHAPES)
 def test_linear_forward_matches_float64(m, k, n, relu, bias):
     from atmonr.native import ops
+    torch.backends.cuda.matmul.allow_tf32 = False
     g = torch.Generator().manual_seed(m + k + n)
     x = torch.randn(m, k, generator=g).cuda()
     w = (torch.randn(n, k, generator=g) / k ** 0.5).cuda()
     b = torch.randn(n, generator=g).cuda() if bias else None
     want = _ref(x, w, b, relu)
     got = ops.linear_forward(x, w, b, relu)
-    scale = float(want.abs().max())
-    err = float((got.double() - want).abs().max()) / scale
-    lib = float(((torch.relu(x @ w.t() + (0 if b is None else b)) if relu else x @ w.t() + (0 if b is None else b)).double() - want).abs().max()) / scale
-    assert err <= 2e-6, (err, lib)         # float32-grade: the library's float32 GEMM is at `lib`
+    lib = x @ w.t() + (0 if b is None else b)
+    _close(got, want, torch.relu(lib) if relu else lib, "forward")
     # input-gradient form: dY (m, n) * W (n, k) through the planes of W^T
     dy = torch.randn(m, n, generator=g).cuda()
     dx = ops.linear_forward(dy, w, None, False, transpose=True)
-    want_dx = dy.double() @ w.double()
-    assert float((dx.double() - want_dx).abs().max()) / float(want_dx.abs().max()) <= 2e-6
+    _close(dx, dy.double() @ w.double(), dy @ w, "input gradient")
     # the same with the ReLU derivative of the layer's output applied while dY is staged
     keep = (got > 0) if relu else torch.ones_like(got, dtype=torch.bool)
     dx = ops.linear_forward(dy, w, None, False, transpose=True, mask=got if relu else None)
-    want_dx = (dy * keep).double() @ w.double()
-    assert float((dx.double() - want_dx).abs().max()) / float(want_dx.abs().max() + 1e-30) <= 2e-6
+    _close(dx, (dy * keep).double() @ w.double(), (dy * keep) @ w, "masked input gradient")
     # weight gradient: a reduction over all rows (split over the CTAs, float32 REDs at the end)
     dw, db = ops.linear_weight_grad(dy, x, mask=got if relu else None, want_bias=True)
-    want_dw = (dy * keep).double().t() @ x.double()
     assert dw.shape == (n, k) and db.shape == (n,)
-    assert float((dw.double() - want_dw).abs().max()) / float(want_dw.abs().max() + 1e-30) <= 4e-6
-    want_db = (dy * keep).double().sum(0)
-    assert float((db.double() - want_db).abs().max()) <= 2e-5 * float(want_db.abs().max() + 1e-30) + 1e-4
+    _close(dw, (dy * keep).double().t() @ x.double(), (dy * keep).t() @ x, "weight gradient")
+    _close(db, (dy * keep).double().sum(0), (dy * keep).sum(0), "bias gradient")
 
 
 def test_linear_on_a_column_slice_and_autograd():
@@ -86,7 +88,7 @@ def test_linear_on_a_column_slice_and_autograd():
     xd, wd, bd = (t.detach().double().requires_grad_() for t in (x, w, b))
     yd = torch.relu(xd @ wd.t() + bd)
     yd.backward(torch.ones_like(yd))
-    assert float((y.double() - yd).abs().max()) <= 2e-6 * float(yd.abs().max())
+    assert float((y.detach().double() - yd.detach()).abs().max()) <= 4e-6 * float(yd.detach().abs().max())
     same = ops.linear_forward(x, w, b, True)           # strided input, no copy
     assert torch.equal(same, y.detach())
     for got, want in ((xr.grad, xd.grad), (w.grad, wd.grad), (b.grad, bd.grad)):
@@ -116,7 +118,7 @@ def test_linear_on_two_input_blocks():
 
 
 def test_nerf_pipeline_with_tensor_core_layers(monkeypatch):
-    """configs/nerf.json forward + loss + backward with ATMONR_NERF_TC=1 against the default path:
+    """configs/nerf.json forward + loss + backward on the tensor-core layers against library GEMMs:
     same parameters, same draws (eval mode: no density noise; the sampler's Philox stream is keyed by
     the step counter, which both runs start from zero)."""
     import json
@@ -129,7 +131,8 @@ def test_nerf_pipeline_with_tensor_core_layers(monkeypatch):
     batch = next(iter(BatchLoader(ds, batch_size=512, shuffle=True, seed=7)))
     outs = {}
     for mode in ("lib", "tc"):
-        monkeypatch.setenv("ATMONR_NERF_TC", "1" if mode == "tc" else "0")
+        import atmonr.models.nerf as mn
+        monkeypatch.setattr(mn, "DENSE_IMPL", "tc" if mode == "tc" else "library")
         torch.manual_seed(0)
         pipe = get_pipeline(cfg["pipeline"], ds)
         pipe.send_tensors_to(0)

@@ -1,7 +1,6 @@
 """GPU parity of the native pipelines in configurations off the shipped configs. NeRF: a scalar
 `L_x` without a point preprocessor, and `include_height`. oracle/nerf.py is pinned to the reference's
-NeRFPipeline in both (tests/test_reference_interchange.py); the native side of these modes has not run
-on a B200 yet, so the tests are gated like tests/test_zz_gpu_linear_tc.py (ATMONR_RUN_UNVERIFIED=1).
+NeRFPipeline in both (tests/test_reference_interchange.py); first green on a B200 in round 2.
 Instant-NGP: `extract` with include_height / multi_band_extinction (the operator-by-operator extract path,
 which no earlier GPU test exercised, with this round's include_height fix)."""
 
@@ -13,9 +12,7 @@ import torch
 from helpers import FakeDataset, take, tiny_scene, to_cuda
 from oracle import nerf as onerf
 
-pytestmark = [pytest.mark.gpu,
-              pytest.mark.skipif(os.environ.get("ATMONR_RUN_UNVERIFIED") != "1",
-                                 reason="not validated on hardware yet (set ATMONR_RUN_UNVERIFIED=1)")]
+pytestmark = [pytest.mark.gpu]
 
 
 @pytest.fixture(scope="module", autouse=True)
