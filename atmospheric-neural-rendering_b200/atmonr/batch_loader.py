@@ -5,7 +5,11 @@ list of B ints (batch_loader.py:45-49); here one permutation per epoch is drawn 
 (torch's generators, drawn exactly like the reference's RandomSampler does, so `torch.manual_seed`
 reproduces the reference's batch order) and sliced, which removes the O(B) Python
 work per step. Under torch.distributed every rank draws the SAME permutation and
-takes its own contiguous slice of each global batch (data-parallel ray sharding).
+takes its own contiguous slice of each global batch (data-parallel ray sharding). Every global batch
+is cut to a multiple of world_size (at most world_size - 1 rays of the ragged last batch of an epoch
+are left out, and a last batch smaller than world_size is skipped on ALL ranks), so the shards are
+equal-sized: no rank ever sees an empty shard or skips the gradient collective, and the mean of the
+per-rank mean losses IS the mean over the global batch.
 """
 
 from __future__ import annotations
@@ -28,7 +32,10 @@ class BatchLoader:
 
     def __len__(self) -> int:
         n = self.idx.shape[0]
-        return n // self.batch_size if self.drop_last else -(-n // self.batch_size)
+        full, tail = divmod(n, self.batch_size)
+        if self.drop_last or tail < max(1, self.world_size):   # a tail below world_size cannot be sharded
+            return full
+        return full + 1
 
     def __iter__(self) -> Iterator[dict[str, torch.Tensor]]:
         n = self.idx.shape[0]
@@ -49,6 +56,6 @@ class BatchLoader:
         for b in range(len(self)):
             idx = order[b * self.batch_size:(b + 1) * self.batch_size]
             if self.world_size > 1:
-                per = -(-idx.shape[0] // self.world_size)
+                per = idx.shape[0] // self.world_size              # equal shards; < world_size rays left out
                 idx = idx[self.rank * per:(self.rank + 1) * per]
             yield self.dataset.__getbatch__(idx)

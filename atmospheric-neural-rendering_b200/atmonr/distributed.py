@@ -67,7 +67,26 @@ def all_reduce_gradients(optimizer) -> None:
 
 
 def broadcast_parameters(tensors) -> None:
+    """Rank 0's values reach every rank. The broadcast writes in place under no_grad, which bumps the
+    tensor's version counter, so a cached fp16 shadow (atmonr.native.modules.shadow_of) is rebuilt."""
     if not is_active():
         return
-    for t in tensors:
-        td.broadcast(t.data if hasattr(t, "data") else t, src=0)
+    with torch.no_grad():
+        for t in tensors:
+            td.broadcast(t, src=0)
+            if hasattr(t, "_atmonr_shadow"):
+                t._atmonr_shadow = None
+
+
+def merge_disjoint_updates(values: torch.Tensor, touched: torch.Tensor) -> torch.Tensor:
+    """values (..., n) holds this rank's updates at the columns flagged in touched (n,) bool; the ranks
+    touched DISJOINT columns (ray shards of the same global batches). Returns values with every rank's
+    updates merged in (columns nobody touched keep their local value, which is the same on all ranks).
+    One SUM all-reduce of the masked values + one of the mask."""
+    if not is_active():
+        return values
+    t = touched.to(values.dtype)
+    upd = values * t
+    td.all_reduce(upd, op=td.ReduceOp.SUM)
+    td.all_reduce(t, op=td.ReduceOp.SUM)
+    return torch.where(t > 0, upd, values)

@@ -45,7 +45,9 @@ class InstantNGPPipeline(Pipeline):
         if self.loss_name not in ops.LOSS_KINDS:
             raise KeyError(self.loss_name)
         self.fused_state = self._make_fused_state()
-        # data-parallel bookkeeping (set by atmonr.distributed.shard_pipeline)
+        # data-parallel bookkeeping (Trainer sets it under torchrun): the stratified draws are keyed by
+        # (seed, draw counter, GLOBAL ray index in the batch, bin), so a batch gets the same draws
+        # however it is sharded; shards are equal-sized (BatchLoader), hence base = rank * local rays
         self.rank, self.world_size = 0, 1
 
     # -------------------------------------------------------------------------------------
@@ -83,11 +85,14 @@ class InstantNGPPipeline(Pipeline):
             getattr(self, name).to(device)
 
     def get_optimizer(self, config: dict) -> Optimizer:
-        """instant_ngp.py:107-127: AdamW, weight decay on the MLPs only."""
+        """instant_ngp.py:107-127: AdamW, weight decay on the MLPs only. All three encoder parameters
+        are listed, the empty one of dir_encoder (SH + identity have no weights) included, exactly like
+        the reference (tcnn exposes a 0-element Parameter): the groups are [0,1,2] / [3,4,5], so
+        optimizer state dicts interchange with reference checkpoints. FusedAdamW.step skips it."""
         enc = chain(self.pos_encoder.parameters(), self.dir_encoder.parameters(), self.surf_encoder.parameters())
         mlp = chain(self.pos_mlp.parameters(), self.dir_mlp.parameters(), self.surf_mlp.parameters())
         return FusedAdamW(
-            [{"params": [p for p in enc if p.numel()], "weight_decay": 0},
+            [{"params": list(enc), "weight_decay": 0},
              {"params": list(mlp), "weight_decay": config["weight_decay"]}],
             **config,
         )
@@ -99,6 +104,7 @@ class InstantNGPPipeline(Pipeline):
         if self.fused_state is None:
             return self._forward_modular(ray_batch, u)
         st = self.fused_state
+        st.ray_index_base = self.rank * ray_batch["origin"].shape[0]
         shadows = (self.pos_encoder.table_f16(), self.pos_mlp.weights_f16(), self.dir_mlp.weights_f16(),
                    self.surf_encoder.table_f16(), self.surf_mlp.weights_f16())
         cmap, catmo, csurf = fused.NGPRenderFn.apply(
@@ -114,6 +120,7 @@ class InstantNGPPipeline(Pipeline):
         forward() picks them up when it is given the same `origin` tensor; results are those of
         an in-line sampler call with the same draw counter."""
         if self.fused_state is not None and self.training:
+            self.fused_state.ray_index_base = self.rank * ray_batch["origin"].shape[0]
             fused.schedule_prefetch(self.fused_state, ray_batch["origin"], ray_batch["dir"], ray_batch["len"])
 
     def _forward_modular(self, ray_batch, u=None):
@@ -161,6 +168,11 @@ class InstantNGPPipeline(Pipeline):
         pts = torch.cat([pts[..., :2], pts[..., 2:3] / self.config["alt_compress_factor"], pts[..., 3:]], dim=-1)
         out = self.pos_mlp(self.pos_encoder(pts.float()))
         return torch.clip(out[..., : self.num_density_outputs], min=0)
+
+    def set_draw_counter(self, n: int) -> None:
+        """Resume: continue the stratified-draw stream after `n` training steps instead of replaying it."""
+        if self.fused_state is not None:
+            self.fused_state.step = int(n)
 
     def compute_loss(self, ray_batch, results) -> torch.Tensor:
         """instant_ngp.py:249-263, one kernel: band select + loss + d(loss)/d(colour map)."""

@@ -54,6 +54,8 @@ class Trainer:
         self.config, self.dataset, self.pipeline = config, dataset, pipeline
         self.device = torch.cuda.current_device()
         self.rank, self.world_size = dist.rank(), dist.world_size()
+        if hasattr(pipeline, "world_size"):
+            pipeline.rank, pipeline.world_size = self.rank, self.world_size
         if config["all_gpu"]:
             assert config["num_workers"] == 0
             self.dataloader = BatchLoader(dataset, batch_size=config["batch_size"], shuffle=True,
@@ -101,6 +103,7 @@ class Trainer:
         # its own step index), and the progress pixels are scattered into a device buffer that is
         # copied into the host-side ProgressTracker once per epoch, before it is used.
         dev_pix = None           # (3, n_rays) on the device: total / surface / atmosphere predictions
+        touched = None           # (n_rays,) rays this rank predicted in the current epoch (data-parallel merge)
         waiting: list = []       # (iteration, loss tensor) not yet read back
 
         def flush_losses():
@@ -135,7 +138,12 @@ class Trainer:
                     dev_pix = torch.zeros((3, progress.pred_pixels.shape[0]), device=pix.device)
                     for k, name in enumerate(("pred_pixels", "pred_pixels_surf", "pred_pixels_atmo")):
                         dev_pix[k] = torch.from_numpy(getattr(progress, name)).to(pix.device)
-                dev_pix.index_copy_(1, batch["idx"].to(pix.device, torch.long), pix)
+                ray = batch["idx"].to(pix.device, torch.long)
+                dev_pix.index_copy_(1, ray, pix)
+                if self.world_size > 1:
+                    if touched is None:
+                        touched = torch.zeros(dev_pix.shape[1], device=pix.device, dtype=torch.bool)
+                    touched[ray] = True
                 if self.iter_count >= self.config["num_iters"]:
                     break
                 if self.iter_count % self.config["print_frequency"] == 0:
@@ -146,6 +154,11 @@ class Trainer:
                         last_len = len(line)
             flush_losses()
             if dev_pix is not None:
+                if touched is not None:
+                    # every rank predicted only its own ray shards: merge them so that rank 0's image,
+                    # PSNR / SSIM and TensorBoard panels are those of the single-GPU run
+                    dev_pix = dist.merge_disjoint_updates(dev_pix, touched)
+                    touched.zero_()
                 host_pix = dev_pix.cpu().numpy()
                 progress.pred_pixels[:], progress.pred_pixels_surf[:], progress.pred_pixels_atmo[:] = host_pix
             self._end_of_epoch(progress, output_path, last_len)
@@ -213,3 +226,5 @@ class Trainer:
         self.tensorboard_dir = ckpt["tensorboard_dir"]
         self.writer = _make_writer(self.tensorboard_dir) if self.rank == 0 else _NullWriter()
         self.epoch_idx, self.iter_count = ckpt["epoch_idx"], ckpt["iter_count"]
+        if hasattr(self.pipeline, "set_draw_counter"):
+            self.pipeline.set_draw_counter(self.iter_count)

@@ -34,17 +34,26 @@ def parse_args() -> argparse.Namespace:
 
 
 def setup_dir(args: argparse.Namespace, config: dict) -> Path:
+    """The existence checks and the mkdir run on rank 0 only; the other ranks wait for its verdict
+    (a slower rank must not trip over the directory rank 0 has just created)."""
     out = Path(f"data/output/{args.exp_name}")
-    if args.resume:
-        assert out.exists(), f"--resume: {out} does not exist"
-    else:
-        assert args.overwrite or not out.exists(), f"{out} exists (use --overwrite)"
+    error = ""
     if dist.rank() == 0:
-        os.makedirs(out, exist_ok=True)
-        with open(out / "args.json", "w") as fh:
-            json.dump(vars(args), fh, indent=4)
-        with open(out / "config.json", "w") as fh:
-            json.dump(config, fh, indent=4)
+        if args.resume and not out.exists():
+            error = f"--resume: {out} does not exist"
+        elif not args.resume and not args.overwrite and out.exists():
+            error = f"{out} exists (use --overwrite)"
+        else:
+            os.makedirs(out, exist_ok=True)
+            with open(out / "args.json", "w") as fh:
+                json.dump(vars(args), fh, indent=4)
+            with open(out / "config.json", "w") as fh:
+                json.dump(config, fh, indent=4)
+    if dist.is_active():
+        box = [error]
+        torch.distributed.broadcast_object_list(box, src=0)   # also the barrier: the files exist afterwards
+        error = box[0]
+    assert not error, error
     return out
 
 

@@ -59,8 +59,21 @@ def _worker(rank, world, port, out):
     before = torch.cat([q.detach().flatten() for q in pipe.parameters()]).clone()
     dist.broadcast_parameters(pipe.parameters())
     after = torch.cat([q.detach().flatten() for q in pipe.parameters()]).clone()
+    # progress pixels: each rank writes its own shard's predictions; after the merge every rank holds all
+    pix = torch.full((3, 1000), -1.0)
+    touched = torch.zeros(1000, dtype=torch.bool)
+    for b in seen[:3]:
+        ray = b.long()
+        pix[:, ray] = torch.stack([ray.float(), 2 * ray.float(), 3 * ray.float()])
+        touched[ray] = True
+    merged = dist.merge_disjoint_updates(pix, touched)
+    # ragged epochs: n % (batch * world) != 0, incl. tails smaller than the world size
+    ragged = {}
+    for n in (1000, 1001, 129, 130, 131, 257):
+        ld = BatchLoader(_Rays(n), batch_size=128, shuffle=True, rank=r, world_size=w, seed=1)
+        ragged[n] = (len(ld), [b["idx"].numel() for b in ld])
     torch.save({"seen": seen, "grad": p.grad.clone(), "first": first["idx"].clone(), "nerf_before": before,
-                "nerf_after": after}, out.format(rank))
+                "nerf_after": after, "merged": merged, "touched": touched, "ragged": ragged}, out.format(rank))
     td.destroy_process_group()
 
 
@@ -79,6 +92,18 @@ def test_ray_sharding_and_gradient_allreduce(tmp_path):
     p = torch.nn.Parameter(torch.tensor([0.5, -1.5]))
     ((p[0] * x + p[1]) ** 2).mean().backward()
     assert torch.allclose(r0["grad"], p.grad, rtol=1e-5)
+    # progress pixels of both ranks' shards are on every rank after the merge
+    assert torch.equal(r0["merged"], r1["merged"])
+    both = r0["touched"] | r1["touched"]
+    assert int(both.sum()) == 3 * 128 and not bool((r0["touched"] & r1["touched"]).any())
+    ray = torch.arange(1000.0)
+    assert torch.equal(r0["merged"][:, both], torch.stack([ray, 2 * ray, 3 * ray])[:, both])
+    assert bool((r0["merged"][:, ~both] == -1).all())
+    # ragged tails: same number of batches and the same (non-zero) shard size on every rank
+    assert r0["ragged"] == r1["ragged"]
+    for n, (length, sizes) in r0["ragged"].items():
+        assert length == len(sizes) and all(sz > 0 for sz in sizes), (n, length, sizes)
+    assert r0["ragged"][129] == (1, [64]) and r0["ragged"][130] == (2, [64, 1]) and r0["ragged"][131] == (2, [64, 1])
     # parameter broadcast: the ranks started from different values and end with rank 0's
     assert r0["nerf_before"].numel() > 1000 and not torch.equal(r0["nerf_before"], r1["nerf_before"])
     assert torch.equal(r0["nerf_after"], r0["nerf_before"]) and torch.equal(r1["nerf_after"], r0["nerf_before"])
