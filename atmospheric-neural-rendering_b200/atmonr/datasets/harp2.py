@@ -206,8 +206,9 @@ class HARP2Dataset(Dataset):
         }
 
     def __getbatch__(self, idx: torch.Tensor) -> dict[str, torch.Tensor]:
-        # ATMONR_NATIVE_GATHER=1: the seven gathers in one launch (atmonr_gather_batch, csrc/rays.cu)
-        if os.environ.get("ATMONR_NATIVE_GATHER") == "1" and self.ray_origin_norm.is_cuda and torch.is_tensor(idx) \
+        # the seven gathers in one launch (atmonr_gather_batch, csrc/rays.cu); ATMONR_NATIVE_GATHER=0 keeps
+        # torch indexing (cross-check)
+        if os.environ.get("ATMONR_NATIVE_GATHER", "1") != "0" and self.ray_origin_norm.is_cuda and torch.is_tensor(idx) \
                 and idx.dtype == torch.int64 and idx.dim() == 1:
             return ops.gather_batch(self._ray_tables(), idx.to(self.ray_origin_norm.device))
         return self[idx]

@@ -104,9 +104,11 @@ def get_rays(lat, lon, alt, thetav, phiv, ray_origin_height, tol: float = 10.0, 
     """Ray entry (top of the shell at `ray_origin_height`) and exit (surface) for every
     pixel/view. wgs_84.py:223-290. Returns origins (P*A,3), directions (P*A,3), lengths (P*A,).
 
-    With ATMONR_NATIVE_RAYS=1 and CUDA inputs the chunk is computed by the library's ray-setup
-    kernels (`atmonr_get_rays`, csrc/rays.cu: same dtype flow, same chunk-wide refinement loop)."""
-    if os.environ.get("ATMONR_NATIVE_RAYS") == "1" and lat.is_cuda:
+    CUDA inputs are computed by the library's ray-setup kernels (`atmonr_get_rays`, csrc/rays.cu: same
+    dtype flow, same chunk-wide refinement loop); ATMONR_NATIVE_RAYS=0 keeps the torch expressions
+    below on the device as well (the cross-check of tests/test_zz_gpu_rays.py). CPU inputs (dataset
+    interchange tests in the build container) always take the torch expressions."""
+    if lat.is_cuda and os.environ.get("ATMONR_NATIVE_RAYS", "1") != "0":
         from atmonr.native import ops
         return ops.get_rays(lat, lon, alt, thetav, phiv, ray_origin_height, tol, max_iters)
     x, y, z = horizontal_to_cartesian(lat.double(), lon.double(), alt.double())

@@ -29,7 +29,7 @@ NVCC_FLAGS = [
     "-std=c++17", "-O3", "-lineinfo", "-fmad=false",
     "-gencode", "arch=compute_100a,code=sm_100a",
     "-Xcompiler", "-fPIC",
-]
+] + os.environ.get("ATMONR_NVCC_EXTRA", "").split()   # tuning experiments (-DATM_FWD_CTAS=8 ...); part of the cache key
 # (object name, source, extra defines)
 UNITS = [
     ("basic", "atmonr_b200.cu", ["-DATM_PART=0"]),

@@ -38,6 +38,8 @@ ENTRY = {
     "k_ngp_sample_points": "atmonr_ngp_sample_points", "k_field_fwd_tc": "atmonr_ngp_field_fwd_tc",
     "k_composite_fwd": "atmonr_composite_fwd", "k_composite_bwd": "atmonr_composite_bwd",
     "k_field_bwd_tc2": "atmonr_ngp_field_bwd_tc", "k_extract_sigma_tc": "atmonr_extract_sigma_tc",
+    "k_adamw": "atmonr_adamw_step", "k_dense_tc": "atmonr_dense_fwd_tc", "k_dense_dw_tc": "atmonr_dense_dw_tc",
+    "k_linear_tc": "atmonr_linear_fwd_tc", "k_linear_dw_tc": "atmonr_linear_dw_tc",
 }
 
 
@@ -68,6 +70,8 @@ def full_summary(rep: str, tag: str, cmd: str, rays: int, write_traffic: bool = 
            "the bench line); counters are per launch. `stalls` = warp-state sampling split (pc sampling).", ""]
     traffic = {"rays": rays, "source": f"profiles/{tag}_ncu_full_summary.md (ncu --set full, dram__bytes_read.sum + "
                                         "dram__bytes_write.sum per launch)"}
+    counters_path = os.path.join(ROOT, "profiles", "ncu_counters.json")
+    counters = json.load(open(counters_path)) if os.path.exists(counters_path) else {}
     for r in data:
         name = short(r[ki])
         out += [f"## {name}", "```"]
@@ -88,9 +92,28 @@ def full_summary(rep: str, tag: str, cmd: str, rays: int, write_traffic: bool = 
                 scale = {"byte": 1, "Kbyte": 1e3, "Mbyte": 1e6, "Gbyte": 1e9, "Tbyte": 1e12}[u]
                 return float(v.replace(",", "")) * scale
             traffic[ent] = {"dram_bytes_per_launch": to_bytes(*vals["dram__bytes_read.sum"]) + to_bytes(*vals["dram__bytes_write.sum"])}
+
+            def num(m):
+                return float(vals[m][0].replace(",", "")) if m in vals and vals[m][0] not in ("", "n/a") else None
+            dur_unit = {"ns": 1e-6, "us": 1e-3, "ms": 1.0, "s": 1e3}.get(vals["gpu__time_duration.sum"][1], 1e-6)
+            # per launch, from ONE ncu --set full capture; bench.py divides the byte / sector counts by the
+            # LIVE CUDA-event duration of the same kernel (the ncu duration is a serialised cold-cache replay)
+            counters[ent] = {
+                "source": f"profiles/{tag}_ncu_full_summary.md", "workload_rays": rays,
+                "ncu_duration_ms": num("gpu__time_duration.sum") * dur_unit,
+                "dram_bytes": traffic[ent]["dram_bytes_per_launch"],
+                "l2_sectors_read": num("lts__t_sectors_srcunit_tex_op_read.sum"),
+                "l2_sectors_red": num("lts__t_sectors_srcunit_tex_op_red.sum"),
+                "l2_throughput_pct": num("lts__throughput.avg.pct_of_peak_sustained_elapsed"),
+                "tensor_pipe_pct": num("sm__pipe_tensor_cycles_active.avg.pct_of_peak_sustained_active"),
+                "issue_active_pct": num("smsp__issue_active.avg.pct_of_peak_sustained_active"),
+                "warps_active_pct": num("sm__warps_active.avg.pct_of_peak_sustained_active"),
+                "top_stalls": [f"{n} {100 * f:.1f}%" for f, n in split[:3]],
+            }
     open(os.path.join(ROOT, "profiles", f"{tag}_ncu_full_summary.md"), "w").write("\n".join(out))
     if write_traffic:
         json.dump(traffic, open(os.path.join(ROOT, "profiles", "ncu_dram_traffic.json"), "w"), indent=1)
+    json.dump(counters, open(counters_path, "w"), indent=1)
 
 
 def launch_list(path: str, tag: str, cmd: str, bench: dict | None) -> None:

@@ -64,7 +64,7 @@ def test_bad_arguments_report_errors():
 
 
 def test_native_ray_dispatch_needs_cuda_tensors(monkeypatch):
-    """ATMONR_NATIVE_RAYS only reroutes CUDA inputs; CPU tensors keep the torch expressions (dataset
+    """The ray-setup kernels only take CUDA inputs; CPU tensors keep the torch expressions (dataset
     construction without a GPU, e.g. this test-suite), and the operator itself refuses CPU tensors."""
     from atmonr.geospatial.wgs_84 import get_rays
     from atmonr.native import lib as L, ops

@@ -1,7 +1,7 @@
 """GPU parity of the dataset-side kernels (csrc/rays.cu): atmonr_get_rays against the oracle's
 build_rays (pinned bit for bit to the reference's get_rays) and the host build of the same code,
 atmonr_gather_batch against torch indexing (bit-exact). The file sorts last on purpose: these two
-entry points are opt-in (ATMONR_NATIVE_RAYS / ATMONR_NATIVE_GATHER) until they have been green on
+entry points were opt-in (ATMONR_NATIVE_RAYS / ATMONR_NATIVE_GATHER) until they had been green on
 a B200 once."""
 
 import ctypes as C
@@ -78,11 +78,13 @@ def test_get_rays_edge_cases():
 
 
 def test_get_rays_dispatch_builds_the_same_dataset(monkeypatch):
-    """HARP2Dataset built with ATMONR_NATIVE_RAYS=1 against the default (torch expressions on the GPU)."""
+    """HARP2Dataset built with the ray-setup kernels (default) against the torch expressions on the GPU
+    (ATMONR_NATIVE_RAYS=0)."""
     import json, os
     from helpers import ROOT
     from atmonr.datasets.factory import get_dataset
     cfg = json.load(open(os.path.join(ROOT, "configs", "instant_ngp.json")))["dataset"]
+    monkeypatch.setenv("ATMONR_NATIVE_RAYS", "0")
     base = get_dataset(cfg, "synthetic:H=24,W=20,seed=2")
     monkeypatch.setenv("ATMONR_NATIVE_RAYS", "1")
     nat = get_dataset(cfg, "synthetic:H=24,W=20,seed=2")
@@ -122,6 +124,7 @@ def test_gather_batch_is_bit_exact(monkeypatch):
     with pytest.raises(L.NativeLibraryError):
         ops.gather_batch({**ds._ray_tables(), "rad": ds.ray_rad.double()}, torch.tensor([0], device="cuda"))
     # the loader path: same batches with and without the fused gather
+    monkeypatch.setenv("ATMONR_NATIVE_GATHER", "0")
     a = [b for b in BatchLoader(ds, batch_size=1000, shuffle=True, seed=3)]
     monkeypatch.setenv("ATMONR_NATIVE_GATHER", "1")
     c = [b for b in BatchLoader(ds, batch_size=1000, shuffle=True, seed=3)]
