@@ -18,7 +18,12 @@
 // twelve MMAs of chunk c (a stage is recycled when the commit of the MMAs that read it has arrived).
 // B is split ONCE per step by atmonr_linear_prep (optionally transposed: the input-gradient product
 // dX = dY * W is the same kernel on the planes of W^T) and stored in HBM already in tile order, so
-// its staging is a plain 16-byte copy; X is split on the fly by the loading threads.
+// its staging is ONE bulk asynchronous copy per plane (cp.async.bulk, completion on an mbarrier: no
+// thread touches the weights); X is split on the fly by the loading threads. The output tile goes
+// through shared memory (the operand stages are free by then) so that the global stores are whole
+// contiguous rows (a thread owns one ROW of the accumulator: direct stores would touch 32 rows per
+// warp instruction; measured round 2: 100 k cycles per tile with per-thread weight copies and
+// direct stores, 12.4 k of which are tensor-core time).
 #include <cuda_bf16.h>
 
 #include "common.cuh"
@@ -35,8 +40,8 @@ constexpr int kThreads = 256;
 constexpr int kATile = kRows * kChunk * 2;        // 8 KB: one bf16 plane of the X chunk
 constexpr int kBTile = kCols * kChunk * 2;        // 16 KB: one bf16 plane of the B chunk
 constexpr int kStage = 3 * kATile + 3 * kBTile;   // 72 KB
-constexpr int kBar = 2 * kStage;                  // two mbarriers
-constexpr int kTmemPtr = kBar + 16;
+constexpr int kBar = 2 * kStage;                  // bar[s]: stage s consumed by its MMAs; full[s]: B planes of stage s landed
+constexpr int kTmemPtr = kBar + 32;
 constexpr int kBytes = kTmemPtr + 16;
 constexpr uint32_t kTmemCols = 256;
 }  // namespace lin
@@ -121,9 +126,12 @@ k_linear_tc(const float* __restrict__ x, int64_t ldx, const float* __restrict__ 
   uint32_t* tmem_ptr = reinterpret_cast<uint32_t*>(smem + lin::kTmemPtr);
   const int tid = threadIdx.x, warp = tid >> 5;
   if (warp == 0) tmem_alloc<lin::kTmemCols>(tmem_ptr);
+  uint64_t* full = bar + 2;
   if (tid == 0) {
     mbar_init(bar, 1);
     mbar_init(bar + 1, 1);
+    mbar_init(full, 1);
+    mbar_init(full + 1, 1);
     fence_mbar_init();
   }
   fence_async_smem();
@@ -147,6 +155,17 @@ k_linear_tc(const float* __restrict__ x, int64_t ldx, const float* __restrict__ 
     uint8_t* stage = smem + s * lin::kStage;
     // the MMAs of chunk c-2 read this stage: wait for their commit (completion number (c>>1)-1 of bar[s])
     if (c >= 2) mbar_wait(bar + s, (uint32_t)(((c >> 1) - 1) & 1));
+    // ---- B chunk: three planes, already split and in tile order: the first n_cols rows of a plane are
+    // its first n_cols * 64 bytes -> one bulk copy per plane, announced on full[s]. (This thread has
+    // passed the wait above, so the MMAs that read the stage before are done.)
+    if (tid == 0) {
+      const uint8_t* src = b_src + (size_t)c * 3 * lin::kBTile;
+      uint8_t* dst = stage + 3 * lin::kATile;
+      const uint32_t bytes = (uint32_t)n_cols * 64u;
+      mbar_expect_tx(full + s, 3u * bytes);
+#pragma unroll
+      for (int p = 0; p < 3; ++p) bulk_g2s(dst + p * lin::kBTile, src + p * lin::kBTile, bytes, full + s);
+    }
     // ---- X chunk: 128 rows x 32 columns float32 -> three bf16 planes (2 groups of 8 values per thread)
 #pragma unroll
     for (int it = 0; it < 2; ++it) {
@@ -171,19 +190,11 @@ k_linear_tc(const float* __restrict__ x, int64_t ldx, const float* __restrict__ 
       st_chunk(stage + lin::kATile, r, cc, lin::kChunk, mid);
       st_chunk(stage + 2 * lin::kATile, r, cc, lin::kChunk, lo);
     }
-    // ---- B chunk: three planes, already split and in tile order: 16-byte copies of the rows in use
-    {
-      const uint4* src = reinterpret_cast<const uint4*>(b_src + (size_t)c * 3 * lin::kBTile);
-      uint4* dst = reinterpret_cast<uint4*>(stage + 3 * lin::kATile);
-      const int per_plane = n_cols * 4;                 // 16-byte chunks of the rows in use (rows are 64 B)
-      for (int p = 0; p < 3; ++p)
-        for (int i = tid; i < per_plane; i += lin::kThreads)
-          dst[p * (lin::kBTile / 16) + i] = __ldg(src + p * (lin::kBTile / 16) + i);
-    }
     fence_async_smem();
     tc_fence_before();
     __syncthreads();
     if (warp == 0) {
+      mbar_wait(full + s, (uint32_t)((c >> 1) & 1));   // the weight planes of this chunk have landed
       tc_fence_after();
       const uint32_t a0 = sbase + s * lin::kStage, b0 = a0 + 3 * lin::kATile;
       // (A plane, B plane): hi*hi, hi*mid, mid*hi, mid*mid, hi*lo, lo*hi
@@ -206,10 +217,14 @@ k_linear_tc(const float* __restrict__ x, int64_t ldx, const float* __restrict__ 
     mbar_wait(bar + (last & 1), (uint32_t)((last >> 1) & 1));
     tc_fence_after();
   }
-  // ---- epilogue: thread (warp w, lane) owns row (w % 4) * 32 + lane, columns (w / 4) * 128 .. + 128
+  // ---- epilogue: thread (warp w, lane) owns row (w % 4) * 32 + lane, columns (w / 4) * 128 .. + 128 of
+  // the accumulator. bias + activation, then the tile is staged in shared memory (row pitch n_cols + 4
+  // floats: the 16-byte stores of 8 lanes = 8 rows fall into distinct banks) and written out row by
+  // row, a warp covering 512 contiguous bytes per instruction.
   {
+    float* tile = reinterpret_cast<float*>(smem);      // the operand stages are free: every MMA is complete
+    const int pitch = n_cols + 4;
     const int r = (warp & 3) * 32 + (tid & 31);
-    const int64_t row = row0 + r;
     const int c_lo = (warp >> 2) * 128;
 #pragma unroll 1
     for (int cb = 0; cb < 128; cb += 16) {
@@ -217,17 +232,37 @@ k_linear_tc(const float* __restrict__ x, int64_t ldx, const float* __restrict__ 
       if (col >= n_cols) break;                          // warp-uniform
       float v[16];
       tmem_ld16(tmem_addr(acc, warp, col), v);
-      if (row < M) {
-        float* dst = y + row * ldy + n0 + col;
 #pragma unroll
-        for (int j = 0; j < 16; ++j) {
-          const int n = n0 + col + j;
-          if (n < n_out) {
-            float o = v[j] + (bias ? bias[n] : 0.0f);
-            if (act == 1) o = fmaxf(o, 0.0f);
-            dst[j] = o;
-          }
-        }
+      for (int j = 0; j < 16; ++j) {
+        const int n = n0 + col + j;
+        float o = v[j] + ((bias && n < n_out) ? __ldg(bias + n) : 0.0f);
+        if (act == 1) o = fmaxf(o, 0.0f);
+        v[j] = o;
+      }
+      float4* dst = reinterpret_cast<float4*>(tile + r * pitch + col);
+#pragma unroll
+      for (int q = 0; q < 4; ++q) dst[q] = make_float4(v[4 * q], v[4 * q + 1], v[4 * q + 2], v[4 * q + 3]);
+    }
+    __syncthreads();
+    const int n_valid = min(n_cols, n_out - n0);         // real output columns of this CTA
+    const int rows = (int)min((int64_t)lin::kRows, M - row0);
+    const bool vec = (ldy & 3) == 0 && (n0 & 3) == 0 && (reinterpret_cast<uintptr_t>(y) & 15) == 0;
+    if (vec) {
+      const int q_per_row = n_valid >> 2;                // whole float4 groups
+      for (int i = tid; i < rows * q_per_row; i += lin::kThreads) {
+        const int rr = i / q_per_row, q = i - rr * q_per_row;
+        *reinterpret_cast<float4*>(y + (row0 + rr) * ldy + n0 + 4 * q) =
+            *reinterpret_cast<const float4*>(tile + rr * pitch + 4 * q);
+      }
+      const int tail = n_valid & 3;
+      for (int i = tid; i < rows * tail; i += lin::kThreads) {
+        const int rr = i / tail, cc = (n_valid & ~3) + (i - rr * tail);
+        y[(row0 + rr) * ldy + n0 + cc] = tile[rr * pitch + cc];
+      }
+    } else {
+      for (int i = tid; i < rows * n_valid; i += lin::kThreads) {
+        const int rr = i / n_valid, cc = i - rr * n_valid;
+        y[(row0 + rr) * ldy + n0 + cc] = tile[rr * pitch + cc];
       }
     }
   }

@@ -25,7 +25,7 @@
 #define ATM_DW
 #endif
 #ifdef ATM_DEBUG_NO_SCATTER
-#define ATM_SCATTER_ON (d.x == 123456.0f)
+#define ATM_SCATTER_ON (invS == 123456.0f)
 #else
 #define ATM_SCATTER_ON true
 #endif
@@ -158,8 +158,7 @@ constexpr int kWD2 = kWD1 + 2048;   // dir_mlp layer 1  [32][32]
 constexpr int kWD3 = kWD2 + 2048;   // dir_mlp output   [16][32]
 constexpr int kA = kWD3 + 1024;     // activation tile  [128][32], rewritten in place layer after layer
 constexpr int kLv = kA + 8192;      // level table, 16 x 32 B
-constexpr int kPos = kLv + 512;     // encoder inputs of the tile, 3 x 128 floats (run-walking encoder)
-constexpr int kBar = kPos + 3 * 128 * 4;
+constexpr int kBar = kLv + 512;
 constexpr int kTmemPtr = kBar + 8;
 constexpr int kBytes = kTmemPtr + 8;
 // one 32-column accumulator; the 16-wide outputs reuse its first columns (a layer's accumulator
@@ -275,45 +274,6 @@ __device__ __forceinline__ void encode_to_tile(const LevelRow* __restrict__ lv, 
   }
 }
 
-// ---- run-walking encoder (forward / extraction) -------------------------------------------------
-// Consecutive rows of a tile are consecutive samples of a ray (or consecutive altitudes of a voxel
-// column), which stay inside one grid cell for many rows on the coarse levels (the per-thread
-// encoder above re-derives 8 entries and re-issues 8 gathers per row and level: 68 % L1 hits, and
-// ~109 issued instructions per row and level, which is what bounds the kernel). Here the work is
-// re-mapped like the backward's scatter: thread (grp = tid & 7, level = tid >> 3) walks the 16 rows
-// 16 grp .. 16 grp + 15 of ONE level, keeps the 8 corner entries of the current cell in registers
-// and only re-indexes / re-gathers when the cell changes; per row it is left with the cell, the 8
-// weights and 8 packed-half FMAs. A warp holds 4 adjacent levels, so coarse-level warps almost never
-// take the gather path. Same arithmetic per row as level_issue()/level_finish(): bit-identical.
-// The walk starts at row (grp) of the group and wraps, so that the 8 groups of a warp touch
-// 8 different rows-mod-8: their 4-byte stores into the core-matrix layout (and their reads of pos)
-// fall into distinct banks. pos = 3 x 128 floats in shared memory, written before a CTA barrier.
-__device__ __forceinline__ void encode_tile_runs(const LevelRow& L, int level, const __half2* __restrict__ table,
-                                                 const float* pos, uint8_t* tile, int grp) {
-  const uint32_t* base = reinterpret_cast<const uint32_t*>(table + L.offset);
-  uint32_t c_run[3] = {0xffffffffu, 0xffffffffu, 0xffffffffu};
-  uint32_t v[8];
-#pragma unroll
-  for (int c = 0; c < 8; ++c) v[c] = 0u;
-  uint8_t* col = tile + (level >> 2) * kCore + (level & 3) * 4;
-#pragma unroll 1
-  for (int s = 0; s < 16; ++s) {
-    const int r = (grp << 4) | ((s + grp) & 15);
-    const float p[3] = {pos[r], pos[128 + r], pos[256 + r]};
-    uint32_t cell[3];
-    float frac[3];
-    grid_cell<3>(p, L.scale, cell, frac);
-    if (cell[0] != c_run[0] || cell[1] != c_run[1] || cell[2] != c_run[2]) {
-      uint32_t e[8];
-      corner_entries3(L, cell, e);
-#pragma unroll
-      for (int c = 0; c < 8; ++c) v[c] = __ldg(entry_ptr(base, e[c]));
-      c_run[0] = cell[0], c_run[1] = cell[1], c_run[2] = cell[2];
-    }
-    *reinterpret_cast<uint32_t*>(col + (r >> 3) * (4 * kCore) + (r & 7) * 16) = level_finish(v, frac);
-  }
-}
-
 // dir_mlp input row: [SH2(dir) | pos_out[1..15] | 1.0 x 13] (instant_ngp.py:165-169 + tcnn padding)
 __device__ __forceinline__ void dir_input_row(const float* __restrict__ dir, const float (&po)[16], float (&v)[32]) {
   float sh[4];
@@ -369,34 +329,35 @@ k_field_fwd_tc(atmonr_grid_t g, const __half2* __restrict__ table, const __half*
   const uint32_t sbase = smem_u32(smem), sa = sbase + fwd::kA;
   uint8_t* A = smem + fwd::kA;
   uint32_t phase = 0;
-  float* pos = reinterpret_cast<float*>(smem + fwd::kPos);
-  const int grp = tid & 7, my_level = tid >> 3;
-  const LevelRow myL = lv[my_level];
-  // this thread's encoder input of the first tile (afterwards: requested one tile ahead)
-  auto load_pos = [&](int64_t t, float (&q)[3]) {
-    const int64_t ii = t * kTile + tid;
-    const int64_t jj = ii < M ? ii : M - 1;
-    q[0] = __ldg(x01 + 3 * jj), q[1] = __ldg(x01 + 3 * jj + 1), q[2] = __ldg(x01 + 3 * jj + 2);
-  };
-  float pn[3] = {0.0f, 0.0f, 0.0f};
-  if ((int64_t)blockIdx.x * kTile < M) load_pos(blockIdx.x, pn);
+  const uint64_t keep_pol = l2_policy_keep(), stream_pol = l2_policy_stream();
 
   for (int64_t tile = blockIdx.x; tile * kTile < M; tile += gridDim.x) {
     const int64_t i = tile * kTile + tid;
     const bool valid = i < M;
     const int64_t j = valid ? i : M - 1;
     // ---- hash-grid encoding -> A (the previous tile's last MMA has been waited for)
-    pos[tid] = pn[0], pos[128 + tid] = pn[1], pos[256 + tid] = pn[2];
-    __syncthreads();
-    if ((tile + gridDim.x) * kTile < M) load_pos(tile + gridDim.x, pn);   // lands during this tile
-    encode_tile_runs(myL, my_level, table, pos, A, grp);
+    {
+#ifdef ATM_L2_HINTS
+      const float p[3] = {ldg_f32_hint(x01 + 3 * j, stream_pol), ldg_f32_hint(x01 + 3 * j + 1, stream_pol),
+                          ldg_f32_hint(x01 + 3 * j + 2, stream_pol)};
+#else
+      const float p[3] = {x01[3 * j], x01[3 * j + 1], x01[3 * j + 2]};
+#endif
+      encode_to_tile(lv, table, p, A, tid, keep_pol);
+      if (enc_out && valid) {
+        uint4* dst = reinterpret_cast<uint4*>(enc_out + i * 32);
+#pragma unroll
+        for (int cc = 0; cc < 4; ++cc) {
+#ifdef ATM_L2_HINTS
+          stg_u128_hint(dst + cc, ld_chunk(A, tid, cc, 32), stream_pol);
+#else
+          dst[cc] = ld_chunk(A, tid, cc, 32);
+#endif
+        }
+      }
+    }
     publish_and_sync();
     if (warp == 0) issue_layer<32>(acc, sa, sbase + fwd::kW1P, bar);
-    if (enc_out && valid) {   // this row's features -> the backward's cache, underneath the first MMA
-      uint4* dst = reinterpret_cast<uint4*>(enc_out + i * 32);
-#pragma unroll
-      for (int cc = 0; cc < 4; ++cc) dst[cc] = ld_chunk(A, tid, cc, 32);
-    }
     mbar_wait(bar, phase), phase ^= 1;
     tc_fence_after();
     relu_acc_to_tile(mine, A, tid);
@@ -477,9 +438,7 @@ k_extract_sigma_tc(atmonr_frame_t f, GeoFrame gf, atmonr_grid_t g, const __half2
   const uint32_t sbase = smem_u32(smem), sa = sbase + fwd::kA;
   uint8_t* A = smem + fwd::kA;
   uint32_t phase = 0;
-  float* pos = reinterpret_cast<float*>(smem + fwd::kPos);
-  const int grp = tid & 7, my_level = tid >> 3;
-  const LevelRow myL = lv[my_level];
+  const uint64_t keep_pol = l2_policy_keep();
   for (int64_t tile = blockIdx.x; tile * kTile < n; tile += gridDim.x) {
     const int64_t i = tile * kTile + tid;
     const bool valid = i < n;
@@ -488,13 +447,10 @@ k_extract_sigma_tc(atmonr_frame_t f, GeoFrame gf, atmonr_grid_t g, const __half2
       double c0 = pts[3 * j], c1 = pts[3 * j + 1], c2 = pts[3 * j + 2];
       if (f.enabled) preprocess_f64(f, gf, c0, c1, c2, c0, c1, c2);
       // instant_ngp.py:224-233 stay in float64; tcnn casts its input to float32
-      pos[tid] = (float)((c0 + 1.0) / 2.0);
-      pos[128 + tid] = (float)((c1 + 1.0) / 2.0);
-      pos[256 + tid] = (float)(((c2 + 1.0) / 2.0) / (double)alt_compress);
+      const float p[3] = {(float)((c0 + 1.0) / 2.0), (float)((c1 + 1.0) / 2.0),
+                          (float)(((c2 + 1.0) / 2.0) / (double)alt_compress)};
+      encode_to_tile(lv, table, p, A, tid, keep_pol);
     }
-    __syncthreads();
-    // consecutive voxels of a column differ in altitude only: the same cell runs as along a ray
-    encode_tile_runs(myL, my_level, table, pos, A, grp);
     publish_and_sync();
     if (warp == 0) issue_layer<32>(acc, sa, sbase + fwd::kW1P, bar);
     mbar_wait(bar, phase), phase ^= 1;
@@ -1136,11 +1092,29 @@ k_field_bwd_tc2(atmonr_grid_t g, const __half* __restrict__ pos_w, const __half*
       bool open = false;
 #pragma unroll
       for (int c = 0; c < 16; ++c) acc[c] = 0.0f;
+      // The L2 processes REDs per 32-byte sector request (profiles/r3_l2_ubench.json: 43.5 G sector
+      // requests/s whether a request carries one or four lanes' 8 bytes), and these REDs are what bounds
+      // the kernel (1.05e9 requests per launch = 24 ms at that rate). The corners x and x+1 of a cell are
+      // neighbouring entries of one aligned 16-byte pair whenever their entries differ in bit 0 only
+      // (hashed levels: x even, since (x ^ h) and ((x | 1) ^ h) differ in bit 0; dense levels: entry even):
+      // those pairs go out as ONE red.v4.f32.
       auto flush = [&]() {  // entries are only needed here, once per run of samples in one cell
         uint32_t e[8];
         corner_entries3(L, c_run, e);
 #pragma unroll
-        for (int c = 0; c < 8; ++c) red_add_f32x2(reinterpret_cast<float*>(entry_ptr(base, e[c])), acc[2 * c], acc[2 * c + 1]);
+        for (int c = 0; c < 8; c += 2) {
+#ifndef ATM_NO_PAIRED_RED
+          if ((e[c] ^ e[c + 1]) == 1u) {
+            const bool lo_first = (e[c] & 1u) == 0u;
+            red_add_f32x4(reinterpret_cast<float*>(entry_ptr(base, e[c] & ~1u)),
+                          lo_first ? acc[2 * c] : acc[2 * c + 2], lo_first ? acc[2 * c + 1] : acc[2 * c + 3],
+                          lo_first ? acc[2 * c + 2] : acc[2 * c], lo_first ? acc[2 * c + 3] : acc[2 * c + 1]);
+            continue;
+          }
+#endif
+          red_add_f32x2(reinterpret_cast<float*>(entry_ptr(base, e[c])), acc[2 * c], acc[2 * c + 1]);
+          red_add_f32x2(reinterpret_cast<float*>(entry_ptr(base, e[c + 1])), acc[2 * c + 2], acc[2 * c + 3]);
+        }
       };
 #pragma unroll 1
       while (nz) {

@@ -103,6 +103,21 @@ __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
       : "memory");
 }
 
+// ---- bulk asynchronous copy global -> shared (TMA engine, no tensor map) ------------------------
+// One thread announces `bytes` on the mbarrier and issues the copy; the barrier's phase completes
+// when the bytes have landed (and every other expected arrival has happened). Source, destination
+// and size are multiples of 16 bytes. The data is written through the async proxy, which is the
+// proxy tcgen05.mma reads operands through: no extra fence between the barrier wait and the MMA.
+__device__ __forceinline__ void mbar_expect_tx(uint64_t* bar, uint32_t bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void bulk_g2s(void* smem_dst, const void* gmem_src, uint32_t bytes, uint64_t* bar) {
+  asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(
+                   smem_u32(smem_dst)),
+               "l"(gmem_src), "r"(bytes), "r"(smem_u32(bar))
+               : "memory");
+}
+
 // MN-major operand whose K direction skips row groups: the two 8-row K groups of one MMA are
 // `k_group_stride` row groups apart (see issue_dweight_t in ngp_fused.cu).
 __device__ __forceinline__ uint64_t desc_mn_major_strided(uint32_t saddr, int C, int k_group_stride) {
