@@ -150,6 +150,29 @@ k_linear_tc(const float* __restrict__ x, int64_t ldx, const float* __restrict__ 
                       (!mask || ((ldm & 3) == 0 && (reinterpret_cast<uintptr_t>(mask) & 15) == 0)) &&
                       (!x2 || ((ldx2 & 3) == 0 && (reinterpret_cast<uintptr_t>(x2) & 15) == 0));
 
+  // this thread's 2 x 8 values of a chunk: a quarter warp (8 lanes) owns the 8 rows of ONE core matrix =
+  // 128 contiguous bytes of shared memory (no bank conflicts); in global memory the warp reads 8 rows x
+  // 128 contiguous bytes
+  float xv[2][8];
+  auto fetch_x = [&](int c) {
+#pragma unroll
+    for (int it = 0; it < 2; ++it) {
+      const int r = ((warp + it * (lin::kThreads / 32)) << 3) | (tid & 7), cc = (tid >> 3) & 3;
+      const int64_t row = row0 + r;
+      const int k0 = c * lin::kChunk + cc * 8;
+#pragma unroll
+      for (int j = 0; j < 8; ++j) xv[it][j] = 0.0f;
+      if (row < M) {
+        // columns [0, k_split) come from x, [k_split, k_in) from x2 (k_split is a multiple of 8: a group
+        // of 8 never straddles the two)
+        const bool second = k0 >= k_split;
+        const float* src = second ? x2 + row * ldx2 + (k0 - k_split) : x + row * ldx + k0;
+        load8(src, mask ? mask + row * ldm + k0 : nullptr, (second ? k_in : k_split) - k0, vec_ok, xv[it]);
+      }
+    }
+  };
+  fetch_x(0);
+
   for (int c = 0; c < k_chunks; ++c) {
     const int s = c & 1;
     uint8_t* stage = smem + s * lin::kStage;
@@ -166,26 +189,20 @@ k_linear_tc(const float* __restrict__ x, int64_t ldx, const float* __restrict__ 
 #pragma unroll
       for (int p = 0; p < 3; ++p) bulk_g2s(dst + p * lin::kBTile, src + p * lin::kBTile, bytes, full + s);
     }
-    // ---- X chunk: 128 rows x 32 columns float32 -> three bf16 planes (2 groups of 8 values per thread)
+    // ---- X chunk: 128 rows x 32 columns float32 -> three bf16 planes (2 groups of 8 values per thread).
+    // The values were requested one chunk ahead (xv: registers), so the global-load latency sits
+    // underneath the previous chunk's split, barrier and MMAs; the next chunk is requested now.
+    float cur[2][8];
+#pragma unroll
+    for (int it = 0; it < 2; ++it)
+#pragma unroll
+      for (int j = 0; j < 8; ++j) cur[it][j] = xv[it][j];
+    if (c + 1 < k_chunks) fetch_x(c + 1);
 #pragma unroll
     for (int it = 0; it < 2; ++it) {
-      // a quarter warp (8 lanes) writes the 8 rows of ONE core matrix = 128 contiguous bytes of shared
-      // memory (no bank conflicts); in global memory the warp reads 8 rows x 128 contiguous bytes
       const int r = ((warp + it * (lin::kThreads / 32)) << 3) | (tid & 7), cc = (tid >> 3) & 3;
-      const int64_t row = row0 + r;
-      const int k0 = c * lin::kChunk + cc * 8;
-      float v[8];
-#pragma unroll
-      for (int j = 0; j < 8; ++j) v[j] = 0.0f;
-      if (row < M) {
-        // columns [0, k_split) come from x, [k_split, k_in) from x2 (k_split is a multiple of 8: a group
-        // of 8 never straddles the two)
-        const bool second = k0 >= k_split;
-        const float* src = second ? x2 + row * ldx2 + (k0 - k_split) : x + row * ldx + k0;
-        load8(src, mask ? mask + row * ldm + k0 : nullptr, (second ? k_in : k_split) - k0, vec_ok, v);
-      }
       uint4 hi, mid, lo;
-      split8(v, hi, mid, lo);
+      split8(cur[it], hi, mid, lo);
       st_chunk(stage, r, cc, lin::kChunk, hi);
       st_chunk(stage + lin::kATile, r, cc, lin::kChunk, mid);
       st_chunk(stage + 2 * lin::kATile, r, cc, lin::kChunk, lo);
@@ -294,11 +311,13 @@ constexpr uint32_t kTmemCols = 512;
 }  // namespace ldw
 
 // rows [row_lo, row_lo + 32) x columns [c0, c0 + 256) of a row-major float32 matrix -> three bf16
-// planes in the [32][256] tile layout (zero outside the matrix)
-__device__ __forceinline__ void stage_rows(const float* __restrict__ src, int64_t ld, const float* __restrict__ src2,
+// planes in the [32][256] tile layout (zero outside the matrix), in two halves so that the global
+// loads of the NEXT chunk are in flight while the current one is split and stored:
+// fetch_rows() requests this thread's 4 x 8 values into registers, store_rows() splits and stores them.
+__device__ __forceinline__ void fetch_rows(const float* __restrict__ src, int64_t ld, const float* __restrict__ src2,
                                            int64_t ld2, int split, const float* __restrict__ mask, int64_t ldm,
-                                           int64_t row_lo, int64_t M, int c0, int cols, bool vec_ok, uint8_t* tile,
-                                           int tid, float* colsum = nullptr) {
+                                           int64_t row_lo, int64_t M, int c0, int cols, bool vec_ok, int tid,
+                                           float (&v)[4][8]) {
   const int warp = tid >> 5, lane = tid & 31;
 #pragma unroll
   for (int it = 0; it < 4; ++it) {
@@ -306,20 +325,27 @@ __device__ __forceinline__ void stage_rows(const float* __restrict__ src, int64_
     const int r = ((wi >> 3) << 3) | (lane & 7), cc = ((wi & 7) << 2) | (lane >> 3);
     const int64_t row = row_lo + r;
     const int k0 = c0 + cc * 8;
-    float v[8];
 #pragma unroll
-    for (int j = 0; j < 8; ++j) v[j] = 0.0f;
+    for (int j = 0; j < 8; ++j) v[it][j] = 0.0f;
     if (row < M && k0 < cols) {
       const bool second = k0 >= split;   // columns [split, cols) live in src2
       load8(second ? src2 + row * ld2 + (k0 - split) : src + row * ld + k0, mask ? mask + row * ldm + k0 : nullptr,
-            (second ? cols : split) - k0, vec_ok, v);
+            (second ? cols : split) - k0, vec_ok, v[it]);
     }
+  }
+}
+__device__ __forceinline__ void store_rows(const float (&v)[4][8], uint8_t* tile, int tid, float* colsum = nullptr) {
+  const int warp = tid >> 5, lane = tid & 31;
+#pragma unroll
+  for (int it = 0; it < 4; ++it) {
+    const int wi = warp + it * (ldw::kThreads / 32);
+    const int r = ((wi >> 3) << 3) | (lane & 7), cc = ((wi & 7) << 2) | (lane >> 3);
     if (colsum) {  // a thread's column group cc is the same in every iteration and every chunk
 #pragma unroll
-      for (int j = 0; j < 8; ++j) colsum[j] += v[j];
+      for (int j = 0; j < 8; ++j) colsum[j] += v[it][j];
     }
     uint4 hi, mid, lo;
-    split8(v, hi, mid, lo);
+    split8(v[it], hi, mid, lo);
     st_chunk(tile, r, cc, ldw::kWide, hi);
     st_chunk(tile + ldw::kTile, r, cc, ldw::kWide, mid);
     st_chunk(tile + 2 * ldw::kTile, r, cc, ldw::kWide, lo);
@@ -367,14 +393,25 @@ k_linear_dw_tc(const float* __restrict__ dy, int64_t ldy, const float* __restric
   for (int j = 0; j < 8; ++j) colsum[j] = 0.0f;
   const bool want_db = db != nullptr && blockIdx.z == 0;
 
+  float vdy[4][8], vxx[4][8];   // this thread's values of the chunk being staged; requested one chunk ahead
+  fetch_rows(dy, ldy, nullptr, 0, n_out, mask, ldm, c_lo * ldw::kChunk, M, n0, n_out, vy, tid, vdy);
+  fetch_rows(x, ldx, x2, ldx2, k_split, nullptr, 0, c_lo * ldw::kChunk, M, k0, k_in, vx, tid, vxx);
   int it = 0;
   for (int64_t c = c_lo; c < c_hi; ++c, ++it) {
     const int s = it & 1;
     uint8_t* stage = smem + s * ldw::kStage;
+    float cdy[4][8], cxx[4][8];
+#pragma unroll
+    for (int a = 0; a < 4; ++a)
+#pragma unroll
+      for (int j = 0; j < 8; ++j) cdy[a][j] = vdy[a][j], cxx[a][j] = vxx[a][j];
+    if (c + 1 < c_hi) {
+      fetch_rows(dy, ldy, nullptr, 0, n_out, mask, ldm, (c + 1) * ldw::kChunk, M, n0, n_out, vy, tid, vdy);
+      fetch_rows(x, ldx, x2, ldx2, k_split, nullptr, 0, (c + 1) * ldw::kChunk, M, k0, k_in, vx, tid, vxx);
+    }
     if (it >= 2) mbar_wait(bar + s, (uint32_t)(((it >> 1) - 1) & 1));
-    stage_rows(dy, ldy, nullptr, 0, n_out, mask, ldm, c * ldw::kChunk, M, n0, n_out, vy, stage, tid,
-               want_db ? colsum : nullptr);
-    stage_rows(x, ldx, x2, ldx2, k_split, nullptr, 0, c * ldw::kChunk, M, k0, k_in, vx, stage + 3 * ldw::kTile, tid);
+    store_rows(cdy, stage, tid, want_db ? colsum : nullptr);
+    store_rows(cxx, stage + 3 * ldw::kTile, tid);
     fence_async_smem();
     tc_fence_before();
     __syncthreads();
