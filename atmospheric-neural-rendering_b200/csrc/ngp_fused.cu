@@ -1092,29 +1092,14 @@ k_field_bwd_tc2(atmonr_grid_t g, const __half* __restrict__ pos_w, const __half*
       bool open = false;
 #pragma unroll
       for (int c = 0; c < 16; ++c) acc[c] = 0.0f;
-      // The L2 processes REDs per 32-byte sector request (profiles/r3_l2_ubench.json: 43.5 G sector
-      // requests/s whether a request carries one or four lanes' 8 bytes), and these REDs are what bounds
-      // the kernel (1.05e9 requests per launch = 24 ms at that rate). The corners x and x+1 of a cell are
-      // neighbouring entries of one aligned 16-byte pair whenever their entries differ in bit 0 only
-      // (hashed levels: x even, since (x ^ h) and ((x | 1) ^ h) differ in bit 0; dense levels: entry even):
-      // those pairs go out as ONE red.v4.f32.
+      // (Pairing the x / x+1 corners of a cell into one red.v4.f32 when their entries share an aligned
+      // 16-byte pair was measured: 34.5 vs 32.4 ms. The scatter is not what bounds this kernel: without
+      // any RED it runs 26.8 ms, profiles/README.md.)
       auto flush = [&]() {  // entries are only needed here, once per run of samples in one cell
         uint32_t e[8];
         corner_entries3(L, c_run, e);
 #pragma unroll
-        for (int c = 0; c < 8; c += 2) {
-#ifndef ATM_NO_PAIRED_RED
-          if ((e[c] ^ e[c + 1]) == 1u) {
-            const bool lo_first = (e[c] & 1u) == 0u;
-            red_add_f32x4(reinterpret_cast<float*>(entry_ptr(base, e[c] & ~1u)),
-                          lo_first ? acc[2 * c] : acc[2 * c + 2], lo_first ? acc[2 * c + 1] : acc[2 * c + 3],
-                          lo_first ? acc[2 * c + 2] : acc[2 * c], lo_first ? acc[2 * c + 3] : acc[2 * c + 1]);
-            continue;
-          }
-#endif
-          red_add_f32x2(reinterpret_cast<float*>(entry_ptr(base, e[c])), acc[2 * c], acc[2 * c + 1]);
-          red_add_f32x2(reinterpret_cast<float*>(entry_ptr(base, e[c + 1])), acc[2 * c + 2], acc[2 * c + 3]);
-        }
+        for (int c = 0; c < 8; ++c) red_add_f32x2(reinterpret_cast<float*>(entry_ptr(base, e[c])), acc[2 * c], acc[2 * c + 1]);
       };
 #pragma unroll 1
       while (nz) {
@@ -1168,6 +1153,374 @@ k_field_bwd_tc2(atmonr_grid_t g, const __half* __restrict__ pos_w, const __half*
   if (warp == 0) tmem_dealloc<bwd2::kTmemCols>(tmem);
 }
 
+
+// =========================================================================================
+// fused radiance field, backward, FOUR independent 128-row pipelines per CTA (one CTA per SM)
+// =========================================================================================
+// Same arithmetic and the same stage sequence as k_field_bwd_tc2. What changes is how many tiles an SM
+// has in flight. Measured (round 2, B200, 2^18 rays x 1024): the 256-row kernel spends 23.0 ms on the
+// recompute + input-gradient chain alone, +4 ms for the weight-gradient MMAs, +5.5 ms for the scatter,
+// while the MMAs it issues occupy the tensor pipe's issue path for ~14 ms: each of the 9 stages of a
+// tile is a round trip (operand tile -> barrier -> issue -> commit -> mbarrier -> tcgen05.ld) of
+// ~1400 cycles with ~100 cycles of work per warp in it, and two CTAs per SM are the only overlap.
+// Here ONE CTA per SM runs four tiles at once: 16 epilogue warps (pipeline p = warp / 4 owns sample
+// rows 128 p .. 128 p + 127 of a 512-row group, TMEM lanes = its rows, accumulator columns 32 p ..)
+// and one issuer warp that serves the pipelines in a fixed round-robin order, blocking on each
+// pipeline's named barrier in turn: while pipeline p runs its epilogue, the issuer and the tensor
+// pipe work for p+1, p+2, p+3. The weights are shared, and so are the weight-gradient accumulators
+// (the MMAs of all pipelines are issued by one thread and execute in order, so accumulating into one
+// TMEM region from four pipelines is an ordinary accumulate chain). With 512 TMEM columns per CTA
+// every layer's weight gradient concatenates two sample groups per MMA (20 instead of 28 MMAs/tile).
+namespace bwd4 {
+constexpr int kPipes = 4;
+constexpr int kRows = 128;                       // rows per pipeline
+constexpr int kThreads = kPipes * kRows + 32 * kPipes;    // 16 epilogue warps + one MMA-issuer warp per pipeline
+// per-pipeline shared-memory region
+constexpr int kX = 0;
+constexpr int kH = kX + 8192;
+constexpr int kDIN = kH + 8192;
+constexpr int kH1 = kDIN + 8192;
+constexpr int kH2 = kH1 + 8192;
+constexpr int kDO = kH2 + 8192;                  // [128][16]
+constexpr int kPos = kDO + 4096;                 // 3 x 136 floats (rows skewed by row / 16)
+constexpr int kPipeBytes = kPos + 3 * 136 * 4 + 32;   // 46720: a multiple of 128
+// CTA-wide
+constexpr int kW = kPipes * kPipeBytes;          // the five weight tiles (also absorb the last over-read)
+constexpr int kLv = kW + 8192;
+constexpr int kBar = kLv + 512;                  // done[4], free[4]
+constexpr int kTmemPtr = kBar + 64;
+constexpr int kBytes = kTmemPtr + 16;
+constexpr uint32_t kTmemCols = 512;
+constexpr int cAcc = 0;                          // + 32 p
+constexpr int cDWd3 = 128, cDW2p = 160, cDWd2 = 192, cDWd1 = 256, cDW1p = 320;
+static_assert(kPipeBytes % 128 == 0, "pipeline regions must keep the 128-byte tile alignment");
+}  // namespace bwd4
+
+template <int N>
+__device__ __forceinline__ void issue_layer1(uint32_t acc, uint32_t a_tile, uint32_t w_tile) {
+  constexpr uint32_t idesc = make_idesc(128, N, 0, 0);
+#pragma unroll
+  for (int k = 0; k < 2; ++k)
+    umma_f16(acc, desc_k_major(a_tile + k * 2 * kCore, 32), desc_k_major(w_tile + k * 2 * kCore, 32), idesc, k);
+}
+// named barriers 1 + p: the 128 epilogue threads of pipeline p arrive, the issuer warp syncs (count 160);
+// named barriers 5 + p: the 128 epilogue threads of pipeline p among themselves
+__device__ __forceinline__ void pipe_arrive(int p) {
+  fence_async_smem();
+  tc_fence_before();
+  asm volatile("bar.arrive %0, 160;" ::"r"(1 + p) : "memory");
+}
+__device__ __forceinline__ void pipe_wait(int p) {
+  asm volatile("bar.sync %0, 160;" ::"r"(1 + p) : "memory");
+  tc_fence_after();
+}
+__device__ __forceinline__ void pipe_sync(int p) { asm volatile("bar.sync %0, 128;" ::"r"(5 + p) : "memory"); }
+
+template <bool COMPACT>
+__global__ void __launch_bounds__(bwd4::kThreads, 1)
+k_field_bwd_tc4(atmonr_grid_t g, const __half* __restrict__ pos_w, const __half* __restrict__ dir_w,
+                const float* __restrict__ x01, const float* __restrict__ dirs, const __half* __restrict__ enc_in,
+                const float* __restrict__ dsigma_raw, const float* __restrict__ dcolor_raw,
+                const float* __restrict__ grad_absmax, int64_t M_samples, int N, float* __restrict__ dtable,
+                float* __restrict__ dpos_w, float* __restrict__ ddir_w, const uint32_t* __restrict__ active_idx,
+                const uint32_t* __restrict__ n_active) {
+  const int64_t M = COMPACT ? (int64_t)*n_active : M_samples;  // rows
+  extern __shared__ __align__(128) uint8_t smem[];
+  uint64_t* done = reinterpret_cast<uint64_t*>(smem + bwd4::kBar);        // done[p]: committed MMAs of pipeline p's stage
+  uint64_t* free_ = done + bwd4::kPipes;                                   // free[p]: every MMA reading p's tile is complete
+  uint32_t* tmem_ptr = reinterpret_cast<uint32_t*>(smem + bwd4::kTmemPtr);
+  const int tid = threadIdx.x, warp = tid >> 5;
+  LevelRow* lv = reinterpret_cast<LevelRow*>(smem + bwd4::kLv);
+  load_level_table(g, lv);
+  load_field_weights(smem + bwd4::kW, pos_w, dir_w);
+  if (warp == 0) tmem_alloc<bwd4::kTmemCols>(tmem_ptr);
+  if (tid == 0) {
+    for (int p = 0; p < 2 * bwd4::kPipes; ++p) mbar_init(done + p, 1);
+    fence_mbar_init();
+  }
+  publish_and_sync();
+  tc_fence_after();
+  const uint32_t tmem = *tmem_ptr;
+  const uint32_t sb = smem_u32(smem), sw = sb + bwd4::kW;
+  float S = 1.0f;
+  if (grad_absmax) {
+    const float amax = *grad_absmax;
+    if (amax > 0.0f && amax < INFINITY) S = exp2f(fminf(fmaxf(floorf(log2f(2048.0f / amax)), -60.0f), 60.0f));
+  }
+  const float invS = 1.0f / S;
+  // zero the (shared) weight-gradient accumulators: columns 128 .. 383 of all 128 lanes
+  if (warp < 4) {
+    tmem_st_zero128(tmem_addr(tmem, warp, bwd4::cDWd3));
+    tmem_st_zero128(tmem_addr(tmem, warp, bwd4::cDWd3 + 128));
+    tmem_st_wait();
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const int64_t n_tiles = (M + bwd4::kRows - 1) / bwd4::kRows;
+  // tile of pipeline p in iteration `it` of this CTA: ((it * gridDim + blockIdx) * 4 + p)
+  const int64_t group_stride = (int64_t)gridDim.x * bwd4::kPipes;
+  const int64_t first_tile = (int64_t)blockIdx.x * bwd4::kPipes;
+
+  if (warp >= bwd4::kPipes * 4) {
+    // ------------------------------- MMA issuer warps: one per pipeline ----------------------
+    // (all 32 lanes run this code converged; umma_f16 / umma_commit elect the issuing lane)
+    // Each issuer only ever blocks on ITS pipeline's barrier, so the pipelines drift apart freely (a
+    // single issuer serving the four pipelines in a fixed order was measured at 39 - 50 ms: one
+    // pipeline in its scatter phase held up the other three). The weight-gradient accumulators are
+    // shared: they are zeroed below and every MMA accumulates (the tensor pipe executes the MMAs of
+    // all four issuers in one queue; consecutive accumulations into one TMEM region are the ordinary
+    // K-loop dependence).
+    const int p = warp - bwd4::kPipes * 4;
+    const uint32_t pb = sb + p * bwd4::kPipeBytes;
+    const uint32_t acc = tmem + bwd4::cAcc + 32 * p;
+    for (int64_t tile = first_tile + p; tile < n_tiles; tile += group_stride) {
+      pipe_wait(p);
+      issue_layer1<32>(acc, pb + bwd4::kX, sw + fwd::kW1P); umma_commit(done + p);
+      pipe_wait(p);
+      issue_layer1<16>(acc, pb + bwd4::kH, sw + fwd::kW2P); umma_commit(done + p);
+      pipe_wait(p);
+      issue_layer1<32>(acc, pb + bwd4::kDIN, sw + fwd::kWD1); umma_commit(done + p);
+      pipe_wait(p);
+      issue_layer1<32>(acc, pb + bwd4::kH1, sw + fwd::kWD2); umma_commit(done + p);
+      pipe_wait(p);  // S0: DO = dL/d(dir_mlp out), H2
+      issue_dinput<16>(acc, pb + bwd4::kDO, sw + fwd::kWD3);
+      umma_commit(done + p);
+      ATM_DW issue_dweight_t<16, 2, 128>(tmem + bwd4::cDWd3, pb + bwd4::kH2, pb + bwd4::kDO, 1u);
+      pipe_wait(p);  // S1: X = dL/dh2
+      issue_dinput<32>(acc, pb + bwd4::kX, sw + fwd::kWD2);
+      umma_commit(done + p);
+      ATM_DW issue_dweight_t<32, 2, 128>(tmem + bwd4::cDWd2, pb + bwd4::kH1, pb + bwd4::kX, 1u);
+      pipe_wait(p);  // S2: H2 = dL/dh1
+      issue_dinput<32>(acc, pb + bwd4::kH2, sw + fwd::kWD1);
+      umma_commit(done + p);
+      ATM_DW issue_dweight_t<32, 2, 128>(tmem + bwd4::cDWd1, pb + bwd4::kDIN, pb + bwd4::kH2, 1u);
+      pipe_wait(p);  // S3: DO = dL/d(pos_mlp out)
+      issue_dinput<16>(acc, pb + bwd4::kDO, sw + fwd::kW2P);
+      umma_commit(done + p);
+      ATM_DW issue_dweight_t<16, 2, 128>(tmem + bwd4::cDW2p, pb + bwd4::kH, pb + bwd4::kDO, 1u);
+      pipe_wait(p);  // S4: H1 = dL/dh, DIN = encoded features again
+      issue_dinput<32>(acc, pb + bwd4::kH1, sw + fwd::kW1P);
+      umma_commit(done + p);
+      ATM_DW issue_dweight_t<32, 2, 128>(tmem + bwd4::cDW1p, pb + bwd4::kDIN, pb + bwd4::kH1, 1u);
+      umma_commit(free_ + p);  // tile boundary: every MMA that reads this tile's buffers
+      __syncwarp();
+    }
+  } else {
+    // ------------------------------- epilogue warps ---------------------------------------------
+    const int p = warp >> 2;                    // pipeline
+    const int row = tid & (bwd4::kRows - 1);    // row of the pipeline's tile == TMEM lane
+    uint8_t* base = smem + p * bwd4::kPipeBytes;
+    uint8_t* X = base + bwd4::kX;
+    uint8_t* H = base + bwd4::kH;
+    uint8_t* DIN = base + bwd4::kDIN;
+    uint8_t* H1 = base + bwd4::kH1;
+    uint8_t* H2 = base + bwd4::kH2;
+    uint8_t* DO = base + bwd4::kDO;
+    float* pos = reinterpret_cast<float*>(base + bwd4::kPos);
+    uint64_t* my_done = done + p;
+    uint64_t* my_free = free_ + p;
+    const uint32_t my32 = tmem_addr(tmem, warp, bwd4::cAcc + 32 * p);
+    uint32_t phase = 0, phase2 = 0, seen_tile = 0;
+    const int64_t my_first = first_tile + p;
+    // This thread's inputs of the NEXT tile (encoded features, position) are loaded into registers
+    // before the scatter phase of the current tile, so a tile never starts with an exposed global load.
+    uint4 nx[4];
+    float npos[3];
+    int64_t nsample = 0;     // sample index of the next tile's row
+    uint32_t idx_ahead = 0;  // COMPACT: list entry of this thread's row one tile further
+    auto load_idx = [&](int64_t t) -> uint32_t {
+      if (!COMPACT || t >= n_tiles) return 0u;
+      const int64_t ii = t * bwd4::kRows + row;
+      return __ldg(active_idx + (ii < M ? ii : M - 1));
+    };
+    auto fetch_inputs = [&](int64_t t) {
+      const int64_t ii = t * bwd4::kRows + row;
+      int64_t jj = ii < M ? ii : M - 1;
+      if (COMPACT) {
+        jj = (int64_t)idx_ahead;
+        idx_ahead = load_idx(t + group_stride);
+      }
+      nsample = jj;
+      const uint4* src = reinterpret_cast<const uint4*>(enc_in + jj * 32);
+#pragma unroll
+      for (int cc = 0; cc < 4; ++cc) nx[cc] = __ldg(src + cc);
+      npos[0] = __ldg(x01 + 3 * jj), npos[1] = __ldg(x01 + 3 * jj + 1), npos[2] = __ldg(x01 + 3 * jj + 2);
+    };
+    if (my_first < n_tiles) {
+      idx_ahead = load_idx(my_first);
+      fetch_inputs(my_first);
+    }
+
+    for (int64_t tile = my_first; tile < n_tiles; tile += group_stride, seen_tile = 1) {
+      const int64_t i = tile * bwd4::kRows + row;  // row (indexes the incoming gradients)
+      const bool valid = i < M;
+      const int64_t j = nsample;                   // sample (indexes enc_in, x01, dirs)
+      if (seen_tile) mbar_wait(my_free, phase2), phase2 ^= 1;
+      const uint4* enc_row = reinterpret_cast<const uint4*>(enc_in + j * 32);
+      // ---------------- recompute the activations ----------------
+#pragma unroll
+      for (int cc = 0; cc < 4; ++cc) st_chunk(X, row, cc, 32, nx[cc]);
+      pipe_arrive(p);
+      {
+        const int at = row + (row >> 4);
+        pos[at] = npos[0], pos[136 + at] = npos[1], pos[272 + at] = npos[2];
+      }
+      float4 dc_in = make_float4(0.0f, 0.0f, 0.0f, 0.0f);
+      float ds_in = 0.0f;
+      if (valid) dc_in = __ldg(reinterpret_cast<const float4*>(dcolor_raw + 4 * i)), ds_in = __ldg(dsigma_raw + i);
+      const float* dptr = dirs + (size_t)((uint32_t)j / (uint32_t)N) * 3;  // the ray's direction (dir_mlp input)
+      const float dr[3] = {__ldg(dptr), __ldg(dptr + 1), __ldg(dptr + 2)};
+      mbar_wait(my_done, phase), phase ^= 1;
+      tc_fence_after();
+      float v[32];
+      tmem_ld32(my32, v);
+      store_row32<true>(H, row, v);
+      pipe_arrive(p);
+      mbar_wait(my_done, phase), phase ^= 1;
+      tc_fence_after();
+      {
+        float po[16];
+        tmem_ld16(my32, po);
+        dir_input_row(dr, po, v);
+      }
+      store_row32<false>(DIN, row, v);
+      pipe_arrive(p);
+      mbar_wait(my_done, phase), phase ^= 1;
+      tc_fence_after();
+      tmem_ld32(my32, v);
+      store_row32<true>(H1, row, v);
+      pipe_arrive(p);
+      mbar_wait(my_done, phase), phase ^= 1;
+      tc_fence_after();
+      tmem_ld32(my32, v);
+      store_row32<true>(H2, row, v);
+      // ---------------- backward ----------------
+      {
+        float dout[16];
+#pragma unroll
+        for (int k = 0; k < 16; ++k) dout[k] = 0.0f;
+        dout[0] = dc_in.x * S, dout[1] = dc_in.y * S, dout[2] = dc_in.z * S, dout[3] = dc_in.w * S;
+        store_row16(DO, row, dout);
+      }
+      pipe_arrive(p);  // S0
+      mbar_wait(my_done, phase), phase ^= 1;
+      tc_fence_after();
+      tmem_ld32(my32, v);
+      store_row32_masked(X, H2, row, v);  // dL/dh2 -> X (layer 0 finished with the encoded features)
+      pipe_arrive(p);  // S1
+      mbar_wait(my_done, phase), phase ^= 1;  // covers dW(d3): DO and H2 are free
+      tc_fence_after();
+      tmem_ld32(my32, v);
+      store_row32_masked(H2, H1, row, v);  // dL/dh1 -> H2
+      pipe_arrive(p);  // S2
+      mbar_wait(my_done, phase), phase ^= 1;  // covers dW(d2): X and H1 are free
+      tc_fence_after();
+      tmem_ld32(my32, v);
+      {
+        float dpo[16];
+        dpo[0] = ds_in * S;
+#pragma unroll
+        for (int k = 1; k < 16; ++k) dpo[k] = v[3 + k];
+        store_row16(DO, row, dpo);  // dL/d(pos_mlp out) -> DO
+      }
+      pipe_arrive(p);  // S3
+      mbar_wait(my_done, phase), phase ^= 1;  // covers dW(d1): H2 and DIN are free
+      tc_fence_after();
+      tmem_ld32(my32, v);
+      store_row32_masked(H1, H, row, v);  // dL/dh -> H1
+#pragma unroll
+      for (int cc = 0; cc < 4; ++cc) st_chunk(DIN, row, cc, 32, enc_row[cc]);  // encoded features again -> DIN
+      pipe_arrive(p);  // S4
+      mbar_wait(my_done, phase), phase ^= 1;  // covers dW(2p): DO and H are free
+      tc_fence_after();
+      // ---- table-gradient scatter with run-length merging (see k_field_bwd_tc2) ------------------
+      tmem_ld32(my32, v);
+      tc_fence_before();
+      {
+        float* srow = reinterpret_cast<float*>(X) + row * 32;      // X and H: 16 KB of fp32 staging
+        const int swz = (row ^ (row >> 4)) & 7;
+#pragma unroll
+        for (int k = 0; k < 8; ++k)   // 16-byte chunks, XOR-swizzled by the row to spread banks
+          *reinterpret_cast<float4*>(srow + ((k ^ swz) << 2)) =
+              make_float4(v[4 * k] * invS, v[4 * k + 1] * invS, v[4 * k + 2] * invS, v[4 * k + 3] * invS);
+      }
+      pipe_sync(p);
+      if (tile + group_stride < n_tiles) fetch_inputs(tile + group_stride);
+      {
+        const int grp = row & 7, lvl = row >> 3;   // 8 groups of 16 rows x 16 levels
+        const LevelRow L = lv[lvl];
+        float2* tbase = reinterpret_cast<float2*>(dtable) + L.offset;
+        const float* stage = reinterpret_cast<const float*>(X);
+        const int64_t row0 = tile * bwd4::kRows + grp * 16;
+        const float* srow0 = stage + grp * 16 * 32 + ((lvl & 1) << 1);
+        uint32_t nz = 0;
+#pragma unroll
+        for (int r = 0; r < 16; ++r) {
+          const float2 d = *reinterpret_cast<const float2*>(srow0 + r * 32 + ((((lvl >> 1) ^ ((r ^ grp) & 7))) << 2));
+          nz |= (d.x != 0.0f || d.y != 0.0f) ? (1u << r) : 0u;
+        }
+        if (row0 + 16 > M) nz &= row0 < M ? (1u << (int)(M - row0)) - 1u : 0u;
+        if (!ATM_SCATTER_ON) nz = 0;
+        float acc[16];
+        uint32_t c_run[3] = {0xffffffffu, 0xffffffffu, 0xffffffffu};
+        bool open = false;
+#pragma unroll
+        for (int c = 0; c < 16; ++c) acc[c] = 0.0f;
+        auto flush = [&]() {  // entries are only needed here, once per run of samples in one cell
+          uint32_t e[8];
+          corner_entries3(L, c_run, e);
+#pragma unroll
+          for (int c = 0; c < 8; ++c) red_add_f32x2(reinterpret_cast<float*>(entry_ptr(tbase, e[c])), acc[2 * c], acc[2 * c + 1]);
+        };
+#pragma unroll 1
+        while (nz) {
+          const int r = __ffs(nz) - 1;
+          nz &= nz - 1u;
+          const int rr = grp * 16 + r;
+          const float2 d = *reinterpret_cast<const float2*>(srow0 + r * 32 + ((((lvl >> 1) ^ ((r ^ grp) & 7))) << 2));
+          const float* pp = pos + rr + (rr >> 4);
+          const float q[3] = {pp[0], pp[136], pp[272]};
+          uint32_t cell[3];
+          float frac[3], w[8];
+          grid_cell<3>(q, L.scale, cell, frac);
+          corner_weights3(frac, w);
+          if (open && (cell[0] != c_run[0] || cell[1] != c_run[1] || cell[2] != c_run[2])) {
+            flush();
+#pragma unroll
+            for (int c = 0; c < 16; ++c) acc[c] = 0.0f;
+          }
+#pragma unroll
+          for (int c = 0; c < 8; ++c) {
+            acc[2 * c] = fmaf(w[c], d.x, acc[2 * c]);
+            acc[2 * c + 1] = fmaf(w[c], d.y, acc[2 * c + 1]);
+          }
+          c_run[0] = cell[0], c_run[1] = cell[1], c_run[2] = cell[2];
+          open = true;
+        }
+        if (open) flush();
+      }
+      pipe_sync(p);  // the staging area is the next tile's X/H
+    }
+    // this pipeline's last tile: its free[] completion has not been consumed by anybody
+    if (seen_tile) mbar_wait(my_free, phase2);
+  }
+
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  if (warp < 2 && first_tile < n_tiles) {
+    const int lane = tid & 31;
+    flush_dweight_t<32, 2>(tmem, bwd4::cDW1p, warp, lane, 32, invS, dpos_w);
+    flush_dweight_t<16, 2>(tmem, bwd4::cDW2p, warp, lane, 16, invS, dpos_w + 1024);
+    flush_dweight_t<32, 2>(tmem, bwd4::cDWd1, warp, lane, 32, invS, ddir_w);
+    flush_dweight_t<32, 2>(tmem, bwd4::cDWd2, warp, lane, 32, invS, ddir_w + 1024);
+    flush_dweight_t<16, 2>(tmem, bwd4::cDWd3, warp, lane, 16, invS, ddir_w + 2048);
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 0) tmem_dealloc<bwd4::kTmemCols>(tmem);
+}
 
 
 }  // namespace atm
@@ -1252,6 +1605,18 @@ int atmonr_ngp_field_bwd_tc(const atmonr_grid_t* g, const void* table, const atm
   if (M == 0) return 0;
   ATM_REQUIRE(M < ((int64_t)1 << 31), "atmonr_ngp_field_bwd_tc", "B*N must be below 2^31 per call (chunk the batch)");
   const bool use_wide = getenv("ATMONR_BWD_NARROW") == nullptr;  // read per call: tests toggle it
+  const char* pipes = getenv("ATMONR_BWD_PIPES");                // "2": the 256-row kernel, two CTAs per SM (cross-check)
+  if (enc && use_wide && !(pipes && pipes[0] == '2')) {
+    cudaError_t e4 = cudaFuncSetAttribute(k_field_bwd_tc4<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, bwd4::kBytes);
+    if (e4 != cudaSuccess) return fail("atmonr_ngp_field_bwd_tc", cudaGetErrorString(e4));
+    const int64_t groups = (M + bwd4::kPipes * bwd4::kRows - 1) / (bwd4::kPipes * bwd4::kRows);
+    const int grid4 = (int)(groups < (int64_t)tc_num_sms() ? groups : (int64_t)tc_num_sms());
+    k_field_bwd_tc4<false><<<grid4, bwd4::kThreads, bwd4::kBytes, reinterpret_cast<cudaStream_t>(stream)>>>(
+        *g, (const __half*)pos_w, (const __half*)dir_w, x01, dirs, (const __half*)enc, dsigma_raw, dcolor_raw,
+        grad_absmax, M, N, dtable, dpos_w, ddir_w, nullptr, nullptr);
+    ATM_CHECK_LAUNCH("atmonr_ngp_field_bwd_tc");
+    return 0;
+  }
   if (enc && use_wide) {
     cudaError_t e2 = cudaFuncSetAttribute(k_field_bwd_tc2<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, bwd2::kBytes);
     if (e2 != cudaSuccess) return fail("atmonr_ngp_field_bwd_tc", cudaGetErrorString(e2));
@@ -1287,6 +1652,18 @@ int atmonr_ngp_field_bwd_tc_compact(const atmonr_grid_t* g, const atmonr_mlp_t* 
   if (M == 0) return 0;
   ATM_REQUIRE(M < ((int64_t)1 << 31), "atmonr_ngp_field_bwd_tc_compact", "B*N must be below 2^31 per call (chunk the batch)");
   ATM_REQUIRE(enc && active_idx && n_active && dsigma_c && dcolor_c, "atmonr_ngp_field_bwd_tc_compact", "null argument");
+  const char* pipes = getenv("ATMONR_BWD_PIPES");
+  if (!(pipes && pipes[0] == '2')) {
+    cudaError_t e4 = cudaFuncSetAttribute(k_field_bwd_tc4<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, bwd4::kBytes);
+    if (e4 != cudaSuccess) return fail("atmonr_ngp_field_bwd_tc_compact", cudaGetErrorString(e4));
+    const int64_t groups = (M + bwd4::kPipes * bwd4::kRows - 1) / (bwd4::kPipes * bwd4::kRows);  // upper bound
+    const int grid4 = (int)(groups < (int64_t)tc_num_sms() ? groups : (int64_t)tc_num_sms());
+    k_field_bwd_tc4<true><<<grid4, bwd4::kThreads, bwd4::kBytes, reinterpret_cast<cudaStream_t>(stream)>>>(
+        *g, (const __half*)pos_w, (const __half*)dir_w, x01, dirs, (const __half*)enc, dsigma_c, dcolor_c, grad_absmax, M,
+        N, dtable, dpos_w, ddir_w, active_idx, n_active);
+    ATM_CHECK_LAUNCH("atmonr_ngp_field_bwd_tc_compact");
+    return 0;
+  }
   cudaError_t e2 = cudaFuncSetAttribute(k_field_bwd_tc2<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, bwd2::kBytes);
   if (e2 != cudaSuccess) return fail("atmonr_ngp_field_bwd_tc_compact", cudaGetErrorString(e2));
   const int64_t tiles2 = (M + bwd2::kRows - 1) / bwd2::kRows;  // upper bound: the list length is only known on the device

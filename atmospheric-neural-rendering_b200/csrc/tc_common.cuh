@@ -203,6 +203,14 @@ __device__ __forceinline__ void tmem_ld32(uint32_t taddr, float (&v)[32]) {
   for (int i = 0; i < 32; ++i) v[i] = __uint_as_float(r[i]);
 }
 
+// registers -> TMEM: 128 consecutive columns of this warp's 32 lanes set to zero
+__device__ __forceinline__ void tmem_st_zero128(uint32_t taddr) {
+#pragma unroll
+  for (int c = 0; c < 128; c += 8)
+    asm volatile("tcgen05.st.sync.aligned.32x32b.x8.b32 [%0], {%1,%1,%1,%1,%1,%1,%1,%1};" ::"r"(taddr + c), "r"(0u) : "memory");
+}
+__device__ __forceinline__ void tmem_st_wait() { asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory"); }
+
 // TMEM address of (lane quarter of this warp, column)
 __device__ __forceinline__ uint32_t tmem_addr(uint32_t base, int warp, int col) {
   return base + ((uint32_t)((warp & 3) * 32) << 16) + (uint32_t)col;
