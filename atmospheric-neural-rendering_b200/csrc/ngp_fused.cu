@@ -752,425 +752,44 @@ k_field_bwd_tc(atmonr_grid_t g, const __half2* __restrict__ table, const __half*
 
 
 // =========================================================================================
-// fused radiance field, backward, 256-row tiles (two 128-row MMA halves per CTA)
+// fused radiance field, backward, FOUR independent 128-row pipelines per CTA (one CTA per SM)
 // =========================================================================================
-// Same arithmetic as k_field_bwd_tc. Differences: 256 threads own 256 sample rows, so each
-// barrier / MMA round trip serves twice the samples and 16 warps per SM are resident (2 CTAs);
-// shared memory is reused along the backward chain so that two CTAs fit:
-//   X   : encoded features (until layer 0 is done)  -> dL/dh2
-//   H   : pos_mlp hidden
-//   DIN : dir_mlp input                              -> encoded features again (re-read from
-//                                                        the forward's cache for dW of layer 0)
+// Same arithmetic as k_field_bwd_tc (the 128-row kernel above, which re-gathers the table when the
+// forward's encoding cache is absent); this one reads the cached encoding and is built for throughput.
+//
+// A tile (128 sample rows) goes through 9 tensor-core round trips: 4 recompute layers (activations
+// are recomputed from the cached encoding, not stored) and 5 backward stages, each = "epilogue warps
+// write an operand tile -> named barrier -> issuer warp issues the input-gradient MMAs, commits, then
+// issues the stage's weight-gradient MMAs (which run while the epilogue warps already process the
+// committed result) -> mbarrier -> tcgen05.ld". Shared memory is reused along the chain:
+//   X   : encoded features (until layer 0 is done)  -> dL/dh2          -> fp32 staging of the scatter
+//   H   : pos_mlp hidden                                                -> fp32 staging of the scatter
+//   DIN : dir_mlp input                              -> encoded features again (for dW of layer 0)
 //   H1  : dir_mlp hidden 0                           -> dL/dh
 //   H2  : dir_mlp hidden 1                           -> dL/dh1
 //   DO  : dL/d(dir_mlp out)                          -> dL/d(pos_mlp out)
 // A buffer is only overwritten after the mbarrier wait that proves its last MMA reader is done
-// (tcgen05.commit covers every MMA issued before it).
-namespace bwd2 {
-constexpr int kRows = 256;
-constexpr int kThreads = 288;            // 8 epilogue warps (one sample row per thread) + the MMA-issuer warp
-constexpr int kX = 0;
-constexpr int kH = kX + 16384;
-constexpr int kDIN = kH + 16384;
-constexpr int kH1 = kDIN + 16384;
-constexpr int kH2 = kH1 + 16384;
-constexpr int kDO = kH2 + 16384;      // [256][16]
-constexpr int kW = kDO + 8192;        // weights last: they also absorb the 128-row over-reads
-constexpr int kLv = kW + 8192;
-constexpr int kPos = kLv + 512;       // sample positions of the tile, 3 x 272 floats (skewed rows)
-constexpr int kBar = kPos + 3 * 272 * 4;
-constexpr int kBar2 = kBar + 8;
-constexpr int kTmemPtr = kBar2 + 8;
-constexpr int kBytes = kTmemPtr + 8;
-constexpr uint32_t kTmemCols = 256;
-constexpr int cHalf = 32;             // per-half accumulator (the 16-wide results use its first columns)
-// weight-gradient accumulators (issue_dweight_t): the two 16-column layers and one 32-column
-// layer concatenate two sample groups per MMA, the other two layers take the columns that are left
-constexpr int cDWd3 = 64, cDW2p = 96, cDWd2 = 128, cDWd1 = 192, cDW1p = 224;
-}  // namespace bwd2
-
-template <int N>
-__device__ __forceinline__ void issue_layer2(uint32_t tmem, int col, uint32_t a_tile, uint32_t w_tile) {
-  constexpr uint32_t idesc = make_idesc(128, N, 0, 0);
-#pragma unroll
-  for (int h = 0; h < 2; ++h)
-#pragma unroll
-    for (int k = 0; k < 2; ++k)
-      umma_f16(tmem + h * bwd2::cHalf + col, desc_k_major(a_tile + h * 8192 + k * 2 * kCore, 32),
-               desc_k_major(w_tile + k * 2 * kCore, 32), idesc, k);
-}
-template <int KD>
-__device__ __forceinline__ void issue_dinput2(uint32_t tmem, uint32_t d_tile, uint32_t w_tile) {
-  constexpr uint32_t idesc = make_idesc(128, 32, 0, 1);
-#pragma unroll
-  for (int h = 0; h < 2; ++h)
-#pragma unroll
-    for (int k = 0; k < KD / 16; ++k)
-      umma_f16(tmem + h * bwd2::cHalf, desc_k_major(d_tile + h * 16 * (KD / 8) * kCore + k * 2 * kCore, KD),
-               desc_mn_major(w_tile + k * 2 * 4 * kCore, 32), idesc, k);
-}
-// named barrier 1: epilogue warps arrive (non-blocking) when their rows of a stage's operand tile
-// are written, the issuer warp waits on it; named barrier 2: the 256 epilogue threads only
-__device__ __forceinline__ void stage_arrive() {
-  fence_async_smem();
-  tc_fence_before();
-  asm volatile("bar.arrive 1, 288;" ::: "memory");
-}
-__device__ __forceinline__ void stage_wait() {
-  asm volatile("bar.sync 1, 288;" ::: "memory");
-  tc_fence_after();
-}
-__device__ __forceinline__ void epilogue_sync() { asm volatile("bar.sync 2, 256;" ::: "memory"); }
-
+// (tcgen05.commit covers every MMA issued before it by the same thread).
+//
+// One round trip is ~1400 cycles with ~100 instructions of work per warp in it, so what matters is how
+// many INDEPENDENT tiles an SM has in flight and how freely they drift apart. Measured (round 2, B200,
+// 2^18 rays x 1024): two CTAs per SM with 256-row tiles (two halves in lock-step behind one issuer
+// warp): 32.4 ms, of which 23.0 ms is the recompute + input-gradient chain alone, +4 ms weight-gradient
+// MMAs, +5.5 ms scatter. This kernel: ONE CTA per SM runs four 128-row pipelines (pipeline p = epilogue
+// warps 4p .. 4p+3, TMEM lanes = its rows, accumulator columns 32 p ..) and FOUR issuer warps, one per
+// pipeline, each blocking only on its own pipeline's named barrier: 27.0 ms. (One issuer warp serving
+// the four pipelines in a fixed order: 39 ms, with a static software-pipelined slot schedule: 47-50 ms;
+// a pipeline in its scatter phase holds up the other three.) The weights are shared, and so are the
+// weight-gradient accumulators: they are zeroed once and every pipeline's MMAs accumulate into them
+// (one tensor-pipe queue per SM; consecutive accumulations into one TMEM region are the ordinary
+// K-loop dependence). With 512 TMEM columns per CTA every layer's weight gradient concatenates two
+// sample groups per MMA (issue_dweight_t, WAYS = 2): 20 weight-gradient MMAs per tile.
+//
 // COMPACT: the rows are not samples 0..M-1 but the `*n_active` samples listed in active_idx (the
 // ones whose incoming gradient can be non-zero, written by k_composite_bwd in compact mode together
 // with their gradients dsigma_raw / dcolor_raw, which are then indexed by ROW, not by sample).
 // A sample with a zero incoming gradient contributes exactly zero to every output of this kernel,
 // so leaving it out changes nothing but the time.
-template <bool COMPACT>
-__global__ void __launch_bounds__(bwd2::kThreads, 2)
-k_field_bwd_tc2(atmonr_grid_t g, const __half* __restrict__ pos_w, const __half* __restrict__ dir_w,
-                const float* __restrict__ x01, const float* __restrict__ dirs, const __half* __restrict__ enc_in,
-                const float* __restrict__ dsigma_raw, const float* __restrict__ dcolor_raw,
-                const float* __restrict__ grad_absmax, int64_t M_samples, int N, float* __restrict__ dtable,
-                float* __restrict__ dpos_w, float* __restrict__ ddir_w, const uint32_t* __restrict__ active_idx,
-                const uint32_t* __restrict__ n_active) {
-  const int64_t M = COMPACT ? (int64_t)*n_active : M_samples;  // rows
-  extern __shared__ __align__(128) uint8_t smem[];
-  uint64_t* bar = reinterpret_cast<uint64_t*>(smem + bwd2::kBar);
-  uint64_t* bar2 = reinterpret_cast<uint64_t*>(smem + bwd2::kBar2);
-  uint32_t* tmem_ptr = reinterpret_cast<uint32_t*>(smem + bwd2::kTmemPtr);
-  const int tid = threadIdx.x, warp = tid >> 5;
-  LevelRow* lv = reinterpret_cast<LevelRow*>(smem + bwd2::kLv);
-  load_level_table(g, lv);
-  load_field_weights(smem + bwd2::kW, pos_w, dir_w);
-  if (warp == 0) tmem_alloc<bwd2::kTmemCols>(tmem_ptr);
-  if (tid == 0) {
-    mbar_init(bar, 1);
-    mbar_init(bar2, 1);
-    fence_mbar_init();
-  }
-  publish_and_sync();
-  tc_fence_after();
-  const uint32_t tmem = *tmem_ptr;
-  const uint32_t sb = smem_u32(smem), sw = sb + bwd2::kW;
-  float S = 1.0f;
-  if (grad_absmax) {
-    const float amax = *grad_absmax;
-    if (amax > 0.0f && amax < INFINITY) S = exp2f(fminf(fmaxf(floorf(log2f(2048.0f / amax)), -60.0f), 60.0f));
-  }
-  const float invS = 1.0f / S;
-  const bool cta_has_work = (int64_t)blockIdx.x * bwd2::kRows < M;
-
-  if (warp == 8) {
-    // ------------------------------- MMA issuer warp ----------------------------------------
-    // (all 32 lanes run this code converged; umma_f16 / umma_commit elect the issuing lane)
-    // Every tcgen05.mma of the CTA is issued here, so the epilogue warps never stall behind the
-    // (long) weight-gradient issue sequences: a stage's input-gradient MMAs are committed first,
-    // its weight-gradient MMAs are issued while the epilogue warps already work on the result.
-    uint32_t seen_tile = 0;
-    for (int64_t tile = blockIdx.x; tile * bwd2::kRows < M; tile += gridDim.x, seen_tile = 1) {
-      stage_wait();  // X = encoded features
-      {
-        issue_layer2<32>(tmem, 0, sb + bwd2::kX, sw + fwd::kW1P);
-        umma_commit(bar);
-      }
-      stage_wait();  // H
-      {
-        issue_layer2<16>(tmem, 0, sb + bwd2::kH, sw + fwd::kW2P);
-        umma_commit(bar);
-      }
-      stage_wait();  // DIN
-      {
-        issue_layer2<32>(tmem, 0, sb + bwd2::kDIN, sw + fwd::kWD1);
-        umma_commit(bar);
-      }
-      stage_wait();  // H1
-      {
-        issue_layer2<32>(tmem, 0, sb + bwd2::kH1, sw + fwd::kWD2);
-        umma_commit(bar);
-      }
-      stage_wait();  // S0: DO = dL/d(dir_mlp out), H2
-      {
-        issue_dinput2<16>(tmem, sb + bwd2::kDO, sw + fwd::kWD3);
-        umma_commit(bar);
-        ATM_DW issue_dweight_t<16, 2, 256>(tmem + bwd2::cDWd3, sb + bwd2::kH2, sb + bwd2::kDO, seen_tile);
-      }
-      stage_wait();  // S1: X = dL/dh2
-      {
-        issue_dinput2<32>(tmem, sb + bwd2::kX, sw + fwd::kWD2);
-        umma_commit(bar);
-        ATM_DW issue_dweight_t<32, 2, 256>(tmem + bwd2::cDWd2, sb + bwd2::kH1, sb + bwd2::kX, seen_tile);
-      }
-      stage_wait();  // S2: H2 = dL/dh1
-      {
-        issue_dinput2<32>(tmem, sb + bwd2::kH2, sw + fwd::kWD1);
-        umma_commit(bar);
-        ATM_DW issue_dweight_t<32, 1, 256>(tmem + bwd2::cDWd1, sb + bwd2::kDIN, sb + bwd2::kH2, seen_tile);
-      }
-      stage_wait();  // S3: DO = dL/d(pos_mlp out)
-      {
-        issue_dinput2<16>(tmem, sb + bwd2::kDO, sw + fwd::kW2P);
-        umma_commit(bar);
-        ATM_DW issue_dweight_t<16, 2, 256>(tmem + bwd2::cDW2p, sb + bwd2::kH, sb + bwd2::kDO, seen_tile);
-      }
-      stage_wait();  // S4: H1 = dL/dh, DIN = encoded features again
-      {
-        issue_dinput2<32>(tmem, sb + bwd2::kH1, sw + fwd::kW1P);
-        umma_commit(bar);
-        ATM_DW issue_dweight_t<32, 1, 256>(tmem + bwd2::cDW1p, sb + bwd2::kDIN, sb + bwd2::kH1, seen_tile);
-        umma_commit(bar2);  // tile boundary: every MMA that reads this tile's buffers
-      }
-      __syncwarp();
-    }
-  } else {
-  // ------------------------------- epilogue warps ---------------------------------------------
-  const uint32_t my32 = tmem_addr(tmem, warp, (warp >> 2) * bwd2::cHalf), my16 = my32;
-  uint8_t* X = smem + bwd2::kX;
-  uint8_t* H = smem + bwd2::kH;
-  uint8_t* DIN = smem + bwd2::kDIN;
-  uint8_t* H1 = smem + bwd2::kH1;
-  uint8_t* H2 = smem + bwd2::kH2;
-  uint8_t* DO = smem + bwd2::kDO;
-  uint32_t phase = 0, phase2 = 0, seen_tile = 0;
-  // This thread's inputs of the NEXT tile (encoded features, position) are loaded into registers
-  // before the scatter phase of the current tile, so a tile never starts with an exposed global
-  // load (that wait was 15 % of the epilogue warps' time).
-  uint4 nx[4];
-  float npos[3];
-  int64_t nsample = 0;     // sample index of the next tile's row
-  uint32_t idx_ahead = 0;  // COMPACT: list entry of this thread's row one tile further (so that the row
-                           // loads below never wait for the index load)
-  auto load_idx = [&](int64_t t) -> uint32_t {
-    if (!COMPACT || t * bwd2::kRows >= M) return 0u;
-    const int64_t ii = t * bwd2::kRows + tid;
-    return __ldg(active_idx + (ii < M ? ii : M - 1));
-  };
-  if (cta_has_work) idx_ahead = load_idx(blockIdx.x);
-  auto fetch_inputs = [&](int64_t t) {
-    const int64_t ii = t * bwd2::kRows + tid;
-    int64_t jj = ii < M ? ii : M - 1;
-    if (COMPACT) {
-      jj = (int64_t)idx_ahead;
-      idx_ahead = load_idx(t + gridDim.x);
-    }
-    nsample = jj;
-    const uint4* src = reinterpret_cast<const uint4*>(enc_in + jj * 32);
-#pragma unroll
-    for (int cc = 0; cc < 4; ++cc) nx[cc] = __ldg(src + cc);
-    npos[0] = __ldg(x01 + 3 * jj), npos[1] = __ldg(x01 + 3 * jj + 1), npos[2] = __ldg(x01 + 3 * jj + 2);
-  };
-  if (cta_has_work) fetch_inputs(blockIdx.x);
-
-  for (int64_t tile = blockIdx.x; tile * bwd2::kRows < M; tile += gridDim.x, seen_tile = 1) {
-    const int64_t i = tile * bwd2::kRows + tid;  // row (indexes the incoming gradients)
-    const bool valid = i < M;
-    const int64_t j = nsample;                   // sample (indexes enc_in, x01, dirs)
-    if (seen_tile) mbar_wait(bar2, phase2), phase2 ^= 1;
-    const uint4* enc_row = reinterpret_cast<const uint4*>(enc_in + j * 32);
-    // ---------------- recompute the activations ----------------
-#pragma unroll
-    for (int cc = 0; cc < 4; ++cc) st_chunk(X, tid, cc, 32, nx[cc]);
-    stage_arrive();
-    // this row's position: needed only by the scatter at the end of the tile (row index skewed by
-    // row/16 so that the scatter's 16-rows-apart reads hit distinct banks)
-    {
-      float* pos = reinterpret_cast<float*>(smem + bwd2::kPos);
-      const int at = tid + (tid >> 4);
-      pos[at] = npos[0], pos[272 + at] = npos[1], pos[544 + at] = npos[2];
-    }
-    // incoming gradients of this row: needed at stages S0 / S3, requested now
-    float4 dc_in = make_float4(0.0f, 0.0f, 0.0f, 0.0f);
-    float ds_in = 0.0f;
-    if (valid) dc_in = __ldg(reinterpret_cast<const float4*>(dcolor_raw + 4 * i)), ds_in = __ldg(dsigma_raw + i);
-    const float* dptr = dirs + (size_t)((uint32_t)j / (uint32_t)N) * 3;  // the ray's direction (dir_mlp input)
-    const float dr[3] = {__ldg(dptr), __ldg(dptr + 1), __ldg(dptr + 2)};
-    mbar_wait(bar, phase), phase ^= 1;
-    tc_fence_after();
-    float v[32];
-    tmem_ld32(my32, v);
-    store_row32<true>(H, tid, v);
-    stage_arrive();
-    mbar_wait(bar, phase), phase ^= 1;
-    tc_fence_after();
-    {
-      float po[16];
-      tmem_ld16(my16, po);
-      dir_input_row(dr, po, v);
-    }
-    store_row32<false>(DIN, tid, v);
-    stage_arrive();
-    mbar_wait(bar, phase), phase ^= 1;
-    tc_fence_after();
-    tmem_ld32(my32, v);
-    store_row32<true>(H1, tid, v);
-    stage_arrive();
-    mbar_wait(bar, phase), phase ^= 1;
-    tc_fence_after();
-    tmem_ld32(my32, v);
-    store_row32<true>(H2, tid, v);
-    // ---------------- backward ----------------
-    {
-      float dout[16];
-#pragma unroll
-      for (int k = 0; k < 16; ++k) dout[k] = 0.0f;
-      dout[0] = dc_in.x * S, dout[1] = dc_in.y * S, dout[2] = dc_in.z * S, dout[3] = dc_in.w * S;
-      store_row16(DO, tid, dout);
-    }
-    stage_arrive();  // S0
-    mbar_wait(bar, phase), phase ^= 1;
-    tc_fence_after();
-    tmem_ld32(my32, v);
-    store_row32_masked(X, H2, tid, v);  // dL/dh2 -> X (layer 0 finished with the encoded features)
-    stage_arrive();  // S1
-    mbar_wait(bar, phase), phase ^= 1;  // covers dW(d3): DO and H2 are free
-    tc_fence_after();
-    tmem_ld32(my32, v);
-    store_row32_masked(H2, H1, tid, v);  // dL/dh1 -> H2
-    stage_arrive();  // S2
-    mbar_wait(bar, phase), phase ^= 1;  // covers dW(d2): X and H1 are free
-    tc_fence_after();
-    tmem_ld32(my32, v);
-    {
-      float dpo[16];
-      dpo[0] = ds_in * S;
-#pragma unroll
-      for (int k = 1; k < 16; ++k) dpo[k] = v[3 + k];
-      store_row16(DO, tid, dpo);  // dL/d(pos_mlp out) -> DO
-    }
-    stage_arrive();  // S3
-    mbar_wait(bar, phase), phase ^= 1;  // covers dW(d1): H2 and DIN are free
-    tc_fence_after();
-    tmem_ld32(my32, v);
-    store_row32_masked(H1, H, tid, v);  // dL/dh -> H1
-#pragma unroll
-    for (int cc = 0; cc < 4; ++cc) st_chunk(DIN, tid, cc, 32, enc_row[cc]);  // encoded features again -> DIN
-    stage_arrive();  // S4
-    mbar_wait(bar, phase), phase ^= 1;
-    tc_fence_after();
-    // ---- table-gradient scatter with run-length merging --------------------------------------
-    // dL/d(encoded features) of the whole tile is staged in shared memory (fp32, X..H are free
-    // now), then the work is re-mapped: thread (g, q) walks the 16 CONSECUTIVE samples
-    // 16g..16g+15 of level q. Consecutive samples of a ray mostly stay in the same grid cell,
-    // so their 8 corner contributions are merged in registers and written with one vector RED
-    // per corner per cell run instead of one per sample (the REDs were the kernel's bottleneck:
-    // ~1.3 cycles per lane-RED per SM).
-    tmem_ld32(my32, v);
-    tc_fence_before();
-    {
-      float* srow = reinterpret_cast<float*>(smem + bwd2::kX) + tid * 32;
-      const int swz = (tid ^ (tid >> 4)) & 7;
-#pragma unroll
-      for (int k = 0; k < 8; ++k)   // 16-byte chunks, XOR-swizzled by the row to spread banks
-        *reinterpret_cast<float4*>(srow + ((k ^ swz) << 2)) =
-            make_float4(v[4 * k] * invS, v[4 * k + 1] * invS, v[4 * k + 2] * invS, v[4 * k + 3] * invS);
-    }
-    epilogue_sync();
-    if ((tile + gridDim.x) * bwd2::kRows < M) fetch_inputs(tile + gridDim.x);
-    {
-      // a warp holds 2 levels x 16 sample groups: cell runs of one level end at similar rates,
-      // so coarse-level warps almost never execute the flush path
-      const int grp = tid & 15, lvl = tid >> 4;
-      const LevelRow L = lv[lvl];
-      float2* base = reinterpret_cast<float2*>(dtable) + L.offset;
-      const float* stage = reinterpret_cast<const float*>(smem + bwd2::kX);
-      const int64_t row0 = tile * bwd2::kRows + grp * 16;
-      // Most samples carry NO gradient (empty space: density <= 0 kills both dL/dsigma and the
-      // compositing weight), so the rows with a non-zero dL/d(features) are found first, with 16
-      // independent shared-memory reads in flight, and only those are walked.
-      const float* srow0 = stage + grp * 16 * 32 + ((lvl & 1) << 1);
-      uint32_t nz = 0;
-#pragma unroll
-      for (int r = 0; r < 16; ++r) {
-        const float2 d = *reinterpret_cast<const float2*>(srow0 + r * 32 + ((((lvl >> 1) ^ ((r ^ grp) & 7))) << 2));
-        nz |= (d.x != 0.0f || d.y != 0.0f) ? (1u << r) : 0u;
-      }
-      if (row0 + 16 > M) nz &= row0 < M ? (1u << (int)(M - row0)) - 1u : 0u;
-      if (!ATM_SCATTER_ON) nz = 0;
-      float acc[16];
-      uint32_t c_run[3] = {0xffffffffu, 0xffffffffu, 0xffffffffu};
-      bool open = false;
-#pragma unroll
-      for (int c = 0; c < 16; ++c) acc[c] = 0.0f;
-      // (Pairing the x / x+1 corners of a cell into one red.v4.f32 when their entries share an aligned
-      // 16-byte pair was measured: 34.5 vs 32.4 ms. The scatter is not what bounds this kernel: without
-      // any RED it runs 26.8 ms, profiles/README.md.)
-      auto flush = [&]() {  // entries are only needed here, once per run of samples in one cell
-        uint32_t e[8];
-        corner_entries3(L, c_run, e);
-#pragma unroll
-        for (int c = 0; c < 8; ++c) red_add_f32x2(reinterpret_cast<float*>(entry_ptr(base, e[c])), acc[2 * c], acc[2 * c + 1]);
-      };
-#pragma unroll 1
-      while (nz) {
-        const int r = __ffs(nz) - 1;
-        nz &= nz - 1u;
-        const int row = grp * 16 + r;
-        const float2 d = *reinterpret_cast<const float2*>(srow0 + r * 32 + ((((lvl >> 1) ^ ((r ^ grp) & 7))) << 2));
-        const float* pos = reinterpret_cast<const float*>(smem + bwd2::kPos) + row + (row >> 4);
-        const float p[3] = {pos[0], pos[272], pos[544]};
-        uint32_t cell[3];
-        float frac[3], w[8];
-        grid_cell<3>(p, L.scale, cell, frac);
-        corner_weights3(frac, w);
-        if (open && (cell[0] != c_run[0] || cell[1] != c_run[1] || cell[2] != c_run[2])) {
-          flush();
-#pragma unroll
-          for (int c = 0; c < 16; ++c) acc[c] = 0.0f;
-        }
-#pragma unroll
-        for (int c = 0; c < 8; ++c) {
-          acc[2 * c] = fmaf(w[c], d.x, acc[2 * c]);
-          acc[2 * c + 1] = fmaf(w[c], d.y, acc[2 * c + 1]);
-        }
-        c_run[0] = cell[0], c_run[1] = cell[1], c_run[2] = cell[2];
-        open = true;
-      }
-      if (open) flush();
-    }
-    epilogue_sync();  // the staging area is the next tile's X/H
-  }
-  }  // epilogue warps
-
-  // the last tile's weight-gradient MMAs: its bar2 completion has not been consumed by anybody
-  if (cta_has_work) {
-    const int64_t my_tiles = ((M + bwd2::kRows - 1) / bwd2::kRows - blockIdx.x + gridDim.x - 1) / gridDim.x;
-    mbar_wait(bar2, (uint32_t)((my_tiles - 1) & 1));
-  }
-  tc_fence_before();
-  __syncthreads();
-  tc_fence_after();
-  if (warp < 2 && cta_has_work) {
-    const int lane = tid & 31;
-    flush_dweight_t<32, 1>(tmem, bwd2::cDW1p, warp, lane, 32, invS, dpos_w);
-    flush_dweight_t<16, 2>(tmem, bwd2::cDW2p, warp, lane, 16, invS, dpos_w + 1024);
-    flush_dweight_t<32, 1>(tmem, bwd2::cDWd1, warp, lane, 32, invS, ddir_w);
-    flush_dweight_t<32, 2>(tmem, bwd2::cDWd2, warp, lane, 32, invS, ddir_w + 1024);
-    flush_dweight_t<16, 2>(tmem, bwd2::cDWd3, warp, lane, 16, invS, ddir_w + 2048);
-  }
-  tc_fence_before();
-  __syncthreads();
-  if (warp == 0) tmem_dealloc<bwd2::kTmemCols>(tmem);
-}
-
-
-// =========================================================================================
-// fused radiance field, backward, FOUR independent 128-row pipelines per CTA (one CTA per SM)
-// =========================================================================================
-// Same arithmetic and the same stage sequence as k_field_bwd_tc2. What changes is how many tiles an SM
-// has in flight. Measured (round 2, B200, 2^18 rays x 1024): the 256-row kernel spends 23.0 ms on the
-// recompute + input-gradient chain alone, +4 ms for the weight-gradient MMAs, +5.5 ms for the scatter,
-// while the MMAs it issues occupy the tensor pipe's issue path for ~14 ms: each of the 9 stages of a
-// tile is a round trip (operand tile -> barrier -> issue -> commit -> mbarrier -> tcgen05.ld) of
-// ~1400 cycles with ~100 cycles of work per warp in it, and two CTAs per SM are the only overlap.
-// Here ONE CTA per SM runs four tiles at once: 16 epilogue warps (pipeline p = warp / 4 owns sample
-// rows 128 p .. 128 p + 127 of a 512-row group, TMEM lanes = its rows, accumulator columns 32 p ..)
-// and one issuer warp that serves the pipelines in a fixed round-robin order, blocking on each
-// pipeline's named barrier in turn: while pipeline p runs its epilogue, the issuer and the tensor
-// pipe work for p+1, p+2, p+3. The weights are shared, and so are the weight-gradient accumulators
-// (the MMAs of all pipelines are issued by one thread and execute in order, so accumulating into one
-// TMEM region from four pipelines is an ordinary accumulate chain). With 512 TMEM columns per CTA
-// every layer's weight gradient concatenates two sample groups per MMA (20 instead of 28 MMAs/tile).
 namespace bwd4 {
 constexpr int kPipes = 4;
 constexpr int kRows = 128;                       // rows per pipeline
@@ -1434,7 +1053,18 @@ k_field_bwd_tc4(atmonr_grid_t g, const __half* __restrict__ pos_w, const __half*
       pipe_arrive(p);  // S4
       mbar_wait(my_done, phase), phase ^= 1;  // covers dW(2p): DO and H are free
       tc_fence_after();
-      // ---- table-gradient scatter with run-length merging (see k_field_bwd_tc2) ------------------
+      // ---- table-gradient scatter with run-length merging --------------------------------------
+      // dL/d(encoded features) of the tile is staged in shared memory (fp32, X and H are free now),
+      // then the work is re-mapped: thread (g, q) walks the 16 CONSECUTIVE samples 16g..16g+15 of
+      // level q. Consecutive samples of a ray mostly stay in the same grid cell, so their 8 corner
+      // contributions are merged in registers and written with one vector RED per corner per cell
+      // run instead of one per sample. Most samples carry NO gradient (density <= 0 kills both
+      // dL/dsigma and the compositing weight: 64 % of the rows on the benchmark, exactly zero in
+      // float32 as well, profiles/r3_backward_rows.json), so the rows with a non-zero gradient are
+      // found first (16 independent shared-memory reads) and only those are walked.
+      // (Pairing the x / x+1 corners of a cell into one red.v4.f32 when their entries share an aligned
+      // 16-byte pair was measured: +2 ms. The REDs are not what bounds the kernel: without any RED it
+      // is only 5.5 ms faster.)
       tmem_ld32(my32, v);
       tc_fence_before();
       {
@@ -1605,24 +1235,12 @@ int atmonr_ngp_field_bwd_tc(const atmonr_grid_t* g, const void* table, const atm
   if (M == 0) return 0;
   ATM_REQUIRE(M < ((int64_t)1 << 31), "atmonr_ngp_field_bwd_tc", "B*N must be below 2^31 per call (chunk the batch)");
   const bool use_wide = getenv("ATMONR_BWD_NARROW") == nullptr;  // read per call: tests toggle it
-  const char* pipes = getenv("ATMONR_BWD_PIPES");                // "2": the 256-row kernel, two CTAs per SM (cross-check)
-  if (enc && use_wide && !(pipes && pipes[0] == '2')) {
+  if (enc && use_wide) {
     cudaError_t e4 = cudaFuncSetAttribute(k_field_bwd_tc4<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, bwd4::kBytes);
     if (e4 != cudaSuccess) return fail("atmonr_ngp_field_bwd_tc", cudaGetErrorString(e4));
     const int64_t groups = (M + bwd4::kPipes * bwd4::kRows - 1) / (bwd4::kPipes * bwd4::kRows);
     const int grid4 = (int)(groups < (int64_t)tc_num_sms() ? groups : (int64_t)tc_num_sms());
     k_field_bwd_tc4<false><<<grid4, bwd4::kThreads, bwd4::kBytes, reinterpret_cast<cudaStream_t>(stream)>>>(
-        *g, (const __half*)pos_w, (const __half*)dir_w, x01, dirs, (const __half*)enc, dsigma_raw, dcolor_raw,
-        grad_absmax, M, N, dtable, dpos_w, ddir_w, nullptr, nullptr);
-    ATM_CHECK_LAUNCH("atmonr_ngp_field_bwd_tc");
-    return 0;
-  }
-  if (enc && use_wide) {
-    cudaError_t e2 = cudaFuncSetAttribute(k_field_bwd_tc2<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, bwd2::kBytes);
-    if (e2 != cudaSuccess) return fail("atmonr_ngp_field_bwd_tc", cudaGetErrorString(e2));
-    const int64_t tiles2 = (M + bwd2::kRows - 1) / bwd2::kRows;
-    const int grid2 = (int)(tiles2 < (int64_t)tc_num_sms() * 2 ? tiles2 : (int64_t)tc_num_sms() * 2);
-    k_field_bwd_tc2<false><<<grid2, bwd2::kThreads, bwd2::kBytes, reinterpret_cast<cudaStream_t>(stream)>>>(
         *g, (const __half*)pos_w, (const __half*)dir_w, x01, dirs, (const __half*)enc, dsigma_raw, dcolor_raw,
         grad_absmax, M, N, dtable, dpos_w, ddir_w, nullptr, nullptr);
     ATM_CHECK_LAUNCH("atmonr_ngp_field_bwd_tc");
@@ -1652,23 +1270,11 @@ int atmonr_ngp_field_bwd_tc_compact(const atmonr_grid_t* g, const atmonr_mlp_t* 
   if (M == 0) return 0;
   ATM_REQUIRE(M < ((int64_t)1 << 31), "atmonr_ngp_field_bwd_tc_compact", "B*N must be below 2^31 per call (chunk the batch)");
   ATM_REQUIRE(enc && active_idx && n_active && dsigma_c && dcolor_c, "atmonr_ngp_field_bwd_tc_compact", "null argument");
-  const char* pipes = getenv("ATMONR_BWD_PIPES");
-  if (!(pipes && pipes[0] == '2')) {
-    cudaError_t e4 = cudaFuncSetAttribute(k_field_bwd_tc4<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, bwd4::kBytes);
-    if (e4 != cudaSuccess) return fail("atmonr_ngp_field_bwd_tc_compact", cudaGetErrorString(e4));
-    const int64_t groups = (M + bwd4::kPipes * bwd4::kRows - 1) / (bwd4::kPipes * bwd4::kRows);  // upper bound
-    const int grid4 = (int)(groups < (int64_t)tc_num_sms() ? groups : (int64_t)tc_num_sms());
-    k_field_bwd_tc4<true><<<grid4, bwd4::kThreads, bwd4::kBytes, reinterpret_cast<cudaStream_t>(stream)>>>(
-        *g, (const __half*)pos_w, (const __half*)dir_w, x01, dirs, (const __half*)enc, dsigma_c, dcolor_c, grad_absmax, M,
-        N, dtable, dpos_w, ddir_w, active_idx, n_active);
-    ATM_CHECK_LAUNCH("atmonr_ngp_field_bwd_tc_compact");
-    return 0;
-  }
-  cudaError_t e2 = cudaFuncSetAttribute(k_field_bwd_tc2<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, bwd2::kBytes);
-  if (e2 != cudaSuccess) return fail("atmonr_ngp_field_bwd_tc_compact", cudaGetErrorString(e2));
-  const int64_t tiles2 = (M + bwd2::kRows - 1) / bwd2::kRows;  // upper bound: the list length is only known on the device
-  const int grid2 = (int)(tiles2 < (int64_t)tc_num_sms() * 2 ? tiles2 : (int64_t)tc_num_sms() * 2);
-  k_field_bwd_tc2<true><<<grid2, bwd2::kThreads, bwd2::kBytes, reinterpret_cast<cudaStream_t>(stream)>>>(
+  cudaError_t e4 = cudaFuncSetAttribute(k_field_bwd_tc4<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, bwd4::kBytes);
+  if (e4 != cudaSuccess) return fail("atmonr_ngp_field_bwd_tc_compact", cudaGetErrorString(e4));
+  const int64_t groups = (M + bwd4::kPipes * bwd4::kRows - 1) / (bwd4::kPipes * bwd4::kRows);  // upper bound
+  const int grid4 = (int)(groups < (int64_t)tc_num_sms() ? groups : (int64_t)tc_num_sms());
+  k_field_bwd_tc4<true><<<grid4, bwd4::kThreads, bwd4::kBytes, reinterpret_cast<cudaStream_t>(stream)>>>(
       *g, (const __half*)pos_w, (const __half*)dir_w, x01, dirs, (const __half*)enc, dsigma_c, dcolor_c, grad_absmax, M,
       N, dtable, dpos_w, ddir_w, active_idx, n_active);
   ATM_CHECK_LAUNCH("atmonr_ngp_field_bwd_tc_compact");
