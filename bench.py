@@ -8,7 +8,9 @@
 
 Prints ONE JSON line (rank 0). `value` = device-resident inputs; `e2e` = the same step through
 the pipeline API with pinned-host batches (H2D of the batch + D2H of the loss inside the timed
-region). Scaling is weak: every rank processes `--rays` rays per step.
+region). Scaling is weak: every rank processes `--rays` rays per step; for N > 1 the line also carries
+`strong_scaling` (the SAME global batches of `--rays` and of 8192 rays split over the N ranks).
+The loss of every timed step is checked to be finite and identical on all ranks' reductions.
 """
 
 from __future__ import annotations
@@ -44,7 +46,7 @@ def parse():
     ap.add_argument("--impl", default="native", choices=["native", "reference"])
     ap.add_argument("--rays", type=int, default=1 << 18, help="rays per step per GPU")
     ap.add_argument("--samples", type=int, default=1024)
-    ap.add_argument("--granule", default="synthetic:H=256,W=256,seed=0")
+    ap.add_argument("--granule", default="synthetic:H=512,W=512,seed=0", help="SURVEY 8d bench granule: 512 x 512 pixels x 90 views")
     ap.add_argument("--cpu-rays", type=int, default=256, help="rays per step of the CPU baseline sample")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--compact-backward", action="store_true",
@@ -184,32 +186,73 @@ def gpu_nerf_rate(dataset, dev, rays: int = 4096, steps: int = 5) -> dict:
     from atmonr.batch_loader import BatchLoader
     from atmonr.pipelines.factory import get_pipeline
 
+    from atmonr import distributed as dist
+    world, rank = dist.world_size(), dist.rank()
     cfg = nerf_config()
+    torch.manual_seed(0)
     pipe = get_pipeline(cfg["pipeline"], dataset)
     pipe.send_tensors_to(dev.index)
+    dist.broadcast_parameters(pipe.parameters())
     opt = pipe.get_optimizer(cfg["trainer"]["optimizer"])
-    batch = next(iter(BatchLoader(dataset, batch_size=rays, shuffle=True, seed=7)))
+    # weak scaling (BASELINE.json configs[4]: NeRF on 8 GPUs): `rays` rays per GPU, each rank its own rays,
+    # gradients of the two MLPs (1.2 M parameters) all-reduced over NCCL
+    batch = next(iter(BatchLoader(dataset, batch_size=rays, shuffle=True, seed=7 + rank)))
+    last = []
 
     def step():
         loss = pipe.compute_loss(batch, pipe.forward(batch))
         opt.zero_grad()
         loss.backward()
+        dist.all_reduce_gradients(opt)
         opt.step()
+        last[:] = [loss.detach()]
+
+    def sync():
+        torch.cuda.synchronize()
+        if world > 1:
+            torch.distributed.barrier()
+            torch.cuda.synchronize()
 
     for _ in range(3):
         step()
-    torch.cuda.synchronize()
+    sync()
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     e0.record()
     for _ in range(steps):
         step()
     e1.record()
-    torch.cuda.synchronize()
-    ms = e0.elapsed_time(e1) / steps
-    return {"value": rays * 1e3 / ms, "unit": UNIT, "rays_per_step": rays, "ms_per_step": ms,
+    sync()
+    t = torch.tensor([e0.elapsed_time(e1) / steps], device=dev)
+    if world > 1:
+        torch.distributed.all_reduce(t, op=torch.distributed.ReduceOp.MAX)
+    ms = float(t)
+    assert bool(torch.isfinite(last[0])), "NeRF step produced a non-finite loss"
+    peaks = _load_json("MEASURED_PEAKS.json")
+    tpeak = float(peaks.get("bf16_tflops_sustained", 1400.0))
+    flop32 = 922e6 * rays                      # 922 MFLOP per ray, forward + backward, float32-equivalent
+    products = 6 if _nerf_dense_impl() == "tc" else 1
+    tf = flop32 * products / (ms * 1e-3) / 1e12    # per GPU
+    c = _load_json("profiles", "ncu_counters.json")
+    roof = {"bound": "tensor", "achieved": tf, "peak": tpeak, "unit": "TFLOP/s", "frac": tf / tpeak,
+            "float32_equivalent_TFLOPs": flop32 / (ms * 1e-3) / 1e12, "tensor_products_per_float32_product": products,
+            "peak_source": "MEASURED_PEAKS.json bf16_tflops_sustained" if peaks else "fallback 1400 TFLOP/s",
+            "tensor_pipe_pct_ncu": {k: c[k].get("tensor_pipe_pct") for k in ("atmonr_linear_fwd_tc", "atmonr_linear_dw_tc") if k in c},
+            "traffic": None,
+            "note": "whole NeRF step (MLP + sampling + compositing + Adam) against the dense bf16 tensor peak: each float32 "
+                    "product is six bf16 tensor-core products (three-term split of both operands), counted as executed"}
+    return {"value": world * rays * 1e3 / ms, "unit": UNIT, "rays_per_step_per_gpu": rays, "n_gpus": world, "ms_per_step": ms,
+            "roofline": roof,
             "note": "configs/nerf.json, coarse 64 + fine 192 samples, hidden 256; MLP layers are "
                     + ("tcgen05 bf16x3-split products (csrc/linear_tc.cu)" if _nerf_dense_impl() == "tc"
                        else "cuBLAS fp32 GEMMs (cross-check)")}
+
+
+def _load_json(*parts) -> dict:
+    path = os.path.join(ROOT, *parts)
+    try:
+        return json.load(open(path))
+    except (OSError, ValueError):
+        return {}
 
 
 def _nerf_dense_impl() -> str:
@@ -280,6 +323,8 @@ def run_native(args) -> None:
     if args.compact_backward:
         _fused.COMPACT_BWD = True
 
+    losses = []   # device scalars of the timed steps (read back after the timed region)
+
     def step(batch, upcoming=None):
         # the NEXT batch is announced first: its sample points are computed on a side stream
         # underneath this step's backward (InstantNGPPipeline.prefetch); one sampler launch per step
@@ -291,7 +336,22 @@ def run_native(args) -> None:
         loss.backward()
         dist.all_reduce_gradients(opt)
         opt.step()
+        losses.append(loss.detach())
         return loss
+
+    def check_losses(what):
+        """Every timed step produced a finite loss; the parameters stay identical on all ranks (same
+        summed gradients, same update): the checksum of the MLP weights is compared across ranks."""
+        vals = torch.stack(losses).float()
+        losses.clear()
+        assert bool(torch.isfinite(vals).all()), f"{what}: non-finite loss {vals.tolist()}"
+        if world > 1:
+            chk = torch.stack([p.detach().double().sum() for p in (pipe.pos_mlp.params, pipe.dir_mlp.params, pipe.surf_mlp.params)])
+            lo, hi = chk.clone(), chk.clone()
+            torch.distributed.all_reduce(lo, op=torch.distributed.ReduceOp.MIN)
+            torch.distributed.all_reduce(hi, op=torch.distributed.ReduceOp.MAX)
+            assert torch.equal(lo, hi), f"{what}: parameters differ between ranks"
+        return [float(v) for v in vals]
 
     def barrier():
         torch.cuda.synchronize()
@@ -326,7 +386,9 @@ def run_native(args) -> None:
     profile_range = os.environ.get("ATMONR_CUDA_PROFILER_RANGE") == "1"  # ncu --profile-from-start off
     if profile_range:
         torch.cuda.profiler.start()
+    losses.clear()
     ms_total = timed(K, lambda i: step(batches[i % nb], batches[(i + 1) % nb]))
+    step_losses = check_losses("device-resident run")
     if profile_range:
         torch.cuda.profiler.stop()
     launches = L.STATS.launches
@@ -360,23 +422,68 @@ def run_native(args) -> None:
         "atmonr_adamw_step": 30 * N_PARAMS, "atmonr_ngp_sample_points": 16 * M + 28 * B,
         "atmonr_composite_fwd": 24 * M, "atmonr_composite_bwd": 44 * M,
     }
-    traffic_file = os.path.join(ROOT, "profiles", "ncu_dram_traffic.json")
-    traffic = json.load(open(traffic_file)) if os.path.exists(traffic_file) else {}
     peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json"))) if os.path.exists(os.path.join(ROOT, "MEASURED_PEAKS.json")) else {}
     hbm_peak = float(peaks.get("hbm_gbs", 6650.0))
-    n_top = max(1, calls.get(top, 1) // min(K, 3))
-    achieved = alg_bytes.get(top, 0) / (per_step[top] / n_top * 1e-3) / 1e9 if top in alg_bytes else None
+    tensor_peak = float(peaks.get("bf16_tflops_sustained", 1400.0))
+    peak_src = "MEASURED_PEAKS.json" if peaks else "fallback 6650 GB/s / 1400 TFLOP/s (B200_PROFILING.md)"
+    counters = _load_json("profiles", "ncu_counters.json")       # per launch, one ncu --set full capture (summarise_ncu.py)
+    l2u = _load_json("profiles", "r3_l2_ubench.json").get("patterns", {})   # measured L2 gather / RED peaks (profiles/ubench)
+    l2_read_peak = l2u.get("gather4", {}).get("sector_GBps")     # 32-byte sectors/s x 32 B, independent random gathers
+    l2_red_peak = l2u.get("red8", {}).get("sector_GBps")         # RED sector requests/s x 32 B
+    n_per = {k: max(1, calls.get(k, 1) // min(K, 3)) for k in per_step}
+
+    def kernel_detail(k):
+        """Three views of one kernel from the SAME run's CUDA-event time: algorithmic bytes vs the HBM copy
+        peak (the contract's recipe), executed L2 sectors vs the measured L2 gather / RED peaks, DRAM bytes
+        vs the HBM peak; the sector / byte counts and the tensor-pipe share come from the committed ncu capture
+        of the same kernel at the same ray count (counts do not depend on the clock; durations are live)."""
+        sec = per_step[k] / n_per[k] * 1e-3
+        d = {"ms": round(per_step[k] / n_per[k], 3)}
+        if k in alg_bytes:
+            d["algorithmic_GBps"] = round(alg_bytes[k] / sec / 1e9, 1)
+            d["algorithmic_frac_of_hbm_peak"] = round(alg_bytes[k] / sec / 1e9 / hbm_peak, 3)
+        c = counters.get(k)
+        if c and c.get("workload_rays") == B:
+            rd, red = c.get("l2_sectors_read") or 0, c.get("l2_sectors_red") or 0
+            d["executed_l2_read_GBps"] = round(rd * 32 / sec / 1e9, 1)
+            d["executed_l2_red_GBps"] = round(red * 32 / sec / 1e9, 1)
+            if l2_read_peak:
+                d["l2_read_frac_of_measured_gather_peak"] = round(rd * 32 / sec / 1e9 / l2_read_peak, 3)
+            if l2_red_peak and red:
+                d["l2_red_frac_of_measured_red_peak"] = round(red * 32 / sec / 1e9 / l2_red_peak, 3)
+            d["dram_GBps"] = round(c["dram_bytes"] / sec / 1e9, 1)
+            d["dram_frac_of_hbm_peak"] = round(c["dram_bytes"] / sec / 1e9 / hbm_peak, 3)
+            d["dram_bytes_per_launch"] = c["dram_bytes"]
+            d["tensor_pipe_pct_ncu"] = c.get("tensor_pipe_pct")
+            d["issue_active_pct_ncu"] = c.get("issue_active_pct")
+            d["top_stalls_ncu"] = c.get("top_stalls")
+            d["counters_from"] = c.get("source")
+        return d
+
+    detail = {k: kernel_detail(k) for k in sorted(per_step, key=per_step.get, reverse=True)[:6]}
+    top_d = detail[top]
+    achieved = top_d.get("algorithmic_GBps")
+    # what binds the dominant kernel according to its ncu capture (not according to the formula below)
+    if top_d.get("dram_frac_of_hbm_peak", 0) > 0.6:
+        bound = "hbm"
+    elif (top_d.get("tensor_pipe_pct_ncu") or 0) > 50:
+        bound = "tensor"
+    else:
+        bound = "latency"
     roofline = {
-        "kernel": top, "bound": "hbm", "achieved": achieved, "peak": hbm_peak, "unit": "GB/s",
+        "kernel": top, "bound": bound, "achieved": achieved, "peak": hbm_peak, "unit": "GB/s",
         "frac": (achieved / hbm_peak) if achieved else None,
-        "traffic": traffic.get(top, {}).get("dram_bytes_per_launch") if traffic.get("rays") == B else None,
+        "traffic": top_d.get("dram_bytes_per_launch"),
         "algorithmic_bytes_per_launch": alg_bytes.get(top),
-        "peak_source": "MEASURED_PEAKS.json hbm_gbs" if peaks else "fallback 6650 GB/s (B200_PROFILING.md)",
-        "note": "algorithmic bytes = table gathers / gradient scatters per SURVEY 8d (each 2-feature RED counted as "
-                "4 B like the reference's half2 atomics); this traffic is served by L2 (the table and most of its "
-                "gradient are L2-resident), so frac is table traffic quoted against the HBM copy peak",
-        "achieved_gbs_by_kernel": {k: round(alg_bytes[k] / (per_step[k] / max(1, calls.get(k, 1) // min(K, 3)) * 1e-3) / 1e9, 1)
-                                   for k in per_step if k in alg_bytes},
+        "peak_source": peak_src,
+        "note": "achieved / frac follow the contract's recipe: ALGORITHMIC table bytes (SURVEY 8d: 512 B gathered or scattered per "
+                "sample, each 2-feature RED counted as 4 B like the reference's half2 atomics) / live CUDA-event time / "
+                "measured HBM copy peak. The table traffic is served by L1/L2, and the kernel executes fewer bytes than "
+                "that (zero rows are skipped, cell runs merged): `by_kernel` gives the executed L2 sector rate against the "
+                "MEASURED L2 gather / RED peaks (profiles/r3_l2_ubench.json), DRAM bytes against the HBM peak and the ncu "
+                "tensor-pipe share. `bound` is what the ncu capture says: 'latency' = neither memory system nor tensor "
+                "pipe above 60 % / 50 %; the kernel waits on tcgen05 round trips (top stall reasons listed).",
+        "by_kernel": detail,
         "ms_per_step_by_kernel": {k: round(v, 3) for k, v in sorted(per_step.items(), key=lambda kv: -kv[1])},
     }
 
@@ -399,10 +506,37 @@ def run_native(args) -> None:
     staged[0] = h2d(0)
     if prefetch:
         pipe.prefetch(staged[0])
+    losses.clear()
     ms_e2e = timed(K, e2e_step) / K
+    check_losses("end-to-end run")
     staged.clear()
     e2e = {"value": world * B * 1e3 / ms_e2e, "unit": UNIT, "h2d_bytes_per_step": h2d_bytes, "d2h_bytes_per_step": 4,
            "ms_per_step": ms_e2e}
+
+    # ---- strong scaling (N > 1): the SAME global batch split over the ranks --------------------------
+    # The weak-scaling `value` above keeps 2^18 rays per GPU, where the gradient all-reduce (191 MB fp32)
+    # is ~1 % of the step. Here the global batch is fixed: `--rays` rays (and the shipped 8192 rays of
+    # configs/instant_ngp.json) per step over all ranks, so the per-GPU compute shrinks with N while the
+    # all-reduce and the dense AdamW do not. Efficiency is for the driver / reader to compute from the
+    # N = 1 line's ms_per_step (the same global batch on one GPU is the N = 1 `value` itself).
+    strong = None
+    if world > 1:
+        strong = {}
+        for label, glob in (("global_rays_2^18", B), ("global_rays_8192", 8192)):
+            per = glob // world
+            if per < 1:
+                continue
+            shard = [{k: v[:per].contiguous() for k, v in b.items()} for b in batches]
+            for i in range(3):
+                step(shard[i % nb], shard[(i + 1) % nb])
+            losses.clear()
+            n_s = K if glob == B else 10 * K
+            ms_s = timed(n_s, lambda i: step(shard[i % nb], shard[(i + 1) % nb])) / n_s
+            check_losses(f"strong scaling {label}")
+            strong[label] = {"global_rays": per * world, "rays_per_gpu": per, "ms_per_step": ms_s,
+                             "value": per * world * 1e3 / ms_s, "unit": UNIT}
+        strong["note"] = ("same global batch over all ranks; gradients all-reduced (sum) over NCCL and averaged in the "
+                          "fused AdamW; compare ms_per_step with the N = 1 run at the same global batch")
 
     # ---- extraction: voxel queries/s (BASELINE.json metric, second half), inputs resident in HBM ----
     # SURVEY 8d workload: a dense grid of voxel columns over the granule x 81 altitudes (0..20 km, step
@@ -426,16 +560,28 @@ def run_native(args) -> None:
             pipe.extract(vox)
         ms_ext = timed(5, lambda i: pipe.extract(vox)) / 5
     pipe.train()
+    # SURVEY 8d per voxel: 512 B gathered + 24 B in (float64 xyz) + 4 B out; 1536 MAC on the tensor cores
+    ext_c = counters.get("atmonr_extract_sigma_tc", {})
+    ext_gbs = 540.0 * n_vox / (ms_ext * 1e-3) / 1e9
     extract = {"value": world * n_vox * 1e3 / ms_ext, "unit": "voxels/s", "voxels_per_call_per_gpu": n_vox,
                "ms_per_call": ms_ext,
-               "workload": f"voxel grid, {per_call} columns x {n_alt} altitudes per call, float64 points (scripts/extract.py voxelgrid mode)"}
+               "workload": f"voxel grid, {per_call} columns x {n_alt} altitudes per call, float64 points (scripts/extract.py voxelgrid mode)",
+               "roofline": {"kernel": "atmonr_extract_sigma_tc", "bound": "latency", "achieved": ext_gbs, "peak": hbm_peak,
+                            "unit": "GB/s", "frac": ext_gbs / hbm_peak, "algorithmic_bytes_per_voxel": 540,
+                            "traffic": ext_c.get("dram_bytes") if ext_c.get("workload_voxels") == n_vox else None,
+                            "executed_l2_read_frac_of_measured_gather_peak":
+                                (round(ext_c["l2_sectors_read"] * 32 / (ms_ext * 1e-3) / 1e9 / l2_read_peak, 3)
+                                 if ext_c.get("l2_sectors_read") and l2_read_peak and ext_c.get("workload_voxels") == n_vox else None),
+                            "tensor_pipe_pct_ncu": ext_c.get("tensor_pipe_pct"), "issue_active_pct_ncu": ext_c.get("issue_active_pct"),
+                            "note": "algorithmic table bytes (L1/L2-served) against the HBM copy peak, as for the training kernels; "
+                                    "the float64 geodesy in front (FP64 pipe) and the gathers' issue slots bound it"}}
 
+    nerf = gpu_nerf_rate(dataset, dev)          # every rank (data-parallel NeRF line at N > 1)
     if rank != 0:
         return
-    # the NeRF line and the CPU baselines belong to the N = 1 run (rank 0 would otherwise keep the
-    # other ranks' GPUs idle for ~20 s of host work in every run of the scaling sweep)
+    # the CPU baselines belong to the N = 1 run (rank 0 would otherwise keep the other ranks' GPUs idle
+    # for ~20 s of host work in every run of the scaling sweep)
     solo = world == 1
-    nerf = gpu_nerf_rate(dataset, dev) if solo else None
     cpu = cpu_step_rate(args.samples, args.cpu_rays, 2, 1) if solo and not args.no_cpu_baseline else None
     cpu_nerf = cpu_nerf_rate() if solo and not args.no_cpu_baseline else None
     line = {
@@ -450,7 +596,9 @@ def run_native(args) -> None:
                          if _fused.COMPACT_BWD else "dense (every sample)"),
             "l2": "inputs larger than L2: per-step working set (x01, sigma, colour, gradients) is several GB",
         },
+        "loss_first_last": [step_losses[0], step_losses[-1]],
         "clocks": clock_info, "e2e": e2e, "gpu_launches": launches, "roofline": roofline, "extract": extract,
+        "strong_scaling": strong,
         "cpu_baseline": {k: cpu[k] for k in ("value", "unit", "cores", "kind", "sample")} if cpu else None,
         "nerf": nerf, "cpu_baseline_nerf": cpu_nerf,
     }
