@@ -65,7 +65,7 @@ def full_summary(rep: str, tag: str, cmd: str, rays: int, write_traffic: bool = 
     head, units, data = rows[0], rows[1], rows[2:]
     ki = head.index("Kernel Name")
     stall_cols = [i for i, c in enumerate(head) if c.startswith("smsp__pcsamp_warps_issue_stalled") and "not_issued" not in c]
-    out = [f"# ncu --set full, {tag}, bench.py default configuration", "", f"`{cmd}`", "",
+    out = [f"# ncu --set full, {tag}", "", f"`{cmd}`", "",
            "Durations under ncu are serialised, cache-flushed replays (longer than the live CUDA-event times of "
            "the bench line); counters are per launch. `stalls` = warp-state sampling split (pc sampling).", ""]
     traffic = {"rays": rays, "source": f"profiles/{tag}_ncu_full_summary.md (ncu --set full, dram__bytes_read.sum + "
@@ -100,6 +100,7 @@ def full_summary(rep: str, tag: str, cmd: str, rays: int, write_traffic: bool = 
             # LIVE CUDA-event duration of the same kernel (the ncu duration is a serialised cold-cache replay)
             counters[ent] = {
                 "source": f"profiles/{tag}_ncu_full_summary.md", "workload_rays": rays,
+                "workload_voxels": 32768 * 81 if ent.startswith("atmonr_extract") else None,
                 "ncu_duration_ms": num("gpu__time_duration.sum") * dur_unit,
                 "dram_bytes": traffic[ent]["dram_bytes_per_launch"],
                 "l2_sectors_read": num("lts__t_sectors_srcunit_tex_op_read.sum"),
