@@ -37,7 +37,7 @@ METRICS = [
 ENTRY = {
     "k_ngp_sample_points": "atmonr_ngp_sample_points", "k_field_fwd_tc": "atmonr_ngp_field_fwd_tc",
     "k_composite_fwd": "atmonr_composite_fwd", "k_composite_bwd": "atmonr_composite_bwd",
-    "k_field_bwd_tc2": "atmonr_ngp_field_bwd_tc", "k_extract_sigma_tc": "atmonr_extract_sigma_tc",
+    "k_field_bwd_tc4": "atmonr_ngp_field_bwd_tc", "k_field_bwd_tc2": "atmonr_ngp_field_bwd_tc", "k_extract_sigma_tc": "atmonr_extract_sigma_tc",
     "k_adamw": "atmonr_adamw_step", "k_dense_tc": "atmonr_dense_fwd_tc", "k_dense_dw_tc": "atmonr_dense_dw_tc",
     "k_linear_tc": "atmonr_linear_fwd_tc", "k_linear_dw_tc": "atmonr_linear_dw_tc",
 }
@@ -54,7 +54,7 @@ def entry_of(kernel: str) -> str | None:
             # the last template argument of k_field_bwd_tc2<COMPACT> / k_composite_bwd<K, V, COMPACT>
             args = kernel[kernel.index("<") + 1:kernel.rindex(">")].split(",") if "<" in kernel else []
             compact = bool(args) and args[-1].strip() in ("1", "true") and (
-                (k == "k_field_bwd_tc2") or (k == "k_composite_bwd" and len(args) == 3))
+                (k in ("k_field_bwd_tc2", "k_field_bwd_tc4")) or (k == "k_composite_bwd" and len(args) == 3))
             return v + ("_compact" if compact else "")
     return None
 
