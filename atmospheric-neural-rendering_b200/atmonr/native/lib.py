@@ -74,6 +74,7 @@ SIGNATURES = {
     "atmonr_composite_fwd": [P, P, P, P, F32, I64, I32, I32, I32, I32, P, P, P, P, P, P, P],
     "atmonr_composite_bwd": [P, P, P, P, P, P, P, P, F32, I64, I32, I32, I32, I32, P, P, P, P, P, P],
     "atmonr_composite_bwd_compact": [P, P, P, P, P, P, P, P, F32, I64, I32, I32, I32, I32, P, P, P, P, P, P, P],
+    "atmonr_composite_bwd_weights": [P, P, P, P, P, P, P, P, P, P, F32, I64, I32, I32, I32, I32, P, P, P, P, P],
     "atmonr_band_loss": [P, P, P, F32, I32, I64, I32, F32, P, P, P, P],
     "atmonr_adamw_step": [P, P, P, P, P, I64, F64, F64, F64, F64, F64, I64, F64, I32, P],
     "atmonr_extract_sigma": [FP, GP, P, MP, P, P, I64, F32, P, P],
@@ -81,6 +82,12 @@ SIGNATURES = {
     "atmonr_positional_encoding": [P, I64, I32, C.POINTER(C.c_int32), I32, P, P],
     "atmonr_positional_encoding_f64": [P, I64, I32, C.POINTER(C.c_int32), I32, P, P],
     "atmonr_sample_pdf": [P, P, P, I64, I32, I32, P, P, P],
+    "atmonr_sample_pdf_train": [P, P, P, I64, I32, I32, P, P, P, P, P],
+    "atmonr_sample_pdf_bwd": [P, P, P, P, P, P, P, I64, I32, I32, P, P, P],
+    "atmonr_nerf_encode": [FP, P, P, P, I64, I32, C.POINTER(C.c_int32), I32, P, I32, P, P],
+    "atmonr_nerf_encode_bwd": [FP, P, P, P, P, P, I32, I64, I32, C.POINTER(C.c_int32), P, P],
+    "atmonr_composite_dz": [P, I64, I32, F32, P, P],
+    "atmonr_append_heights": [P, I64, F64, C.POINTER(C.c_double), F64, P, P],
     "atmonr_tc_probe": [P, P, I32, P, P],
     "atmonr_linear_prep": [P, I32, I32, I32, P, P],
     "atmonr_linear_fwd_tc": [P, I64, P, I64, I32, P, I64, P, P, I64, I32, I32, I32, P, I64, P],

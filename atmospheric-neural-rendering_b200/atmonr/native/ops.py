@@ -330,26 +330,28 @@ def composite_forward(z, color, sigma, color_surf, z_scale, relu, want_weights=T
 
 
 def composite_backward(z, color, sigma, color_surf, catmo, tsurf, d_atmo, d_surf, z_scale, relu, want_dz=False,
-                       grad_absmax=None):
+                       grad_absmax=None, weights=None, d_weights=None):
+    """atmonr_composite_bwd; with `d_weights` (dL/d of the per-sample weights the forward returned, NeRF
+    coarse pass) atmonr_composite_bwd_weights. want_dz: also dL/dz (atmonr_composite_dz)."""
     b, n = z.shape
     k, v = color.shape[-1], sigma.shape[-1]
     dcolor = torch.empty_like(color)
     dsigma = torch.empty_like(sigma)
     dcs = torch.empty_like(color_surf) if color_surf is not None else None
     ddelta = torch.empty_like(z) if want_dz else None
-    L.call("atmonr_composite_bwd", L.ptr(z), L.ptr(color), L.ptr(sigma), L.ptr(color_surf), L.ptr(catmo), L.ptr(tsurf),
-           L.ptr(d_atmo), L.ptr(d_surf), float(z_scale), b, n, k, v, int(relu), L.ptr(dcolor), L.ptr(dsigma),
-           L.ptr(dcs), L.ptr(ddelta), L.ptr(grad_absmax), L.stream())
+    if d_weights is not None:
+        L.call("atmonr_composite_bwd_weights", L.ptr(z), L.ptr(color), L.ptr(sigma), L.ptr(color_surf), L.ptr(catmo),
+               L.ptr(tsurf), L.ptr(weights), L.ptr(d_atmo), L.ptr(d_surf), L.ptr(d_weights), float(z_scale), b, n, k, v,
+               int(relu), L.ptr(dcolor), L.ptr(dsigma), L.ptr(dcs), L.ptr(ddelta), L.stream())
+    else:
+        L.call("atmonr_composite_bwd", L.ptr(z), L.ptr(color), L.ptr(sigma), L.ptr(color_surf), L.ptr(catmo),
+               L.ptr(tsurf), L.ptr(d_atmo), L.ptr(d_surf), float(z_scale), b, n, k, v, int(relu), L.ptr(dcolor),
+               L.ptr(dsigma), L.ptr(dcs), L.ptr(ddelta), L.ptr(grad_absmax), L.stream())
     if not want_dz:
         return dcolor, dsigma, dcs
-    # delta_i = hi_i - lo_i with hi_i = (z_i+z_{i+1})/2 (last: z_{N-1}), lo_i = (z_{i-1}+z_i)/2 (first: 0)
-    dz = torch.zeros_like(z)
-    dz[:, :-1] += 0.5 * ddelta[:, :-1]
-    dz[:, 1:] += 0.5 * ddelta[:, :-1]
-    dz[:, -1] += ddelta[:, -1]
-    dz[:, :-1] -= 0.5 * ddelta[:, 1:]
-    dz[:, 1:] -= 0.5 * ddelta[:, 1:]
-    return dcolor, dsigma, dcs, dz * z_scale
+    dz = torch.empty_like(z)
+    L.call("atmonr_composite_dz", L.ptr(ddelta), b, n, float(z_scale), L.ptr(dz), L.stream())
+    return dcolor, dsigma, dcs, dz
 
 
 def composite_backward_compact(z, color, sigma, color_surf, catmo, tsurf, d_atmo, d_surf, z_scale, relu,
@@ -373,28 +375,29 @@ def composite_backward_compact(z, color, sigma, color_surf, catmo, tsurf, d_atmo
 
 class CompositeFn(torch.autograd.Function):
     """graphics_utils.py render / render_with_surface, differentiable w.r.t. colour, density,
-    surface colour and (NeRF fine pass) the sample distances z."""
+    surface colour, the sample distances z (NeRF fine pass) and THROUGH the returned per-sample weights
+    (NeRF coarse pass: they define the fine sampler's CDF, samplers.py:72-74)."""
 
     @staticmethod
     def forward(ctx, z, color, sigma, color_surf, z_scale, relu):
         z, color, sigma = _c(z, _f32), _c(color, _f32), _c(sigma, _f32)
         cs = _c(color_surf, _f32) if color_surf is not None else None
         cmap, catmo, csurf, tsurf, weights, alpha = composite_forward(z, color, sigma, cs, z_scale, relu)
-        ctx.save_for_backward(z, color, sigma, cs, catmo, tsurf)
+        ctx.save_for_backward(z, color, sigma, cs, catmo, tsurf, weights)
         ctx.z_scale, ctx.relu = z_scale, relu
-        ctx.want_dz = z.requires_grad
-        ctx.mark_non_differentiable(weights, alpha)
+        ctx.mark_non_differentiable(alpha)
         return cmap, catmo, csurf, weights, alpha
 
     @staticmethod
-    def backward(ctx, g_map, g_atmo, g_surf, _gw, _ga):
-        z, color, sigma, cs, catmo, tsurf = ctx.saved_tensors
+    def backward(ctx, g_map, g_atmo, g_surf, g_w, _ga):
+        z, color, sigma, cs, catmo, tsurf, weights = ctx.saved_tensors
         zero = torch.zeros_like(catmo)
         g_map = zero if g_map is None else g_map
         d_atmo = _c(g_map + (g_atmo if g_atmo is not None else 0), _f32)
         d_surf = _c(g_map + (g_surf if g_surf is not None else 0), _f32)
         out = composite_backward(z, color, sigma, cs, catmo, tsurf, d_atmo, d_surf, ctx.z_scale, ctx.relu,
-                                 want_dz=ctx.needs_input_grad[0])
+                                 want_dz=ctx.needs_input_grad[0], weights=weights,
+                                 d_weights=_c(g_w, _f32) if g_w is not None else None)
         dz = out[3] if ctx.needs_input_grad[0] else None
         return dz, out[0], out[1], out[2], None, None
 
@@ -465,3 +468,82 @@ def sample_pdf_z(weights, z_coarse, u):
     inds = torch.empty((b, nf), device=zc.device, dtype=torch.int64)
     L.call("atmonr_sample_pdf", L.ptr(w), L.ptr(zc), L.ptr(u), b, nc, nf, L.ptr(z), L.ptr(inds), L.stream())
     return z, inds
+
+
+class InverseCdfFn(torch.autograd.Function):
+    """samplers.py:72-101: (weights (B,Nc), z_coarse (B,Nc), u (B,Nf)) -> (z_sorted (B,Nc+Nf), inds, cdf).
+    Forward atmonr_sample_pdf_train, backward atmonr_sample_pdf_bwd (the reference's graph: only the bin
+    width is detached, samplers.py:96, so gradients reach the coarse weights through the CDF)."""
+
+    @staticmethod
+    def forward(ctx, weights, z_coarse, u):
+        w, zc, u = _c(weights, _f32), _c(z_coarse, _f32), _c(u, _f32)
+        b, nc = zc.shape
+        nf = u.shape[1]
+        z = torch.empty((b, nc + nf), device=zc.device, dtype=_f32)
+        inds = torch.empty((b, nf), device=zc.device, dtype=torch.int64)
+        cdf = torch.empty((b, nc - 1), device=zc.device, dtype=_f32)
+        src = torch.empty((b, nc + nf), device=zc.device, dtype=torch.int32)
+        L.call("atmonr_sample_pdf_train", L.ptr(w), L.ptr(zc), L.ptr(u), b, nc, nf, L.ptr(z), L.ptr(inds), L.ptr(cdf),
+               L.ptr(src), L.stream())
+        ctx.save_for_backward(w, zc, u, cdf, inds, src)
+        ctx.mark_non_differentiable(inds, cdf)
+        return z, inds, cdf
+
+    @staticmethod
+    def backward(ctx, gz, _gi, _gc):
+        w, zc, u, cdf, inds, src = ctx.saved_tensors
+        b, nc = zc.shape
+        nf = u.shape[1]
+        dw = torch.empty_like(w) if ctx.needs_input_grad[0] else None
+        dzc = torch.empty_like(zc) if ctx.needs_input_grad[1] else None
+        L.call("atmonr_sample_pdf_bwd", L.ptr(_c(gz, _f32)), L.ptr(src), L.ptr(w), L.ptr(zc), L.ptr(u), L.ptr(cdf),
+               L.ptr(inds), b, nc, nf, L.ptr(dw), L.ptr(dzc), L.stream())
+        return dw, dzc, None
+
+
+class NerfEncodeFn(torch.autograd.Function):
+    """pipelines/nerf.py:104-135 for one pass: z (B,N) -> x (B*N, 2 sum(L_x) + 6 L_d) = [encoded preprocessed
+    point | encoded ray direction] and the preprocessed points (B*N,3). One kernel forward
+    (atmonr_nerf_encode); backward = dL/dz in one kernel (atmonr_nerf_encode_bwd: encoding derivative,
+    float64 geodetic Jacobian, projection on the direction)."""
+
+    @staticmethod
+    def forward(ctx, z, origin, direction, frame, pos_freqs, dir_freqs):
+        z, o, d = _c(z, _f32), _c(origin, _f32), _c(direction, _f32)
+        b, n = z.shape
+        fr = (C.c_int32 * 3)(*pos_freqs)
+        width = 2 * sum(pos_freqs) + 6 * dir_freqs
+        ld = (width + 3) // 4 * 4        # 16-byte aligned rows for the dense layers' vector loads
+        x = torch.empty((b * n, ld), device=z.device, dtype=_f32)
+        pts_n = torch.empty((b * n, 3), device=z.device, dtype=_f32)
+        L.call("atmonr_nerf_encode", C.byref(frame), L.ptr(o), L.ptr(d), L.ptr(z), b, n, fr, int(dir_freqs), L.ptr(x), ld,
+               L.ptr(pts_n), L.stream())
+        ctx.frame, ctx.pos_freqs = frame, tuple(pos_freqs)
+        ctx.save_for_backward(z, o, d, pts_n)
+        ctx.mark_non_differentiable(pts_n)
+        return (x if ld == width else x[:, :width]), pts_n
+
+    @staticmethod
+    def backward(ctx, gx, _gp):
+        if not ctx.needs_input_grad[0]:
+            return None, None, None, None, None, None
+        z, o, d, pts_n = ctx.saved_tensors
+        b, n = z.shape
+        gx, ldg = _rows(gx)
+        gz = torch.empty_like(z)
+        fr = (C.c_int32 * 3)(*ctx.pos_freqs)
+        L.call("atmonr_nerf_encode_bwd", C.byref(ctx.frame), L.ptr(o), L.ptr(d), L.ptr(z), L.ptr(pts_n), gx.data_ptr(), ldg,
+               b, n, fr, L.ptr(gz), L.stream())
+        return gz, None, None, None, None, None
+
+
+def append_heights(pts: torch.Tensor, ray_origin_height: float, scale: float, offset) -> torch.Tensor:
+    """samplers.py:168-195 on the device: (..., 3) float32 -> (..., 4)."""
+    p = _c(pts, _f32)
+    flat = p.reshape(-1, 3)
+    out = torch.empty((flat.shape[0], 4), device=p.device, dtype=_f32)
+    off = (C.c_double * 3)(*[float(v) for v in offset])
+    L.call("atmonr_append_heights", L.ptr(flat), flat.shape[0], float(scale), off, float(ray_origin_height), L.ptr(out),
+           L.stream())
+    return out.view(*pts.shape[:-1], 4)

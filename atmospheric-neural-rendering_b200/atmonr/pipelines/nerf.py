@@ -1,12 +1,15 @@
 """NeRF pipeline (reference: src/atmonr/pipelines/nerf.py): coarse + fine hierarchical sampling
 with sinusoidal positional encoding and the AtmoNeRF MLPs.
 
-Kernels of libatmonr_b200 used here: stratified sampler, point preprocessor, positional
-encoding, inverse-CDF sampling + sort, compositing (forward/backward incl. d/dz). The reference
-keeps the gradient path fine-loss -> fine sample positions -> coarse weights alive
-(samplers.py:96 only detaches the bin width); that path needs d(preprocess)/d(point), which is
-evaluated through the float64 torch expressions of atmonr.geospatial.wgs_84 (same operations as
-the reference), and only for the fine pass.
+Every stage is a kernel of libatmonr_b200, forward and backward: stratified sampler, inverse-CDF
+sampling + sort (atmonr_sample_pdf_train / _bwd), point on the ray + geodetic preprocessing +
+positional encodings of point and direction in one pass (atmonr_nerf_encode / _bwd), the eleven
+dense layers on tcgen05 (models/nerf.py), compositing (atmonr_composite_fwd / _bwd / _bwd_weights).
+The reference keeps the gradient path fine loss -> fine sample distances -> coarse weights alive
+(samplers.py:96 only detaches the bin width): here it runs through atmonr_nerf_encode_bwd (encoding
+derivative + float64 geodetic Jacobian), atmonr_composite_dz, atmonr_sample_pdf_bwd and
+atmonr_composite_bwd_weights instead of torch graphs. `include_height`, an integer L_x or a
+preprocessor without a frame description take the operator-by-operator path below.
 """
 
 from __future__ import annotations
@@ -22,9 +25,9 @@ from atmonr.encoders import positional_encoding
 from atmonr.geospatial.wgs_84 import cartesian_to_horizontal
 from atmonr.graphics_utils import render
 from atmonr.models.nerf import get_model
-from atmonr.native import ops
+from atmonr.native import lib as L, ops
 from atmonr.pipelines.pipeline import Pipeline
-from atmonr.samplers import append_heights, sample_pdf, sample_uniform_bins
+from atmonr.samplers import append_heights, inverse_cdf_z, sample_pdf, sample_uniform_bins
 
 
 class NeRFPipeline(Pipeline):
@@ -64,34 +67,55 @@ class NeRFPipeline(Pipeline):
         alt = 2 * alt / frame.origin_height - 1
         return torch.clip(torch.stack([lat, lon, alt], dim=-1).to(pts.dtype), min=-1, max=1)
 
+    def _fused_frame(self):
+        """Frame description for atmonr_nerf_encode, or None when the configuration needs the modular path."""
+        cfg = self.config
+        l_x = cfg["encoder"]["L_x"]
+        if cfg["include_height"] or not (isinstance(l_x, list) and len(l_x) == 3) or not isinstance(cfg["encoder"]["L_d"], int):
+            return None
+        if not self.point_preprocessor:
+            return L.disabled_frame()
+        return getattr(self.point_preprocessor, "frame", None)
+
     def _forward(self, mode: str, ray_batch, weights_coarse=None, z_vals_coarse=None):
         """nerf.py:73-167."""
         assert (mode == "coarse") == (z_vals_coarse is None)
         cfg = self.config
         b = ray_batch["origin"].shape[0]
         l_x, l_d = cfg["encoder"]["L_x"], cfg["encoder"]["L_d"]
-        if mode == "coarse":
-            n = cfg["sampler"]["N_c"]
-            pts, z_vals = sample_uniform_bins(ray_batch, n_bins=n)
+        frame = self._fused_frame()
+        pts = None
+        if frame is not None:
+            # sample distances -> [encoded point | encoded direction] rows, one kernel each way
+            if mode == "coarse":
+                n = cfg["sampler"]["N_c"]
+                z_vals = sample_uniform_bins(ray_batch, n_bins=n)[1]
+            else:
+                n = cfg["sampler"]["N_c"] + cfg["sampler"]["N_f"]
+                u = torch.rand((b, cfg["sampler"]["N_f"]), device=z_vals_coarse.device)
+                z_vals = inverse_cdf_z(weights_coarse[..., 0], z_vals_coarse, u)
+            x = ops.NerfEncodeFn.apply(z_vals, ray_batch["origin"], ray_batch["dir"], frame, tuple(l_x), l_d)[0]
         else:
-            n = cfg["sampler"]["N_c"] + cfg["sampler"]["N_f"]
-            pts, z_vals = sample_pdf(ray_batch, weights_coarse, z_vals_coarse, n_samples=cfg["sampler"]["N_f"])
-        pts = self._preprocess(pts)
-        if cfg["include_height"]:
-            pts = append_heights(pts, self.ray_origin_height, self.scale, self.offset)
-        pts_enc = positional_encoding(pts, l_x).view((b * n, -1))
-        dirs = ray_batch["dir"][:, None].repeat(1, n, 1)
-        dirs_enc = positional_encoding(dirs, l_d).view((b * n, -1))
-        color, sigma = self.nerf[mode](torch.cat([pts_enc, dirs_enc], dim=1))
+            if mode == "coarse":
+                n = cfg["sampler"]["N_c"]
+                pts, z_vals = sample_uniform_bins(ray_batch, n_bins=n)
+            else:
+                n = cfg["sampler"]["N_c"] + cfg["sampler"]["N_f"]
+                pts, z_vals = sample_pdf(ray_batch, weights_coarse, z_vals_coarse, n_samples=cfg["sampler"]["N_f"])
+            pts = self._preprocess(pts)
+            if cfg["include_height"]:
+                pts = append_heights(pts, self.ray_origin_height, self.scale, self.offset)
+            pts_enc = positional_encoding(pts, l_x).view((b * n, -1))
+            dirs = ray_batch["dir"][:, None].repeat(1, n, 1)
+            dirs_enc = positional_encoding(dirs, l_d).view((b * n, -1))
+            x = torch.cat([pts_enc, dirs_enc], dim=1)
+        color, sigma = self.nerf[mode](x)
         color = color.view(b, n, -1)
         sigma = sigma.view(b, n, 1 if mode == "coarse" else -1)
         color = torch.exp(torch.clamp(color, max=11))  # nerf.py:150 (after the sigmoid)
         sigma = F.relu(sigma)
         z_km = z_vals * (self.scale / 1000)
-        if mode == "coarse" and torch.is_grad_enabled() and sigma.requires_grad:
-            color_map, weights = _composite_torch(z_km, color, sigma)  # weights feed sample_pdf's graph
-        else:
-            color_map, _, weights = render(z_km, color, sigma)
+        color_map, _, weights = render(z_km, color, sigma)   # the weights stay differentiable (CompositeFn)
         results = {f"color_{mode}": color, f"sigma_{mode}": sigma, f"color_map_{mode}": color_map,
                    f"weights_{mode}": weights, f"z_vals_{mode}": z_vals}
         if cfg["include_height"]:
@@ -141,15 +165,3 @@ class NeRFPipeline(Pipeline):
         self.training = False
         for net in self.nerf.values():
             net.eval()
-
-
-def _composite_torch(z_km, color, sigma):
-    """graphics_utils.py:28-48 as a torch graph; used for the coarse pass in training, where the
-    per-sample weights must stay differentiable (they define the fine sampler's CDF)."""
-    mid = (z_km[..., :-1] + z_km[..., 1:]) / 2
-    edges = torch.cat([z_km[..., :1] * 0, mid, z_km[..., -1:]], dim=-1)
-    delta = torch.diff(edges, dim=-1)[..., None]
-    alpha = 1 - torch.exp(-sigma * delta)
-    ones = torch.ones_like(alpha[:, :1])
-    weights = alpha * torch.cumprod(torch.cat([ones, 1 - alpha + 1e-10], dim=1), dim=1)[:, :-1]
-    return torch.sum(color * weights, dim=1), weights

@@ -18,51 +18,17 @@ def sample_uniform_bins(ray_batch: Mapping[str, torch.Tensor], n_bins: int = 64,
     return ops.sample_uniform(origin, ray_batch["dir"], ray_batch["len"], n_bins, u=u, random=False)
 
 
-class _InverseCdfFn(torch.autograd.Function):
-    """z of the fine samples (sorted together with the coarse ones). Forward is the
-    atmonr_sample_pdf kernel; backward follows the reference's graph: only the bin width is
-    detached (samplers.py:96), so gradients reach the coarse weights through the CDF and the
-    coarse z through the concatenation."""
-
-    @staticmethod
-    def forward(ctx, weights, z_coarse, u):
-        z, inds = ops.sample_pdf_z(weights, z_coarse, u)
-        ctx.mark_non_differentiable(inds)
-        return z, inds
-
-    @staticmethod
-    def backward(ctx, gz, _gi):
-        raise NotImplementedError(
-            "differentiating through sample_pdf: use atmonr.samplers.sample_pdf(differentiable=True)"
-        )
-
-
-def _inverse_cdf_torch(w, z_coarse, u):
-    """Differentiable path (torch graph, same operations as samplers.py:72-101)."""
-    w = w[:, 1:-1]
-    pdf = (w + 1e-8) / torch.sum(w + 1e-8, dim=1, keepdim=True)
-    cdf = torch.cumsum(pdf, dim=1)
-    cdf = torch.cat([torch.zeros_like(cdf[..., :1]), cdf], dim=1)
-    inds = torch.searchsorted(cdf.detach(), u.contiguous(), right=True)
-    lo = torch.clamp(inds - 1, min=0)
-    hi = torch.clamp(inds, max=cdf.shape[-1] - 1)
-    mids = 0.5 * (z_coarse[..., 1:] + z_coarse[..., :-1])
-    c_lo, c_hi = torch.gather(cdf, 1, lo), torch.gather(cdf, 1, hi)
-    m_lo, m_hi = torch.gather(mids, 1, lo), torch.gather(mids, 1, hi)
-    den = c_hi - c_lo
-    den = torch.where(den < 1e-8, torch.ones_like(den), den)
-    fine = m_lo + (u - c_lo) / den * (m_hi - m_lo).detach()
-    return torch.sort(torch.cat([z_coarse, fine], -1), -1)[0]
+def inverse_cdf_z(weights: torch.Tensor, z_vals_c: torch.Tensor, u: torch.Tensor) -> torch.Tensor:
+    """samplers.py:72-101: sorted union of the coarse distances and the inverse-CDF samples; differentiable
+    like the reference's graph (kernels forward and backward, atmonr.native.ops.InverseCdfFn)."""
+    return ops.InverseCdfFn.apply(weights, z_vals_c, u)[0]
 
 
 def sample_pdf(ray_batch, pdf_discrete, z_vals_c, n_samples: int = 128):
     """samplers.py:50-103 -> pts (B, N_c+n_samples, 3), z_vals (B, N_c+n_samples)."""
     w = pdf_discrete[..., 0]
     u = torch.rand((w.shape[0], n_samples), device=w.device)
-    if torch.is_grad_enabled() and (w.requires_grad or z_vals_c.requires_grad):
-        z = _inverse_cdf_torch(w, z_vals_c, u)
-    else:
-        z, _ = _InverseCdfFn.apply(w, z_vals_c, u)
+    z = inverse_cdf_z(w, z_vals_c, u)
     pts = ray_batch["origin"][:, None] + ray_batch["dir"][:, None] * z[..., None]
     return pts, z
 
@@ -84,7 +50,10 @@ def sample_biased_bins(ray_batch, n_bins: int, ray_origin_height: float, alpha: 
 
 
 def append_heights(pts, ray_origin_height: float, scale: float, offset: torch.Tensor):
-    """samplers.py:168-195: append ellipsoidal height / ray_origin_height as a 4th coordinate."""
+    """samplers.py:168-195: append ellipsoidal height / ray_origin_height as a 4th coordinate
+    (atmonr_append_heights; the float64 torch expressions only where the points carry a gradient)."""
+    if not (torch.is_grad_enabled() and pts.requires_grad) and pts.dtype == torch.float32:
+        return ops.append_heights(pts, ray_origin_height, scale, offset.tolist())
     from atmonr.geospatial.wgs_84 import cartesian_to_horizontal
 
     xyz = pts.double() * scale + offset[None, None]

@@ -39,6 +39,7 @@ UNITS = [
     ("fused", "ngp_fused.cu", []),
     ("rays", "rays.cu", []),
     ("linear", "linear_tc.cu", []),
+    ("nerfpts", "nerf_points.cu", []),
 ]
 
 

@@ -560,7 +560,10 @@ k_composite_fwd(const float* __restrict__ z, const float* __restrict__ color, co
 // active_idx and the list length to *n_active (zeroed by the caller). A ray's samples stay
 // consecutive and in order (one atomicAdd per ray reserves its block). Empty space costs the field
 // backward nothing that way.
-template <int K, int V, bool COMPACT>
+// GW: the per-sample weights w_i,v = alpha T are an output that somebody differentiates as well (NeRF
+// coarse pass: they define the fine sampler's CDF, samplers.py:72-74): g_weights (B,N,V) = dL/dw joins
+// q_i, and Q_v gains sum_i w_i g_weights_i (one pass over the saved weights in front).
+template <int K, int V, bool COMPACT, bool GW = false>
 __global__ void __launch_bounds__(128)
 k_composite_bwd(const float* __restrict__ z, const float* __restrict__ color, const float* __restrict__ sigma,
                 const float* __restrict__ color_surf, const float* __restrict__ catmo,
@@ -568,7 +571,8 @@ k_composite_bwd(const float* __restrict__ z, const float* __restrict__ color, co
                 const float* __restrict__ g_surf, float zs, int64_t B, int N, int relu,
                 float* __restrict__ dcolor, float* __restrict__ dsigma, float* __restrict__ dcolor_surf,
                 float* __restrict__ ddelta, float* __restrict__ grad_absmax, uint32_t* __restrict__ active_idx,
-                uint32_t* __restrict__ n_active) {
+                uint32_t* __restrict__ n_active, const float* __restrict__ g_weights = nullptr,
+                const float* __restrict__ weights = nullptr) {
   const int lane = threadIdx.x & 31;
   const int64_t ray = (blockIdx.x * (int64_t)blockDim.x + threadIdx.x) >> 5;
   if (ray >= B) return;
@@ -623,6 +627,17 @@ k_composite_bwd(const float* __restrict__ z, const float* __restrict__ color, co
       SG[v] += S * gs[k] * cs;
       if (lane == 0 && dcolor_surf) dcolor_surf[ray * K + k] = (relu && !(raw > 0.0f)) ? 0.0f : gs[k] * S;
     }
+  }
+  if (GW) {
+    float extra[V];
+#pragma unroll
+    for (int v = 0; v < V; ++v) extra[v] = 0.0f;
+    for (int i = lane; i < N; i += 32) {
+#pragma unroll
+      for (int v = 0; v < V; ++v) extra[v] += weights[(ray * N + i) * V + v] * g_weights[(ray * N + i) * V + v];
+    }
+#pragma unroll
+    for (int v = 0; v < V; ++v) Qtot[v] += warp_sum(extra[v]);
   }
   float amax = 0.0f;  // largest |gradient| written by this lane (for the fp16 scale of field_bwd_tc)
   RawSample<K, V> r0 = load_raw<K, V>(zr, color, sigma, ray * N, lane, N);
@@ -680,6 +695,7 @@ k_composite_bwd(const float* __restrict__ z, const float* __restrict__ color, co
         q = ga[v] * c[v];
         dc[v] = ga[v] * w;
       }
+      if (GW && in) q += g_weights[(ray * N + i) * V + v];
       const float wq = in ? w * q : 0.0f;
       const float qincl = carryQ[v] + warp_scan_sum(wq, lane);
       carryT[v] *= __shfl_sync(0xffffffffu, incl, 31);
@@ -1299,6 +1315,28 @@ int atmonr_composite_bwd(const float* z, const float* color, const float* sigma,
   ATM_KV_DISPATCH(K, V, CALL)
 #undef CALL
   ATM_CHECK_LAUNCH("atmonr_composite_bwd");
+  return 0;
+}
+
+int atmonr_composite_bwd_weights(const float* z, const float* color, const float* sigma, const float* color_surf,
+                                 const float* color_map_atmo, const float* trans_surf, const float* weights,
+                                 const float* d_atmo, const float* d_surf, const float* d_weights, float z_scale,
+                                 int64_t B, int N, int K, int V, int relu, float* dcolor, float* dsigma,
+                                 float* dcolor_surf, float* ddelta, void* stream) {
+  if (B == 0) return 0;
+  ATM_REQUIRE(color_map_atmo && d_atmo && dcolor && dsigma && weights && d_weights, "atmonr_composite_bwd_weights",
+              "null argument");
+  ATM_REQUIRE(!color_surf || trans_surf, "atmonr_composite_bwd_weights", "trans_surf required with a surface");
+  ATM_REQUIRE(K != 4 || ((reinterpret_cast<uintptr_t>(color) | reinterpret_cast<uintptr_t>(dcolor)) & 15u) == 0,
+              "atmonr_composite_bwd_weights", "color and dcolor must be 16-byte aligned");
+  const int grid = grid_for(B * 32, 128);
+#define CALL(KK, VV)                                                                                                  \
+  k_composite_bwd<KK, VV, false, true><<<grid, 128, 0, S(stream)>>>(                                                  \
+      z, color, sigma, color_surf, color_map_atmo, trans_surf, d_atmo, d_surf, z_scale, B, N, relu, dcolor, dsigma,    \
+      dcolor_surf, ddelta, nullptr, nullptr, nullptr, d_weights, weights)
+  ATM_KV_DISPATCH(K, V, CALL)
+#undef CALL
+  ATM_CHECK_LAUNCH("atmonr_composite_bwd_weights");
   return 0;
 }
 

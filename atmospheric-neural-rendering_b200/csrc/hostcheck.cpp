@@ -6,6 +6,7 @@
 #include <vector>
 
 #include "device_math.cuh"
+#include "nerf_points.cuh"
 #include "ray_setup.cuh"
 
 template <int D>
@@ -99,6 +100,25 @@ int hc_get_rays(const float* lat, const float* lon, const float* alt, const floa
   }
   for (int64_t i = 0; i < n; ++i) atm::ray_outputs(rs[i], cur[i], origin + 3 * i, dir + 3 * i, len[i]);
   return iters;
+}
+
+// csrc/nerf_points.cu, per sample on the host: rows [pos | dir] and preprocessed points; then dL/dz
+void hc_nerf_encode(const atmonr_frame_t* f, const float* o, const float* d, const float* z, int64_t B, int N,
+                    const int32_t* pos_freqs, int dir_freqs, float* x, int ldx, float* pts_n) {
+  const atm::GeoFrame gf = atm::make_geo_frame(*f);
+  atm::NerfEncCfg c;
+  atm::nerf_enc_cfg(pos_freqs, dir_freqs, c);
+  for (int64_t i = 0; i < B * N; ++i)
+    atm::nerf_encode_sample(*f, gf, o + 3 * (i / N), d + 3 * (i / N), z[i], c, x + i * ldx, pts_n + 3 * i);
+}
+
+void hc_nerf_encode_bwd(const atmonr_frame_t* f, const float* o, const float* d, const float* z, const float* pts_n,
+                        const float* g, int ldg, int64_t B, int N, const int32_t* pos_freqs, float* gz) {
+  const atm::GeoFrame gf = atm::make_geo_frame(*f);
+  atm::NerfEncCfg c;
+  atm::nerf_enc_cfg(pos_freqs, 0, c);
+  for (int64_t i = 0; i < B * N; ++i)
+    gz[i] = atm::nerf_encode_sample_bwd(*f, gf, o + 3 * (i / N), d + 3 * (i / N), z[i], pts_n + 3 * i, g + i * ldg, c);
 }
 
 }  // extern "C"

@@ -218,6 +218,17 @@ int atmonr_composite_bwd(const float* z, const float* color, const float* sigma,
                          float* dsigma, float* dcolor_surf, float* ddelta, float* grad_absmax,
                          void* stream);
 
+/* atmonr_composite_bwd for callers that ALSO differentiate the per-sample weights it returned
+ * (NeRF coarse pass: the weights define the fine sampler's CDF, samplers.py:72-74): weights (B,N,V) as
+ * written by atmonr_composite_fwd, d_weights (B,N,V) = dL/dweights; their contribution is added to
+ * dsigma / ddelta (the weights do not depend on colour). */
+int atmonr_composite_bwd_weights(const float* z, const float* color, const float* sigma,
+                                 const float* color_surf, const float* color_map_atmo,
+                                 const float* trans_surf, const float* weights, const float* d_atmo,
+                                 const float* d_surf, const float* d_weights, float z_scale,
+                                 int64_t B, int N, int K, int V, int relu, float* dcolor,
+                                 float* dsigma, float* dcolor_surf, float* ddelta, void* stream);
+
 /* The same backward, writing dcolor / dsigma only for the samples that can carry a gradient, as a
  * list: active_idx (capacity B*N) receives their sample indices (a ray's samples stay consecutive
  * and ordered), dcolor_c (capacity B*N, K) and dsigma_c (capacity B*N, V) their gradients by list
@@ -276,6 +287,44 @@ int atmonr_positional_encoding_f64(const double* pts, int64_t M, int C, const in
  * column), z_coarse (B,Nc), u (B,Nf) -> z_sorted (B,Nc+Nf), inds (B,Nf) int64. */
 int atmonr_sample_pdf(const float* weights, const float* z_coarse, const float* u, int64_t B,
                       int Nc, int Nf, float* z_sorted, int64_t* inds, void* stream);
+/* The same with the by-products the training path needs: cdf (B,Nc-1) = the CDF the bin search ran on
+ * (inds == searchsorted(cdf, u, right=True) exactly), src (B,Nc+Nf) int32 = for every position of
+ * z_sorted the input it came from (0..Nc-1: coarse sample, Nc+s: fine sample s). Either may be NULL. */
+int atmonr_sample_pdf_train(const float* weights, const float* z_coarse, const float* u, int64_t B,
+                            int Nc, int Nf, float* z_sorted, int64_t* inds, float* cdf,
+                            int32_t* src, void* stream);
+/* Backward of sample_pdf as the reference's autograd graph defines it (samplers.py:72-101; only the
+ * bin width is detached, :96): g_z_sorted (B,Nc+Nf) -> d_weights (B,Nc) (zero in the first and last
+ * column, which samplers.py:72 drops) and d_z_coarse (B,Nc); either output may be NULL. */
+int atmonr_sample_pdf_bwd(const float* g_z_sorted, const int32_t* src, const float* weights,
+                          const float* z_coarse, const float* u, const float* cdf,
+                          const int64_t* inds, int64_t B, int Nc, int Nf, float* d_weights,
+                          float* d_z_coarse, void* stream);
+/* pipelines/nerf.py:104-135 for one network pass, per sample i of ray r = i / N:
+ *   p = origin[r] + dir[r] * z[i]  ->  harp2.py:372-386 `horizontal` preprocessing when frame->enabled
+ *   x[i] = [ positional_encoding(p, pos_freqs) (list layout, encoders.py:21-27)
+ *          | positional_encoding(dir[r], dir_freqs) (int layout, encoders.py:14-20) ],  row stride ldx
+ *   pts_n[i] = the preprocessed point (B*N,3).
+ * The direction encoding is evaluated per sample from the ray's direction (nothing of shape (B,N,3)
+ * is repeated or concatenated). */
+int atmonr_nerf_encode(const atmonr_frame_t* frame, const float* origin, const float* dir,
+                       const float* z, int64_t B, int N, const int32_t* pos_freqs_host, int dir_freqs,
+                       float* x, int ldx, float* pts_n, void* stream);
+/* dL/dz (B*N) of the chain above given g_x = dL/dx (row stride ldg; the first 2*sum(pos_freqs)
+ * columns are read): derivative of the positional encoding, Jacobian of the geodetic conversion in
+ * float64 (wgs_84.py:56-97 differentiated, clip mask of harp2.py:386 included) and projection on the
+ * ray direction. The reference obtains the same numbers from autograd through its float64 torch
+ * expressions. */
+int atmonr_nerf_encode_bwd(const atmonr_frame_t* frame, const float* origin, const float* dir,
+                           const float* z, const float* pts_n, const float* g_x, int ldg, int64_t B,
+                           int N, const int32_t* pos_freqs_host, float* g_z, void* stream);
+/* dL/d(Voronoi cell widths, km) as written by atmonr_composite_bwd -> dL/dz (graphics_utils.py:30-36
+ * differentiated; z_scale = km per unit of z). */
+int atmonr_composite_dz(const float* ddelta, int64_t B, int N, float z_scale, float* dz, void* stream);
+/* samplers.py:168-195 append_heights: out (M,4) = [pts | height(pts * scale + offset) / ray_origin_height]
+ * with the float64 Bowring step of wgs_84.py:56-97. offset_host: 3 doubles on the host. */
+int atmonr_append_heights(const float* pts, int64_t M, double scale, const double* offset_host,
+                          double ray_origin_height, float* out, void* stream);
 
 /* ---- AtmoNeRF dense layers (models/nerf.py:6-93: eleven biased nn.Linear) on tcgen05 -----------
  * Float32 in and out, float32-accurate: every operand is split into three bfloat16 terms and each

@@ -363,3 +363,48 @@ def test_nerf_model_default_path_is_unchanged_on_cpu(monkeypatch):
     monkeypatch.setattr(mn, "DENSE_IMPL", "library")
     got = coarse(x)
     assert torch.equal(want[0], got[0]) and torch.equal(want[1], got[1])
+
+
+@pytest.mark.parametrize("with_frame", [True, False])
+def test_host_build_of_nerf_point_encoder_matches_oracle_forward_and_gradient(with_frame):
+    """csrc/nerf_points.cuh (atmonr_nerf_encode / _bwd, host build): rows [PE(preprocess(o + d z)) | PE(d)]
+    against the oracle's preprocessing + encoders, and dL/dz (positional-encoding derivative, analytic
+    float64 geodetic Jacobian, projection on the direction) against autograd through the oracle's float64
+    expressions of wgs_84.py:56-97 (tolerance 2e-4 of the gradient scale: float32 sums of terms up to
+    2^13 pi large, the Jacobian itself agrees to 2e-7)."""
+    from oracle import nerf as onerf
+    from atmonr.native import lib as L
+    scene = tiny_scene()
+    b = take(scene.batch, slice(0, 40))
+    n, lx, ld = 12, [10, 10, 6], 4
+    g = torch.Generator().manual_seed(5)
+    z = (torch.rand(40, n, generator=g) * b["len"][:, None]).contiguous()
+    z[0, 0] = b["len"][0] * 1.5        # below the ellipsoid: altitude clipped, its gradient masked
+    fr = _frame_struct(scene.frame) if with_frame else L.disabled_frame()
+    width = 2 * sum(lx) + 6 * ld
+    o, d = b["origin"].numpy().copy(), b["dir"].numpy().copy()
+    x = np.zeros((40 * n, width), np.float32)
+    pn = np.zeros((40 * n, 3), np.float32)
+    freqs = (C.c_int32 * 3)(*lx)
+    hc = _hc()
+    hc.hc_nerf_encode(C.byref(fr), _p(o), _p(d), _p(z.numpy()), C.c_int64(40), n, freqs, ld, _p(x), width, _p(pn))
+
+    zt = z.clone().requires_grad_()
+    pts = b["origin"][:, None] + b["dir"][:, None] * zt[..., None]
+    ptn = geodesy.preprocess_horizontal(pts, scene.frame) if with_frame else pts
+    want = torch.cat([onerf.pe_per_axis(ptn, lx).view(40 * n, -1),
+                      onerf.pe_interleaved(b["dir"][:, None].repeat(1, n, 1), ld).view(40 * n, -1)], dim=1)
+    assert np.abs(pn - ptn.detach().view(-1, 3).numpy()).max() < 1.5e-7
+    # the highest frequencies multiply the last-bit differences of the preprocessed point by 2^9 pi
+    assert np.abs(x - want.detach().numpy()).max() < 5e-4
+    assert np.abs(x[:, :6] - want.detach().numpy()[:, :6]).max() < 2e-6
+
+    gx = torch.randn(40 * n, width, generator=g)
+    (want * gx).sum().backward()
+    gz = np.zeros((40, n), np.float32)
+    hc.hc_nerf_encode_bwd(C.byref(fr), _p(o), _p(d), _p(z.numpy()), _p(pn), _p(gx.numpy()), width, C.c_int64(40), n, freqs, _p(gz))
+    ref = zt.grad.numpy()
+    assert np.abs(ref).max() > 0
+    assert np.abs(gz - ref).max() <= 2e-4 * np.abs(ref).max()
+    if with_frame:
+        assert scene.frame is not None and abs(float(ptn.detach().view(-1, 3)[0, 2])) == 1.0   # the clipped sample is in the set

@@ -201,11 +201,7 @@ def test_sample_biased_bins_matches_reference(tag, alpha):
 
 
 def test_append_heights_matches_reference():
-    import sys
-    sys.path.insert(0, os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "atmospheric-neural-rendering_b200"))
-    from atmonr import samplers
-    got = samplers.append_heights(TX("ah_pts"), 20000.0, float(GX["ah_scale"]), TX("ah_offset"))
-    close(got, TX("ah_out"))
+    """(The package's append_heights is a kernel: tests/test_gpu_nerf_native.py checks it against the same vectors.)"""
     want = sampling.append_heights(TX("ah_pts"), 20000.0, float(GX["ah_scale"]), TX("ah_offset"))
     close(want, TX("ah_out"))
 
@@ -231,30 +227,6 @@ def test_voxel_traversal_matches_reference(tag):
         graphics_utils.voxel_traversal(u, end[:5])
 
 
-def test_package_sample_pdf_differentiable_path_matches_reference():
-    """atmonr.samplers.sample_pdf on the differentiable path (the torch graph the NeRF coarse -> fine
-    gradient flows through; plain torch, so it runs here) against the reference's output for the same
-    generator state, and its gradients against the oracle's (pinned through the NeRF pipeline golden)."""
-    import sys
-    sys.path.insert(0, os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "atmospheric-neural-rendering_b200"))
-    from atmonr import samplers
-    o, d, ln = _batch()
-    batch = {"origin": o[:7], "dir": d[:7], "len": ln[:7]}
-    w = T("pdf_w").clone().requires_grad_()
-    zc = T("pdf_zc").clone().requires_grad_()
-    torch.manual_seed(77)
-    pts, z = samplers.sample_pdf(batch, w, zc, n_samples=24)
-    close(z.detach(), T("pdf_z")); close(pts.detach(), T("pdf_pts"))
-    g = torch.rand(z.shape, generator=torch.Generator().manual_seed(1))
-    (z * g).sum().backward()
-    w2 = T("pdf_w").clone().requires_grad_()
-    zc2 = T("pdf_zc").clone().requires_grad_()
-    _, z2, _ = sampling.sample_pdf(o[:7], d[:7], w2, zc2, T("pdf_u"))
-    (z2 * g).sum().backward()
-    close(w.grad, w2.grad, rtol=1e-6, atol=1e-9); close(zc.grad, zc2.grad, rtol=1e-6, atol=1e-9)
-    assert float(w.grad.abs().max()) > 0
-
-
 def test_spherical_helpers_match_reference():
     """geospatial/spherical.py (used by the global-grid extract layout): WGS-84 <-> spherical Earth and
     the above-sea-level stretch."""
@@ -265,17 +237,6 @@ def test_spherical_helpers_match_reference():
     close(spherical.wgs_84_to_spherical(x.clone()), TX("sph_fwd"))
     close(spherical.spherical_to_wgs84(spherical.wgs_84_to_spherical(x.clone())), TX("sph_back"))
     close(spherical.stretch_above_sea_level(spherical.wgs_84_to_spherical(x.clone()), 12.0), TX("sph_stretch"))
-
-
-def test_package_coarse_compositing_graph_matches_reference():
-    """pipelines/nerf.py: the coarse pass composites through a torch graph (its weights feed the fine
-    sampler's CDF); same numbers as the reference's render (golden) and the same weights."""
-    import sys
-    sys.path.insert(0, os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "atmospheric-neural-rendering_b200"))
-    from atmonr.pipelines.nerf import _composite_torch
-    for tag in ("1", "4"):
-        c, w = _composite_torch(T("r_z"), T("r_col"), T(f"r_sg{tag}"))
-        close(c, T(f"r_c{tag}"), rtol=1e-6, atol=1e-7); close(w, T(f"r_w{tag}"), rtol=1e-6, atol=1e-8)
 
 
 def test_vincenty_functions_match_reference():
