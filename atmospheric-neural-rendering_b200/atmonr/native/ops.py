@@ -9,6 +9,7 @@ CPU implementation: CPU tensors raise.
 from __future__ import annotations
 
 import ctypes as C
+import os
 
 import torch
 
@@ -137,9 +138,15 @@ gather_batch.check = False
 # ------------------------------------------------------------------------------------------
 # AtmoNeRF dense layers on tcgen05 (float32-accurate bf16x3 split), csrc/linear_tc.cu
 # ------------------------------------------------------------------------------------------
-def linear_planes_bytes(n_out: int, k_in: int) -> int:
+# bf16 terms per float32 operand of the tensor-core dense layers (include/atmonr_b200.h): 2 = three partial
+# products, error ~2^-16 of a product (the training default, checked against the float32 oracle at 1e-3 on the
+# radiances), 3 = six partial products, float32-exact (cross-check; ATMONR_LINEAR_TERMS=3)
+LINEAR_TERMS = int(os.environ.get("ATMONR_LINEAR_TERMS", "2"))
+
+
+def linear_planes_bytes(n_out: int, k_in: int, terms: int | None = None) -> int:
     """Size of the split copy of a (n_out, k_in) matrix (include/atmonr_b200.h: atmonr_linear_prep)."""
-    return -(-n_out // 256) * -(-k_in // 32) * 3 * 16384
+    return -(-n_out // 256) * -(-k_in // 32) * (terms or LINEAR_TERMS) * 16384
 
 
 def _rows(t: torch.Tensor):
@@ -168,7 +175,7 @@ def _segments(x: torch.Tensor, x2):
 
 
 def linear_forward(x: torch.Tensor, weight: torch.Tensor, bias, relu: bool, transpose: bool = False,
-                   mask: torch.Tensor | None = None, x2: torch.Tensor | None = None) -> torch.Tensor:
+                   mask: torch.Tensor | None = None, x2: torch.Tensor | None = None, terms: int | None = None) -> torch.Tensor:
     """act(X' @ B.T + bias) with B = weight (n_out, k_in), or B = weight.T when `transpose` (then
     weight is (k_in, n_out)); X = x or [x | x2]; X' = X where mask > 0 and 0 elsewhere when a mask is
     given. x, x2 and mask may be column slices of wider float32 tensors."""
@@ -186,17 +193,18 @@ def linear_forward(x: torch.Tensor, weight: torch.Tensor, bias, relu: bool, tran
         if tuple(mask.shape) != (m, k_in):
             raise ValueError("linear_forward: mask and input must have the same shape")
         mp = mask.data_ptr()
-    planes = torch.empty(linear_planes_bytes(n_out, k_in), device=x.device, dtype=torch.uint8)
+    terms = terms or LINEAR_TERMS
+    planes = torch.empty(linear_planes_bytes(n_out, k_in, terms), device=x.device, dtype=torch.uint8)
     y = torch.empty((m, n_out), device=x.device, dtype=_f32)
-    L.call("atmonr_linear_prep", L.ptr(weight), n_out, k_in, int(transpose), L.ptr(planes), L.stream())
+    L.call("atmonr_linear_prep", L.ptr(weight), n_out, k_in, int(transpose), terms, L.ptr(planes), L.stream())
     b = None if bias is None else _c(bias.detach(), _f32)
     L.call("atmonr_linear_fwd_tc", x.data_ptr(), ldx, x2p, ldx2, k_split, mp, ldm, L.ptr(planes), L.ptr(b), m, n_out,
-           k_in, int(relu), L.ptr(y), n_out, L.stream())
+           k_in, int(relu), terms, L.ptr(y), n_out, L.stream())
     return y
 
 
 def linear_weight_grad(dy: torch.Tensor, x: torch.Tensor, mask: torch.Tensor | None = None,
-                       x2: torch.Tensor | None = None, want_bias: bool = False):
+                       x2: torch.Tensor | None = None, want_bias: bool = False, terms: int | None = None):
     """dW (n_out, k_in) = dy'.T @ X over all rows; X = x or [x | x2]; dy' = dy where mask > 0 (mask: the
     layer's output). With want_bias also db (n_out) = column sums of dy', from the same pass: (dW, db)."""
     dy, ldy = _rows(dy)
@@ -213,7 +221,7 @@ def linear_weight_grad(dy: torch.Tensor, x: torch.Tensor, mask: torch.Tensor | N
     dw = torch.zeros((n_out, k_in), device=x.device, dtype=_f32)
     db = torch.zeros((n_out,), device=x.device, dtype=_f32) if want_bias else None
     L.call("atmonr_linear_dw_tc", dy.data_ptr(), ldy, mp, ldm, x.data_ptr(), ldx, x2p, ldx2, k_split, x.shape[0], n_out,
-           k_in, L.ptr(dw), L.ptr(db), L.stream())
+           k_in, terms or LINEAR_TERMS, L.ptr(dw), L.ptr(db), L.stream())
     return (dw, db) if want_bias else dw
 
 

@@ -11,6 +11,13 @@
 // manage) and the product is assembled from the six significant partial products
 //      hi*hi + hi*mid + mid*hi + mid*mid + hi*lo + lo*hi                (dropped terms <= 2^-25)
 // as six tcgen05.mma.kind::f16 (bf16 inputs, float32 accumulate) into ONE accumulator in TMEM.
+// TERMS = 2 is the two-term flavour  v = hi + lo  (16 significand bits) with the three products
+//      hi*hi + hi*lo + lo*hi                                            (dropped terms <= 2^-17)
+// i.e. a product error of ~2^-16 relative, sixty times below what one TF32 pass delivers and
+// measured at < 1e-4 of the rendered radiances (tests/test_zz_gpu_linear_tc.py): half the tensor-core
+// work and two thirds of the staging, and the stages shrink enough for TWO CTAs per SM, whose
+// independent tiles hide each other's global-load latency. The NeRF pipeline trains with TERMS = 2;
+// TERMS = 3 stays available (ATMONR_LINEAR_TERMS=3) as the float32-exact cross-check.
 //
 // Tile: 128 rows of X x up to 256 columns of Y per CTA (grid.y walks wider layers: fc9 has 256+V
 // outputs), K in chunks of 32. Operand tiles live in shared memory in the no-swizzle core-matrix
@@ -39,11 +46,17 @@ constexpr int kChunk = 32;                        // K per stage
 constexpr int kThreads = 256;
 constexpr int kATile = kRows * kChunk * 2;        // 8 KB: one bf16 plane of the X chunk
 constexpr int kBTile = kCols * kChunk * 2;        // 16 KB: one bf16 plane of the B chunk
-constexpr int kStage = 3 * kATile + 3 * kBTile;   // 72 KB
-constexpr int kBar = 2 * kStage;                  // bar[s]: stage s consumed by its MMAs; full[s]: B planes of stage s landed
-constexpr int kTmemPtr = kBar + 32;
-constexpr int kBytes = kTmemPtr + 16;
+constexpr int kHalf = 128;                        // columns of one epilogue pass
+constexpr int kOutTile = kRows * (kHalf + 4) * 4; // 66 KB: staged output, one column half
 constexpr uint32_t kTmemCols = 256;
+template <int TERMS>
+struct Map {
+  static constexpr int kStage = TERMS * kATile + TERMS * kBTile;   // 72 KB (3 terms) / 48 KB (2 terms)
+  static constexpr int kBar = 2 * kStage;   // bar[s]: stage s consumed by its MMAs; full[s]: B planes of stage s landed
+  static constexpr int kTmemPtr = kBar + 32;
+  static constexpr int kBytes = kTmemPtr + 16;
+  static_assert(kOutTile <= 2 * kStage, "the staged output half must fit in the operand stages");
+};
 }  // namespace lin
 
 __host__ __device__ constexpr uint32_t make_idesc_bf16(int M, int N) {
@@ -69,6 +82,48 @@ __device__ __forceinline__ void split8(const float (&v)[8], uint4& hi, uint4& mi
   }
 }
 
+// v[8] -> two bf16 planes (hi, lo)
+__device__ __forceinline__ void split8(const float (&v)[8], uint4& hi, uint4& lo) {
+  uint32_t* h = reinterpret_cast<uint32_t*>(&hi);
+  uint32_t* l = reinterpret_cast<uint32_t*>(&lo);
+#pragma unroll
+  for (int j = 0; j < 4; ++j) {
+    const float a = v[2 * j], b = v[2 * j + 1];
+    const __nv_bfloat162 ph = __floats2bfloat162_rn(a, b);
+    const __nv_bfloat162 pl = __floats2bfloat162_rn(a - __bfloat162float(ph.x), b - __bfloat162float(ph.y));
+    h[j] = *reinterpret_cast<const uint32_t*>(&ph);
+    l[j] = *reinterpret_cast<const uint32_t*>(&pl);
+  }
+}
+// split 8 values into TERMS planes `pitch` bytes apart, at 16-byte chunk (r, cc) of a [rows][width] tile
+template <int TERMS>
+__device__ __forceinline__ void split_store(const float (&v)[8], uint8_t* tile, int pitch, int r, int cc, int width) {
+  if (TERMS == 3) {
+    uint4 hi, mid, lo;
+    split8(v, hi, mid, lo);
+    st_chunk(tile, r, cc, width, hi);
+    st_chunk(tile + pitch, r, cc, width, mid);
+    st_chunk(tile + 2 * pitch, r, cc, width, lo);
+  } else {
+    uint4 hi, lo;
+    split8(v, hi, lo);
+    st_chunk(tile, r, cc, width, hi);
+    st_chunk(tile + pitch, r, cc, width, lo);
+  }
+}
+// (A plane, B plane) of the significant partial products
+template <int TERMS> struct Products;
+template <> struct Products<3> {
+  static constexpr int kN = 6;
+  __device__ static constexpr int a(int t) { return t == 0 ? 0 : t == 1 ? 0 : t == 2 ? 1 : t == 3 ? 1 : t == 4 ? 0 : 2; }
+  __device__ static constexpr int b(int t) { return t == 0 ? 0 : t == 1 ? 1 : t == 2 ? 0 : t == 3 ? 1 : t == 4 ? 2 : 0; }
+};
+template <> struct Products<2> {
+  static constexpr int kN = 3;
+  __device__ static constexpr int a(int t) { return t == 2 ? 1 : 0; }
+  __device__ static constexpr int b(int t) { return t == 1 ? 1 : 0; }
+};
+
 // eight consecutive float32 of a row (`left` = columns left in the row; fewer than 8 -> zero fill),
 // optionally zeroed where the matching entry of `m` is not positive (the ReLU derivative of the
 // layer's output, applied while the gradient operand is staged)
@@ -92,7 +147,8 @@ __device__ __forceinline__ void load8(const float* __restrict__ src, const float
 }
 
 // B (n_out, k_in) float32 row-major, or its transpose when `transpose` (then the source is
-// (k_in, n_out) row-major) -> planes[(tile * k_chunks + chunk) * 3 + plane][256 x 32 bf16, tile layout]
+// (k_in, n_out) row-major) -> planes[(tile * k_chunks + chunk) * TERMS + plane][256 x 32 bf16, tile layout]
+template <int TERMS>
 __global__ void k_linear_prep(const float* __restrict__ w, int n_out, int k_in, int transpose, int k_chunks,
                               int n_tiles, uint8_t* __restrict__ planes) {
   const int groups = k_chunks * 4;  // 8-column groups per row
@@ -108,22 +164,20 @@ __global__ void k_linear_prep(const float* __restrict__ w, int n_out, int k_in, 
     if (row < n_out && k < k_in) x = transpose ? w[(size_t)k * n_out + row] : w[(size_t)row * k_in + k];
     v[j] = x;
   }
-  uint4 hi, mid, lo;
-  split8(v, hi, mid, lo);
   const int tile = row / lin::kCols, r = row % lin::kCols, chunk = grp >> 2, cc = grp & 3;
-  uint8_t* base = planes + ((size_t)tile * k_chunks + chunk) * 3 * lin::kBTile;
-  st_chunk(base, r, cc, lin::kChunk, hi);
-  st_chunk(base + lin::kBTile, r, cc, lin::kChunk, mid);
-  st_chunk(base + 2 * lin::kBTile, r, cc, lin::kChunk, lo);
+  uint8_t* base = planes + ((size_t)tile * k_chunks + chunk) * TERMS * lin::kBTile;
+  split_store<TERMS>(v, base, lin::kBTile, r, cc, lin::kChunk);
 }
 
-__global__ void __launch_bounds__(lin::kThreads, 1)
+template <int TERMS>
+__global__ void __launch_bounds__(lin::kThreads, TERMS == 2 ? 2 : 1)
 k_linear_tc(const float* __restrict__ x, int64_t ldx, const float* __restrict__ x2, int64_t ldx2, int k_split,
             const float* __restrict__ mask, int64_t ldm, const uint8_t* __restrict__ planes, const float* __restrict__ bias, int64_t M, int n_out, int k_in,
             int k_chunks, int act, float* __restrict__ y, int64_t ldy) {
   extern __shared__ __align__(128) uint8_t smem[];
-  uint64_t* bar = reinterpret_cast<uint64_t*>(smem + lin::kBar);          // bar[s]: MMAs that read stage s are done
-  uint32_t* tmem_ptr = reinterpret_cast<uint32_t*>(smem + lin::kTmemPtr);
+  using MapT = lin::Map<TERMS>;
+  uint64_t* bar = reinterpret_cast<uint64_t*>(smem + MapT::kBar);          // bar[s]: MMAs that read stage s are done
+  uint32_t* tmem_ptr = reinterpret_cast<uint32_t*>(smem + MapT::kTmemPtr);
   const int tid = threadIdx.x, warp = tid >> 5;
   if (warp == 0) tmem_alloc<lin::kTmemCols>(tmem_ptr);
   uint64_t* full = bar + 2;
@@ -145,7 +199,7 @@ k_linear_tc(const float* __restrict__ x, int64_t ldx, const float* __restrict__ 
   const int n0 = blockIdx.y * lin::kCols;                                  // first output column of this CTA
   const int n_cols = min(lin::kCols, ((n_out + 15) / 16) * 16 - n0);       // MMA N (multiple of 16)
   const uint32_t idesc = make_idesc_bf16(lin::kRows, n_cols);
-  const uint8_t* b_src = planes + (size_t)blockIdx.y * k_chunks * 3 * lin::kBTile;
+  const uint8_t* b_src = planes + (size_t)blockIdx.y * k_chunks * TERMS * lin::kBTile;
   const bool vec_ok = (ldx & 3) == 0 && (reinterpret_cast<uintptr_t>(x) & 15) == 0 &&
                       (!mask || ((ldm & 3) == 0 && (reinterpret_cast<uintptr_t>(mask) & 15) == 0)) &&
                       (!x2 || ((ldx2 & 3) == 0 && (reinterpret_cast<uintptr_t>(x2) & 15) == 0));
@@ -175,21 +229,21 @@ k_linear_tc(const float* __restrict__ x, int64_t ldx, const float* __restrict__ 
 
   for (int c = 0; c < k_chunks; ++c) {
     const int s = c & 1;
-    uint8_t* stage = smem + s * lin::kStage;
+    uint8_t* stage = smem + s * MapT::kStage;
     // the MMAs of chunk c-2 read this stage: wait for their commit (completion number (c>>1)-1 of bar[s])
     if (c >= 2) mbar_wait(bar + s, (uint32_t)(((c >> 1) - 1) & 1));
-    // ---- B chunk: three planes, already split and in tile order: the first n_cols rows of a plane are
+    // ---- B chunk: TERMS planes, already split and in tile order: the first n_cols rows of a plane are
     // its first n_cols * 64 bytes -> one bulk copy per plane, announced on full[s]. (This thread has
     // passed the wait above, so the MMAs that read the stage before are done.)
     if (tid == 0) {
-      const uint8_t* src = b_src + (size_t)c * 3 * lin::kBTile;
-      uint8_t* dst = stage + 3 * lin::kATile;
+      const uint8_t* src = b_src + (size_t)c * TERMS * lin::kBTile;
+      uint8_t* dst = stage + TERMS * lin::kATile;
       const uint32_t bytes = (uint32_t)n_cols * 64u;
-      mbar_expect_tx(full + s, 3u * bytes);
+      mbar_expect_tx(full + s, (uint32_t)TERMS * bytes);
 #pragma unroll
-      for (int p = 0; p < 3; ++p) bulk_g2s(dst + p * lin::kBTile, src + p * lin::kBTile, bytes, full + s);
+      for (int p = 0; p < TERMS; ++p) bulk_g2s(dst + p * lin::kBTile, src + p * lin::kBTile, bytes, full + s);
     }
-    // ---- X chunk: 128 rows x 32 columns float32 -> three bf16 planes (2 groups of 8 values per thread).
+    // ---- X chunk: 128 rows x 32 columns float32 -> TERMS bf16 planes (2 groups of 8 values per thread).
     // The values were requested one chunk ahead (xv: registers), so the global-load latency sits
     // underneath the previous chunk's split, barrier and MMAs; the next chunk is requested now.
     float cur[2][8];
@@ -201,11 +255,7 @@ k_linear_tc(const float* __restrict__ x, int64_t ldx, const float* __restrict__ 
 #pragma unroll
     for (int it = 0; it < 2; ++it) {
       const int r = ((warp + it * (lin::kThreads / 32)) << 3) | (tid & 7), cc = (tid >> 3) & 3;
-      uint4 hi, mid, lo;
-      split8(cur[it], hi, mid, lo);
-      st_chunk(stage, r, cc, lin::kChunk, hi);
-      st_chunk(stage + lin::kATile, r, cc, lin::kChunk, mid);
-      st_chunk(stage + 2 * lin::kATile, r, cc, lin::kChunk, lo);
+      split_store<TERMS>(cur[it], stage, lin::kATile, r, cc, lin::kChunk);
     }
     fence_async_smem();
     tc_fence_before();
@@ -213,15 +263,15 @@ k_linear_tc(const float* __restrict__ x, int64_t ldx, const float* __restrict__ 
     if (warp == 0) {
       mbar_wait(full + s, (uint32_t)((c >> 1) & 1));   // the weight planes of this chunk have landed
       tc_fence_after();
-      const uint32_t a0 = sbase + s * lin::kStage, b0 = a0 + 3 * lin::kATile;
-      // (A plane, B plane): hi*hi, hi*mid, mid*hi, mid*mid, hi*lo, lo*hi
-      const int pa[6] = {0, 0, 1, 1, 0, 2}, pb[6] = {0, 1, 0, 1, 2, 0};
+      const uint32_t a0 = sbase + s * MapT::kStage, b0 = a0 + TERMS * lin::kATile;
+      // (A plane, B plane): hi*hi, hi*mid, mid*hi, mid*mid, hi*lo, lo*hi  /  hi*hi, hi*lo, lo*hi
+      using Pr = Products<TERMS>;
 #pragma unroll
       for (int k = 0; k < lin::kChunk / 16; ++k) {
 #pragma unroll
-        for (int t = 0; t < 6; ++t) {
-          const uint64_t ad = desc_k_major(a0 + pa[t] * lin::kATile + k * 2 * kCore, lin::kChunk);
-          const uint64_t bd = desc_k_major(b0 + pb[t] * lin::kBTile + k * 2 * kCore, lin::kChunk);
+        for (int t = 0; t < Pr::kN; ++t) {
+          const uint64_t ad = desc_k_major(a0 + Pr::a(t) * lin::kATile + k * 2 * kCore, lin::kChunk);
+          const uint64_t bd = desc_k_major(b0 + Pr::b(t) * lin::kBTile + k * 2 * kCore, lin::kChunk);
           umma_f16(acc, ad, bd, idesc, (c | k | t) != 0 ? 1u : 0u);
         }
       }
@@ -234,52 +284,57 @@ k_linear_tc(const float* __restrict__ x, int64_t ldx, const float* __restrict__ 
     mbar_wait(bar + (last & 1), (uint32_t)((last >> 1) & 1));
     tc_fence_after();
   }
-  // ---- epilogue: thread (warp w, lane) owns row (w % 4) * 32 + lane, columns (w / 4) * 128 .. + 128 of
-  // the accumulator. bias + activation, then the tile is staged in shared memory (row pitch n_cols + 4
-  // floats: the 16-byte stores of 8 lanes = 8 rows fall into distinct banks) and written out row by
-  // row, a warp covering 512 contiguous bytes per instruction.
+  // ---- epilogue, one 128-column half of the accumulator at a time: thread (warp w, lane) owns row
+  // (w % 4) * 32 + lane and columns (w / 4) * 64 .. + 64 of the half. bias + activation, then the half is
+  // staged in shared memory (the operand stages are free: every MMA is complete; row pitch 132 floats:
+  // the 16-byte stores of 8 lanes = 8 rows fall into distinct banks) and written out row by row, a
+  // warp covering 512 contiguous bytes per instruction.
   {
-    float* tile = reinterpret_cast<float*>(smem);      // the operand stages are free: every MMA is complete
-    const int pitch = n_cols + 4;
+    float* tile = reinterpret_cast<float*>(smem);
+    constexpr int pitch = lin::kHalf + 4;
     const int r = (warp & 3) * 32 + (tid & 31);
-    const int c_lo = (warp >> 2) * 128;
-#pragma unroll 1
-    for (int cb = 0; cb < 128; cb += 16) {
-      const int col = c_lo + cb;
-      if (col >= n_cols) break;                          // warp-uniform
-      float v[16];
-      tmem_ld16(tmem_addr(acc, warp, col), v);
-#pragma unroll
-      for (int j = 0; j < 16; ++j) {
-        const int n = n0 + col + j;
-        float o = v[j] + ((bias && n < n_out) ? __ldg(bias + n) : 0.0f);
-        if (act == 1) o = fmaxf(o, 0.0f);
-        v[j] = o;
-      }
-      float4* dst = reinterpret_cast<float4*>(tile + r * pitch + col);
-#pragma unroll
-      for (int q = 0; q < 4; ++q) dst[q] = make_float4(v[4 * q], v[4 * q + 1], v[4 * q + 2], v[4 * q + 3]);
-    }
-    __syncthreads();
     const int n_valid = min(n_cols, n_out - n0);         // real output columns of this CTA
     const int rows = (int)min((int64_t)lin::kRows, M - row0);
     const bool vec = (ldy & 3) == 0 && (n0 & 3) == 0 && (reinterpret_cast<uintptr_t>(y) & 15) == 0;
-    if (vec) {
-      const int q_per_row = n_valid >> 2;                // whole float4 groups
-      for (int i = tid; i < rows * q_per_row; i += lin::kThreads) {
-        const int rr = i / q_per_row, q = i - rr * q_per_row;
-        *reinterpret_cast<float4*>(y + (row0 + rr) * ldy + n0 + 4 * q) =
-            *reinterpret_cast<const float4*>(tile + rr * pitch + 4 * q);
+    for (int h0 = 0; h0 < n_cols; h0 += lin::kHalf) {
+      if (h0 > 0) __syncthreads();                       // the previous half has been written out
+#pragma unroll 1
+      for (int cb = 0; cb < 64; cb += 16) {
+        const int lc = (warp >> 2) * 64 + cb, col = h0 + lc;
+        if (col >= n_cols) break;                        // warp-uniform
+        float v[16];
+        tmem_ld16(tmem_addr(acc, warp, col), v);
+#pragma unroll
+        for (int j = 0; j < 16; ++j) {
+          const int n = n0 + col + j;
+          float o = v[j] + ((bias && n < n_out) ? __ldg(bias + n) : 0.0f);
+          if (act == 1) o = fmaxf(o, 0.0f);
+          v[j] = o;
+        }
+        float4* dst = reinterpret_cast<float4*>(tile + r * pitch + lc);
+#pragma unroll
+        for (int q = 0; q < 4; ++q) dst[q] = make_float4(v[4 * q], v[4 * q + 1], v[4 * q + 2], v[4 * q + 3]);
       }
-      const int tail = n_valid & 3;
-      for (int i = tid; i < rows * tail; i += lin::kThreads) {
-        const int rr = i / tail, cc = (n_valid & ~3) + (i - rr * tail);
-        y[(row0 + rr) * ldy + n0 + cc] = tile[rr * pitch + cc];
-      }
-    } else {
-      for (int i = tid; i < rows * n_valid; i += lin::kThreads) {
-        const int rr = i / n_valid, cc = i - rr * n_valid;
-        y[(row0 + rr) * ldy + n0 + cc] = tile[rr * pitch + cc];
+      __syncthreads();
+      const int w_valid = min(lin::kHalf, n_valid - h0);   // real columns of this half
+      if (w_valid <= 0) continue;                          // uniform
+      float* yh = y + n0 + h0;
+      if (vec) {
+        const int q_per_row = w_valid >> 2;                // whole float4 groups
+        for (int i = tid; i < rows * q_per_row; i += lin::kThreads) {
+          const int rr = i / q_per_row, q = i - rr * q_per_row;
+          *reinterpret_cast<float4*>(yh + (row0 + rr) * ldy + 4 * q) = *reinterpret_cast<const float4*>(tile + rr * pitch + 4 * q);
+        }
+        const int tail = w_valid & 3;
+        for (int i = tid; i < rows * tail; i += lin::kThreads) {
+          const int rr = i / tail, cc = (w_valid & ~3) + (i - rr * tail);
+          yh[(row0 + rr) * ldy + cc] = tile[rr * pitch + cc];
+        }
+      } else {
+        for (int i = tid; i < rows * w_valid; i += lin::kThreads) {
+          const int rr = i / w_valid, cc = i - rr * w_valid;
+          yh[(row0 + rr) * ldy + cc] = tile[rr * pitch + cc];
+        }
       }
     }
   }
@@ -303,11 +358,14 @@ constexpr int kChunk = 32;                         // rows per stage (the MMA K 
 constexpr int kWide = 256;                         // columns of a staged operand block
 constexpr int kThreads = 256;
 constexpr int kTile = kChunk * kWide * 2;          // 16 KB: one bf16 plane of one operand
-constexpr int kStage = 6 * kTile;                  // 96 KB
-constexpr int kBar = 2 * kStage;
-constexpr int kTmemPtr = kBar + 16;
-constexpr int kBytes = kTmemPtr + 16;
 constexpr uint32_t kTmemCols = 512;
+template <int TERMS>
+struct Map {
+  static constexpr int kStage = 2 * TERMS * kTile;   // 96 KB (3 terms) / 64 KB (2 terms)
+  static constexpr int kBar = 2 * kStage;
+  static constexpr int kTmemPtr = kBar + 16;
+  static constexpr int kBytes = kTmemPtr + 16;
+};
 }  // namespace ldw
 
 // rows [row_lo, row_lo + 32) x columns [c0, c0 + 256) of a row-major float32 matrix -> three bf16
@@ -334,6 +392,7 @@ __device__ __forceinline__ void fetch_rows(const float* __restrict__ src, int64_
     }
   }
 }
+template <int TERMS>
 __device__ __forceinline__ void store_rows(const float (&v)[4][8], uint8_t* tile, int tid, float* colsum = nullptr) {
   const int warp = tid >> 5, lane = tid & 31;
 #pragma unroll
@@ -344,21 +403,19 @@ __device__ __forceinline__ void store_rows(const float (&v)[4][8], uint8_t* tile
 #pragma unroll
       for (int j = 0; j < 8; ++j) colsum[j] += v[it][j];
     }
-    uint4 hi, mid, lo;
-    split8(v[it], hi, mid, lo);
-    st_chunk(tile, r, cc, ldw::kWide, hi);
-    st_chunk(tile + ldw::kTile, r, cc, ldw::kWide, mid);
-    st_chunk(tile + 2 * ldw::kTile, r, cc, ldw::kWide, lo);
+    split_store<TERMS>(v[it], tile, ldw::kTile, r, cc, ldw::kWide);
   }
 }
 
+template <int TERMS>
 __global__ void __launch_bounds__(ldw::kThreads, 1)
 k_linear_dw_tc(const float* __restrict__ dy, int64_t ldy, const float* __restrict__ mask, int64_t ldm,
                const float* __restrict__ x, int64_t ldx, const float* __restrict__ x2, int64_t ldx2, int k_split,
                int64_t M, int n_out, int k_in, float* __restrict__ dw, float* __restrict__ db) {
   extern __shared__ __align__(128) uint8_t smem[];
-  uint64_t* bar = reinterpret_cast<uint64_t*>(smem + ldw::kBar);
-  uint32_t* tmem_ptr = reinterpret_cast<uint32_t*>(smem + ldw::kTmemPtr);
+  using MapT = ldw::Map<TERMS>;
+  uint64_t* bar = reinterpret_cast<uint64_t*>(smem + MapT::kBar);
+  uint32_t* tmem_ptr = reinterpret_cast<uint32_t*>(smem + MapT::kTmemPtr);
   const int tid = threadIdx.x, warp = tid >> 5;
   // this CTA's slab of 32-row chunks
   const int64_t chunks = (M + ldw::kChunk - 1) / ldw::kChunk;
@@ -399,7 +456,7 @@ k_linear_dw_tc(const float* __restrict__ dy, int64_t ldy, const float* __restric
   int it = 0;
   for (int64_t c = c_lo; c < c_hi; ++c, ++it) {
     const int s = it & 1;
-    uint8_t* stage = smem + s * ldw::kStage;
+    uint8_t* stage = smem + s * MapT::kStage;
     float cdy[4][8], cxx[4][8];
 #pragma unroll
     for (int a = 0; a < 4; ++a)
@@ -410,24 +467,24 @@ k_linear_dw_tc(const float* __restrict__ dy, int64_t ldy, const float* __restric
       fetch_rows(x, ldx, x2, ldx2, k_split, nullptr, 0, (c + 1) * ldw::kChunk, M, k0, k_in, vx, tid, vxx);
     }
     if (it >= 2) mbar_wait(bar + s, (uint32_t)(((it >> 1) - 1) & 1));
-    store_rows(cdy, stage, tid, want_db ? colsum : nullptr);
-    store_rows(cxx, stage + 3 * ldw::kTile, tid);
+    store_rows<TERMS>(cdy, stage, tid, want_db ? colsum : nullptr);
+    store_rows<TERMS>(cxx, stage + TERMS * ldw::kTile, tid);
     fence_async_smem();
     tc_fence_before();
     __syncthreads();
     if (warp == 0) {
       tc_fence_after();
-      const uint32_t a0 = sbase + s * ldw::kStage, b0 = a0 + 3 * ldw::kTile;
-      const int pa[6] = {0, 0, 1, 1, 0, 2}, pb[6] = {0, 1, 0, 1, 2, 0};
+      const uint32_t a0 = sbase + s * MapT::kStage, b0 = a0 + TERMS * ldw::kTile;
+      using Pr = Products<TERMS>;
       for (int h = 0; h < m_halves; ++h) {
 #pragma unroll
         for (int k = 0; k < ldw::kChunk / 16; ++k) {
 #pragma unroll
-          for (int t = 0; t < 6; ++t) {
+          for (int t = 0; t < Pr::kN; ++t) {
             // two 8-row groups per K step; columns 128 h .. of dY are 16 h core matrices further on
             const uint32_t koff = k * 2 * (ldw::kWide / 8) * kCore;
-            const uint64_t ad = desc_mn_major(a0 + pa[t] * ldw::kTile + koff + h * 16 * kCore, ldw::kWide);
-            const uint64_t bd = desc_mn_major(b0 + pb[t] * ldw::kTile + koff, ldw::kWide);
+            const uint64_t ad = desc_mn_major(a0 + Pr::a(t) * ldw::kTile + koff + h * 16 * kCore, ldw::kWide);
+            const uint64_t bd = desc_mn_major(b0 + Pr::b(t) * ldw::kTile + koff, ldw::kWide);
             umma_f16(acc + h * 256, ad, bd, idesc, (it | k | t) != 0 ? 1u : 0u);
           }
         }
@@ -480,22 +537,30 @@ static inline cudaStream_t S(void* s) { return reinterpret_cast<cudaStream_t>(s)
 
 extern "C" {
 
-int atmonr_linear_prep(const float* w, int n_out, int k_in, int transpose, void* planes, void* stream) {
+#define ATM_TERMS_DISPATCH(terms, CALL) \
+  if ((terms) == 3) { CALL(3); } else { CALL(2); }
+
+int atmonr_linear_prep(const float* w, int n_out, int k_in, int transpose, int terms, void* planes, void* stream) {
   ATM_REQUIRE(w && planes, "atmonr_linear_prep", "null pointer");
   ATM_REQUIRE(n_out > 0 && k_in > 0, "atmonr_linear_prep", "empty matrix");
+  ATM_REQUIRE(terms == 2 || terms == 3, "atmonr_linear_prep", "terms must be 2 or 3");
   const int n_tiles = (n_out + lin::kCols - 1) / lin::kCols, k_chunks = (k_in + lin::kChunk - 1) / lin::kChunk;
   const int64_t total = (int64_t)n_tiles * lin::kCols * k_chunks * 4;
-  k_linear_prep<<<grid_for(total, 256), 256, 0, S(stream)>>>(w, n_out, k_in, transpose, k_chunks, n_tiles,
-                                                             reinterpret_cast<uint8_t*>(planes));
+#define CALL(T) \
+  k_linear_prep<T><<<grid_for(total, 256), 256, 0, S(stream)>>>(w, n_out, k_in, transpose, k_chunks, n_tiles, \
+                                                                reinterpret_cast<uint8_t*>(planes))
+  ATM_TERMS_DISPATCH(terms, CALL)
+#undef CALL
   ATM_CHECK_LAUNCH("atmonr_linear_prep");
   return 0;
 }
 
 int atmonr_linear_fwd_tc(const float* x, int64_t ldx, const float* x2, int64_t ldx2, int k_split, const float* mask,
                          int64_t ldm, const void* planes, const float* bias, int64_t M, int n_out, int k_in, int act,
-                         float* y, int64_t ldy, void* stream) {
+                         int terms, float* y, int64_t ldy, void* stream) {
   ATM_REQUIRE(M >= 0 && n_out > 0 && k_in > 0, "atmonr_linear_fwd_tc", "bad shape");
   ATM_REQUIRE(act == 0 || act == 1, "atmonr_linear_fwd_tc", "act must be 0 (none) or 1 (ReLU)");
+  ATM_REQUIRE(terms == 2 || terms == 3, "atmonr_linear_fwd_tc", "terms must be 2 or 3");
   if (M == 0) return 0;
   ATM_REQUIRE(x && planes && y, "atmonr_linear_fwd_tc", "null pointer");
   if (!x2) k_split = k_in;
@@ -504,21 +569,27 @@ int atmonr_linear_fwd_tc(const float* x, int64_t ldx, const float* x2, int64_t l
   ATM_REQUIRE(ldx >= k_split && (!x2 || ldx2 >= k_in - k_split) && ldy >= n_out && (!mask || ldm >= k_in),
               "atmonr_linear_fwd_tc", "row stride smaller than the row");
   ATM_REQUIRE((M + lin::kRows - 1) / lin::kRows < (1ll << 31), "atmonr_linear_fwd_tc", "too many rows");
-  cudaError_t e = cudaFuncSetAttribute(k_linear_tc, cudaFuncAttributeMaxDynamicSharedMemorySize, lin::kBytes);
-  if (e != cudaSuccess) return fail("atmonr_linear_fwd_tc", cudaGetErrorString(e));
   const int n_tiles = (n_out + lin::kCols - 1) / lin::kCols, k_chunks = (k_in + lin::kChunk - 1) / lin::kChunk;
   dim3 grid((unsigned)((M + lin::kRows - 1) / lin::kRows), (unsigned)n_tiles);
-  k_linear_tc<<<grid, lin::kThreads, lin::kBytes, S(stream)>>>(x, ldx, x2, ldx2, k_split, mask, ldm,
-                                                               reinterpret_cast<const uint8_t*>(planes), bias, M, n_out,
-                                                               k_in, k_chunks, act, y, ldy);
+#define CALL(T)                                                                                                        \
+  {                                                                                                                    \
+    cudaError_t e = cudaFuncSetAttribute(k_linear_tc<T>, cudaFuncAttributeMaxDynamicSharedMemorySize, lin::Map<T>::kBytes); \
+    if (e != cudaSuccess) return fail("atmonr_linear_fwd_tc", cudaGetErrorString(e));                                  \
+    k_linear_tc<T><<<grid, lin::kThreads, lin::Map<T>::kBytes, S(stream)>>>(                                           \
+        x, ldx, x2, ldx2, k_split, mask, ldm, reinterpret_cast<const uint8_t*>(planes), bias, M, n_out, k_in, k_chunks, \
+        act, y, ldy);                                                                                                  \
+  }
+  ATM_TERMS_DISPATCH(terms, CALL)
+#undef CALL
   ATM_CHECK_LAUNCH("atmonr_linear_fwd_tc");
   return 0;
 }
 
 int atmonr_linear_dw_tc(const float* dy, int64_t ldy, const float* mask, int64_t ldm, const float* x, int64_t ldx,
-                        const float* x2, int64_t ldx2, int k_split, int64_t M, int n_out, int k_in, float* dw,
-                        float* db, void* stream) {
+                        const float* x2, int64_t ldx2, int k_split, int64_t M, int n_out, int k_in, int terms,
+                        float* dw, float* db, void* stream) {
   ATM_REQUIRE(M >= 0 && n_out > 0 && k_in > 0, "atmonr_linear_dw_tc", "bad shape");
+  ATM_REQUIRE(terms == 2 || terms == 3, "atmonr_linear_dw_tc", "terms must be 2 or 3");
   if (M == 0) return 0;
   ATM_REQUIRE(dy && x && dw, "atmonr_linear_dw_tc", "null pointer");
   if (!x2) k_split = k_in;
@@ -526,8 +597,6 @@ int atmonr_linear_dw_tc(const float* dy, int64_t ldy, const float* mask, int64_t
               "k_split must be a multiple of 8 inside (0, k_in]");
   ATM_REQUIRE(ldy >= n_out && ldx >= k_split && (!x2 || ldx2 >= k_in - k_split) && (!mask || ldm >= n_out),
               "atmonr_linear_dw_tc", "row stride smaller than the row");
-  cudaError_t e = cudaFuncSetAttribute(k_linear_dw_tc, cudaFuncAttributeMaxDynamicSharedMemorySize, ldw::kBytes);
-  if (e != cudaSuccess) return fail("atmonr_linear_dw_tc", cudaGetErrorString(e));
   int dev = 0, sms = 0;
   if (cudaGetDevice(&dev) != cudaSuccess || cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess)
     return fail("atmonr_linear_dw_tc", "cannot query the device");
@@ -537,8 +606,15 @@ int atmonr_linear_dw_tc(const float* dy, int64_t ldy, const float* mask, int64_t
   if (slabs < 1) slabs = 1;
   if (slabs > chunks) slabs = chunks;
   dim3 grid((unsigned)slabs, (unsigned)ny, (unsigned)nz);
-  k_linear_dw_tc<<<grid, ldw::kThreads, ldw::kBytes, S(stream)>>>(dy, ldy, mask, ldm, x, ldx, x2, ldx2, k_split, M, n_out,
-                                                                  k_in, dw, db);
+#define CALL(T)                                                                                                           \
+  {                                                                                                                       \
+    cudaError_t e = cudaFuncSetAttribute(k_linear_dw_tc<T>, cudaFuncAttributeMaxDynamicSharedMemorySize, ldw::Map<T>::kBytes); \
+    if (e != cudaSuccess) return fail("atmonr_linear_dw_tc", cudaGetErrorString(e));                                      \
+    k_linear_dw_tc<T><<<grid, ldw::kThreads, ldw::Map<T>::kBytes, S(stream)>>>(dy, ldy, mask, ldm, x, ldx, x2, ldx2,      \
+                                                                              k_split, M, n_out, k_in, dw, db);           \
+  }
+  ATM_TERMS_DISPATCH(terms, CALL)
+#undef CALL
   ATM_CHECK_LAUNCH("atmonr_linear_dw_tc");
   return 0;
 }

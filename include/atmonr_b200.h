@@ -339,21 +339,25 @@ int atmonr_append_heights(const float* pts, int64_t M, double scale, const doubl
  *   B is given as `planes`, produced once per step by atmonr_linear_prep from w (n_out, k_in)
  *   row-major, or, with transpose != 0, from the transpose of w (k_in, n_out) row-major (the
  *   input-gradient product dX = dY * W is this call on the planes of W^T). planes:
- *       ceil(n_out / 256) * ceil(k_in / 32) * 3 * 16384 bytes.
+ *       ceil(n_out / 256) * ceil(k_in / 32) * terms * 16384 bytes.
  *   bias (n_out) may be NULL; act: 0 none, 1 ReLU.
+ *   terms: 3 = the float32-exact flavour above (six products); 2 = two bf16 terms per operand and the
+ *   three products hi*hi + hi*lo + lo*hi (product error ~2^-16 relative: half the tensor-core work,
+ *   two CTAs per SM); the planes must have been prepared with the same `terms`.
  * atmonr_linear_dw_tc:   dW (n_out, k_in) += dY' (M, n_out)^T * X (M, k_in)   (dW contiguous,
  *   zeroed or pre-loaded by the caller; mask (M, n_out) as above, applied to dY; x / x2 / k_split
  *   as above). db (n_out, may be NULL) += column sums of dY' (the bias gradient, accumulated by
  *   the threads that stage dY). */
-int atmonr_linear_prep(const float* w, int n_out, int k_in, int transpose, void* planes,
+int atmonr_linear_prep(const float* w, int n_out, int k_in, int transpose, int terms, void* planes,
                        void* stream);
 int atmonr_linear_fwd_tc(const float* x, int64_t ldx, const float* x2, int64_t ldx2, int k_split,
                          const float* mask, int64_t ldm, const void* planes, const float* bias,
-                         int64_t M, int n_out, int k_in, int act, float* y, int64_t ldy,
+                         int64_t M, int n_out, int k_in, int act, int terms, float* y, int64_t ldy,
                          void* stream);
 int atmonr_linear_dw_tc(const float* dy, int64_t ldy, const float* mask, int64_t ldm,
                         const float* x, int64_t ldx, const float* x2, int64_t ldx2, int k_split,
-                        int64_t M, int n_out, int k_in, float* dw, float* db, void* stream);
+                        int64_t M, int n_out, int k_in, int terms, float* dw, float* db,
+                        void* stream);
 
 /* ---- tensor-core self test -------------------------------------------------------------------
  * One 128-row tile through the three tcgen05 operand configurations of the fused kernels.

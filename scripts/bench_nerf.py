@@ -31,7 +31,8 @@ def main() -> None:
     rays = int(os.environ.get("ATMONR_NERF_RAYS", "4096"))
     ds = get_dataset(bench.nerf_config()["dataset"], "synthetic:H=64,W=64,seed=0")
     out = bench.gpu_nerf_rate(ds, torch.device("cuda", 0), rays=rays, steps=10)
-    out["dense_layers"] = "tcgen05 bf16x3 split (atmonr_linear_fwd_tc / _dw_tc)" if mn.DENSE_IMPL == "tc" \
+    from atmonr.native import ops
+    out["dense_layers"] = f"tcgen05, {ops.LINEAR_TERMS} bf16 terms per operand (atmonr_linear_fwd_tc / _dw_tc)" if mn.DENSE_IMPL == "tc" \
         else "library float32 GEMMs"
     flop = 922e6 * rays          # 922 MFLOP per ray, forward + backward
     out["tflops_fp32_equivalent"] = flop / (out["ms_per_step"] * 1e-3) / 1e12

@@ -34,7 +34,7 @@ def _oracle_cdf(w):
 def test_sample_pdf_bin_indices_are_exact_and_gradients_match(b, nc, nf):
     """samplers.py:72-101. Bin indices: EXACTLY searchsorted(cdf, u, right=True) on the CDF the kernel
     built (north_star: bit-exact sample bin indices given identical uniforms and CDF); that CDF is the
-    oracle's to one float32 ulp (torch's CPU sum / cumsum orders are not reproducible across vector
+    oracle's to a few float32 ulps (torch's CPU sum / cumsum orders are not reproducible across vector
     widths), and wherever u is further than that from a CDF edge the indices equal the oracle's.
     Gradients w.r.t. the coarse weights (through the CDF) and the coarse distances: the oracle's autograd."""
     L, ops = _ops()
@@ -53,9 +53,9 @@ def test_sample_pdf_bin_indices_are_exact_and_gradients_match(b, nc, nf):
     assert torch.allclose(z.detach().cpu(), z_o.detach(), atol=1e-5)
     assert torch.equal(inds, torch.searchsorted(cdf, u.cuda().contiguous(), right=True))
     cdf_o = _oracle_cdf(w)
-    assert float((cdf.cpu() - cdf_o).abs().max()) <= 1.2e-7
+    assert float((cdf.cpu() - cdf_o).abs().max()) <= 4e-7      # a few ulps: the total's last bit moves every entry
     gap = (u[:, :, None] - cdf_o[:, None, :]).abs().min(dim=2)[0]
-    clear = gap > 3e-7
+    clear = gap > 1e-6
     assert float(clear.float().mean()) > 0.99 and torch.equal(inds.cpu()[clear], inds_o[clear])
     gz = torch.randn(b, nc + nf, generator=g)
     (z_o * gz).sum().backward()

@@ -4,7 +4,10 @@ matrix products, torch autograd and the default (library GEMM) NeRF pipeline.
 Tolerances: every product is required to be as close to the float64 result as max(4e-6 of the output
 scale [2e-5 for the row-reduction of the weight gradient], twice the error of the library float32
 product of the same operands): "float32-grade", not a fixed ulp count, because the rounding of a K-
-(or M-) term float32 sum grows with the number of terms (see _close)."""
+(or M-) term float32 sum grows with the number of terms (see _close). That is the three-term flavour
+(terms = 3, six partial products). The two-term flavour the pipelines train with (terms = 2: three partial
+products, operands carried to 16 significand bits) is held to 5e-5 of the output scale per product (2e-4
+for the weight gradient), and the whole NeRF step to 3e-4 on the colour maps, inside north_star's 1e-3."""
 
 import os
 
@@ -34,12 +37,19 @@ SHAPES = [  # (M, k_in, n_out, relu, bias): the layer shapes of configs/nerf.jso
 ]
 
 
+@pytest.fixture(params=[3, 2], ids=["terms3", "terms2"])
+def terms(request, monkeypatch):
+    from atmonr.native import ops
+    monkeypatch.setattr(ops, "LINEAR_TERMS", request.param)
+    return request.param
+
+
 def _ref(x, w, b, relu):
     y = x.double() @ w.double().t() + (0 if b is None else b.double())
     return torch.relu(y) if relu else y
 
 
-def _close(got, want64, lib32, what):
+def _close(got, want64, lib32, what, terms=3):
     """float32-grade: within max(tol, 2 x the library float32 product's error) of the float64 result,
     relative to the output scale. tol = 4e-6 for chains of up to ~100 tensor-core accumulations (K <= 332:
     21 K-steps x 6 products); the TMEM accumulator TRUNCATES each float32 addition (measured: the error
@@ -49,11 +59,13 @@ def _close(got, want64, lib32, what):
     err = float((got.double() - want64).abs().max()) / scale
     lib = float((lib32.double() - want64).abs().max()) / scale
     tol = 2e-5 if what in ("weight gradient", "bias gradient") else 4e-6
+    if terms == 2 and what != "bias gradient":   # (the bias gradient is a float32 column sum, no split involved)
+        tol = 2e-4 if what == "weight gradient" else 5e-5
     assert err <= max(tol, 2 * lib), (what, err, lib)
 
 
 @pytest.mark.parametrize("m,k,n,relu,bias", SHAPES)
-def test_linear_forward_matches_float64(m, k, n, relu, bias):
+def test_linear_forward_matches_float64(m, k, n, relu, bias, terms):
     from atmonr.native import ops
     torch.backends.cuda.matmul.allow_tf32 = False
     g = torch.Generator().manual_seed(m + k + n)
@@ -63,24 +75,25 @@ def test_linear_forward_matches_float64(m, k, n, relu, bias):
     want = _ref(x, w, b, relu)
     got = ops.linear_forward(x, w, b, relu)
     lib = x @ w.t() + (0 if b is None else b)
-    _close(got, want, torch.relu(lib) if relu else lib, "forward")
+    _close(got, want, torch.relu(lib) if relu else lib, "forward", terms)
     # input-gradient form: dY (m, n) * W (n, k) through the planes of W^T
     dy = torch.randn(m, n, generator=g).cuda()
     dx = ops.linear_forward(dy, w, None, False, transpose=True)
-    _close(dx, dy.double() @ w.double(), dy @ w, "input gradient")
+    _close(dx, dy.double() @ w.double(), dy @ w, "input gradient", terms)
     # the same with the ReLU derivative of the layer's output applied while dY is staged
     keep = (got > 0) if relu else torch.ones_like(got, dtype=torch.bool)
     dx = ops.linear_forward(dy, w, None, False, transpose=True, mask=got if relu else None)
-    _close(dx, (dy * keep).double() @ w.double(), (dy * keep) @ w, "masked input gradient")
+    _close(dx, (dy * keep).double() @ w.double(), (dy * keep) @ w, "masked input gradient", terms)
     # weight gradient: a reduction over all rows (split over the CTAs, float32 REDs at the end)
     dw, db = ops.linear_weight_grad(dy, x, mask=got if relu else None, want_bias=True)
     assert dw.shape == (n, k) and db.shape == (n,)
-    _close(dw, (dy * keep).double().t() @ x.double(), (dy * keep).t() @ x, "weight gradient")
-    _close(db, (dy * keep).double().sum(0), (dy * keep).sum(0), "bias gradient")
+    _close(dw, (dy * keep).double().t() @ x.double(), (dy * keep).t() @ x, "weight gradient", terms)
+    _close(db, (dy * keep).double().sum(0), (dy * keep).sum(0), "bias gradient", terms)
 
 
-def test_linear_on_a_column_slice_and_autograd():
+def test_linear_on_a_column_slice_and_autograd(terms):
     from atmonr.native import ops
+    ftol, gtol = (4e-6, 1e-5) if terms == 3 else (5e-5, 1e-4)
     g = torch.Generator().manual_seed(0)
     wide = torch.randn(700, 100, generator=g).cuda()
     x = wide[:, :76]                                   # models/nerf.py: x_pos = x[:, :pos_channels]
@@ -92,16 +105,17 @@ def test_linear_on_a_column_slice_and_autograd():
     xd, wd, bd = (t.detach().double().requires_grad_() for t in (x, w, b))
     yd = torch.relu(xd @ wd.t() + bd)
     yd.backward(torch.ones_like(yd))
-    assert float((y.detach().double() - yd.detach()).abs().max()) <= 4e-6 * float(yd.detach().abs().max())
+    assert float((y.detach().double() - yd.detach()).abs().max()) <= ftol * float(yd.detach().abs().max())
     same = ops.linear_forward(x, w, b, True)           # strided input, no copy
     assert torch.equal(same, y.detach())
     for got, want in ((xr.grad, xd.grad), (w.grad, wd.grad), (b.grad, bd.grad)):
-        assert float((got.double() - want).abs().max()) <= 1e-5 * float(want.abs().max())
+        assert float((got.double() - want).abs().max()) <= gtol * float(want.abs().max())
 
 
-def test_linear_on_two_input_blocks():
+def test_linear_on_two_input_blocks(terms):
     """fc6 / fc10: relu(fc(cat([x, x2]))) with the concatenation read in place, forward and backward."""
     from atmonr.native import ops
+    ftol, gtol = (4e-6, 1e-5) if terms == 3 else (5e-5, 1e-4)
     g = torch.Generator().manual_seed(2)
     for k1, k2, n in ((256, 76, 256), (256, 24, 128), (20, 12, 8)):   # the last one is not a multiple of 8: cat fallback
         feat = torch.randn(900, k1 + 4, generator=g).cuda()
@@ -115,13 +129,13 @@ def test_linear_on_two_input_blocks():
         d = [t.detach().double().requires_grad_() for t in (x1, x2, w, b)]
         yd = torch.relu(torch.cat([d[0], d[1]], 1) @ d[2].t() + d[3])
         yd.backward(gy.double())
-        assert float((y.detach().double() - yd.detach()).abs().max()) <= 4e-6 * float(yd.detach().abs().max())
+        assert float((y.detach().double() - yd.detach()).abs().max()) <= ftol * float(yd.detach().abs().max())
         for got, want in zip((x1.grad, x2.grad, w.grad, b.grad), (t.grad for t in d)):
             assert got.shape == want.shape
-            assert float((got.double() - want).abs().max()) <= 1e-5 * float(want.abs().max())
+            assert float((got.double() - want).abs().max()) <= gtol * float(want.abs().max())
 
 
-def test_nerf_pipeline_with_tensor_core_layers(monkeypatch):
+def test_nerf_pipeline_with_tensor_core_layers(monkeypatch, terms):
     """configs/nerf.json forward + loss + backward on the tensor-core layers against library GEMMs:
     same parameters, same draws (eval mode: no density noise; the sampler's Philox stream is keyed by
     the step counter, which both runs start from zero)."""
@@ -148,7 +162,10 @@ def test_nerf_pipeline_with_tensor_core_layers(monkeypatch):
         grads = torch.cat([p.grad.flatten() for net in pipe.nerf.values() for p in net.parameters()])
         outs[mode] = (res["color_map_fine"].detach(), res["color_map_coarse"].detach(), float(loss), grads)
     a, b = outs["lib"], outs["tc"]
+    ctol, gtol = (1e-4, 1e-3) if terms == 3 else (3e-4, 3e-3)
     for x, y in ((a[0], b[0]), (a[1], b[1])):
-        assert float((x - y).abs().max()) <= 1e-4 * float(x.abs().max())      # north_star: 1e-3 relative
-    assert abs(a[2] - b[2]) <= 1e-4 * abs(a[2])
-    assert float((a[3] - b[3]).abs().max()) <= 1e-3 * float(a[3].abs().max())
+        assert float((x - y).abs().max()) <= ctol * float(x.abs().max())      # north_star: 1e-3 relative
+    assert abs(a[2] - b[2]) <= ctol * abs(a[2])
+    assert float((a[3] - b[3]).abs().max()) <= gtol * float(a[3].abs().max())
+    print(f"terms={terms}: colour map rel err {float((a[0] - b[0]).abs().max() / a[0].abs().max()):.2e}, "
+          f"loss rel err {abs(a[2] - b[2]) / abs(a[2]):.2e}, gradient rel err {float((a[3] - b[3]).abs().max() / a[3].abs().max()):.2e}")
