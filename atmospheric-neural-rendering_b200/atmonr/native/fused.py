@@ -57,6 +57,34 @@ class NGPState:
     last: dict = field(default_factory=dict)
     pending: list = field(default_factory=list)   # sample points of announced batches (schedule_prefetch)
     side_stream: torch.cuda.Stream | None = None
+    grad_bufs: list | None = None                 # persistent gradient buffers (see _gradient_buffers)
+
+
+# Persistent gradient buffers: data_ptr -> [clean]. The backward accumulates into buffers that live as long
+# as the pipeline; FusedAdamW recognises them by address and asks the AdamW kernel to zero each gradient in
+# the pass that consumes it (atmonr_adamw_step, zero_grad = 1), so no 191 MB memset runs per step. A buffer
+# is only handed out while it is known to be zero ("clean"); otherwise (two backward passes without an
+# optimizer step in between, a foreign optimizer) fresh zeroed tensors are used, exactly as before.
+PERSISTENT_GRADS: dict[int, list] = {}
+
+
+def _gradient_buffers(st: NGPState, sizes, dev):
+    if st.grad_bufs is None or any(b.numel() != n or b.device != dev for b, n in zip(st.grad_bufs, sizes)):
+        for b in st.grad_bufs or []:
+            PERSISTENT_GRADS.pop(b.data_ptr(), None)
+        st.grad_bufs = [torch.zeros(n, device=dev, dtype=_f32) for n in sizes]
+        for b in st.grad_bufs:
+            PERSISTENT_GRADS[b.data_ptr()] = [True]
+    out = []
+    for b, n in zip(st.grad_bufs, sizes):
+        flag = PERSISTENT_GRADS[b.data_ptr()]
+        if flag[0]:
+            flag[0] = False
+            # a fresh alias: autograd adopts a gradient it holds the only reference to without copying it
+            out.append(b.view(-1))
+        else:
+            out.append(torch.zeros(n, device=dev, dtype=_f32))
+    return out
 
 
 def _sample_seed(st: NGPState) -> int:
@@ -210,12 +238,7 @@ class NGPRenderFn(torch.autograd.Function):
             dcolor, dsigma, dcs = ops.composite_backward(
                 z, color_raw.view(b, n, 4), sigma_raw.view(b, n, 1), cs_raw, catmo, tsurf, d_atmo, d_surf,
                 st.z_scale, relu=True, grad_absmax=absmax)
-        n_t, n_pw, n_dw, n_s, n_sw = ctx.sizes
-        d_table = torch.zeros(n_t, device=dev, dtype=_f32)
-        d_pw = torch.zeros(n_pw, device=dev, dtype=_f32)
-        d_dw = torch.zeros(n_dw, device=dev, dtype=_f32)
-        d_s = torch.zeros(n_s, device=dev, dtype=_f32)
-        d_sw = torch.zeros(n_sw, device=dev, dtype=_f32)
+        d_table, d_pw, d_dw, d_s, d_sw = _gradient_buffers(st, ctx.sizes, dev)
         if FIELD_IMPL == "simt":
             L.call("atmonr_ngp_field_bwd", C.byref(st.grid3), L.ptr(t16), C.byref(st.pos_mlp), L.ptr(pw16),
                    C.byref(st.dir_mlp), L.ptr(dw16), L.ptr(x01), L.ptr(direction), L.ptr(dsigma), L.ptr(dcolor), b, n,

@@ -16,6 +16,7 @@ import torch
 from torch.optim import Optimizer
 
 from atmonr.native import ops
+from atmonr.native.fused import PERSISTENT_GRADS
 from atmonr.native.modules import shadow_of
 
 
@@ -43,7 +44,11 @@ class FusedAdamW(Optimizer):
                     state["exp_avg_sq"] = torch.zeros_like(p)
                 state["step"] += 1
                 grad = p.grad if p.grad.is_contiguous() else p.grad.contiguous()
+                # a persistent gradient buffer of the fused backward: zeroed by the kernel that consumes it
+                flag = PERSISTENT_GRADS.get(grad.data_ptr())
                 ops.adamw_step(p.data, grad, state["exp_avg"], state["exp_avg_sq"], shadow_of(p),
                                group["lr"], beta1, beta2, group["eps"], group["weight_decay"],
-                               int(state["step"].item()), grad_scale=self.grad_scale)
+                               int(state["step"].item()), grad_scale=self.grad_scale, zero_grad=flag is not None)
+                if flag is not None:
+                    flag[0] = True
         return loss

@@ -230,7 +230,9 @@ def gpu_nerf_rate(dataset, dev, rays: int = 4096, steps: int = 5) -> dict:
     peaks = _load_json("MEASURED_PEAKS.json")
     tpeak = float(peaks.get("bf16_tflops_sustained", 1400.0))
     flop32 = 922e6 * rays                      # 922 MFLOP per ray, forward + backward, float32-equivalent
-    products = 6 if _nerf_dense_impl() == "tc" else 1
+    from atmonr.native import ops as _ops
+    terms = _ops.LINEAR_TERMS
+    products = {3: 6, 2: 3}[terms] if _nerf_dense_impl() == "tc" else 1
     tf = flop32 * products / (ms * 1e-3) / 1e12    # per GPU
     c = _load_json("profiles", "ncu_counters.json")
     roof = {"bound": "tensor", "achieved": tf, "peak": tpeak, "unit": "TFLOP/s", "frac": tf / tpeak,
@@ -239,11 +241,11 @@ def gpu_nerf_rate(dataset, dev, rays: int = 4096, steps: int = 5) -> dict:
             "tensor_pipe_pct_ncu": {k: c[k].get("tensor_pipe_pct") for k in ("atmonr_linear_fwd_tc", "atmonr_linear_dw_tc") if k in c},
             "traffic": None,
             "note": "whole NeRF step (MLP + sampling + compositing + Adam) against the dense bf16 tensor peak: each float32 "
-                    "product is six bf16 tensor-core products (three-term split of both operands), counted as executed"}
+                    f"product is {products} bf16 tensor-core products ({terms}-term split of both operands), counted as executed"}
     return {"value": world * rays * 1e3 / ms, "unit": UNIT, "rays_per_step_per_gpu": rays, "n_gpus": world, "ms_per_step": ms,
             "roofline": roof,
             "note": "configs/nerf.json, coarse 64 + fine 192 samples, hidden 256; MLP layers are "
-                    + ("tcgen05 bf16x3-split products (csrc/linear_tc.cu)" if _nerf_dense_impl() == "tc"
+                    + (f"tcgen05 products of {terms}-term bf16 splits (csrc/linear_tc.cu)" if _nerf_dense_impl() == "tc"
                        else "cuBLAS fp32 GEMMs (cross-check)")}
 
 

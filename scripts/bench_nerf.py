@@ -30,7 +30,7 @@ def main() -> None:
         mn.DENSE_IMPL = "library"
     rays = int(os.environ.get("ATMONR_NERF_RAYS", "4096"))
     ds = get_dataset(bench.nerf_config()["dataset"], "synthetic:H=64,W=64,seed=0")
-    out = bench.gpu_nerf_rate(ds, torch.device("cuda", 0), rays=rays, steps=10)
+    out = bench.gpu_nerf_rate(ds, torch.device("cuda", 0), rays=rays, steps=int(os.environ.get("ATMONR_NERF_STEPS", "10")))
     from atmonr.native import ops
     out["dense_layers"] = f"tcgen05, {ops.LINEAR_TERMS} bf16 terms per operand (atmonr_linear_fwd_tc / _dw_tc)" if mn.DENSE_IMPL == "tc" \
         else "library float32 GEMMs"
