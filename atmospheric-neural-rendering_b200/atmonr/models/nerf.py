@@ -5,8 +5,9 @@ position at layer 6, a density head on layer 9 (with unit Gaussian noise while t
 direction-conditioned colour head. The layers are torch.nn.Linear modules, so parameter names
 (`fc1`..`fc11`) match the reference and checkpoints interchange. On the device forward, input
 gradient and weight gradient of every layer run on tcgen05 (csrc/linear_tc.cu: float32 operands
-split into three bfloat16 terms, six partial products, float32 accumulation in TMEM; validated on a
-B200 in round 2, tests/test_zz_gpu_linear_tc.py). `DENSE_IMPL = "library"` switches the layers to
+split into bfloat16 terms, partial products accumulated in float32 in TMEM; validated on a B200 in
+round 2, tests/test_zz_gpu_linear_tc.py), the whole network as one autograd node with a hand-written
+backward chain (atmonr.native.nerf_mlp). `DENSE_IMPL = "library"` switches the layers to
 torch's float32 GEMMs: used by the tests and by scripts/bench_nerf.py as the cross-check, never by
 the pipelines.
 """
@@ -61,6 +62,13 @@ class AtmoNeRF(nn.Module):
 
     def forward(self, x: torch.Tensor):
         """models/nerf.py:75-93 -> (colour in (0,1), density >= 0)."""
+        if x.is_cuda and DENSE_IMPL == "tc":
+            # the whole MLP as one autograd node over the tensor-core products (atmonr.native.nerf_mlp)
+            from atmonr.native.nerf_mlp import NerfMlpFn
+            noise = torch.randn((x.shape[0], self.volume_channels), device=x.device) if self.training else None
+            params = [t for k in range(1, 12) for t in (getattr(self, f"fc{k}").weight, getattr(self, f"fc{k}").bias)]
+            rgb, sigma = NerfMlpFn.apply(x, noise, self.pos_channels, self.hidden_dim, *params)
+            return torch.sigmoid(rgb), F.relu(sigma)
         x_pos, d = x[:, : self.pos_channels], x[:, self.pos_channels:]
         feat, sigma = self.forward_pos_only(x_pos)
         hid = self._layer(10, feat[:, : self.hidden_dim], True, x2=d)

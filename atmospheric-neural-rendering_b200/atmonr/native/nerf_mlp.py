@@ -1,0 +1,117 @@
+"""The AtmoNeRF MLP (reference: src/atmonr/models/nerf.py:48-93) as ONE autograd node over the tcgen05
+dense-layer kernels (csrc/linear_tc.cu).
+
+Forward: the eleven layers in order, bias + ReLU in each product's epilogue, the two concatenations
+(fc6: [h5 | x_pos], fc10: [feat | x_dir]) read in place. Backward: the chain written out by hand, so that
+
+  * every input-gradient product writes the PRE-activation gradient of the layer below it (the ReLU
+    derivative of that layer's output is applied in the product's epilogue, `out_mask`): no product reads
+    a mask in its main loop (measured round 2: with the mask staged next to the gradient operand, half of
+    the warp samples of the weight-gradient kernel sat on that load);
+  * columns nobody differentiates are never computed (the 24 direction columns of fc10's input gradient;
+    the position-encoding gradient unless the sample distances carry one, i.e. in the coarse pass);
+  * the density head's gradient is dropped into the last columns of fc9's output gradient by the product
+    that writes the first 256 (no concatenation, no per-layer autograd bookkeeping, no slice copies).
+
+The parameters stay the `fc1`..`fc11` nn.Linear modules of atmonr.models.nerf.AtmoNeRF (checkpoints
+interchange with the reference); this node only borrows their tensors.
+"""
+
+from __future__ import annotations
+
+import torch
+
+from atmonr.native import ops
+
+_f32 = torch.float32
+
+
+class NerfMlpFn(torch.autograd.Function):
+    """(x (M, pos + dir), density_noise (M, V) | None, w1, b1, ..., w11, b11) -> (rgb_raw (M, out), sigma_pre (M, V)).
+    rgb_raw is fc11's output (before the sigmoid of models/nerf.py:91), sigma_pre the density head of fc9 plus
+    the noise (before the ReLU of :71)."""
+
+    @staticmethod
+    def forward(ctx, x, noise, pos_channels, hidden, *params):
+        w = params[0::2]
+        b = params[1::2]
+        x, _ = ops._rows(x)
+        x_pos, x_dir = x[:, :pos_channels], x[:, pos_channels:]
+        acts = []                      # post-ReLU outputs of fc1..fc8 (inputs of fc2..fc9)
+        h = ops.linear_forward(x_pos, w[0], b[0], True)
+        acts.append(h)
+        for k in range(1, 5):          # fc2..fc5
+            h = ops.linear_forward(h, w[k], b[k], True)
+            acts.append(h)
+        h = ops.linear_forward(h, w[5], b[5], True, x2=x_pos)      # fc6: skip connection
+        acts.append(h)
+        for k in (6, 7):               # fc7, fc8
+            h = ops.linear_forward(h, w[k], b[k], True)
+            acts.append(h)
+        feat = ops.linear_forward(h, w[8], b[8], False)            # fc9: (M, hidden + V), no activation
+        hid = ops.linear_forward(feat[:, :hidden], w[9], b[9], True, x2=x_dir)   # fc10
+        rgb = ops.linear_forward(hid, w[10], b[10], False)         # fc11
+        sigma = feat[:, hidden:]
+        sigma = sigma + noise if noise is not None else sigma.clone()
+        ctx.save_for_backward(x, feat, hid, *acts, *w)
+        ctx.pos_channels, ctx.hidden = pos_channels, hidden
+        ctx.x_needs_grad = ctx.needs_input_grad[0]
+        return rgb, sigma
+
+    @staticmethod
+    def backward(ctx, d_rgb, d_sigma):
+        saved = ctx.saved_tensors
+        x, feat, hid = saved[:3]
+        acts = saved[3:11]
+        w = saved[11:]
+        pc, hd = ctx.pos_channels, ctx.hidden
+        x_pos, x_dir = x[:, :pc], x[:, pc:]
+        m = x.shape[0]
+        grads = [None] * 22
+
+        def wgrad(k, dy, xin, x2=None):
+            grads[2 * k], grads[2 * k + 1] = ops.linear_weight_grad(dy, xin, x2=x2, want_bias=True)
+
+        d_rgb = ops._c(d_rgb, _f32)
+        # fc11: pre-activation gradient of fc10 comes out masked by hid > 0
+        wgrad(10, d_rgb, hid)
+        d_hid = ops.linear_forward(d_rgb, w[10], None, False, transpose=True, out_mask=hid)
+        # fc10: only the `feat` columns of its input carry a gradient; they land in the first `hidden`
+        # columns of fc9's output gradient, the density gradient goes into the remaining ones
+        wgrad(9, d_hid, feat[:, :hd], x2=x_dir)
+        v = feat.shape[1] - hd
+        ld9 = (feat.shape[1] + 3) // 4 * 4
+        d_feat = torch.empty((m, ld9), device=x.device, dtype=_f32)
+        ops.linear_forward(d_hid, w[9][:, :hd], None, False, transpose=True, out=d_feat)
+        if d_sigma is not None:
+            d_feat[:, hd:hd + v] = d_sigma
+        else:
+            d_feat[:, hd:hd + v] = 0
+        d9 = d_feat[:, :hd + v]
+        # fc9 .. fc7
+        wgrad(8, d9, acts[7])
+        d = ops.linear_forward(d9, w[8], None, False, transpose=True, out_mask=acts[7])
+        wgrad(7, d, acts[6])
+        d = ops.linear_forward(d, w[7], None, False, transpose=True, out_mask=acts[6])
+        wgrad(6, d, acts[5])
+        d = ops.linear_forward(d, w[6], None, False, transpose=True, out_mask=acts[5])
+        # fc6: input [h5 | x_pos]
+        wgrad(5, d, acts[4], x2=x_pos)
+        d_pos = None
+        if ctx.x_needs_grad:
+            d_pos = ops.linear_forward(d, w[5][:, hd:], None, False, transpose=True)
+        d = ops.linear_forward(d, w[5][:, :hd], None, False, transpose=True, out_mask=acts[4])
+        # fc5 .. fc2
+        for k in (4, 3, 2, 1):
+            wgrad(k, d, acts[k - 1])
+            d = ops.linear_forward(d, w[k], None, False, transpose=True, out_mask=acts[k - 1])
+        # fc1
+        wgrad(0, d, x_pos)
+        dx = None
+        if ctx.x_needs_grad:
+            # the direction columns carry no gradient (the rays are data); the position columns are written
+            # in place by the product (row stride = the width of x)
+            dx = torch.zeros((m, x.shape[1]), device=x.device, dtype=_f32)
+            ops.linear_forward(d, w[0], None, False, transpose=True, out=dx)
+            dx[:, :pc] += d_pos
+        return (dx, None, None, None, *grads)

@@ -175,10 +175,13 @@ def _segments(x: torch.Tensor, x2):
 
 
 def linear_forward(x: torch.Tensor, weight: torch.Tensor, bias, relu: bool, transpose: bool = False,
-                   mask: torch.Tensor | None = None, x2: torch.Tensor | None = None, terms: int | None = None) -> torch.Tensor:
+                   mask: torch.Tensor | None = None, x2: torch.Tensor | None = None, terms: int | None = None,
+                   out_mask: torch.Tensor | None = None, out: torch.Tensor | None = None) -> torch.Tensor:
     """act(X' @ B.T + bias) with B = weight (n_out, k_in), or B = weight.T when `transpose` (then
     weight is (k_in, n_out)); X = x or [x | x2]; X' = X where mask > 0 and 0 elsewhere when a mask is
-    given. x, x2 and mask may be column slices of wider float32 tensors."""
+    given; the result is zeroed where out_mask (m, n_out) <= 0 when that is given. x, x2, mask and out_mask
+    may be column slices of wider float32 tensors; `out`: a (m, >= n_out) float32 tensor (or column slice
+    starting at a multiple of 4) that receives the result instead of a new tensor."""
     if not weight.is_cuda:
         raise L.NativeLibraryError("libatmonr_b200 operates on CUDA tensors only (no CPU fallback)")
     x, ldx, x2, x2p, ldx2, k_split, k_cols = _segments(x, x2)
@@ -194,12 +197,24 @@ def linear_forward(x: torch.Tensor, weight: torch.Tensor, bias, relu: bool, tran
             raise ValueError("linear_forward: mask and input must have the same shape")
         mp = mask.data_ptr()
     terms = terms or LINEAR_TERMS
+    omp, ldom = None, 0
+    if out_mask is not None:
+        out_mask, ldom = _rows(out_mask)
+        if out_mask.shape[0] != m or out_mask.shape[1] < n_out:
+            raise ValueError("linear_forward: out_mask must be (rows, >= n_out)")
+        omp = out_mask.data_ptr()
     planes = torch.empty(linear_planes_bytes(n_out, k_in, terms), device=x.device, dtype=torch.uint8)
-    y = torch.empty((m, n_out), device=x.device, dtype=_f32)
+    if out is None:
+        y = torch.empty((m, n_out), device=x.device, dtype=_f32)
+        yp, ldy = y.data_ptr(), n_out
+    else:
+        if out.dtype != _f32 or out.dim() != 2 or out.shape[0] != m or out.shape[1] < n_out or out.stride(1) != 1:
+            raise ValueError("linear_forward: `out` must be a (rows, >= n_out) float32 tensor with contiguous rows")
+        y, yp, ldy = out, out.data_ptr(), out.stride(0)
     L.call("atmonr_linear_prep", L.ptr(weight), n_out, k_in, int(transpose), terms, L.ptr(planes), L.stream())
     b = None if bias is None else _c(bias.detach(), _f32)
     L.call("atmonr_linear_fwd_tc", x.data_ptr(), ldx, x2p, ldx2, k_split, mp, ldm, L.ptr(planes), L.ptr(b), m, n_out,
-           k_in, int(relu), terms, L.ptr(y), n_out, L.stream())
+           k_in, int(relu), terms, omp, ldom, yp, ldy, L.stream())
     return y
 
 

@@ -78,11 +78,18 @@ __global__ void k_preprocess_f64(atmonr_frame_t f, GeoFrame gf, const double* __
 // instant_ngp.py:139-160 in one pass: stratified sample -> ECEF -> geodetic -> [0,1]^3 with
 // compressed altitude. One thread per sample; consecutive threads walk along a ray.
 // (General form: any N, any pointer alignment. The training path uses k_ngp_sample_points4.)
+// HEIGHT (`include_height`, instant_ngp.py:155-156 -> samplers.py:168-195): a fourth coordinate, the
+// ellipsoidal height of (x0, x1, x2) * scale + offset over ray_origin_height, taken BEFORE the altitude
+// compression of the third one (instant_ngp.py:160 comes after append_heights); x01 then has 4 columns.
+struct HeightArgs {
+  double scale, ox, oy, oz, origin_height;
+};
+template <bool HEIGHT>
 __global__ void k_ngp_sample_points(atmonr_frame_t f, GeoFrame gf, const float* __restrict__ o,
                                     const float* __restrict__ d, const float* __restrict__ len,
                                     const float* __restrict__ u, const float* __restrict__ bins,
                                     int64_t total, int N, int mode, uint64_t seed, uint64_t base,
-                                    float alt_compress, float* __restrict__ x01, float* __restrict__ z) {
+                                    float alt_compress, HeightArgs ha, float* __restrict__ x01, float* __restrict__ z) {
   const int64_t idx = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
   if (idx >= total) return;
   const int64_t ray = idx / N;
@@ -98,9 +105,17 @@ __global__ void k_ngp_sample_points(atmonr_frame_t f, GeoFrame gf, const float* 
   if (f.enabled) preprocess_f32(f, gf, p[0], p[1], p[2], c0, c1, c2);
   float x0, x1, x2;
   to_unit_cube(c0, c1, c2, alt_compress, x0, x1, x2);
-  x01[idx * 3] = x0;
-  x01[idx * 3 + 1] = x1;
-  x01[idx * 3 + 2] = x2;
+  if (HEIGHT) {
+    const float x2u = (c2 + 1.0f) / 2.0f;   // uncompressed
+    double lat, lon, alt;
+    ecef_to_geodetic((double)x0 * ha.scale + ha.ox, (double)x1 * ha.scale + ha.oy, (double)x2u * ha.scale + ha.oz, lat,
+                     lon, alt);
+    reinterpret_cast<float4*>(x01)[idx] = make_float4(x0, x1, x2, (float)(alt / ha.origin_height));
+  } else {
+    x01[idx * 3] = x0;
+    x01[idx * 3 + 1] = x1;
+    x01[idx * 3 + 2] = x2;
+  }
 }
 
 // Same arithmetic, one thread per aligned group of FOUR consecutive bins of a ray (N % 4 == 0,
@@ -248,75 +263,96 @@ constexpr int kNumBands = 4;
 
 #if ATM_PART_FIELD
 // Assemble the padded dir_mlp input from the ray direction and the pos_mlp output
-// (instant_ngp.py:165-169; tcnn Composite{SH2, Identity} then 1.0 padding to 32).
+// (instant_ngp.py:165-169; tcnn Composite{SH2, Identity} then 1.0 padding to a multiple of 16).
+// V = number of densities (`multi_band_extinction`: V = 4): the first V outputs of pos_mlp are densities,
+// the other 16 - V are features, so the input is 4 + 16 - V wide: 19 -> 32 (V = 1), 16 -> 16 (V = 4).
+template <int V>
+struct DirIn {
+  static constexpr int kWidthIn = V == 1 ? 32 : 16;
+};
+template <int V>
 __device__ __forceinline__ void build_dir_input(const float* __restrict__ dir, const float (&po)[kOutPad],
-                                                __half2 (&din)[16]) {
-  float v[32];
+                                                __half2 (&din)[DirIn<V>::kWidthIn / 2]) {
+  constexpr int W = DirIn<V>::kWidthIn;
+  float v[W];
   float sh[4];
   sh_degree2(dir[0], dir[1], dir[2], sh);
 #pragma unroll
   for (int k = 0; k < 4; ++k) v[k] = sh[k];
 #pragma unroll
-  for (int k = 1; k < kOutPad; ++k) v[3 + k] = po[k];
+  for (int k = V; k < kOutPad; ++k) v[4 + k - V] = po[k];
 #pragma unroll
-  for (int k = 19; k < 32; ++k) v[k] = 1.0f;
+  for (int k = 20 - V; k < W; ++k) v[k] = 1.0f;
 #pragma unroll
-  for (int k = 0; k < 16; ++k) din[k] = __floats2half2_rn(v[2 * k], v[2 * k + 1]);
+  for (int k = 0; k < W / 2; ++k) din[k] = __floats2half2_rn(v[2 * k], v[2 * k + 1]);
 }
 
+// D = grid dimensionality (4 with `include_height`), V = densities per sample (4 with
+// `multi_band_extinction`); the shipped configuration is <3, 1>.
+template <int D, int V>
 __global__ void __launch_bounds__(kTile)
 k_field_fwd(atmonr_grid_t g, const __half2* __restrict__ table, const __half* __restrict__ pos_w,
             const __half* __restrict__ dir_w, const float* __restrict__ x01, const float* __restrict__ dirs,
             int64_t M, int N, float* __restrict__ sigma_raw, float* __restrict__ color_raw) {
-  __shared__ __align__(16) float sW[PosMlp::kNumWeights + DirMlp::kNumWeights];
+  constexpr int DIN = DirIn<V>::kWidthIn;
+  using DirM = MlpShape<DIN, 2>;
+  __shared__ __align__(16) float sW[PosMlp::kNumWeights + DirM::kNumWeights];
   float* sWp = sW;
   float* sWd = sW + PosMlp::kNumWeights;
   load_weights(pos_w, sWp, PosMlp::kNumWeights);
-  load_weights(dir_w, sWd, DirMlp::kNumWeights);
+  load_weights(dir_w, sWd, DirM::kNumWeights);
   __syncthreads();
   for (int64_t tile = blockIdx.x; tile * kTile < M; tile += gridDim.x) {
     const int64_t i = tile * kTile + threadIdx.x;
     if (i >= M) continue;
-    const float p[3] = {x01[3 * i], x01[3 * i + 1], x01[3 * i + 2]};
-    __half2 enc[16], hp[1][16], din[16], hd[2][16];
-    hash_encode<3>(g, table, p, enc);
+    float p[D];
+#pragma unroll
+    for (int k = 0; k < D; ++k) p[k] = x01[D * i + k];
+    __half2 enc[16], hp[1][16], din[DIN / 2], hd[2][16];
+    hash_encode<D>(g, table, p, enc);
     float po[kOutPad];
     mlp_forward<32, 1, kOutPad>(sWp, enc, hp, po);
-    sigma_raw[i] = po[0];
-    build_dir_input(dirs + (i / N) * 3, po, din);
+#pragma unroll
+    for (int v = 0; v < V; ++v) sigma_raw[V * i + v] = po[v];
+    build_dir_input<V>(dirs + (i / N) * 3, po, din);
     float c[kNumBands];
-    mlp_forward<32, 2, kNumBands>(sWd, din, hd, c);
+    mlp_forward<DIN, 2, kNumBands>(sWd, din, hd, c);
     *reinterpret_cast<float4*>(color_raw + 4 * i) = make_float4(c[0], c[1], c[2], c[3]);
   }
 }
 
+template <int D, int V>
 __global__ void __launch_bounds__(kTile)
 k_field_bwd(atmonr_grid_t g, const __half2* __restrict__ table, const __half* __restrict__ pos_w,
             const __half* __restrict__ dir_w, const float* __restrict__ x01, const float* __restrict__ dirs,
             const float* __restrict__ dsigma_raw, const float* __restrict__ dcolor_raw, int64_t M, int N,
             float* __restrict__ dtable, float* __restrict__ dpos_w, float* __restrict__ ddir_w) {
+  constexpr int DIN = DirIn<V>::kWidthIn;
+  using DirM = MlpShape<DIN, 2>;
   extern __shared__ __align__(16) float smem[];
   float* sWp = smem;
   float* sWd = sWp + PosMlp::kNumWeights;
-  float* sdWp = sWd + DirMlp::kNumWeights;
+  float* sdWp = sWd + DirM::kNumWeights;
   float* sdWd = sdWp + PosMlp::kNumWeights;
-  float* scratch = sdWd + DirMlp::kNumWeights;
+  float* scratch = sdWd + DirM::kNumWeights;
   load_weights(pos_w, sWp, PosMlp::kNumWeights);
-  load_weights(dir_w, sWd, DirMlp::kNumWeights);
-  for (int i = threadIdx.x; i < PosMlp::kNumWeights + DirMlp::kNumWeights; i += blockDim.x) sdWp[i] = 0.0f;
+  load_weights(dir_w, sWd, DirM::kNumWeights);
+  for (int i = threadIdx.x; i < PosMlp::kNumWeights + DirM::kNumWeights; i += blockDim.x) sdWp[i] = 0.0f;
   __syncthreads();
   for (int64_t tile = blockIdx.x; tile * kTile < M; tile += gridDim.x) {
     const int64_t i = tile * kTile + threadIdx.x;
     const bool valid = i < M;
     const int64_t j = valid ? i : 0;
-    const float p[3] = {x01[3 * j], x01[3 * j + 1], x01[3 * j + 2]};
-    __half2 enc[16], hp[1][16], din[16], hd[2][16];
-    hash_encode<3>(g, table, p, enc);
+    float p[D];
+#pragma unroll
+    for (int k = 0; k < D; ++k) p[k] = x01[D * j + k];
+    __half2 enc[16], hp[1][16], din[DIN / 2], hd[2][16];
+    hash_encode<D>(g, table, p, enc);
     float po[kOutPad];
     mlp_forward<32, 1, kOutPad>(sWp, enc, hp, po);
-    build_dir_input(dirs + (j / N) * 3, po, din);
+    build_dir_input<V>(dirs + (j / N) * 3, po, din);
     float c[kNumBands];
-    mlp_forward<32, 2, kNumBands>(sWd, din, hd, c);
+    mlp_forward<DIN, 2, kNumBands>(sWd, din, hd, c);
 
     float dout[kOutPad];
 #pragma unroll
@@ -325,18 +361,19 @@ k_field_bwd(atmonr_grid_t g, const __half2* __restrict__ table, const __half* __
       const float4 dc = *reinterpret_cast<const float4*>(dcolor_raw + 4 * i);
       dout[0] = dc.x; dout[1] = dc.y; dout[2] = dc.z; dout[3] = dc.w;
     }
-    float ddin[32];
-    mlp_backward<32, 2>(sWd, sdWd, scratch, din, hd, dout, ddin);
+    float ddin[DIN];
+    mlp_backward<DIN, 2>(sWd, sdWd, scratch, din, hd, dout, ddin);
     float dpo[kOutPad];
-    dpo[0] = valid ? dsigma_raw[i] : 0.0f;
 #pragma unroll
-    for (int k = 1; k < kOutPad; ++k) dpo[k] = ddin[3 + k];
+    for (int v = 0; v < V; ++v) dpo[v] = valid ? dsigma_raw[V * i + v] : 0.0f;
+#pragma unroll
+    for (int k = V; k < kOutPad; ++k) dpo[k] = ddin[4 + k - V];
     float denc[32];
     mlp_backward<32, 1>(sWp, sdWp, scratch, enc, hp, dpo, denc);
-    if (valid) hash_scatter<3>(g, dtable, p, denc, 1.0f);
+    if (valid) hash_scatter<D>(g, dtable, p, denc, 1.0f);
   }
   flush_dw(sdWp, dpos_w, PosMlp::kNumWeights);
-  flush_dw(sdWd, ddir_w, DirMlp::kNumWeights);
+  flush_dw(sdWd, ddir_w, DirM::kNumWeights);
 }
 
 #endif  // ATM_PART_FIELD
@@ -1127,10 +1164,26 @@ int atmonr_ngp_sample_points(const atmonr_frame_t* f, const float* origin, const
   if (make_sampler_job(job, f, origin, dir, len, u, bins, B, N, mode, seed, ray_index_base, alt_compress, x01, z))
     k_ngp_sample_points4<<<grid_for(job.groups, 128), 128, 0, S(stream)>>>(job);
   else
-    k_ngp_sample_points<<<grid_for(B * N, 256), 256, 0, S(stream)>>>(*f, make_geo_frame(*f), origin, dir, len, u, bins,
-                                                                    B * N, N, mode, seed, ray_index_base, alt_compress,
-                                                                    x01, z);
+    k_ngp_sample_points<false><<<grid_for(B * N, 256), 256, 0, S(stream)>>>(*f, make_geo_frame(*f), origin, dir, len, u,
+                                                                           bins, B * N, N, mode, seed, ray_index_base,
+                                                                           alt_compress, HeightArgs{}, x01, z);
   ATM_CHECK_LAUNCH("atmonr_ngp_sample_points");
+  return 0;
+}
+
+int atmonr_ngp_sample_points_height(const atmonr_frame_t* f, const float* origin, const float* dir, const float* len,
+                                    const float* u, const float* bins, int64_t B, int N, int mode, uint64_t seed,
+                                    uint64_t ray_index_base, float alt_compress, double scale, const double* offset_host,
+                                    double ray_origin_height, float* x01, float* z, void* stream) {
+  ATM_REQUIRE(f && offset_host, "atmonr_ngp_sample_points_height", "null frame / offset");
+  ATM_REQUIRE(mode >= 0 && mode <= 2 && (mode != 1 || u), "atmonr_ngp_sample_points_height", "bad mode / missing u");
+  ATM_REQUIRE((reinterpret_cast<uintptr_t>(x01) & 15u) == 0, "atmonr_ngp_sample_points_height", "x01 must be 16-byte aligned");
+  if (B * N == 0) return 0;
+  const HeightArgs ha{scale, offset_host[0], offset_host[1], offset_host[2], ray_origin_height};
+  k_ngp_sample_points<true><<<grid_for(B * N, 256), 256, 0, S(stream)>>>(*f, make_geo_frame(*f), origin, dir, len, u, bins,
+                                                                          B * N, N, mode, seed, ray_index_base,
+                                                                          alt_compress, ha, x01, z);
+  ATM_CHECK_LAUNCH("atmonr_ngp_sample_points_height");
   return 0;
 }
 
@@ -1199,22 +1252,34 @@ int atmonr_mlp_bwd(const atmonr_mlp_t* m, const void* w, const float* x, const f
 
 #endif  // ATM_PART_MLP
 #if ATM_PART_FIELD
+// -> number of densities V (1 or 4), or -1 with the error recorded
 static int check_field(const atmonr_grid_t* g, const atmonr_mlp_t* pm, const atmonr_mlp_t* dm, const char* name) {
-  ATM_REQUIRE(g && g->n_dims == 3 && g->n_feat == 2 && g->n_levels == 16, name, "field needs a 3-D grid with 16 levels x 2 features");
+  ATM_REQUIRE(g && (g->n_dims == 3 || g->n_dims == 4) && g->n_feat == 2 && g->n_levels == 16, name,
+              "field needs a 3-D or 4-D grid with 16 levels x 2 features");
   ATM_REQUIRE(is_shape(pm, 32, 1) && pm->n_in == 32 && pm->n_out == 16, name, "pos_mlp must be 32 -> [32] -> 16");
-  ATM_REQUIRE(is_shape(dm, 32, 2) && dm->n_in == 19 && dm->n_out == 4, name, "dir_mlp must be 19 -> [32,32] -> 4");
-  return 0;
+  const bool v1 = is_shape(dm, 32, 2) && dm->n_in == 19 && dm->n_out == 4;
+  const bool v4 = is_shape(dm, 16, 2) && dm->n_in == 16 && dm->n_out == 4;
+  ATM_REQUIRE(v1 || v4, name, "dir_mlp must be 19 -> [32,32] -> 4 (one density) or 16 -> [32,32] -> 4 (four densities)");
+  return v1 ? 1 : 4;
 }
+
+#define ATM_DV_DISPATCH(D, V, CALL)                                        \
+  if ((D) == 3 && (V) == 1) { CALL(3, 1); } else if ((D) == 4 && (V) == 1) { CALL(4, 1); } \
+  else if ((D) == 3) { CALL(3, 4); } else { CALL(4, 4); }
 
 int atmonr_ngp_field_fwd(const atmonr_grid_t* g, const void* table, const atmonr_mlp_t* pm, const void* pos_w,
                          const atmonr_mlp_t* dm, const void* dir_w, const float* x01, const float* dirs, int64_t B,
                          int N, float* sigma_raw, float* color_raw, void* stream) {
-  if (check_field(g, pm, dm, "atmonr_ngp_field_fwd")) return -1;
+  const int V = check_field(g, pm, dm, "atmonr_ngp_field_fwd");
+  if (V < 0) return -1;
   const int64_t M = B * N;
   if (M == 0) return 0;
   const int grid = grid_for((M + kTile - 1) / kTile, 1, num_sms() * 16);
-  k_field_fwd<<<grid, kTile, 0, S(stream)>>>(*g, (const __half2*)table, (const __half*)pos_w, (const __half*)dir_w,
-                                            x01, dirs, M, N, sigma_raw, color_raw);
+#define CALL(DD, VV)                                                                                           \
+  k_field_fwd<DD, VV><<<grid, kTile, 0, S(stream)>>>(*g, (const __half2*)table, (const __half*)pos_w,          \
+                                                    (const __half*)dir_w, x01, dirs, M, N, sigma_raw, color_raw)
+  ATM_DV_DISPATCH(g->n_dims, V, CALL)
+#undef CALL
   ATM_CHECK_LAUNCH("atmonr_ngp_field_fwd");
   return 0;
 }
@@ -1223,15 +1288,22 @@ int atmonr_ngp_field_bwd(const atmonr_grid_t* g, const void* table, const atmonr
                          const atmonr_mlp_t* dm, const void* dir_w, const float* x01, const float* dirs,
                          const float* dsigma_raw, const float* dcolor_raw, int64_t B, int N, float* dtable,
                          float* dpos_w, float* ddir_w, void* stream) {
-  if (check_field(g, pm, dm, "atmonr_ngp_field_bwd")) return -1;
+  const int V = check_field(g, pm, dm, "atmonr_ngp_field_bwd");
+  if (V < 0) return -1;
   const int64_t M = B * N;
   if (M == 0) return 0;
-  const size_t smem = (2 * (PosMlp::kNumWeights + DirMlp::kNumWeights) + BwdScratch<32>::kFloats) * sizeof(float);
-  if (set_smem(k_field_bwd, smem, "atmonr_ngp_field_bwd")) return -1;
+  const int dir_weights = V == 1 ? MlpShape<32, 2>::kNumWeights : MlpShape<16, 2>::kNumWeights;
+  const size_t smem = (2 * (PosMlp::kNumWeights + dir_weights) + BwdScratch<32>::kFloats) * sizeof(float);
   const int grid = grid_for((M + kTile - 1) / kTile, 1, num_sms() * 3);
-  k_field_bwd<<<grid, kTile, smem, S(stream)>>>(*g, (const __half2*)table, (const __half*)pos_w,
-                                               (const __half*)dir_w, x01, dirs, dsigma_raw, dcolor_raw, M, N,
-                                               dtable, dpos_w, ddir_w);
+#define CALL(DD, VV)                                                                                               \
+  {                                                                                                                \
+    if (set_smem(k_field_bwd<DD, VV>, smem, "atmonr_ngp_field_bwd")) return -1;                                    \
+    k_field_bwd<DD, VV><<<grid, kTile, smem, S(stream)>>>(*g, (const __half2*)table, (const __half*)pos_w,         \
+                                                         (const __half*)dir_w, x01, dirs, dsigma_raw, dcolor_raw, \
+                                                         M, N, dtable, dpos_w, ddir_w);                            \
+  }
+  ATM_DV_DISPATCH(g->n_dims, V, CALL)
+#undef CALL
   ATM_CHECK_LAUNCH("atmonr_ngp_field_bwd");
   return 0;
 }

@@ -173,7 +173,7 @@ template <int TERMS>
 __global__ void __launch_bounds__(lin::kThreads, TERMS == 2 ? 2 : 1)
 k_linear_tc(const float* __restrict__ x, int64_t ldx, const float* __restrict__ x2, int64_t ldx2, int k_split,
             const float* __restrict__ mask, int64_t ldm, const uint8_t* __restrict__ planes, const float* __restrict__ bias, int64_t M, int n_out, int k_in,
-            int k_chunks, int act, float* __restrict__ y, int64_t ldy) {
+            int k_chunks, int act, const float* __restrict__ out_mask, int64_t ldom, float* __restrict__ y, int64_t ldy) {
   extern __shared__ __align__(128) uint8_t smem[];
   using MapT = lin::Map<TERMS>;
   uint64_t* bar = reinterpret_cast<uint64_t*>(smem + MapT::kBar);          // bar[s]: MMAs that read stage s are done
@@ -207,8 +207,11 @@ k_linear_tc(const float* __restrict__ x, int64_t ldx, const float* __restrict__ 
   // this thread's 2 x 8 values of a chunk: a quarter warp (8 lanes) owns the 8 rows of ONE core matrix =
   // 128 contiguous bytes of shared memory (no bank conflicts); in global memory the warp reads 8 rows x
   // 128 contiguous bytes
-  float xv[2][8];
-  auto fetch_x = [&](int c) {
+  // The values are requested TWO chunks ahead (two register sets, xa for even and xb for odd chunks): one
+  // chunk's worth of bytes in flight per CTA (16 KB) did not cover the global-load latency (ncu round 2:
+  // 35 % of the warp samples on the long scoreboard, DRAM at a third of its rate).
+  float xa[2][8], xb[2][8];
+  auto fetch_x = [&](int c, float (&xv)[2][8]) {
 #pragma unroll
     for (int it = 0; it < 2; ++it) {
       const int r = ((warp + it * (lin::kThreads / 32)) << 3) | (tid & 7), cc = (tid >> 3) & 3;
@@ -216,7 +219,7 @@ k_linear_tc(const float* __restrict__ x, int64_t ldx, const float* __restrict__ 
       const int k0 = c * lin::kChunk + cc * 8;
 #pragma unroll
       for (int j = 0; j < 8; ++j) xv[it][j] = 0.0f;
-      if (row < M) {
+      if (row < M && c < k_chunks) {
         // columns [0, k_split) come from x, [k_split, k_in) from x2 (k_split is a multiple of 8: a group
         // of 8 never straddles the two)
         const bool second = k0 >= k_split;
@@ -225,7 +228,8 @@ k_linear_tc(const float* __restrict__ x, int64_t ldx, const float* __restrict__ 
       }
     }
   };
-  fetch_x(0);
+  fetch_x(0, xa);
+  fetch_x(1, xb);
 
   for (int c = 0; c < k_chunks; ++c) {
     const int s = c & 1;
@@ -243,15 +247,21 @@ k_linear_tc(const float* __restrict__ x, int64_t ldx, const float* __restrict__ 
 #pragma unroll
       for (int p = 0; p < TERMS; ++p) bulk_g2s(dst + p * lin::kBTile, src + p * lin::kBTile, bytes, full + s);
     }
-    // ---- X chunk: 128 rows x 32 columns float32 -> TERMS bf16 planes (2 groups of 8 values per thread).
-    // The values were requested one chunk ahead (xv: registers), so the global-load latency sits
-    // underneath the previous chunk's split, barrier and MMAs; the next chunk is requested now.
+    // ---- X chunk: 128 rows x 32 columns float32 -> TERMS bf16 planes (2 groups of 8 values per thread)
     float cur[2][8];
+    if (s == 0) {
 #pragma unroll
-    for (int it = 0; it < 2; ++it)
+      for (int it = 0; it < 2; ++it)
 #pragma unroll
-      for (int j = 0; j < 8; ++j) cur[it][j] = xv[it][j];
-    if (c + 1 < k_chunks) fetch_x(c + 1);
+        for (int j = 0; j < 8; ++j) cur[it][j] = xa[it][j];
+      fetch_x(c + 2, xa);
+    } else {
+#pragma unroll
+      for (int it = 0; it < 2; ++it)
+#pragma unroll
+        for (int j = 0; j < 8; ++j) cur[it][j] = xb[it][j];
+      fetch_x(c + 2, xb);
+    }
 #pragma unroll
     for (int it = 0; it < 2; ++it) {
       const int r = ((warp + it * (lin::kThreads / 32)) << 3) | (tid & 7), cc = (tid >> 3) & 3;
@@ -319,21 +329,33 @@ k_linear_tc(const float* __restrict__ x, int64_t ldx, const float* __restrict__ 
       const int w_valid = min(lin::kHalf, n_valid - h0);   // real columns of this half
       if (w_valid <= 0) continue;                          // uniform
       float* yh = y + n0 + h0;
-      if (vec) {
+      // out_mask (M, n_out): the output is zeroed where out_mask <= 0 -- the ReLU derivative of the layer
+      // whose OUTPUT this product's result is the gradient of, applied where the rows are written out with
+      // coalesced accesses (so that no downstream product has to read a mask in its main loop)
+      const float* omh = out_mask ? out_mask + n0 + h0 : nullptr;
+      if (vec && (!omh || ((ldom & 3) == 0 && (reinterpret_cast<uintptr_t>(out_mask) & 15) == 0))) {
         const int q_per_row = w_valid >> 2;                // whole float4 groups
         for (int i = tid; i < rows * q_per_row; i += lin::kThreads) {
           const int rr = i / q_per_row, q = i - rr * q_per_row;
-          *reinterpret_cast<float4*>(yh + (row0 + rr) * ldy + 4 * q) = *reinterpret_cast<const float4*>(tile + rr * pitch + 4 * q);
+          float4 v = *reinterpret_cast<const float4*>(tile + rr * pitch + 4 * q);
+          if (omh) {
+            const float4 m = *reinterpret_cast<const float4*>(omh + (row0 + rr) * ldom + 4 * q);
+            v.x = m.x > 0.0f ? v.x : 0.0f, v.y = m.y > 0.0f ? v.y : 0.0f;
+            v.z = m.z > 0.0f ? v.z : 0.0f, v.w = m.w > 0.0f ? v.w : 0.0f;
+          }
+          *reinterpret_cast<float4*>(yh + (row0 + rr) * ldy + 4 * q) = v;
         }
         const int tail = w_valid & 3;
         for (int i = tid; i < rows * tail; i += lin::kThreads) {
           const int rr = i / tail, cc = (w_valid & ~3) + (i - rr * tail);
-          yh[(row0 + rr) * ldy + cc] = tile[rr * pitch + cc];
+          const float v = tile[rr * pitch + cc];
+          yh[(row0 + rr) * ldy + cc] = (omh && !(omh[(row0 + rr) * ldom + cc] > 0.0f)) ? 0.0f : v;
         }
       } else {
         for (int i = tid; i < rows * w_valid; i += lin::kThreads) {
           const int rr = i / w_valid, cc = i - rr * w_valid;
-          yh[(row0 + rr) * ldy + cc] = tile[rr * pitch + cc];
+          const float v = tile[rr * pitch + cc];
+          yh[(row0 + rr) * ldy + cc] = (omh && !(omh[(row0 + rr) * ldom + cc] > 0.0f)) ? 0.0f : v;
         }
       }
     }
@@ -557,7 +579,7 @@ int atmonr_linear_prep(const float* w, int n_out, int k_in, int transpose, int t
 
 int atmonr_linear_fwd_tc(const float* x, int64_t ldx, const float* x2, int64_t ldx2, int k_split, const float* mask,
                          int64_t ldm, const void* planes, const float* bias, int64_t M, int n_out, int k_in, int act,
-                         int terms, float* y, int64_t ldy, void* stream) {
+                         int terms, const float* out_mask, int64_t ldom, float* y, int64_t ldy, void* stream) {
   ATM_REQUIRE(M >= 0 && n_out > 0 && k_in > 0, "atmonr_linear_fwd_tc", "bad shape");
   ATM_REQUIRE(act == 0 || act == 1, "atmonr_linear_fwd_tc", "act must be 0 (none) or 1 (ReLU)");
   ATM_REQUIRE(terms == 2 || terms == 3, "atmonr_linear_fwd_tc", "terms must be 2 or 3");
@@ -566,7 +588,8 @@ int atmonr_linear_fwd_tc(const float* x, int64_t ldx, const float* x2, int64_t l
   if (!x2) k_split = k_in;
   ATM_REQUIRE(k_split > 0 && k_split <= k_in && (k_split == k_in || k_split % 8 == 0), "atmonr_linear_fwd_tc",
               "k_split must be a multiple of 8 inside (0, k_in]");
-  ATM_REQUIRE(ldx >= k_split && (!x2 || ldx2 >= k_in - k_split) && ldy >= n_out && (!mask || ldm >= k_in),
+  ATM_REQUIRE(ldx >= k_split && (!x2 || ldx2 >= k_in - k_split) && ldy >= n_out && (!mask || ldm >= k_in) &&
+                  (!out_mask || ldom >= n_out),
               "atmonr_linear_fwd_tc", "row stride smaller than the row");
   ATM_REQUIRE((M + lin::kRows - 1) / lin::kRows < (1ll << 31), "atmonr_linear_fwd_tc", "too many rows");
   const int n_tiles = (n_out + lin::kCols - 1) / lin::kCols, k_chunks = (k_in + lin::kChunk - 1) / lin::kChunk;
@@ -577,7 +600,7 @@ int atmonr_linear_fwd_tc(const float* x, int64_t ldx, const float* x2, int64_t l
     if (e != cudaSuccess) return fail("atmonr_linear_fwd_tc", cudaGetErrorString(e));                                  \
     k_linear_tc<T><<<grid, lin::kThreads, lin::Map<T>::kBytes, S(stream)>>>(                                           \
         x, ldx, x2, ldx2, k_split, mask, ldm, reinterpret_cast<const uint8_t*>(planes), bias, M, n_out, k_in, k_chunks, \
-        act, y, ldy);                                                                                                  \
+        act, out_mask, ldom, y, ldy);                                                                                  \
   }
   ATM_TERMS_DISPATCH(terms, CALL)
 #undef CALL

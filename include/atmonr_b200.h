@@ -116,6 +116,15 @@ int atmonr_ngp_sample_points(const atmonr_frame_t* frame_host, const float* orig
                              const float* bins, int64_t B, int N, int mode, uint64_t seed,
                              uint64_t ray_index_base, float alt_compress, float* x01, float* z,
                              void* stream);
+/* The same with `include_height` (instant_ngp.py:155-156 -> samplers.py:168-195): x01 (B*N,4), the fourth
+ * column = ellipsoidal height of the [0,1]^3 point (before the altitude compression) * scale + offset
+ * over ray_origin_height. offset_host: 3 doubles on the host. */
+int atmonr_ngp_sample_points_height(const atmonr_frame_t* frame_host, const float* origin,
+                                    const float* dir, const float* len, const float* u,
+                                    const float* bins, int64_t B, int N, int mode, uint64_t seed,
+                                    uint64_t ray_index_base, float alt_compress, double scale,
+                                    const double* offset_host, double ray_origin_height, float* x01,
+                                    float* z, void* stream);
 
 /* ---- tcnn.Encoding HashGrid forward/backward (instant_ngp.py:163,236) --------------------
  * x (M, x_stride) float32, the first n_dims columns are used. table: fp16 shadow of the
@@ -341,6 +350,10 @@ int atmonr_append_heights(const float* pts, int64_t M, double scale, const doubl
  *   input-gradient product dX = dY * W is this call on the planes of W^T). planes:
  *       ceil(n_out / 256) * ceil(k_in / 32) * terms * 16384 bytes.
  *   bias (n_out) may be NULL; act: 0 none, 1 ReLU.
+ *   out_mask (M, n_out; may be NULL): Y is zeroed where out_mask <= 0, applied while the rows are written
+ *   out. In the backward chain of an MLP the input gradient dX = dY * W of layer l+1 IS the gradient of
+ *   layer l's post-ReLU output, whose values are out_mask: the result is then layer l's pre-activation
+ *   gradient and neither product of layer l has to read a mask in its main loop.
  *   terms: 3 = the float32-exact flavour above (six products); 2 = two bf16 terms per operand and the
  *   three products hi*hi + hi*lo + lo*hi (product error ~2^-16 relative: half the tensor-core work,
  *   two CTAs per SM); the planes must have been prepared with the same `terms`.
@@ -352,8 +365,8 @@ int atmonr_linear_prep(const float* w, int n_out, int k_in, int transpose, int t
                        void* stream);
 int atmonr_linear_fwd_tc(const float* x, int64_t ldx, const float* x2, int64_t ldx2, int k_split,
                          const float* mask, int64_t ldm, const void* planes, const float* bias,
-                         int64_t M, int n_out, int k_in, int act, int terms, float* y, int64_t ldy,
-                         void* stream);
+                         int64_t M, int n_out, int k_in, int act, int terms, const float* out_mask,
+                         int64_t ldom, float* y, int64_t ldy, void* stream);
 int atmonr_linear_dw_tc(const float* dy, int64_t ldy, const float* mask, int64_t ldm,
                         const float* x, int64_t ldx, const float* x2, int64_t ldx2, int k_split,
                         int64_t M, int n_out, int k_in, int terms, float* dw, float* db,

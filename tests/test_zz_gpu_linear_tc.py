@@ -169,3 +169,58 @@ def test_nerf_pipeline_with_tensor_core_layers(monkeypatch, terms):
     assert float((a[3] - b[3]).abs().max()) <= gtol * float(a[3].abs().max())
     print(f"terms={terms}: colour map rel err {float((a[0] - b[0]).abs().max() / a[0].abs().max()):.2e}, "
           f"loss rel err {abs(a[2] - b[2]) / abs(a[2]):.2e}, gradient rel err {float((a[3] - b[3]).abs().max() / a[3].abs().max()):.2e}")
+
+
+def test_linear_output_mask_and_preallocated_output(terms):
+    """`out_mask` (the ReLU derivative of the layer below, applied while the input gradient is written out)
+    and `out` (a column block of a wider tensor receives the product): the backward chain of
+    atmonr.native.nerf_mlp is built from these two."""
+    from atmonr.native import ops
+    g = torch.Generator().manual_seed(11)
+    tol = 4e-6 if terms == 3 else 5e-5
+    for m, k, n in ((700, 128, 256), (300, 256, 76), (129, 260, 256)):
+        dy = torch.randn(m, k, generator=g).cuda()
+        w = (torch.randn(k, n, generator=g) / k ** 0.5).cuda()          # dX = dY @ W, W (k, n)
+        below = torch.randn(m, n + 3, generator=g).cuda()[:, :n]         # a column slice as the mask
+        want = (dy.double() @ w.double()) * (below > 0)
+        got = ops.linear_forward(dy, w, None, False, transpose=True, out_mask=below)
+        assert got.shape == (m, n)
+        assert float((got.double() - want).abs().max()) <= tol * float(want.abs().max())
+        assert bool((got[below <= 0] == 0).all())
+        wide = torch.full((m, n + 8), 7.0, device="cuda")
+        ops.linear_forward(dy, w, None, False, transpose=True, out=wide)
+        assert float((wide[:, :n].double() - dy.double() @ w.double()).abs().max()) <= tol * float(want.abs().max())
+        assert bool((wide[:, n:] == 7.0).all())                            # columns beyond the product are untouched
+
+
+def test_nerf_mlp_node_matches_the_layer_by_layer_model(terms):
+    """atmonr.native.nerf_mlp.NerfMlpFn (one autograd node, hand-written backward chain) against the same
+    AtmoNeRF evaluated with torch's float32 layers + autograd: outputs, parameter gradients and the gradient
+    w.r.t. the encoded position (the fine pass differentiates it; the direction columns get none)."""
+    import atmonr.models.nerf as mn
+    torch.manual_seed(3)
+    coarse, fine = mn.get_model(256, 4, [14, 14, 10], 4, False)
+    g = torch.Generator().manual_seed(5)
+    for net in (coarse, fine):
+        net = net.cuda().eval()
+        x = (torch.rand(3000, 100, generator=g) * 2 - 1).cuda()
+        gc = torch.randn(3000, 4, generator=g).cuda()
+        gs = torch.randn(3000, net.volume_channels, generator=g).cuda()
+        outs = {}
+        for impl in ("library", "tc"):
+            mn.DENSE_IMPL = impl
+            try:
+                xr = x.clone().requires_grad_()
+                net.zero_grad()
+                c, s = net(xr)
+                ((c * gc).sum() + (s * gs).sum()).backward()
+                outs[impl] = (c.detach(), s.detach(), xr.grad.clone(), [p.grad.clone() for p in net.parameters()])
+            finally:
+                mn.DENSE_IMPL = "tc"
+        a, b = outs["library"], outs["tc"]
+        rel = lambda u, v: float((u - v).abs().max() / (u.abs().max() + 1e-30))
+        ftol, gtol = (2e-5, 2e-4) if terms == 3 else (1e-4, 1e-3)
+        assert rel(a[0], b[0]) <= ftol and rel(a[1], b[1]) <= ftol
+        assert rel(a[2][:, :76], b[2][:, :76]) <= gtol and float(b[2][:, 76:].abs().max()) == 0
+        for pa, pb in zip(a[3], b[3]):
+            assert pa.shape == pb.shape and rel(pa, pb) <= gtol
