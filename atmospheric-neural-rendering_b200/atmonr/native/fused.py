@@ -50,6 +50,8 @@ class NGPState:
     n_samples: int
     alt_compress: float
     z_scale: float            # scale / 1000 (normalised distance -> km)
+    n_density: int = 1        # 4 with `multi_band_extinction` (instant_ngp.py:46-50)
+    height: tuple | None = None   # (scale, offset, ray_origin_height) with `include_height`: 4-D grid
     seed: int = 0
     step: int = 0             # advances once per forward: new stratified draws every step
     ray_index_base: int = 0   # global index of the first ray of this rank's shard
@@ -110,7 +112,7 @@ def schedule_prefetch(st: NGPState, origin, direction, length) -> None:
     b, n = o.shape[0], st.n_samples
     if st.bins is None or st.bins.device != o.device or st.bins.numel() != n:
         st.bins = ops.linspace_bins(n, o.device)
-    x01 = torch.empty((b * n, 3), device=o.device, dtype=_f32)
+    x01 = torch.empty((b * n, 3 if st.height is None else 4), device=o.device, dtype=_f32)
     z = torch.empty((b, n), device=o.device, dtype=_f32)
     ready = torch.cuda.Event()
     ready.record()
@@ -141,7 +143,7 @@ def _launch_one(st: NGPState, p: dict, on_side_stream: bool) -> None:
         run_on = cur
     with torch.cuda.stream(run_on):
         ops.ngp_sample_points(st.frame, o, d, ln, st.n_samples, st.alt_compress, random=True, seed=p["seed"],
-                              ray_index_base=p["ray_index_base"], bins=st.bins, out=(p["x01"], p["z"]))
+                              ray_index_base=p["ray_index_base"], bins=st.bins, out=(p["x01"], p["z"]), height=st.height)
         p["done"] = torch.cuda.Event()
         p["done"].record()
 
@@ -162,11 +164,18 @@ def take_prefetched(st: NGPState, origin):
     return p["x01"], p["z"]
 
 
+def field_impl(st: NGPState) -> str:
+    """The tcgen05 kernels cover the shipped shape (3-D grid, one density); `include_height` (4-D grid) and
+    `multi_band_extinction` (four densities) run the same launch chain on the thread-per-sample kernels,
+    which are templated on both (csrc/atmonr_b200.cu: k_field_fwd / k_field_bwd <D, V>)."""
+    return "simt" if (FIELD_IMPL == "simt" or st.n_density != 1 or st.height is not None) else "tc"
+
+
 def field_forward(st: NGPState, table16, pos_w16, dir_w16, x01, dirs, b, n, want_enc=False):
-    """-> (sigma_raw (M,), color_raw (M,4), enc (M,32) fp16 | None)."""
-    sigma_raw = torch.empty(b * n, device=x01.device, dtype=_f32)
+    """-> (sigma_raw (M, V), color_raw (M,4), enc (M,32) fp16 | None)."""
+    sigma_raw = torch.empty((b * n, st.n_density), device=x01.device, dtype=_f32)
     color_raw = torch.empty((b * n, 4), device=x01.device, dtype=_f32)
-    if FIELD_IMPL == "simt":
+    if field_impl(st) == "simt":
         L.call("atmonr_ngp_field_fwd", C.byref(st.grid3), L.ptr(table16), C.byref(st.pos_mlp), L.ptr(pos_w16),
                C.byref(st.dir_mlp), L.ptr(dir_w16), L.ptr(x01), L.ptr(dirs), b, n, L.ptr(sigma_raw), L.ptr(color_raw),
                L.stream())
@@ -201,19 +210,20 @@ class NGPRenderFn(torch.autograd.Function):
             if st.bins is None or st.bins.device != origin.device or st.bins.numel() != n:
                 st.bins = ops.linspace_bins(n, origin.device)
             x01, z = ops.ngp_sample_points(st.frame, origin, direction, length, n, st.alt_compress, u=u, random=True,
-                                           seed=_sample_seed(st), ray_index_base=st.ray_index_base, bins=st.bins)
+                                           seed=_sample_seed(st), ray_index_base=st.ray_index_base, bins=st.bins,
+                                           height=st.height)
         needs_grad = any(ctx.needs_input_grad[:3])  # (grad mode is off inside Function.forward)
         sigma_raw, color_raw, enc = field_forward(st, t16, pw16, dw16, x01, direction, b, n, want_enc=needs_grad)
         cs_raw = surface_forward(st, s16, sw16, origin, direction, length)
         cmap, catmo, csurf, tsurf, _, _ = ops.composite_forward(
-            z, color_raw.view(b, n, 4), sigma_raw.view(b, n, 1), cs_raw, st.z_scale, relu=True,
+            z, color_raw.view(b, n, 4), sigma_raw.view(b, n, st.n_density), cs_raw, st.z_scale, relu=True,
             want_weights=False, want_alpha=False)
         ctx.st = st
         ctx.enc = enc
         ctx.save_for_backward(t16, pw16, dw16, s16, sw16, origin, direction, length, x01, z, sigma_raw, color_raw,
                               cs_raw, catmo, tsurf)
         ctx.sizes = (pos_table.numel(), pos_w.numel(), dir_w.numel(), surf_table.numel(), surf_w.numel())
-        st.last = {"z": z, "sigma_raw": sigma_raw.view(b, n, 1), "color_raw": color_raw.view(b, n, 4),
+        st.last = {"z": z, "sigma_raw": sigma_raw.view(b, n, st.n_density), "color_raw": color_raw.view(b, n, 4),
                    "color_surf_raw": cs_raw, "x01": x01}
         return cmap, catmo, csurf
 
@@ -227,22 +237,25 @@ class NGPRenderFn(torch.autograd.Function):
         g_map = torch.zeros_like(catmo) if g_map is None else g_map
         d_atmo = (g_map + g_atmo if g_atmo is not None else g_map).contiguous().float()
         d_surf = (g_map + g_surf if g_surf is not None else g_map).contiguous().float()
-        absmax = torch.zeros(1, device=dev, dtype=_f32) if FIELD_IMPL != "simt" else None
-        compact = COMPACT_BWD and FIELD_IMPL != "simt" and ctx.enc is not None and os.environ.get("ATMONR_BWD_NARROW") is None
+        simt = field_impl(st) == "simt"
+        v = st.n_density
+        absmax = torch.zeros(1, device=dev, dtype=_f32) if not simt else None
+        compact = COMPACT_BWD and not simt and ctx.enc is not None and os.environ.get("ATMONR_BWD_NARROW") is None
         if compact:
             act_idx, n_act, dcolor, dsigma, dcs = ops.composite_backward_compact(
-                z, color_raw.view(b, n, 4), sigma_raw.view(b, n, 1), cs_raw, catmo, tsurf, d_atmo, d_surf,
+                z, color_raw.view(b, n, 4), sigma_raw.view(b, n, v), cs_raw, catmo, tsurf, d_atmo, d_surf,
                 st.z_scale, relu=True, grad_absmax=absmax)
             st.last["n_active"] = n_act
         else:
             dcolor, dsigma, dcs = ops.composite_backward(
-                z, color_raw.view(b, n, 4), sigma_raw.view(b, n, 1), cs_raw, catmo, tsurf, d_atmo, d_surf,
+                z, color_raw.view(b, n, 4), sigma_raw.view(b, n, v), cs_raw, catmo, tsurf, d_atmo, d_surf,
                 st.z_scale, relu=True, grad_absmax=absmax)
         d_table, d_pw, d_dw, d_s, d_sw = _gradient_buffers(st, ctx.sizes, dev)
-        if FIELD_IMPL == "simt":
+        if simt:
             L.call("atmonr_ngp_field_bwd", C.byref(st.grid3), L.ptr(t16), C.byref(st.pos_mlp), L.ptr(pw16),
                    C.byref(st.dir_mlp), L.ptr(dw16), L.ptr(x01), L.ptr(direction), L.ptr(dsigma), L.ptr(dcolor), b, n,
                    L.ptr(d_table), L.ptr(d_pw), L.ptr(d_dw), L.stream())
+            launch_prefetch(st)
         elif compact:
             L.call("atmonr_ngp_field_bwd_tc_compact", C.byref(st.grid3), C.byref(st.pos_mlp), L.ptr(pw16),
                    C.byref(st.dir_mlp), L.ptr(dw16), L.ptr(x01), L.ptr(direction), L.ptr(ctx.enc), L.ptr(act_idx),
@@ -274,11 +287,14 @@ class LazyResults(dict):
     they are detached (the trainer never differentiates through them)."""
 
     LAZY = ("color_fine", "sigma_fine", "weights_fine", "z_vals_fine", "color_surf")
+    LAZY_HEIGHT = ("norm_heights_fine",)        # instant_ngp.py:204-205, `include_height` only
 
     def __init__(self, eager: dict, st: NGPState):
         super().__init__(eager)
         self._st = st
         self._buf = dict(st.last)
+        if st.height is not None:
+            self.LAZY = self.LAZY + self.LAZY_HEIGHT
 
     def _materialise(self, key):
         b = self._buf
@@ -288,6 +304,8 @@ class LazyResults(dict):
             return torch.relu(b["sigma_raw"])[:, :-1]
         if key == "z_vals_fine":
             return b["z"]
+        if key == "norm_heights_fine":
+            return b["x01"][:, 3].view(b["z"].shape)
         if key == "color_surf":
             return torch.relu(b["color_surf_raw"])
         if key == "weights_fine":
@@ -312,6 +330,6 @@ def extract_sigma(st: NGPState, table16, pos_w16, pts: torch.Tensor) -> torch.Te
     p = pts.contiguous().double()
     n = p.shape[0]
     out = torch.empty(n, device=p.device, dtype=_f32)
-    L.call("atmonr_extract_sigma" if FIELD_IMPL == "simt" else "atmonr_extract_sigma_tc", C.byref(st.frame), C.byref(st.grid3), L.ptr(table16), C.byref(st.pos_mlp),
+    L.call("atmonr_extract_sigma" if field_impl(st) == "simt" else "atmonr_extract_sigma_tc", C.byref(st.frame), C.byref(st.grid3), L.ptr(table16), C.byref(st.pos_mlp),
            L.ptr(pos_w16), L.ptr(p), n, float(st.alt_compress), L.ptr(out), L.stream())
     return out.view(n, 1)

@@ -63,23 +63,33 @@ def preprocess_horizontal(frame: L.FrameT, pts: torch.Tensor) -> torch.Tensor:
 
 
 def ngp_sample_points(frame, origin, direction, length, n, alt_compress, u=None, random=True, seed=0,
-                      ray_index_base=0, bins=None, out=None):
-    """Fused instant_ngp.py:139-160 -> (x01 (B*n,3), z (B,n)); `out` = preallocated (x01, z)."""
+                      ray_index_base=0, bins=None, out=None, height=None):
+    """Fused instant_ngp.py:139-160 -> (x01 (B*n,3), z (B,n)); `out` = preallocated (x01, z).
+    height = (scale, offset (3 floats), ray_origin_height): `include_height`, x01 gets a fourth column
+    (atmonr_ngp_sample_points_height)."""
     origin, direction, length = _c(origin, _f32), _c(direction, _f32), _c(length, _f32)
     b = origin.shape[0]
+    d = 4 if height is not None else 3
     mode = 1 if u is not None else (2 if random else 0)
     if u is not None:
         u = _c(u, _f32)
     if out is not None:
         x01, z = out
-        assert x01.shape == (b * n, 3) and z.shape == (b, n) and x01.dtype == _f32 and z.dtype == _f32
+        assert x01.shape == (b * n, d) and z.shape == (b, n) and x01.dtype == _f32 and z.dtype == _f32
     else:
-        x01 = torch.empty((b * n, 3), device=origin.device, dtype=_f32)
+        x01 = torch.empty((b * n, d), device=origin.device, dtype=_f32)
         z = torch.empty((b, n), device=origin.device, dtype=_f32)
     if bins is None:
         bins = linspace_bins(n, origin.device)
-    L.call("atmonr_ngp_sample_points", C.byref(frame), L.ptr(origin), L.ptr(direction), L.ptr(length), L.ptr(u),
-           L.ptr(bins), b, n, mode, seed, ray_index_base, float(alt_compress), L.ptr(x01), L.ptr(z), L.stream())
+    if height is not None:
+        scale, offset, h0 = height
+        off = (C.c_double * 3)(*[float(v) for v in offset])
+        L.call("atmonr_ngp_sample_points_height", C.byref(frame), L.ptr(origin), L.ptr(direction), L.ptr(length), L.ptr(u),
+               L.ptr(bins), b, n, mode, seed, ray_index_base, float(alt_compress), float(scale), off, float(h0),
+               L.ptr(x01), L.ptr(z), L.stream())
+    else:
+        L.call("atmonr_ngp_sample_points", C.byref(frame), L.ptr(origin), L.ptr(direction), L.ptr(length), L.ptr(u),
+               L.ptr(bins), b, n, mode, seed, ray_index_base, float(alt_compress), L.ptr(x01), L.ptr(z), L.stream())
     return x01, z
 
 

@@ -2,9 +2,9 @@
 
 Same plugin surface (constructor, module names, state-dict layout, result keys, AdamW parameter
 groups). The six tiny-cuda-nn modules are replaced by atmonr.native.modules.{Encoding,Network};
-with the shipped configuration the whole forward/backward runs through the fused kernels of
-libatmonr_b200 (atmonr.native.fused), otherwise through the modular operators chained exactly
-like the reference's forward.
+the whole forward/backward runs through the fused launch chain of libatmonr_b200
+(atmonr.native.fused; `include_height` and `multi_band_extinction` included), and through the modular
+operators chained exactly like the reference's forward for shapes the chain does not cover.
 """
 
 from __future__ import annotations
@@ -52,13 +52,17 @@ class InstantNGPPipeline(Pipeline):
 
     # -------------------------------------------------------------------------------------
     def _make_fused_state(self):
-        """The fused kernels cover the shipped configuration: 3-D grid (16 levels x 2), one density,
-        4 bands, pos_mlp 32->[32]->16, dir_mlp 19->[32,32]->4, surf 2-D grid + SH -> [32,32] -> 4,
-        and either the 'horizontal' preprocessor or none."""
+        """The fused launch chain covers: 3-D grid (or 4-D with `include_height`), 16 levels x 2 features,
+        one density (or four with `multi_band_extinction`), 4 bands, pos_mlp 32->[32]->16, dir_mlp
+        19->[32,32]->4 (16->[32,32]->4 with four densities), surf 2-D grid + SH -> [32,32] -> 4, and either the
+        'horizontal' preprocessor or none. The shipped shape runs on the tcgen05 kernels, the two optional
+        inputs on the thread-per-sample kernels of the same chain (atmonr.native.fused.field_impl)."""
         cfg = self.config
         frame = getattr(self.point_preprocessor, "frame", None)
+        nd = self.num_density_outputs
+        dir_in = (32, 2) if nd == 1 else (16, 2)
         ok = (
-            self.num_density_outputs == 1 and cfg["num_bands"] == 4 and not cfg["include_height"]
+            nd in (1, 4) and cfg["num_bands"] == 4
             and (self.point_preprocessor is None or frame is not None)
             and self.pos_encoder.grid is not None and self.pos_encoder.grid.n_levels == 16
             and len(self.pos_encoder.parts) == 1
@@ -66,17 +70,20 @@ class InstantNGPPipeline(Pipeline):
             and [p[0] for p in self.surf_encoder.parts] == ["HashGrid", "SphericalHarmonics"]
             and [p[0] for p in self.dir_encoder.parts] == ["SphericalHarmonics", "Identity"]
             and (self.pos_mlp.shape.in_pad, self.pos_mlp.shape.n_hidden) == (32, 1)
-            and (self.dir_mlp.shape.in_pad, self.dir_mlp.shape.n_hidden) == (32, 2)
+            and (self.dir_mlp.shape.in_pad, self.dir_mlp.shape.n_hidden) == dir_in
             and (self.surf_mlp.shape.in_pad, self.surf_mlp.shape.n_hidden) == (48, 2)
         )
         if not ok:
             return None
+        height = None
+        if cfg["include_height"]:   # samplers.py:168-195 on the [0,1]^3 point (instant_ngp.py:155-156)
+            height = (float(self.scale), [float(v) for v in self.offset.tolist()], float(self.ray_origin_height))
         return fused.NGPState(
             frame=frame if frame is not None else L.disabled_frame(),
             grid3=self.pos_encoder.grid, grid2=self.surf_encoder.grid,
             pos_mlp=self.pos_mlp.shape, dir_mlp=self.dir_mlp.shape, surf_mlp=self.surf_mlp.shape,
             n_samples=int(cfg["num_samples_per_ray"]), alt_compress=float(cfg["alt_compress_factor"]),
-            z_scale=self.scale / 1000,
+            z_scale=self.scale / 1000, n_density=nd, height=height,
         )
 
     def send_tensors_to(self, device: int) -> None:
@@ -158,8 +165,9 @@ class InstantNGPPipeline(Pipeline):
 
     def extract(self, pts: torch.Tensor) -> torch.Tensor:
         """instant_ngp.py:208-247: (n,3) normalised scene points -> (n, n_density) extinction."""
-        if self.fused_state is not None:
-            return fused.extract_sigma(self.fused_state, self.pos_encoder.table_f16(), self.pos_mlp.weights_f16(), pts)
+        st = self.fused_state
+        if st is not None and st.n_density == 1 and st.height is None:
+            return fused.extract_sigma(st, self.pos_encoder.table_f16(), self.pos_mlp.weights_f16(), pts)
         if self.point_preprocessor:
             pts = self.point_preprocessor(pts[None])[0]
         pts = (pts + 1) / 2

@@ -299,9 +299,11 @@ def test_ngp_pipeline_forward_loss_gradients_vs_oracle(scene, impl, monkeypatch)
 @pytest.mark.parametrize("height,multi_band", [(True, False), (False, True), (True, True)])
 def test_ngp_optional_inputs_vs_oracle(scene, height, multi_band):
     """`include_height` (4-D hash grid over [x, y, z/8, h], samplers.py:168-195) and
-    `multi_band_extinction` (one density per band): off in the shipped configs, served by the
-    operator-by-operator path. include_height excludes the 'horizontal' preprocessor
-    (pipeline.py:30-32)."""
+    `multi_band_extinction` (one density per band): off in the shipped configs. Both run through the fused
+    launch chain (height-column sampler, field kernels templated on the grid dimensionality and the number
+    of densities, compositing with one density per band) AND through the operator-by-operator path; each
+    is compared with the oracle. include_height excludes the 'horizontal' preprocessor (pipeline.py:30-32)."""
+    from atmonr.native import fused
     cfg = ngp_config(24)
     cfg["include_height"], cfg["multi_band_extinction"] = height, multi_band
     if height:
@@ -319,18 +321,27 @@ def test_ngp_optional_inputs_vs_oracle(scene, height, multi_band):
     from atmonr.pipelines.instant_ngp import InstantNGPPipeline
     pipe = InstantNGPPipeline(cfg, ds)
     pipe.send_tensors_to(0)
-    assert pipe.fused_state is None          # not the fused kernels' configuration
+    st = pipe.fused_state
+    assert st is not None and fused.field_impl(st) == "simt"
+    assert st.n_density == (4 if multi_band else 1) and (st.height is not None) == height
     load_params(pipe, params)
     bc = to_cuda(b)
-    out = pipe.forward(bc, u=u.cuda())
-    lg = pipe.compute_loss(bc, out)
-    lg.backward()
-    assert out["sigma_fine"].shape[-1] == (4 if multi_band else 1)
-    for key in ("color_map_fine", "color_map_atmo", "color_map_surf", "sigma_fine", "color_fine"):
-        assert rel_err(out[key], res[key]) < 2e-3, key
-    assert rel_err(lg, loss) < 1e-3
-    for name in ("pos_mlp", "dir_mlp", "surf_mlp", "pos_encoder", "surf_encoder"):
-        assert rel_err(getattr(pipe, name).params.grad, params[name].grad) < 4e-3, name
+    for path in ("fused", "modular"):
+        if path == "modular":
+            pipe.fused_state = None
+        for name in ("pos_mlp", "dir_mlp", "surf_mlp", "pos_encoder", "surf_encoder"):
+            getattr(pipe, name).params.grad = None
+        out = pipe.forward(bc, u=u.cuda())
+        lg = pipe.compute_loss(bc, out)
+        lg.backward()
+        assert out["sigma_fine"].shape[-1] == (4 if multi_band else 1)
+        for key in ("color_map_fine", "color_map_atmo", "color_map_surf", "sigma_fine", "color_fine"):
+            assert rel_err(out[key], res[key]) < 2e-3, (path, key)
+        if height:
+            assert rel_err(out["norm_heights_fine"], res["pts01"][:, 3].view(40, 24)) < 1e-6, path
+        assert rel_err(lg, loss) < 1e-3, path
+        for name in ("pos_mlp", "dir_mlp", "surf_mlp", "pos_encoder", "surf_encoder"):
+            assert rel_err(getattr(pipe, name).params.grad, params[name].grad) < 4e-3, (path, name)
 
 
 def test_ngp_training_tracks_oracle(scene):
