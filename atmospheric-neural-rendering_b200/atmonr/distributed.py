@@ -3,9 +3,11 @@ scripts/train.py:94).
 
 One process per GPU (torchrun), every rank holds the full parameters and ray tables, each global
 batch is split into equal contiguous ray shards, every rank computes the MEAN loss of its shard
-and the gradients are summed with one NCCL all-reduce per parameter tensor and scaled by
-1/world_size inside the fused AdamW kernel -- identical to the single-GPU global-mean loss when
-the shards are equal-sized. Extraction shards voxel columns with no communication.
+and the gradients are summed over NCCL and scaled by 1/world_size inside the fused AdamW kernel --
+identical to the single-GPU global-mean loss when the shards are equal-sized. The small tensors
+(MLPs) are all-reduced; the two hash tables are reduce-scattered, updated slice-wise and their fp16
+shadow all-gathered (atmonr.optim.FusedAdamW.shard_large_parameters). Extraction shards voxel
+columns with no communication.
 """
 
 from __future__ import annotations
@@ -57,9 +59,10 @@ def all_reduce_gradients(optimizer) -> None:
     fused = hasattr(optimizer, "grad_scale")
     if fused:
         optimizer.grad_scale = 1.0 / world
+    sharded = getattr(optimizer, "is_sharded", lambda p: False)
     for group in optimizer.param_groups:
         for p in group["params"]:
-            if p.grad is None:
+            if p.grad is None or sharded(p):      # sharded tensors are reduce-scattered inside step()
                 continue
             td.all_reduce(p.grad, op=td.ReduceOp.SUM)
             if not fused:

@@ -9,6 +9,8 @@ NCCL before the optimizer step (atmonr.distributed).
 
 from __future__ import annotations
 
+import os
+
 from datetime import datetime
 from pathlib import Path
 
@@ -67,6 +69,9 @@ class Trainer:
         self.iter_count = 0
         self.num_epochs = int(-(self.config["num_iters"] // -len(self.dataloader)))
         self.optimizer = pipeline.get_optimizer(self.config["optimizer"])
+        if self.world_size > 1 and hasattr(self.optimizer, "shard_large_parameters") and os.environ.get("ATMONR_DP_SHARD", "1") != "0":
+            # hash tables: reduce-scatter -> AdamW on 1/world of the entries -> all-gather of the fp16 shadow
+            self.optimizer.shard_large_parameters()
         sched = self.config["scheduler"]
         if sched["type"] == "target_lr":
             gamma = (sched["final_lr"] / self.config["optimizer"]["lr"]) ** (1 / self.num_epochs)
@@ -184,6 +189,8 @@ class Trainer:
         self.epoch_idx += 1
         if self.config["scheduler"]["type"] == "target_lr":
             self.scheduler.step()
+        if hasattr(self.optimizer, "consolidate"):
+            self.optimizer.consolidate()     # collective: float32 masters / moments of all slices, before the checkpoint
         if self.rank != 0:
             return
         metrics = self.dataset.get_image_metrics(pred, target)

@@ -306,8 +306,27 @@ k_linear_tc(const float* __restrict__ x, int64_t ldx, const float* __restrict__ 
     const int n_valid = min(n_cols, n_out - n0);         // real output columns of this CTA
     const int rows = (int)min((int64_t)lin::kRows, M - row0);
     const bool vec = (ldy & 3) == 0 && (n0 & 3) == 0 && (reinterpret_cast<uintptr_t>(y) & 15) == 0;
+    const bool om_vec = !out_mask || ((ldom & 3) == 0 && (reinterpret_cast<uintptr_t>(out_mask) & 15) == 0);
     for (int h0 = 0; h0 < n_cols; h0 += lin::kHalf) {
       if (h0 > 0) __syncthreads();                       // the previous half has been written out
+      const int w_valid = min(lin::kHalf, n_valid - h0);   // real columns of this half
+      // out_mask (M, n_out): the output is zeroed where out_mask <= 0 -- the ReLU derivative of the layer
+      // whose OUTPUT this product's result is the gradient of, applied where the rows are written out with
+      // coalesced accesses (so that no downstream product has to read a mask in its main loop).
+      const float* omh = out_mask ? out_mask + n0 + h0 : nullptr;
+      // Full half of a full tile (the common case): thread t writes the 16-byte groups t, t + 256, ... of
+      // the 128 x 32 groups; its 16 mask groups are requested HERE, before the accumulator is staged, so
+      // that their latency sits underneath the TMEM reads and the shared-memory pass (one dependent global
+      // load per written group measured 62 % of the warp samples on the long scoreboard).
+      const bool fast = vec && om_vec && rows == lin::kRows && w_valid == lin::kHalf;
+      float4 mreg[16];
+      if (fast && omh) {
+#pragma unroll
+        for (int u = 0; u < 16; ++u) {
+          const int i = tid + u * lin::kThreads;
+          mreg[u] = *reinterpret_cast<const float4*>(omh + (row0 + (i >> 5)) * ldom + 4 * (i & 31));
+        }
+      }
 #pragma unroll 1
       for (int cb = 0; cb < 64; cb += 16) {
         const int lc = (warp >> 2) * 64 + cb, col = h0 + lc;
@@ -326,14 +345,22 @@ k_linear_tc(const float* __restrict__ x, int64_t ldx, const float* __restrict__ 
         for (int q = 0; q < 4; ++q) dst[q] = make_float4(v[4 * q], v[4 * q + 1], v[4 * q + 2], v[4 * q + 3]);
       }
       __syncthreads();
-      const int w_valid = min(lin::kHalf, n_valid - h0);   // real columns of this half
       if (w_valid <= 0) continue;                          // uniform
       float* yh = y + n0 + h0;
-      // out_mask (M, n_out): the output is zeroed where out_mask <= 0 -- the ReLU derivative of the layer
-      // whose OUTPUT this product's result is the gradient of, applied where the rows are written out with
-      // coalesced accesses (so that no downstream product has to read a mask in its main loop)
-      const float* omh = out_mask ? out_mask + n0 + h0 : nullptr;
-      if (vec && (!omh || ((ldom & 3) == 0 && (reinterpret_cast<uintptr_t>(out_mask) & 15) == 0))) {
+      if (fast) {
+#pragma unroll
+        for (int u = 0; u < 16; ++u) {
+          const int i = tid + u * lin::kThreads;
+          const int rr = i >> 5, q = i & 31;
+          float4 v = *reinterpret_cast<const float4*>(tile + rr * pitch + 4 * q);
+          if (omh) {
+            const float4 m = mreg[u];
+            v.x = m.x > 0.0f ? v.x : 0.0f, v.y = m.y > 0.0f ? v.y : 0.0f;
+            v.z = m.z > 0.0f ? v.z : 0.0f, v.w = m.w > 0.0f ? v.w : 0.0f;
+          }
+          *reinterpret_cast<float4*>(yh + (row0 + rr) * ldy + 4 * q) = v;
+        }
+      } else if (vec && om_vec) {
         const int q_per_row = w_valid >> 2;                // whole float4 groups
         for (int i = tid; i < rows * q_per_row; i += lin::kThreads) {
           const int rr = i / q_per_row, q = i - rr * q_per_row;

@@ -305,6 +305,9 @@ def run_native(args) -> None:
     pipe.send_tensors_to(local)
     dist.broadcast_parameters(pipe.parameters())
     opt = pipe.get_optimizer(OPT_CFG)
+    dp_sharded = world > 1 and os.environ.get("ATMONR_DP_SHARD", "1") != "0"
+    if dp_sharded:
+        opt.shard_large_parameters()      # tables: reduce-scatter -> AdamW on 1/world -> all-gather of the fp16 shadow
     B, K, W = args.rays, args.steps, args.warmup
 
     # fixed set of batches, each rank its own rays (weak scaling)
@@ -594,6 +597,8 @@ def run_native(args) -> None:
             "workload": f"Instant-NGP (configs/instant_ngp.json) train step, {B} rays/GPU x {args.samples} samples/ray, "
                         f"{args.granule} HARP2-shaped granule, 4 bands 10/10/60/10 views",
             "rays_per_gpu": B, "samples_per_ray": args.samples, "parallelism": f"dp{world}",
+            "gradient_exchange": ("hash tables: reduce-scatter -> AdamW on 1/world of the entries -> all-gather of the fp16 "
+                                  "shadow; MLPs: all-reduce" if dp_sharded else ("all-reduce" if world > 1 else "none")),
             "backward": (f"samples with a non-zero incoming gradient only ({active_fraction:.3f} of all samples in the last step; exact)"
                          if _fused.COMPACT_BWD else "dense (every sample)"),
             "l2": "inputs larger than L2: per-step working set (x01, sigma, colour, gradients) is several GB",

@@ -116,3 +116,83 @@ def test_shard_slice_partitions():
             parts = [shard_slice(n, r, w) for r in range(w)]
             covered = [i for s in parts for i in range(s.start, s.stop)]
             assert covered == list(range(n))
+
+
+def _torch_adamw_step(param, grad, exp_avg, exp_avg_sq, param_f16, lr, beta1, beta2, eps, weight_decay, step,
+                      grad_scale=1.0, zero_grad=False):
+    """Stand-in for the CUDA kernel on CPU tensors (test infrastructure: the kernel itself is checked against
+    torch.optim.AdamW on the GPU): torch's single-tensor AdamW arithmetic, in place, shadow refreshed."""
+    g = grad * grad_scale
+    param.mul_(1 - lr * weight_decay)
+    exp_avg.lerp_(g, 1 - beta1)
+    exp_avg_sq.mul_(beta2).addcmul_(g, g, value=1 - beta2)
+    denom = (exp_avg_sq.sqrt() / (1 - beta2 ** step) ** 0.5).add_(eps)
+    param.addcdiv_(exp_avg, denom, value=-lr / (1 - beta1 ** step))
+    if param_f16 is not None:
+        param_f16.copy_(param.half())
+    if zero_grad:
+        grad.zero_()
+
+
+def _sharded_worker(rank, world, port, out):
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port), RANK=str(rank), WORLD_SIZE=str(world), LOCAL_RANK=str(rank))
+    import sys
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    sys.path.insert(0, os.path.join(root, "atmospheric-neural-rendering_b200"))
+    from atmonr import distributed as dist
+    from atmonr.native import ops
+    from atmonr.native.modules import shadow_of
+    from atmonr.optim import FusedAdamW
+    ops.adamw_step = _torch_adamw_step
+    dist.init_from_env("gloo")
+    torch.manual_seed(0)
+    big = torch.nn.Parameter(torch.randn(4096))      # "hash table": sharded
+    small = torch.nn.Parameter(torch.randn(40))      # "MLP": all-reduced
+    opt = FusedAdamW([{"params": [big], "weight_decay": 0.0}, {"params": [small], "weight_decay": 0.01}],
+                     lr=1e-2, betas=(0.9, 0.99), eps=1e-15)
+    opt.shard_large_parameters(min_numel=1024)
+    assert opt.is_sharded(big) and not opt.is_sharded(small)
+    shadows = []
+    for it in range(3):
+        g = torch.Generator().manual_seed(10 * it + rank)        # every rank its own gradient
+        big.grad, small.grad = torch.randn(4096, generator=g), torch.randn(40, generator=g)
+        dist.all_reduce_gradients(opt)
+        opt.step()
+        shadows.append(shadow_of(big).clone())
+    stale = big.detach().clone()
+    opt.consolidate()
+    torch.save({"big": big.detach().clone(), "small": small.detach().clone(), "shadow": shadows, "stale": stale,
+                "m": opt.state[big]["exp_avg"].clone(), "v": opt.state[big]["exp_avg_sq"].clone(),
+                "state_keys": sorted(opt.state_dict()["state"][0])}, out.format(rank))
+    td.destroy_process_group()
+
+
+def test_sharded_optimizer_equals_the_replicated_one(tmp_path):
+    """FusedAdamW.shard_large_parameters: reduce-scatter -> AdamW on this rank's slice -> all-gather
+    of the fp16 shadow, against one process that applies AdamW to the mean of the two ranks' gradients; the
+    shadow is complete on every rank after every step, the float32 master and the moments after consolidate()."""
+    world, port = 2, _free_port()
+    out = str(tmp_path / "sh{}.pt")
+    mp.spawn(_sharded_worker, args=(world, port, out), nprocs=world, join=True)
+    r0, r1 = torch.load(out.format(0)), torch.load(out.format(1))
+    torch.manual_seed(0)
+    big, small = torch.randn(4096), torch.randn(40)
+    mb, vb, ms, vs = torch.zeros(4096), torch.zeros(4096), torch.zeros(40), torch.zeros(40)
+    want_shadow = []
+    for it in range(3):
+        gs = [torch.Generator().manual_seed(10 * it + r) for r in range(2)]
+        gb, gsm = [], []
+        for g in gs:
+            gb.append(torch.randn(4096, generator=g)); gsm.append(torch.randn(40, generator=g))
+        _torch_adamw_step(big, gb[0] + gb[1], mb, vb, None, 1e-2, 0.9, 0.99, 1e-15, 0.0, it + 1, grad_scale=0.5)
+        _torch_adamw_step(small, gsm[0] + gsm[1], ms, vs, None, 1e-2, 0.9, 0.99, 1e-15, 0.01, it + 1, grad_scale=0.5)
+        want_shadow.append(big.half())
+    for r in (r0, r1):
+        assert torch.allclose(r["big"], big, rtol=1e-6, atol=1e-7) and torch.allclose(r["small"], small, rtol=1e-6, atol=1e-7)
+        assert torch.allclose(r["m"], mb, rtol=1e-6, atol=1e-8) and torch.allclose(r["v"], vb, rtol=1e-6, atol=1e-10)
+        for got, want in zip(r["shadow"], want_shadow):
+            assert torch.equal(got, want)
+        assert r["state_keys"] == ["exp_avg", "exp_avg_sq", "step"]
+    # before consolidate() each rank's master copy was current on its own half only
+    assert torch.allclose(r0["stale"][:2048], big[:2048], rtol=1e-6, atol=1e-7) and not torch.allclose(r0["stale"][2048:], big[2048:])
+    assert torch.allclose(r1["stale"][2048:], big[2048:], rtol=1e-6, atol=1e-7) and not torch.allclose(r1["stale"][:2048], big[:2048])

@@ -223,6 +223,7 @@ def test_nerf_mlp_node_matches_the_layer_by_layer_model(terms):
         errs = {"colour": rel(a[0], b[0]), "density": rel(a[1], b[1]), "dx_pos": rel(a[2][:, :76], b[2][:, :76]),
                 "params": max(rel(pa, pb) for pa, pb in zip(a[3], b[3]))}
         print(f"terms={terms} V={net.volume_channels}:", {k: f"{v:.2e}" for k, v in errs.items()})
+        print("   per parameter:", [f"{n}:{rel(pa, pb):.1e}" for (n, _), pa, pb in zip(net.named_parameters(), a[3], b[3])])
         assert errs["colour"] <= ftol and errs["density"] <= ftol, errs
         assert errs["dx_pos"] <= gtol and float(b[2][:, 76:].abs().max()) == 0, errs
         for pa, pb in zip(a[3], b[3]):
