@@ -48,7 +48,11 @@ class NerfMlpFn(torch.autograd.Function):
         for k in (6, 7):               # fc7, fc8
             h = ops.linear_forward(h, w[k], b[k], True)
             acts.append(h)
-        feat = ops.linear_forward(h, w[8], b[8], False)            # fc9: (M, hidden + V), no activation
+        # fc9: (M, hidden + V), no activation; rows padded to a multiple of 4 floats so that fc10 and the weight
+        # gradients read them with 16-byte loads (hidden + 1 columns in the coarse network)
+        n9 = w[8].shape[0]
+        feat = ops.linear_forward(h, w[8], b[8], False,
+                                  out=torch.empty((x.shape[0], (n9 + 3) // 4 * 4), device=x.device, dtype=_f32))[:, :n9]
         hid = ops.linear_forward(feat[:, :hidden], w[9], b[9], True, x2=x_dir)   # fc10
         rgb = ops.linear_forward(hid, w[10], b[10], False)         # fc11
         sigma = feat[:, hidden:]
