@@ -91,7 +91,7 @@ SIGNATURES = {
     "atmonr_append_heights": [P, I64, F64, C.POINTER(C.c_double), F64, P, P],
     "atmonr_tc_probe": [P, P, I32, P, P],
     "atmonr_linear_prep": [P, I32, I32, I32, I32, P, P],
-    "atmonr_linear_fwd_tc": [P, I64, P, I64, I32, P, I64, P, P, I64, I32, I32, I32, I32, P, I64, P, I64, P],
+    "atmonr_linear_fwd_tc": [P, I64, P, I64, I32, P, I64, P, P, I64, I32, I32, I32, I32, P, I64, P, P, P, I64, P],
     "atmonr_linear_dw_tc": [P, I64, P, I64, P, I64, P, I64, I32, I64, I32, I32, I32, P, P, P],
     "atmonr_ngp_field_fwd_tc": [GP, P, MP, P, MP, P, P, P, I64, I32, P, P, P, P],
     "atmonr_ngp_field_bwd_tc": [GP, P, MP, P, MP, P, P, P, P, P, P, P, I64, I32, P, P, P, P],

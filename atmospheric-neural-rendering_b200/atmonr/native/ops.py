@@ -186,12 +186,15 @@ def _segments(x: torch.Tensor, x2):
 
 def linear_forward(x: torch.Tensor, weight: torch.Tensor, bias, relu: bool, transpose: bool = False,
                    mask: torch.Tensor | None = None, x2: torch.Tensor | None = None, terms: int | None = None,
-                   out_mask: torch.Tensor | None = None, out: torch.Tensor | None = None) -> torch.Tensor:
+                   out_mask: torch.Tensor | None = None, out: torch.Tensor | None = None,
+                   out_bits: torch.Tensor | None = None, want_bits: bool = False):
     """act(X' @ B.T + bias) with B = weight (n_out, k_in), or B = weight.T when `transpose` (then
     weight is (k_in, n_out)); X = x or [x | x2]; X' = X where mask > 0 and 0 elsewhere when a mask is
     given; the result is zeroed where out_mask (m, n_out) <= 0 when that is given. x, x2, mask and out_mask
     may be column slices of wider float32 tensors; `out`: a (m, >= n_out) float32 tensor (or column slice
-    starting at a multiple of 4) that receives the result instead of a new tensor."""
+    starting at a multiple of 4) that receives the result instead of a new tensor. want_bits (with relu,
+    n_out % 128 == 0): also return the sign bits of the result, (m, n_out / 32) int32 in the kernel's own
+    layout; out_bits: such an array, used like out_mask (32 bytes per 256-wide row instead of 1 KB)."""
     if not weight.is_cuda:
         raise L.NativeLibraryError("libatmonr_b200 operates on CUDA tensors only (no CPU fallback)")
     x, ldx, x2, x2p, ldx2, k_split, k_cols = _segments(x, x2)
@@ -221,11 +224,14 @@ def linear_forward(x: torch.Tensor, weight: torch.Tensor, bias, relu: bool, tran
         if out.dtype != _f32 or out.dim() != 2 or out.shape[0] != m or out.shape[1] < n_out or out.stride(1) != 1:
             raise ValueError("linear_forward: `out` must be a (rows, >= n_out) float32 tensor with contiguous rows")
         y, yp, ldy = out, out.data_ptr(), out.stride(0)
+    bits = torch.empty((m, n_out // 32), device=x.device, dtype=torch.int32) if want_bits else None
+    if out_bits is not None and tuple(out_bits.shape) != (m, n_out // 32):
+        raise ValueError("linear_forward: out_bits must be (rows, n_out / 32)")
     L.call("atmonr_linear_prep", L.ptr(weight), n_out, k_in, int(transpose), terms, L.ptr(planes), L.stream())
     b = None if bias is None else _c(bias.detach(), _f32)
     L.call("atmonr_linear_fwd_tc", x.data_ptr(), ldx, x2p, ldx2, k_split, mp, ldm, L.ptr(planes), L.ptr(b), m, n_out,
-           k_in, int(relu), terms, omp, ldom, yp, ldy, L.stream())
-    return y
+           k_in, int(relu), terms, omp, ldom, L.ptr(out_bits), L.ptr(bits), yp, ldy, L.stream())
+    return (y, bits) if want_bits else y
 
 
 def linear_weight_grad(dy: torch.Tensor, x: torch.Tensor, mask: torch.Tensor | None = None,

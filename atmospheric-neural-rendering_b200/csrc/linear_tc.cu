@@ -173,7 +173,8 @@ template <int TERMS>
 __global__ void __launch_bounds__(lin::kThreads, TERMS == 2 ? 2 : 1)
 k_linear_tc(const float* __restrict__ x, int64_t ldx, const float* __restrict__ x2, int64_t ldx2, int k_split,
             const float* __restrict__ mask, int64_t ldm, const uint8_t* __restrict__ planes, const float* __restrict__ bias, int64_t M, int n_out, int k_in,
-            int k_chunks, int act, const float* __restrict__ out_mask, int64_t ldom, float* __restrict__ y, int64_t ldy) {
+            int k_chunks, int act, const float* __restrict__ out_mask, int64_t ldom, const uint32_t* __restrict__ bits_in,
+            uint32_t* __restrict__ bits_out, float* __restrict__ y, int64_t ldy) {
   extern __shared__ __align__(128) uint8_t smem[];
   using MapT = lin::Map<TERMS>;
   uint64_t* bar = reinterpret_cast<uint64_t*>(smem + MapT::kBar);          // bar[s]: MMAs that read stage s are done
@@ -307,25 +308,40 @@ k_linear_tc(const float* __restrict__ x, int64_t ldx, const float* __restrict__ 
     const int rows = (int)min((int64_t)lin::kRows, M - row0);
     const bool vec = (ldy & 3) == 0 && (n0 & 3) == 0 && (reinterpret_cast<uintptr_t>(y) & 15) == 0;
     const bool om_vec = !out_mask || ((ldom & 3) == 0 && (reinterpret_cast<uintptr_t>(out_mask) & 15) == 0);
+    const int wpr = (n_out >> 7) << 2;                   // sign-bit words per row: 4 per 128 columns
     for (int h0 = 0; h0 < n_cols; h0 += lin::kHalf) {
       if (h0 > 0) __syncthreads();                       // the previous half has been written out
       const int w_valid = min(lin::kHalf, n_valid - h0);   // real columns of this half
-      // out_mask (M, n_out): the output is zeroed where out_mask <= 0 -- the ReLU derivative of the layer
-      // whose OUTPUT this product's result is the gradient of, applied where the rows are written out with
-      // coalesced accesses (so that no downstream product has to read a mask in its main loop).
+      // out_mask (M, n_out) floats / bits_in (M, n_out / 32) words: the output is zeroed where the mask is
+      // <= 0 / the bit is clear -- the ReLU derivative of the layer whose OUTPUT this product's result is
+      // the gradient of, applied where the rows are written out with coalesced accesses (so that no
+      // downstream product has to read a mask in its main loop). bits_out: the sign bits of this
+      // product's own ReLU output, for the backward pass to use that way (32 bytes per 256-wide row
+      // instead of re-reading 1 KB of activations). Bit layout, shared by writer and reader: row r,
+      // 128-column half h, word k (0..3), bit q  <->  column 128 h + 4 q + k, i.e. exactly the (lane,
+      // component) that handles the column in the loops below.
       const float* omh = out_mask ? out_mask + n0 + h0 : nullptr;
-      // Full half of a full tile (the common case): thread t writes the 16-byte groups t, t + 256, ... of
-      // the 128 x 32 groups; its 16 mask groups are requested HERE, before the accumulator is staged, so
-      // that their latency sits underneath the TMEM reads and the shared-memory pass (one dependent global
-      // load per written group measured 62 % of the warp samples on the long scoreboard).
-      const bool fast = vec && om_vec && rows == lin::kRows && w_valid == lin::kHalf;
+      // Whole, aligned half (every 256-/128-wide layer): thread t handles the 16-byte groups t, t + 256, ...
+      // = row (t / 32) + 8 u, group lane. Its 16 mask groups (or sign words) are requested HERE, before
+      // the accumulator is staged, so that their latency sits underneath the TMEM reads and the
+      // shared-memory pass (one dependent global load per written group measured 62 % of the warp
+      // samples on the long scoreboard).
+      const bool fast = vec && om_vec && w_valid == lin::kHalf;
+      const int lane = tid & 31, wrow = tid >> 5;
+      const int bword = ((n0 + h0) >> 7) << 2;
       float4 mreg[16];
       if (fast && omh) {
 #pragma unroll
-        for (int u = 0; u < 16; ++u) {
-          const int i = tid + u * lin::kThreads;
-          mreg[u] = *reinterpret_cast<const float4*>(omh + (row0 + (i >> 5)) * ldom + 4 * (i & 31));
-        }
+        for (int u = 0; u < 16; ++u)
+          if (wrow + 8 * u < rows)
+            mreg[u] = *reinterpret_cast<const float4*>(omh + (row0 + wrow + 8 * u) * ldom + 4 * lane);
+      } else if (fast && bits_in) {
+#pragma unroll
+        for (int u = 0; u < 16; ++u)
+          if (wrow + 8 * u < rows) {
+            const uint4 b = *reinterpret_cast<const uint4*>(bits_in + (row0 + wrow + 8 * u) * wpr + bword);
+            mreg[u] = make_float4(__uint_as_float(b.x), __uint_as_float(b.y), __uint_as_float(b.z), __uint_as_float(b.w));
+          }
       }
 #pragma unroll 1
       for (int cb = 0; cb < 64; cb += 16) {
@@ -350,15 +366,24 @@ k_linear_tc(const float* __restrict__ x, int64_t ldx, const float* __restrict__ 
       if (fast) {
 #pragma unroll
         for (int u = 0; u < 16; ++u) {
-          const int i = tid + u * lin::kThreads;
-          const int rr = i >> 5, q = i & 31;
-          float4 v = *reinterpret_cast<const float4*>(tile + rr * pitch + 4 * q);
+          const int rr = wrow + 8 * u;
+          if (rr >= rows) break;                           // warp-uniform
+          float4 v = *reinterpret_cast<const float4*>(tile + rr * pitch + 4 * lane);
           if (omh) {
             const float4 m = mreg[u];
             v.x = m.x > 0.0f ? v.x : 0.0f, v.y = m.y > 0.0f ? v.y : 0.0f;
             v.z = m.z > 0.0f ? v.z : 0.0f, v.w = m.w > 0.0f ? v.w : 0.0f;
+          } else if (bits_in) {
+            const float4 m = mreg[u];
+            v.x = ((__float_as_uint(m.x) >> lane) & 1u) ? v.x : 0.0f, v.y = ((__float_as_uint(m.y) >> lane) & 1u) ? v.y : 0.0f;
+            v.z = ((__float_as_uint(m.z) >> lane) & 1u) ? v.z : 0.0f, v.w = ((__float_as_uint(m.w) >> lane) & 1u) ? v.w : 0.0f;
           }
-          *reinterpret_cast<float4*>(yh + (row0 + rr) * ldy + 4 * q) = v;
+          *reinterpret_cast<float4*>(yh + (row0 + rr) * ldy + 4 * lane) = v;
+          if (bits_out) {
+            const uint32_t b0 = __ballot_sync(0xffffffffu, v.x > 0.0f), b1 = __ballot_sync(0xffffffffu, v.y > 0.0f);
+            const uint32_t b2 = __ballot_sync(0xffffffffu, v.z > 0.0f), b3 = __ballot_sync(0xffffffffu, v.w > 0.0f);
+            if (lane == 0) *reinterpret_cast<uint4*>(bits_out + (row0 + rr) * wpr + bword) = make_uint4(b0, b1, b2, b3);
+          }
         }
       } else if (vec && om_vec) {
         const int q_per_row = w_valid >> 2;                // whole float4 groups
@@ -499,25 +524,34 @@ k_linear_dw_tc(const float* __restrict__ dy, int64_t ldy, const float* __restric
   for (int j = 0; j < 8; ++j) colsum[j] = 0.0f;
   const bool want_db = db != nullptr && blockIdx.z == 0;
 
-  float vdy[4][8], vxx[4][8];   // this thread's values of the chunk being staged; requested one chunk ahead
-  fetch_rows(dy, ldy, nullptr, 0, n_out, mask, ldm, c_lo * ldw::kChunk, M, n0, n_out, vy, tid, vdy);
-  fetch_rows(x, ldx, x2, ldx2, k_split, nullptr, 0, c_lo * ldw::kChunk, M, k0, k_in, vx, tid, vxx);
+  // This thread's values of the chunks being staged, requested TWO chunks ahead: set A serves the even
+  // iterations, set B the odd ones; a set is refilled (chunk it + 2) right after its values have been split
+  // and stored, so two chunks (128 KB per SM) are in flight while the tensor core works on a third. (One
+  // chunk ahead left the kernel at a third of the DRAM rate, the staging warps waiting on the loads.)
+  float ady[4][8], axx[4][8], bdy[4][8], bxx[4][8];
+  auto fetch = [&](int64_t c, float (&vdy)[4][8], float (&vxx)[4][8]) {
+    // past the slab: row_lo >= the slab's end; fetch_rows zero-fills rows >= M, and a chunk past c_hi is
+    // never staged, so clamping to M keeps the loads inside the matrices
+    const int64_t row_lo = c < c_hi ? c * ldw::kChunk : M;
+    fetch_rows(dy, ldy, nullptr, 0, n_out, mask, ldm, row_lo, M, n0, n_out, vy, tid, vdy);
+    fetch_rows(x, ldx, x2, ldx2, k_split, nullptr, 0, row_lo, M, k0, k_in, vx, tid, vxx);
+  };
+  fetch(c_lo, ady, axx);
+  fetch(c_lo + 1, bdy, bxx);
   int it = 0;
   for (int64_t c = c_lo; c < c_hi; ++c, ++it) {
     const int s = it & 1;
     uint8_t* stage = smem + s * MapT::kStage;
-    float cdy[4][8], cxx[4][8];
-#pragma unroll
-    for (int a = 0; a < 4; ++a)
-#pragma unroll
-      for (int j = 0; j < 8; ++j) cdy[a][j] = vdy[a][j], cxx[a][j] = vxx[a][j];
-    if (c + 1 < c_hi) {
-      fetch_rows(dy, ldy, nullptr, 0, n_out, mask, ldm, (c + 1) * ldw::kChunk, M, n0, n_out, vy, tid, vdy);
-      fetch_rows(x, ldx, x2, ldx2, k_split, nullptr, 0, (c + 1) * ldw::kChunk, M, k0, k_in, vx, tid, vxx);
-    }
     if (it >= 2) mbar_wait(bar + s, (uint32_t)(((it >> 1) - 1) & 1));
-    store_rows<TERMS>(cdy, stage, tid, want_db ? colsum : nullptr);
-    store_rows<TERMS>(cxx, stage + TERMS * ldw::kTile, tid);
+    if (s == 0) {
+      store_rows<TERMS>(ady, stage, tid, want_db ? colsum : nullptr);
+      store_rows<TERMS>(axx, stage + TERMS * ldw::kTile, tid);
+      fetch(c + 2, ady, axx);
+    } else {
+      store_rows<TERMS>(bdy, stage, tid, want_db ? colsum : nullptr);
+      store_rows<TERMS>(bxx, stage + TERMS * ldw::kTile, tid);
+      fetch(c + 2, bdy, bxx);
+    }
     fence_async_smem();
     tc_fence_before();
     __syncthreads();
@@ -606,7 +640,8 @@ int atmonr_linear_prep(const float* w, int n_out, int k_in, int transpose, int t
 
 int atmonr_linear_fwd_tc(const float* x, int64_t ldx, const float* x2, int64_t ldx2, int k_split, const float* mask,
                          int64_t ldm, const void* planes, const float* bias, int64_t M, int n_out, int k_in, int act,
-                         int terms, const float* out_mask, int64_t ldom, float* y, int64_t ldy, void* stream) {
+                         int terms, const float* out_mask, int64_t ldom, const void* bits_in, void* bits_out, float* y,
+                         int64_t ldy, void* stream) {
   ATM_REQUIRE(M >= 0 && n_out > 0 && k_in > 0, "atmonr_linear_fwd_tc", "bad shape");
   ATM_REQUIRE(act == 0 || act == 1, "atmonr_linear_fwd_tc", "act must be 0 (none) or 1 (ReLU)");
   ATM_REQUIRE(terms == 2 || terms == 3, "atmonr_linear_fwd_tc", "terms must be 2 or 3");
@@ -619,6 +654,15 @@ int atmonr_linear_fwd_tc(const float* x, int64_t ldx, const float* x2, int64_t l
                   (!out_mask || ldom >= n_out),
               "atmonr_linear_fwd_tc", "row stride smaller than the row");
   ATM_REQUIRE((M + lin::kRows - 1) / lin::kRows < (1ll << 31), "atmonr_linear_fwd_tc", "too many rows");
+  if (bits_in || bits_out) {
+    // the sign-bit forms live on the whole-half, 16-byte path of the epilogue
+    ATM_REQUIRE(n_out % 128 == 0 && (ldy & 3) == 0 && (reinterpret_cast<uintptr_t>(y) & 15) == 0, "atmonr_linear_fwd_tc",
+                "sign bits need n_out % 128 == 0 and 16-byte aligned output rows");
+    ATM_REQUIRE(!(bits_in && out_mask), "atmonr_linear_fwd_tc", "give out_mask or bits_in, not both");
+    ATM_REQUIRE(!bits_out || act == 1, "atmonr_linear_fwd_tc", "bits_out records a ReLU output (act must be 1)");
+    ATM_REQUIRE(((reinterpret_cast<uintptr_t>(bits_in) | reinterpret_cast<uintptr_t>(bits_out)) & 15) == 0,
+                "atmonr_linear_fwd_tc", "sign-bit arrays must be 16-byte aligned");
+  }
   const int n_tiles = (n_out + lin::kCols - 1) / lin::kCols, k_chunks = (k_in + lin::kChunk - 1) / lin::kChunk;
   dim3 grid((unsigned)((M + lin::kRows - 1) / lin::kRows), (unsigned)n_tiles);
 #define CALL(T)                                                                                                        \
@@ -627,7 +671,7 @@ int atmonr_linear_fwd_tc(const float* x, int64_t ldx, const float* x2, int64_t l
     if (e != cudaSuccess) return fail("atmonr_linear_fwd_tc", cudaGetErrorString(e));                                  \
     k_linear_tc<T><<<grid, lin::kThreads, lin::Map<T>::kBytes, S(stream)>>>(                                           \
         x, ldx, x2, ldx2, k_split, mask, ldm, reinterpret_cast<const uint8_t*>(planes), bias, M, n_out, k_in, k_chunks, \
-        act, out_mask, ldom, y, ldy);                                                                                  \
+        act, out_mask, ldom, reinterpret_cast<const uint32_t*>(bits_in), reinterpret_cast<uint32_t*>(bits_out), y, ldy); \
   }
   ATM_TERMS_DISPATCH(terms, CALL)
 #undef CALL

@@ -354,6 +354,9 @@ int atmonr_append_heights(const float* pts, int64_t M, double scale, const doubl
  *   out. In the backward chain of an MLP the input gradient dX = dY * W of layer l+1 IS the gradient of
  *   layer l's post-ReLU output, whose values are out_mask: the result is then layer l's pre-activation
  *   gradient and neither product of layer l has to read a mask in its main loop.
+ *   bits_out (M, n_out / 32 uint32; may be NULL; needs act == 1 and n_out % 128 == 0): receives the sign bits
+ *   (Y > 0) of this product's ReLU output; bits_in: such an array used in place of out_mask (32 bytes per
+ *   256-wide row instead of 1 KB). The bit layout is private to this entry point.
  *   terms: 3 = the float32-exact flavour above (six products); 2 = two bf16 terms per operand and the
  *   three products hi*hi + hi*lo + lo*hi (product error ~2^-16 relative: half the tensor-core work,
  *   two CTAs per SM); the planes must have been prepared with the same `terms`.
@@ -366,7 +369,8 @@ int atmonr_linear_prep(const float* w, int n_out, int k_in, int transpose, int t
 int atmonr_linear_fwd_tc(const float* x, int64_t ldx, const float* x2, int64_t ldx2, int k_split,
                          const float* mask, int64_t ldm, const void* planes, const float* bias,
                          int64_t M, int n_out, int k_in, int act, int terms, const float* out_mask,
-                         int64_t ldom, float* y, int64_t ldy, void* stream);
+                         int64_t ldom, const void* bits_in, void* bits_out, float* y, int64_t ldy,
+                         void* stream);
 int atmonr_linear_dw_tc(const float* dy, int64_t ldy, const float* mask, int64_t ldm,
                         const float* x, int64_t ldx, const float* x2, int64_t ldx2, int k_split,
                         int64_t M, int n_out, int k_in, int terms, float* dw, float* db,

@@ -339,11 +339,11 @@ def test_linear_tc_host_side():
     with pytest.raises(L.NativeLibraryError):
         ops.linear_forward(torch.zeros(4, 8), torch.zeros(3, 8), None, False)
     with pytest.raises(L.NativeLibraryError, match="act must be"):
-        L.call("atmonr_linear_fwd_tc", None, 8, None, 0, 0, None, 0, None, None, 4, 3, 8, 2, 3, None, 0, None, 3, None)
+        L.call("atmonr_linear_fwd_tc", None, 8, None, 0, 0, None, 0, None, None, 4, 3, 8, 2, 3, None, 0, None, None, None, 3, None)
     with pytest.raises(L.NativeLibraryError, match="terms must be"):
-        L.call("atmonr_linear_fwd_tc", None, 8, None, 0, 0, None, 0, None, None, 4, 3, 8, 0, 4, None, 0, None, 3, None)
+        L.call("atmonr_linear_fwd_tc", None, 8, None, 0, 0, None, 0, None, None, 4, 3, 8, 0, 4, None, 0, None, None, None, 3, None)
     with pytest.raises(L.NativeLibraryError, match="null pointer"):
-        L.call("atmonr_linear_fwd_tc", None, 8, None, 0, 0, None, 0, None, None, 4, 3, 8, 0, 2, None, 0, None, 3, None)
+        L.call("atmonr_linear_fwd_tc", None, 8, None, 0, 0, None, 0, None, None, 4, 3, 8, 0, 2, None, 0, None, None, None, 3, None)
     with pytest.raises(L.NativeLibraryError, match="null pointer"):
         L.call("atmonr_linear_dw_tc", None, 3, None, 0, None, 8, None, 0, 0, 4, 3, 8, 3, None, None, None)
     L.call("atmonr_linear_dw_tc", None, 3, None, 0, None, 8, None, 0, 0, 0, 3, 8, 2, None, None, None)             # no rows
@@ -351,7 +351,7 @@ def test_linear_tc_host_side():
         L.call("atmonr_linear_prep", None, 3, 8, 0, 3, None, None)
     with pytest.raises(L.NativeLibraryError, match="terms must be"):
         L.call("atmonr_linear_dw_tc", None, 3, None, 0, None, 8, None, 0, 0, 4, 3, 8, 1, None, None, None)
-    L.call("atmonr_linear_fwd_tc", None, 8, None, 0, 0, None, 0, None, None, 0, 3, 8, 0, 3, None, 0, None, 3, None)   # no rows: nothing to do
+    L.call("atmonr_linear_fwd_tc", None, 8, None, 0, 0, None, 0, None, None, 0, 3, 8, 0, 3, None, 0, None, None, None, 3, None)   # no rows: nothing to do
 
 
 def test_nerf_model_default_path_is_unchanged_on_cpu(monkeypatch):

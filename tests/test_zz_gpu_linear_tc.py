@@ -193,6 +193,30 @@ def test_linear_output_mask_and_preallocated_output(terms):
         assert bool((wide[:, n:] == 7.0).all())                            # columns beyond the product are untouched
 
 
+def test_linear_relu_sign_bits(terms):
+    """want_bits / out_bits: the forward product records the sign bits of its ReLU output, the input-gradient
+    product of the layer above applies them in its epilogue; same result as masking with the activations
+    themselves (out_mask), incl. a ragged last tile and a 128-wide layer."""
+    from atmonr.native import ops
+    g = torch.Generator().manual_seed(13)
+    for m, k, n in ((1000, 76, 256), (129, 256, 128), (4096, 332, 256)):
+        x = torch.randn(m, k, generator=g).cuda()
+        w = (torch.randn(n, k, generator=g) / k ** 0.5).cuda()
+        b = torch.randn(n, generator=g).cuda()
+        y, bits = ops.linear_forward(x, w, b, True, want_bits=True)
+        assert bits.shape == (m, n // 32) and bits.dtype == torch.int32
+        assert torch.equal(y, ops.linear_forward(x, w, b, True))
+        # the bits say exactly y > 0 (population count per row, independent of the private bit layout)
+        pop = sum(((bits >> s) & 1).sum(dim=1) for s in range(32))
+        assert torch.equal(pop, (y > 0).sum(dim=1))
+        dy = torch.randn(m, 64, generator=g).cuda()
+        w2 = (torch.randn(64, n, generator=g) / 8).cuda()
+        a = ops.linear_forward(dy, w2, None, False, transpose=True, out_mask=y)
+        c = ops.linear_forward(dy, w2, None, False, transpose=True, out_bits=bits)
+        assert torch.equal(a, c)
+        assert bool((c[y <= 0] == 0).all()) and float(c.abs().max()) > 0
+
+
 def test_nerf_mlp_node_matches_the_layer_by_layer_model(terms):
     """atmonr.native.nerf_mlp.NerfMlpFn (one autograd node, hand-written backward chain) against the same
     AtmoNeRF evaluated with torch's float32 layers + autograd: outputs, parameter gradients and the gradient
