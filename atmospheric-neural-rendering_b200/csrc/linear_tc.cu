@@ -54,7 +54,8 @@ struct Map {
   static constexpr int kStage = TERMS * kATile + TERMS * kBTile;   // 72 KB (3 terms) / 48 KB (2 terms)
   static constexpr int kBar = 2 * kStage;   // bar[s]: stage s consumed by its MMAs; full[s]: B planes of stage s landed
   static constexpr int kTmemPtr = kBar + 32;
-  static constexpr int kBytes = kTmemPtr + 16;
+  static constexpr int kBias = kTmemPtr + 16;   // this CTA's 256 bias values (zero where there is none)
+  static constexpr int kBytes = kBias + kCols * 4;
   static_assert(kOutTile <= 2 * kStage, "the staged output half must fit in the operand stages");
 };
 }  // namespace lin
@@ -180,6 +181,8 @@ k_linear_tc(const float* __restrict__ x, int64_t ldx, const float* __restrict__ 
   uint64_t* bar = reinterpret_cast<uint64_t*>(smem + MapT::kBar);          // bar[s]: MMAs that read stage s are done
   uint32_t* tmem_ptr = reinterpret_cast<uint32_t*>(smem + MapT::kTmemPtr);
   const int tid = threadIdx.x, warp = tid >> 5;
+  const int64_t row0 = (int64_t)blockIdx.x * lin::kRows;
+  const int n0 = blockIdx.y * lin::kCols;                                  // first output column of this CTA
   if (warp == 0) tmem_alloc<lin::kTmemCols>(tmem_ptr);
   uint64_t* full = bar + 2;
   if (tid == 0) {
@@ -189,6 +192,8 @@ k_linear_tc(const float* __restrict__ x, int64_t ldx, const float* __restrict__ 
     mbar_init(full + 1, 1);
     fence_mbar_init();
   }
+  float* sbias = reinterpret_cast<float*>(smem + MapT::kBias);
+  sbias[tid] = (bias && n0 + tid < n_out) ? __ldg(bias + n0 + tid) : 0.0f;   // kThreads == kCols
   fence_async_smem();
   tc_fence_before();
   __syncthreads();
@@ -196,8 +201,6 @@ k_linear_tc(const float* __restrict__ x, int64_t ldx, const float* __restrict__ 
   const uint32_t acc = *tmem_ptr;
   const uint32_t sbase = smem_u32(smem);
 
-  const int64_t row0 = (int64_t)blockIdx.x * lin::kRows;
-  const int n0 = blockIdx.y * lin::kCols;                                  // first output column of this CTA
   const int n_cols = min(lin::kCols, ((n_out + 15) / 16) * 16 - n0);       // MMA N (multiple of 16)
   const uint32_t idesc = make_idesc_bf16(lin::kRows, n_cols);
   const uint8_t* b_src = planes + (size_t)blockIdx.y * k_chunks * TERMS * lin::kBTile;
@@ -212,20 +215,28 @@ k_linear_tc(const float* __restrict__ x, int64_t ldx, const float* __restrict__ 
   // chunk's worth of bytes in flight per CTA (16 KB) did not cover the global-load latency (ncu round 2:
   // 35 % of the warp samples on the long scoreboard, DRAM at a third of its rate).
   float xa[2][8], xb[2][8];
+  // this thread's two rows (64 apart) and its 8-column group inside a chunk are the same for every chunk:
+  // the row pointers are formed once per tile (the per-chunk 64-bit products were a quarter of all issued
+  // instructions)
+  const int cc8 = ((tid >> 3) & 3) * 8;
+  const int64_t frow = row0 + ((warp << 3) | (tid & 7));
+  const float* xr = x + frow * ldx + cc8;
+  const float* x2r = x2 ? x2 + frow * ldx2 + (cc8 - k_split) : nullptr;
+  const float* mr = mask ? mask + frow * ldm + cc8 : nullptr;
+  const int64_t step_x = 64 * ldx, step_x2 = 64 * ldx2, step_m = 64 * ldm;
   auto fetch_x = [&](int c, float (&xv)[2][8]) {
+    const int k0 = c * lin::kChunk + cc8;
+    const bool second = k0 >= k_split;
+    const int left = (second ? k_in : k_split) - k0;
 #pragma unroll
     for (int it = 0; it < 2; ++it) {
-      const int r = ((warp + it * (lin::kThreads / 32)) << 3) | (tid & 7), cc = (tid >> 3) & 3;
-      const int64_t row = row0 + r;
-      const int k0 = c * lin::kChunk + cc * 8;
 #pragma unroll
       for (int j = 0; j < 8; ++j) xv[it][j] = 0.0f;
-      if (row < M && c < k_chunks) {
+      if (frow + it * 64 < M && c < k_chunks) {
         // columns [0, k_split) come from x, [k_split, k_in) from x2 (k_split is a multiple of 8: a group
         // of 8 never straddles the two)
-        const bool second = k0 >= k_split;
-        const float* src = second ? x2 + row * ldx2 + (k0 - k_split) : x + row * ldx + k0;
-        load8(src, mask ? mask + row * ldm + k0 : nullptr, (second ? k_in : k_split) - k0, vec_ok, xv[it]);
+        const float* src = (second ? x2r + it * step_x2 : xr + it * step_x) + c * lin::kChunk;
+        load8(src, mr ? mr + it * step_m + c * lin::kChunk : nullptr, left, vec_ok, xv[it]);
       }
     }
   };
@@ -331,15 +342,17 @@ k_linear_tc(const float* __restrict__ x, int64_t ldx, const float* __restrict__ 
       const int bword = ((n0 + h0) >> 7) << 2;
       float4 mreg[16];
       if (fast && omh) {
+        const float* mp = omh + (row0 + wrow) * ldom + 4 * lane;
+        const int64_t mstep = 8 * ldom;
 #pragma unroll
         for (int u = 0; u < 16; ++u)
-          if (wrow + 8 * u < rows)
-            mreg[u] = *reinterpret_cast<const float4*>(omh + (row0 + wrow + 8 * u) * ldom + 4 * lane);
+          if (wrow + 8 * u < rows) mreg[u] = *reinterpret_cast<const float4*>(mp + u * mstep);
       } else if (fast && bits_in) {
+        const uint32_t* bp = bits_in + (row0 + wrow) * wpr + bword;
 #pragma unroll
         for (int u = 0; u < 16; ++u)
           if (wrow + 8 * u < rows) {
-            const uint4 b = *reinterpret_cast<const uint4*>(bits_in + (row0 + wrow + 8 * u) * wpr + bword);
+            const uint4 b = *reinterpret_cast<const uint4*>(bp + u * 8 * wpr);
             mreg[u] = make_float4(__uint_as_float(b.x), __uint_as_float(b.y), __uint_as_float(b.z), __uint_as_float(b.w));
           }
       }
@@ -349,26 +362,29 @@ k_linear_tc(const float* __restrict__ x, int64_t ldx, const float* __restrict__ 
         if (col >= n_cols) break;                        // warp-uniform
         float v[16];
         tmem_ld16(tmem_addr(acc, warp, col), v);
-#pragma unroll
-        for (int j = 0; j < 16; ++j) {
-          const int n = n0 + col + j;
-          float o = v[j] + ((bias && n < n_out) ? __ldg(bias + n) : 0.0f);
-          if (act == 1) o = fmaxf(o, 0.0f);
-          v[j] = o;
-        }
+        const float4* bq = reinterpret_cast<const float4*>(sbias + col);   // same address in every lane: broadcast
         float4* dst = reinterpret_cast<float4*>(tile + r * pitch + lc);
 #pragma unroll
-        for (int q = 0; q < 4; ++q) dst[q] = make_float4(v[4 * q], v[4 * q + 1], v[4 * q + 2], v[4 * q + 3]);
+        for (int q = 0; q < 4; ++q) {
+          const float4 bb = bq[q];
+          float4 o = make_float4(v[4 * q] + bb.x, v[4 * q + 1] + bb.y, v[4 * q + 2] + bb.z, v[4 * q + 3] + bb.w);
+          if (act == 1) o = make_float4(fmaxf(o.x, 0.0f), fmaxf(o.y, 0.0f), fmaxf(o.z, 0.0f), fmaxf(o.w, 0.0f));
+          dst[q] = o;
+        }
       }
       __syncthreads();
       if (w_valid <= 0) continue;                          // uniform
       float* yh = y + n0 + h0;
       if (fast) {
+        float* yp = yh + (row0 + wrow) * ldy + 4 * lane;
+        const int64_t ystep = 8 * ldy;
+        uint32_t* bo = bits_out ? bits_out + (row0 + wrow) * wpr + bword : nullptr;
+        const float* tp = tile + wrow * pitch + 4 * lane;
 #pragma unroll
         for (int u = 0; u < 16; ++u) {
           const int rr = wrow + 8 * u;
           if (rr >= rows) break;                           // warp-uniform
-          float4 v = *reinterpret_cast<const float4*>(tile + rr * pitch + 4 * lane);
+          float4 v = *reinterpret_cast<const float4*>(tp + u * 8 * pitch);
           if (omh) {
             const float4 m = mreg[u];
             v.x = m.x > 0.0f ? v.x : 0.0f, v.y = m.y > 0.0f ? v.y : 0.0f;
@@ -378,11 +394,11 @@ k_linear_tc(const float* __restrict__ x, int64_t ldx, const float* __restrict__ 
             v.x = ((__float_as_uint(m.x) >> lane) & 1u) ? v.x : 0.0f, v.y = ((__float_as_uint(m.y) >> lane) & 1u) ? v.y : 0.0f;
             v.z = ((__float_as_uint(m.z) >> lane) & 1u) ? v.z : 0.0f, v.w = ((__float_as_uint(m.w) >> lane) & 1u) ? v.w : 0.0f;
           }
-          *reinterpret_cast<float4*>(yh + (row0 + rr) * ldy + 4 * lane) = v;
-          if (bits_out) {
+          *reinterpret_cast<float4*>(yp + u * ystep) = v;
+          if (bo) {
             const uint32_t b0 = __ballot_sync(0xffffffffu, v.x > 0.0f), b1 = __ballot_sync(0xffffffffu, v.y > 0.0f);
             const uint32_t b2 = __ballot_sync(0xffffffffu, v.z > 0.0f), b3 = __ballot_sync(0xffffffffu, v.w > 0.0f);
-            if (lane == 0) *reinterpret_cast<uint4*>(bits_out + (row0 + rr) * wpr + bword) = make_uint4(b0, b1, b2, b3);
+            if (lane == 0) *reinterpret_cast<uint4*>(bo + u * 8 * wpr) = make_uint4(b0, b1, b2, b3);
           }
         }
       } else if (vec && om_vec) {
@@ -529,12 +545,31 @@ k_linear_dw_tc(const float* __restrict__ dy, int64_t ldy, const float* __restric
   // and stored, so two chunks (128 KB per SM) are in flight while the tensor core works on a third. (One
   // chunk ahead left the kernel at a third of the DRAM rate, the staging warps waiting on the loads.)
   float ady[4][8], axx[4][8], bdy[4][8], bxx[4][8];
+  // A thread's column group (8 columns of dY, 8 of X) is the same for every row group and every chunk,
+  // and its rows are 8 it + (lane & 7): the operand pointers advance by 32 rows per fetch (the fetches are
+  // issued in chunk order), so no 64-bit product is formed inside the loop.
+  const int lane_ = tid & 31, ccw = ((warp & 7) << 2) | (lane_ >> 3), r7 = lane_ & 7;
+  const int kdy = n0 + ccw * 8, kx = k0 + ccw * 8;
+  const bool dy_on = kdy < n_out, x_on = kx < k_in, x_second = kx >= k_split;
+  const int dy_left = n_out - kdy, x_left = (x_second ? k_in : k_split) - kx;
+  const int64_t xld = x_second ? ldx2 : ldx;
+  const float* dyq = dy + (c_lo * ldw::kChunk + r7) * ldy + kdy;
+  const float* mkq = mask ? mask + (c_lo * ldw::kChunk + r7) * ldm + kdy : nullptr;
+  const float* xq = (x_second ? x2 + (kx - k_split) : x + kx) + (c_lo * ldw::kChunk + r7) * xld;
+  const int64_t ldy8 = 8 * ldy, ldm8 = 8 * ldm, xld8 = 8 * xld;
   auto fetch = [&](int64_t c, float (&vdy)[4][8], float (&vxx)[4][8]) {
-    // past the slab: row_lo >= the slab's end; fetch_rows zero-fills rows >= M, and a chunk past c_hi is
-    // never staged, so clamping to M keeps the loads inside the matrices
-    const int64_t row_lo = c < c_hi ? c * ldw::kChunk : M;
-    fetch_rows(dy, ldy, nullptr, 0, n_out, mask, ldm, row_lo, M, n0, n_out, vy, tid, vdy);
-    fetch_rows(x, ldx, x2, ldx2, k_split, nullptr, 0, row_lo, M, k0, k_in, vx, tid, vxx);
+    const int64_t row_lo = c * ldw::kChunk + r7;
+#pragma unroll
+    for (int a = 0; a < 4; ++a) {
+#pragma unroll
+      for (int j = 0; j < 8; ++j) vdy[a][j] = 0.0f, vxx[a][j] = 0.0f;
+      if (c < c_hi && row_lo + 8 * a < M) {
+        if (dy_on) load8(dyq + a * ldy8, mkq ? mkq + a * ldm8 : nullptr, dy_left, vy, vdy[a]);
+        if (x_on) load8(xq + a * xld8, nullptr, x_left, vx, vxx[a]);
+      }
+    }
+    dyq += 4 * ldy8, xq += 4 * xld8;
+    if (mkq) mkq += 4 * ldm8;
   };
   fetch(c_lo, ady, axx);
   fetch(c_lo + 1, bdy, bxx);
