@@ -224,6 +224,15 @@ k_linear_tc(const float* __restrict__ x, int64_t ldx, const float* __restrict__ 
   const float* x2r = x2 ? x2 + frow * ldx2 + (cc8 - k_split) : nullptr;
   const float* mr = mask ? mask + frow * ldm + cc8 : nullptr;
   const int64_t step_x = 64 * ldx, step_x2 = 64 * ldx2, step_m = 64 * ldm;
+  // The K loop reads a row in eight 128-byte pieces, one per chunk, with a whole chunk period between two
+  // of them: the DRAM sees scattered 128-byte requests and the loads come back after ~3.5 us (ncu round 2:
+  // 64 KB in flight per SM, a third of the DRAM rate). So every row of the tile is requested ONCE, whole,
+  // into the L2 up front (one bulk prefetch per row and input block); the chunk loads then hit the L2.
+  if (vec_ok && tid < lin::kRows && row0 + tid < M) {
+    const uint32_t b1 = ((uint32_t)k_split * 4u) & ~15u, b2 = ((uint32_t)(k_in - k_split) * 4u) & ~15u;
+    if (b1) prefetch_l2_bulk(x + (row0 + tid) * ldx, b1);
+    if (x2 && b2) prefetch_l2_bulk(x2 + (row0 + tid) * ldx2, b2);
+  }
   auto fetch_x = [&](int c, float (&xv)[2][8]) {
     const int k0 = c * lin::kChunk + cc8;
     const bool second = k0 >= k_split;

@@ -216,6 +216,11 @@ __device__ __forceinline__ uint32_t tmem_addr(uint32_t base, int warp, int col) 
   return base + ((uint32_t)((warp & 3) * 32) << 16) + (uint32_t)col;
 }
 
+// Ask the L2 for `bytes` (a multiple of 16) at the 16-byte aligned global address p; nothing waits on it.
+__device__ __forceinline__ void prefetch_l2_bulk(const void* p, uint32_t bytes) {
+  asm volatile("cp.async.bulk.prefetch.L2.global [%0], %1;" ::"l"(p), "r"(bytes) : "memory");
+}
+
 // ---- staging helpers ---------------------------------------------------------------------------
 // Row `r` of a tile with C columns: write 8 fp16 values (one 16-byte chunk) at column chunk `cc`.
 __device__ __forceinline__ void st_chunk(uint8_t* tile, int r, int cc, int C, uint4 v) {
