@@ -252,22 +252,30 @@ k_linear_tc(const float* __restrict__ x, int64_t ldx, const float* __restrict__ 
   fetch_x(0, xa);
   fetch_x(1, xb);
 
+  // ---- B chunks: TERMS planes, already split and in tile order: the first n_cols rows of a plane are its
+  // first n_cols * 64 bytes -> one bulk copy per plane, announced on full[stage]. The copy of chunk c + 1 is
+  // issued during iteration c (as soon as the MMAs of chunk c - 1, which read that stage, have committed),
+  // the first two right here: issued at the top of its own iteration, a copy's L2 round trip was exposed in
+  // every chunk (8 x ~1.7 us of a 27 us tile).
+  auto issue_b = [&](int c) {
+    const int sb = c & 1;
+    const uint8_t* src = b_src + (size_t)c * TERMS * lin::kBTile;
+    uint8_t* dst = smem + sb * MapT::kStage + TERMS * lin::kATile;
+    const uint32_t bytes = (uint32_t)n_cols * 64u;
+    mbar_expect_tx(full + sb, (uint32_t)TERMS * bytes);
+#pragma unroll
+    for (int p = 0; p < TERMS; ++p) bulk_g2s(dst + p * lin::kBTile, src + p * lin::kBTile, bytes, full + sb);
+  };
+  if (tid == 0) {
+    issue_b(0);
+    if (k_chunks > 1) issue_b(1);
+  }
+
   for (int c = 0; c < k_chunks; ++c) {
     const int s = c & 1;
     uint8_t* stage = smem + s * MapT::kStage;
     // the MMAs of chunk c-2 read this stage: wait for their commit (completion number (c>>1)-1 of bar[s])
     if (c >= 2) mbar_wait(bar + s, (uint32_t)(((c >> 1) - 1) & 1));
-    // ---- B chunk: TERMS planes, already split and in tile order: the first n_cols rows of a plane are
-    // its first n_cols * 64 bytes -> one bulk copy per plane, announced on full[s]. (This thread has
-    // passed the wait above, so the MMAs that read the stage before are done.)
-    if (tid == 0) {
-      const uint8_t* src = b_src + (size_t)c * TERMS * lin::kBTile;
-      uint8_t* dst = stage + TERMS * lin::kATile;
-      const uint32_t bytes = (uint32_t)n_cols * 64u;
-      mbar_expect_tx(full + s, (uint32_t)TERMS * bytes);
-#pragma unroll
-      for (int p = 0; p < TERMS; ++p) bulk_g2s(dst + p * lin::kBTile, src + p * lin::kBTile, bytes, full + s);
-    }
     // ---- X chunk: 128 rows x 32 columns float32 -> TERMS bf16 planes (2 groups of 8 values per thread)
     float cur[2][8];
     if (s == 0) {
@@ -287,6 +295,11 @@ k_linear_tc(const float* __restrict__ x, int64_t ldx, const float* __restrict__ 
     for (int it = 0; it < 2; ++it) {
       const int r = ((warp + it * (lin::kThreads / 32)) << 3) | (tid & 7), cc = (tid >> 3) & 3;
       split_store<TERMS>(cur[it], stage, lin::kATile, r, cc, lin::kChunk);
+    }
+    if (tid == 0 && c >= 1 && c + 1 < k_chunks) {
+      // chunk c - 1 (the other stage) is the ((c-1)>>1)-th completion of its barrier
+      mbar_wait(bar + (s ^ 1), (uint32_t)(((c - 1) >> 1) & 1));
+      issue_b(c + 1);
     }
     fence_async_smem();
     tc_fence_before();
@@ -455,7 +468,9 @@ k_linear_tc(const float* __restrict__ x, int64_t ldx, const float* __restrict__ 
 namespace ldw {
 constexpr int kChunk = 32;                         // rows per stage (the MMA K dimension)
 constexpr int kWide = 256;                         // columns of a staged operand block
-constexpr int kThreads = 256;
+constexpr int kThreads = 512;                         // 16 warps: the staging code is a chain of dependent conversions,
+                                                   // 8 warps left the SM at an IPC of 0.9 (ncu round 2)
+constexpr int kIts = 32 / (kThreads / 32);         // 8-row x 128-byte items per thread and operand: 32 warp items per chunk
 constexpr int kTile = kChunk * kWide * 2;          // 16 KB: one bf16 plane of one operand
 constexpr uint32_t kTmemCols = 512;
 template <int TERMS>
@@ -474,10 +489,10 @@ struct Map {
 __device__ __forceinline__ void fetch_rows(const float* __restrict__ src, int64_t ld, const float* __restrict__ src2,
                                            int64_t ld2, int split, const float* __restrict__ mask, int64_t ldm,
                                            int64_t row_lo, int64_t M, int c0, int cols, bool vec_ok, int tid,
-                                           float (&v)[4][8]) {
+                                           float (&v)[ldw::kIts][8]) {
   const int warp = tid >> 5, lane = tid & 31;
 #pragma unroll
-  for (int it = 0; it < 4; ++it) {
+  for (int it = 0; it < ldw::kIts; ++it) {
     const int wi = warp + it * (ldw::kThreads / 32);             // 32 warp items: 4 row groups x 8 column blocks
     const int r = ((wi >> 3) << 3) | (lane & 7), cc = ((wi & 7) << 2) | (lane >> 3);
     const int64_t row = row_lo + r;
@@ -492,10 +507,10 @@ __device__ __forceinline__ void fetch_rows(const float* __restrict__ src, int64_
   }
 }
 template <int TERMS>
-__device__ __forceinline__ void store_rows(const float (&v)[4][8], uint8_t* tile, int tid, float* colsum = nullptr) {
+__device__ __forceinline__ void store_rows(const float (&v)[ldw::kIts][8], uint8_t* tile, int tid, float* colsum = nullptr) {
   const int warp = tid >> 5, lane = tid & 31;
 #pragma unroll
-  for (int it = 0; it < 4; ++it) {
+  for (int it = 0; it < ldw::kIts; ++it) {
     const int wi = warp + it * (ldw::kThreads / 32);
     const int r = ((wi >> 3) << 3) | (lane & 7), cc = ((wi & 7) << 2) | (lane >> 3);
     if (colsum) {  // a thread's column group cc is the same in every iteration and every chunk
@@ -553,11 +568,12 @@ k_linear_dw_tc(const float* __restrict__ dy, int64_t ldy, const float* __restric
   // iterations, set B the odd ones; a set is refilled (chunk it + 2) right after its values have been split
   // and stored, so two chunks (128 KB per SM) are in flight while the tensor core works on a third. (One
   // chunk ahead left the kernel at a third of the DRAM rate, the staging warps waiting on the loads.)
-  float ady[4][8], axx[4][8], bdy[4][8], bxx[4][8];
+  float ady[ldw::kIts][8], axx[ldw::kIts][8], bdy[ldw::kIts][8], bxx[ldw::kIts][8];
   // A thread's column group (8 columns of dY, 8 of X) is the same for every row group and every chunk,
-  // and its rows are 8 it + (lane & 7): the operand pointers advance by 32 rows per fetch (the fetches are
-  // issued in chunk order), so no 64-bit product is formed inside the loop.
-  const int lane_ = tid & 31, ccw = ((warp & 7) << 2) | (lane_ >> 3), r7 = lane_ & 7;
+  // and its rows are 8 (warp / 8 + (kThreads / 256) it) + (lane & 7): the operand pointers advance by 32
+  // rows per fetch (the fetches are issued in chunk order), so no 64-bit product is formed inside the loop.
+  constexpr int kRowStep = 8 * (ldw::kThreads / 256);   // rows between two items of a thread
+  const int lane_ = tid & 31, ccw = ((warp & 7) << 2) | (lane_ >> 3), r7 = ((warp >> 3) << 3) | (lane_ & 7);
   const int kdy = n0 + ccw * 8, kx = k0 + ccw * 8;
   const bool dy_on = kdy < n_out, x_on = kx < k_in, x_second = kx >= k_split;
   const int dy_left = n_out - kdy, x_left = (x_second ? k_in : k_split) - kx;
@@ -565,20 +581,20 @@ k_linear_dw_tc(const float* __restrict__ dy, int64_t ldy, const float* __restric
   const float* dyq = dy + (c_lo * ldw::kChunk + r7) * ldy + kdy;
   const float* mkq = mask ? mask + (c_lo * ldw::kChunk + r7) * ldm + kdy : nullptr;
   const float* xq = (x_second ? x2 + (kx - k_split) : x + kx) + (c_lo * ldw::kChunk + r7) * xld;
-  const int64_t ldy8 = 8 * ldy, ldm8 = 8 * ldm, xld8 = 8 * xld;
-  auto fetch = [&](int64_t c, float (&vdy)[4][8], float (&vxx)[4][8]) {
+  const int64_t ldy8 = kRowStep * ldy, ldm8 = kRowStep * ldm, xld8 = kRowStep * xld;
+  auto fetch = [&](int64_t c, float (&vdy)[ldw::kIts][8], float (&vxx)[ldw::kIts][8]) {
     const int64_t row_lo = c * ldw::kChunk + r7;
 #pragma unroll
-    for (int a = 0; a < 4; ++a) {
+    for (int a = 0; a < ldw::kIts; ++a) {
 #pragma unroll
       for (int j = 0; j < 8; ++j) vdy[a][j] = 0.0f, vxx[a][j] = 0.0f;
-      if (c < c_hi && row_lo + 8 * a < M) {
+      if (c < c_hi && row_lo + kRowStep * a < M) {
         if (dy_on) load8(dyq + a * ldy8, mkq ? mkq + a * ldm8 : nullptr, dy_left, vy, vdy[a]);
         if (x_on) load8(xq + a * xld8, nullptr, x_left, vx, vxx[a]);
       }
     }
-    dyq += 4 * ldy8, xq += 4 * xld8;
-    if (mkq) mkq += 4 * ldm8;
+    dyq += ldw::kChunk * ldy, xq += ldw::kChunk * xld;
+    if (mkq) mkq += ldw::kChunk * ldm;
   };
   fetch(c_lo, ady, axx);
   fetch(c_lo + 1, bdy, bxx);
@@ -638,9 +654,10 @@ k_linear_dw_tc(const float* __restrict__ dy, int64_t ldy, const float* __restric
   // ---- epilogue: accumulator h, lane = row (n_out index), columns = k_in index
   for (int h = 0; h < m_halves; ++h) {
     const int n = n0 + h * 128 + (warp & 3) * 32 + (tid & 31);
-    const int col_lo = (warp >> 2) * 128;
+    constexpr int kColsPerWarp = 256 / (ldw::kThreads / 128);      // the warps of a lane quarter split the columns
+    const int col_lo = (warp >> 2) * kColsPerWarp;
 #pragma unroll 1
-    for (int cb = 0; cb < 128; cb += 16) {
+    for (int cb = 0; cb < kColsPerWarp; cb += 16) {
       const int col = col_lo + cb;
       if (col >= n_cols) break;                                  // warp-uniform
       float v[16];
