@@ -147,6 +147,51 @@ __device__ __forceinline__ void load8(const float* __restrict__ src, const float
   }
 }
 
+// ---- staging in groups of FOUR values ------------------------------------------------------------
+// The activations are staged by warp instructions that read 8 rows x 64 contiguous bytes (lane / 4 =
+// row of an 8-row group, lane % 4 = 16-byte piece): whole 32-byte sectors, each requested once, and the
+// 8-byte shared-memory stores of a warp fill two core matrices exactly (128 contiguous bytes each: no
+// bank conflicts). The first version read 8 rows x four 16-byte pieces 32 bytes apart and the other
+// halves with a second instruction: every sector twice, and the L1 data pipe at 70-85 % of its
+// wavefront rate was what bound both dense-layer kernels (ncu round 2).
+// four consecutive float32 of a row (`left` = columns left in the row; fewer than 4 -> zero fill),
+// optionally zeroed where the matching entry of `m` is not positive
+__device__ __forceinline__ void load4(const float* __restrict__ src, const float* __restrict__ m, int left, bool vec_ok,
+                                      float (&v)[4]) {
+  if (vec_ok && left >= 4) {
+    const float4 p = *reinterpret_cast<const float4*>(src);
+    v[0] = p.x, v[1] = p.y, v[2] = p.z, v[3] = p.w;
+    if (m) {
+      const float4 a = *reinterpret_cast<const float4*>(m);
+      if (!(a.x > 0.0f)) v[0] = 0.0f;
+      if (!(a.y > 0.0f)) v[1] = 0.0f;
+      if (!(a.z > 0.0f)) v[2] = 0.0f;
+      if (!(a.w > 0.0f)) v[3] = 0.0f;
+    }
+  } else {
+#pragma unroll
+    for (int j = 0; j < 4; ++j)
+      if (j < left) v[j] = (m && !(m[j] > 0.0f)) ? 0.0f : src[j];
+  }
+}
+// split 4 values into TERMS planes `pitch` bytes apart; `at` = the 8-byte slot of the values in plane 0
+template <int TERMS>
+__device__ __forceinline__ void split_store4(const float (&v)[4], uint8_t* at, int pitch) {
+  uint2 pl[TERMS];
+  float r[4] = {v[0], v[1], v[2], v[3]};
+#pragma unroll
+  for (int t = 0; t < TERMS; ++t) {
+    const __nv_bfloat162 a = __floats2bfloat162_rn(r[0], r[1]), b = __floats2bfloat162_rn(r[2], r[3]);
+    pl[t] = make_uint2(*reinterpret_cast<const uint32_t*>(&a), *reinterpret_cast<const uint32_t*>(&b));
+    if (t + 1 < TERMS) {   // what this term leaves (exact in float32)
+      r[0] -= __bfloat162float(a.x), r[1] -= __bfloat162float(a.y);
+      r[2] -= __bfloat162float(b.x), r[3] -= __bfloat162float(b.y);
+    }
+  }
+#pragma unroll
+  for (int t = 0; t < TERMS; ++t) *reinterpret_cast<uint2*>(at + t * pitch) = pl[t];
+}
+
 // B (n_out, k_in) float32 row-major, or its transpose when `transpose` (then the source is
 // (k_in, n_out) row-major) -> planes[(tile * k_chunks + chunk) * TERMS + plane][256 x 32 bf16, tile layout]
 template <int TERMS>
@@ -214,38 +259,34 @@ k_linear_tc(const float* __restrict__ x, int64_t ldx, const float* __restrict__ 
   // The values are requested TWO chunks ahead (two register sets, xa for even and xb for odd chunks): one
   // chunk's worth of bytes in flight per CTA (16 KB) did not cover the global-load latency (ncu round 2:
   // 35 % of the warp samples on the long scoreboard, DRAM at a third of its rate).
-  float xa[2][8], xb[2][8];
-  // this thread's two rows (64 apart) and its 8-column group inside a chunk are the same for every chunk:
-  // the row pointers are formed once per tile (the per-chunk 64-bit products were a quarter of all issued
-  // instructions)
-  const int cc8 = ((tid >> 3) & 3) * 8;
-  const int64_t frow = row0 + ((warp << 3) | (tid & 7));
-  const float* xr = x + frow * ldx + cc8;
-  const float* x2r = x2 ? x2 + frow * ldx2 + (cc8 - k_split) : nullptr;
-  const float* mr = mask ? mask + frow * ldm + cc8 : nullptr;
-  const int64_t step_x = 64 * ldx, step_x2 = 64 * ldx2, step_m = 64 * ldm;
-  // The K loop reads a row in eight 128-byte pieces, one per chunk, with a whole chunk period between two
-  // of them: the DRAM sees scattered 128-byte requests and the loads come back after ~3.5 us (ncu round 2:
-  // 64 KB in flight per SM, a third of the DRAM rate). So every row of the tile is requested ONCE, whole,
-  // into the L2 up front (one bulk prefetch per row and input block); the chunk loads then hit the L2.
-  if (vec_ok && tid < lin::kRows && row0 + tid < M) {
-    const uint32_t b1 = ((uint32_t)k_split * 4u) & ~15u, b2 = ((uint32_t)(k_in - k_split) * 4u) & ~15u;
-    if (b1) prefetch_l2_bulk(x + (row0 + tid) * ldx, b1);
-    if (x2 && b2) prefetch_l2_bulk(x2 + (row0 + tid) * ldx2, b2);
-  }
-  auto fetch_x = [&](int c, float (&xv)[2][8]) {
-    const int k0 = c * lin::kChunk + cc8;
+  float xa[4][4], xb[4][4];
+  // This thread's part of a chunk (128 rows x 32 columns): 4 consecutive columns (16 bytes) of four rows
+  // 32 apart. A warp instruction reads 8 rows x 64 bytes: warp w takes the 64-byte half (w & 1) of the row
+  // groups (w >> 1) + 4 it. Row and column are the same for every chunk: the pointers are formed once per
+  // tile (the per-chunk 64-bit products were a quarter of all issued instructions).
+  const int lane_f = tid & 31;
+  const int kq = ((warp & 1) << 4) | ((lane_f & 3) << 2);          // first of this thread's 4 columns in a chunk
+  const int fr0 = ((warp >> 1) << 3) | (lane_f >> 2);              // its first row in the tile
+  const int64_t frow = row0 + fr0;
+  const float* xr = x + frow * ldx + kq;
+  const float* x2r = x2 ? x2 + frow * ldx2 + (kq - k_split) : nullptr;
+  const float* mr = mask ? mask + frow * ldm + kq : nullptr;
+  const int64_t step_x = 32 * ldx, step_x2 = 32 * ldx2, step_m = 32 * ldm;
+  // byte offset of (row fr0, column kq) in a plane of the A tile; + 2048 per 32 rows
+  const uint32_t a_off = (uint32_t)((fr0 >> 3) * (lin::kChunk >> 3) * kCore + (kq >> 3) * kCore + (fr0 & 7) * 16 + (kq & 7) * 2);
+  auto fetch_x = [&](int c, float (&xv)[4][4]) {
+    const int k0 = c * lin::kChunk + kq;
     const bool second = k0 >= k_split;
     const int left = (second ? k_in : k_split) - k0;
 #pragma unroll
-    for (int it = 0; it < 2; ++it) {
+    for (int it = 0; it < 4; ++it) {
 #pragma unroll
-      for (int j = 0; j < 8; ++j) xv[it][j] = 0.0f;
-      if (frow + it * 64 < M && c < k_chunks) {
+      for (int j = 0; j < 4; ++j) xv[it][j] = 0.0f;
+      if (frow + it * 32 < M && c < k_chunks) {
         // columns [0, k_split) come from x, [k_split, k_in) from x2 (k_split is a multiple of 8: a group
-        // of 8 never straddles the two)
+        // of 4 never straddles the two)
         const float* src = (second ? x2r + it * step_x2 : xr + it * step_x) + c * lin::kChunk;
-        load8(src, mr ? mr + it * step_m + c * lin::kChunk : nullptr, left, vec_ok, xv[it]);
+        load4(src, mr ? mr + it * step_m + c * lin::kChunk : nullptr, left, vec_ok, xv[it]);
       }
     }
   };
@@ -276,26 +317,23 @@ k_linear_tc(const float* __restrict__ x, int64_t ldx, const float* __restrict__ 
     uint8_t* stage = smem + s * MapT::kStage;
     // the MMAs of chunk c-2 read this stage: wait for their commit (completion number (c>>1)-1 of bar[s])
     if (c >= 2) mbar_wait(bar + s, (uint32_t)(((c >> 1) - 1) & 1));
-    // ---- X chunk: 128 rows x 32 columns float32 -> TERMS bf16 planes (2 groups of 8 values per thread)
-    float cur[2][8];
+    // ---- X chunk: 128 rows x 32 columns float32 -> TERMS bf16 planes (4 groups of 4 values per thread)
+    float cur[4][4];
     if (s == 0) {
 #pragma unroll
-      for (int it = 0; it < 2; ++it)
+      for (int it = 0; it < 4; ++it)
 #pragma unroll
-        for (int j = 0; j < 8; ++j) cur[it][j] = xa[it][j];
+        for (int j = 0; j < 4; ++j) cur[it][j] = xa[it][j];
       fetch_x(c + 2, xa);
     } else {
 #pragma unroll
-      for (int it = 0; it < 2; ++it)
+      for (int it = 0; it < 4; ++it)
 #pragma unroll
-        for (int j = 0; j < 8; ++j) cur[it][j] = xb[it][j];
+        for (int j = 0; j < 4; ++j) cur[it][j] = xb[it][j];
       fetch_x(c + 2, xb);
     }
 #pragma unroll
-    for (int it = 0; it < 2; ++it) {
-      const int r = ((warp + it * (lin::kThreads / 32)) << 3) | (tid & 7), cc = (tid >> 3) & 3;
-      split_store<TERMS>(cur[it], stage, lin::kATile, r, cc, lin::kChunk);
-    }
+    for (int it = 0; it < 4; ++it) split_store4<TERMS>(cur[it], stage + a_off + it * 2048, lin::kATile);
     if (tid == 0 && c >= 1 && c + 1 < k_chunks) {
       // chunk c - 1 (the other stage) is the ((c-1)>>1)-th completion of its barrier
       mbar_wait(bar + (s ^ 1), (uint32_t)(((c - 1) >> 1) & 1));
@@ -559,42 +597,54 @@ k_linear_dw_tc(const float* __restrict__ dy, int64_t ldy, const float* __restric
 
   // bias gradient = column sums of the (masked) dY: the staging threads see every value anyway; the
   // CTAs of the first k_in block add theirs
-  float colsum[8];
-#pragma unroll
-  for (int j = 0; j < 8; ++j) colsum[j] = 0.0f;
+  float colsum[4] = {0.0f, 0.0f, 0.0f, 0.0f};
   const bool want_db = db != nullptr && blockIdx.z == 0;
 
   // This thread's values of the chunks being staged, requested TWO chunks ahead: set A serves the even
   // iterations, set B the odd ones; a set is refilled (chunk it + 2) right after its values have been split
   // and stored, so two chunks (128 KB per SM) are in flight while the tensor core works on a third. (One
   // chunk ahead left the kernel at a third of the DRAM rate, the staging warps waiting on the loads.)
-  float ady[ldw::kIts][8], axx[ldw::kIts][8], bdy[ldw::kIts][8], bxx[ldw::kIts][8];
-  // A thread's column group (8 columns of dY, 8 of X) is the same for every row group and every chunk,
-  // and its rows are 8 (warp / 8 + (kThreads / 256) it) + (lane & 7): the operand pointers advance by 32
-  // rows per fetch (the fetches are issued in chunk order), so no 64-bit product is formed inside the loop.
-  constexpr int kRowStep = 8 * (ldw::kThreads / 256);   // rows between two items of a thread
-  const int lane_ = tid & 31, ccw = ((warp & 7) << 2) | (lane_ >> 3), r7 = ((warp >> 3) << 3) | (lane_ & 7);
-  const int kdy = n0 + ccw * 8, kx = k0 + ccw * 8;
+  float ady[4][4], axx[4][4], bdy[4][4], bxx[4][4];
+  // A thread's part of a chunk (32 rows x 256 columns per operand): 4 consecutive columns (16 bytes) of the
+  // rows 8 it + lane / 4; a warp instruction reads 8 rows x 64 bytes, warp w the columns 16 w .. 16 w + 15
+  // (see load4). Columns are the same for every row group and every chunk, the operand pointers advance by
+  // 32 rows per fetch (the fetches are issued in chunk order): no 64-bit product inside the loop.
+  static_assert(ldw::kThreads == 512, "staging map: 16 warps x 16 columns = 256 columns");
+  const int lane_ = tid & 31, ccol = (warp << 4) | ((lane_ & 3) << 2), r8 = lane_ >> 2;
+  const int kdy = n0 + ccol, kx = k0 + ccol;
   const bool dy_on = kdy < n_out, x_on = kx < k_in, x_second = kx >= k_split;
   const int dy_left = n_out - kdy, x_left = (x_second ? k_in : k_split) - kx;
   const int64_t xld = x_second ? ldx2 : ldx;
-  const float* dyq = dy + (c_lo * ldw::kChunk + r7) * ldy + kdy;
-  const float* mkq = mask ? mask + (c_lo * ldw::kChunk + r7) * ldm + kdy : nullptr;
-  const float* xq = (x_second ? x2 + (kx - k_split) : x + kx) + (c_lo * ldw::kChunk + r7) * xld;
-  const int64_t ldy8 = kRowStep * ldy, ldm8 = kRowStep * ldm, xld8 = kRowStep * xld;
-  auto fetch = [&](int64_t c, float (&vdy)[ldw::kIts][8], float (&vxx)[ldw::kIts][8]) {
-    const int64_t row_lo = c * ldw::kChunk + r7;
+  const float* dyq = dy + (c_lo * ldw::kChunk + r8) * ldy + kdy;
+  const float* mkq = mask ? mask + (c_lo * ldw::kChunk + r8) * ldm + kdy : nullptr;
+  const float* xq = (x_second ? x2 + (kx - k_split) : x + kx) + (c_lo * ldw::kChunk + r8) * xld;
+  const int64_t ldy8 = 8 * ldy, ldm8 = 8 * ldm, xld8 = 8 * xld;
+  // byte offset of (row r8, column ccol) in a plane of a [32][256] tile; + 4096 per 8 rows
+  const uint32_t t_off = (uint32_t)((ccol >> 3) * kCore + r8 * 16 + (ccol & 7) * 2);
+  auto fetch = [&](int64_t c, float (&vdy)[4][4], float (&vxx)[4][4]) {
+    const int64_t row_lo = c * ldw::kChunk + r8;
 #pragma unroll
-    for (int a = 0; a < ldw::kIts; ++a) {
+    for (int a = 0; a < 4; ++a) {
 #pragma unroll
-      for (int j = 0; j < 8; ++j) vdy[a][j] = 0.0f, vxx[a][j] = 0.0f;
-      if (c < c_hi && row_lo + kRowStep * a < M) {
-        if (dy_on) load8(dyq + a * ldy8, mkq ? mkq + a * ldm8 : nullptr, dy_left, vy, vdy[a]);
-        if (x_on) load8(xq + a * xld8, nullptr, x_left, vx, vxx[a]);
+      for (int j = 0; j < 4; ++j) vdy[a][j] = 0.0f, vxx[a][j] = 0.0f;
+      if (c < c_hi && row_lo + 8 * a < M) {
+        if (dy_on) load4(dyq + a * ldy8, mkq ? mkq + a * ldm8 : nullptr, dy_left, vy, vdy[a]);
+        if (x_on) load4(xq + a * xld8, nullptr, x_left, vx, vxx[a]);
       }
     }
     dyq += ldw::kChunk * ldy, xq += ldw::kChunk * xld;
     if (mkq) mkq += ldw::kChunk * ldm;
+  };
+  auto stage_rows = [&](const float (&vdy)[4][4], const float (&vxx)[4][4], uint8_t* stage) {
+#pragma unroll
+    for (int a = 0; a < 4; ++a) {
+      if (want_db) {
+#pragma unroll
+        for (int j = 0; j < 4; ++j) colsum[j] += vdy[a][j];
+      }
+      split_store4<TERMS>(vdy[a], stage + t_off + a * 4096, ldw::kTile);
+      split_store4<TERMS>(vxx[a], stage + TERMS * ldw::kTile + t_off + a * 4096, ldw::kTile);
+    }
   };
   fetch(c_lo, ady, axx);
   fetch(c_lo + 1, bdy, bxx);
@@ -604,12 +654,10 @@ k_linear_dw_tc(const float* __restrict__ dy, int64_t ldy, const float* __restric
     uint8_t* stage = smem + s * MapT::kStage;
     if (it >= 2) mbar_wait(bar + s, (uint32_t)(((it >> 1) - 1) & 1));
     if (s == 0) {
-      store_rows<TERMS>(ady, stage, tid, want_db ? colsum : nullptr);
-      store_rows<TERMS>(axx, stage + TERMS * ldw::kTile, tid);
+      stage_rows(ady, axx, stage);
       fetch(c + 2, ady, axx);
     } else {
-      store_rows<TERMS>(bdy, stage, tid, want_db ? colsum : nullptr);
-      store_rows<TERMS>(bxx, stage + TERMS * ldw::kTile, tid);
+      stage_rows(bdy, bxx, stage);
       fetch(c + 2, bdy, bxx);
     }
     fence_async_smem();
@@ -640,15 +688,15 @@ k_linear_dw_tc(const float* __restrict__ dy, int64_t ldy, const float* __restric
     mbar_wait(bar + (last & 1), (uint32_t)((last >> 1) & 1));
     tc_fence_after();
   }
-  if (want_db) {  // lanes l, l^1, l^2, l^4 hold the same 8 columns for different rows
-    const int lane = tid & 31, col0 = n0 + (((warp & 7) << 2) | (lane >> 3)) * 8;
+  if (want_db) {  // the 8 lanes with the same lane % 4 hold the same 4 columns for different rows
+    const int lane = tid & 31;
 #pragma unroll
-    for (int j = 0; j < 8; ++j) {
+    for (int j = 0; j < 4; ++j) {
       float v = colsum[j];
-      v += __shfl_xor_sync(0xffffffffu, v, 1);
-      v += __shfl_xor_sync(0xffffffffu, v, 2);
       v += __shfl_xor_sync(0xffffffffu, v, 4);
-      if ((lane & 7) == 0 && col0 + j < n_out) atomicAdd(db + col0 + j, v);
+      v += __shfl_xor_sync(0xffffffffu, v, 8);
+      v += __shfl_xor_sync(0xffffffffu, v, 16);
+      if ((lane >> 2) == 0 && kdy + j < n_out) atomicAdd(db + kdy + j, v);
     }
   }
   // ---- epilogue: accumulator h, lane = row (n_out index), columns = k_in index

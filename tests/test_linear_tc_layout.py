@@ -43,6 +43,16 @@ def st_chunk(buf, base, r, cc, C, vals16):
     buf[off // 2: off // 2 + 8] = vals16
 
 
+def split4(v):
+    """split_store4() of the kernel: 4 float32 -> three 8-byte groups of bf16 bit patterns."""
+    return split8(v)
+
+
+def st4(buf, at, vals16):
+    """8 bytes (4 bf16 values) at byte offset `at`."""
+    buf[at // 2: at // 2 + 4] = vals16
+
+
 def fetch(buf, start, lbo, sbo, mn_major, rows, k_lo=0):
     """What one K = 16 MMA reads: (rows x 16) float32 through a descriptor (buf is uint16-addressed)."""
     r, k = np.meshgrid(np.arange(rows), np.arange(16), indexing="ij")
@@ -99,23 +109,23 @@ def linear_cta(x, mask, planes, bias, M, n_out, k_in, act, bx, by, y, x2=None, k
         s = c & 1
         stage = s * STAGE
         for tid in range(THREADS):
-            warp = tid >> 5
-            for it in range(2):
-                r = ((warp + it * (THREADS // 32)) << 3) | (tid & 7)
-                cc = (tid >> 3) & 3
-                row, k0 = row0 + r, c * CHUNK + cc * 8
-                v = np.zeros(8, np.float32)
+            warp, lane = tid >> 5, tid & 31
+            kq = ((warp & 1) << 4) | ((lane & 3) << 2)           # first of the thread's 4 columns in a chunk
+            fr0 = ((warp >> 1) << 3) | (lane >> 2)               # its first row in the tile
+            a_off = (fr0 >> 3) * (CHUNK >> 3) * K_CORE + (kq >> 3) * K_CORE + (fr0 & 7) * 16 + (kq & 7) * 2
+            for it in range(4):
+                row, k0 = row0 + fr0 + 32 * it, c * CHUNK + kq
+                v = np.zeros(4, np.float32)
                 if row < M:
                     second = k0 >= k_split
                     left = (k_in if second else k_split) - k0
-                    for j in range(8):
+                    for j in range(4):
                         if j < left:
                             val = x2[row, k0 - k_split + j] if second else x[row, k0 + j]
                             v[j] = 0.0 if (mask is not None and not mask[row, k0 + j] > 0) else val
-                hi, mid, lo = split8(v)
-                st_chunk(smem, stage, r, cc, CHUNK, hi)
-                st_chunk(smem, stage + A_TILE, r, cc, CHUNK, mid)
-                st_chunk(smem, stage + 2 * A_TILE, r, cc, CHUNK, lo)
+                hi, mid, lo = split4(v)
+                for pl, vals in enumerate((hi, mid, lo)):
+                    st4(smem, stage + pl * A_TILE + a_off + it * 2048, vals)
         per_plane = n_cols * 4
         for p in range(3):
             src = (b_src + c * 3 * B_TILE + p * B_TILE) // 2
@@ -188,29 +198,31 @@ DW_TILE = DW_CHUNK * WIDE * 2
 DW_STAGE = 6 * DW_TILE
 
 
+DW_THREADS = 512
+
+
 def stage_rows(smem, tile, src, mask, row_lo, M, c0, cols, src2=None, split=None, colsum=None):
-    for tid in range(THREADS):
+    for tid in range(DW_THREADS):
         warp, lane = tid >> 5, tid & 31
-        for it in range(4):
-            wi = warp + it * (THREADS // 32)
-            r = ((wi >> 3) << 3) | (lane & 7)
-            cc = ((wi & 7) << 2) | (lane >> 3)
-            row, k0 = row_lo + r, c0 + cc * 8
-            v = np.zeros(8, np.float32)
+        ccol, r8 = (warp << 4) | ((lane & 3) << 2), lane >> 2
+        t_off = (ccol >> 3) * K_CORE + r8 * 16 + (ccol & 7) * 2
+        k0 = c0 + ccol
+        for a in range(4):
+            row = row_lo + r8 + 8 * a
+            v = np.zeros(4, np.float32)
             if row < M and k0 < cols:
                 sp = cols if src2 is None else split
                 second = k0 >= sp
                 left = (cols if second else sp) - k0
-                for j in range(8):
+                for j in range(4):
                     if j < left:
                         val = src2[row, k0 - sp + j] if second else src[row, k0 + j]
                         v[j] = 0.0 if (mask is not None and not mask[row, k0 + j] > 0) else val
             if colsum is not None:
                 colsum[tid] += v
-            hi, mid, lo = split8(v)
-            st_chunk(smem, tile, r, cc, WIDE, hi)
-            st_chunk(smem, tile + DW_TILE, r, cc, WIDE, mid)
-            st_chunk(smem, tile + 2 * DW_TILE, r, cc, WIDE, lo)
+            hi, mid, lo = split4(v)
+            for pl, vals in enumerate((hi, mid, lo)):
+                st4(smem, tile + pl * DW_TILE + t_off + a * 4096, vals)
 
 
 def dw_cta(dy, mask, x, M, n_out, k_in, bx, gx, by, bz, dw, x2=None, k_split=None, db=None):
@@ -224,7 +236,7 @@ def dw_cta(dy, mask, x, M, n_out, k_in, bx, gx, by, bz, dw, x2=None, k_split=Non
     n_cols = min(WIDE, -(-(k_in - k0) // 16) * 16)
     smem = np.full(2 * DW_STAGE // 2, 0x7FC0, np.uint16)
     acc = np.zeros((2, 128, n_cols), np.float64)
-    colsum = np.zeros((THREADS, 8)) if (db is not None and bz == 0) else None
+    colsum = np.zeros((DW_THREADS, 4)) if (db is not None and bz == 0) else None
     for it, c in enumerate(range(c_lo, c_hi)):
         stage = (it & 1) * DW_STAGE
         stage_rows(smem, stage, dy, mask, c * DW_CHUNK, M, n0, n_out, colsum=colsum)
@@ -238,21 +250,21 @@ def dw_cta(dy, mask, x, M, n_out, k_in, bx, gx, by, bz, dw, x2=None, k_split=Non
                     b = fetch(smem, b0 + PB[t] * DW_TILE + koff, (WIDE >> 3) * K_CORE, K_CORE, True, n_cols)
                     acc[h] += a.astype(np.float64) @ b.astype(np.float64).T
     if colsum is not None:
-        for tid in range(THREADS):
+        for tid in range(DW_THREADS):
             warp, lane = tid >> 5, tid & 31
-            if lane & 7:
+            if lane >> 2:
                 continue
-            col0 = n0 + (((warp & 7) << 2) | (lane >> 3)) * 8
-            total = sum(colsum[tid ^ q] for q in range(8))        # the three xor-shuffles
-            for j in range(8):
-                if col0 + j < n_out:
-                    db[col0 + j] += total[j]
+            kdy = n0 + ((warp << 4) | ((lane & 3) << 2))
+            total = sum(colsum[tid ^ (q << 2)] for q in range(8))   # the three xor-shuffles (4, 8, 16)
+            for j in range(4):
+                if kdy + j < n_out:
+                    db[kdy + j] += total[j]
     for h in range(m_halves):
-        for tid in range(THREADS):
+        for tid in range(DW_THREADS):
             warp = tid >> 5
             n = n0 + h * 128 + (warp & 3) * 32 + (tid & 31)
-            col_lo = (warp >> 2) * 128
-            for cb in range(0, 128, 16):
+            col_lo = (warp >> 2) * 64
+            for cb in range(0, 64, 16):
                 col = col_lo + cb
                 if col >= n_cols:
                     break
