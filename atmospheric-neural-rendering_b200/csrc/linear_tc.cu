@@ -264,9 +264,12 @@ k_linear_tc(const float* __restrict__ x, int64_t ldx, const float* __restrict__ 
   // 32 apart. A warp instruction reads 8 rows x 64 bytes: warp w takes the 64-byte half (w & 1) of the row
   // groups (w >> 1) + 4 it. Row and column are the same for every chunk: the pointers are formed once per
   // tile (the per-chunk 64-bit products were a quarter of all issued instructions).
+  // (lanes 0-15 fill one core matrix, lanes 16-31 the next one: each half-warp's 8-byte stores cover 128
+  // contiguous bytes of shared memory, no bank conflict)
   const int lane_f = tid & 31;
-  const int kq = ((warp & 1) << 4) | ((lane_f & 3) << 2);          // first of this thread's 4 columns in a chunk
-  const int fr0 = ((warp >> 1) << 3) | (lane_f >> 2);              // its first row in the tile
+  const int piece = (lane_f & 1) | ((lane_f >> 4) << 1);           // 16-byte piece of the 64-byte half row
+  const int kq = ((warp & 1) << 4) | (piece << 2);                 // first of this thread's 4 columns in a chunk
+  const int fr0 = ((warp >> 1) << 3) | ((lane_f >> 1) & 7);        // its first row in the tile
   const int64_t frow = row0 + fr0;
   const float* xr = x + frow * ldx + kq;
   const float* x2r = x2 ? x2 + frow * ldx2 + (kq - k_split) : nullptr;
@@ -610,7 +613,8 @@ k_linear_dw_tc(const float* __restrict__ dy, int64_t ldy, const float* __restric
   // (see load4). Columns are the same for every row group and every chunk, the operand pointers advance by
   // 32 rows per fetch (the fetches are issued in chunk order): no 64-bit product inside the loop.
   static_assert(ldw::kThreads == 512, "staging map: 16 warps x 16 columns = 256 columns");
-  const int lane_ = tid & 31, ccol = (warp << 4) | ((lane_ & 3) << 2), r8 = lane_ >> 2;
+  // (lanes 0-15 fill one core matrix, lanes 16-31 the next one: no shared-memory bank conflict)
+  const int lane_ = tid & 31, ccol = (warp << 4) | ((((lane_ & 1) | ((lane_ >> 4) << 1))) << 2), r8 = (lane_ >> 1) & 7;
   const int kdy = n0 + ccol, kx = k0 + ccol;
   const bool dy_on = kdy < n_out, x_on = kx < k_in, x_second = kx >= k_split;
   const int dy_left = n_out - kdy, x_left = (x_second ? k_in : k_split) - kx;
@@ -688,15 +692,15 @@ k_linear_dw_tc(const float* __restrict__ dy, int64_t ldy, const float* __restric
     mbar_wait(bar + (last & 1), (uint32_t)((last >> 1) & 1));
     tc_fence_after();
   }
-  if (want_db) {  // the 8 lanes with the same lane % 4 hold the same 4 columns for different rows
+  if (want_db) {  // the 8 lanes that differ in bits 1-3 hold the same 4 columns for different rows
     const int lane = tid & 31;
 #pragma unroll
     for (int j = 0; j < 4; ++j) {
       float v = colsum[j];
+      v += __shfl_xor_sync(0xffffffffu, v, 2);
       v += __shfl_xor_sync(0xffffffffu, v, 4);
       v += __shfl_xor_sync(0xffffffffu, v, 8);
-      v += __shfl_xor_sync(0xffffffffu, v, 16);
-      if ((lane >> 2) == 0 && kdy + j < n_out) atomicAdd(db + kdy + j, v);
+      if ((lane & 14) == 0 && kdy + j < n_out) atomicAdd(db + kdy + j, v);
     }
   }
   // ---- epilogue: accumulator h, lane = row (n_out index), columns = k_in index

@@ -110,8 +110,9 @@ def linear_cta(x, mask, planes, bias, M, n_out, k_in, act, bx, by, y, x2=None, k
         stage = s * STAGE
         for tid in range(THREADS):
             warp, lane = tid >> 5, tid & 31
-            kq = ((warp & 1) << 4) | ((lane & 3) << 2)           # first of the thread's 4 columns in a chunk
-            fr0 = ((warp >> 1) << 3) | (lane >> 2)               # its first row in the tile
+            piece = (lane & 1) | ((lane >> 4) << 1)
+            kq = ((warp & 1) << 4) | (piece << 2)                # first of the thread's 4 columns in a chunk
+            fr0 = ((warp >> 1) << 3) | ((lane >> 1) & 7)         # its first row in the tile
             a_off = (fr0 >> 3) * (CHUNK >> 3) * K_CORE + (kq >> 3) * K_CORE + (fr0 & 7) * 16 + (kq & 7) * 2
             for it in range(4):
                 row, k0 = row0 + fr0 + 32 * it, c * CHUNK + kq
@@ -204,7 +205,7 @@ DW_THREADS = 512
 def stage_rows(smem, tile, src, mask, row_lo, M, c0, cols, src2=None, split=None, colsum=None):
     for tid in range(DW_THREADS):
         warp, lane = tid >> 5, tid & 31
-        ccol, r8 = (warp << 4) | ((lane & 3) << 2), lane >> 2
+        ccol, r8 = (warp << 4) | (((lane & 1) | ((lane >> 4) << 1)) << 2), (lane >> 1) & 7
         t_off = (ccol >> 3) * K_CORE + r8 * 16 + (ccol & 7) * 2
         k0 = c0 + ccol
         for a in range(4):
@@ -252,10 +253,10 @@ def dw_cta(dy, mask, x, M, n_out, k_in, bx, gx, by, bz, dw, x2=None, k_split=Non
     if colsum is not None:
         for tid in range(DW_THREADS):
             warp, lane = tid >> 5, tid & 31
-            if lane >> 2:
+            if lane & 14:
                 continue
-            kdy = n0 + ((warp << 4) | ((lane & 3) << 2))
-            total = sum(colsum[tid ^ (q << 2)] for q in range(8))   # the three xor-shuffles (4, 8, 16)
+            kdy = n0 + ((warp << 4) | (((lane & 1) | ((lane >> 4) << 1)) << 2))
+            total = sum(colsum[tid ^ (q << 1)] for q in range(8))   # the three xor-shuffles (2, 4, 8)
             for j in range(4):
                 if kdy + j < n_out:
                     db[kdy + j] += total[j]
