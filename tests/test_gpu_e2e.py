@@ -52,12 +52,21 @@ def test_train_and_extract_scripts(tmp_path):
     assert r.returncode != 0 and "NotImplementedError" in r.stderr
 
 
-def test_nerf_pipeline_matches_oracle(monkeypatch):
+@pytest.mark.parametrize("size", ["small", "configs/nerf.json"])
+def test_nerf_pipeline_matches_oracle(monkeypatch, size):
+    """The native NeRF pipeline against oracle/nerf.py (pinned to the reference's NeRFPipeline) on identical
+    draws: a small network, and the shipped configuration (configs/nerf.json: hidden 256, 64 + 128 samples,
+    L_x [14, 14, 10], L_d 4) -- north_star: rendered radiances and densities within 1e-3 relative."""
     from atmonr.pipelines.nerf import NeRFPipeline
     scene = tiny_scene()
-    cfg = {"type": "NeRF", "include_height": False, "point_preprocessor": "horizontal", "num_bands": 4,
-           "ray_origin_height": 20000, "sampler": {"N_c": 8, "N_f": 16}, "encoder": {"L_x": [14, 14, 10], "L_d": 4},
-           "mlp_hidden_dim": 32}
+    if size == "small":
+        cfg = {"type": "NeRF", "include_height": False, "point_preprocessor": "horizontal", "num_bands": 4,
+               "ray_origin_height": 20000, "sampler": {"N_c": 8, "N_f": 16}, "encoder": {"L_x": [14, 14, 10], "L_d": 4},
+               "mlp_hidden_dim": 32}
+    else:
+        cfg = json.load(open(os.path.join(ROOT, "configs", "nerf.json")))["pipeline"]
+        assert cfg["mlp_hidden_dim"] == 256 and cfg["sampler"] == {"N_c": 64, "N_f": 128}
+    n_c, n_f = cfg["sampler"]["N_c"], cfg["sampler"]["N_f"]
     orc = onerf.NeRFOracle(cfg, scene.frame)
     params = orc.init_params(seed=3)
     pipe = NeRFPipeline(cfg, FakeDataset(scene))
@@ -66,7 +75,7 @@ def test_nerf_pipeline_matches_oracle(monkeypatch):
     pipe.eval()   # no density noise: deterministic given the two uniform draws
     b = take(scene.batch, slice(0, 40))
     g = torch.Generator().manual_seed(8)
-    u_c, u_f = torch.rand(40, 8, generator=g), torch.rand(40, 16, generator=g)
+    u_c, u_f = torch.rand(40, n_c, generator=g), torch.rand(40, n_f, generator=g)
     draws = [u_c, u_f]
     real_rand = torch.rand
     monkeypatch.setattr(torch, "rand", lambda *a, **k: draws.pop(0).to(k.get("device", "cpu")) if draws else real_rand(*a, **k))
