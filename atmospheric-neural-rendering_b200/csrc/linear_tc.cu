@@ -159,6 +159,7 @@ __device__ __forceinline__ void load8(const float* __restrict__ src, const float
 __device__ __forceinline__ void load4(const float* __restrict__ src, const float* __restrict__ m, int left, bool vec_ok,
                                       float (&v)[4]) {
   if (vec_ok && left >= 4) {
+    // (ld.global.cg, past the L1, was measured: 8 % slower)
     const float4 p = *reinterpret_cast<const float4*>(src);
     v[0] = p.x, v[1] = p.y, v[2] = p.z, v[3] = p.w;
     if (m) {
@@ -215,6 +216,21 @@ __global__ void k_linear_prep(const float* __restrict__ w, int n_out, int k_in, 
   split_store<TERMS>(v, base, lin::kBTile, r, cc, lin::kChunk);
 }
 
+#ifdef ATM_LIN_TIMING
+// phase timestamps (SM clock) of 64 CTAs from the middle of the grid: tuning aid, not part of the product build
+__device__ long long g_lin_timing[64 * 8];
+__device__ long long g_lin_timing2[64 * 8];
+#define ATM_LIN_STAMP2(slot)                                                                      \
+  if (c == 5 && tid == 0 && blockIdx.y == 0 && blockIdx.x >= gridDim.x / 2 && blockIdx.x < gridDim.x / 2 + 64) \
+    g_lin_timing2[(blockIdx.x - gridDim.x / 2) * 8 + (slot)] = clock64();
+#define ATM_LIN_STAMP(slot)                                                                       \
+  if (tid == 0 && blockIdx.y == 0 && blockIdx.x >= gridDim.x / 2 && blockIdx.x < gridDim.x / 2 + 64) \
+    g_lin_timing[(blockIdx.x - gridDim.x / 2) * 8 + (slot)] = clock64();
+#else
+#define ATM_LIN_STAMP(slot)
+#define ATM_LIN_STAMP2(slot)
+#endif
+
 template <int TERMS>
 __global__ void __launch_bounds__(lin::kThreads, TERMS == 2 ? 2 : 1)
 k_linear_tc(const float* __restrict__ x, int64_t ldx, const float* __restrict__ x2, int64_t ldx2, int k_split,
@@ -228,6 +244,7 @@ k_linear_tc(const float* __restrict__ x, int64_t ldx, const float* __restrict__ 
   const int tid = threadIdx.x, warp = tid >> 5;
   const int64_t row0 = (int64_t)blockIdx.x * lin::kRows;
   const int n0 = blockIdx.y * lin::kCols;                                  // first output column of this CTA
+  ATM_LIN_STAMP(0)
   if (warp == 0) tmem_alloc<lin::kTmemCols>(tmem_ptr);
   uint64_t* full = bar + 2;
   if (tid == 0) {
@@ -293,6 +310,7 @@ k_linear_tc(const float* __restrict__ x, int64_t ldx, const float* __restrict__ 
       }
     }
   };
+  ATM_LIN_STAMP(1)
   fetch_x(0, xa);
   fetch_x(1, xb);
 
@@ -318,8 +336,12 @@ k_linear_tc(const float* __restrict__ x, int64_t ldx, const float* __restrict__ 
   for (int c = 0; c < k_chunks; ++c) {
     const int s = c & 1;
     uint8_t* stage = smem + s * MapT::kStage;
+    if (c == 1) { ATM_LIN_STAMP(2) }
+    if (c == 4) { ATM_LIN_STAMP(3) }
     // the MMAs of chunk c-2 read this stage: wait for their commit (completion number (c>>1)-1 of bar[s])
+    ATM_LIN_STAMP2(0)
     if (c >= 2) mbar_wait(bar + s, (uint32_t)(((c >> 1) - 1) & 1));
+    ATM_LIN_STAMP2(1)
     // ---- X chunk: 128 rows x 32 columns float32 -> TERMS bf16 planes (4 groups of 4 values per thread)
     float cur[4][4];
     if (s == 0) {
@@ -335,18 +357,23 @@ k_linear_tc(const float* __restrict__ x, int64_t ldx, const float* __restrict__ 
         for (int j = 0; j < 4; ++j) cur[it][j] = xb[it][j];
       fetch_x(c + 2, xb);
     }
+    ATM_LIN_STAMP2(2)
 #pragma unroll
     for (int it = 0; it < 4; ++it) split_store4<TERMS>(cur[it], stage + a_off + it * 2048, lin::kATile);
+    ATM_LIN_STAMP2(3)
     if (tid == 0 && c >= 1 && c + 1 < k_chunks) {
       // chunk c - 1 (the other stage) is the ((c-1)>>1)-th completion of its barrier
       mbar_wait(bar + (s ^ 1), (uint32_t)(((c - 1) >> 1) & 1));
       issue_b(c + 1);
     }
+    ATM_LIN_STAMP2(4)
     fence_async_smem();
     tc_fence_before();
     __syncthreads();
+    ATM_LIN_STAMP2(5)
     if (warp == 0) {
       mbar_wait(full + s, (uint32_t)((c >> 1) & 1));   // the weight planes of this chunk have landed
+      ATM_LIN_STAMP2(6)
       tc_fence_after();
       const uint32_t a0 = sbase + s * MapT::kStage, b0 = a0 + TERMS * lin::kATile;
       // (A plane, B plane): hi*hi, hi*mid, mid*hi, mid*mid, hi*lo, lo*hi  /  hi*hi, hi*lo, lo*hi
@@ -363,12 +390,14 @@ k_linear_tc(const float* __restrict__ x, int64_t ldx, const float* __restrict__ 
       umma_commit(bar + s);
     }
   }
+  ATM_LIN_STAMP(4)
   // every MMA has been issued by warp 0 in order; the last commit covers them all
   {
     const int last = k_chunks - 1;
     mbar_wait(bar + (last & 1), (uint32_t)((last >> 1) & 1));
     tc_fence_after();
   }
+  ATM_LIN_STAMP(5)
   // ---- epilogue, one 128-column half of the accumulator at a time: thread (warp w, lane) owns row
   // (w % 4) * 32 + lane and columns (w / 4) * 64 .. + 64 of the half. bias + activation, then the half is
   // staged in shared memory (the operand stages are free: every MMA is complete; row pitch 132 floats:
@@ -491,9 +520,11 @@ k_linear_tc(const float* __restrict__ x, int64_t ldx, const float* __restrict__ 
       }
     }
   }
+  ATM_LIN_STAMP(6)
   tc_fence_before();
   __syncthreads();
   if (warp == 0) tmem_dealloc<lin::kTmemCols>(acc);
+  ATM_LIN_STAMP(7)
 }
 
 // =========================================================================================
@@ -825,5 +856,14 @@ int atmonr_linear_dw_tc(const float* dy, int64_t ldy, const float* mask, int64_t
   ATM_CHECK_LAUNCH("atmonr_linear_dw_tc");
   return 0;
 }
+
+#ifdef ATM_LIN_TIMING
+int atmonr_debug_lin_timing(long long* out_host) {
+  return cudaMemcpyFromSymbol(out_host, atm::g_lin_timing, sizeof(long long) * 64 * 8) == cudaSuccess ? 0 : -1;
+}
+int atmonr_debug_lin_timing2(long long* out_host) {
+  return cudaMemcpyFromSymbol(out_host, atm::g_lin_timing2, sizeof(long long) * 64 * 8) == cudaSuccess ? 0 : -1;
+}
+#endif
 
 }  // extern "C"
