@@ -38,7 +38,7 @@ using namespace tc;
 // weight-gradient MMAs with sample-group concatenation
 // =========================================================================================
 // dW[o][i] = sum_s delta[s][o] * act[s][i] has a tiny output (<= 32 x 32) and a huge K (samples),
-// while a tcgen05.mma of M = 128 costs ~40 cycles whatever N <= 64 is (scratch/ubench): the cost
+// while a tcgen05.mma of M = 128 costs ~40 cycles whatever N <= 64 is (micro-benchmark, round 1): the cost
 // is the number of MMAs. Both operands are read MN-major from [rows][C] tiles whose 8-row groups
 // are contiguous blocks of (C/8)*128 bytes, so column group C/8 + j of row group g IS column
 // group j of row group g + 1: reading "too many" columns concatenates the following row groups

@@ -1,5 +1,5 @@
 #!/usr/bin/env bash
-# usage (on the GPU box): bash scratch/validate.sh <tag>  -- tests, bench line, ncu launch list, ncu full captures
+# usage (on the GPU box): bash scripts/validate_gpu.sh <tag>  -- tests, bench line, ncu launch list, ncu full captures
 tag=${1:-r3}
 o=gpurun_out
 mkdir -p $o
