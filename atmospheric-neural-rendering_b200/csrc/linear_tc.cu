@@ -31,6 +31,14 @@
 // contiguous rows (a thread owns one ROW of the accumulator: direct stores would touch 32 rows per
 // warp instruction; measured round 2: 100 k cycles per tile with per-thread weight copies and
 // direct stores, 12.4 k of which are tensor-core time).
+//
+// Where a tile's time goes now (-DATM_LIN_TIMING + scripts/diag_lin_timing.py, 786 432 x 256 x 256, two
+// CTAs per SM): 47 k cycles per 128-row tile = prologue 1.5 k, first chunk 8 k (the first activations
+// come from DRAM), seven more chunks 3.3 k each, of which 2 k are spent waiting for activations that
+// were requested TWO chunks (6 k cycles) earlier, epilogue 10-14 k; the six MMAs of a chunk take 0.8 k.
+// The tensor pipe is therefore 25 % busy; what would raise it is more activation bytes in flight per SM
+// than two register sets per CTA allow (bulk copies of the float32 rows into a shared-memory ring need
+// the space the second CTA occupies), i.e. bf16 activations between the layers.
 #include <cuda_bf16.h>
 
 #include "common.cuh"
@@ -124,28 +132,6 @@ template <> struct Products<2> {
   __device__ static constexpr int a(int t) { return t == 2 ? 1 : 0; }
   __device__ static constexpr int b(int t) { return t == 1 ? 1 : 0; }
 };
-
-// eight consecutive float32 of a row (`left` = columns left in the row; fewer than 8 -> zero fill),
-// optionally zeroed where the matching entry of `m` is not positive (the ReLU derivative of the
-// layer's output, applied while the gradient operand is staged)
-__device__ __forceinline__ void load8(const float* __restrict__ src, const float* __restrict__ m, int left, bool vec_ok,
-                                      float (&v)[8]) {
-  if (vec_ok && left >= 8) {
-    const float4 p = *reinterpret_cast<const float4*>(src), q = *reinterpret_cast<const float4*>(src + 4);
-    v[0] = p.x, v[1] = p.y, v[2] = p.z, v[3] = p.w, v[4] = q.x, v[5] = q.y, v[6] = q.z, v[7] = q.w;
-    if (m) {
-      const float4 a = *reinterpret_cast<const float4*>(m), b = *reinterpret_cast<const float4*>(m + 4);
-      const float mm[8] = {a.x, a.y, a.z, a.w, b.x, b.y, b.z, b.w};
-#pragma unroll
-      for (int j = 0; j < 8; ++j)
-        if (!(mm[j] > 0.0f)) v[j] = 0.0f;
-    }
-  } else {
-#pragma unroll
-    for (int j = 0; j < 8; ++j)
-      if (j < left) v[j] = (m && !(m[j] > 0.0f)) ? 0.0f : src[j];
-  }
-}
 
 // ---- staging in groups of FOUR values ------------------------------------------------------------
 // The activations are staged by warp instructions that read 8 rows x 64 contiguous bytes (lane / 4 =
@@ -542,7 +528,6 @@ constexpr int kChunk = 32;                         // rows per stage (the MMA K 
 constexpr int kWide = 256;                         // columns of a staged operand block
 constexpr int kThreads = 512;                         // 16 warps: the staging code is a chain of dependent conversions,
                                                    // 8 warps left the SM at an IPC of 0.9 (ncu round 2)
-constexpr int kIts = 32 / (kThreads / 32);         // 8-row x 128-byte items per thread and operand: 32 warp items per chunk
 constexpr int kTile = kChunk * kWide * 2;          // 16 KB: one bf16 plane of one operand
 constexpr uint32_t kTmemCols = 512;
 template <int TERMS>
@@ -553,45 +538,6 @@ struct Map {
   static constexpr int kBytes = kTmemPtr + 16;
 };
 }  // namespace ldw
-
-// rows [row_lo, row_lo + 32) x columns [c0, c0 + 256) of a row-major float32 matrix -> three bf16
-// planes in the [32][256] tile layout (zero outside the matrix), in two halves so that the global
-// loads of the NEXT chunk are in flight while the current one is split and stored:
-// fetch_rows() requests this thread's 4 x 8 values into registers, store_rows() splits and stores them.
-__device__ __forceinline__ void fetch_rows(const float* __restrict__ src, int64_t ld, const float* __restrict__ src2,
-                                           int64_t ld2, int split, const float* __restrict__ mask, int64_t ldm,
-                                           int64_t row_lo, int64_t M, int c0, int cols, bool vec_ok, int tid,
-                                           float (&v)[ldw::kIts][8]) {
-  const int warp = tid >> 5, lane = tid & 31;
-#pragma unroll
-  for (int it = 0; it < ldw::kIts; ++it) {
-    const int wi = warp + it * (ldw::kThreads / 32);             // 32 warp items: 4 row groups x 8 column blocks
-    const int r = ((wi >> 3) << 3) | (lane & 7), cc = ((wi & 7) << 2) | (lane >> 3);
-    const int64_t row = row_lo + r;
-    const int k0 = c0 + cc * 8;
-#pragma unroll
-    for (int j = 0; j < 8; ++j) v[it][j] = 0.0f;
-    if (row < M && k0 < cols) {
-      const bool second = k0 >= split;   // columns [split, cols) live in src2
-      load8(second ? src2 + row * ld2 + (k0 - split) : src + row * ld + k0, mask ? mask + row * ldm + k0 : nullptr,
-            (second ? cols : split) - k0, vec_ok, v[it]);
-    }
-  }
-}
-template <int TERMS>
-__device__ __forceinline__ void store_rows(const float (&v)[ldw::kIts][8], uint8_t* tile, int tid, float* colsum = nullptr) {
-  const int warp = tid >> 5, lane = tid & 31;
-#pragma unroll
-  for (int it = 0; it < ldw::kIts; ++it) {
-    const int wi = warp + it * (ldw::kThreads / 32);
-    const int r = ((wi >> 3) << 3) | (lane & 7), cc = ((wi & 7) << 2) | (lane >> 3);
-    if (colsum) {  // a thread's column group cc is the same in every iteration and every chunk
-#pragma unroll
-      for (int j = 0; j < 8; ++j) colsum[j] += v[it][j];
-    }
-    split_store<TERMS>(v[it], tile, ldw::kTile, r, cc, ldw::kWide);
-  }
-}
 
 template <int TERMS>
 __global__ void __launch_bounds__(ldw::kThreads, 1)
