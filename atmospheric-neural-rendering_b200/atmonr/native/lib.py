@@ -56,6 +56,7 @@ GP, FP, MP = C.POINTER(GridT), C.POINTER(FrameT), C.POINTER(MlpT)
 SIGNATURES = {
     "atmonr_abi_version": [],
     "atmonr_last_error": [],
+    "atmonr_l2_persist": [P, C.c_size_t, F32, P],
     "atmonr_grid_layout": [I32, I32, I32, I32, F32, GP],
     "atmonr_get_rays": [P, P, P, P, P, I64, F32, F64, I32, P, P, P, P, C.POINTER(C.c_int), P],
     "atmonr_gather_batch": [P, P, P, P, P, P, P, P, I64, I64, P, P, P, P, P, P, P, P, P],
@@ -125,7 +126,8 @@ def load() -> C.CDLL:
 
 
 # kernels launched by each entry point (for launch accounting in bench.py)
-LAUNCHES = {"atmonr_band_loss": 2, "atmonr_grid_layout": 0, "atmonr_abi_version": 0, "atmonr_last_error": 0}
+LAUNCHES = {"atmonr_band_loss": 2, "atmonr_grid_layout": 0, "atmonr_abi_version": 0, "atmonr_last_error": 0,
+            "atmonr_l2_persist": 0}
 
 
 class CallStats:

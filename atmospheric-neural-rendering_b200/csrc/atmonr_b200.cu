@@ -1095,6 +1095,42 @@ extern "C" {
 int atmonr_abi_version(void) { return ATMONR_ABI_VERSION; }
 const char* atmonr_last_error(void) { return g_last_error; }
 
+int atmonr_l2_persist(const void* ptr, size_t bytes, float hit_ratio, void* stream) {
+  // cudaAccessPolicyWindow on `stream`: accesses to [ptr, ptr + bytes) by kernels launched on the stream
+  // afterwards are kept in the L2's persisting set-aside; bytes == 0 clears the window.
+  int dev = 0, max_window = 0, max_persist = 0;
+  if (cudaGetDevice(&dev) != cudaSuccess) return fail("atmonr_l2_persist", "no device");
+  cudaDeviceGetAttribute(&max_window, cudaDevAttrMaxAccessPolicyWindowSize, dev);
+  cudaDeviceGetAttribute(&max_persist, cudaDevAttrMaxPersistingL2CacheSize, dev);
+  cudaStreamAttrValue attr;
+  memset(&attr, 0, sizeof(attr));
+  if (bytes == 0 || !ptr) {
+    attr.accessPolicyWindow.num_bytes = 0;
+    attr.accessPolicyWindow.hitProp = cudaAccessPropertyNormal;
+    attr.accessPolicyWindow.missProp = cudaAccessPropertyNormal;
+    cudaStreamSetAttribute(S(stream), cudaStreamAttributeAccessPolicyWindow, &attr);
+    cudaCtxResetPersistingL2Cache();
+    return 0;
+  }
+  ATM_REQUIRE(max_window > 0 && max_persist > 0, "atmonr_l2_persist", "the device has no persisting L2");
+  size_t want = bytes < (size_t)max_persist ? bytes : (size_t)max_persist;
+  if (cudaDeviceSetLimit(cudaLimitPersistingL2CacheSize, want) != cudaSuccess) {
+    cudaGetLastError();
+    return fail("atmonr_l2_persist", "cudaDeviceSetLimit(cudaLimitPersistingL2CacheSize) failed");
+  }
+  attr.accessPolicyWindow.base_ptr = const_cast<void*>(ptr);
+  attr.accessPolicyWindow.num_bytes = bytes < (size_t)max_window ? bytes : (size_t)max_window;
+  attr.accessPolicyWindow.hitRatio = hit_ratio * (float)((double)want / (double)attr.accessPolicyWindow.num_bytes < 1.0
+                                                        ? (double)want / (double)attr.accessPolicyWindow.num_bytes : 1.0);
+  attr.accessPolicyWindow.hitProp = cudaAccessPropertyPersisting;
+  attr.accessPolicyWindow.missProp = cudaAccessPropertyStreaming;
+  if (cudaStreamSetAttribute(S(stream), cudaStreamAttributeAccessPolicyWindow, &attr) != cudaSuccess) {
+    cudaGetLastError();
+    return fail("atmonr_l2_persist", "cudaStreamSetAttribute(access policy window) failed");
+  }
+  return 0;
+}
+
 int atmonr_grid_layout(int n_dims, int n_levels, int log2_hashmap_size, int base_resolution,
                        float per_level_scale, atmonr_grid_t* out) {
   ATM_REQUIRE(out, "atmonr_grid_layout", "null output");

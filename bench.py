@@ -309,6 +309,9 @@ def run_native(args) -> None:
     if dp_sharded:
         opt.shard_large_parameters()      # tables: reduce-scatter -> AdamW on 1/world -> all-gather of the fp16 shadow
     B, K, W = args.rays, args.steps, args.warmup
+    if os.environ.get("ATMONR_L2_PERSIST"):   # tuning experiment: pin the fp16 table in the L2's persisting set-aside
+        t16 = pipe.pos_encoder.table_f16()
+        L.call("atmonr_l2_persist", L.ptr(t16), t16.numel() * 2, float(os.environ["ATMONR_L2_PERSIST"]), L.stream())
 
     # fixed set of batches, each rank its own rays (weak scaling)
     loader = BatchLoader(dataset, batch_size=B, shuffle=True, seed=1234 + rank)

@@ -63,6 +63,12 @@ typedef struct {
 int atmonr_abi_version(void);
 const char* atmonr_last_error(void);
 
+/* Optional tuning call (no reference counterpart): keep [ptr, ptr + bytes) -- the fp16 hash table the
+ * field kernels gather from -- in the L2's persisting set-aside for kernels launched on `stream`
+ * afterwards (cudaAccessPolicyWindow; hit_ratio in (0, 1], scaled down when the set-aside is smaller
+ * than the range). bytes == 0 clears the window. */
+int atmonr_l2_persist(const void* ptr, size_t bytes, float hit_ratio, void* stream);
+
 /* Host only (no GPU needed): level table of tcnn's GridEncoding. */
 int atmonr_grid_layout(int n_dims, int n_levels, int log2_hashmap_size, int base_resolution,
                        float per_level_scale, atmonr_grid_t* out_host);
