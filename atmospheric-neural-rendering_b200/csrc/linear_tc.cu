@@ -259,10 +259,10 @@ k_linear_tc(const float* __restrict__ x, int64_t ldx, const float* __restrict__ 
   // this thread's 2 x 8 values of a chunk: a quarter warp (8 lanes) owns the 8 rows of ONE core matrix =
   // 128 contiguous bytes of shared memory (no bank conflicts); in global memory the warp reads 8 rows x
   // 128 contiguous bytes
-  // The values are requested TWO chunks ahead (two register sets, xa for even and xb for odd chunks): one
+  // The values are requested THREE chunks ahead (three register sets, set = chunk % 3): one
   // chunk's worth of bytes in flight per CTA (16 KB) did not cover the global-load latency (ncu round 2:
   // 35 % of the warp samples on the long scoreboard, DRAM at a third of its rate).
-  float xa[4][4], xb[4][4];
+  float xa[4][4], xb[4][4], xc[4][4];   // chunks c, c + 1, c + 2 in flight (set = chunk % 3)
   // This thread's part of a chunk (128 rows x 32 columns): 4 consecutive columns (16 bytes) of four rows
   // 32 apart. A warp instruction reads 8 rows x 64 bytes: warp w takes the 64-byte half (w & 1) of the row
   // groups (w >> 1) + 4 it. Row and column are the same for every chunk: the pointers are formed once per
@@ -299,6 +299,7 @@ k_linear_tc(const float* __restrict__ x, int64_t ldx, const float* __restrict__ 
   ATM_LIN_STAMP(1)
   fetch_x(0, xa);
   fetch_x(1, xb);
+  fetch_x(2, xc);
 
   // ---- B chunks: TERMS planes, already split and in tile order: the first n_cols rows of a plane are its
   // first n_cols * 64 bytes -> one bulk copy per plane, announced on full[stage]. The copy of chunk c + 1 is
@@ -319,6 +320,7 @@ k_linear_tc(const float* __restrict__ x, int64_t ldx, const float* __restrict__ 
     if (k_chunks > 1) issue_b(1);
   }
 
+  int set3 = 0;
   for (int c = 0; c < k_chunks; ++c) {
     const int s = c & 1;
     uint8_t* stage = smem + s * MapT::kStage;
@@ -329,23 +331,23 @@ k_linear_tc(const float* __restrict__ x, int64_t ldx, const float* __restrict__ 
     if (c >= 2) mbar_wait(bar + s, (uint32_t)(((c >> 1) - 1) & 1));
     ATM_LIN_STAMP2(1)
     // ---- X chunk: 128 rows x 32 columns float32 -> TERMS bf16 planes (4 groups of 4 values per thread)
-    float cur[4][4];
-    if (s == 0) {
+    // the set of chunk c is split and stored, then refilled with chunk c + 3: three chunks' worth of loads
+    // (48 KB per CTA) stay in flight -- with two, 2 k of every 3 k-cycle chunk were spent waiting for them
+    if (set3 == 0) {
 #pragma unroll
-      for (int it = 0; it < 4; ++it)
+      for (int it = 0; it < 4; ++it) split_store4<TERMS>(xa[it], stage + a_off + it * 2048, lin::kATile);
+      fetch_x(c + 3, xa);
+    } else if (set3 == 1) {
 #pragma unroll
-        for (int j = 0; j < 4; ++j) cur[it][j] = xa[it][j];
-      fetch_x(c + 2, xa);
+      for (int it = 0; it < 4; ++it) split_store4<TERMS>(xb[it], stage + a_off + it * 2048, lin::kATile);
+      fetch_x(c + 3, xb);
     } else {
 #pragma unroll
-      for (int it = 0; it < 4; ++it)
-#pragma unroll
-        for (int j = 0; j < 4; ++j) cur[it][j] = xb[it][j];
-      fetch_x(c + 2, xb);
+      for (int it = 0; it < 4; ++it) split_store4<TERMS>(xc[it], stage + a_off + it * 2048, lin::kATile);
+      fetch_x(c + 3, xc);
     }
+    set3 = set3 == 2 ? 0 : set3 + 1;
     ATM_LIN_STAMP2(2)
-#pragma unroll
-    for (int it = 0; it < 4; ++it) split_store4<TERMS>(cur[it], stage + a_off + it * 2048, lin::kATile);
     ATM_LIN_STAMP2(3)
     if (tid == 0 && c >= 1 && c + 1 < k_chunks) {
       // chunk c - 1 (the other stage) is the ((c-1)>>1)-th completion of its barrier
