@@ -32,13 +32,15 @@
 // warp instruction; measured round 2: 100 k cycles per tile with per-thread weight copies and
 // direct stores, 12.4 k of which are tensor-core time).
 //
-// Where a tile's time goes now (-DATM_LIN_TIMING + scripts/diag_lin_timing.py, 786 432 x 256 x 256, two
-// CTAs per SM): 47 k cycles per 128-row tile = prologue 1.5 k, first chunk 8 k (the first activations
-// come from DRAM), seven more chunks 3.3 k each, of which 2 k are spent waiting for activations that
-// were requested TWO chunks (6 k cycles) earlier, epilogue 10-14 k; the six MMAs of a chunk take 0.8 k.
-// The tensor pipe is therefore 25 % busy; what would raise it is more activation bytes in flight per SM
-// than two register sets per CTA allow (bulk copies of the float32 rows into a shared-memory ring need
-// the space the second CTA occupies), i.e. bf16 activations between the layers.
+// Where a tile's time went with TWO register sets (-DATM_LIN_TIMING + scripts/diag_lin_timing.py,
+// 786 432 x 256 x 256, two CTAs per SM): 47 k cycles per 128-row tile = prologue 1.5 k, first chunk 8 k
+// (the first activations come from DRAM), seven more chunks 3.3 k each, of which 2 k were spent waiting
+// for activations requested two chunks (6 k cycles) earlier, epilogue 10-14 k; the six MMAs of a chunk
+// take 0.8 k. Hence three sets (three chunks, 48 KB per CTA, in flight): layer 0.55 -> 0.51 ms, NeRF step
+// 25.4 -> 23.8 ms; a fourth set fits the 128 registers but was slower (24.4 ms). The tensor pipe is 29 %
+// busy; raising it further needs more activation bytes in flight per SM than registers allow (bulk copies
+// of float32 rows into a shared-memory ring need the space the second CTA occupies), i.e. bf16
+// activations between the layers.
 #include <cuda_bf16.h>
 
 #include "common.cuh"
