@@ -30,6 +30,15 @@ inline int nerf_enc_cfg(const int32_t* pos_freqs, int dir_freqs, NerfEncCfg& c) 
 // ------------------------------------------------------------------------------------------------
 // forward, one sample: row = [pos encoding | dir encoding], pn = preprocessed point
 // ------------------------------------------------------------------------------------------------
+// sin and cos of one phase with ONE argument reduction on the device (the phases reach 2^13 pi)
+ATM_HD void sin_cos(float arg, float& sn, float& cs) {
+#if defined(__CUDA_ARCH__)
+  sincosf(arg, &sn, &cs);
+#else
+  sn = sinf(arg), cs = cosf(arg);
+#endif
+}
+
 ATM_HD void nerf_encode_sample(const atmonr_frame_t& f, const GeoFrame& gf, const float* o, const float* d, float zz,
                                const NerfEncCfg& cfg, float* row, float* pn) {
   // samplers.py:101 / :45: origin + dir * z, two float32 operations
@@ -41,9 +50,10 @@ ATM_HD void nerf_encode_sample(const atmonr_frame_t& f, const GeoFrame& gf, cons
     const int L = cfg.freqs[a];
     float fr = 1.0f;
     for (int l = 0; l < L; ++l) {
-      const float arg = (fr * PI_F) * p[a];
-      row[cfg.col0[a] + l] = sinf(arg);
-      row[cfg.col0[a] + L + l] = cosf(arg);
+      float sn, cs;
+      sin_cos((fr * PI_F) * p[a], sn, cs);
+      row[cfg.col0[a] + l] = sn;
+      row[cfg.col0[a] + L + l] = cs;
       fr *= 2.0f;
     }
   }
@@ -51,9 +61,10 @@ ATM_HD void nerf_encode_sample(const atmonr_frame_t& f, const GeoFrame& gf, cons
   for (int a = 0; a < 3; ++a) {
     float fr = 1.0f;
     for (int l = 0; l < cfg.dir_freqs; ++l) {
-      const float arg = (fr * PI_F) * d[a];
-      drow[a * 2 * cfg.dir_freqs + 2 * l] = sinf(arg);
-      drow[a * 2 * cfg.dir_freqs + 2 * l + 1] = cosf(arg);
+      float sn, cs;
+      sin_cos((fr * PI_F) * d[a], sn, cs);
+      drow[a * 2 * cfg.dir_freqs + 2 * l] = sn;
+      drow[a * 2 * cfg.dir_freqs + 2 * l + 1] = cs;
       fr *= 2.0f;
     }
   }
@@ -78,9 +89,10 @@ ATM_HD float nerf_encode_sample_bwd(const atmonr_frame_t& f, const GeoFrame& gf,
     float fr = 1.0f, acc = 0.0f;
     for (int l = 0; l < L; ++l) {
       const float c = fr * PI_F;
-      const float arg = c * p;
+      float sn, cs;
+      sin_cos(c * p, sn, cs);
       // d sin(c p) = c cos(c p), d cos(c p) = -c sin(c p)
-      acc += (grow[cfg.col0[a] + l] * cosf(arg) - grow[cfg.col0[a] + L + l] * sinf(arg)) * c;
+      acc += (grow[cfg.col0[a] + l] * cs - grow[cfg.col0[a] + L + l] * sn) * c;
       fr *= 2.0f;
     }
     gp[a] = acc;
