@@ -684,21 +684,54 @@ k_linear_dw_tc(const float* __restrict__ dy, int64_t ldy, const float* __restric
       if ((lane & 14) == 0 && kdy + j < n_out) atomicAdd(db + kdy + j, v);
     }
   }
-  // ---- epilogue: accumulator h, lane = row (n_out index), columns = k_in index
-  for (int h = 0; h < m_halves; ++h) {
-    const int n = n0 + h * 128 + (warp & 3) * 32 + (tid & 31);
-    constexpr int kColsPerWarp = 256 / (ldw::kThreads / 128);      // the warps of a lane quarter split the columns
-    const int col_lo = (warp >> 2) * kColsPerWarp;
+  // ---- epilogue: accumulator h, TMEM lane = row of dW (n_out index), columns = k_in index. A thread owns
+  // one ROW of the accumulator, so REDs issued straight from the registers touch 32 rows = 32 sectors
+  // per warp instruction (all CTAs add into the same 256 x 256 block: 148 x 65 536 scalar REDs = 9.7 M
+  // sectors, ~0.1 ms of a 0.14 ms coarse-pass launch). The block goes through shared memory instead (the
+  // operand stages are free: every MMA is complete), one 128-column half at a time, and is added with
+  // red.global.add.v4.f32 along the rows: a warp instruction covers 512 contiguous bytes (16 sectors for
+  // 128 values instead of 32 sectors for 32).
+  {
+    float* tile = reinterpret_cast<float*>(smem);
+    constexpr int kHalfCols = 128, pitch = kHalfCols + 4;          // 128 x 132 floats = 66 KB <= one stage pair
+    static_assert(128 * pitch * 4 <= 2 * MapT::kStage, "the staged half must fit in the operand stages");
+    const int lane = tid & 31, wrow = tid >> 5;
+    const bool vec = (k_in & 3) == 0 && (k0 & 3) == 0 && (reinterpret_cast<uintptr_t>(dw) & 15) == 0;
+    for (int h = 0; h < m_halves; ++h) {
+      for (int h0 = 0; h0 < n_cols; h0 += kHalfCols) {
+        __syncthreads();                                           // the previous half has been added
+        const int r = (warp & 3) * 32 + lane;                      // TMEM lane of this thread
 #pragma unroll 1
-    for (int cb = 0; cb < kColsPerWarp; cb += 16) {
-      const int col = col_lo + cb;
-      if (col >= n_cols) break;                                  // warp-uniform
-      float v[16];
-      tmem_ld16(tmem_addr(acc, warp, h * 256 + col), v);
-      if (n < n_out) {
+        for (int cb = 0; cb < 32; cb += 16) {                      // 4 warps per lane quarter x 32 columns
+          const int lc = (warp >> 2) * 32 + cb, col = h0 + lc;
+          if (col >= n_cols) break;                                // warp-uniform
+          float v[16];
+          tmem_ld16(tmem_addr(acc, warp, h * 256 + col), v);
+          float4* dst = reinterpret_cast<float4*>(tile + r * pitch + lc);
 #pragma unroll
-        for (int j = 0; j < 16; ++j)
-          if (k0 + col + j < k_in) atomicAdd(dw + (size_t)n * k_in + k0 + col + j, v[j]);
+          for (int q = 0; q < 4; ++q) dst[q] = make_float4(v[4 * q], v[4 * q + 1], v[4 * q + 2], v[4 * q + 3]);
+        }
+        __syncthreads();
+        const int w_valid = min(kHalfCols, k_in - k0 - h0);        // real columns of this half
+        const int rows = min(128, n_out - n0 - h * 128);           // real rows of this accumulator
+        if (w_valid <= 0 || rows <= 0) continue;                   // uniform
+        float* base = dw + (size_t)(n0 + h * 128) * k_in + k0 + h0;
+        if (vec && w_valid == kHalfCols) {
+#pragma unroll
+          for (int u = 0; u < 8; ++u) {                            // 128 rows x 32 groups of 4 over 512 threads
+            const int rr = wrow + 16 * u;
+            if (rr >= rows) break;                                 // warp-uniform
+            const float4 v = *reinterpret_cast<const float4*>(tile + rr * pitch + 4 * lane);
+            asm volatile("red.global.add.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(base + (size_t)rr * k_in + 4 * lane),
+                         "f"(v.x), "f"(v.y), "f"(v.z), "f"(v.w)
+                         : "memory");
+          }
+        } else {
+          for (int i = tid; i < rows * w_valid; i += ldw::kThreads) {
+            const int rr = i / w_valid, cc = i - rr * w_valid;
+            atomicAdd(base + (size_t)rr * k_in + cc, tile[rr * pitch + cc]);
+          }
+        }
       }
     }
   }
