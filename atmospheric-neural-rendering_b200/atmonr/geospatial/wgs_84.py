@@ -134,13 +134,21 @@ def get_rays(lat, lon, alt, thetav, phiv, ray_origin_height, tol: float = 10.0, 
 
 
 def filter_rays(ray_origin, ray_dir, ray_rad):
-    """Mask of rays whose origin, direction and radiance are all finite. wgs_84.py:293-313."""
+    """Mask of rays whose origin, direction and radiance hold no NaN. wgs_84.py:293-313. CUDA inputs:
+    `atmonr_filter_rays` (csrc/rays.cu); ATMONR_NATIVE_RAYS=0 / CPU inputs: the torch expressions."""
+    if ray_origin.is_cuda and os.environ.get("ATMONR_NATIVE_RAYS", "1") != "0":
+        from atmonr.native import ops
+        return ops.filter_rays(ray_origin, ray_dir, ray_rad)
     bad = ray_origin.isnan().any(dim=1) | ray_dir.isnan().any(dim=1) | ray_rad.isnan()
     return ~bad
 
 
 def normalize_rays(ray_origin, ray_dir, ray_len):
-    """Scale/offset that maps origins and end points into [-1,1]^3. wgs_84.py:316-339."""
+    """Scale/offset that maps origins and end points into [-1,1]^3. wgs_84.py:316-339. CUDA inputs:
+    `atmonr_ray_extent` + `atmonr_normalize_origins` (csrc/rays.cu), bit for bit the expressions below."""
+    if ray_origin.is_cuda and os.environ.get("ATMONR_NATIVE_RAYS", "1") != "0":
+        from atmonr.native import ops
+        return ops.normalize_rays(ray_origin, ray_dir, ray_len)
     ends = torch.cat([ray_origin, ray_origin + ray_dir * ray_len[:, None]], dim=0)
     hi = ends.max(dim=0)[0].double()
     lo = ends.min(dim=0)[0].double()

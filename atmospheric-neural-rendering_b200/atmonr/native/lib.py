@@ -59,6 +59,9 @@ SIGNATURES = {
     "atmonr_l2_persist": [P, C.c_size_t, F32, P],
     "atmonr_grid_layout": [I32, I32, I32, I32, F32, GP],
     "atmonr_get_rays": [P, P, P, P, P, I64, F32, F64, I32, P, P, P, P, C.POINTER(C.c_int), P],
+    "atmonr_filter_rays": [P, P, P, I64, P, P],
+    "atmonr_ray_extent": [P, P, P, I64, P, P, P],
+    "atmonr_normalize_origins": [P, I64, P, F64, P, P],
     "atmonr_gather_batch": [P, P, P, P, P, P, P, P, I64, I64, P, P, P, P, P, P, P, P, P],
     "atmonr_sample_uniform": [P, P, P, P, P, I64, I32, I32, U64, U64, P, P, P],
     "atmonr_preprocess_horizontal": [FP, P, P, I64, I32, P],
@@ -127,7 +130,7 @@ def load() -> C.CDLL:
 
 # kernels launched by each entry point (for launch accounting in bench.py)
 LAUNCHES = {"atmonr_band_loss": 2, "atmonr_grid_layout": 0, "atmonr_abi_version": 0, "atmonr_last_error": 0,
-            "atmonr_l2_persist": 0}
+            "atmonr_l2_persist": 0, "atmonr_ray_extent": 2}
 
 
 class CallStats:

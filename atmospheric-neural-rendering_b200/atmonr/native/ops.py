@@ -116,6 +116,41 @@ def get_rays(lat, lon, alt, thetav, phiv, ray_origin_height, tol: float = 10.0, 
     return origin, direction, length
 
 
+def filter_rays(ray_origin, ray_dir, ray_rad):
+    """wgs_84.py:293-313: torch.bool mask of the rays without a NaN in origin, direction or radiance."""
+    ray_origin, ray_dir, ray_rad = (_c(t, _f32) for t in (ray_origin, ray_dir, ray_rad))
+    n = ray_rad.numel()
+    if ray_origin.shape != (n, 3) or ray_dir.shape != (n, 3):
+        raise ValueError("ray_origin and ray_dir must be (n, 3) for n radiances")
+    valid = torch.empty((n,), device=ray_rad.device, dtype=torch.bool)
+    L.call("atmonr_filter_rays", L.ptr(ray_origin), L.ptr(ray_dir), L.ptr(ray_rad), n, L.ptr(valid), L.stream())
+    return valid
+
+
+RAY_EXTENT_WORK_BYTES = 37888   # ATMONR_RAY_EXTENT_WORK_BYTES of include/atmonr_b200.h
+
+
+def normalize_rays(ray_origin, ray_dir, ray_len):
+    """wgs_84.py:316-339: (origins normalised into [-1, 1]^3 float32, scale as a Python float, offset
+    as a float64[3] device tensor). The bounding box and the normalisation are kernels; the two lines
+    between them (:336-337, six numbers) are the reference's own float64 expressions."""
+    ray_origin, ray_dir, ray_len = (_c(t, _f32) for t in (ray_origin, ray_dir, ray_len))
+    n = ray_len.numel()
+    if ray_origin.shape != (n, 3) or ray_dir.shape != (n, 3):
+        raise ValueError("ray_origin and ray_dir must be (n, 3) for n lengths")
+    dev = ray_origin.device
+    hi_lo = torch.empty((6,), device=dev, dtype=_f32)
+    work = torch.empty((RAY_EXTENT_WORK_BYTES // 4,), device=dev, dtype=_f32)
+    L.call("atmonr_ray_extent", L.ptr(ray_origin), L.ptr(ray_dir), L.ptr(ray_len), n, L.ptr(hi_lo), L.ptr(work),
+           L.stream())
+    hi, lo = hi_lo[:3].double(), hi_lo[3:].double()
+    scale = ((hi - lo).max() / 2).item()
+    offset = ((hi + lo) / 2).contiguous()
+    out = torch.empty_like(ray_origin)
+    L.call("atmonr_normalize_origins", L.ptr(ray_origin), n, L.ptr(offset), float(scale), L.ptr(out), L.stream())
+    return out, scale, offset
+
+
 def gather_batch(tables: dict, index: torch.Tensor) -> dict:
     """harp2.py:392-420: the per-ray tables {origin, dir, alt, rad, len, idx, irgb_idx} gathered at
     `index` (int64, negative values count from the end) in one launch. An out-of-range index raises

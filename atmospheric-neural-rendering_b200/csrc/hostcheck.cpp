@@ -102,6 +102,28 @@ int hc_get_rays(const float* lat, const float* lon, const float* alt, const floa
   return iters;
 }
 
+// wgs_84.py:293-339 with the per-ray functions of csrc/rays.cu (k_filter_rays, k_ray_extent_*, k_normalize_origins)
+void hc_filter_rays(const float* origin, const float* dir, const float* rad, int64_t n, uint8_t* valid) {
+  for (int64_t i = 0; i < n; ++i) valid[i] = atm::ray_is_valid(origin + 3 * i, dir + 3 * i, rad[i]) ? 1 : 0;
+}
+
+void hc_ray_extent(const float* origin, const float* dir, const float* len, int64_t n, float* hi_lo) {
+  // two partial boxes merged at the end, like the kernel's partial / final passes
+  atm::RayExtent a, b;
+  atm::extent_init(a), atm::extent_init(b);
+  for (int64_t i = 0; i < n; ++i) atm::extent_add_ray((i & 1) ? b : a, origin + 3 * i, dir + 3 * i, len[i]);
+  atm::extent_merge(a, b);
+  for (int k = 0; k < 3; ++k) {
+    const bool bad = (a.nan_axes >> k) & 1u;
+    hi_lo[k] = bad ? NAN : a.hi[k];
+    hi_lo[3 + k] = bad ? NAN : a.lo[k];
+  }
+}
+
+void hc_normalize_origins(const float* origin, int64_t n, const double* offset, double scale, float* out) {
+  for (int64_t i = 0; i < 3 * n; ++i) out[i] = atm::normalize_coord(origin[i], offset[i % 3], scale);
+}
+
 // csrc/nerf_points.cu, per sample on the host: rows [pos | dir] and preprocessed points; then dL/dz
 void hc_nerf_encode(const atmonr_frame_t* f, const float* o, const float* d, const float* z, int64_t B, int N,
                     const int32_t* pos_freqs, int dir_freqs, float* x, int ldx, float* pts_n) {

@@ -93,4 +93,56 @@ ATM_HD void ray_outputs(const RaySetup& r, double len, float* origin, float* dir
   dir[0] = (float)r.dx, dir[1] = (float)r.dy, dir[2] = (float)r.dz;
 }
 
+// ---- wgs_84.py:293-313 filter_rays / :316-339 normalize_rays -----------------
+// A ray is kept when its origin, its direction and its radiance hold no NaN.
+ATM_HD bool ray_is_valid(const float* origin, const float* dir, float rad) {
+  bool bad = rad != rad;
+  for (int k = 0; k < 3; ++k) bad = bad || origin[k] != origin[k] || dir[k] != dir[k];
+  return !bad;
+}
+
+// lower end of the ray, `origin + dir * len` in float32: product and sum round separately (the
+// build disables contraction), as the two eager torch kernels of wgs_84.py:333 do
+ATM_HD float ray_end_coord(float origin, float dir, float len) { return origin + dir * len; }
+
+// running bounding box of the points of wgs_84.py:333-335; a NaN coordinate makes torch's max/min
+// NaN, so NaNs are counted per axis instead of being dropped by the comparisons
+struct RayExtent {
+  float hi[3], lo[3];
+  uint32_t nan_axes;
+};
+ATM_HD void extent_init(RayExtent& e) {
+  for (int k = 0; k < 3; ++k) e.hi[k] = -INFINITY, e.lo[k] = INFINITY;
+  e.nan_axes = 0u;
+}
+ATM_HD void extent_add(RayExtent& e, int k, float v) {
+  if (v != v) {
+    e.nan_axes |= 1u << k;
+  } else {
+    e.hi[k] = v > e.hi[k] ? v : e.hi[k];
+    e.lo[k] = v < e.lo[k] ? v : e.lo[k];
+  }
+}
+ATM_HD void extent_add_ray(RayExtent& e, const float* origin, const float* dir, float len) {
+  for (int k = 0; k < 3; ++k) {
+    extent_add(e, k, origin[k]);
+    extent_add(e, k, ray_end_coord(origin[k], dir[k], len));
+  }
+}
+ATM_HD void extent_merge(RayExtent& e, const RayExtent& o) {
+  for (int k = 0; k < 3; ++k) {
+    e.hi[k] = o.hi[k] > e.hi[k] ? o.hi[k] : e.hi[k];
+    e.lo[k] = o.lo[k] < e.lo[k] ? o.lo[k] : e.lo[k];
+  }
+  e.nan_axes |= o.nan_axes;
+}
+
+// wgs_84.py:338 `clamp((origin - offset) / scale, -1, 1).float()`: float32 origin minus float64 offset,
+// float64 quotient; a NaN fails both comparisons and stays NaN, like torch.clamp
+ATM_HD float normalize_coord(float origin, double offset, double scale) {
+  double v = ((double)origin - offset) / scale;
+  v = v < -1.0 ? -1.0 : (v > 1.0 ? 1.0 : v);
+  return (float)v;
+}
+
 }  // namespace atm

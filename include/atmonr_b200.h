@@ -89,6 +89,27 @@ int atmonr_get_rays(const float* lat, const float* lon, const float* alt, const 
                     int max_iters, float* origin, float* dir, float* len, void* work,
                     int* n_iters_host, void* stream);
 
+/* ---- geospatial/wgs_84.py:293-313 filter_rays (once per run) ----------------------------------
+ * valid[i] = 1 when none of origin[i] (3), dir[i] (3), rad[i] is NaN, else 0; `valid` is one byte per
+ * ray (the storage of a torch.bool tensor). n = 0 is a no-op. */
+int atmonr_filter_rays(const float* origin, const float* dir, const float* rad, int64_t n,
+                       uint8_t* valid, void* stream);
+
+/* ---- geospatial/wgs_84.py:316-339 normalize_rays (once per run) --------------------------------
+ * First half (:333-335): the bounding box of the ray origins and of the rays' lower ends
+ * `origin + dir * len` (float32, product and sum rounded separately, as the eager reference does).
+ * hi_lo (device, 6 floats) receives max x,y,z then min x,y,z; an axis that holds a NaN gives NaN like
+ * torch.max / torch.min. n must be > 0. work: ATMONR_RAY_EXTENT_WORK_BYTES of device scratch.
+ * The caller forms `scale = max(hi - lo) / 2` and `offset = (hi + lo) / 2` in float64 (:336-337: a
+ * Python float and a float64[3] device tensor), then calls the second half (:338):
+ * out[i][k] = float(clamp((double(origin[i][k]) - offset[k]) / scale, -1, 1)); offset is a DEVICE
+ * pointer to three doubles. */
+#define ATMONR_RAY_EXTENT_WORK_BYTES 37888
+int atmonr_ray_extent(const float* origin, const float* dir, const float* len, int64_t n,
+                      float* hi_lo, void* work, void* stream);
+int atmonr_normalize_origins(const float* origin, int64_t n, const double* offset, double scale,
+                             float* out, void* stream);
+
 /* ---- datasets/harp2.py:392-420 __getitem__ / __getbatch__ (every step) ----------------------
  * The seven advanced-index gathers of a batch in one launch. Tables of R rays: origin (R,3),
  * dir (R,3), alt (R), rad (R), len (R) float32, ray_idx (R) int32, band (R) int64 (irgb_idx);

@@ -295,6 +295,57 @@ def test_host_build_of_ray_setup_matches_oracle_chunk_semantics():
     assert np.abs(ln0 - want0).max() <= 2e-2
 
 
+def _hc_normalize_rays(o, d, ln):
+    """wgs_84.py:316-339 the way atmonr.native.ops.normalize_rays runs it: box (native code), the two
+    float64 lines of :336-337 (torch), normalisation (native code)."""
+    hc = _hc()
+    o, d, ln = (np.ascontiguousarray(x, dtype=np.float32) for x in (o, d, ln))
+    n = ln.shape[0]
+    hi_lo = np.zeros(6, np.float32)
+    hc.hc_ray_extent(_p(o), _p(d), _p(ln), C.c_int64(n), _p(hi_lo))
+    hi, lo = torch.from_numpy(hi_lo[:3]).double(), torch.from_numpy(hi_lo[3:]).double()
+    scale = ((hi - lo).max() / 2).item()
+    offset = ((hi + lo) / 2).contiguous()
+    out = np.zeros_like(o)
+    hc.hc_normalize_origins(_p(o), C.c_int64(n), _p(offset.numpy()), C.c_double(scale), _p(out))
+    return out, scale, offset, hi_lo
+
+
+def test_host_build_of_filter_and_normalize_rays_matches_reference_vectors():
+    """SURVEY 8a row a2 (wgs_84.py:293-339): the per-ray functions of k_filter_rays / k_ray_extent_* /
+    k_normalize_origins, compiled for the host, against the reference's own normalize_rays outputs
+    (golden) and the oracle: mask, scale, offset and normalised origins BIT FOR BIT."""
+    G = np.load(os.path.join(ROOT, "tests", "golden", "reference_vectors.npz"))
+    out, scale, offset, _ = _hc_normalize_rays(G["rays_origin"], G["rays_dir"], G["rays_len"])
+    assert scale == float(G["rays_scale"]) and np.array_equal(offset.numpy(), G["rays_offset"])
+    assert np.array_equal(out, G["rays_origin_norm"])
+    # a HARP2-shaped table with NaN pixels, against the oracle
+    rng = np.random.default_rng(11)
+    n = 5000
+    o = (rng.standard_normal((n, 3)) * 2e5 + np.array([1.3e6, -5.0e6, 3.6e6])).astype(np.float32)
+    d = rng.standard_normal((n, 3)).astype(np.float32)
+    d /= np.linalg.norm(d, axis=1, keepdims=True)
+    ln = (2e4 + 2e4 * rng.random(n)).astype(np.float32)
+    rad = rng.random(n).astype(np.float32)
+    o[7, 1] = np.nan; d[90, 2] = np.nan; rad[300] = np.nan; o[4000] = np.nan; rad[4000] = np.nan
+    valid = np.zeros(n, np.uint8)
+    _hc().hc_filter_rays(_p(o), _p(d), _p(rad), C.c_int64(n), _p(valid))
+    want_valid = geodesy.valid_ray_mask(*map(torch.from_numpy, (o, d, rad))).numpy()
+    assert np.array_equal(valid.astype(bool), want_valid) and valid.sum() == n - 4
+    keep = valid.astype(bool)
+    out, scale, offset, hi_lo = _hc_normalize_rays(o[keep], d[keep], ln[keep])
+    want, want_scale, want_offset = geodesy.normalize_rays(*map(torch.from_numpy, (o[keep], d[keep], ln[keep])))
+    assert scale == want_scale and torch.equal(offset, want_offset) and np.array_equal(out, want.numpy())
+    assert out.min() >= -1 and out.max() <= 1
+    # an unfiltered NaN poisons its axis like torch.max / torch.min; the other axes keep their box
+    _, _, _, hi_lo_nan = _hc_normalize_rays(o, d, ln)
+    assert np.isnan(hi_lo_nan[[1, 4]]).all()          # y: o[7,1]; x and z hold NaN as well (o[4000], d[90,2])
+    assert np.isnan(hi_lo_nan).all()
+    o2 = o[keep].copy(); o2[5, 2] = np.nan
+    _, _, _, hl = _hc_normalize_rays(o2, d[keep], ln[keep])
+    assert np.isnan(hl[[2, 5]]).all() and np.array_equal(hl[[0, 1, 3, 4]], hi_lo[[0, 1, 3, 4]])
+
+
 # ---------------------------------------------------------------- dense layer on tcgen05 (csrc/linear_tc.cu)
 def _bf16_round(a):
     """float32 -> nearest-even bfloat16, returned as float32 (numpy has no bfloat16)."""

@@ -1,6 +1,7 @@
 """GPU parity of the dataset-side kernels (csrc/rays.cu): atmonr_get_rays against the oracle's
 build_rays (pinned bit for bit to the reference's get_rays) and the host build of the same code,
-atmonr_gather_batch against torch indexing (bit-exact). The file sorts last on purpose: these two
+atmonr_filter_rays / atmonr_ray_extent / atmonr_normalize_origins against the reference's expressions
+(bit-exact), atmonr_gather_batch against torch indexing (bit-exact). The file sorts last on purpose: these two
 entry points were opt-in (ATMONR_NATIVE_RAYS / ATMONR_NATIVE_GATHER) until they had been green on
 a B200 once."""
 
@@ -94,6 +95,56 @@ def test_get_rays_dispatch_builds_the_same_dataset(monkeypatch):
     # one float32 ulp of an ECEF coordinate (0.5 m) moves the bounding box by 2e-6 of its size
     assert abs(base.scale - nat.scale) <= 1e-5 * base.scale
     assert float((base.ray_origin_norm - nat.ray_origin_norm).abs().max()) <= 3e-5
+
+
+def test_filter_and_normalize_rays_are_bit_exact():
+    """SURVEY 8a row a2 (wgs_84.py:293-339): atmonr_filter_rays / atmonr_ray_extent /
+    atmonr_normalize_origins against the reference's torch expressions evaluated on the same device
+    tensors and against the oracle on the CPU: mask, scale (a Python float), offset (float64[3]) and the
+    normalised origins are EQUAL, for a table larger than one pass of the reduction grid."""
+    import atmonr.geospatial.wgs_84 as W
+    from atmonr.native import ops
+    for n, seed in ((1, 0), (257, 1), (700_001, 2)):
+        g = torch.Generator().manual_seed(seed)
+        o = torch.randn(n, 3, generator=g) * 2e5 + torch.tensor([1.3e6, -5.0e6, 3.6e6])
+        d = torch.nn.functional.normalize(torch.randn(n, 3, generator=g), dim=1)
+        ln = 2e4 + 2e4 * torch.rand(n, generator=g)
+        rad = torch.rand(n, generator=g)
+        if n > 100:
+            o[7, 1] = float("nan"); d[90, 2] = float("nan"); rad[30] = float("nan"); o[n - 1] = float("nan")
+        oc, dc, lc, rc = (t.cuda() for t in (o, d, ln, rad))
+        valid = ops.filter_rays(oc, dc, rc)
+        assert valid.dtype == torch.bool and torch.equal(valid.cpu(), geodesy.valid_ray_mask(o, d, rad))
+        assert int(valid.sum()) == (n - 4 if n > 100 else n)
+        ok, dk, lk = oc[valid], dc[valid].contiguous(), lc[valid]
+        got, scale, offset = ops.normalize_rays(ok, dk, lk)
+        # the reference's expressions on the device (torch reductions are exact for max / min)
+        ends = torch.cat([ok, ok + dk * lk[:, None]], dim=0)
+        hi, lo = ends.max(dim=0)[0].double(), ends.min(dim=0)[0].double()
+        want_scale, want_offset = ((hi - lo).max() / 2).item(), (hi + lo) / 2
+        want = torch.clamp((ok - want_offset) / want_scale, -1, 1).float()
+        assert isinstance(scale, float) and scale == want_scale
+        assert offset.dtype == torch.float64 and offset.is_cuda and torch.equal(offset, want_offset)
+        # (torch's CUDA division by a Python scalar multiplies by the float64 reciprocal, its CPU division
+        # divides: the two float64 quotients can differ in the last bit, which survives the rounding to
+        # float32 for about one value in 2^28. The kernel divides, like the CPU run the oracle is pinned to.)
+        assert got.dtype == torch.float32 and float((got - want).abs().max()) <= 1.2e-7
+        assert float((got != want).float().mean()) <= 1e-6
+        w_cpu, s_cpu, off_cpu = geodesy.normalize_rays(ok.cpu(), dk.cpu(), lk.cpu())
+        assert s_cpu == scale and torch.equal(off_cpu, offset.cpu()) and torch.equal(w_cpu, got.cpu())
+        # the dispatching functions of the package take the kernels for CUDA tensors
+        got2, scale2, offset2 = W.normalize_rays(ok, dk, lk)
+        assert torch.equal(got2, got) and scale2 == scale and torch.equal(offset2, offset)
+        assert torch.equal(W.filter_rays(oc, dc, rc), valid)
+    # an unfiltered NaN poisons its axis of the box (torch.max / torch.min), scale and every origin with it
+    got, scale, offset = ops.normalize_rays(oc, dc, lc)
+    assert scale != scale and bool(offset.isnan().all()) and bool(got.isnan().all())
+    # empty tables: the mask of nothing is empty, the box of nothing is an error (torch.max raises as well)
+    e3, e1 = torch.empty(0, 3, device="cuda"), torch.empty(0, device="cuda")
+    assert ops.filter_rays(e3, e3, e1).shape == (0,)
+    from atmonr.native.lib import NativeLibraryError
+    with pytest.raises(NativeLibraryError):
+        ops.normalize_rays(e3, e3, e1)
 
 
 def test_gather_batch_is_bit_exact(monkeypatch):
