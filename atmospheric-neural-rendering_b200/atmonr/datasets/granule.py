@@ -41,6 +41,7 @@ class SyntheticGranule:
         v = len(wl)
         # image rows run south -> north in the file (HARP2Dataset flips them so north is up)
         lat0, lon0 = float(opts["lat0"]), float(opts["lon0"])
+        self.lat0, self.lon0, self.seed = lat0, lon0, int(opts["seed"])
         lat = np.linspace(lat0, lat0 + 5.0, h, dtype=np.float32)[:, None] + np.zeros((1, w), np.float32)
         lon = np.linspace(lon0, lon0 + 5.0, w, dtype=np.float32)[None, :] + np.zeros((h, 1), np.float32)
         lon = np.where(lon > 180.0, lon - 360.0, lon).astype(np.float32)
@@ -62,6 +63,40 @@ class SyntheticGranule:
 
     def field(self, name: str) -> np.ndarray:
         return self._fields[name]
+
+    # ---- stand-ins for the two auxiliary products the extract layouts read (datasets/harp2_extract.py) ----
+    def l1c_geolocation(self, step_km: float = 5.0) -> dict[str, np.ndarray]:
+        """What `HARP2L1CExtractDataset` reads from the granule's L1C file (harp2_extract.py:149-166): the
+        5 km L1C bin grid of the scene, float32 (bins_along_track, bins_across_track) latitude, longitude
+        and height, rows south -> north like the file (the reader flips them), fill values as NaN (the two
+        southern corner bins, as in swath-shaped L1C grids)."""
+        step = step_km / 111.0
+        n_lat, n_lon = int(5.0 / step), int(5.0 / (step / np.cos(np.deg2rad(self.lat0 + 2.5))))
+        lat = (self.lat0 + (np.arange(n_lat, dtype=np.float32) + 0.5) * np.float32(5.0 / n_lat))[:, None] + np.zeros((1, n_lon), np.float32)
+        lon = (self.lon0 + (np.arange(n_lon, dtype=np.float32) + 0.5) * np.float32(5.0 / n_lon))[None, :] + np.zeros((n_lat, 1), np.float32)
+        lon = np.where(lon > 180.0, lon - 360.0, lon).astype(np.float32)
+        rng = np.random.default_rng(self.seed + 101)
+        height = (rng.uniform(0.0, 40.0, (n_lat, n_lon))).astype(np.float32)
+        out = {"latitude": lat.astype(np.float32).copy(), "longitude": lon.copy(), "height": height}
+        for a in out.values():
+            a[0, 0] = a[0, -1] = np.nan
+        return out
+
+    def earthcare_track(self, n_along: int = 160, n_height: int = 90) -> dict[str, np.ndarray]:
+        """What `HARP2EarthCAREExtractDataset` reads from an ATLID `ATL_EBD_2A` file
+        (harp2_extract.py:626-650): a ground track crossing the scene from its south-west to its
+        north-east corner (float64 latitude / longitude per profile) and the joint-standard-grid height of
+        every range bin, top first, from above the shell down to below the ellipsoid, slightly different
+        from profile to profile (so the reference's all-profiles altitude mask has something to drop)."""
+        t = np.linspace(-0.1, 1.1, n_along)
+        lat = self.lat0 + 5.0 * t
+        lon = self.lon0 + 5.0 * t
+        lon = np.where(lon > 180.0, lon - 360.0, lon)
+        rng = np.random.default_rng(self.seed + 202)
+        base = np.linspace(24000.0, -600.0, n_height)[None, :]
+        height = base + rng.uniform(-40.0, 40.0, (n_along, 1)) + np.zeros((1, n_height))
+        return {"latitude": lat.astype(np.float64), "longitude": lon.astype(np.float64),
+                "height": height.astype(np.float64), "file_type": "ATL_EBD_2A"}
 
 
 class NetCDFGranule:

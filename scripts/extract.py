@@ -1,8 +1,7 @@
 """Query a trained pipeline for the extinction coefficient on a voxel grid.
 
-Same command line as the reference's scripts/extract.py. Only --coord-mode voxelgrid is built
-(the L1C / EarthCARE / globalgrid layouts are visualisation modes outside this build's scope and
-raise NotImplementedError). Under torchrun the voxel columns are split contiguously over the
+Same command line as the reference's scripts/extract.py, all four coordinate modes (voxelgrid, l1c,
+globalgrid, earthcare: atmonr/datasets/harp2_extract.py). Under torchrun the voxel columns are split contiguously over the
 ranks with no communication; rank 0 gathers and writes the file.
 """
 
@@ -22,14 +21,14 @@ from atmonr.geospatial.spherical import EARTH_RADIUS
 from atmonr.pipelines.factory import get_pipeline
 
 
-def _comma_separated(text: str) -> list[float]:
-    return [float(t) for t in text.split(",")]
+def _comma_separated(text: str) -> list[int]:
+    return [int(t) for t in text.split(",")]
 
 
 def parse_args() -> argparse.Namespace:
     ap = argparse.ArgumentParser()
     ap.add_argument("--exp-name", type=str, required=True)
-    ap.add_argument("--coord-mode", type=str, required=True, help="voxelgrid (others are out of scope in this build)")
+    ap.add_argument("--coord-mode", type=str, required=True, help="l1c, voxelgrid, globalgrid or earthcare")
     ap.add_argument("--extract-filename", type=str, required=True)
     ap.add_argument("--batch-size", type=int, default=32768, help="voxel columns per batch")
     ap.add_argument("--min-alt", type=float)
@@ -70,7 +69,10 @@ def main() -> None:
     num_bands = BANDS[config["dataset"]["type"]] if config["pipeline"].get("multi_band_extinction", False) else 1
     n_pts = extract_dataset.idx.shape[0]
     sigma = torch.zeros((n_pts, num_bands), device=device)
-    # contiguous shard of voxel columns per rank (columns = groups of n_alt points)
+    # contiguous shard of voxel columns per rank (columns = groups of n_alt points; the earthcare and
+    # globalgrid tables are not column-shaped and are sharded point by point)
+    if args.coord_mode.lower() not in ("l1c", "voxelgrid"):
+        n_alt = 1
     n_cols = n_pts // n_alt
     cols = dist.shard_slice(n_cols, rank, world)
     lo, hi = cols.start * n_alt, cols.stop * n_alt

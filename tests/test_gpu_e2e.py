@@ -48,7 +48,27 @@ def test_train_and_extract_scripts(tmp_path):
     z = np.load(out / "ext.npz")
     ext = z["extinction_coefficient"]
     assert ext.ndim == 4 and ext.shape[2] == 21 and ext.shape[3] == 1 and np.isfinite(ext).all() and (ext >= 0).all()
-    r = run(os.path.join(ROOT, "scripts", "extract.py"), "--exp-name", "t0", "--coord-mode", "globalgrid", "--extract-filename", "x.nc")
+    # the other coordinate modes of the reference's script, on the granule's stand-in products
+    r = run(os.path.join(ROOT, "scripts", "extract.py"), "--exp-name", "t0", "--coord-mode", "earthcare",
+            "--extract-filename", "curtain.nc", "--earthcare-filename", "synthetic", "--earthcare-range", "10,150")
+    assert r.returncode == 0, r.stderr[-2000:]
+    cur = np.load(out / "curtain.npz")
+    ext = cur["extinction_coefficient"]
+    assert ext.shape[0] == 140 and ext.shape[:2] == cur["height"].shape and np.isfinite(ext).all() and (ext >= 0).all()
+    r = run(os.path.join(ROOT, "scripts", "extract.py"), "--exp-name", "t0", "--coord-mode", "L1C",
+            "--extract-filename", "l1c.nc", "--alt-step", "5000", "--batch-size", "4096")
+    assert r.returncode == 0, r.stderr[-2000:]
+    l1c = np.load(out / "l1c.npz")
+    ext, lat = l1c["extinction_coefficient"], l1c["latitude"]
+    assert ext.shape == (*lat.shape, 5, 1) and np.isnan(lat).sum() == 2            # the two fill bins of the L1C grid
+    assert np.isfinite(ext[~np.isnan(lat)]).all() and (ext[~np.isnan(lat)] >= 0).all()
+    r = run(os.path.join(ROOT, "scripts", "extract.py"), "--exp-name", "t0", "--coord-mode", "globalgrid",
+            "--extract-filename", "grid.vdb", "--grid-res", "0.4")
+    assert r.returncode == 0, r.stderr[-2000:]
+    vox, sig = np.load(out / "voxels.npy"), np.load(out / "sigma.npy")             # the reference's fallback without OpenVDB
+    assert vox.ndim == 2 and vox.shape[1] == 3 and sig.shape == (vox.shape[0], 1) and vox.shape[0] > 100
+    assert np.isfinite(sig).all() and (sig >= 0).all()
+    r = run(os.path.join(ROOT, "scripts", "extract.py"), "--exp-name", "t0", "--coord-mode", "octree", "--extract-filename", "x.nc")
     assert r.returncode != 0 and "NotImplementedError" in r.stderr
 
 

@@ -8,6 +8,7 @@ import os
 import subprocess
 import sys
 
+import numpy as np
 import pytest
 import torch
 
@@ -635,6 +636,195 @@ def test_vincenty_voxel_grid_matches_the_reference_layout(tmp_path, spec, kw):
     xyz = grid.xyz.view(*grid.shp, 3)[:, :, 0]
     step_ew = (xyz[:, 1:] - xyz[:, :-1]).norm(dim=-1)
     assert float((step_ew / kw["horizontal_step"] - 1).abs().max()) < 0.25
+
+
+# ------------------------------------------------------------------------------------------
+# the other three coordinate modes of scripts/extract.py: L1C, EarthCARE, global grid
+# ------------------------------------------------------------------------------------------
+_L1B_NAME = "PACE_HARP2.20240101T000000.L1B.V3.nc"          # the L1C class parses this (harp2_extract.py:141)
+LAYOUT_CHILD = (DATASET_CHILD.split("idx = torch.arange(0, len(ds), 97)")[0]
+                .replace("fake.nc", _L1B_NAME)
+                .replace("    def __init__(self, path): pass\n", "    def __init__(self, path): self.path = str(path)\n")
+                .replace("        group, name = path.split(\"/\")\n",
+                         "        group, name = path.split(\"/\")\n"
+                         "        if \"L1C\" in self.path: return Var(gran.l1c_geolocation()[name])\n")) + r"""
+import h5py
+from atmonr.datasets import harp2_extract as ref_ext
+mode, kw = sys.argv[7], json.loads(sys.argv[8])
+out = {}
+if mode == "l1c":
+    Path("data/HARP2_L1C").mkdir(parents=True)
+    Path("data/HARP2_L1C/PACE_HARP2.20240101T000000.L1C.V3.5km.nc").touch()      # present: no download
+    grid = ref_ext.HARP2L1CExtractDataset(ds, **kw)
+    out = {"shp": tuple(grid.shp), "lat": grid.lat, "lon": grid.lon, "height": grid.height, "sample_alt": grid.sample_alt}
+elif mode == "earthcare":
+    track = gran.earthcare_track()
+    class H5Var:
+        def __init__(self, a): self.a = a
+        def __getitem__(self, k): return self.a[k] if not isinstance(self.a, bytes) else self.a
+    h5py.Dataset = H5Var
+    table = {"HeaderData/FixedProductHeader/File_Type": H5Var(kw.pop("file_type", track["file_type"]).encode()),
+             "ScienceData/height": H5Var(track["height"]), "ScienceData/latitude": H5Var(track["latitude"]),
+             "ScienceData/longitude": H5Var(track["longitude"])}
+    h5py.File = lambda path: table
+    try:
+        grid = ref_ext.HARP2EarthCAREExtractDataset(ds, **kw)
+        out = {"shp": tuple(grid.shp), "lat": grid.lat, "lon": grid.lon, "alt": grid.alt}
+    except NotImplementedError as err:
+        torch.save({"error": str(err)}, sys.argv[6]); sys.exit(0)
+else:
+    # the reference's constructor cannot finish (harp2_extract.py:896 chains two tensor comparisons):
+    # stop it at the altitude computation that precedes that line and keep what it has built
+    class Reached(Exception): pass
+    def stop(x, y, z): raise Reached
+    ref_ext.cartesian_to_horizontal = stop
+    ref_ext.tqdm = lambda it, **k: it
+    grid = object.__new__(ref_ext.HARP2GlobalGridExtractDataset)
+    try:
+        ref_ext.HARP2GlobalGridExtractDataset.__init__(grid, ds, **kw)
+        raise SystemExit("the reference's global grid finished: update this test")
+    except Reached:
+        pass
+    out = {"voxels": grid.voxels}
+    grid.idx = torch.arange(grid.xyz.shape[0], dtype=torch.int32)
+out.update(xyz=grid.xyz, idx=grid.idx, batch=grid.__getbatch__(torch.arange(0, 40, 7)))
+torch.save(out, sys.argv[6])
+"""
+
+
+def _reference_layout(tmp_path, spec, mode, kw):
+    cfg = json.load(open(os.path.join(ROOT, "configs", "instant_ngp.json")))["dataset"]
+    out = str(tmp_path / "ref_layout.pt")
+    r = subprocess.run([sys.executable, "-c", LAYOUT_CHILD, os.path.join(ROOT, "tests", "golden"),
+                        os.path.join(ROOT, "atmospheric-neural-rendering_b200", "atmonr", "datasets", "granule.py"),
+                        spec, json.dumps(cfg), str(tmp_path), out, mode, json.dumps(kw)], capture_output=True, text=True, timeout=600)
+    assert r.returncode == 0, r.stderr[-3000:]
+    from atmonr.datasets.harp2 import HARP2Dataset
+    return torch.load(out, weights_only=False), HARP2Dataset(dict(cfg), spec, device=torch.device("cpu"))
+
+
+@pytest.mark.parametrize("spec,kw", [
+    ("synthetic:H=10,W=9,seed=4", {"alt_step": 2500.0}),
+    ("synthetic:H=10,W=9,seed=4,lat0=-62,lon0=177.5", {"alt_step": 1000.0, "min_alt": 500.0, "max_alt": 9000.0}),
+])
+def test_l1c_layout_matches_the_reference_class(tmp_path, spec, kw):
+    """HARP2L1CExtractDataset (harp2_extract.py:115-186) fed the same L1C geolocation through a stand-in
+    netCDF4.Dataset: the point table, the index table and the per-bin fields bit for bit (fill values as
+    NaN, north first)."""
+    from atmonr.datasets.factory import get_extract_dataset
+    ref, ds = _reference_layout(tmp_path, spec, "l1c", kw)
+    grid = get_extract_dataset("L1C", ds, horizontal_step=3000.0, scale=1.0, **kw)     # the script passes every flag
+    assert tuple(grid.shp) == ref["shp"] and torch.equal(grid.sample_alt, ref["sample_alt"])
+    assert grid.xyz.dtype == torch.float64 and grid.xyz.shape == ref["xyz"].shape
+    for name in ("lat", "lon", "height", "xyz"):
+        got, want = getattr(grid, name), ref[name]
+        assert got.dtype == want.dtype and torch.equal(got.isnan(), want.isnan()), name
+        assert torch.equal(got.nan_to_num(), want.nan_to_num()), name
+    assert bool(grid.xyz.isnan().any()) and float(grid.lat[0, 5, 0]) > float(grid.lat[-1, 5, 0])   # fill bins; north first
+    assert torch.equal(grid.idx, ref["idx"])
+    b = grid.__getbatch__(torch.arange(0, 40, 7))
+    assert set(b) == set(ref["batch"]) and torch.equal(b["idx"], ref["batch"]["idx"])
+    # the voxel grid's writer serves this layout as well
+    sigma = torch.rand(grid.xyz.shape[0], 1)
+    grid.dump(tmp_path / "l1c_extract.nc", sigma)
+    stored = np.load(tmp_path / "l1c_extract.npz")
+    assert stored["extinction_coefficient"].shape == (*ref["shp"], grid.sample_alt.shape[0], 1)
+    assert np.array_equal(stored["height"], ref["height"].numpy(), equal_nan=True) and tuple(grid.shp) == ref["shp"]
+
+
+@pytest.mark.parametrize("spec,kw", [
+    ("synthetic:H=10,W=9,seed=4", {"earthcare_filename": "synthetic", "earthcare_range": None}),
+    ("synthetic:H=10,W=9,seed=4,lat0=-62,lon0=177.5", {"earthcare_filename": "synthetic", "earthcare_range": [12, 131]}),
+])
+def test_earthcare_layout_matches_the_reference_class(tmp_path, spec, kw):
+    """HARP2EarthCAREExtractDataset (harp2_extract.py:599-675) fed the same ATLID track through a stand-in
+    h5py.File: profile range, the all-profiles altitude mask, the curtain's point table: bit for bit."""
+    from atmonr.datasets.factory import get_extract_dataset
+    ref, ds = _reference_layout(tmp_path, spec, "earthcare", kw)
+    grid = get_extract_dataset("earthcare", ds, alt_step=250.0, **kw)
+    assert tuple(grid.shp) == ref["shp"] and grid.shp[1] < 90          # range bins outside the shell were dropped
+    for name in ("lat", "lon", "alt"):
+        assert np.array_equal(getattr(grid, name), ref[name]), name
+    assert grid.xyz.dtype == ref["xyz"].dtype == torch.float64 and torch.equal(grid.xyz, ref["xyz"])
+    assert torch.equal(grid.idx, ref["idx"])
+    b = grid.__getbatch__(torch.arange(0, 40, 7))
+    assert torch.equal(b["xyz"], ref["batch"]["xyz"]) and torch.equal(b["idx"], ref["batch"]["idx"])
+    grid.dump(tmp_path / "curtain.nc", torch.rand(grid.xyz.shape[0], 4))
+    stored = np.load(tmp_path / "curtain.npz")
+    assert stored["extinction_coefficient"].shape == (*ref["shp"], 4) and stored["height"].shape == ref["shp"]
+    assert np.array_equal(stored["longitude"], ref["lon"][:, 0]) and float(stored["attr_neural_rendering_scene_scale"]) == ds.scale
+    with pytest.raises(AssertionError):
+        get_extract_dataset("earthcare", ds, earthcare_filename="synthetic", earthcare_range=[5, 5])
+
+
+def test_earthcare_layout_rejects_other_products_like_the_reference(tmp_path, monkeypatch):
+    from atmonr.datasets import granule
+    from atmonr.datasets.factory import get_extract_dataset
+    spec = "synthetic:H=10,W=9,seed=4"
+    ref, ds = _reference_layout(tmp_path, spec, "earthcare", {"earthcare_filename": "synthetic", "earthcare_range": None, "file_type": "ATL_NOM_1B"})
+    track = granule.SyntheticGranule.earthcare_track
+    monkeypatch.setattr(granule.SyntheticGranule, "earthcare_track", lambda self: {**track(self), "file_type": "ATL_NOM_1B"})
+    with pytest.raises(NotImplementedError) as err:
+        get_extract_dataset("earthcare", ds, earthcare_filename="synthetic", earthcare_range=None)
+    assert str(err.value) == ref["error"]
+    # a product file: the .npz stand-in for the HDF5 file, same variable paths
+    monkeypatch.chdir(tmp_path)
+    os.makedirs("data/EarthCARE", exist_ok=True)
+    t = track(ds.granule)
+    np.savez(os.path.join("data", "EarthCARE", "ECA_EXAE_ATL_EBD_2A_x.npz"), **{
+        "HeaderData/FixedProductHeader/File_Type": np.bytes_(b"ATL_EBD_2A"), "ScienceData/height": t["height"],
+        "ScienceData/latitude": t["latitude"], "ScienceData/longitude": t["longitude"]})
+    monkeypatch.setattr(granule.SyntheticGranule, "earthcare_track", track)
+    from_file = get_extract_dataset("earthcare", ds, earthcare_filename="ECA_EXAE_ATL_EBD_2A_x.h5", earthcare_range=None)
+    synthetic = get_extract_dataset("earthcare", ds, earthcare_filename="synthetic", earthcare_range=None)
+    assert torch.equal(from_file.xyz, synthetic.xyz)
+
+
+@pytest.mark.parametrize("spec,kw", [
+    ("synthetic:H=10,W=9,seed=4", {"scale": 100 / 6.378e6, "grid_res": 0.4, "vstretch": 12, "lon_crop": 0.05}),
+    ("synthetic:H=8,W=7,seed=2,lat0=-42,lon0=100", {"scale": 100 / 6.378e6, "grid_res": 0.25, "vstretch": None, "lon_crop": 0.1}),
+])
+def test_global_grid_layout_matches_the_reference_class(tmp_path, spec, kw):
+    """HARP2GlobalGridExtractDataset (harp2_extract.py:794-903) up to the line the reference cannot
+    execute (:896): the voxels crossed by the granule's rays in the stretched spherical frame, the
+    per-layer longitude crop, the un-stretched WGS-84 voxel centres: the same SET of (voxel, centre)
+    rows. This package then applies the cull the reference's comment describes."""
+    from oracle import geodesy
+    from atmonr.datasets.factory import get_extract_dataset
+    ref, ds = _reference_layout(tmp_path, spec, "globalgrid", kw)
+    grid = get_extract_dataset("globalgrid", ds, alt_step=250.0, **kw)
+    assert ref["voxels"].dtype == grid.voxels.dtype == torch.int32 and ref["xyz"].dtype == grid.xyz.dtype == torch.float32
+    alt = geodesy.ecef_to_geodetic(*(ref["xyz"][:, k] for k in range(3)))[2]
+    keep = ~((alt <= 0) | (alt > 20000.0))
+    assert 0 < int(keep.sum()) <= keep.numel() and ref["voxels"].shape[0] > 50
+    rows = lambda vox, xyz: sorted(map(tuple, torch.cat([vox.double(), xyz.double()], dim=1).tolist()))
+    assert rows(grid.voxels, grid.xyz) == rows(ref["voxels"][keep], ref["xyz"][keep])
+    assert torch.equal(grid.idx, torch.arange(int(keep.sum()), dtype=torch.int32))
+    # every kept voxel centre lies inside the shell and (un-cropped) under the granule's rays
+    got_alt = geodesy.ecef_to_geodetic(*(grid.xyz.double()[:, k] for k in range(3)))[2]
+    assert float(got_alt.min()) > 0 and float(got_alt.max()) <= 20000.0
+    # the reference's own fallback writer (no OpenVDB bindings): voxels.npy + sigma.npy
+    sigma = torch.rand(grid.xyz.shape[0], 1)
+    grid.dump(tmp_path / "grid.vdb", sigma)
+    assert np.array_equal(np.load(tmp_path / "voxels.npy"), grid.voxels.numpy())
+    assert np.array_equal(np.load(tmp_path / "sigma.npy"), sigma.numpy())
+    with pytest.raises(FileExistsError):
+        grid.dump(tmp_path / "grid.vdb", sigma)
+    with pytest.raises(AssertionError):
+        get_extract_dataset("globalgrid", ds, scale=1.0, grid_res=1.0, vstretch=0.5)
+
+
+def test_extract_modes_are_the_reference_registry():
+    """datasets/factory.py:24-33: the four coordinate modes, case-insensitive; anything else raises."""
+    from atmonr.datasets import factory
+    assert sorted(factory._EXTRACT_DATASETS["HARP2"]) == ["earthcare", "globalgrid", "l1c", "voxelgrid"]
+    ds = FakeDataset(tiny_scene())
+    ds.config = {"type": "HARP2", "ray_origin_height": 20000}
+    with pytest.raises(NotImplementedError):
+        factory.get_extract_dataset("octree", ds)
+    ds.config = {"type": "AirHARP"}
+    with pytest.raises(NotImplementedError):
+        factory.get_extract_dataset("voxelgrid", ds)
 
 
 REF_SCRIPTS = "/root/reference/scripts"

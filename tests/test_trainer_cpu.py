@@ -167,4 +167,4 @@ def test_extract_dataset_dump(tmp_path, layout):
     assert out["latitude"].shape == out["longitude"].shape == out["height"].shape == (rows, cols)
     assert out["altitude"].shape == (n_alt,) and out["x_wgs84"].shape == (rows, cols, n_alt)
     with pytest.raises(NotImplementedError):
-        get_extract_dataset("globalgrid", ds)
+        get_extract_dataset("octree", ds)
