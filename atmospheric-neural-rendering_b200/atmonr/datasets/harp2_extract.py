@@ -2,15 +2,15 @@
 
 Only what feeds `pipeline.extract` on the hot path is built here: the point table `xyz`
 (float64, (rows*cols*levels, 3), WGS-84 Cartesian) and `idx` (int32), `__getbatch__`, and a
-`dump` that stores the extinction grid. Differences from the reference, all outside the hot
-path: by default the horizontal layout is a regular lat/lon grid whose spacing
-equals `horizontal_step` metres at the scene centre; `layout="vincenty"` (or
-ATMONR_EXTRACT_LAYOUT=vincenty) lays the columns out like the reference, along Vincenty geodesics
-between the granule's corners (harp2_extract.py:219-330; pinned to the reference class in
-tests/test_reference_interchange.py). The reference's DEM lookup only fills the `height` variable of
-the output file (the query points are placed above the ELLIPSOID either way); the DEM file is not
-shipped, so `height` is zero here. Output is netCDF when `netCDF4` is installed, else `.npz` with the
-same variable names.
+`dump` that stores the extinction grid. The columns are laid out like the reference's, along Vincenty
+geodesics between the granule's corners (harp2_extract.py:219-330; pinned to the reference class in
+tests/test_reference_interchange.py); `layout="regular"` (or ATMONR_EXTRACT_LAYOUT=regular) gives a
+regular lat/lon grid whose spacing equals `horizontal_step` metres at the scene centre instead (the dense
+grid SURVEY 8d specifies for the extraction benchmark; it also serves scenes whose corner pixels have no
+valid view, which the reference's layout rejects). Differences from the reference, outside the hot path
+(SURVEY 8f-1/3): the reference's DEM lookup only fills the `height` variable of the output file (the query
+points are placed above the ELLIPSOID either way); the DEM file is not shipped, so `height` is zero here.
+Output is netCDF when `netCDF4` is installed, else `.npz` with the same variable names.
 
 The other three coordinate modes of scripts/extract.py are point-table LAYOUTS around the
 same `pipeline.extract` call: `HARP2L1CExtractDataset` (harp2_extract.py:115-186: the 5 km L1C bin
@@ -104,7 +104,7 @@ class HARP2VoxelGridExtractDataset(_ExtractTable):
     def __init__(self, dataset, horizontal_step: float, alt_step: float, min_alt: float | None = None,
                  max_alt: float | None = None, *args, layout: str | None = None, **kwargs) -> None:
         self.dataset = dataset
-        self.layout = layout or os.environ.get("ATMONR_EXTRACT_LAYOUT", "regular")
+        self.layout = layout or os.environ.get("ATMONR_EXTRACT_LAYOUT", "vincenty")
         if self.layout not in ("regular", "vincenty"):
             raise ValueError(f"unknown extract layout {self.layout!r}")
         self.device = dataset.lat.device

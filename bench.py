@@ -554,7 +554,7 @@ def run_native(args) -> None:
     n_vox = 32768 * 81
     lat_span_m = math.radians(float(dataset.lat[~dataset.lat.isnan()].max() - dataset.lat[~dataset.lat.isnan()].min())) * 6378137.0
     h_step = lat_span_m / 620.0   # ~620 x ~500 columns over the 5 x 5 degree granule: > 4 x 32768 columns
-    grid_ds = HARP2VoxelGridExtractDataset(dataset, horizontal_step=h_step, alt_step=250.0)
+    grid_ds = HARP2VoxelGridExtractDataset(dataset, horizontal_step=h_step, alt_step=250.0, layout="regular")
     n_alt = int(grid_ds.sample_alt.shape[0])
     n_cols = len(grid_ds) // n_alt
     per_call = min(32768, n_cols // max(world, 1))
