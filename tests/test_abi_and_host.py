@@ -98,6 +98,36 @@ def test_grid_layout_matches_oracle_bit_for_bit(dims, key):
         assert g.n_entries == (21141696 if dims == 3 else 2761000)
 
 
+def test_level_table_does_not_depend_on_how_tcnn_rounds_the_level_scale():
+    """Round-1 review: oracle/tcnn_spec.py evaluates `exp2(l * log2(per_level_scale)) * base - 1` in float64
+    and rounds once, tiny-cuda-nn evaluates it in float32 (`exp2f`, `log2f`; on the device `exp2f` is a 2-ulp
+    approximation), so the two scales can differ in the last bits. Quantified here for the shipped grids
+    (configs/instant_ngp.json: 3-D table 2^21, 2-D table 2^19, and the 4-D `include_height` table):
+    * the literal float32 evaluation is within 8 ulps of the once-rounded scale at every level;
+    * no level's scale lies within 500 ulps of an integer (level 0 is exactly 15 under any evaluation), so
+      `res = ceil(scale) + 1`, and with it every level size, every offset and which levels hash, is the
+      same for ANY evaluation that close: the TABLE LAYOUT cannot differ from tiny-cuda-nn's;
+    * what can differ is `pos = scale * x + 0.5` by <= 8 ulps of the scale: 1e-3 of a cell at the finest level
+      (scale 2047), i.e. an interpolation-weight change below the fp16 resolution of the features."""
+    import json
+    from oracle import tcnn_spec
+    cfg = json.load(open(os.path.join(ROOT, "configs", "instant_ngp.json")))["pipeline"]["instant_ngp"]
+    grids = [(3, cfg["encoding"]), (4, cfg["encoding"]), (2, cfg["surface_encoding"]["nested"][0])]
+    f32 = np.float32
+    for dims, g in grids:
+        assert g["otype"] == "HashGrid"
+        lv = tcnn_spec.grid_levels(dims, g["n_levels"], g["log2_hashmap_size"], g["base_resolution"], g["per_level_scale"])
+        pls, base = f32(g["per_level_scale"]), f32(g["base_resolution"])
+        literal = np.array([f32(np.exp2(f32(l) * np.log2(pls))) * base - f32(1) for l in range(g["n_levels"])], dtype=f32)
+        ulp = np.spacing(lv["scale"]).astype(np.float64)
+        off_by = np.abs(literal.astype(np.float64) - lv["scale"].astype(np.float64)) / ulp
+        assert off_by.max() <= 8
+        to_integer = np.abs(lv["scale"].astype(np.float64) - np.round(lv["scale"].astype(np.float64))) / ulp
+        assert lv["scale"][0] == 15.0 and literal[0] == 15.0 and to_integer[1:].min() > 500
+        assert np.array_equal(np.ceil(literal).astype(np.uint32) + 1, lv["res"])
+        assert float(off_by.max() * ulp[-1]) <= 1.1e-3          # cells, at x = 1 on the finest level
+
+
 def _hc():
     lib = C.CDLL(os.path.join(ROOT, "atmospheric-neural-rendering_b200", "lib", "libatmonr_hostcheck.so"))
     return lib
