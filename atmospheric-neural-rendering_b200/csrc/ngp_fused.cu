@@ -234,16 +234,36 @@ __device__ __forceinline__ void level_issue(const LevelRow& L, const __half2* __
                                             uint32_t (&v)[8], float (&frac)[3], uint64_t keep) {
   uint32_t cell[3], e[8];
   grid_cell<3>(p, L.scale, cell, frac);
-  corner_entries3(L, cell, e);
   const uint32_t* base = reinterpret_cast<const uint32_t*>(table + L.offset);
-#pragma unroll
-  for (int c = 0; c < 8; ++c) {
 #ifdef ATM_L2_HINTS
-    v[c] = ldg_u32_hint(entry_ptr(base, e[c]), keep);
+#define ATM_GATHER(ptr) ldg_u32_hint(ptr, keep)
 #else
-    v[c] = __ldg(entry_ptr(base, e[c]));
+#define ATM_GATHER(ptr) __ldg(ptr)
 #endif
+#ifndef ATM_NO_DENSE_PAIRS
+  if (L.hashed == 0u) {
+    // Dense level: the +1 corner in x is the NEXT entry in memory, so the 8 gathers need 4 addresses
+    // (the second load of a pair is an immediate offset). Same entries as corner_entries3: corner c =
+    // e0 + (c & 1) + (c & 2 ? stride1 : 0) + (c & 4 ? stride2 : 0); the all-+1 corner is the largest,
+    // so one compare proves that no corner wraps (cells below 2^16 cannot overflow uint32).
+    const uint32_t e0 = cell[0] + cell[1] * L.stride1 + cell[2] * L.stride2;
+    if ((cell[0] | cell[1] | cell[2]) < 65536u && e0 + 1u + L.stride1 + L.stride2 < L.size) {
+      const uint32_t* q0 = entry_ptr(base, e0);
+      const uint32_t* q1 = entry_ptr(base, e0 + L.stride1);
+      const uint32_t* q2 = entry_ptr(base, e0 + L.stride2);
+      const uint32_t* q3 = entry_ptr(base, e0 + L.stride1 + L.stride2);
+      v[0] = ATM_GATHER(q0), v[1] = ATM_GATHER(q0 + 1);
+      v[2] = ATM_GATHER(q1), v[3] = ATM_GATHER(q1 + 1);
+      v[4] = ATM_GATHER(q2), v[5] = ATM_GATHER(q2 + 1);
+      v[6] = ATM_GATHER(q3), v[7] = ATM_GATHER(q3 + 1);
+      return;
+    }
   }
+#endif
+  corner_entries3(L, cell, e);
+#pragma unroll
+  for (int c = 0; c < 8; ++c) v[c] = ATM_GATHER(entry_ptr(base, e[c]));
+#undef ATM_GATHER
 }
 __device__ __forceinline__ uint32_t level_finish(const uint32_t (&v)[8], const float (&frac)[3]) {
   float w[8];
