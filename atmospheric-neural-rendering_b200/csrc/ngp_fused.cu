@@ -294,6 +294,104 @@ __device__ __forceinline__ void encode_to_tile(const LevelRow* __restrict__ lv, 
   }
 }
 
+// ---- the same loop for the forward / extraction kernels, trimmed for instruction issue -----------
+// Those kernels are bound by instruction issue, and ~20 of the ~120 instructions a level costs were
+// address bookkeeping: the shared-memory window base rebuilt per level (the level table and the tile
+// were reached through generic pointers), the row's tile offset rebuilt from the thread index per
+// level, the level's table base formed from the kernel parameter and an offset per level. Here the
+// level table holds the 64-bit base pointer of every level, shared memory is addressed with 32-bit
+// shared-window addresses formed once per tile, and the row address is kept in a register.
+// Arithmetic, corner order and entries are those of level_issue() / level_finish(): bit-identical.
+struct FwdLevel {  // 32 bytes per level
+  float scale;
+  uint32_t hashed, size, stride1;  // `hashed` as in LevelRow
+  uint32_t stride2, pad;
+  const uint32_t* base;  // first entry of the level in the fp16 table (one entry = 4 bytes)
+};
+static_assert(sizeof(FwdLevel) == sizeof(LevelRow), "the forward kernels keep FwdLevel rows where LevelRow rows were");
+
+__device__ __forceinline__ void load_fwd_levels(const atmonr_grid_t& g, const __half2* __restrict__ table, FwdLevel* rows) {
+  if (threadIdx.x < ATMONR_MAX_LEVELS) {
+    const int l = threadIdx.x;
+    FwdLevel r;
+    r.scale = g.scale[l];
+    r.size = g.size[l];
+    uint64_t dense = 1;
+    for (int k = 0; k < g.n_dims; ++k) dense *= g.res[l];
+    r.hashed = (dense > (uint64_t)r.size ? 1u : 0u) | (((r.size & (r.size - 1u)) == 0u) ? 2u : 0u);
+    r.stride1 = g.res[l];
+    r.stride2 = g.res[l] * g.res[l];
+    r.pad = 0;
+    r.base = reinterpret_cast<const uint32_t*>(table + g.offset[l]);
+    rows[l] = r;
+  }
+}
+
+__device__ __forceinline__ FwdLevel lds_fwd_level(uint32_t saddr) {
+  FwdLevel L;
+  uint32_t sc, lo, hi;
+  // volatile: must not be hoisted above the barrier that publishes the table
+  asm volatile("ld.shared.v4.b32 {%0, %1, %2, %3}, [%4];" : "=r"(sc), "=r"(L.hashed), "=r"(L.size), "=r"(L.stride1) : "r"(saddr));
+  asm volatile("ld.shared.v4.b32 {%0, %1, %2, %3}, [%4+16];" : "=r"(L.stride2), "=r"(L.pad), "=r"(lo), "=r"(hi) : "r"(saddr));
+  L.scale = __uint_as_float(sc);
+  L.base = reinterpret_cast<const uint32_t*>(((uint64_t)hi << 32) | lo);
+  return L;
+}
+
+__device__ __forceinline__ void level_issue_s(uint32_t level_saddr, const float (&p)[3], uint32_t (&v)[8],
+                                              float (&frac)[3], uint64_t keep) {
+  const FwdLevel L = lds_fwd_level(level_saddr);
+  uint32_t cell[3], e[8];
+  grid_cell<3>(p, L.scale, cell, frac);
+#ifdef ATM_L2_HINTS
+#define ATM_GATHER(ptr) ldg_u32_hint(ptr, keep)
+#else
+#define ATM_GATHER(ptr) __ldg(ptr)
+#endif
+  if (L.hashed == 0u) {  // dense level: 4 addresses for the 8 gathers (see level_issue)
+    const uint32_t e0 = cell[0] + cell[1] * L.stride1 + cell[2] * L.stride2;
+    if ((cell[0] | cell[1] | cell[2]) < 65536u && e0 + 1u + L.stride1 + L.stride2 < L.size) {
+      const uint32_t* q0 = entry_ptr(L.base, e0);
+      const uint32_t* q1 = entry_ptr(L.base, e0 + L.stride1);
+      const uint32_t* q2 = entry_ptr(L.base, e0 + L.stride2);
+      const uint32_t* q3 = entry_ptr(L.base, e0 + L.stride1 + L.stride2);
+      v[0] = ATM_GATHER(q0), v[1] = ATM_GATHER(q0 + 1);
+      v[2] = ATM_GATHER(q1), v[3] = ATM_GATHER(q1 + 1);
+      v[4] = ATM_GATHER(q2), v[5] = ATM_GATHER(q2 + 1);
+      v[6] = ATM_GATHER(q3), v[7] = ATM_GATHER(q3 + 1);
+      return;
+    }
+  }
+  LevelRow R;
+  R.hashed = L.hashed, R.size = L.size, R.stride1 = L.stride1, R.stride2 = L.stride2;
+  corner_entries3(R, cell, e);
+#pragma unroll
+  for (int c = 0; c < 8; ++c) v[c] = ATM_GATHER(entry_ptr(L.base, e[c]));
+#undef ATM_GATHER
+}
+
+// lv: FwdLevel rows in shared memory; tile: the activation tile; r: this thread's row
+__device__ __forceinline__ void encode_to_tile_s(const FwdLevel* lv, const float (&p)[3], uint8_t* tile, int r,
+                                                 uint64_t keep) {
+  const uint32_t lv_s = smem_u32(lv);
+  uint32_t row_s = smem_u32(tile) + tile_off(r, 0, 32);
+  asm volatile("" : "+r"(row_s));  // opaque: held in a register instead of being rebuilt from the thread index per level
+  // two register sets, two levels per iteration: level l + 1 is issued before level l is interpolated
+  uint32_t va[8], vb[8];
+  float fa[3], fb[3];
+  constexpr uint32_t kRow = (uint32_t)sizeof(FwdLevel);
+  level_issue_s(lv_s, p, va, fa, keep);
+#pragma unroll 1
+  for (int l = 0; l < ATMONR_MAX_LEVELS; l += 2) {
+    level_issue_s(lv_s + (uint32_t)(l + 1) * kRow, p, vb, fb, keep);
+    // features 2l, 2l+1 of row r: chunk l/4 (128 B apart), 4 bytes per level inside the chunk
+    const uint32_t at = row_s + (uint32_t)((l >> 2) * kCore + (l & 3) * 4);
+    asm volatile("st.shared.b32 [%0], %1;" ::"r"(at), "r"(level_finish(va, fa)) : "memory");
+    if (l + 2 < ATMONR_MAX_LEVELS) level_issue_s(lv_s + (uint32_t)(l + 2) * kRow, p, va, fa, keep);
+    asm volatile("st.shared.b32 [%0+4], %1;" ::"r"(at), "r"(level_finish(vb, fb)) : "memory");
+  }
+}
+
 // dir_mlp input row: [SH2(dir) | pos_out[1..15] | 1.0 x 13] (instant_ngp.py:165-169 + tcnn padding)
 __device__ __forceinline__ void dir_input_row(const float* __restrict__ dir, const float (&po)[16], float (&v)[32]) {
   float sh[4];
@@ -334,8 +432,8 @@ k_field_fwd_tc(atmonr_grid_t g, const __half2* __restrict__ table, const __half*
   uint64_t* bar = reinterpret_cast<uint64_t*>(smem + fwd::kBar);
   uint32_t* tmem_ptr = reinterpret_cast<uint32_t*>(smem + fwd::kTmemPtr);
   const int tid = threadIdx.x, warp = tid >> 5;
-  LevelRow* lv = reinterpret_cast<LevelRow*>(smem + fwd::kLv);
-  load_level_table(g, lv);
+  FwdLevel* lv = reinterpret_cast<FwdLevel*>(smem + fwd::kLv);
+  load_fwd_levels(g, table, lv);
   load_field_weights(smem, pos_w, dir_w);
   if (warp == 0) tmem_alloc<fwd::kTmemCols>(tmem_ptr);
   if (tid == 0) {
@@ -363,7 +461,7 @@ k_field_fwd_tc(atmonr_grid_t g, const __half2* __restrict__ table, const __half*
 #else
       const float p[3] = {x01[3 * j], x01[3 * j + 1], x01[3 * j + 2]};
 #endif
-      encode_to_tile(lv, table, p, A, tid, keep_pol);
+      encode_to_tile_s(lv, p, A, tid, keep_pol);
       if (enc_out && valid) {
         uint4* dst = reinterpret_cast<uint4*>(enc_out + i * 32);
 #pragma unroll
@@ -442,8 +540,8 @@ k_extract_sigma_tc(atmonr_frame_t f, GeoFrame gf, atmonr_grid_t g, const __half2
   uint64_t* bar = reinterpret_cast<uint64_t*>(smem + fwd::kBar);
   uint32_t* tmem_ptr = reinterpret_cast<uint32_t*>(smem + fwd::kTmemPtr);
   const int tid = threadIdx.x, warp = tid >> 5;
-  LevelRow* lv = reinterpret_cast<LevelRow*>(smem + fwd::kLv);
-  load_level_table(g, lv);
+  FwdLevel* lv = reinterpret_cast<FwdLevel*>(smem + fwd::kLv);
+  load_fwd_levels(g, table, lv);
   load_matrix_tile(pos_w, smem + fwd::kW1P, 32, 32);
   load_matrix_tile(pos_w + 1024, smem + fwd::kW2P, 16, 32);
   if (warp == 0) tmem_alloc<fwd::kTmemCols>(tmem_ptr);
@@ -469,7 +567,7 @@ k_extract_sigma_tc(atmonr_frame_t f, GeoFrame gf, atmonr_grid_t g, const __half2
       // instant_ngp.py:224-233 stay in float64; tcnn casts its input to float32
       const float p[3] = {(float)((c0 + 1.0) / 2.0), (float)((c1 + 1.0) / 2.0),
                           (float)(((c2 + 1.0) / 2.0) / (double)alt_compress)};
-      encode_to_tile(lv, table, p, A, tid, keep_pol);
+      encode_to_tile_s(lv, p, A, tid, keep_pol);
     }
     publish_and_sync();
     if (warp == 0) issue_layer<32>(acc, sa, sbase + fwd::kW1P, bar);
