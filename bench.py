@@ -466,6 +466,8 @@ def run_native(args) -> None:
             d["issue_active_pct_ncu"] = c.get("issue_active_pct")
             d["top_stalls_ncu"] = c.get("top_stalls")
             d["counters_from"] = c.get("source")
+            if c.get("note"):
+                d["counters_note"] = c["note"]
         return d
 
     detail = {k: kernel_detail(k) for k in sorted(per_step, key=per_step.get, reverse=True)[:6]}
