@@ -191,7 +191,7 @@ class HARP2VoxelGridExtractDataset(_ExtractTable):
 
     def dump(self, path: Path, sigma: torch.Tensor) -> None:
         """Store the extinction grid (variable names follow harp2_extract.py:429-596)."""
-        rows, cols, n_alt = self.shp
+        rows, cols, n_alt = self.lat.shape          # (the L1C layout keeps the 2-D bin shape in `shp`)
         ext = sigma.detach().float().cpu().numpy().reshape(rows, cols, n_alt, -1)
         xyz = self.xyz.cpu().numpy().reshape(rows, cols, n_alt, 3)
         fields = {
@@ -219,7 +219,8 @@ class HARP2VoxelGridExtractDataset(_ExtractTable):
 class HARP2L1CExtractDataset(HARP2VoxelGridExtractDataset):
     """harp2_extract.py:115-186: voxel columns over the bins of the granule's level-1C grid (5 km, map
     projected: evenly spaced, unlike the view-dependent L1B geolocation), at the user's altitude levels
-    above the ELLIPSOID (the L1C `height` only goes into the output file). `dump` is the voxel grid's."""
+    above the ELLIPSOID (the L1C `height` only goes into the output file). `dump` is the voxel grid's
+    (harp2_extract.py:100-112 shares `_extract_to_netCDF` between the two as well)."""
 
     def __init__(self, dataset, alt_step: float, min_alt: float | None = None, max_alt: float | None = None,
                  *args, l1c_path: Path | None = None, **kwargs) -> None:
@@ -248,14 +249,6 @@ class HARP2L1CExtractDataset(HARP2VoxelGridExtractDataset):
         self.shp = tuple(lat.shape)                 # the reference keeps the 2-D bin shape here
         self.xyz = torch.stack([x, y, z], dim=-1).view(-1, 3)
         self.idx = torch.arange(self.xyz.shape[0], dtype=torch.int32)
-
-    def dump(self, path: Path, sigma: torch.Tensor) -> None:
-        shp2 = self.shp
-        self.shp = (*shp2, self.sample_alt.shape[0])
-        try:
-            super().dump(path, sigma)
-        finally:
-            self.shp = shp2
 
 
 class HARP2EarthCAREExtractDataset(_ExtractTable):
