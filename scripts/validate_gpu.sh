@@ -1,11 +1,13 @@
 #!/usr/bin/env bash
 # usage (on the GPU box): bash scripts/validate_gpu.sh <tag>  -- tests, bench line, ncu launch list, ncu full captures
+# (ATMONR_VALIDATE_QUICK=1: tests, bench line and CPU arm only -- the r4 pass of profiles/, ~6 GPU-minutes)
 tag=${1:-r3}
 o=gpurun_out
 mkdir -p $o
 timeout 1500 python -m pytest tests -m gpu -x -q > $o/${tag}_pytest_gpu.log 2>&1; echo "pytest rc $?"; tail -3 $o/${tag}_pytest_gpu.log
 python bench.py > $o/${tag}_bench.json 2> $o/${tag}_bench.err || { tail -20 $o/${tag}_bench.err; exit 1; }
 python bench.py --impl reference --steps 2 --warmup 1 > $o/${tag}_bench_reference.json 2>> $o/${tag}_bench.err
+[ -n "$ATMONR_VALIDATE_QUICK" ] && exit 0
 export ATMONR_BENCH_NO_CLOCKS=1
 python bench.py --steps 2 --warmup 3 --no-cpu-baseline > $o/${tag}_plain.log 2>&1 &&
 ncu --metrics gpu__time_duration.sum --clock-control none --csv --log-file $o/${tag}_launches.csv \
