@@ -376,6 +376,32 @@ def test_host_build_of_filter_and_normalize_rays_matches_reference_vectors():
     assert np.isnan(hl[[2, 5]]).all() and np.array_equal(hl[[0, 1, 3, 4]], hi_lo[[0, 1, 3, 4]])
 
 
+def test_host_build_of_normalize_rays_edge_cases():
+    """Ragged and degenerate ray tables through the kernel code (host build) against the oracle, bit for bit:
+    one ray, a zero-length ray alone (scale 0: the reference's 0/0 -> NaN), identical rays, huge and tiny
+    coordinates, tables whose size is not a multiple of anything."""
+    rng = np.random.default_rng(5)
+    cases = []
+    for n in (1, 2, 3, 31, 33, 257, 1000):
+        o = (rng.standard_normal((n, 3)) * 10.0 ** rng.integers(-3, 7)).astype(np.float32)
+        d = rng.standard_normal((n, 3)).astype(np.float32)
+        ln = (rng.random(n) * 10.0 ** rng.integers(-2, 5)).astype(np.float32)
+        cases.append((o, d, ln))
+    one = np.array([[1.0, 2.0, 3.0]], np.float32)
+    cases.append((one, np.array([[0.0, 0.0, 1.0]], np.float32), np.array([0.0], np.float32)))      # scale == 0
+    cases.append((np.repeat(one, 5, 0), np.zeros((5, 3), np.float32), np.ones(5, np.float32)))      # one point, five times
+    cases.append((np.array([[3e38, -3e38, 0.0], [-3e38, 3e38, 1.0]], np.float32), np.zeros((2, 3), np.float32), np.ones(2, np.float32)))
+    for o, d, ln in cases:
+        out, scale, offset, _ = _hc_normalize_rays(o, d, ln)
+        want, want_scale, want_offset = geodesy.normalize_rays(*map(torch.from_numpy, (o, d, ln)))
+        assert (scale == want_scale) or (scale != scale and want_scale != want_scale)
+        assert np.array_equal(offset.numpy(), want_offset.numpy(), equal_nan=True)
+        assert np.array_equal(out, want.numpy(), equal_nan=True), (o.shape, scale)
+    # the zero-scale table really is the NaN case of the reference
+    out, scale, _, _ = _hc_normalize_rays(*cases[7])
+    assert scale == 0.0 and np.isnan(out).all()
+
+
 # ---------------------------------------------------------------- dense layer on tcgen05 (csrc/linear_tc.cu)
 def _bf16_round(a):
     """float32 -> nearest-even bfloat16, returned as float32 (numpy has no bfloat16)."""
